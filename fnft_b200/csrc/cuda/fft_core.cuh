@@ -1,0 +1,271 @@
+// fnft_b200 -- complex-double FFT building blocks (replacement for the Kiss FFT
+// the reference vendors: /root/reference/src/3rd_party/kiss_fft/kiss_fft.c:21-408,
+// reached through include/private/fnft__fft_wrapper.h:43-199).
+//
+// Conventions (same as the reference wrapper, fnft__fft_wrapper.h:79-80,102):
+//   forward  X[k] = sum_n x[n] exp(-2*pi*i*k*n/N)
+//   inverse  x[n] = sum_k X[k] exp(+2*pi*i*k*n/N)      (UNNORMALISED)
+//
+// Design: power-of-two lengths only (callers zero-pad / wrap-correct, linear
+// convolution does not care about the FFT length).  A transform that fits in
+// shared memory is done in place as a sequence of radix-16/8/4/2 passes:
+//   forward = decimation in frequency, natural order in -> digit-reversed out
+//   inverse = decimation in time,     digit-reversed in -> natural order out
+// so no reordering pass is ever needed for convolutions.  Elements are stored
+// with an XOR swizzle of the low three index bits so that every pass (strided
+// or contiguous) is free of shared-memory bank conflicts for 16-byte accesses.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// compile-time roots of unity, exp(2*pi*i*k/64) via a quadrant table
+// ---------------------------------------------------------------------------
+HD constexpr double fnftb_cos64(int k)
+{
+    // cos(2*pi*k/64), k in [0, 64); first quadrant tabulated (nearest doubles)
+    constexpr double t[17] = {
+                              1.0,
+                              0.9951847266721969,
+                              0.9807852804032304,
+                              0.9569403357322088,
+                              0.9238795325112867,
+                              0.881921264348355,
+                              0.8314696123025452,
+                              0.773010453362737,
+                              0.7071067811865476,
+                              0.6343932841636455,
+                              0.5555702330196023,
+                              0.4713967368259978,
+                              0.38268343236508984,
+                              0.29028467725446233,
+                              0.19509032201612833,
+                              0.09801714032956077,
+                              0.0};
+    k &= 63;
+    if (k > 32)
+        k = 64 - k;  // cos is even
+    return (k <= 16) ? t[k] : -t[32 - k];
+}
+HD constexpr double fnftb_sin64(int k) { return fnftb_cos64(k - 16); }
+
+// v *= exp(DIR * 2*pi*i * K / R) with trivial cases folded at compile time
+template <int R, int K, int DIR>
+HD cplx mul_root(cplx v)
+{
+    constexpr int k64 = (K * (64 / R)) & 63;
+    if constexpr (k64 == 0) {
+        return v;
+    } else if constexpr (k64 == 16) {
+        return (DIR > 0) ? cmuli(v) : cmulmi(v);
+    } else if constexpr (k64 == 32) {
+        return cneg(v);
+    } else if constexpr (k64 == 48) {
+        return (DIR > 0) ? cmulmi(v) : cmuli(v);
+    } else {
+        constexpr double c = fnftb_cos64(k64);
+        constexpr double s = (DIR > 0) ? fnftb_sin64(k64) : -fnftb_sin64(k64);
+        return make_cplx(v.x * c - v.y * s, v.x * s + v.y * c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// register-resident DFT of length R in {1,2,4,...,64}, natural order in/out
+// (radix-2 decimation-in-time recursion, fully unrolled by the compiler)
+// ---------------------------------------------------------------------------
+template <int R, int DIR, int K>
+struct DftCombine {
+    HD static void run(cplx *v, const cplx *e, const cplx *o)
+    {
+        const cplx t = mul_root<R, K, DIR>(o[K]);
+        v[K] = cadd(e[K], t);
+        v[K + R / 2] = csub(e[K], t);
+        if constexpr (K + 1 < R / 2)
+            DftCombine<R, DIR, K + 1>::run(v, e, o);
+    }
+};
+
+template <int R, int DIR>
+struct Dft {
+    HD static void run(cplx *v)
+    {
+        if constexpr (R == 1) {
+            return;
+        } else if constexpr (R == 2) {
+            const cplx a = v[0], b = v[1];
+            v[0] = cadd(a, b);
+            v[1] = csub(a, b);
+        } else {
+            cplx e[R / 2], o[R / 2];
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j) {
+                e[j] = v[2 * j];
+                o[j] = v[2 * j + 1];
+            }
+            Dft<R / 2, DIR>::run(e);
+            Dft<R / 2, DIR>::run(o);
+            DftCombine<R, DIR, 0>::run(v, e, o);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// shared-memory index swizzle (see header comment)
+// ---------------------------------------------------------------------------
+HD int swz(int i) { return i ^ ((i >> 3) & 7); }
+
+// Twiddle table: tw[k] = exp(-2*pi*i*k/twn), k < twn (global memory, read-only).
+struct TwTable {
+    const cplx *tw;
+    int twn;
+};
+
+// w = exp(-2*pi*i * m / len) from the table (len divides twn), DIR selects conj
+template <int DIR>
+HD cplx tw_lookup(const TwTable &T, int m, int len)
+{
+    const cplx w = LDG(&T.tw[(size_t)m * (size_t)(T.twn / len)]);
+    return (DIR > 0) ? cconj(w) : w;
+}
+
+// ---------------------------------------------------------------------------
+// one radix-R butterfly of an in-place pass over the array S (one FFT)
+//   u    : butterfly index within this FFT, 0 <= u < n/R
+//   s    : element stride of this pass (power of two), sub-FFT length = R*s
+// forward (DIF):  y_j = DFT_R(x)_j * w_{R*s}^{j*o}
+// inverse (DIT):  y   = IDFT_R( x_j * conj(w_{R*s}^{j*o}) )
+// ---------------------------------------------------------------------------
+template <int R, int DIR>
+HD void fft_pass_butterfly(cplx *S, int u, int log2s, const TwTable &T)
+{
+    const int s = 1 << log2s;
+    const int g = u >> log2s;
+    const int o = u & (s - 1);
+    const int base = g * (R * s) + o;
+    const int len = R * s;
+    cplx v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        v[j] = S[swz(base + j * s)];
+    if constexpr (DIR > 0) {
+        if (o != 0) {
+#pragma unroll
+            for (int j = 1; j < R; ++j)
+                v[j] = cmul(v[j], tw_lookup<+1>(T, j * o, len));
+        }
+    }
+    Dft<R, DIR>::run(v);
+    if constexpr (DIR < 0) {
+        if (o != 0) {
+#pragma unroll
+            for (int j = 1; j < R; ++j)
+                v[j] = cmul(v[j], tw_lookup<-1>(T, j * o, len));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        S[swz(base + j * s)] = v[j];
+}
+
+// One pass over `nfft` transforms stored back to back (stride n) in shared memory.
+template <int R, int DIR>
+HD void fft_pass_all(cplx *S, int nfft, int log2n, int log2s, int tid, int nt,
+                     const TwTable &T)
+{
+    const int log2bpf = log2n - ilog2i(R);  // butterflies per FFT (log2)
+    const int nb = nfft << log2bpf;
+    for (int b = tid; b < nb; b += nt) {
+        const int f = b >> log2bpf;
+        const int u = b & ((1 << log2bpf) - 1);
+        fft_pass_butterfly<R, DIR>(S + ((size_t)f << log2n), u, log2s, T);
+    }
+}
+
+template <int DIR>
+HD void fft_pass_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, int tid,
+                          int nt, const TwTable &T)
+{
+    switch (R) {
+    case 16: fft_pass_all<16, DIR>(S, nfft, log2n, log2s, tid, nt, T); break;
+    case 8: fft_pass_all<8, DIR>(S, nfft, log2n, log2s, tid, nt, T); break;
+    case 4: fft_pass_all<4, DIR>(S, nfft, log2n, log2s, tid, nt, T); break;
+    case 2: fft_pass_all<2, DIR>(S, nfft, log2n, log2s, tid, nt, T); break;
+    default: break;
+    }
+}
+
+// Radix plan: as many radix-16 passes as possible, the remainder (8/4/2) LAST so
+// that every earlier pass has stride >= 8 elements (bank-conflict-free together
+// with swz()).  n = 1 gives an empty plan.
+static inline FftPlan make_fft_plan(int n)
+{
+    FftPlan P;
+    memset(&P, 0, sizeof(P));
+    P.n = n;
+    P.log2n = 0;
+    while ((1 << P.log2n) < n)
+        ++P.log2n;
+    int rem = P.log2n;
+    int tail = rem % 4;  // log2 of the last radix (0 => none)
+    // avoid a trailing radix-2 after radix-16s when a 8+4 / 8+8 split is nicer
+    int n16 = rem / 4;
+    if (tail == 1 && n16 >= 1) {  // 16*2 -> 8*4
+        n16 -= 1;
+        for (int i = 0; i < n16; ++i)
+            P.radix[P.npass++] = 16;
+        P.radix[P.npass++] = 8;
+        P.radix[P.npass++] = 4;
+        return P;
+    }
+    if (tail == 2 && n16 >= 1) {  // 16*4 -> 8*8
+        n16 -= 1;
+        for (int i = 0; i < n16; ++i)
+            P.radix[P.npass++] = 16;
+        P.radix[P.npass++] = 8;
+        P.radix[P.npass++] = 8;
+        return P;
+    }
+    for (int i = 0; i < n16; ++i)
+        P.radix[P.npass++] = 16;
+    if (tail)
+        P.radix[P.npass++] = 1 << tail;
+    return P;
+}
+
+// log2 of the stride of the FIRST forward pass (= n / radix[0]); the frequency
+// index k of the element stored at position pos after the forward transform
+// satisfies  k mod radix[0] == pos >> log2_first_stride.
+HD int plan_first_stride_log2(const FftPlan &P)
+{
+    return (P.npass == 0) ? 0 : P.log2n - ilog2i(P.radix[0]);
+}
+
+// In-place forward transforms of `nfft` arrays of length P.n (shared memory).
+// Must be called by all threads of the block program (contains BLOCK_SYNCs).
+#define FNFTB_SMEM_FFT_FWD(S, nfft, P, nt, T)                                         \
+    do {                                                                              \
+        int _l2s = (P).log2n;                                                         \
+        for (int _p = 0; _p < (P).npass; ++_p) {                                      \
+            const int _R = (P).radix[_p];                                             \
+            _l2s -= ilog2i(_R);                                                       \
+            FOR_THREADS(tid, nt)                                                      \
+            {                                                                         \
+                fft_pass_dispatch<-1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, T);  \
+            }                                                                         \
+            BLOCK_SYNC();                                                             \
+        }                                                                             \
+    } while (0)
+
+// In-place inverse (unnormalised) transforms, consuming the forward's ordering.
+#define FNFTB_SMEM_FFT_INV(S, nfft, P, nt, T)                                         \
+    do {                                                                              \
+        int _l2s = 0;                                                                 \
+        for (int _p = (P).npass - 1; _p >= 0; --_p) {                                 \
+            const int _R = (P).radix[_p];                                             \
+            FOR_THREADS(tid, nt)                                                      \
+            {                                                                         \
+                fft_pass_dispatch<+1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, T);  \
+            }                                                                         \
+            BLOCK_SYNC();                                                             \
+            _l2s += ilog2i(_R);                                                       \
+        }                                                                             \
+    } while (0)

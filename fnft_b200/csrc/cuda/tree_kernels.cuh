@@ -1,0 +1,679 @@
+// fnft_b200 -- block programs for the per-sample transfer-matrix construction and
+// the 2x2 polynomial product tree.
+//
+// Replaces, for a whole batch of signals at once:
+//   fnft__akns_fscatter   /root/reference/src/private/fnft__akns_fscatter.c:64-925
+//                         (leaf cases :118-245, :402-433; zero-frequency expm :46-59)
+//   fnft__poly_fmult2x2   /root/reference/src/private/fnft__poly_fmult.c:381-546
+//                         (pair product :239-328, rescale :330-374)
+//
+// Device data layout ("level buffers"): level l holds, per signal, n_l matrices of
+// degree d_l; element (signal s, matrix m, entry e in {11,12,21,22}, coefficient i)
+// lives at  ((s*n_l + m)*4 + e)*(d_l+1) + i, coefficients highest power first
+// exactly like the reference (fnft__poly_fmult.c:396-401).  Matrix m of level 0
+// is sample D-1-m (fnft__akns_fscatter.c:408) so that the tree computes
+// M_{D-1} * ... * M_0.
+//
+// Normalisation (fnft__poly_fmult.c:330-374,492-493) is applied lazily: the
+// producer of a matrix records max|coeff| in mx[s*n_l+m]; the consumer scales
+// its inputs by 2^-floor(log2(max)) on load and adds the exponents to W[s].
+// Powers of two commute with everything, so result*2^W is unchanged.
+#pragma once
+#include "fft_core.cuh"
+
+// akns scheme ids understood by the leaf kernel (values of
+// fnft__akns_discretization_t, include/private/fnft__akns_discretization_t.h:43-72)
+enum {
+    FNFTB_AKNS_2SPLIT2_MODAL = 0,
+    FNFTB_AKNS_2SPLIT1A = 1,
+    FNFTB_AKNS_2SPLIT1B = 2,
+    FNFTB_AKNS_2SPLIT2A = 3,
+    FNFTB_AKNS_2SPLIT2B = 4,
+    FNFTB_AKNS_2SPLIT2S = 5,
+    FNFTB_AKNS_2SPLIT3S = 8,
+    FNFTB_AKNS_2SPLIT4B = 10,
+    FNFTB_AKNS_4SPLIT4B = 21
+};
+
+// how the second potential r is obtained
+enum { FNFTB_R_NSE = 0 /* r = -kappa*conj(q) */, FNFTB_R_KDV = 1 /* r = -1 */,
+       FNFTB_R_EXPLICIT = 2 };
+
+// ---------------------------------------------------------------------------
+// complex elementary functions needed by the leaves
+// ---------------------------------------------------------------------------
+HD cplx c_sqrt(cplx z)
+{
+    // principal square root, branch cut on the negative real axis
+    const double ax = fabs(z.x), ay = fabs(z.y);
+    if (ax == 0.0 && ay == 0.0)
+        return make_cplx(0.0, z.y);
+    const double m = hypot(z.x, z.y);
+    double t = sqrt(0.5 * (m + ax));
+    double re, im;
+    if (z.x >= 0.0) {
+        re = t;
+        im = z.y / (2.0 * t);
+    } else {
+        re = ay / (2.0 * t);
+        im = copysign(t, z.y);
+    }
+    return make_cplx(re, im);
+}
+HD cplx c_cos(cplx z)
+{
+    double s, c;
+    SINCOS(z.x, &s, &c);
+    return make_cplx(c * cosh(z.y), -s * sinh(z.y));
+}
+HD cplx c_sin(cplx z)
+{
+    double s, c;
+    SINCOS(z.x, &s, &c);
+    return make_cplx(s * cosh(z.y), c * sinh(z.y));
+}
+// sinc as in misc_CSINC (src/private/fnft__misc.c:306-314)
+HD cplx c_sinc(cplx z)
+{
+    if (hypot(z.x, z.y) >= 1.0e-8)
+        return cdiv(c_sin(z), z);
+    return c_cos(cscale(z, 0.57735026918962576450914878050196 /* 1/sqrt(3) */));
+}
+// expm([0 q; r 0]*h): returns (cos D, q*h*sinc D, r*h*sinc D), D = h*sqrt(-q r)
+// (fnft__akns_fscatter.c:46-59)
+HD void zero_freq_expm(cplx *M, double h, cplx q, cplx r)
+{
+    const cplx Delta = cscale(c_sqrt(cneg(cmul(q, r))), h);
+    const cplx del = cscale(c_sinc(Delta), h);
+    M[0] = c_cos(Delta);
+    M[1] = cmul(q, del);
+    M[2] = cmul(r, del);
+}
+
+// ---------------------------------------------------------------------------
+// leaf kernel: one thread per (signal, level-0 matrix)
+// ---------------------------------------------------------------------------
+struct LeafArgs {
+    const cplx *q;   // [B][D]
+    const cplx *r;   // [B][D] or NULL
+    cplx *out;       // level-0 buffer
+    double *mx;      // [B][npad]  (set to 1.0: leaves are not rescaled)
+    int B, D, npad, deg0;
+    int rmode, kappa, scheme;
+    double eps_t;
+    int *status;     // per-signal status (nonzero = error), may be NULL
+};
+
+HD void leaf_matrix(cplx *p /*[4][deg0+1]*/, int scheme, int deg0, double eps_t, cplx q,
+                    cplx r, int *err)
+{
+    cplx *p11 = p, *p12 = p + (deg0 + 1), *p21 = p + 2 * (deg0 + 1), *p22 = p + 3 * (deg0 + 1);
+    const cplx Z = czero();
+    switch (scheme) {
+    case FNFTB_AKNS_2SPLIT2_MODAL: {  // fnft__akns_fscatter.c:118-147
+        const double sclr = eps_t * hypot(q.x, q.y);
+        if (q.x == r.x && sclr >= 1.0)
+            *err = 1;
+        const cplx one_m = csub(make_cplx(1.0, 0.0), cmul(cscale(q, eps_t), cscale(r, eps_t)));
+        const cplx scl = cdiv(make_cplx(1.0, 0.0), c_sqrt(one_m));
+        p11[0] = Z;
+        p11[1] = scl;
+        p12[0] = cmul(scl, cscale(q, eps_t));
+        p12[1] = Z;
+        p21[0] = Z;
+        p21[1] = cmul(scl, cscale(r, eps_t));
+        p22[0] = scl;
+        p22[1] = Z;
+        break;
+    }
+    case FNFTB_AKNS_2SPLIT1A: {  // :149-176
+        cplx e[3];
+        zero_freq_expm(e, eps_t / deg0, q, r);
+        p11[0] = Z;
+        p11[1] = e[0];
+        p12[0] = Z;
+        p12[1] = e[1];
+        p21[0] = e[2];
+        p21[1] = Z;
+        p22[0] = e[0];
+        p22[1] = Z;
+        break;
+    }
+    case FNFTB_AKNS_2SPLIT1B:
+    case FNFTB_AKNS_2SPLIT2A: {  // :178-203
+        cplx e[3];
+        zero_freq_expm(e, eps_t / deg0, q, r);
+        p11[0] = Z;
+        p11[1] = e[0];
+        p12[0] = e[1];
+        p12[1] = Z;
+        p21[0] = Z;
+        p21[1] = e[2];
+        p22[0] = e[0];
+        p22[1] = Z;
+        break;
+    }
+    case FNFTB_AKNS_2SPLIT2B: {  // :204-230
+        cplx e[3];
+        zero_freq_expm(e, 0.5 * eps_t / deg0, q, r);
+        p11[0] = cmul(e[1], e[2]);
+        p11[1] = cmul(e[0], e[0]);
+        p12[0] = cmul(e[0], e[1]);
+        p12[1] = p12[0];
+        p21[0] = cmul(e[0], e[2]);
+        p21[1] = p21[0];
+        p22[0] = p11[1];
+        p22[1] = p11[0];
+        break;
+    }
+    case FNFTB_AKNS_2SPLIT2S: {  // :232-258
+        cplx e[3];
+        zero_freq_expm(e, eps_t / deg0, q, r);
+        p11[0] = Z;
+        p11[1] = e[0];
+        p12[0] = cscale(e[1], 0.5);
+        p12[1] = p12[0];
+        p21[0] = cscale(e[2], 0.5);
+        p21[1] = p21[0];
+        p22[0] = e[0];
+        p22[1] = Z;
+        break;
+    }
+    case FNFTB_AKNS_2SPLIT4B:
+    case FNFTB_AKNS_4SPLIT4B: {  // :402-433
+        cplx a[3], b[3];
+        zero_freq_expm(a, 0.5 * eps_t / deg0, q, r);
+        zero_freq_expm(b, eps_t / deg0, q, r);
+        const double third = 1.0 / 3.0;
+        // products are written exactly in the reference's association order
+        p11[0] = cscale(csub(cscale(cmul(cmul(b[0], a[1]), a[2]), 4.0), cmul(b[1], b[2])), third);
+        p11[1] = cscale(cscale(cadd(cmul(cmul(b[1], a[0]), a[2]), cmul(cmul(b[2], a[0]), a[1])), 4.0), third);
+        p11[2] = cscale(csub(cscale(cmul(cmul(b[0], a[0]), a[0]), 4.0), cmul(b[0], b[0])), third);
+        p12[0] = cscale(csub(cscale(cmul(cmul(b[0], a[0]), a[1]), 4.0), cmul(b[0], b[1])), third);
+        p12[1] = cscale(cscale(cadd(cmul(cmul(b[1], a[0]), a[0]), cmul(cmul(b[2], a[1]), a[1])), 4.0), third);
+        p12[2] = p12[0];
+        p21[0] = cscale(csub(cscale(cmul(cmul(b[0], a[0]), a[2]), 4.0), cmul(b[0], b[2])), third);
+        p21[1] = cscale(cscale(cadd(cmul(cmul(b[2], a[0]), a[0]), cmul(cmul(b[1], a[2]), a[2])), 4.0), third);
+        p21[2] = p21[0];
+        p22[0] = p11[2];
+        p22[1] = p11[1];
+        p22[2] = p11[0];
+        break;
+    }
+    default:
+        *err = 2;
+        for (int i = 0; i < 4 * (deg0 + 1); ++i)
+            p[i] = Z;
+        break;
+    }
+}
+
+BLK void blk_leaf(const LeafArgs &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        const long long total = (long long)a.B * a.npad;
+        if (gid < total) {
+            const int s = (int)(gid / a.npad);
+            const int m = (int)(gid % a.npad);
+            cplx p[4 * 3];  // deg0 <= 2 for every scheme implemented here
+            int err = 0;
+            if (m < a.D) {
+                const size_t idx = (size_t)s * a.D + (size_t)(a.D - 1 - m);
+                const cplx q = a.q[idx];
+                cplx r;
+                if (a.rmode == FNFTB_R_NSE)
+                    r = (a.kappa == 1) ? make_cplx(-q.x, q.y) : make_cplx(q.x, -q.y);
+                else if (a.rmode == FNFTB_R_KDV)
+                    r = make_cplx(-1.0, 0.0);
+                else
+                    r = a.r[idx];
+                leaf_matrix(p, a.scheme, a.deg0, a.eps_t, q, r, &err);
+            } else {
+                // padding with z^deg * I  (fnft__poly_fmult.c:422-438)
+                for (int i = 0; i < 4 * (a.deg0 + 1); ++i)
+                    p[i] = czero();
+                p[0] = make_cplx(1.0, 0.0);
+                p[3 * (a.deg0 + 1)] = make_cplx(1.0, 0.0);
+            }
+            cplx *o = a.out + (size_t)gid * 4 * (a.deg0 + 1);
+            for (int i = 0; i < 4 * (a.deg0 + 1); ++i)
+                o[i] = p[i];
+            a.mx[gid] = 1.0;
+            if (err && a.status)
+                a.status[s] = err;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// shared helpers for the pair-product kernels
+// ---------------------------------------------------------------------------
+// exponent a = floor(log2(max)) used by poly_rescale2x2 (fnft__poly_fmult.c:364)
+HD int rescale_exponent(double mx)
+{
+    return (mx > 0.0 && mx < 1.0e308) ? floor_log2(mx) : 0;
+}
+
+#ifdef FNFTB_EMUL
+static inline void atomic_max_double(double *p, double v)
+{
+    if (v > *p)
+        *p = v;
+}
+static inline void atomic_add_int(int *p, int v) { *p += v; }
+#else
+DEV void atomic_max_double(double *p, double v)
+{
+    // valid for non-negative doubles (bit patterns are ordered like the values)
+    atomicMax((unsigned long long *)p, (unsigned long long)__double_as_longlong(v));
+}
+DEV void atomic_add_int(int *p, int v) { atomicAdd(p, v); }
+#endif
+
+struct PairArgs {
+    const cplx *in;       // level buffer, n_in matrices of degree d_in per signal
+    cplx *out;            // level buffer, n_in/2 matrices of degree 2*d_in
+    const double *mx_in;  // [B][n_in]
+    double *mx_out;       // [B][n_in/2]  (must be zeroed when atomics are used)
+    int *W;               // [B]
+    cplx *gbuf;           // [B][pairs][4][R][N2] partial row results (R > 1)
+    int B, n_in, d_in;
+    int normalize;
+    int N;        // cyclic convolution length (power of two, >= 2*d_in)
+    int wrap;     // 1 if N == 2*d_in (top coefficient handled analytically)
+    int R, N2;    // N = R * N2; R == 1: whole product inside one CTA
+    int G;        // pairs per CTA (R == 1)
+    FftPlan plan; // plan for length N2
+    TwTable T;
+};
+
+HD double load_scale(const PairArgs &a, size_t mat /* s*n_in + m */, int *expo)
+{
+    if (!a.normalize) {
+        *expo = 0;
+        return 1.0;
+    }
+    const int e = rescale_exponent(a.mx_in[mat]);
+    *expo = e;
+    return ldexp(1.0, -e);
+}
+
+// Small-degree pair products by direct convolution: one thread per
+// (signal, pair, output entry).  d_in is a template parameter so that the
+// accumulators stay in registers.
+template <int DIN>
+BLK void blk_pair_direct(const PairArgs &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const int npairs = a.n_in / 2;
+        const long long gid = (long long)bid.x * nt + tid;
+        const long long total = (long long)a.B * npairs * 4;
+        if (gid < total) {
+            const int e = (int)(gid & 3);
+            const long long sp = gid >> 2;  // s*npairs + pair
+            const int pair = (int)(sp % npairs);
+            const int s = (int)(sp / npairs);
+            const int row = e >> 1, col = e & 1;
+            const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair;
+            int eA, eB;
+            const double sA = load_scale(a, matA, &eA);
+            const double sB = load_scale(a, matA + 1, &eB);
+            const cplx *A = a.in + matA * 4 * (DIN + 1);
+            const cplx *Bm = A + 4 * (DIN + 1);
+            const cplx *Ar0 = A + (row * 2 + 0) * (DIN + 1);
+            const cplx *Ar1 = A + (row * 2 + 1) * (DIN + 1);
+            const cplx *B0c = Bm + (0 * 2 + col) * (DIN + 1);
+            const cplx *B1c = Bm + (1 * 2 + col) * (DIN + 1);
+            cplx acc[2 * DIN + 1];
+#pragma unroll
+            for (int k = 0; k < 2 * DIN + 1; ++k)
+                acc[k] = czero();
+            cplx b0[DIN + 1], b1[DIN + 1];
+#pragma unroll
+            for (int j = 0; j <= DIN; ++j) {
+                b0[j] = cscale(B0c[j], sB);
+                b1[j] = cscale(B1c[j], sB);
+            }
+#pragma unroll
+            for (int i = 0; i <= DIN; ++i) {
+                const cplx a0 = cscale(Ar0[i], sA), a1 = cscale(Ar1[i], sA);
+#pragma unroll
+                for (int j = 0; j <= DIN; ++j) {
+                    cfma(acc[i + j], a0, b0[j]);
+                    cfma(acc[i + j], a1, b1[j]);
+                }
+            }
+            cplx *o = a.out + ((size_t)sp * 4 + e) * (2 * DIN + 1);
+            double m2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 2 * DIN + 1; ++k) {
+                o[k] = acc[k];
+                m2 = fmax(m2, cabs2(acc[k]));
+            }
+            atomic_max_double(&a.mx_out[sp], sqrt(m2));
+            if (e == 0 && a.normalize)
+                atomic_add_int(&a.W[s], eA + eB);
+        }
+    }
+}
+
+// FFT-based pair product.
+//   R == 1 : CTA handles G consecutive pairs of one signal completely.
+//            grid.x = B * ceil(npairs / G)
+//   R  > 1 : CTA (s, pair, k1) computes the bins k == k1 (mod R) of the length-N
+//            cyclic product from length-N2 transforms and writes the length-N2
+//            inverse transform of those bins to gbuf; blk_pair_combine finishes.
+//            grid.x = B * npairs * R
+// Shared memory: cplx S[8][G][N2] followed by cplx top[8][G], double sc[2][G],
+// double red[nt].
+HD size_t pair_smem_bytes(int G, int N2, int nt)
+{
+    return sizeof(cplx) * ((size_t)8 * G * N2 + 8 * G) + sizeof(double) * (2 * G + nt);
+}
+
+BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
+{
+    const int npairs = a.n_in / 2;
+    const int G = a.G, N2 = a.N2, R = a.R;
+    const int din1 = a.d_in + 1;
+    cplx *S = (cplx *)smem;
+    cplx *top = S + (size_t)8 * G * N2;
+    double *sc = (double *)(top + 8 * G);
+    double *red = sc + 2 * G;
+
+    int s, pair0, k1;
+    if (R == 1) {
+        const int cpb = (npairs + G - 1) / G;  // CTAs per signal
+        s = bid.x / cpb;
+        pair0 = (bid.x % cpb) * G;
+        k1 = 0;
+    } else {
+        k1 = bid.x % R;
+        const int sp = bid.x / R;
+        pair0 = sp % npairs;
+        s = sp / npairs;
+    }
+    const int nbody = a.wrap ? a.d_in : din1;  // coefficients that enter the FFT
+
+    // phase 0: per-matrix scale factors, exponent bookkeeping
+    FOR_THREADS(tid, nt)
+    {
+        for (int t2 = tid; t2 < 2 * G; t2 += nt) {
+            const int g = t2 >> 1, side = t2 & 1;
+            const int pair = pair0 + g;
+            double scale = 0.0;
+            if (pair < npairs) {
+                int e;
+                scale = load_scale(a, (size_t)s * a.n_in + 2 * (size_t)pair + side, &e);
+                if (a.normalize && k1 == 0 && e != 0)
+                    atomic_add_int(&a.W[s], e);
+            }
+            sc[side * G + g] = scale;
+        }
+    }
+    BLOCK_SYNC();
+
+    // phase A: load (and for R > 1 fold the radix-R column step into the load)
+    FOR_THREADS(tid, nt)
+    {
+        if (R == 1) {
+            const int total = 8 * G * N2;
+            for (int idx = tid; idx < total; idx += nt) {
+                const int i = idx % N2;
+                const int pg = idx / N2;  // p*G + g
+                const int g = pg % G, p = pg / G;
+                const int pair = pair0 + g;
+                cplx v = czero();
+                if (pair < npairs && i < nbody) {
+                    const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> 2);
+                    v = cscale(a.in[(mat * 4 + (p & 3)) * din1 + i], sc[(p >> 2) * G + g]);
+                }
+                S[(size_t)pg * N2 + swz(i)] = v;
+            }
+        } else {
+            // y[n2] = w_N^(n2*k1) * sum_{n1<R/2} x[n1*N2+n2] * w_R^(n1*k1)
+            const int half = R / 2;
+            for (int n2 = tid; n2 < N2; n2 += nt) {
+                const cplx wn = cispi(-2.0 * (double)(((long long)n2 * k1) % a.N) / (double)a.N);
+                for (int p = 0; p < 8; ++p) {
+                    const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair0 + (p >> 2);
+                    const cplx *x = a.in + (mat * 4 + (p & 3)) * din1;
+                    cplx acc = czero();
+                    for (int n1 = 0; n1 < half; ++n1) {
+                        const int i = n1 * N2 + n2;
+                        if (i >= nbody)
+                            break;
+                        const cplx wr = cispi(-2.0 * (double)((n1 * k1) % R) / (double)R);
+                        cfma(acc, x[i], wr);
+                    }
+                    S[(size_t)p * N2 + swz(n2)] = cscale(cmul(acc, wn), sc[(p >> 2) * G]);
+                }
+            }
+        }
+        // top coefficients (only used when wrap)
+        for (int pg = tid; pg < 8 * G; pg += nt) {
+            const int g = pg % G, p = pg / G;
+            const int pair = pair0 + g;
+            cplx v = czero();
+            if (a.wrap && pair < npairs) {
+                const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> 2);
+                v = cscale(a.in[(mat * 4 + (p & 3)) * din1 + a.d_in], sc[(p >> 2) * G + g]);
+            }
+            top[pg] = v;
+        }
+    }
+    BLOCK_SYNC();
+
+    // phase B: 8*G forward transforms of length N2
+    FNFTB_SMEM_FFT_FWD(S, 8 * G, a.plan, nt, a.T);
+
+    // phase C: pointwise 2x2 products; results overwrite the A-side arrays
+    const int fs = plan_first_stride_log2(a.plan);
+    FOR_THREADS(tid, nt)
+    {
+        const int total = G * N2;
+        for (int idx = tid; idx < total; idx += nt) {
+            const int pos = idx % N2;
+            const int g = idx / N2;
+            double sgn = 0.0;  // (-1)^k of the true frequency index k of this bin
+            if (a.wrap) {
+                if (R == 1)
+                    sgn = ((pos >> fs) & 1) ? -1.0 : 1.0;
+                else
+                    sgn = (k1 & 1) ? -1.0 : 1.0;
+            }
+            const int ph = swz(pos);
+            cplx v[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const cplx t = top[p * G + g];
+                const cplx x = S[((size_t)p * G + g) * N2 + ph];
+                v[p] = make_cplx(x.x + sgn * t.x, x.y + sgn * t.y);
+            }
+            // [A11 A12; A21 A22] * [B11 B12; B21 B22], A = v[0..3], B = v[4..7]
+            cplx c11 = cmul(v[0], v[4]);
+            cfma(c11, v[1], v[6]);
+            cplx c12 = cmul(v[0], v[5]);
+            cfma(c12, v[1], v[7]);
+            cplx c21 = cmul(v[2], v[4]);
+            cfma(c21, v[3], v[6]);
+            cplx c22 = cmul(v[2], v[5]);
+            cfma(c22, v[3], v[7]);
+            S[((size_t)0 * G + g) * N2 + ph] = c11;
+            S[((size_t)1 * G + g) * N2 + ph] = c12;
+            S[((size_t)2 * G + g) * N2 + ph] = c21;
+            S[((size_t)3 * G + g) * N2 + ph] = c22;
+        }
+    }
+    BLOCK_SYNC();
+
+    // phase D: 4*G inverse transforms
+    FNFTB_SMEM_FFT_INV(S, 4 * G, a.plan, nt, a.T);
+
+    // phase E: write out
+    if (R > 1) {
+        FOR_THREADS(tid, nt)
+        {
+            cplx *gb = a.gbuf + (((size_t)s * npairs + pair0) * 4) * (size_t)R * N2;
+            for (int idx = tid; idx < 4 * N2; idx += nt) {
+                const int n2 = idx % N2, e = idx / N2;
+                gb[((size_t)e * R + k1) * N2 + n2] = S[(size_t)e * N2 + swz(n2)];
+            }
+        }
+        return;
+    }
+    const int dout1 = 2 * a.d_in + 1;
+    const double invN = 1.0 / (double)a.N;
+    for (int g = 0; g < G; ++g) {
+        const int pair = pair0 + g;
+        if (pair >= npairs)
+            break;
+        FOR_THREADS(tid, nt)
+        {
+            cplx ct[4];
+            {
+                const cplx tA11 = top[0 * G + g], tA12 = top[1 * G + g], tA21 = top[2 * G + g],
+                           tA22 = top[3 * G + g];
+                const cplx tB11 = top[4 * G + g], tB12 = top[5 * G + g], tB21 = top[6 * G + g],
+                           tB22 = top[7 * G + g];
+                ct[0] = cmul(tA11, tB11);
+                cfma(ct[0], tA12, tB21);
+                ct[1] = cmul(tA11, tB12);
+                cfma(ct[1], tA12, tB22);
+                ct[2] = cmul(tA21, tB11);
+                cfma(ct[2], tA22, tB21);
+                ct[3] = cmul(tA21, tB12);
+                cfma(ct[3], tA22, tB22);
+            }
+            cplx *o = a.out + ((size_t)s * npairs + pair) * 4 * dout1;
+            double m2 = 0.0;
+            for (int idx = tid; idx < 4 * dout1; idx += nt) {
+                const int i = idx % dout1, e = idx / dout1;
+                cplx v;
+                if (a.wrap && i == a.N) {
+                    v = ct[e];
+                } else {
+                    v = cscale(S[((size_t)e * G + g) * N2 + swz(i)], invN);
+                    if (a.wrap && i == 0)
+                        v = csub(v, ct[e]);
+                }
+                o[idx] = v;
+                m2 = fmax(m2, cabs2(v));
+            }
+            red[tid] = m2;
+        }
+        BLOCK_SYNC();
+        FOR_THREADS(tid, nt)
+        {
+            if (tid == 0) {
+                double m2 = 0.0;
+                for (int t = 0; t < nt; ++t)
+                    m2 = fmax(m2, red[t]);
+                a.mx_out[(size_t)s * npairs + pair] = sqrt(m2);
+            }
+        }
+        BLOCK_SYNC();
+    }
+}
+
+// Finishes a row-split product: radix-R inverse column step, 1/N scaling, wrap
+// correction, max|coeff|.  One thread per (signal, pair, entry, n2).
+template <int R>
+BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const int npairs = a.n_in / 2;
+        const int N2 = a.N2;
+        const long long gid = (long long)bid.x * nt + tid;
+        const long long total = (long long)a.B * npairs * 4 * N2;
+        if (gid < total) {
+            const int n2 = (int)(gid % N2);
+            const long long spe = gid / N2;  // (s*npairs + pair)*4 + e
+            const int e = (int)(spe & 3);
+            const long long sp = spe >> 2;
+            const int s = (int)(sp / npairs);
+            const int pair = (int)(sp % npairs);
+            const cplx *gb = a.gbuf + (size_t)spe * R * N2;
+            cplx v[R];
+#pragma unroll
+            for (int k1 = 0; k1 < R; ++k1) {
+                const cplx w = cispi(2.0 * (double)(((long long)k1 * n2) % a.N) / (double)a.N);
+                v[k1] = cmul(gb[(size_t)k1 * N2 + n2], w);
+            }
+            Dft<R, +1>::run(v);
+            const int dout1 = 2 * a.d_in + 1;  // == N + 1 when wrap, <= N otherwise
+            const int din1 = a.d_in + 1;
+            cplx *o = a.out + (size_t)spe * dout1;
+            const double invN = 1.0 / (double)a.N;
+            double m2 = 0.0;
+            cplx ct = czero();
+            if (n2 == 0 && a.wrap) {
+                // product of the top coefficients of row (e>>1) of A and column (e&1) of B
+                const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair;
+                int eA, eB;
+                const double sA = load_scale(a, matA, &eA), sB = load_scale(a, matA + 1, &eB);
+                const cplx *A = a.in + matA * 4 * din1;
+                const cplx *Bm = A + 4 * din1;
+                const int row = e >> 1, col = e & 1;
+                const cplx a0 = cscale(A[(row * 2 + 0) * din1 + a.d_in], sA);
+                const cplx a1 = cscale(A[(row * 2 + 1) * din1 + a.d_in], sA);
+                const cplx b0 = cscale(Bm[(0 * 2 + col) * din1 + a.d_in], sB);
+                const cplx b1 = cscale(Bm[(1 * 2 + col) * din1 + a.d_in], sB);
+                ct = cmul(a0, b0);
+                cfma(ct, a1, b1);
+                o[a.N] = ct;
+                m2 = cabs2(ct);
+            }
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) {
+                const int i = n1 * N2 + n2;
+                if (i >= dout1)
+                    break;
+                cplx c = cscale(v[n1], invN);
+                if (i == 0)
+                    c = csub(c, ct);  // ct == 0 unless wrap
+                o[i] = c;
+                m2 = fmax(m2, cabs2(c));
+            }
+            atomic_max_double(&a.mx_out[sp], sqrt(m2));
+        }
+    }
+}
+
+// Final step: apply the pending scale of the single remaining matrix, strip the
+// padding-induced trailing coefficients and emit [B][4][deg_out+1] plus W.
+struct FinalArgs {
+    const cplx *in;      // level buffer with 1 matrix per signal, degree d_full
+    const double *mx_in; // [B]
+    cplx *tm;            // [B][4][deg_out+1]
+    int *W;              // [B]
+    int B, d_full, deg_out, normalize;
+};
+
+BLK void blk_tree_final(const FinalArgs &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        const long long per = 4LL * (a.deg_out + 1);
+        const long long total = (long long)a.B * per;
+        if (gid < total) {
+            const int s = (int)(gid / per);
+            const int rem = (int)(gid % per);
+            const int e = rem / (a.deg_out + 1), i = rem % (a.deg_out + 1);
+            int ex = 0;
+            double scale = 1.0;
+            if (a.normalize) {
+                ex = rescale_exponent(a.mx_in[s]);
+                scale = ldexp(1.0, -ex);
+            }
+            a.tm[gid] = cscale(a.in[((size_t)s * 4 + e) * (a.d_full + 1) + i], scale);
+            if (rem == 0 && a.normalize)
+                a.W[s] += ex;  // the tree kernels of this signal have all finished
+        }
+    }
+}
