@@ -1,0 +1,298 @@
+// fnft_b200 -- bound-state kernels: Newton refinement of eigenvalues on the slow
+// Boffetta-Osborne / CF4_2 recurrence and the norming constants.
+//
+// Replaces, for a batch of (signal, eigenvalue) pairs:
+//   fnft__nse_scatter_bound_states   /root/reference/src/private/fnft__nse_scatter_bound_states.c:29-667
+//       forward sweep with lambda-derivative  :281-338
+//       backward sweep                         :480-530
+//       a, a' and the choice of b             :639-654
+//   nsev_refine_bound_states_newton  /root/reference/src/fnft_nsev.c:973-1038
+//   misc_l2norm2 (imaginary-part bound)        /root/reference/src/private/fnft__misc.c:90-112
+//
+// Work decomposition of this first version: one thread per (signal, eigenvalue),
+// sequential over the D samples (the recurrence is a product of 4x4 block
+// triangular matrices; the warp-parallel chunked scan is the planned refinement).
+#pragma once
+#include "tree_kernels.cuh"
+
+HD cplx c_exp(cplx z)
+{
+    double s, c;
+    SINCOS(z.y, &s, &c);
+    const double e = exp(z.x);
+    return make_cplx(e * c, e * s);
+}
+// cosh and sinh of a complex argument
+HD void c_coshsinh(cplx z, cplx *ch, cplx *sh)
+{
+    double s, c;
+    SINCOS(z.y, &s, &c);
+    const double chx = cosh(z.x), shx = sinh(z.x);
+    *ch = make_cplx(chx * c, shx * s);
+    *sh = make_cplx(shx * c, chx * s);
+}
+
+// One BO step at spectral parameter l with step h (h < 0 for the backward sweep):
+// U = expm([[-i l, q],[r, i l]] h) and, if WITH_D, dU/dl
+// (fnft__nse_scatter_bound_states.c:297-322).
+template <bool WITH_D>
+HD void bo_step(cplx q, cplx r, cplx l, double h, cplx U[4], cplx Ud[4])
+{
+    const cplx l2 = cmul(l, l);
+    const cplx ks = csub(cmul(q, r), l2);
+    const cplx k = c_sqrt(ks);
+    cplx ch, shk;
+    c_coshsinh(cscale(k, h), &ch, &shk);
+    cplx sh;
+    if (ks.x != 0.0 || ks.y != 0.0)
+        sh = cdiv(shk, k);
+    else
+        sh = make_cplx(h, 0.0);
+    const cplx u1 = cmuli(cmul(l, sh));  // l*sh*i
+    U[0] = csub(ch, u1);
+    U[1] = cmul(q, sh);
+    U[2] = cmul(r, sh);
+    U[3] = cadd(ch, u1);
+    if (WITH_D) {
+        const cplx chi = cdiv(ch, ks);
+        const cplx ud1 = cmuli(cscale(cmul(l2, chi), h));                    // h*l^2*chi*i
+        const cplx ud2 = cdiv(cmul(l, csub(cscale(ch, h), sh)), ks);         // l*(h*ch-sh)/ks
+        const cplx l2i_ks = cdiv(cmuli(l2), ks);                             // l^2*i/ks
+        // (l*h + i + l^2 i/ks) and (l*h - i - l^2 i/ks)
+        const cplx t1 = make_cplx(l.x * h + l2i_ks.x, l.y * h + 1.0 + l2i_ks.y);
+        const cplx t2 = make_cplx(l.x * h - l2i_ks.x, l.y * h - 1.0 - l2i_ks.y);
+        Ud[0] = csub(ud1, cmul(t1, sh));
+        Ud[1] = cneg(cmul(q, ud2));
+        Ud[2] = cneg(cmul(r, ud2));
+        Ud[3] = csub(cneg(ud1), cmul(t2, sh));
+    }
+}
+
+struct BoundArgs {
+    const cplx *q;     // [B][D] effective (preprocessed) samples, r = -conj(q)
+    int B, D;          // D = number of effective samples
+    int upsampling;    // 1 (BO) or 2 (CF4_2)
+    int Kmax;          // stride of the per-signal eigenvalue arrays
+    const int *K;      // [B] number of eigenvalues per signal
+    cplx *lam;         // [B][Kmax] in/out
+    double T0, T1, eps_t, bc;
+    double lweight;    // 1 for BO, 0.5 for CF4_2 (sum of the method weights)
+    double scl;        // factor of a' (1 or 0.5)
+    int niter;
+    double box0, box1, box2;  // re_min, re_max, im_min
+    const double *box3;       // [B] im_max per signal (NULL => +inf)
+    int *flag;         // [B][Kmax] status per eigenvalue (3 = division by zero)
+    // norming-constant pass
+    cplx *a_out, *ap_out, *b_out;  // [B][Kmax]
+    cplx *phi;         // scratch [(D_given+1)][B*Kmax][2]
+};
+
+// forward sweep: returns PHI(D) and dPHI/dl(D); optionally stores PHI at the given
+// sample points into scratch
+HD void bound_forward(const BoundArgs &a, const cplx *q, cplx lcur, cplx *phi_out, cplx *dphi_out,
+                      cplx *store, size_t store_stride)
+{
+    const cplx l = cscale(lcur, a.lweight);
+    const double tb = a.T0 - a.eps_t * a.bc;
+    // PHI1[0] = exp(-i*l_curr*(T0 - eps*bc))
+    cplx phi1 = c_exp(make_cplx(lcur.y * tb, -lcur.x * tb));
+    cplx phi2 = czero();
+    cplx d1 = cmul(phi1, make_cplx(0.0, -tb));
+    cplx d2 = czero();
+    if (store) {
+        store[0] = phi1;
+        store[1] = phi2;
+    }
+    int count = a.upsampling - 1;
+    size_t ng = 0;
+    for (int n = 0; n < a.D; ++n) {
+        const cplx qn = q[n];
+        const cplx rn = make_cplx(-qn.x, qn.y);
+        cplx U[4], Ud[4];
+        bo_step<true>(qn, rn, l, a.eps_t, U, Ud);
+        cplx c = cmul(Ud[0], phi1);
+        cfma(c, Ud[1], phi2);
+        cfma(c, U[0], d1);
+        cfma(c, U[1], d2);
+        cplx e = cmul(Ud[2], phi1);
+        cfma(e, Ud[3], phi2);
+        cfma(e, U[2], d1);
+        cfma(e, U[3], d2);
+        d1 = c;
+        d2 = e;
+        cplx f = cmul(U[2], phi1);
+        cfma(f, U[3], phi2);
+        cplx g = cmul(U[0], phi1);
+        cfma(g, U[1], phi2);
+        phi1 = g;
+        phi2 = f;
+        if (count == 0) {
+            count = a.upsampling - 1;
+            ++ng;
+            if (store) {
+                store[ng * store_stride] = phi1;
+                store[ng * store_stride + 1] = phi2;
+            }
+        } else {
+            --count;
+        }
+    }
+    phi_out[0] = phi1;
+    phi_out[1] = phi2;
+    dphi_out[0] = d1;
+    dphi_out[1] = d2;
+}
+
+HD void bound_a_aprime(const BoundArgs &a, cplx lcur, const cplx *phi, const cplx *dphi, cplx *aval,
+                       cplx *apval)
+{
+    const double te = a.T1 + a.eps_t * a.bc;
+    const cplx ex = c_exp(make_cplx(-lcur.y * te, lcur.x * te));  // exp(i*l*te)
+    *aval = cmul(phi[0], ex);
+    cplx ap = cmul(dphi[0], ex);
+    cfma(ap, make_cplx(0.0, te), *aval);
+    *apval = cscale(ap, a.scl);
+}
+
+// Newton iterations, one thread per (signal, eigenvalue).  grid.x*nt >= B*Kmax
+BLK void blk_newton(const BoundArgs &a, blk3 bid, int nt, void *)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        if (gid < (long long)a.B * a.Kmax) {
+            const int s = (int)(gid / a.Kmax), i = (int)(gid % a.Kmax);
+            if (i < a.K[s]) {
+                const cplx *q = a.q + (size_t)s * a.D;
+                cplx lam = a.lam[gid];
+                const double im_max = a.box3 ? a.box3[s] : INFINITY;
+                const double eprecision = 2.220446049250313e-16 * 100;
+                int iter = 0, status = 0;
+                while (true) {
+                    cplx phi[2], dphi[2], av, apv;
+                    bound_forward(a, q, lam, phi, dphi, (cplx *)0, 0);
+                    bound_a_aprime(a, lam, phi, dphi, &av, &apv);
+                    if (av.x == 0.0 && av.y == 0.0)
+                        break;
+                    if (apv.x == 0.0 && apv.y == 0.0) {
+                        status = 3;
+                        break;
+                    }
+                    const cplx err = cdiv(av, apv);
+                    lam = csub(lam, err);
+                    ++iter;
+                    if (lam.y > im_max || lam.x > a.box1 || lam.x < a.box0 || lam.y < a.box2)
+                        break;
+                    if (!(hypot(err.x, err.y) > eprecision && iter < a.niter))
+                        break;
+                }
+                a.lam[gid] = lam;
+                a.flag[gid] = status;
+            }
+        }
+    }
+}
+
+// a, a', b for given eigenvalues: forward sweep storing PHI, backward sweep with the
+// error metric of fnft__nse_scatter_bound_states.c:642-654.
+BLK void blk_normconsts(const BoundArgs &a, blk3 bid, int nt, void *)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        const long long tot = (long long)a.B * a.Kmax;
+        if (gid < tot) {
+            const int s = (int)(gid / a.Kmax), i = (int)(gid % a.Kmax);
+            if (i < a.K[s]) {
+                const cplx *q = a.q + (size_t)s * a.D;
+                const cplx lcur = a.lam[gid];
+                const int Dg = a.D / a.upsampling;
+                cplx *store = a.phi + (size_t)gid * 2;
+                const size_t stride = (size_t)tot * 2;
+                cplx phi[2], dphi[2], av, apv;
+                bound_forward(a, q, lcur, phi, dphi, store, stride);
+                bound_a_aprime(a, lcur, phi, dphi, &av, &apv);
+                a.a_out[gid] = av;
+                a.ap_out[gid] = apv;
+                // backward sweep
+                const cplx l = cscale(lcur, a.lweight);
+                const double te = a.T1 + a.eps_t * a.bc;
+                cplx psi1 = czero();
+                cplx psi2 = c_exp(make_cplx(-lcur.y * te, lcur.x * te));
+                double best = INFINITY;
+                cplx bval = czero();
+                int ng = Dg;
+                // candidate at n = D_given (PSI1 = 0 -> metric is inf/NaN, never chosen)
+                int count = a.upsampling - 1;
+                for (int n = a.D - 1; n >= 0; --n) {
+                    const cplx qn = q[n];
+                    const cplx rn = make_cplx(-qn.x, qn.y);
+                    cplx U[4], Ud[4];
+                    bo_step<false>(qn, rn, l, -a.eps_t, U, Ud);
+                    cplx c = cmul(U[2], psi1);
+                    cfma(c, U[3], psi2);
+                    cplx d = cmul(U[0], psi1);
+                    cfma(d, U[1], psi2);
+                    psi1 = d;
+                    psi2 = c;
+                    if (count == 0) {
+                        count = a.upsampling - 1;
+                        --ng;
+                        const cplx p1 = store[(size_t)ng * stride], p2 = store[(size_t)ng * stride + 1];
+                        // tmp = |0.5*log(|(PHI2/PSI2)/(PHI1/PSI1)|)|
+                        const cplx r2 = cdiv(p2, psi2), r1 = cdiv(p1, psi1);
+                        const cplx rr = cdiv(r2, r1);
+                        const double tmp = fabs(0.5 * log(hypot(rr.x, rr.y)));
+                        // the reference scans n ascending and keeps the first strict
+                        // minimum; scanning descending we therefore accept ties
+                        if (tmp <= best) {
+                            best = tmp;
+                            bval = r1;
+                        }
+                    } else {
+                        --count;
+                    }
+                }
+                a.b_out[gid] = bval;
+            }
+        }
+    }
+}
+
+// 1.5 * 0.25 * l2norm2(q)  (src/fnft_nsev.c:582-592, src/private/fnft__misc.c:90-112).
+// One CTA per signal.  q_given[i] = up * q[up*i + (up-1)] for upsampling up = 2
+// (src/fnft_nsev.c:647-651), q itself for up = 1.
+struct NormArgs {
+    const cplx *q;
+    int B, D, upsampling;
+    double T0, T1;
+    double *out;  // [B]
+};
+BLK void blk_imbound(const NormArgs &a, blk3 bid, int nt, void *smem)
+{
+    double *red = (double *)smem;
+    const int s = bid.x;
+    const int Dg = a.D / a.upsampling;
+    const double h = (a.T1 - a.T0) / Dg;
+    FOR_THREADS(tid, nt)
+    {
+        double acc = 0.0;
+        for (int i = tid; i < Dg; i += nt) {
+            const cplx z = a.q[(size_t)s * a.D + (size_t)i * a.upsampling + (a.upsampling - 1)];
+            const double m = hypot(z.x, z.y) * a.upsampling;
+            const double w = (i == 0 || i == Dg - 1) ? 0.5 * h : h;
+            acc += w * m * m;
+        }
+        red[tid] = acc;
+    }
+    BLOCK_SYNC();
+    FOR_THREADS(tid, nt)
+    {
+        if (tid == 0) {
+            double t = 0.0;
+            for (int i = 0; i < nt; ++i)
+                t += red[i];
+            a.out[s] = 1.5 * 0.25 * t;
+        }
+    }
+}

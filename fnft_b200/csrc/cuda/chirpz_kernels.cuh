@@ -1,0 +1,249 @@
+// fnft_b200 -- batched chirp-z evaluation of transfer-matrix polynomials and the
+// continuous-spectrum epilogues.
+//
+// Replaces fnft__poly_chirpz  (/root/reference/src/private/fnft__poly_chirpz.c:33-105)
+// and the loops that follow its two calls in
+//   nsev_compute_contspec     (/root/reference/src/fnft_nsev.c:822-876)
+//   tf2contspec_negxi         (/root/reference/src/fnft_kdvv.c:169-203).
+//
+// Bluestein:  y_n = p[deg-n] A^-n W^(n^2/2),  v_n = W^(-n^2/2) (wrapped),
+//             g = IFFT_L( FFT_L(y) . FFT_L(v) ),  result_m = W^(m^2/2) g_m / L.
+// L is a power of two >= deg + M, factored L = N1 * N2 (four-step FFT):
+//   cz_cols_fwd : generate y (or v) on the fly, N1-point column FFTs, twiddle
+//   cz_rows     : N2-point row FFT, * FFT(v), inverse row FFT      (shared memory)
+//   cz_cols_inv : conj twiddle, inverse column FFTs, * W^(m^2/2)/L, epilogue
+// The spectrum of v depends only on (deg, M, W) and is computed once per batch.
+// Spectra are kept in the digit-reversed order the in-place transforms produce.
+#pragma once
+#include "fft_core.cuh"
+
+enum { FNFTB_CZ_RAW = 0, FNFTB_CZ_NSEV = 1, FNFTB_CZ_KDVV = 2 };
+
+struct CzArgs {
+    // polynomials: coefficient i (highest power first) of poly j of signal s is
+    // tm[s*tm_sstride + ent[j]*(deg+1) + i]
+    const cplx *tm;
+    size_t tm_sstride;
+    int ent[2];
+    int npoly;
+    int deg;
+    int B, M;
+    int L, N1, N2;
+    int C;           // columns per CTA in the column kernels
+    FftPlan plan1, plan2;
+    double lwr, lwi; // ln|W|, arg W
+    double lar, lai; // ln|A|, arg A
+    cplx *ybuf;      // [B][npoly][N1][N2]
+    cplx *vhat;      // [N1][N2]
+    TwTable T;
+    int gen_v;       // cz_cols_fwd: 1 = generate the chirp filter v instead of y
+    int fwd_only;    // cz_rows: 1 = forward transform only (used for vhat)
+    // epilogue
+    int mode;        // FNFTB_CZ_*
+    int cstype;      // NSEV: 0 reflection coefficient, 1 a and b, 2 both
+    cplx *out;
+    size_t out_sstride;
+    const int *W;    // per-signal normalisation exponent (NSEV a/b), may be NULL
+    double xi0, eps_xi;
+    double ph_rho, ph_a, ph_b;  // NSEV boundary phase factors
+    double kdv_ph;              // KDVV: T1 + boundary_coeff*eps_t
+    double kdv_sqrtz;           // KDVV 2SPLIT2A correction: eps_t/deg, else 0
+    int *status;                // [B], set to 3 (division by zero) when H0 == 0
+};
+
+// exp(lr*h_r) * exp(i*(li1*h1 + li2*h2)) with the phase accumulated in
+// double-double so that huge arguments (n^2/2 * arg W) lose no accuracy.
+HD cplx chirp_factor(double mag_arg, double li1, double h1, double li2, double h2)
+{
+    const double p1 = li1 * h1, e1 = fma(li1, h1, -p1);
+    const double p2 = li2 * h2, e2 = fma(li2, h2, -p2);
+    const double s = p1 + p2;
+    const double bb = s - p1;
+    const double t = (p1 - (s - bb)) + (p2 - bb);
+    const double err = t + e1 + e2;
+    double sn, cs;
+    SINCOS(s, &sn, &cs);
+    cplx r = make_cplx(cs - sn * err, sn + cs * err);
+    if (mag_arg != 0.0)
+        r = cscale(r, exp(mag_arg));
+    return r;
+}
+
+HD size_t cz_cols_smem_bytes(int C, int N1, int npoly) { return sizeof(cplx) * (size_t)C * N1 * npoly; }
+
+// grid.x = B * npoly * (N2 / C)   (gen_v: B = npoly = 1)
+BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
+{
+    cplx *S = (cplx *)smem;
+    const int C = a.C, N1 = a.N1, N2 = a.N2;
+    const int tiles = N2 / C;
+    const int tile = bid.x % tiles;
+    const int sj = bid.x / tiles;  // s*npoly + j
+    const int j = sj % a.npoly, s = sj / a.npoly;
+    const int n2_0 = tile * C;
+    const int Np = a.deg + 1;
+    FOR_THREADS(tid, nt)
+    {
+        for (int idx = tid; idx < C * N1; idx += nt) {
+            const int c = idx % C, n1 = idx / C;
+            const long long n = (long long)n1 * N2 + n2_0 + c;
+            cplx v = czero();
+            if (!a.gen_v) {
+                if (n < Np) {
+                    const cplx p = a.tm[(size_t)s * a.tm_sstride + (size_t)a.ent[j] * Np + (a.deg - n)];
+                    const double dn = (double)n;
+                    const cplx ch = chirp_factor(-a.lar * dn + a.lwr * (0.5 * dn * dn), a.lwi,
+                                                 0.5 * dn * dn, -a.lai, dn);
+                    v = cmul(p, ch);
+                }
+            } else {
+                // fnft__poly_chirpz.c:76-82
+                double dn = -1.0;
+                if (n < a.M)
+                    dn = (double)n;
+                else if (n > (long long)a.L - Np)
+                    dn = (double)(a.L - n);
+                if (dn >= 0.0)
+                    v = chirp_factor(-a.lwr * (0.5 * dn * dn), -a.lwi, 0.5 * dn * dn, 0.0, 0.0);
+            }
+            S[(size_t)c * N1 + swz(n1)] = v;
+        }
+    }
+    BLOCK_SYNC();
+    FNFTB_SMEM_FFT_FWD(S, C, a.plan1, nt, a.T);
+    FOR_THREADS(tid, nt)
+    {
+        cplx *dst = (a.gen_v ? a.vhat : a.ybuf + (size_t)sj * a.L);
+        for (int idx = tid; idx < C * N1; idx += nt) {
+            const int c = idx % C, pos = idx / C;
+            const int k1 = plan_freq_of_pos(a.plan1, pos);
+            const int n2 = n2_0 + c;
+            const cplx w = cispi(-2.0 * (double)(((long long)n2 * k1) % a.L) / (double)a.L);
+            dst[(size_t)pos * N2 + n2] = cmul(S[(size_t)c * N1 + swz(pos)], w);
+        }
+    }
+}
+
+// grid.x = B * npoly * N1  (fwd_only: N1)
+BLK void blk_cz_rows(const CzArgs &a, blk3 bid, int nt, void *smem)
+{
+    cplx *S = (cplx *)smem;
+    const int N2 = a.N2;
+    cplx *row = (a.fwd_only ? a.vhat : a.ybuf) + (size_t)bid.x * N2;
+    const int pos1 = bid.x % a.N1;
+    FOR_THREADS(tid, nt)
+    {
+        for (int i = tid; i < N2; i += nt)
+            S[swz(i)] = row[i];
+    }
+    BLOCK_SYNC();
+    FNFTB_SMEM_FFT_FWD(S, 1, a.plan2, nt, a.T);
+    if (a.fwd_only) {
+        FOR_THREADS(tid, nt)
+        {
+            for (int i = tid; i < N2; i += nt)
+                row[i] = S[swz(i)];
+        }
+        return;
+    }
+    FOR_THREADS(tid, nt)
+    {
+        const cplx *vrow = a.vhat + (size_t)pos1 * N2;
+        for (int i = tid; i < N2; i += nt)
+            S[swz(i)] = cmul(S[swz(i)], vrow[i]);
+    }
+    BLOCK_SYNC();
+    FNFTB_SMEM_FFT_INV(S, 1, a.plan2, nt, a.T);
+    FOR_THREADS(tid, nt)
+    {
+        for (int i = tid; i < N2; i += nt)
+            row[i] = S[swz(i)];
+    }
+}
+
+// grid.x = B * (N2 / C); handles all npoly polynomials of a signal so that the
+// epilogue can combine them.  Only output indices m < M are produced.
+BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
+{
+    cplx *S = (cplx *)smem;
+    const int C = a.C, N1 = a.N1, N2 = a.N2;
+    const int tiles = N2 / C;
+    const int tile = bid.x % tiles;
+    const int s = bid.x / tiles;
+    const int n2_0 = tile * C;
+    FOR_THREADS(tid, nt)
+    {
+        for (int j = 0; j < a.npoly; ++j) {
+            const cplx *src = a.ybuf + ((size_t)s * a.npoly + j) * a.L;
+            for (int idx = tid; idx < C * N1; idx += nt) {
+                const int c = idx % C, pos = idx / C;
+                const int k1 = plan_freq_of_pos(a.plan1, pos);
+                const int n2 = n2_0 + c;
+                const cplx w = cispi(2.0 * (double)(((long long)n2 * k1) % a.L) / (double)a.L);
+                S[((size_t)j * C + c) * N1 + swz(pos)] = cmul(src[(size_t)pos * N2 + n2], w);
+            }
+        }
+    }
+    BLOCK_SYNC();
+    FNFTB_SMEM_FFT_INV(S, C * a.npoly, a.plan1, nt, a.T);
+    FOR_THREADS(tid, nt)
+    {
+        const double invL = 1.0 / (double)a.L;
+        for (int idx = tid; idx < C * N1; idx += nt) {
+            const int c = idx % C, n1 = idx / C;
+            const long long m = (long long)n1 * N2 + n2_0 + c;
+            if (m >= a.M)
+                continue;
+            const double dm = (double)m;
+            const cplx ch = cscale(chirp_factor(a.lwr * (0.5 * dm * dm), a.lwi, 0.5 * dm * dm, 0.0, 0.0), invL);
+            cplx H[2];
+            H[1] = czero();
+            for (int j = 0; j < a.npoly; ++j)
+                H[j] = cmul(S[((size_t)j * C + c) * N1 + swz(n1)], ch);
+            cplx *o = a.out + (size_t)s * a.out_sstride;
+            if (a.mode == FNFTB_CZ_RAW) {
+                for (int j = 0; j < a.npoly; ++j)
+                    o[(size_t)j * a.M + m] = H[j];
+            } else if (a.mode == FNFTB_CZ_NSEV) {
+                // src/fnft_nsev.c:846-876; H[0] = H11 (a-poly), H[1] = H21 (b-poly)
+                const double xi = a.xi0 + a.eps_xi * dm;
+                size_t off = 0;
+                if (a.cstype == 0 || a.cstype == 2) {
+                    if (H[0].x == 0.0 && H[0].y == 0.0) {
+                        if (a.status)
+                            a.status[s] = 3;
+                        o[m] = make_cplx(NAN, NAN);
+                    } else {
+                        double sn, cs;
+                        SINCOS(xi * a.ph_rho, &sn, &cs);
+                        o[m] = cdiv(cmul(H[1], make_cplx(cs, sn)), H[0]);
+                    }
+                    off = a.M;
+                }
+                if (a.cstype == 1 || a.cstype == 2) {
+                    const double scale = ldexp(1.0, a.W ? a.W[s] : 0);
+                    double sn, cs;
+                    SINCOS(xi * a.ph_a, &sn, &cs);
+                    o[off + m] = cmul(cscale(H[0], scale), make_cplx(cs, sn));
+                    SINCOS(xi * a.ph_b, &sn, &cs);
+                    o[off + a.M + m] = cmul(cscale(H[1], scale), make_cplx(cs, sn));
+                }
+            } else {
+                // src/fnft_kdvv.c:186-203; H[0] = H12, H[1] = H22, xi grid negated
+                const double xi = -a.xi0 - dm * a.eps_xi;
+                cplx h12 = H[0];
+                if (a.kdv_sqrtz != 0.0) {
+                    double sn, cs;
+                    SINCOS(xi * a.kdv_sqrtz, &sn, &cs);
+                    h12 = cdiv(h12, make_cplx(cs, sn));
+                }
+                double sn, cs;
+                SINCOS(2.0 * xi * a.kdv_ph, &sn, &cs);
+                const cplx num = cmul(make_cplx(cs, sn), h12);
+                // 2*i*xi*H22 - H12
+                const cplx den = make_cplx(-2.0 * xi * H[1].y - h12.x, 2.0 * xi * H[1].x - h12.y);
+                o[m] = cdiv(num, den);
+            }
+        }
+    }
+}

@@ -52,7 +52,11 @@ static inline void emul_sincospi(double a, double *s, double *c)
 // Runs the body exactly once with tid = threadIdx.x.
 #define FOR_THREADS(tid, nt) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
 #define BLOCK_SYNC() __syncthreads()
+#ifdef __CUDA_ARCH__
 #define LDG(p) __ldg(p)
+#else
+#define LDG(p) (*(p))
+#endif
 typedef double2 cplx;
 #define make_cplx(x, y) make_double2((x), (y))
 typedef uint3 blk3;

@@ -1,0 +1,556 @@
+// fnft_b200 -- implementation of the thin C-ABI declared in fnftb_device.h:
+// context / workspace management and the kernel pipelines.
+#include "fnftb_device.h"
+
+#include "bound_kernels.cuh"
+#include "chirpz_driver.cuh"
+#include "resample_kernels.cuh"
+#include "tree_driver.cuh"
+#include "twiddle.h"
+
+#include <string>
+#include <vector>
+
+unsigned long long g_fnftb_launch_count = 0;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s (code %d) at %s:%d", what, code, file, line);
+    g_err = buf;
+    return code ? code : -1;
+}
+#define CU(call)                                                                    \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess)                                                      \
+            return fail((int)_e, cudaGetErrorString(_e), __FILE__, __LINE__);       \
+    } while (0)
+#define RC(call)                                                                    \
+    do {                                                                            \
+        int _rc = (call);                                                           \
+        if (_rc != 0) {                                                             \
+            const char *_m = (_rc > 0) ? cudaGetErrorString((cudaError_t)_rc)       \
+                                       : "internal error";                          \
+            return fail(_rc, _m, __FILE__, __LINE__);                               \
+        }                                                                           \
+    } while (0)
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct fnftb_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cplx *tw = nullptr;
+    int twn = 4096;
+    // staged input
+    size_t B = 0, D = 0;
+    const cplx *q = nullptr, *r = nullptr;
+    Buf qbuf, rbuf, qpre, warn;
+    // tree workspace
+    Buf lev0, lev1, mx0, mx1, gbuf, W, status, tm;
+    // result description
+    size_t deg = 0;        // degree of the transfer matrices held in tm
+    size_t tmB = 0;        // number of matrices held
+    size_t tm_entries = 4; // 4 for matrices, 1 for a standalone polynomial
+    // chirp-z workspace
+    Buf ybuf, vhat, outbuf, pbuf;
+    // bound-state workspace
+    Buf box3, lam, kcnt, flag, aout, apout, bout, phi;
+    int have_box3 = 0;
+};
+
+static int ensure(Buf &b, size_t bytes)
+{
+    if (bytes <= b.cap)
+        return 0;
+    if (b.p)
+        CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    // grow with some slack to avoid repeated reallocations
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        CU(cudaMalloc(&b.p, want));
+    }
+    b.cap = want;
+    return 0;
+}
+
+static void release(Buf &b)
+{
+    if (b.p)
+        cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" {
+
+int fnftb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+const char *fnftb_last_error(void) { return g_err.c_str(); }
+
+unsigned long long fnftb_launch_count(void) { return g_fnftb_launch_count; }
+
+int fnftb_ctx_create(fnftb_ctx **out, int device)
+{
+    if (!out)
+        return fail(-2, "null argument", __FILE__, __LINE__);
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0)
+        return fail(-3, "no CUDA device available (the fnft_b200 hot path has no CPU fallback)",
+                    __FILE__, __LINE__);
+    if (device < 0)
+        CU(cudaGetDevice(&device));
+    if (device >= ndev)
+        return fail(-4, "device index out of range", __FILE__, __LINE__);
+    CU(cudaSetDevice(device));
+    fnftb_ctx *c = new fnftb_ctx();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    std::vector<double> tw(2 * (size_t)c->twn);
+    fnftb_fill_twiddles(tw.data(), (size_t)c->twn);
+    CU(cudaMalloc((void **)&c->tw, sizeof(cplx) * c->twn));
+    CU(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * c->twn, cudaMemcpyHostToDevice));
+    *out = c;
+    return 0;
+}
+
+void fnftb_ctx_destroy(fnftb_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->W,
+                  &c->status, &c->tm, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf,
+                  &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi};
+    for (Buf *b : all)
+        release(*b);
+    if (c->tw)
+        cudaFree(c->tw);
+    if (c->st)
+        cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int fnftb_ctx_device(const fnftb_ctx *c) { return c ? c->device : -1; }
+
+int fnftb_ctx_sync(fnftb_ctx *c)
+{
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+void *fnftb_ctx_stream(fnftb_ctx *c) { return (void *)c->st; }
+
+static size_t per_signal_bytes(size_t D, int deg0, size_t M, int npoly)
+{
+    const size_t npad = next_pow2_sz(D);
+    size_t b = 0;
+    b += 2 * tree_lev_elems(1, npad, (size_t)deg0) * sizeof(cplx);
+    b += 2 * npad * sizeof(double);
+    b += tree_gbuf_elems(1, npad, (size_t)deg0) * sizeof(cplx);
+    b += 4 * ((size_t)deg0 * D + 1) * sizeof(cplx);
+    if (M > 0) {
+        const CzGeom g = cz_geometry((int)((size_t)deg0 * D), (int)M);
+        b += (size_t)npoly * g.L * sizeof(cplx);
+        b += 3 * M * sizeof(cplx);
+    }
+    b += 2 * D * sizeof(cplx);
+    return b;
+}
+
+size_t fnftb_max_chunk(const fnftb_ctx *c, size_t D, int deg0, size_t M, int npoly,
+                       size_t budget_bytes)
+{
+    if (budget_bytes == 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(c->device);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+            free_b = (size_t)8 << 30;
+        budget_bytes = free_b / 2;
+        const size_t cap = (size_t)24 << 30;
+        if (budget_bytes > cap)
+            budget_bytes = cap;
+    }
+    size_t n = budget_bytes / per_signal_bytes(D, deg0, M, npoly);
+    return n < 1 ? 1 : n;
+}
+
+int fnftb_set_signals(fnftb_ctx *c, size_t B, size_t D, const void *q, const void *r, int on_device)
+{
+    if (!c || !q || B == 0 || D == 0)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    c->B = B;
+    c->D = D;
+    c->have_box3 = 0;
+    if (on_device) {
+        c->q = (const cplx *)q;
+        c->r = (const cplx *)r;
+        return 0;
+    }
+    const size_t bytes = B * D * sizeof(cplx);
+    RC(ensure(c->qbuf, bytes));
+    CU(cudaMemcpyAsync(c->qbuf.p, q, bytes, cudaMemcpyHostToDevice, c->st));
+    c->q = (const cplx *)c->qbuf.p;
+    c->r = nullptr;
+    if (r) {
+        RC(ensure(c->rbuf, bytes));
+        CU(cudaMemcpyAsync(c->rbuf.p, r, bytes, cudaMemcpyHostToDevice, c->st));
+        c->r = (const cplx *)c->rbuf.p;
+    }
+    return 0;
+}
+
+static int ensure_tree(fnftb_ctx *c, size_t B, size_t npad, size_t deg0, size_t deg_out)
+{
+    RC(ensure(c->lev0, tree_lev_elems(B, npad, deg0) * sizeof(cplx)));
+    RC(ensure(c->lev1, tree_lev_elems(B, npad, deg0) * sizeof(cplx)));
+    RC(ensure(c->mx0, B * npad * sizeof(double)));
+    RC(ensure(c->mx1, B * npad * sizeof(double)));
+    RC(ensure(c->gbuf, tree_gbuf_elems(B, npad, deg0) * sizeof(cplx)));
+    RC(ensure(c->W, B * sizeof(int)));
+    RC(ensure(c->status, B * sizeof(int)));
+    RC(ensure(c->tm, B * 4 * (deg_out + 1) * sizeof(cplx)));
+    return 0;
+}
+
+static TreeWork tree_work(fnftb_ctx *c)
+{
+    TreeWork w;
+    w.lev[0] = (cplx *)c->lev0.p;
+    w.lev[1] = (cplx *)c->lev1.p;
+    w.mx[0] = (double *)c->mx0.p;
+    w.mx[1] = (double *)c->mx1.p;
+    w.gbuf = (cplx *)c->gbuf.p;
+    w.W = (int *)c->W.p;
+    w.status = (int *)c->status.p;
+    return w;
+}
+
+int fnftb_fscatter(fnftb_ctx *c, const fnftb_scatter_desc *d)
+{
+    if (!c || !d || !c->q)
+        return fail(-2, "invalid argument / no signals staged", __FILE__, __LINE__);
+    if (d->rmode == FNFTB_RMODE_EXPLICIT && !c->r)
+        return fail(-2, "explicit r requested but not staged", __FILE__, __LINE__);
+    if (d->deg0 < 1 || d->deg0 > 2)
+        return fail(-5, "discretization not implemented on the GPU path", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t npad = next_pow2_sz(c->D);
+    const size_t deg_out = (size_t)d->deg0 * c->D;
+    if ((size_t)d->deg0 * npad > ((size_t)1 << 22))
+        return fail(-6, "signal too long for this build", __FILE__, __LINE__);
+    RC(ensure_tree(c, c->B, npad, (size_t)d->deg0, deg_out));
+    TwTable T;
+    T.tw = c->tw;
+    T.twn = c->twn;
+    RC(tree_fscatter(tree_work(c), c->q, c->r, (int)c->B, (int)c->D, d->deg0, d->rmode, d->kappa,
+                     d->scheme, d->eps_t, d->normalize, (cplx *)c->tm.p, T, c->st));
+    c->deg = deg_out;
+    c->tmB = c->B;
+    c->tm_entries = 4;
+    return 0;
+}
+
+int fnftb_fmult2x2(fnftb_ctx *c, size_t deg, size_t n, const void *p_host, int normalize)
+{
+    if (!c || !p_host || n == 0 || deg == 0)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t npad = next_pow2_sz(n);
+    if (deg * npad > ((size_t)1 << 22))
+        return fail(-6, "product too long for this build", __FILE__, __LINE__);
+    RC(ensure_tree(c, 1, npad, deg, deg * n));
+    const size_t bytes = 4 * n * (deg + 1) * sizeof(cplx);
+    RC(ensure(c->pbuf, bytes));
+    CU(cudaMemcpyAsync(c->pbuf.p, p_host, bytes, cudaMemcpyHostToDevice, c->st));
+    TwTable T;
+    T.tw = c->tw;
+    T.twn = c->twn;
+    RC(tree_fmult2x2(tree_work(c), (const cplx *)c->pbuf.p, (int)n, (int)deg, normalize,
+                     (cplx *)c->tm.p, T, c->st));
+    c->deg = deg * n;
+    c->tmB = 1;
+    c->tm_entries = 4;
+    return 0;
+}
+
+size_t fnftb_result_degree(const fnftb_ctx *c) { return c ? c->deg : 0; }
+
+int fnftb_get_transfer_matrix(fnftb_ctx *c, void *tm_host, int32_t *W_host)
+{
+    if (!c || c->tmB == 0)
+        return fail(-2, "no result held", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    if (tm_host)
+        CU(cudaMemcpyAsync(tm_host, c->tm.p, c->tmB * c->tm_entries * (c->deg + 1) * sizeof(cplx),
+                           cudaMemcpyDeviceToHost, c->st));
+    if (W_host)
+        CU(cudaMemcpyAsync(W_host, c->W.p, c->tmB * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int fnftb_get_status(fnftb_ctx *c, int32_t *status_host)
+{
+    if (!c || !status_host || c->tmB == 0)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(status_host, c->status.p, c->tmB * sizeof(int), cudaMemcpyDeviceToHost,
+                       c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int fnftb_set_polynomial(fnftb_ctx *c, size_t deg, const void *p_host)
+{
+    if (!c || !p_host)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure(c->tm, (deg + 1) * sizeof(cplx)));
+    RC(ensure(c->W, sizeof(int)));
+    RC(ensure(c->status, sizeof(int)));
+    CU(cudaMemcpyAsync(c->tm.p, p_host, (deg + 1) * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemsetAsync(c->W.p, 0, sizeof(int), c->st));
+    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->st));
+    c->deg = deg;
+    c->tmB = 1;
+    c->tm_entries = 1;
+    return 0;
+}
+
+int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t out_sstride,
+                   int on_device, int32_t *status_host)
+{
+    if (!c || !d || !out || c->tmB == 0 || d->M == 0 || d->npoly < 1 || d->npoly > 2)
+        return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
+    for (int j = 0; j < d->npoly; ++j)
+        if (d->ent[j] < 0 || (size_t)d->ent[j] >= c->tm_entries)
+            return fail(-2, "entry index out of range", __FILE__, __LINE__);
+    if (c->deg + d->M > ((size_t)1 << 24))
+        return fail(-6, "chirp-z too long for this build", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->tmB;
+    const CzGeom g = cz_geometry((int)c->deg, (int)d->M);
+    RC(ensure(c->ybuf, cz_ybuf_elems(g, B, d->npoly) * sizeof(cplx)));
+    RC(ensure(c->vhat, (size_t)g.L * sizeof(cplx)));
+    cplx *dst = (cplx *)out;
+    if (!on_device) {
+        RC(ensure(c->outbuf, B * out_sstride * sizeof(cplx)));
+        dst = (cplx *)c->outbuf.p;
+    }
+    CzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tm = (const cplx *)c->tm.p;
+    a.tm_sstride = c->tm_entries * (c->deg + 1);
+    a.ent[0] = d->ent[0];
+    a.ent[1] = d->ent[1];
+    a.npoly = d->npoly;
+    a.deg = (int)c->deg;
+    a.B = (int)B;
+    a.M = (int)d->M;
+    a.lwr = d->lwr;
+    a.lwi = d->lwi;
+    a.lar = d->lar;
+    a.lai = d->lai;
+    a.ybuf = (cplx *)c->ybuf.p;
+    a.vhat = (cplx *)c->vhat.p;
+    a.T.tw = c->tw;
+    a.T.twn = c->twn;
+    a.mode = d->mode;
+    a.cstype = d->cstype;
+    a.out = dst;
+    a.out_sstride = out_sstride;
+    a.W = (const int *)c->W.p;
+    a.xi0 = d->xi0;
+    a.eps_xi = d->eps_xi;
+    a.ph_rho = d->ph_rho;
+    a.ph_a = d->ph_a;
+    a.ph_b = d->ph_b;
+    a.kdv_ph = d->kdv_ph;
+    a.kdv_sqrtz = d->kdv_sqrtz;
+    a.status = (int *)c->status.p;
+    RC(cz_run(a, c->st));
+    if (!on_device) {
+        CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    }
+    if (status_host)
+        CU(cudaMemcpyAsync(status_host, c->status.p, B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    if (!on_device || status_host)
+        CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------
+// 4SPLIT4 preprocessing
+// ---------------------------------------------------------------------------
+int fnftb_resample_4split4(fnftb_ctx *c, double eps_t, int32_t *warn_host)
+{
+    if (!c || !c->q)
+        return fail(-2, "no signals staged", __FILE__, __LINE__);
+    const size_t D = c->D;
+    if ((D & (D - 1)) != 0 || D < 4 || D > 4096)
+        return fail(-6, "GPU resampling needs a power-of-two number of samples between 4 and 4096",
+                    __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure(c->qpre, c->B * 2 * D * sizeof(cplx)));
+    RC(ensure(c->warn, c->B * sizeof(int)));
+    ResampleArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.q = c->q;
+    ra.out = (cplx *)c->qpre.p;
+    ra.warn = (int *)c->warn.p;
+    ra.B = (int)c->B;
+    ra.D = (int)D;
+    ra.eps_t = eps_t;
+    ra.plan = make_fft_plan((int)D);
+    ra.T.tw = c->tw;
+    ra.T.twn = c->twn;
+    const int nt = 256;
+    RC((launch_blocks<ResampleArgs, blk_resample_4split4>(ra, (unsigned)c->B, nt,
+                                                          resample_smem_bytes((int)D, nt), c->st)));
+    c->q = (const cplx *)c->qpre.p;
+    c->r = nullptr;
+    c->D = 2 * D;
+    if (warn_host) {
+        CU(cudaMemcpyAsync(warn_host, c->warn.p, c->B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// bound states
+// ---------------------------------------------------------------------------
+static BoundArgs bound_args(fnftb_ctx *c, const fnftb_bound_desc *d)
+{
+    BoundArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = c->q;
+    a.B = (int)c->B;
+    a.D = (int)c->D;
+    a.upsampling = d->upsampling;
+    a.Kmax = d->Kmax;
+    a.K = (const int *)c->kcnt.p;
+    a.lam = (cplx *)c->lam.p;
+    a.T0 = d->T0;
+    a.T1 = d->T1;
+    a.eps_t = d->eps_t;
+    a.bc = d->bc;
+    a.lweight = d->lweight;
+    a.scl = d->scl;
+    a.niter = d->niter;
+    a.box0 = d->box0;
+    a.box1 = d->box1;
+    a.box2 = d->box2;
+    a.box3 = (d->use_box3 && c->have_box3) ? (const double *)c->box3.p : nullptr;
+    a.flag = (int *)c->flag.p;
+    a.a_out = (cplx *)c->aout.p;
+    a.ap_out = (cplx *)c->apout.p;
+    a.b_out = (cplx *)c->bout.p;
+    a.phi = (cplx *)c->phi.p;
+    return a;
+}
+
+int fnftb_imbound(fnftb_ctx *c, int upsampling, double T0, double T1, double *box3_host)
+{
+    if (!c || !c->q)
+        return fail(-2, "no signals staged", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure(c->box3, c->B * sizeof(double)));
+    NormArgs na;
+    na.q = c->q;
+    na.B = (int)c->B;
+    na.D = (int)c->D;
+    na.upsampling = upsampling;
+    na.T0 = T0;
+    na.T1 = T1;
+    na.out = (double *)c->box3.p;
+    RC((launch_blocks<NormArgs, blk_imbound>(na, (unsigned)c->B, 256, 256 * sizeof(double), c->st)));
+    c->have_box3 = 1;
+    if (box3_host) {
+        CU(cudaMemcpyAsync(box3_host, c->box3.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    return 0;
+}
+
+static int stage_eigs(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_host, const void *lam_host)
+{
+    const size_t n = c->B * (size_t)d->Kmax;
+    RC(ensure(c->lam, n * sizeof(cplx)));
+    RC(ensure(c->kcnt, c->B * sizeof(int)));
+    RC(ensure(c->flag, n * sizeof(int)));
+    CU(cudaMemcpyAsync(c->lam.p, lam_host, n * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->kcnt.p, K_host, c->B * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemsetAsync(c->flag.p, 0, n * sizeof(int), c->st));
+    return 0;
+}
+
+int fnftb_newton(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_host, void *lam_host,
+                 int32_t *flag_host)
+{
+    if (!c || !d || !c->q || !K_host || !lam_host || d->Kmax < 1)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(stage_eigs(c, d, K_host, lam_host));
+    const size_t n = c->B * (size_t)d->Kmax;
+    BoundArgs a = bound_args(c, d);
+    RC((launch_blocks<BoundArgs, blk_newton, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st)));
+    CU(cudaMemcpyAsync(lam_host, c->lam.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    if (flag_host)
+        CU(cudaMemcpyAsync(flag_host, c->flag.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int fnftb_normconsts(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_host,
+                     const void *lam_host, void *a_host, void *ap_host, void *b_host)
+{
+    if (!c || !d || !c->q || !K_host || !lam_host || d->Kmax < 1)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(stage_eigs(c, d, K_host, lam_host));
+    const size_t n = c->B * (size_t)d->Kmax;
+    RC(ensure(c->aout, n * sizeof(cplx)));
+    RC(ensure(c->apout, n * sizeof(cplx)));
+    RC(ensure(c->bout, n * sizeof(cplx)));
+    const size_t Dg = c->D / (size_t)d->upsampling;
+    RC(ensure(c->phi, (Dg + 1) * n * 2 * sizeof(cplx)));
+    CU(cudaMemsetAsync(c->aout.p, 0, n * sizeof(cplx), c->st));
+    CU(cudaMemsetAsync(c->apout.p, 0, n * sizeof(cplx), c->st));
+    CU(cudaMemsetAsync(c->bout.p, 0, n * sizeof(cplx), c->st));
+    BoundArgs a = bound_args(c, d);
+    RC((launch_blocks<BoundArgs, blk_normconsts, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st)));
+    if (a_host)
+        CU(cudaMemcpyAsync(a_host, c->aout.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    if (ap_host)
+        CU(cudaMemcpyAsync(ap_host, c->apout.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    if (b_host)
+        CU(cudaMemcpyAsync(b_host, c->bout.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+}  // extern "C"

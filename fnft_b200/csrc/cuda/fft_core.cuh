@@ -239,6 +239,20 @@ HD int plan_first_stride_log2(const FftPlan &P)
     return (P.npass == 0) ? 0 : P.log2n - ilog2i(P.radix[0]);
 }
 
+// frequency index of the element stored at position pos after a forward transform
+HD int plan_freq_of_pos(const FftPlan &P, int pos)
+{
+    int rem = pos, k = 0, mult = 1, l2 = P.log2n;
+    for (int p = 0; p < P.npass; ++p) {
+        l2 -= ilog2i(P.radix[p]);
+        const int j = rem >> l2;
+        rem &= (1 << l2) - 1;
+        k += j * mult;
+        mult *= P.radix[p];
+    }
+    return k;
+}
+
 // In-place forward transforms of `nfft` arrays of length P.n (shared memory).
 // Must be called by all threads of the block program (contains BLOCK_SYNCs).
 #define FNFTB_SMEM_FFT_FWD(S, nfft, P, nt, T)                                         \

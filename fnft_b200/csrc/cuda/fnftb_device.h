@@ -1,0 +1,132 @@
+/*
+ * fnft_b200 -- thin C-ABI between the C host library (csrc/host) and the CUDA
+ * kernels (csrc/cuda).  Plain pointers and sizes only; every function returns 0 on
+ * success or a nonzero code whose text is available from fnftb_last_error().
+ *
+ * A context owns one device, one stream and grow-only device workspaces.  The host
+ * code stages a chunk of signals, runs the fast scattering on it (leaves + product
+ * tree, result kept on the device) and then asks for spectra / coefficients.
+ */
+#ifndef FNFTB_DEVICE_H
+#define FNFTB_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fnftb_ctx fnftb_ctx;
+
+/* values of rmode */
+#define FNFTB_RMODE_NSE 0      /* r = -kappa*conj(q) */
+#define FNFTB_RMODE_KDV 1      /* r = -1 */
+#define FNFTB_RMODE_EXPLICIT 2 /* r given */
+
+/* chirp-z epilogue modes */
+#define FNFTB_MODE_RAW 0
+#define FNFTB_MODE_NSEV 1
+#define FNFTB_MODE_KDVV 2
+
+typedef struct {
+    int rmode;      /* FNFTB_RMODE_* */
+    int kappa;      /* +1 / -1 (NSE only) */
+    int scheme;     /* value of fnft__akns_discretization_t */
+    int deg0;       /* polynomial degree of one step */
+    int normalize;  /* 1: power-of-two rescaling with exponent W */
+    double eps_t;   /* step size entering the leaves */
+} fnftb_scatter_desc;
+
+typedef struct {
+    int mode;       /* FNFTB_MODE_* */
+    int cstype;     /* NSEV: 0 rho, 1 a|b, 2 rho|a|b */
+    int npoly;      /* 1 or 2 */
+    int ent[2];     /* which entries (0=11,1=12,2=21,3=22) are evaluated */
+    size_t M;       /* number of output points */
+    double lwr, lwi;   /* ln|W|, arg W of the chirp step */
+    double lar, lai;   /* ln|A|, arg A of the chirp start */
+    double xi0, eps_xi;
+    double ph_rho, ph_a, ph_b;
+    double kdv_ph, kdv_sqrtz;
+} fnftb_contspec_desc;
+
+int fnftb_device_count(void);
+const char *fnftb_last_error(void);
+unsigned long long fnftb_launch_count(void);
+
+int fnftb_ctx_create(fnftb_ctx **out, int device);
+void fnftb_ctx_destroy(fnftb_ctx *ctx);
+int fnftb_ctx_device(const fnftb_ctx *ctx);
+int fnftb_ctx_sync(fnftb_ctx *ctx);
+/* the context's stream as a cudaStream_t cast to void* (for event timing) */
+void *fnftb_ctx_stream(fnftb_ctx *ctx);
+
+/* Largest number of signals one fscatter+contspec pass may hold given the
+ * workspace budget (bytes; 0 = default budget). */
+size_t fnftb_max_chunk(const fnftb_ctx *ctx, size_t D, int deg0, size_t M, int npoly,
+                       size_t budget_bytes);
+
+/* Stage B signals of D samples.  q (and r if rmode is EXPLICIT) are host pointers
+ * (copied) or, if on_device != 0, device pointers that are used in place. */
+int fnftb_set_signals(fnftb_ctx *ctx, size_t B, size_t D, const void *q, const void *r,
+                      int on_device);
+
+/* 4SPLIT4 preprocessing of the staged signals: replaces them by the 2*D resampled and
+ * weighted samples (device resident).  warn_host[B] (may be NULL) gets 1 where the
+ * signal does not look band-limited. */
+int fnftb_resample_4split4(fnftb_ctx *ctx, double eps_t, int32_t *warn_host);
+
+/* leaves + product tree for the staged signals */
+int fnftb_fscatter(fnftb_ctx *ctx, const fnftb_scatter_desc *desc);
+
+/* product of n given 2x2 matrix polynomials of degree deg (host, reference layout
+ * [4][n][deg+1]); leaves the result in the context like fnftb_fscatter (B = 1). */
+int fnftb_fmult2x2(fnftb_ctx *ctx, size_t deg, size_t n, const void *p_host, int normalize);
+
+/* degree of the transfer matrices currently held */
+size_t fnftb_result_degree(const fnftb_ctx *ctx);
+
+/* copy transfer matrices [B][4][deg+1] and exponents W[B] to the host */
+int fnftb_get_transfer_matrix(fnftb_ctx *ctx, void *tm_host, int32_t *W_host);
+
+/* per-signal status of the last fscatter / contspec (0 = ok) */
+int fnftb_get_status(fnftb_ctx *ctx, int32_t *status_host);
+
+/* replace entry-row `ent` of signal 0's transfer matrix by a host polynomial, or
+ * load a standalone polynomial as a 1-signal / 1-entry "matrix" (for chirp-z of
+ * arbitrary polynomials) */
+int fnftb_set_polynomial(fnftb_ctx *ctx, size_t deg, const void *p_host);
+
+/* chirp-z of the selected entries + epilogue.  out: [B][out_sstride] complex
+ * (host, or device if on_device).  status_host (may be NULL): [B] int32. */
+int fnftb_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, void *out,
+                   size_t out_sstride, int on_device, int32_t *status_host);
+
+/* ---- bound states (Newton on the BO / CF4_2 recurrence) ------------------------ */
+typedef struct {
+    int upsampling;   /* 1: BO, 2: CF4_2 */
+    int Kmax;         /* stride of the per-signal eigenvalue arrays */
+    double T0, T1, eps_t, bc;
+    double lweight;   /* 1 (BO) or 0.5 (CF4_2) */
+    double scl;       /* factor of a' */
+    int niter;
+    double box0, box1, box2; /* re_min, re_max, im_min */
+    int use_box3;     /* 1: per-signal im_max computed by fnftb_imbound */
+} fnftb_bound_desc;
+
+/* per-signal 1.5*0.25*||q||^2 of the staged signals (kept on the device; copied to
+ * box3_host [B] if not NULL) */
+int fnftb_imbound(fnftb_ctx *ctx, int upsampling, double T0, double T1, double *box3_host);
+/* Newton refinement of lam_host[B][Kmax] (in/out), K_host[B] guesses per signal;
+ * flag_host[B][Kmax] (may be NULL): 3 = division by zero */
+int fnftb_newton(fnftb_ctx *ctx, const fnftb_bound_desc *desc, const int32_t *K_host,
+                 void *lam_host, int32_t *flag_host);
+/* a, a', b at the given eigenvalues (each output [B][Kmax], may be NULL) */
+int fnftb_normconsts(fnftb_ctx *ctx, const fnftb_bound_desc *desc, const int32_t *K_host,
+                     const void *lam_host, void *a_host, void *ap_host, void *b_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

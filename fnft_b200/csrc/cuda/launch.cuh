@@ -6,7 +6,7 @@
 
 #ifdef FNFTB_EMUL
 typedef void *fnftb_stream_t;
-template <class Args, void (*F)(const Args &, blk3, int, void *)>
+template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256>
 static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t smem_bytes,
                                 fnftb_stream_t /*st*/)
 {
@@ -23,8 +23,8 @@ static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t sme
 }
 #else
 typedef cudaStream_t fnftb_stream_t;
-template <class Args, void (*F)(const Args &, blk3, int, void *)>
-__global__ void fnftb_kernel(const Args a)
+template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT>
+__global__ void __launch_bounds__(MAXT) fnftb_kernel(const Args a)
 {
     extern __shared__ double2 fnftb_smem[];
     F(a, blockIdx, (int)blockDim.x, (void *)fnftb_smem);
@@ -33,20 +33,22 @@ __global__ void fnftb_kernel(const Args a)
 // number of kernel launches issued by this library (reported by bench.py)
 extern unsigned long long g_fnftb_launch_count;
 
-template <class Args, void (*F)(const Args &, blk3, int, void *)>
+template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256>
 static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t smem_bytes,
                                 fnftb_stream_t st)
 {
     if (grid == 0)
         return 0;
+    if (nt > MAXT)
+        return -77;
     if (smem_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fnftb_kernel<Args, F>,
+        cudaError_t e = cudaFuncSetAttribute(fnftb_kernel<Args, F, MAXT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_bytes);
         if (e != cudaSuccess)
             return (int)e;
     }
-    fnftb_kernel<Args, F><<<grid, nt, smem_bytes, st>>>(a);
+    fnftb_kernel<Args, F, MAXT><<<grid, nt, smem_bytes, st>>>(a);
     ++g_fnftb_launch_count;
     return (int)cudaGetLastError();
 }

@@ -1,0 +1,111 @@
+// fnft_b200 -- signal preprocessing for the fourth-order splitting schemes
+// (4SPLIT4A/B, CF4_2): two band-limited shifts of the samples by -/+ sqrt(3)/6 * eps_t
+// and the 2x2 Gauss-node weighting.
+//
+// Replaces fnft__misc_resample           (/root/reference/src/private/fnft__misc.c:326-407)
+// and the 4SPLIT4 branch of
+//   fnft__nse_discretization_preprocess_signal
+//                                          (/root/reference/src/private/fnft__nse_discretization.c:474-503)
+// with weights from fnft__akns_discretization_method_weights
+//                                          (/root/reference/src/private/fnft__akns_discretization.c:284-298).
+// One CTA per signal; the length-D transforms live in shared memory (D a power of
+// two, D <= 4096 in this version).
+#pragma once
+#include "fft_core.cuh"
+
+struct ResampleArgs {
+    const cplx *q;  // [B][D]
+    cplx *out;      // [B][2*D]
+    int *warn;      // [B] 1 if the spectrum does not look band-limited
+    int B, D;
+    double eps_t;
+    FftPlan plan;
+    TwTable T;
+};
+
+HD size_t resample_smem_bytes(int D, int nt) { return sizeof(cplx) * 2 * (size_t)D + sizeof(double) * 3 * nt; }
+
+BLK void blk_resample_4split4(const ResampleArgs &a, blk3 bid, int nt, void *smem)
+{
+    const int D = a.D;
+    cplx *S1 = (cplx *)smem;
+    cplx *S2 = S1 + D;
+    double *red = (double *)(S2 + D);
+    const int s = bid.x;
+    const cplx *q = a.q + (size_t)s * D;
+    FOR_THREADS(tid, nt)
+    {
+        for (int i = tid; i < D; i += nt)
+            S1[swz(i)] = q[i];
+    }
+    BLOCK_SYNC();
+    FNFTB_SMEM_FFT_FWD(S1, 1, a.plan, nt, a.T);
+    // band-limitation check (fnft__misc.c:368-380): trapezoidal |X|^2 sums over the
+    // two 5% bands next to the Nyquist bin versus the whole spectrum
+    const int Dlp = D / 20;
+    FOR_THREADS(tid, nt)
+    {
+        double lo = 0.0, hi = 0.0, all = 0.0;
+        for (int pos = tid; pos < D; pos += nt) {
+            const int k = plan_freq_of_pos(a.plan, pos);
+            const cplx x = S1[swz(pos)];
+            const double m2 = cabs2(x);
+            all += ((k == 0 || k == D - 1) ? 0.5 : 1.0) * m2;
+            if (Dlp >= 2) {
+                const int j1 = k - (D / 2 - 1 - Dlp);
+                if (j1 >= 0 && j1 < Dlp)
+                    lo += ((j1 == 0 || j1 == Dlp - 1) ? 0.5 : 1.0) * m2;
+                const int j2 = k - (D / 2 + 1);
+                if (j2 >= 0 && j2 < Dlp)
+                    hi += ((j2 == 0 || j2 == Dlp - 1) ? 0.5 : 1.0) * m2;
+            }
+        }
+        red[tid] = lo;
+        red[nt + tid] = hi;
+        red[2 * nt + tid] = all;
+    }
+    BLOCK_SYNC();
+    FOR_THREADS(tid, nt)
+    {
+        if (tid == 0) {
+            double lo = 0.0, hi = 0.0, all = 0.0;
+            for (int t = 0; t < nt; ++t) {
+                lo += red[t];
+                hi += red[nt + t];
+                all += red[2 * nt + t];
+            }
+            // every sum carries the same step h = eps_t, which cancels in the ratio
+            const double ratio = sqrt(lo + hi) / sqrt(all);
+            a.warn[s] = (Dlp >= 2 && ratio > 1.4901161193847656e-08 /* sqrt(eps) */) ? 1 : 0;
+        }
+    }
+    // phase shifts: delta = -/+ eps_t*sqrt(3)/6, freq = k/(D*eps_t) (k signed)
+    FOR_THREADS(tid, nt)
+    {
+        const double scl = (double)D * a.eps_t;
+        const double delta = a.eps_t * (1.7320508075688772 / 6.0);
+        for (int pos = tid; pos < D; pos += nt) {
+            const int k = plan_freq_of_pos(a.plan, pos);
+            const double freq = (k < D / 2) ? (double)k / scl : ((double)k - (double)D) / scl;
+            double sn, cs;
+            SINCOS(2.0 * 3.141592653589793 * delta * freq, &sn, &cs);
+            const cplx x = S1[swz(pos)];
+            S1[swz(pos)] = cmul(x, make_cplx(cs, -sn));  // shift by -delta
+            S2[swz(pos)] = cmul(x, make_cplx(cs, sn));   // shift by +delta
+        }
+    }
+    BLOCK_SYNC();
+    FNFTB_SMEM_FFT_INV(S1, 2, a.plan, nt, a.T);
+    FOR_THREADS(tid, nt)
+    {
+        const double sf = 1.7320508075688772 / 6.0;
+        const double w0 = 0.25 + sf, w1 = 0.25 - sf;
+        const double invD = 1.0 / (double)D;
+        cplx *o = a.out + (size_t)s * 2 * D;
+        for (int i = tid; i < D; i += nt) {
+            const cplx q1 = cscale(S1[swz(i)], invD), q2 = cscale(S2[swz(i)], invD);
+            o[2 * i] = make_cplx(w0 * q1.x + w1 * q2.x, w0 * q1.y + w1 * q2.y);
+            o[2 * i + 1] = make_cplx(w1 * q1.x + w0 * q2.x, w1 * q1.y + w0 * q2.y);
+        }
+    }
+}

@@ -79,7 +79,7 @@ static inline int launch_direct(const PairArgs &pa, fnftb_stream_t st)
 {
     const long long total = (long long)pa.B * (pa.n_in / 2) * 4;
     const int nt = 128;
-    return launch_blocks<PairArgs, blk_pair_direct<DIN>>(pa, (unsigned)((total + nt - 1) / nt), nt,
+    return launch_blocks<PairArgs, blk_pair_direct<DIN>, 128>(pa, (unsigned)((total + nt - 1) / nt), nt,
                                                          0, st);
 }
 
@@ -88,7 +88,7 @@ static inline int launch_combine(const PairArgs &pa, fnftb_stream_t st)
 {
     const long long total = (long long)pa.B * (pa.n_in / 2) * 4 * pa.N2;
     const int nt = 128;
-    return launch_blocks<PairArgs, blk_pair_combine<R>>(pa, (unsigned)((total + nt - 1) / nt), nt,
+    return launch_blocks<PairArgs, blk_pair_combine<R>, 128>(pa, (unsigned)((total + nt - 1) / nt), nt,
                                                         0, st);
 }
 
@@ -152,7 +152,7 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                 if (nt < 64)
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)((npairs + G - 1) / G);
-                rc = launch_blocks<PairArgs, blk_pair_fft>(pa, grid, nt, pair_smem_bytes(G, N, nt),
+                rc = launch_blocks<PairArgs, blk_pair_fft, 512>(pa, grid, nt, pair_smem_bytes(G, N, nt),
                                                            st);
             } else {
                 pa.R = N / smem_n;
@@ -165,7 +165,7 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                 if (nt < 64)
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)npairs * (unsigned)pa.R;
-                rc = launch_blocks<PairArgs, blk_pair_fft>(pa, grid, nt,
+                rc = launch_blocks<PairArgs, blk_pair_fft, 512>(pa, grid, nt,
                                                            pair_smem_bytes(1, smem_n, nt), st);
                 if (rc)
                     return rc;

@@ -1,0 +1,286 @@
+/*
+ * fnft_b200 host library -- fnft_nsev and fnft_nsev_batch.
+ *
+ * Host-side mirror of /root/reference/src/fnft_nsev.c: argument checks (:162-220),
+ * step size (:237), option logic, and the sequence
+ *   fscatter -> continuous spectrum -> bound states -> norming constants
+ * of fnft_nsev_base (:458-565).  All numerical work is done by CUDA kernels reached
+ * through fnftb_device.h; the single-signal entry point is the B = 1 case of the
+ * batched one.
+ */
+#include "fnft_internal.h"
+#include "fnft_nsev_discrete.h"
+
+static const fnft_nsev_opts_t nsev_defaults = {
+    .bound_state_filtering = fnft_nsev_bsfilt_FULL,
+    .bound_state_localization = fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE,
+    .niter = 10,
+    .Dsub = 0,
+    .discspec_type = fnft_nsev_dstype_NORMING_CONSTANTS,
+    .contspec_type = fnft_nsev_cstype_REFLECTION_COEFFICIENT,
+    .normalization_flag = 1,
+    .discretization = fnft_nse_discretization_2SPLIT4B,
+    .richardson_extrapolation_flag = 0};
+
+/* src/fnft_nsev.c:42-45 */
+fnft_nsev_opts_t fnft_nsev_default_opts(void) { return nsev_defaults; }
+
+/* src/fnft_nsev.c:51-57 */
+FNFT_UINT fnft_nsev_max_K(const FNFT_UINT D, fnft_nsev_opts_t const *const opts)
+{
+    const fnft_nse_discretization_t d = opts ? opts->discretization : nsev_defaults.discretization;
+    return fnftb__nse_degree(d) * D;
+}
+
+static FNFT_UINT contspec_len(fnft_nsev_cstype_t t, FNFT_UINT M)
+{
+    switch (t) {
+    case fnft_nsev_cstype_REFLECTION_COEFFICIENT: return M;
+    case fnft_nsev_cstype_AB: return 2 * M;
+    case fnft_nsev_cstype_BOTH: return 3 * M;
+    default: return 0;
+    }
+}
+
+/*
+ * Continuous spectrum of the signals currently staged + scattered in ctx.
+ * Mirrors nsev_compute_contspec (src/fnft_nsev.c:744-891) for the polynomial
+ * (fast) discretizations: chirp constants :822-827, epilogue :846-876.
+ */
+static FNFT_INT nsev_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL const *T,
+                                    FNFT_UINT M, FNFT_REAL const *XI, fnft_nsev_opts_t const *opts,
+                                    FNFT_COMPLEX *out, int on_device, int32_t *status)
+{
+    const fnft_nse_discretization_t disc = opts->discretization;
+    const FNFT_REAL step_div = (FNFT_REAL)(fnftb__nse_degree(disc) * fnftb__nse_upsampling(disc));
+    const FNFT_REAL eps_t = (T[1] - T[0]) / (D_given - 1);
+    const FNFT_REAL eps_xi = (XI[1] - XI[0]) / (M - 1);
+    fnftb_contspec_desc cd;
+    memset(&cd, 0, sizeof(cd));
+    cd.mode = FNFTB_MODE_NSEV;
+    cd.cstype = (int)opts->contspec_type;
+    cd.npoly = 2;
+    cd.ent[0] = 0; /* H11 = a-polynomial */
+    cd.ent[1] = 2; /* H21 = b-polynomial */
+    cd.M = M;
+    /* z = exp(2i*lambda*eps_t/(deg*up)): V from eps_xi, A from -XI[0]; formed as
+     * rounded complex doubles exactly like the reference, then taken apart */
+    const FNFT_COMPLEX V = cexp(2 * I * eps_xi * eps_t / step_div);
+    const FNFT_COMPLEX A = cexp(2 * I * (-XI[0]) * eps_t / step_div);
+    fnftb__logpolar(V, &cd.lwr, &cd.lwi);
+    fnftb__logpolar(A, &cd.lar, &cd.lai);
+    cd.xi0 = XI[0];
+    cd.eps_xi = eps_xi;
+    FNFT_INT ret_code;
+    ret_code = fnftb__nse_phase_factor_rho(eps_t, T[1], &cd.ph_rho, disc);
+    if (ret_code != FNFT_SUCCESS)
+        return E_SUBROUTINE(ret_code);
+    ret_code = fnftb__nse_phase_factor_a(eps_t, D_given, T, &cd.ph_a, disc);
+    if (ret_code != FNFT_SUCCESS)
+        return E_SUBROUTINE(ret_code);
+    ret_code = fnftb__nse_phase_factor_b(eps_t, D_given, T, &cd.ph_b, disc);
+    if (ret_code != FNFT_SUCCESS)
+        return E_SUBROUTINE(ret_code);
+    if (fnftb_contspec(ctx, &cd, out, contspec_len(opts->contspec_type, M), on_device, status) != 0)
+        return E_DEVICE;
+    return FNFT_SUCCESS;
+}
+
+FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
+                         FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                         FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
+                         FNFT_COMPLEX *const bound_states,
+                         FNFT_COMPLEX *const normconsts_or_residues, const FNFT_INT kappa,
+                         fnft_nsev_opts_t const *opts, FNFT_INT *const ret_codes)
+{
+    FNFT_INT ret_code = FNFT_SUCCESS;
+    int32_t *status = NULL;
+
+    /* argument checks of src/fnft_nsev.c:162-180 */
+    if (B == 0)
+        return E_INVALID_ARGUMENT(B);
+    if (D < 2)
+        return E_INVALID_ARGUMENT(D);
+    if (q == NULL)
+        return E_INVALID_ARGUMENT(q);
+    if (T == NULL || T[0] >= T[1])
+        return E_INVALID_ARGUMENT(T);
+    if (contspec != NULL) {
+        if (XI == NULL || XI[0] >= XI[1])
+            return E_INVALID_ARGUMENT(XI);
+    }
+    if (abs(kappa) != 1)
+        return E_INVALID_ARGUMENT(kappa);
+    if (bound_states != NULL) {
+        if (K == NULL)
+            return E_INVALID_ARGUMENT(K_ptr);
+    }
+    if (opts == NULL)
+        opts = &nsev_defaults;
+    if (contspec != NULL && M > 0 && contspec_len(opts->contspec_type, M) == 0)
+        return E_INVALID_ARGUMENT(opts->contspec_type);
+
+    const fnft_nse_discretization_t disc = opts->discretization;
+    fnft__akns_discretization_t akns;
+    ret_code = fnftb__nse_to_akns(disc, &akns);
+    if (ret_code != FNFT_SUCCESS)
+        return E_INVALID_ARGUMENT(opts->discretization);
+    const FNFT_UINT deg0 = fnftb__akns_degree(akns);
+    const FNFT_UINT upsampling = fnftb__akns_upsampling(akns);
+    if (deg0 == 0)
+        return E_NOT_YET_IMPLEMENTED(opts->discretization,
+                                     Only the fast (polynomial) discretizations run on the GPU.);
+    if (!fnftb__akns_on_gpu(akns))
+        return E_NOT_YET_IMPLEMENTED(opts->discretization,
+                                     This splitting scheme has no GPU leaf kernel yet.);
+    if (opts->richardson_extrapolation_flag)
+        return E_NOT_YET_IMPLEMENTED(opts->richardson_extrapolation_flag,
+                                     Richardson extrapolation is not available in the GPU build.);
+    if (upsampling > 2)
+        return E_NOT_YET_IMPLEMENTED(opts->discretization, Unsupported upsampling factor.);
+    if (upsampling == 2 && (D & (D - 1)) != 0)
+        return E_NOT_YET_IMPLEMENTED(D, The GPU resampling step of the 4SPLIT4 schemes needs a power-of-two number of samples.);
+    const int want_contspec = (contspec != NULL && M > 0);
+    const int want_discspec = (kappa == +1 && bound_states != NULL);
+    if (want_discspec && opts->bound_state_localization != fnft_nsev_bsloc_NEWTON)
+        return E_NOT_YET_IMPLEMENTED(opts->bound_state_localization,
+                                     The GPU build localizes bound states with fnft_nsev_bsloc_NEWTON only.);
+    if (want_discspec && Kmax == 0)
+        return E_INVALID_ARGUMENT(Kmax);
+
+    fnftb_ctx *ctx = fnftb__ctx();
+    if (ctx == NULL)
+        return E_OTHER("No usable CUDA device: the fnft_b200 hot path has no CPU fallback.");
+    const int devptr = fnftb__device_pointers();
+
+    const FNFT_REAL eps_t = (T[1] - T[0]) / (D - 1); /* src/fnft_nsev.c:237 */
+    const FNFT_UINT D_eff = D * upsampling;
+    const FNFT_UINT cs_len = want_contspec ? contspec_len(opts->contspec_type, M) : 0;
+
+    size_t chunk = fnftb_max_chunk(ctx, D_eff, (int)deg0, want_contspec ? M : 0, 2,
+                                   fnftb__workspace_limit());
+    if (chunk > B)
+        chunk = B;
+    if (!devptr) {
+        status = malloc(chunk * sizeof(int32_t));
+        if (status == NULL)
+            return E_NOMEM;
+    }
+    if (ret_codes != NULL)
+        for (FNFT_UINT b = 0; b < B; b++)
+            ret_codes[b] = FNFT_SUCCESS;
+
+    fnftb_scatter_desc sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.rmode = FNFTB_RMODE_NSE;
+    sd.kappa = kappa;
+    sd.scheme = (int)akns;
+    sd.deg0 = (int)deg0;
+    sd.normalize = opts->normalization_flag ? 1 : 0;
+    sd.eps_t = eps_t;
+
+    for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
+        const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
+
+        /* preprocessing (src/fnft_nsev.c:272): plain copy for upsampling 1; the
+         * 4SPLIT4 schemes resample on the device */
+        if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, devptr) != 0) {
+            ret_code = E_DEVICE;
+            goto leave_fun;
+        }
+        if (upsampling == 2) {
+            int32_t *warn = devptr ? NULL : malloc(nb * sizeof(int32_t));
+            if (fnftb_resample_4split4(ctx, eps_t, warn) != 0) {
+                free(warn);
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+            if (warn != NULL) {
+                for (FNFT_UINT b = 0; b < nb; b++) {
+                    if (warn[b]) { /* src/private/fnft__misc.c:379-380 */
+                        WARN("Signal does not appear to be bandlimited. Interpolation step may be inaccurate. Try to reduce the step size, or switch to a discretization that does not require interpolation");
+                        break;
+                    }
+                }
+                free(warn);
+            }
+        }
+
+        /* transfer matrix: nse_fscatter (src/fnft_nsev.c:527).  The Newton path never
+         * reads it, so it is only built when a continuous spectrum is wanted. */
+        if (want_contspec) {
+            if (fnftb_fscatter(ctx, &sd) != 0) {
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+        }
+
+        if (want_contspec) {
+            ret_code = nsev_contspec_chunk(ctx, D, T, M, XI, opts, contspec + b0 * cs_len, devptr,
+                                           devptr ? NULL : status);
+            CHECK_RETCODE(ret_code, leave_fun);
+            if (!devptr) {
+                for (FNFT_UINT b = 0; b < nb; b++) {
+                    if (status[b] == FNFT_EC_DIV_BY_ZERO) {
+                        const FNFT_INT ec = E_DIV_BY_ZERO; /* src/fnft_nsev.c:850-852 */
+                        if (ret_codes != NULL)
+                            ret_codes[b0 + b] = ec;
+                        if (ret_code == FNFT_SUCCESS)
+                            ret_code = ec;
+                    }
+                }
+                if (ret_code != FNFT_SUCCESS && ret_codes == NULL)
+                    goto leave_fun;
+            }
+        }
+
+        if (want_discspec) {
+            FNFT_INT rc2 = fnftb__nsev_discrete_chunk(ctx, nb, D_eff, D, T, eps_t, K + b0, Kmax,
+                                                      bound_states + b0 * Kmax,
+                                                      normconsts_or_residues == NULL
+                                                          ? NULL
+                                                          : normconsts_or_residues +
+                                                                b0 * Kmax *
+                                                                    (opts->discspec_type == fnft_nsev_dstype_BOTH ? 2 : 1),
+                                                      opts, ret_codes ? ret_codes + b0 : NULL);
+            if (rc2 != FNFT_SUCCESS && ret_code == FNFT_SUCCESS)
+                ret_code = rc2;
+            if (rc2 != FNFT_SUCCESS && ret_codes == NULL)
+                goto leave_fun;
+        } else if (K != NULL && !devptr) {
+            for (FNFT_UINT b = 0; b < nb; b++)
+                K[b0 + b] = 0; /* src/fnft_nsev.c:558-560 */
+        }
+    }
+
+leave_fun:
+    free(status);
+    return ret_code;
+}
+
+/* include/fnft_nsev.h:371-376, src/fnft_nsev.c:133-453 */
+FNFT_INT fnft_nsev(const FNFT_UINT D, FNFT_COMPLEX *const q, FNFT_REAL const *const T,
+                   const FNFT_UINT M, FNFT_COMPLEX *const contspec, FNFT_REAL const *const XI,
+                   FNFT_UINT *const K_ptr, FNFT_COMPLEX *const bound_states,
+                   FNFT_COMPLEX *const normconsts_or_residues, const FNFT_INT kappa,
+                   fnft_nsev_opts_t *opts)
+{
+    /* K_ptr doubles as "size of the user arrays" (in) and "number found" (out) */
+    if (bound_states != NULL && K_ptr == NULL)
+        return E_INVALID_ARGUMENT(K_ptr);
+    const FNFT_UINT Kmax = (bound_states != NULL && K_ptr != NULL) ? *K_ptr : 0;
+    if (bound_states != NULL && kappa == +1 && Kmax == 0) {
+        /* nothing to refine and nowhere to store: mirror K = 0 result */
+        FNFT_INT rc = fnft_nsev_batch(1, D, q, T, M, contspec, XI, NULL, 0, NULL, NULL, kappa, opts,
+                                      NULL);
+        return rc;
+    }
+    const int devptr = fnftb__device_pointers();
+    if (devptr)
+        fnft_b200_set_device_pointers(0); /* the classic entry point takes host memory */
+    const FNFT_INT rc = fnft_nsev_batch(1, D, q, T, M, contspec, XI, K_ptr, Kmax, bound_states,
+                                        normconsts_or_residues, kappa, opts, NULL);
+    if (devptr)
+        fnft_b200_set_device_pointers(1);
+    return rc;
+}

@@ -1,0 +1,108 @@
+/*
+ * fnft_b200 host library -- per-thread GPU context and runtime controls.
+ * Each calling thread owns one device context (one device, one stream, grow-only
+ * workspaces); contexts are created lazily on first use.
+ */
+#include "fnft_internal.h"
+#include <stdio.h>
+
+static __thread fnftb_ctx *tl_ctx = NULL;
+static __thread int tl_device = -1; /* -1: take FNFT_B200_DEVICE or 0 on first use */
+static __thread int tl_devptr = 0;
+static __thread size_t tl_limit = 0;
+
+fnftb_ctx *fnftb__ctx(void)
+{
+    if (tl_ctx != NULL)
+        return tl_ctx;
+    int dev = tl_device;
+    if (dev < 0) {
+        const char *env = getenv("FNFT_B200_DEVICE");
+        dev = (env != NULL && env[0] != '\0') ? atoi(env) : 0;
+    }
+    if (tl_limit == 0) {
+        const char *env = getenv("FNFT_B200_WORKSPACE_MB");
+        if (env != NULL && env[0] != '\0')
+            tl_limit = (size_t)strtoull(env, NULL, 10) << 20;
+    }
+    if (fnftb_ctx_create(&tl_ctx, dev) != 0) {
+        tl_ctx = NULL;
+        (void)E_DEVICE;
+        return NULL;
+    }
+    tl_device = dev;
+    return tl_ctx;
+}
+
+int fnftb__device_pointers(void) { return tl_devptr; }
+size_t fnftb__workspace_limit(void) { return tl_limit; }
+
+FNFT_INT fnft_b200_device_count(void) { return (FNFT_INT)fnftb_device_count(); }
+
+FNFT_INT fnft_b200_set_device(FNFT_INT device)
+{
+    if (device < 0 || device >= fnftb_device_count())
+        return E_INVALID_ARGUMENT(device);
+    if (tl_ctx != NULL && fnftb_ctx_device(tl_ctx) != device) {
+        fnftb_ctx_destroy(tl_ctx);
+        tl_ctx = NULL;
+    }
+    tl_device = device;
+    return FNFT_SUCCESS;
+}
+
+FNFT_INT fnft_b200_set_device_pointers(FNFT_INT flag)
+{
+    tl_devptr = (flag != 0);
+    return FNFT_SUCCESS;
+}
+
+FNFT_INT fnft_b200_synchronize(void)
+{
+    if (tl_ctx == NULL)
+        return FNFT_SUCCESS;
+    if (fnftb_ctx_sync(tl_ctx) != 0)
+        return E_DEVICE;
+    return FNFT_SUCCESS;
+}
+
+FNFT_INT fnft_b200_set_workspace_limit(FNFT_UINT bytes)
+{
+    tl_limit = bytes;
+    return FNFT_SUCCESS;
+}
+
+void *fnft_b200_stream(void)
+{
+    fnftb_ctx *c = fnftb__ctx();
+    return c ? fnftb_ctx_stream(c) : NULL;
+}
+
+unsigned long long fnft_b200_launch_count(void) { return fnftb_launch_count(); }
+
+void fnft_b200_release(void)
+{
+    if (tl_ctx != NULL)
+        fnftb_ctx_destroy(tl_ctx);
+    tl_ctx = NULL;
+}
+
+/*
+ * ln|z| and arg z.  The chirp-z kernels evaluate W^(n^2/2) as
+ * exp((n^2/2)*ln|W|) * cis((n^2/2)*arg W) with n^2/2 up to ~1e11, so ln|z| must
+ * resolve |z|-1 far below double precision: x^2+y^2-1 is accumulated exactly with
+ * fused multiply-adds before log1p.  (The reference gets the same information from
+ * glibc's clog inside cpow, src/private/fnft__poly_chirpz.c:69-95.)
+ */
+void fnftb__logpolar(FNFT_COMPLEX z, double *ln_abs, double *arg)
+{
+    const double x = creal(z), y = cimag(z);
+    const double px = x * x, ex = fma(x, x, -px);
+    const double py = y * y, ey = fma(y, y, -py);
+    const long double m2m1 = (((long double)px - 1.0L) + (long double)py) + ((long double)ex + (long double)ey);
+    if (fabsl(m2m1) < 0.5L)
+        *ln_abs = (double)(0.5L * log1pl(m2m1));
+    else
+        *ln_abs = (double)(0.5L * logl((long double)px + (long double)py));
+    *arg = (double)atan2l((long double)y, (long double)x);
+}

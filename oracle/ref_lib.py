@@ -36,7 +36,7 @@ class NsevOpts(C.Structure):
         ("contspec_type", C.c_int),
         ("normalization_flag", C.c_int32),
         ("discretization", C.c_int),
-        ("richardson_extrapolation_flag", C.c_int32),
+        ("richardson_extrapolation_flag", C.c_size_t),
     ]
 
 

@@ -5,6 +5,7 @@
 // kernels be checked in the GPU-less container; it is never part of the product.
 #define FNFTB_EMUL 1
 #include "../../fnft_b200/csrc/cuda/tree_driver.cuh"
+#include "../../fnft_b200/csrc/cuda/chirpz_driver.cuh"
 #include "../../fnft_b200/csrc/cuda/twiddle.h"
 #include <vector>
 
@@ -107,6 +108,49 @@ int emul_fmult2x2(const double *p, int n, int deg0, int normalize, double *tm, i
                            use_direct, smem_n);
     W[0] = wk.W[0];
     return rc;
+}
+
+
+// chirp-z of npoly polynomials per signal; see CzArgs for the meaning of the fields
+int emul_chirpz(const double *tm, long tm_sstride, int ent0, int ent1, int npoly, int deg, int B,
+                int M, double lwr, double lwi, double lar, double lai, int mode, int cstype,
+                double *out, long out_sstride, const int *W, double xi0, double eps_xi,
+                double ph_rho, double ph_a, double ph_b, double kdv_ph, double kdv_sqrtz,
+                int *status, int row_n)
+{
+    CzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tm = (const cplx *)tm;
+    a.tm_sstride = (size_t)tm_sstride;
+    a.ent[0] = ent0;
+    a.ent[1] = ent1;
+    a.npoly = npoly;
+    a.deg = deg;
+    a.B = B;
+    a.M = M;
+    a.lwr = lwr;
+    a.lwi = lwi;
+    a.lar = lar;
+    a.lai = lai;
+    a.mode = mode;
+    a.cstype = cstype;
+    a.out = (cplx *)out;
+    a.out_sstride = (size_t)out_sstride;
+    a.W = W;
+    a.xi0 = xi0;
+    a.eps_xi = eps_xi;
+    a.ph_rho = ph_rho;
+    a.ph_a = ph_a;
+    a.ph_b = ph_b;
+    a.kdv_ph = kdv_ph;
+    a.kdv_sqrtz = kdv_sqrtz;
+    a.status = status;
+    a.T = get_tw();
+    const CzGeom g = cz_geometry(deg, M, row_n);
+    std::vector<cplx> ybuf(cz_ybuf_elems(g, (size_t)B, npoly)), vhat((size_t)g.L);
+    a.ybuf = ybuf.data();
+    a.vhat = vhat.data();
+    return cz_run(a, NULL, row_n);
 }
 
 }  // extern "C"
