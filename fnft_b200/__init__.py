@@ -87,6 +87,7 @@ EXPORTED_SYMBOLS = [
     "fnft_b200_device_count", "fnft_b200_set_device", "fnft_b200_set_device_pointers",
     "fnft_b200_synchronize", "fnft_b200_set_workspace_limit", "fnft_b200_stream",
     "fnft_b200_launch_count", "fnft_b200_release",
+    "fnft_b200_profile_enable", "fnft_b200_profile_report",
 ]
 
 _lib = None
@@ -150,6 +151,8 @@ def lib():
     L.fnft_b200_set_workspace_limit.argtypes = [sz]
     L.fnft_b200_stream.restype = vp
     L.fnft_b200_launch_count.restype = C.c_ulonglong
+    L.fnft_b200_profile_enable.argtypes = [i32]
+    L.fnft_b200_profile_report.restype = C.c_char_p
     _lib = L
     return L
 

@@ -43,6 +43,7 @@ struct CzArgs {
     int cstype;      // NSEV: 0 reflection coefficient, 1 a and b, 2 both
     cplx *out;
     size_t out_sstride;
+    size_t out_jstride;  // RAW mode: distance between the outputs of poly 0 and 1 (0 => M)
     const int *W;    // per-signal normalisation exponent (NSEV a/b), may be NULL
     double xi0, eps_xi;
     double ph_rho, ph_a, ph_b;  // NSEV boundary phase factors
@@ -202,8 +203,9 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
                 H[j] = cmul(S[((size_t)j * C + c) * N1 + swz(n1)], ch);
             cplx *o = a.out + (size_t)s * a.out_sstride;
             if (a.mode == FNFTB_CZ_RAW) {
+                const size_t js = a.out_jstride ? a.out_jstride : (size_t)a.M;
                 for (int j = 0; j < a.npoly; ++j)
-                    o[(size_t)j * a.M + m] = H[j];
+                    o[(size_t)j * js + m] = H[j];
             } else if (a.mode == FNFTB_CZ_NSEV) {
                 // src/fnft_nsev.c:846-876; H[0] = H11 (a-poly), H[1] = H21 (b-poly)
                 const double xi = a.xi0 + a.eps_xi * dm;

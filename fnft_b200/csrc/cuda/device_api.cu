@@ -4,6 +4,7 @@
 
 #include "bound_kernels.cuh"
 #include "chirpz_driver.cuh"
+#include "nsep_kernels.cuh"
 #include "resample_kernels.cuh"
 #include "tree_driver.cuh"
 #include "twiddle.h"
@@ -12,6 +13,39 @@
 #include <vector>
 
 unsigned long long g_fnftb_launch_count = 0;
+int g_fnftb_profile_on = 0;
+
+// ---------------------------------------------------------------------------
+// optional per-launch timing (used by bench.py for the roofline numbers)
+// ---------------------------------------------------------------------------
+#include <map>
+struct ProfRec {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void fnftb_profile_begin(const char *name, cudaStream_t st)
+{
+    ProfRec r;
+    r.name = name;
+    r.e0 = prof_event();
+    r.e1 = prof_event();
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+}
+void fnftb_profile_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 
 static thread_local std::string g_err;
 
@@ -62,6 +96,8 @@ struct fnftb_ctx {
     Buf ybuf, vhat, outbuf, pbuf;
     // bound-state workspace
     Buf box3, lam, kcnt, flag, aout, apout, bout, phi;
+    // nsep workspace
+    Buf fpoly, vals, roots, nraw, nkept;
     int have_box3 = 0;
 };
 
@@ -106,6 +142,35 @@ const char *fnftb_last_error(void) { return g_err.c_str(); }
 
 unsigned long long fnftb_launch_count(void) { return g_fnftb_launch_count; }
 
+void fnftb_profile_enable(int on) { g_fnftb_profile_on = on; }
+
+// Sums the recorded launches per kernel name into a text report
+// "name count total_ms\n..." (buffer owned by the library) and clears the records.
+const char *fnftb_profile_report(void)
+{
+    static std::string rep;
+    std::map<std::string, std::pair<long, double>> acc;
+    cudaDeviceSynchronize();
+    for (ProfRec &r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            auto &a = acc[r.name];
+            a.first += 1;
+            a.second += ms;
+        }
+        g_prof_pool.push_back(r.e0);
+        g_prof_pool.push_back(r.e1);
+    }
+    g_prof.clear();
+    rep.clear();
+    char line[256];
+    for (auto &kv : acc) {
+        snprintf(line, sizeof(line), "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        rep += line;
+    }
+    return rep.c_str();
+}
+
 int fnftb_ctx_create(fnftb_ctx **out, int device)
 {
     if (!out)
@@ -140,7 +205,8 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
     cudaStreamSynchronize(c->st);
     Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->W,
                   &c->status, &c->tm, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf,
-                  &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi};
+                  &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
+                  &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept};
     for (Buf *b : all)
         release(*b);
     if (c->tw)
@@ -403,6 +469,215 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
 
 
 // ---------------------------------------------------------------------------
+// periodic NFT: grid search
+// ---------------------------------------------------------------------------
+int fnftb_nsep_derotate(fnftb_ctx *c, double lam_shift, double T0, double eps_t)
+{
+    if (!c || !c->q)
+        return fail(-2, "no signals staged", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure(c->qpre, c->B * c->D * sizeof(cplx)));
+    DerotArgs da;
+    da.q = c->q;
+    da.out = (cplx *)c->qpre.p;
+    da.B = (int)c->B;
+    da.D = (int)c->D;
+    da.lam_shift = lam_shift;
+    da.T0 = T0;
+    da.eps_t = eps_t;
+    const long long tot = (long long)c->B * c->D;
+    RC((launch_blocks<DerotArgs, blk_nsep_derotate>(da, (unsigned)((tot + 255) / 256), 256, 0, c->st,
+                                                     "nsep_derotate")));
+    c->q = (const cplx *)c->qpre.p;
+    return 0;
+}
+
+// ln|z| and arg z of a rounded complex double, resolving |z|-1 exactly (same
+// construction as fnftb__logpolar in the host library)
+static void logpolar_ld(double x, double y, double *ln_abs, double *arg)
+{
+    const double px = x * x, ex = fma(x, x, -px);
+    const double py = y * y, ey = fma(y, y, -py);
+    const long double m2m1 = (((long double)px - 1.0L) + (long double)py) + ((long double)ex + (long double)ey);
+    if (fabsl(m2m1) < 0.5L)
+        *ln_abs = (double)(0.5L * log1pl(m2m1));
+    else
+        *ln_abs = (double)(0.5L * logl((long double)px + (long double)py));
+    *arg = (double)atan2l((long double)y, (long double)x);
+}
+
+// bytes of device workspace the grid search needs per signal
+static size_t nsep_bytes_per_signal(size_t deg, size_t Mpts)
+{
+    const CzGeom g = cz_geometry((int)deg, (int)Mpts);
+    return (2 * (size_t)g.L + 2 * 3 * Mpts + 2 * (deg + 1) + 3 * (deg + 1)) * sizeof(cplx);
+}
+
+size_t fnftb_nsep_chunk(const fnftb_ctx *c, size_t D_eff, int deg0, size_t budget_bytes)
+{
+    if (budget_bytes == 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(c->device);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+            free_b = (size_t)8 << 30;
+        budget_bytes = free_b / 2;
+        const size_t cap = (size_t)16 << 30;
+        if (budget_bytes > cap)
+            budget_bytes = cap;
+    }
+    const size_t deg = (size_t)deg0 * D_eff;
+    const size_t per = nsep_bytes_per_signal(deg, 32 * deg) + per_signal_bytes(D_eff, deg0, 0, 0);
+    size_t n = budget_bytes / per;
+    return n < 1 ? 1 : n;
+}
+
+// Requires fnftb_fscatter to have run on the staged signals.  For every signal:
+// roots of p+ and p- (main spectrum, concatenated, at most Kmax) and of tm12
+// (auxiliary spectrum, at most Mmax), mapped to lambda, filtered, in scan order.
+// status_host[b]: 0 ok, 1 = more roots than the polynomial degree (src/fnft_nsep.c:329-332),
+// bit 4 set = main spectrum truncated, bit 5 set = auxiliary spectrum truncated.
+int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_host, void *main_host,
+                          uint64_t *M_host, void *aux_host, int32_t *status_host)
+{
+    if (!c || !d || c->tmB == 0 || c->tm_entries != 4)
+        return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->tmB, deg = c->deg, d1 = deg + 1;
+    if (deg < 2)
+        return fail(-2, "degree too small", __FILE__, __LINE__);
+    const size_t Mpts = 32 * deg;  // oversampling_factor, src/fnft_nsep.c:43
+    if (deg + Mpts > ((size_t)1 << 24))
+        return fail(-6, "grid search too long for this build", __FILE__, __LINE__);
+    const CzGeom g = cz_geometry((int)deg, (int)Mpts);
+    const int want_main = (main_host != nullptr), want_aux = (aux_host != nullptr);
+    RC(ensure(c->fpoly, B * 2 * d1 * sizeof(cplx)));
+    RC(ensure(c->ybuf, B * 2 * (size_t)g.L * sizeof(cplx)));
+    RC(ensure(c->vhat, (size_t)g.L * sizeof(cplx)));
+    RC(ensure(c->vals, B * 2 * 3 * Mpts * sizeof(cplx)));
+    const size_t cap = deg;  // more than deg roots is an error anyway
+    RC(ensure(c->roots, B * 2 * cap * sizeof(cplx)));
+    RC(ensure(c->nraw, B * 2 * sizeof(int)));
+    RC(ensure(c->nkept, B * 2 * sizeof(int)));
+    std::vector<int> nraw(B * 2), nkept(B * 2);
+    std::vector<cplx> roots;
+    for (size_t b = 0; b < B; ++b)
+        status_host[b] = 0;
+
+    const double eps = (d->PHI1 - d->PHI0) / (double)(Mpts - 1);
+    for (int pass = 0; pass < 2; ++pass) {  // 0: main (p+, p-), 1: aux (tm12)
+        if ((pass == 0 && !want_main) || (pass == 1 && !want_aux))
+            continue;
+        const int npoly = (pass == 0) ? 2 : 1;
+        if (pass == 0) {
+            FloquetArgs fa;
+            fa.tm = (const cplx *)c->tm.p;
+            fa.W = (const int *)c->W.p;
+            fa.P = (cplx *)c->fpoly.p;
+            fa.B = (int)B;
+            fa.deg = (int)deg;
+            const long long tot = (long long)B * d1;
+            RC((launch_blocks<FloquetArgs, blk_nsep_polys>(fa, (unsigned)((tot + 255) / 256), 256, 0,
+                                                          c->st, "nsep_polys")));
+        }
+        for (int k = -1; k <= 1; ++k) {  // three rings, fftgridsearch.c:70-77
+            CzArgs a;
+            memset(&a, 0, sizeof(a));
+            if (pass == 0) {
+                a.tm = (const cplx *)c->fpoly.p;
+                a.tm_sstride = 2 * d1;
+                a.ent[0] = 0;
+                a.ent[1] = 1;
+            } else {
+                a.tm = (const cplx *)c->tm.p;
+                a.tm_sstride = 4 * d1;
+                a.ent[0] = 1;  // tm12
+            }
+            a.npoly = npoly;
+            a.deg = (int)deg;
+            a.B = (int)B;
+            a.M = (int)Mpts;
+            // W = CEXP(I*eps), A = (1 + k*eps)*CEXP(-I*PHI0) formed as rounded complex
+            // doubles like the reference (fftgridsearch.c:68-73), then taken apart
+            logpolar_ld(cos(eps), sin(eps), &a.lwr, &a.lwi);
+            {
+                const double rad = 1.0 + k * eps;
+                logpolar_ld(rad * cos(-d->PHI0), rad * sin(-d->PHI0), &a.lar, &a.lai);
+            }
+            a.ybuf = (cplx *)c->ybuf.p;
+            a.vhat = (cplx *)c->vhat.p;
+            a.T.tw = c->tw;
+            a.T.twn = c->twn;
+            a.mode = FNFTB_CZ_RAW;
+            a.out = (cplx *)c->vals.p + (size_t)(k + 1) * Mpts;
+            a.out_sstride = (size_t)npoly * 3 * Mpts;
+            a.out_jstride = 3 * Mpts;
+            a.status = (int *)c->status.p;
+            RC(cz_run(a, c->st));
+        }
+        ScanArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.vals = (const cplx *)c->vals.p;
+        sa.B = (int)B;
+        sa.npoly = npoly;
+        sa.M = (int)Mpts;
+        sa.PHI0 = d->PHI0;
+        sa.eps = eps;
+        sa.lam_den = d->lam_den;
+        sa.filtering = d->filtering;
+        for (int i = 0; i < 4; ++i)
+            sa.box[i] = d->box[i];
+        sa.lam_shift = d->lam_shift;
+        sa.cap = (int)cap;
+        sa.out = (cplx *)c->roots.p;
+        sa.n_raw = (int *)c->nraw.p;
+        sa.n_kept = (int *)c->nkept.p;
+        const int nt = 256;
+        RC((launch_blocks<ScanArgs, blk_nsep_scan>(sa, (unsigned)(B * npoly), nt, 2 * nt * sizeof(int),
+                                                   c->st, "nsep_scan")));
+        CU(cudaMemcpyAsync(nraw.data(), c->nraw.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(nkept.data(), c->nkept.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        roots.resize(B * npoly * cap);
+        CU(cudaMemcpyAsync(roots.data(), c->roots.p, B * npoly * cap * sizeof(cplx),
+                           cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        for (size_t b = 0; b < B; ++b) {
+            if (pass == 0) {
+                cplx *dst = (cplx *)main_host + b * d->Kmax;
+                size_t K = 0;
+                for (int j = 0; j < 2; ++j) {
+                    if ((size_t)nraw[b * 2 + j] > deg) {
+                        status_host[b] = 1;
+                        break;
+                    }
+                    size_t n = (size_t)nkept[b * 2 + j];
+                    if (n > cap)
+                        n = cap;
+                    if (K + n > d->Kmax) {
+                        status_host[b] |= 16;
+                        n = (K < d->Kmax) ? d->Kmax - K : 0;
+                    }
+                    memcpy(dst + K, roots.data() + (b * 2 + j) * cap, n * sizeof(cplx));
+                    K += n;
+                }
+                K_host[b] = (status_host[b] == 1) ? 0 : K;
+            } else {
+                cplx *dst = (cplx *)aux_host + b * d->Mmax;
+                size_t n = (size_t)nkept[b];
+                if (n > cap)
+                    n = cap;
+                if (n > d->Mmax) {
+                    status_host[b] |= 32;
+                    n = d->Mmax;
+                }
+                memcpy(dst, roots.data() + b * cap, n * sizeof(cplx));
+                M_host[b] = n;
+            }
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // 4SPLIT4 preprocessing
 // ---------------------------------------------------------------------------
 int fnftb_resample_4split4(fnftb_ctx *c, double eps_t, int32_t *warn_host)
@@ -429,7 +704,7 @@ int fnftb_resample_4split4(fnftb_ctx *c, double eps_t, int32_t *warn_host)
     ra.T.twn = c->twn;
     const int nt = 256;
     RC((launch_blocks<ResampleArgs, blk_resample_4split4>(ra, (unsigned)c->B, nt,
-                                                          resample_smem_bytes((int)D, nt), c->st)));
+                                                          resample_smem_bytes((int)D, nt), c->st, "resample_4split4")));
     c->q = (const cplx *)c->qpre.p;
     c->r = nullptr;
     c->D = 2 * D;
@@ -487,7 +762,7 @@ int fnftb_imbound(fnftb_ctx *c, int upsampling, double T0, double T1, double *bo
     na.T0 = T0;
     na.T1 = T1;
     na.out = (double *)c->box3.p;
-    RC((launch_blocks<NormArgs, blk_imbound>(na, (unsigned)c->B, 256, 256 * sizeof(double), c->st)));
+    RC((launch_blocks<NormArgs, blk_imbound>(na, (unsigned)c->B, 256, 256 * sizeof(double), c->st, "bound_imbound")));
     c->have_box3 = 1;
     if (box3_host) {
         CU(cudaMemcpyAsync(box3_host, c->box3.p, c->B * sizeof(double), cudaMemcpyDeviceToHost, c->st));
@@ -517,7 +792,7 @@ int fnftb_newton(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_host,
     RC(stage_eigs(c, d, K_host, lam_host));
     const size_t n = c->B * (size_t)d->Kmax;
     BoundArgs a = bound_args(c, d);
-    RC((launch_blocks<BoundArgs, blk_newton, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st)));
+    RC((launch_blocks<BoundArgs, blk_newton, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st, "bound_newton")));
     CU(cudaMemcpyAsync(lam_host, c->lam.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     if (flag_host)
         CU(cudaMemcpyAsync(flag_host, c->flag.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -542,7 +817,7 @@ int fnftb_normconsts(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_h
     CU(cudaMemsetAsync(c->apout.p, 0, n * sizeof(cplx), c->st));
     CU(cudaMemsetAsync(c->bout.p, 0, n * sizeof(cplx), c->st));
     BoundArgs a = bound_args(c, d);
-    RC((launch_blocks<BoundArgs, blk_normconsts, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st)));
+    RC((launch_blocks<BoundArgs, blk_normconsts, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st, "bound_normconsts")));
     if (a_host)
         CU(cudaMemcpyAsync(a_host, c->aout.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     if (ap_host)

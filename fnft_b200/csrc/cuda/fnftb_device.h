@@ -54,6 +54,9 @@ typedef struct {
 int fnftb_device_count(void);
 const char *fnftb_last_error(void);
 unsigned long long fnftb_launch_count(void);
+/* per-launch CUDA-event timing: enable, run, then read "name count total_ms" lines */
+void fnftb_profile_enable(int on);
+const char *fnftb_profile_report(void);
 
 int fnftb_ctx_create(fnftb_ctx **out, int device);
 void fnftb_ctx_destroy(fnftb_ctx *ctx);
@@ -102,6 +105,22 @@ int fnftb_set_polynomial(fnftb_ctx *ctx, size_t deg, const void *p_host);
  * (host, or device if on_device).  status_host (may be NULL): [B] int32. */
 int fnftb_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, void *out,
                    size_t out_sstride, int on_device, int32_t *status_host);
+
+/* ---- periodic NFT (grid search) --------------------------------------------------- */
+typedef struct {
+    double PHI0, PHI1;   /* angular range of the search on the unit circle */
+    double lam_den;      /* lambda = log(z)/(i*lam_den), lam_den = 2*eps_t/(deg1*upsampling) */
+    int filtering;       /* 0: none, 1: keep only values inside box */
+    double box[4];
+    double lam_shift;    /* added to every returned value */
+    size_t Kmax, Mmax;   /* capacities of the per-signal output rows */
+} fnftb_nsep_desc;
+
+/* q[i] *= exp(2i*lam_shift*(T0 + eps_t*i)) on the staged signals (src/fnft_nsep.c:127-128) */
+int fnftb_nsep_derotate(fnftb_ctx *ctx, double lam_shift, double T0, double eps_t);
+size_t fnftb_nsep_chunk(const fnftb_ctx *ctx, size_t D_eff, int deg0, size_t budget_bytes);
+int fnftb_nsep_gridsearch(fnftb_ctx *ctx, const fnftb_nsep_desc *desc, uint64_t *K_host,
+                          void *main_host, uint64_t *M_host, void *aux_host, int32_t *status_host);
 
 /* ---- bound states (Newton on the BO / CF4_2 recurrence) ------------------------ */
 typedef struct {

@@ -8,7 +8,7 @@
 typedef void *fnftb_stream_t;
 template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256>
 static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t smem_bytes,
-                                fnftb_stream_t /*st*/)
+                                fnftb_stream_t /*st*/, const char * /*name*/ = "")
 {
     void *smem = smem_bytes ? malloc(smem_bytes) : NULL;
     for (unsigned b = 0; b < grid; ++b) {
@@ -32,10 +32,14 @@ __global__ void __launch_bounds__(MAXT) fnftb_kernel(const Args a)
 
 // number of kernel launches issued by this library (reported by bench.py)
 extern unsigned long long g_fnftb_launch_count;
+// optional per-launch timing with CUDA events (device_api.cu); name is a literal
+void fnftb_profile_begin(const char *name, cudaStream_t st);
+void fnftb_profile_end(cudaStream_t st);
+extern int g_fnftb_profile_on;
 
 template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256>
 static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t smem_bytes,
-                                fnftb_stream_t st)
+                                fnftb_stream_t st, const char *name = "")
 {
     if (grid == 0)
         return 0;
@@ -48,7 +52,11 @@ static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t sme
         if (e != cudaSuccess)
             return (int)e;
     }
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin(name, st);
     fnftb_kernel<Args, F, MAXT><<<grid, nt, smem_bytes, st>>>(a);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(st);
     ++g_fnftb_launch_count;
     return (int)cudaGetLastError();
 }

@@ -80,7 +80,7 @@ static inline int launch_direct(const PairArgs &pa, fnftb_stream_t st)
     const long long total = (long long)pa.B * (pa.n_in / 2) * 4;
     const int nt = 128;
     return launch_blocks<PairArgs, blk_pair_direct<DIN>, 128>(pa, (unsigned)((total + nt - 1) / nt), nt,
-                                                         0, st);
+                                                         0, st, "tree_pair_direct");
 }
 
 template <int R>
@@ -89,7 +89,7 @@ static inline int launch_combine(const PairArgs &pa, fnftb_stream_t st)
     const long long total = (long long)pa.B * (pa.n_in / 2) * 4 * pa.N2;
     const int nt = 128;
     return launch_blocks<PairArgs, blk_pair_combine<R>, 128>(pa, (unsigned)((total + nt - 1) / nt), nt,
-                                                        0, st);
+                                                        0, st, "tree_pair_combine");
 }
 
 // Runs all levels.  On entry level buffer 0 holds npad matrices of degree deg0
@@ -153,7 +153,7 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)((npairs + G - 1) / G);
                 rc = launch_blocks<PairArgs, blk_pair_fft, 512>(pa, grid, nt, pair_smem_bytes(G, N, nt),
-                                                           st);
+                                                           st, "tree_pair_fft");
             } else {
                 pa.R = N / smem_n;
                 pa.N2 = smem_n;
@@ -166,7 +166,8 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)npairs * (unsigned)pa.R;
                 rc = launch_blocks<PairArgs, blk_pair_fft, 512>(pa, grid, nt,
-                                                           pair_smem_bytes(1, smem_n, nt), st);
+                                                           pair_smem_bytes(1, smem_n, nt), st,
+                                                           "tree_pair_fft_rows");
                 if (rc)
                     return rc;
                 dev_memset0(pa.mx_out, sizeof(double) * (size_t)B * npairs, st);
@@ -204,7 +205,8 @@ static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, i
     fa.deg_out = deg_out;
     fa.normalize = normalize;
     const long long tot = (long long)B * 4 * (deg_out + 1);
-    return launch_blocks<FinalArgs, blk_tree_final>(fa, (unsigned)((tot + 255) / 256), 256, 0, st);
+    return launch_blocks<FinalArgs, blk_tree_final>(fa, (unsigned)((tot + 255) / 256), 256, 0, st,
+                                                    "tree_final");
 }
 
 // Full fast scattering for a batch: leaves -> tree -> [B][4][deg_out+1] + W[B].
@@ -232,7 +234,8 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
     la.eps_t = eps_t;
     la.status = w.status;
     const long long total = (long long)B * npad;
-    int rc = launch_blocks<LeafArgs, blk_leaf>(la, (unsigned)((total + 127) / 128), 128, 0, st);
+    int rc = launch_blocks<LeafArgs, blk_leaf>(la, (unsigned)((total + 127) / 128), 128, 0, st,
+                                               "tree_leaf");
     if (rc)
         return rc;
     int cur = 0;
@@ -257,7 +260,8 @@ static inline int tree_fmult2x2(const TreeWork &w, const cplx *p_dev, int n, int
     ia.npad = npad;
     ia.deg0 = deg0;
     const long long total = (long long)npad * 4 * (deg0 + 1);
-    int rc = launch_blocks<ImportArgs, blk_import>(ia, (unsigned)((total + 127) / 128), 128, 0, st);
+    int rc = launch_blocks<ImportArgs, blk_import>(ia, (unsigned)((total + 127) / 128), 128, 0, st,
+                                                   "tree_import");
     if (rc)
         return rc;
     int cur = 0;

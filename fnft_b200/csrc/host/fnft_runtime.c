@@ -80,6 +80,10 @@ void *fnft_b200_stream(void)
 
 unsigned long long fnft_b200_launch_count(void) { return fnftb_launch_count(); }
 
+void fnft_b200_profile_enable(FNFT_INT on) { fnftb_profile_enable(on); }
+
+const char *fnft_b200_profile_report(void) { return fnftb_profile_report(); }
+
 void fnft_b200_release(void)
 {
     if (tl_ctx != NULL)

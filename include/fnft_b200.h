@@ -337,6 +337,11 @@ FNFT_INT fnft_b200_set_workspace_limit(FNFT_UINT bytes);
 void *fnft_b200_stream(void);
 /* Kernels launched by this process so far. */
 unsigned long long fnft_b200_launch_count(void);
+/* Per-launch CUDA-event timing of the library's kernels (for benchmarking): enable,
+ * run, then read a text report with one "kernel_name launches total_ms" line per
+ * kernel; reading clears the records. */
+void fnft_b200_profile_enable(FNFT_INT on);
+const char *fnft_b200_profile_report(void);
 /* Releases the calling thread's GPU context. */
 void fnft_b200_release(void);
 

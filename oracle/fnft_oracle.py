@@ -1,0 +1,481 @@
+"""ORACLE -- numpy restatement of the reference's fast forward NFT hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product (fnft_b200/, include/) imports,
+calls, links or executes this module; only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline leg may, and only as the checker.
+
+Parity status: PINNED.  tests/test_oracle.py checks every function below against
+  * the golden vectors of the reference's own unit tests (fmult2x2, chirp-z,
+    akns_fscatter per scheme), lifted into tests/golden/golden.npz by
+    tests/golden/make_golden.py, and
+  * outputs of the unmodified reference library (oracle/_ref, built by
+    oracle/Makefile from /root/reference) on seeded inputs, stored in the same file.
+
+Each function cites the reference code it follows (paths relative to the FNFT tree).
+The algorithms are restated, not translated line by line: loops over pairs /
+frequencies / eigenvalues are numpy-vectorised, the FFT is numpy's (at the same
+transform lengths the reference uses, kiss_fft_next_fast_size).
+"""
+import numpy as np
+
+EPS = np.finfo(np.float64).eps
+
+# values of fnft__akns_discretization_t (include/private/fnft__akns_discretization_t.h:43-72)
+AKNS_2SPLIT2_MODAL, AKNS_2SPLIT1A, AKNS_2SPLIT1B, AKNS_2SPLIT2A, AKNS_2SPLIT2B, AKNS_2SPLIT2S = range(6)
+AKNS_2SPLIT4B = 10
+AKNS_4SPLIT4B = 21
+# values of fnft_nse_discretization_t (include/fnft_nse_discretization_t.h:104-133)
+NSE_2SPLIT2_MODAL, NSE_BO, NSE_2SPLIT1A, NSE_2SPLIT1B, NSE_2SPLIT2A, NSE_2SPLIT2B, NSE_2SPLIT2S = range(7)
+NSE_2SPLIT4B = 11
+NSE_4SPLIT4B = 21
+NSE_CF4_2 = 22
+# fnft_kdv_discretization_t (include/fnft_kdv_discretization_t.h:96-122)
+KDV_2SPLIT1A, KDV_2SPLIT1B, KDV_2SPLIT2A, KDV_2SPLIT2B, KDV_2SPLIT2S = range(5)
+KDV_2SPLIT4B = 9
+KDV_4SPLIT4B = 19
+
+_NSE2AKNS = {NSE_2SPLIT2_MODAL: AKNS_2SPLIT2_MODAL, NSE_2SPLIT1A: AKNS_2SPLIT1A,
+             NSE_2SPLIT1B: AKNS_2SPLIT1B, NSE_2SPLIT2A: AKNS_2SPLIT2A, NSE_2SPLIT2B: AKNS_2SPLIT2B,
+             NSE_2SPLIT2S: AKNS_2SPLIT2S, NSE_2SPLIT4B: AKNS_2SPLIT4B, NSE_4SPLIT4B: AKNS_4SPLIT4B}
+_KDV2AKNS = {KDV_2SPLIT1A: AKNS_2SPLIT1A, KDV_2SPLIT1B: AKNS_2SPLIT1B, KDV_2SPLIT2A: AKNS_2SPLIT2A,
+             KDV_2SPLIT2B: AKNS_2SPLIT2B, KDV_2SPLIT2S: AKNS_2SPLIT2S, KDV_2SPLIT4B: AKNS_2SPLIT4B,
+             KDV_4SPLIT4B: AKNS_4SPLIT4B}
+
+
+def akns_degree(scheme):
+    """src/private/fnft__akns_discretization.c:29-67 (schemes restated here)."""
+    return 2 if scheme in (AKNS_2SPLIT4B, AKNS_4SPLIT4B) else 1
+
+
+def akns_upsampling(scheme):
+    """src/private/fnft__akns_discretization.c:114-154."""
+    return 2 if scheme == AKNS_4SPLIT4B else 1
+
+
+def next_fast_size(n):
+    """kiss_fft_next_fast_size, src/3rd_party/kiss_fft/kiss_fft.c:396-408."""
+    while True:
+        m = n
+        for f in (2, 3, 5):
+            while m % f == 0:
+                m //= f
+        if m <= 1:
+            return n
+        n += 1
+
+
+def nextpow2(n):
+    """misc_nextpowerof2, src/private/fnft__misc.c:316-324."""
+    r = 1
+    while r < n:
+        r *= 2
+    return r
+
+
+def csinc(x):
+    """misc_CSINC, src/private/fnft__misc.c:306-314."""
+    x = np.asarray(x, dtype=np.complex128)
+    small = np.abs(x) < 1.0e-8
+    safe = np.where(small, 1.0, x)
+    return np.where(small, np.cos(x / np.sqrt(3.0 + 0j)), np.sin(safe) / safe)
+
+
+def zero_freq_expm(h, q, r):
+    """akns_fscatter_zero_freq_scatter_matrix, src/private/fnft__akns_fscatter.c:46-59.
+    Returns (M0, M1, M2) = (cos D, q*h*sinc D, r*h*sinc D)."""
+    Delta = h * np.sqrt(-q * r + 0j)
+    dl = h * csinc(Delta)
+    return np.cos(Delta), q * dl, r * dl
+
+
+def akns_leaves(q, r, eps_t, scheme):
+    """Per-sample 2x2 polynomial matrices, src/private/fnft__akns_fscatter.c:116-433.
+    Returns p[4, D, deg+1]; matrix k belongs to sample D-1-k (:408), coefficients
+    highest power first."""
+    q = np.asarray(q, dtype=np.complex128)[::-1]
+    r = np.asarray(r, dtype=np.complex128)[::-1]
+    D = q.shape[0]
+    deg = akns_degree(scheme)
+    p = np.zeros((4, D, deg + 1), dtype=np.complex128)
+    if scheme == AKNS_2SPLIT2_MODAL:  # :118-147
+        scl = 1.0 / np.sqrt(1 - eps_t * q * eps_t * r + 0j)
+        p[0, :, 1] = scl
+        p[1, :, 0] = scl * eps_t * q
+        p[2, :, 1] = scl * eps_t * r
+        p[3, :, 0] = scl
+    elif scheme == AKNS_2SPLIT1A:  # :149-176
+        e0, e1, e2 = zero_freq_expm(eps_t / deg, q, r)
+        p[0, :, 1] = e0
+        p[1, :, 1] = e1
+        p[2, :, 0] = e2
+        p[3, :, 0] = e0
+    elif scheme in (AKNS_2SPLIT1B, AKNS_2SPLIT2A):  # :178-203
+        e0, e1, e2 = zero_freq_expm(eps_t / deg, q, r)
+        p[0, :, 1] = e0
+        p[1, :, 0] = e1
+        p[2, :, 1] = e2
+        p[3, :, 0] = e0
+    elif scheme == AKNS_2SPLIT2B:  # :204-230
+        e0, e1, e2 = zero_freq_expm(0.5 * eps_t / deg, q, r)
+        p[0, :, 0] = e1 * e2
+        p[0, :, 1] = e0 * e0
+        p[1, :, 0] = p[1, :, 1] = e0 * e1
+        p[2, :, 0] = p[2, :, 1] = e0 * e2
+        p[3, :, 0] = p[0, :, 1]
+        p[3, :, 1] = p[0, :, 0]
+    elif scheme == AKNS_2SPLIT2S:  # :232-258
+        e0, e1, e2 = zero_freq_expm(eps_t / deg, q, r)
+        p[0, :, 1] = e0
+        p[1, :, 0] = p[1, :, 1] = e1 / 2
+        p[2, :, 0] = p[2, :, 1] = e2 / 2
+        p[3, :, 0] = e0
+    elif scheme in (AKNS_2SPLIT4B, AKNS_4SPLIT4B):  # :402-433
+        a0, a1, a2 = zero_freq_expm(0.5 * eps_t / deg, q, r)
+        b0, b1, b2 = zero_freq_expm(eps_t / deg, q, r)
+        p[0, :, 0] = (4 * b0 * a1 * a2 - b1 * b2) / 3
+        p[0, :, 1] = 4 * (b1 * a0 * a2 + b2 * a0 * a1) / 3
+        p[0, :, 2] = (4 * b0 * a0 * a0 - b0 * b0) / 3
+        p[1, :, 0] = (4 * b0 * a0 * a1 - b0 * b1) / 3
+        p[1, :, 1] = 4 * (b1 * a0 * a0 + b2 * a1 * a1) / 3
+        p[1, :, 2] = p[1, :, 0]
+        p[2, :, 0] = (4 * b0 * a0 * a2 - b0 * b2) / 3
+        p[2, :, 1] = 4 * (b2 * a0 * a0 + b1 * a2 * a2) / 3
+        p[2, :, 2] = p[2, :, 0]
+        p[3, :, 0] = p[0, :, 2]
+        p[3, :, 1] = p[0, :, 1]
+        p[3, :, 2] = p[0, :, 0]
+    else:
+        raise ValueError("scheme not restated in the oracle")
+    return p
+
+
+def poly_fmult2x2(p, normalize=True):
+    """fnft__poly_fmult2x2, src/private/fnft__poly_fmult.c:381-546.
+    p: [4, n, deg+1].  Returns (result[4, deg_out+1], deg_out, W).
+    Level loop :460-519; pair product by FFT at length next_fast_size(2*deg+1)
+    (:45-48, 239-328); per-pair rescale by 2^-floor(log2(max|c|)) (:330-374)."""
+    p = np.array(p, dtype=np.complex128)
+    _, n, d1 = p.shape
+    deg0 = d1 - 1
+    npad = nextpow2(n)
+    if npad > n:  # pad with z^deg * I, :404-445
+        pad = np.zeros((4, npad - n, d1), dtype=np.complex128)
+        pad[0, :, 0] = 1.0
+        pad[3, :, 0] = 1.0
+        p = np.concatenate([p, pad], axis=1)
+    W = 0
+    deg = deg0
+    while p.shape[1] >= 2:
+        L = next_fast_size(2 * deg + 1)
+        F = np.fft.fft(p, n=L, axis=2)               # zero-padded forward transforms
+        A, Bm = F[:, 0::2, :], F[:, 1::2, :]          # left / right factor of each pair
+        C = np.empty((4,) + A.shape[1:], dtype=np.complex128)
+        C[0] = A[0] * Bm[0] + A[1] * Bm[2]
+        C[1] = A[0] * Bm[1] + A[1] * Bm[3]
+        C[2] = A[2] * Bm[0] + A[3] * Bm[2]
+        C[3] = A[2] * Bm[1] + A[3] * Bm[3]
+        c = np.fft.ifft(C, axis=2)[:, :, :2 * deg + 1]
+        if normalize:
+            mx = np.abs(c).max(axis=(0, 2))
+            a = np.where(mx > 0, np.floor(np.log2(np.where(mx > 0, mx, 1.0))), 0.0)
+            c = c * (2.0 ** (-a))[None, :, None]
+            W += int(a.sum())
+        p = c
+        deg *= 2
+    res = p[:, 0, :]
+    deg_out = deg0 * n
+    return res[:, :deg_out + 1].copy(), deg_out, W
+
+
+def akns_fscatter(q, r, eps_t, scheme, normalize=True):
+    """fnft__akns_fscatter, src/private/fnft__akns_fscatter.c:64-925."""
+    return poly_fmult2x2(akns_leaves(q, r, eps_t, scheme), normalize)
+
+
+def nse_fscatter(q, eps_t, kappa, nse_disc, normalize=True):
+    """fnft__nse_fscatter, src/private/fnft__nse_fscatter.c:44-91 (r = -kappa*conj(q))."""
+    q = np.asarray(q, dtype=np.complex128)
+    return akns_fscatter(q, -kappa * np.conj(q), eps_t, _NSE2AKNS[nse_disc], normalize)
+
+
+def kdv_fscatter(u, eps_t, kdv_disc, normalize=True):
+    """fnft__kdv_fscatter, src/private/fnft__kdv_fscatter.c:45-83 (r = -1)."""
+    u = np.asarray(u, dtype=np.complex128)
+    return akns_fscatter(u, -np.ones_like(u), eps_t, _KDV2AKNS[kdv_disc], normalize)
+
+
+def poly_chirpz(p, A, W, M):
+    """fnft__poly_chirpz, src/private/fnft__poly_chirpz.c:33-105: evaluates p (highest
+    power first) at z_m = 1/(A*W^-m), m < M, by Bluestein with three FFTs."""
+    p = np.asarray(p, dtype=np.complex128)
+    deg = p.shape[0] - 1
+    N = deg + 1
+    L = next_fast_size(N + M - 1)
+    A = complex(A)
+    W = complex(W)
+    n = np.arange(N, dtype=np.float64)
+    y = np.zeros(L, dtype=np.complex128)
+    y[:N] = p[::-1] * np.power(A, -n) * np.power(W, 0.5 * n * n)
+    v = np.zeros(L, dtype=np.complex128)
+    m = np.arange(M, dtype=np.float64)
+    v[:M] = np.power(W, -0.5 * m * m)
+    k = np.arange(L - N + 1, L, dtype=np.float64)
+    v[L - N + 1:] = np.power(W, -0.5 * (L - k) * (L - k))
+    g = np.fft.ifft(np.fft.fft(y) * np.fft.fft(v))    # ifft already divides by L (:95)
+    return np.power(W, 0.5 * m * m) * g[:M]
+
+
+def lambda_to_z(lam, eps_t, scheme):
+    """fnft__akns_discretization_lambda_to_z, src/private/fnft__akns_discretization.c:204-219."""
+    return np.exp(2j * lam * eps_t / (akns_degree(scheme) * akns_upsampling(scheme)))
+
+
+def resample(q, eps_t, delta):
+    """misc_resample, src/private/fnft__misc.c:326-407 (band-limited shift by delta)."""
+    q = np.asarray(q, dtype=np.complex128)
+    D = q.shape[0]
+    i = np.arange(D)
+    freq = np.where(i < D // 2, i, i - D) / (D * eps_t)
+    return np.fft.ifft(np.fft.fft(q) * np.exp(2j * np.pi * delta * freq))
+
+
+def preprocess_signal(q, eps_t, kappa, nse_disc):
+    """nse_discretization_preprocess_signal without subsampling,
+    src/private/fnft__nse_discretization.c:386-656 (:467-473 copy, :474-503 4SPLIT4)."""
+    q = np.asarray(q, dtype=np.complex128)
+    if nse_disc in (NSE_4SPLIT4B, NSE_CF4_2):
+        s = np.sqrt(3.0) / 6.0
+        q1 = resample(q, eps_t, -eps_t * s)
+        q2 = resample(q, eps_t, +eps_t * s)
+        w = (0.25 + s, 0.25 - s, 0.25 - s, 0.25 + s)  # fnft__akns_discretization.c:284-298
+        out = np.empty(2 * q.shape[0], dtype=np.complex128)
+        out[0::2] = w[0] * q1 + w[1] * q2
+        out[1::2] = w[2] * q1 + w[3] * q2
+        return out
+    return q.copy()
+
+
+def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normalize=True):
+    """Continuous spectrum of fnft_nsev for the fast discretizations:
+    src/fnft_nsev.c:133-314 (driver), :458-542 (base), :744-891 (contspec).
+    cstype 0: rho[M]; 1: [a | b]; 2: [rho | a | b]."""
+    q = np.asarray(q, dtype=np.complex128)
+    D = q.shape[0]
+    scheme = _NSE2AKNS[nse_disc]
+    eps_t = (T[1] - T[0]) / (D - 1)
+    qp = preprocess_signal(q, eps_t, kappa, nse_disc)
+    tm, deg, W = akns_fscatter(qp, -kappa * np.conj(qp), eps_t, scheme, normalize)
+    eps_xi = (XI[1] - XI[0]) / (M - 1)
+    xi = XI[0] + eps_xi * np.arange(M)
+    V = lambda_to_z(eps_xi, eps_t, scheme)     # :822-827
+    A = lambda_to_z(-XI[0], eps_t, scheme)
+    H11 = poly_chirpz(tm[0], A, V, M)
+    H21 = poly_chirpz(tm[2], A, V, M)
+    bc = 0.5
+    d1 = akns_degree(scheme)
+    extra = eps_t / d1 if nse_disc in (NSE_2SPLIT2A, NSE_2SPLIT2_MODAL) else 0.0
+    ph_rho = -2.0 * (T[1] + eps_t * bc) + extra                        # nse_discretization.c:240-256
+    ph_a = -eps_t * D + (T[1] + eps_t * bc) - (T[0] - eps_t * bc)      # :263-313
+    ph_b = -eps_t * D - (T[1] + eps_t * bc) - (T[0] - eps_t * bc) + extra  # :320-379
+    out = []
+    if cstype in (0, 2):
+        out.append(H21 * np.exp(1j * xi * ph_rho) / H11)               # :846-855
+    if cstype in (1, 2):
+        scale = 2.0 ** W                                               # :863-876
+        out.append(H11 * scale * np.exp(1j * xi * ph_a))
+        out.append(H21 * scale * np.exp(1j * xi * ph_b))
+    return np.concatenate(out)
+
+
+def kdvv(u, T, M, XI, kdv_disc=KDV_2SPLIT4B):
+    """fnft_kdvv, src/fnft_kdvv.c:59-209 (no preprocessing; xi grid negated)."""
+    u = np.asarray(u, dtype=np.complex128)
+    D = u.shape[0]
+    scheme = _KDV2AKNS[kdv_disc]
+    deg1 = akns_degree(scheme)
+    eps_t = (T[1] - T[0]) / (D - 1)
+    eps_xi = (XI[1] - XI[0]) / (M - 1)
+    tm, deg, _ = akns_fscatter(u, -np.ones_like(u), eps_t, scheme, normalize=False)
+    V = np.exp(-2j * eps_xi * eps_t / deg1)      # :169-170
+    A = np.exp(2j * XI[0] * eps_t / deg1)
+    H12 = poly_chirpz(tm[1], A, V, M)
+    H22 = poly_chirpz(tm[3], A, V, M)
+    xi = -XI[0] - np.arange(M) * eps_xi
+    if kdv_disc == KDV_2SPLIT2A:                 # :186-195
+        H12 = H12 / np.exp(1j * xi * eps_t / deg1)
+    return np.exp(2j * xi * (T[1] + 0.5 * eps_t)) * H12 / (2j * xi * H22 - H12)  # :198-203
+
+
+# ---------------------------------------------------------------------------------
+# bound states
+# ---------------------------------------------------------------------------------
+def _bo_step(q, r, l, h):
+    """One Boffetta-Osborne step and its lambda-derivative,
+    src/private/fnft__nse_scatter_bound_states.c:297-322 (vectorised over l)."""
+    ks = q * r - l * l
+    k = np.sqrt(ks + 0j)
+    ch = np.cosh(k * h)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sh = np.where(ks != 0, np.sinh(k * h) / np.where(ks != 0, k, 1.0), h)
+        chi = ch / ks
+        u1 = l * sh * 1j
+        ud1 = h * l * l * chi * 1j
+        ud2 = l * (h * ch - sh) / ks
+        U = (ch - u1, q * sh, r * sh, ch + u1)
+        Ud = (ud1 - (l * h + 1j + (l * l * 1j) / ks) * sh, -q * ud2, -r * ud2,
+              -ud1 - (l * h - 1j - (l * l * 1j) / ks) * sh)
+    return U, Ud
+
+
+def nse_scatter_bound_states(q, T, lam, upsampling=1):
+    """fnft__nse_scatter_bound_states for BO (upsampling 1) and CF4_2 (upsampling 2),
+    src/private/fnft__nse_scatter_bound_states.c:29-667.  q are the effective
+    (preprocessed) samples, r = -conj(q).  Returns (a, aprime, b)."""
+    q = np.asarray(q, dtype=np.complex128)
+    lam = np.asarray(lam, dtype=np.complex128)
+    D = q.shape[0]
+    Dg = D // upsampling
+    r = -np.conj(q)
+    eps_t = (T[1] - T[0]) / (Dg - 1)
+    bc = 0.5
+    lw = 0.5 if upsampling == 2 else 1.0       # sum of the CF4_2 weights (:214-221, 232-243)
+    scl = 0.5 if upsampling == 2 else 1.0
+    l = lam * lw
+    K = lam.shape[0]
+    PHI = np.zeros((Dg + 1, 2, K), dtype=np.complex128)
+    tb = T[0] - eps_t * bc
+    phi1 = np.exp(-1j * lam * tb)              # :281-284
+    phi2 = np.zeros(K, dtype=np.complex128)
+    d1 = phi1 * (-1j * tb)
+    d2 = np.zeros(K, dtype=np.complex128)
+    PHI[0, 0], PHI[0, 1] = phi1, phi2
+    ng = 0
+    for n in range(D):                          # :289-338
+        U, Ud = _bo_step(q[n], r[n], l, eps_t)
+        c = Ud[0] * phi1 + Ud[1] * phi2 + U[0] * d1 + U[1] * d2
+        d2 = Ud[2] * phi1 + Ud[3] * phi2 + U[2] * d1 + U[3] * d2
+        d1 = c
+        c = U[2] * phi1 + U[3] * phi2
+        phi1 = U[0] * phi1 + U[1] * phi2
+        phi2 = c
+        if (n + 1) % upsampling == 0:
+            ng += 1
+            PHI[ng, 0], PHI[ng, 1] = phi1, phi2
+    te = T[1] + eps_t * bc
+    ex = np.exp(1j * lam * te)
+    a = PHI[Dg, 0] * ex                         # :639-640
+    ap = scl * (d1 * ex + (1j * te) * a)
+    # backward sweep :480-530
+    PSI = np.zeros((Dg + 1, 2, K), dtype=np.complex128)
+    psi1 = np.zeros(K, dtype=np.complex128)
+    psi2 = ex.copy()
+    PSI[Dg, 0], PSI[Dg, 1] = psi1, psi2
+    ng = Dg
+    for n in range(D - 1, -1, -1):
+        U, _ = _bo_step(q[n], r[n], l, -eps_t)
+        c = U[2] * psi1 + U[3] * psi2
+        psi1 = U[0] * psi1 + U[1] * psi2
+        psi2 = c
+        if n % upsampling == 0:
+            ng -= 1
+            PSI[ng, 0], PSI[ng, 1] = psi1, psi2
+    # choice of b :642-654: first strict minimum of the error metric
+    with np.errstate(divide="ignore", invalid="ignore"):
+        metric = np.abs(0.5 * np.log(np.abs((PHI[:, 1] / PSI[:, 1]) / (PHI[:, 0] / PSI[:, 0]))))
+        ratio = PHI[:, 0] / PSI[:, 0]
+    b = np.zeros(K, dtype=np.complex128)
+    for k in range(K):
+        best = np.inf
+        for n in range(Dg + 1):
+            if metric[n, k] < best:
+                best = metric[n, k]
+                b[k] = ratio[n, k]
+    return a, ap, b
+
+
+def l2norm2(z, a, b):
+    """misc_l2norm2, src/private/fnft__misc.c:90-112."""
+    z = np.asarray(z)
+    N = z.shape[0]
+    h = (b - a) / N
+    m = np.abs(z) ** 2
+    return 0.5 * h * m[0] + h * m[1:-1].sum() + 0.5 * h * m[-1]
+
+
+def misc_filter(vals, box):
+    """misc_filter, src/private/fnft__misc.c:114-157 (order preserving)."""
+    return [v for v in vals if (v.real >= box[0]) and (v.real <= box[1]) and (v.imag >= box[2])
+            and (v.imag <= box[3])]
+
+
+def misc_merge(vals, tol):
+    """misc_merge, src/private/fnft__misc.c:228-259 (compares with the ORIGINAL list)."""
+    vals = list(vals)
+    keep = vals[:1]
+    for i in range(1, len(vals)):
+        dist = -1.0
+        for j in range(i):
+            dist = abs(vals[j] - vals[i])
+            if dist < tol:
+                break
+        if dist < tol:
+            continue
+        keep.append(vals[i])
+    return keep
+
+
+def nsev_bound_states_newton(q, T, guesses, nse_disc=NSE_2SPLIT4B, niter=10, bsfilt=2,
+                             dstype=0):
+    """Discrete spectrum of fnft_nsev with bsloc_NEWTON for the fast discretizations:
+    nsev_compute_boundstates src/fnft_nsev.c:595-741, Newton loop :973-1038, norming
+    constants / residues :895-970.  Returns (bound_states, normconsts_or_residues)."""
+    q = np.asarray(q, dtype=np.complex128)
+    D = q.shape[0]
+    eps_t = (T[1] - T[0]) / (D - 1)
+    up = 2 if nse_disc == NSE_4SPLIT4B else 1
+    qp = preprocess_signal(q, eps_t, +1, nse_disc)
+    deg1 = akns_degree(_NSE2AKNS[nse_disc])
+    map_coeff = 2.0 / deg1
+    if bsfilt == 2:      # FULL :633-653
+        re = 0.9 * np.pi / abs(map_coeff * eps_t)
+        qg = qp if up == 1 else up * qp[1::up]
+        box = [-re, re, 0.0, 1.5 * 0.25 * l2norm2(qg, T[0], T[1])]
+    elif bsfilt == 1:    # BASIC :628-632
+        box = [-np.inf, np.inf, 0.0, np.inf]
+    else:
+        box = [-np.inf, np.inf, -np.inf, np.inf]
+    out = []
+    for lam in np.asarray(guesses, dtype=np.complex128):
+        it = 0
+        while niter > 0:  # :1007-1034
+            a, ap, _ = nse_scatter_bound_states(qp, T, np.array([lam]), up)
+            if a[0] == 0:
+                break
+            err = a[0] / ap[0]
+            lam = lam - err
+            it += 1
+            if lam.imag > box[3] or lam.real > box[1] or lam.real < box[0] or lam.imag < box[2]:
+                break
+            if not (abs(err) > 100 * EPS and it < niter):
+                break
+        out.append(lam)
+    if bsfilt != 0:      # :717-724
+        out = misc_merge(misc_filter(out, box), np.sqrt(EPS))
+    bs = np.array(out, dtype=np.complex128)
+    if len(bs) == 0:
+        return bs, np.zeros(0, dtype=np.complex128)
+    a, ap, b = nse_scatter_bound_states(qp, T, bs, up)
+    if dstype == 0:
+        nc = b
+    elif dstype == 1:
+        nc = b / ap
+    else:
+        nc = np.concatenate([b, b / ap])
+    return bs, nc
+
+
+def misc_rel_err(num, exact):
+    """misc_rel_err, src/private/fnft__misc.c:41-51 -- THE parity metric."""
+    num = np.asarray(num)
+    exact = np.asarray(exact)
+    return np.abs(num - exact).sum() / np.abs(exact).sum()

@@ -1,0 +1,86 @@
+"""Shared inputs of the parity tests: the formulas of the reference's own unit tests
+(test/fnft__poly/*.c, test/fnft__akns_fscatter/*.c) and seeded synthetic signals."""
+import numpy as np
+
+
+def rel_err(num, exact):
+    """misc_rel_err (src/private/fnft__misc.c:41-51): sum|num-exact| / sum|exact|."""
+    num, exact = np.asarray(num), np.asarray(exact)
+    return np.abs(num - exact).sum() / np.abs(exact).sum()
+
+
+def fmult2x2_test_input(n, deg=1):
+    """Input of fnft__poly_fmult2x2_test_n_is_(no_)power_of_2.c:(96-99): p[4, n, deg+1]."""
+    i = np.arange((deg + 1) * n, dtype=np.float64)
+    p = np.empty((4, (deg + 1) * n), dtype=np.complex128)
+    for e, off in enumerate((0.0, 0.1, 0.2, 0.3)):
+        p[e] = np.sqrt(i + 1.0) * (np.cos(i + off) + 1j * np.sin(-2.0 * i + off))
+    return p.reshape(4, n, deg + 1)
+
+
+def akns_fscatter_test_input():
+    """q, r, eps_t, z of test/fnft__akns_fscatter/fnft__akns_fscatter_test_*.c:37-38,101-102."""
+    i = np.arange(1, 9, dtype=np.float64)
+    q = (0.41 * np.cos(i) + 0.59j * np.sin(0.28 * i)) * 50
+    r = (0.33 * np.sin(i) + 0.85j * np.cos(0.43 * i)) * 25
+    z = np.array([1.0, np.exp(1j * np.pi / 4), np.exp(1j * 9 * np.pi / 14),
+                  np.exp(1j * 4 * np.pi / 3), np.exp(-1j * np.pi / 5)])
+    return q, r, 0.13, z
+
+
+AKNS_TEST_SCHEMES = {"2split4B": 10, "2split2A": 3, "2split1A": 1, "2split1B": 2, "2split2B": 4,
+                     "2split2S": 5, "2split2_modal": 0}
+
+
+def eval_tm(tm, z):
+    """poly_eval of the four entries at the points z (Horner, highest power first)."""
+    return np.concatenate([np.polyval(tm[e], z) for e in range(4)])
+
+
+CHIRPZ_TEST_P = np.array([1 + 2j, -3 - 0.5j, 0.3, -0.4j])
+CHIRPZ_TEST_A = 0.95
+CHIRPZ_TEST_W = np.exp(0.3j)
+
+
+def sech_chirp(D, T, amp=2.0, chirp=0.3):
+    t = np.linspace(T[0], T[1], D)
+    return amp / np.cosh(t) * np.exp(1j * chirp * t * t)
+
+
+def parity_contract(ours, ref, tol=1e-9):
+    """(i) L1-relative error, (ii) pointwise on |ref| >= 1e-6 max,
+    (iii) absolute on the tails.  Returns the three figures normalised by tol."""
+    ours, ref = np.asarray(ours), np.asarray(ref)
+    mx = np.abs(ref).max()
+    big = np.abs(ref) >= 1e-6 * mx
+    e1 = rel_err(ours, ref)
+    e2 = (np.abs(ours - ref)[big] / np.abs(ref)[big]).max() if big.any() else 0.0
+    e3 = (np.abs(ours - ref)[~big]).max() / mx if (~big).any() else 0.0
+    return e1 / tol, e2 / tol, e3 / tol
+
+
+# ---------------------------------------------------------------------------------
+# build helpers (the product library is built in-tree by `make`; tests build it on
+# demand if it is missing so that the CPU suite is self-contained)
+# ---------------------------------------------------------------------------------
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ensure_lib():
+    path = os.path.join(ROOT, "fnft_b200", "lib", "libfnft_b200.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-j8"], cwd=ROOT)
+    return path
+
+
+def ensure_emul():
+    path = os.path.join(ROOT, "tests", "emul", "libfnftb_emul.so")
+    srcs = [os.path.join(ROOT, "tests", "emul", "emul_lib.cpp")]
+    cud = os.path.join(ROOT, "fnft_b200", "csrc", "cuda")
+    srcs += [os.path.join(cud, f) for f in os.listdir(cud) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+        subprocess.check_call(["make", "emul"], cwd=ROOT)
+    return path

@@ -1,0 +1,142 @@
+"""Generates tests/golden/golden.npz -- run in the BUILD CONTAINER only.
+
+Two sources (both need /root/reference, which does not exist on the GPU box):
+  1. the literal golden arrays of the reference's own unit tests, parsed out of
+     /root/reference/test/**.c (keys "reftest/...");
+  2. outputs of the unmodified reference library (oracle/_ref/libfnft_ref.so, built by
+     oracle/Makefile) on seeded inputs (keys "refrun/...").
+The committed .npz travels to the GPU box; the tests never read /root/reference.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import ref_lib as R  # noqa: E402
+
+REF = "/root/reference"
+
+
+def parse_complex_array(path, name):
+    """Extracts `COMPLEX name[..] = { a + b*I, ... };` from a C file."""
+    src = open(path).read()
+    m = re.search(r"COMPLEX\s+" + re.escape(name) + r"\s*\[[^\]]*\]\s*=\s*\{(.*?)\};", src, re.S)
+    if m is None:
+        raise KeyError(f"{name} not found in {path}")
+    body = m.group(1).replace("\\", " ")
+    vals = []
+    for item in body.split(","):
+        s = item.strip()
+        if not s:
+            continue
+        s = s.replace("I*", "1j*").replace("*I", "*1j")
+        s = re.sub(r"(?<![\w.])I(?![\w.])", "1j", s)
+        vals.append(complex(eval(s, {"__builtins__": {}}, {})))
+    return np.array(vals, dtype=np.complex128)
+
+
+def main():
+    G = {}
+    # ---------------------------------------------------------------- 1. reference tests
+    t = os.path.join(REF, "test")
+    G["reftest/fmult2x2_pow2"] = parse_complex_array(
+        os.path.join(t, "fnft__poly/fnft__poly_fmult2x2_test_n_is_power_of_2.c"), "result_exact")
+    G["reftest/fmult2x2_nopow2"] = parse_complex_array(
+        os.path.join(t, "fnft__poly/fnft__poly_fmult2x2_test_n_is_no_power_of_2.c"), "result_exact")
+    G["reftest/chirpz_M3"] = parse_complex_array(
+        os.path.join(t, "fnft__poly/fnft__poly_chirpz_test.c"), "result_exactM3")
+    G["reftest/chirpz_M6"] = parse_complex_array(
+        os.path.join(t, "fnft__poly/fnft__poly_chirpz_test.c"), "result_exactM6")
+    for nm in ["2split4B", "2split2A", "2split1A", "2split1B", "2split2B", "2split2S", "2split2_modal"]:
+        G[f"reftest/akns_fscatter_{nm}"] = parse_complex_array(
+            os.path.join(t, f"fnft__akns_fscatter/fnft__akns_fscatter_test_{nm}.c"), "result_exact")
+
+    # ---------------------------------------------------------------- 2. reference runs
+    rng = np.random.default_rng(20261018)
+
+    def sig(D, kind):
+        tt = np.linspace(-6, 6, D)
+        if kind == 0:
+            return 1.9 / np.cosh(tt) * np.exp(0.3j * tt * tt + 0.2j)
+        return (rng.standard_normal(D) + 1j * rng.standard_normal(D)) * 0.4 * np.exp(-tt * tt / 8)
+
+    for disc in (11, 4):
+        for D in (2, 3, 37, 64, 100, 256):
+            q = sig(D, D % 2)
+            eps = 12.0 / max(D - 1, 1)
+            ret, tm, deg, W = R.nse_fscatter(q, eps, 1, disc)
+            assert ret == 0
+            G[f"refrun/fscatter/{disc}/{D}/q"] = q
+            G[f"refrun/fscatter/{disc}/{D}/eps"] = np.array(eps)
+            G[f"refrun/fscatter/{disc}/{D}/tm"] = tm * 2.0 ** W
+    R.lib().fnft_errwarn_setprintf(None)
+    for disc in (11, 4, 21):
+        for D in ((37, 64, 256, 1000) if disc != 21 else (64, 256)):
+            for kappa in (1, -1):
+                q = sig(D, 0) if disc == 21 else sig(D, (D // 2) % 2)
+                o = R.nsev_default_opts()
+                o.discretization = disc
+                o.contspec_type = 2
+                ret, cs, *_ = R.nsev(q, [-6, 6], 32, [-3.5, 2.75], kappa, o)
+                assert ret == 0
+                G[f"refrun/nsev/{disc}/{D}/{kappa}/q"] = q
+                G[f"refrun/nsev/{disc}/{D}/{kappa}/cs"] = cs
+    for disc in (9, 19, 2):
+        for D in (64, 100):
+            tt = np.linspace(-16, 15, D)
+            u = 1.7 / np.cosh(tt) ** 2 + 0.3 * np.exp(-(tt - 1) ** 2)
+            o = R.lib().fnft_kdvv_default_opts()
+            o.discretization = disc
+            ret, cs = R.kdvv(u, [-16, 15], 32, [-3.55, 3.95], o)
+            assert ret == 0
+            G[f"refrun/kdvv/{disc}/{D}/u"] = u.astype(np.complex128)
+            G[f"refrun/kdvv/{disc}/{D}/cs"] = cs
+    D = 256
+    tt = np.linspace(-12, 12, D)
+    q = 2.8 / np.cosh(tt) * np.exp(0.3j * tt)
+    g = np.array([0.35j - 0.14, 1.25j - 0.17, 2.2j - 0.1, 0.31j - 0.15])
+    for disc in (11, 21):
+        o = R.nsev_default_opts()
+        o.discretization = disc
+        o.bound_state_localization = 1
+        o.discspec_type = 2
+        ret, cs, K, bs, nc = R.nsev(q, [-12, 12], 0, None, 1, o, K=4, bound_states=g,
+                                    want_contspec=False)
+        assert ret == 0
+        G[f"refrun/bound/{disc}/q"] = q
+        G[f"refrun/bound/{disc}/guesses"] = g
+        G[f"refrun/bound/{disc}/bs"] = bs
+        G[f"refrun/bound/{disc}/nc"] = nc[:2 * K]
+    # a, a', b of the BO recurrence at fixed points (kernel-level pin)
+    lam = np.array([0.4j + 0.1, 1.3j - 0.2, 2.0j])
+    ret, a, ap, b = R.nse_scatter_bound_states(q, -np.conj(q), [-12, 12], lam, 1)
+    assert ret == 0
+    G["refrun/scatter_bo/q"] = q
+    G["refrun/scatter_bo/lam"] = lam
+    G["refrun/scatter_bo/a"] = a
+    G["refrun/scatter_bo/ap"] = ap
+    G["refrun/scatter_bo/b"] = b
+    p = rng.standard_normal(41) + 1j * rng.standard_normal(41)
+    A, W = 0.97 * np.exp(0.2j), 1.0005 * np.exp(0.03j)
+    ret, out = R.poly_chirpz(p, A, W, 25)
+    G["refrun/chirpz/p"] = p
+    G["refrun/chirpz/AW"] = np.array([A, W])
+    G["refrun/chirpz/out"] = out
+    pm = rng.standard_normal((4, 5, 4)) + 1j * rng.standard_normal((4, 5, 4))
+    ret, res, deg, W = R.poly_fmult2x2(3, pm)
+    assert ret == 0
+    G["refrun/fmult2x2_deg3_n5/p"] = pm
+    G["refrun/fmult2x2_deg3_n5/res"] = res * 2.0 ** W
+    out = os.path.join(HERE, "golden.npz")
+    np.savez_compressed(out, **G)
+    print("wrote", out, os.path.getsize(out), "bytes,", len(G), "arrays")
+
+
+if __name__ == "__main__":
+    main()

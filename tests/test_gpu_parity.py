@@ -1,0 +1,300 @@
+"""GPU parity tests (run with -m gpu on a B200): every case calls the CUDA path through
+the C-ABI of libfnft_b200.so and compares with
+  * the reference's own golden vectors and recorded reference outputs (tests/golden),
+  * the numpy oracle on seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at BASELINE.json's full sizes,
+  * the unmodified reference library itself when oracle/_ref travelled to the box.
+Tolerances: the reference's unit-test bound 100*eps where the reference states one;
+otherwise the 1e-9 contract of SURVEY.md 8(c) (L1-relative / pointwise / tail)."""
+import numpy as np
+import pytest
+
+from common import (AKNS_TEST_SCHEMES, CHIRPZ_TEST_A, CHIRPZ_TEST_P, CHIRPZ_TEST_W,
+                    akns_fscatter_test_input, eval_tm, fmult2x2_test_input, parity_contract,
+                    rel_err, sech_chirp)
+from oracle import fnft_oracle as O
+from oracle import ref_lib as R
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fnft_b200
+    if fnft_b200.device_count() < 1:
+        pytest.fail("no CUDA device visible to libfnft_b200.so (there is no CPU fallback to test)")
+    return fnft_b200
+
+
+def _keys(golden, prefix):
+    return sorted({k[len(prefix):].rsplit("/", 1)[0] for k in golden.files if k.startswith(prefix)})
+
+
+# ------------------------------------------------------------------ reference unit tests
+@pytest.mark.parametrize("n,key", [(4, "fmult2x2_pow2"), (5, "fmult2x2_nopow2")])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_fmult2x2_reference_golden(F, golden, n, key, normalize):
+    ret, res, deg, W = F.poly_fmult2x2(1, fmult2x2_test_input(n), normalize)
+    exact = golden["reftest/" + key]
+    assert ret == 0 and deg == exact.size // 4 - 1
+    if normalize:
+        assert W != 0
+    assert rel_err((res * 2.0 ** W).reshape(-1), exact) <= 100 * EPS
+
+
+@pytest.mark.parametrize("M", [3, 6])
+def test_chirpz_reference_golden(F, golden, M):
+    ret, out = F.poly_chirpz(CHIRPZ_TEST_P, CHIRPZ_TEST_A, CHIRPZ_TEST_W, M)
+    assert ret == 0
+    assert rel_err(out, golden[f"reftest/chirpz_M{M}"]) <= 100 * EPS
+
+
+@pytest.mark.parametrize("name", sorted(AKNS_TEST_SCHEMES))
+@pytest.mark.parametrize("normalize", [False, True])
+def test_akns_fscatter_reference_golden(F, golden, name, normalize):
+    q, r, eps_t, z = akns_fscatter_test_input()
+    ret, tm, deg, W = F.akns_fscatter(q, r, eps_t, AKNS_TEST_SCHEMES[name], normalize)
+    assert ret == 0
+    if normalize:
+        assert W != 0
+    assert rel_err(eval_tm(tm * 2.0 ** W, z), golden[f"reftest/akns_fscatter_{name}"]) <= 100 * EPS
+
+
+# ------------------------------------------------------------------ recorded reference runs
+def test_fscatter_vs_reference_runs(F, golden):
+    for case in _keys(golden, "refrun/fscatter/"):
+        disc, D = map(int, case.split("/"))
+        q = golden[f"refrun/fscatter/{case}/q"]
+        ret, tm, deg, W = F.nse_fscatter(q, float(golden[f"refrun/fscatter/{case}/eps"]), 1, disc)
+        ref = golden[f"refrun/fscatter/{case}/tm"]
+        assert ret == 0
+        for e in range(4):
+            if np.abs(ref[e]).sum() > 0:
+                assert rel_err(tm[e] * 2.0 ** W, ref[e]) < 1e-12, case
+
+
+def test_nsev_contspec_vs_reference_runs(F, golden):
+    F.lib().fnft_errwarn_setprintf(None)  # band-limit warnings of the 4SPLIT4B cases
+    for case in _keys(golden, "refrun/nsev/"):
+        disc, D, kappa = map(int, case.split("/"))
+        o = F.nsev_default_opts()
+        o.discretization = disc
+        o.contspec_type = F.CSTYPE_BOTH
+        ret, cs, *_ = F.nsev(golden[f"refrun/nsev/{case}/q"], [-6, 6], 32, [-3.5, 2.75], kappa, o)
+        assert ret == 0, case
+        ref = golden[f"refrun/nsev/{case}/cs"]
+        for part in range(3):
+            assert max(parity_contract(cs[part * 32:(part + 1) * 32], ref[part * 32:(part + 1) * 32])) < 1, case
+
+
+def test_kdvv_vs_reference_runs(F, golden):
+    for case in _keys(golden, "refrun/kdvv/"):
+        disc, D = map(int, case.split("/"))
+        o = F.kdvv_default_opts()
+        o.discretization = disc
+        ret, cs = F.kdvv(golden[f"refrun/kdvv/{case}/u"], [-16, 15], 32, [-3.55, 3.95], o)
+        assert ret == 0
+        assert max(parity_contract(cs, golden[f"refrun/kdvv/{case}/cs"])) < 1, case
+
+
+def test_general_chirpz_and_tree_vs_reference_runs(F, golden):
+    A, W = golden["refrun/chirpz/AW"]
+    ret, out = F.poly_chirpz(golden["refrun/chirpz/p"], A, W, 25)
+    assert ret == 0 and rel_err(out, golden["refrun/chirpz/out"]) < 1e-12
+    ret, res, deg, Wn = F.poly_fmult2x2(3, golden["refrun/fmult2x2_deg3_n5/p"])
+    assert ret == 0 and deg == 15
+    assert rel_err((res * 2.0 ** Wn).reshape(-1), golden["refrun/fmult2x2_deg3_n5/res"].reshape(-1)) < 1e-13
+
+
+def test_bound_states_vs_reference_runs(F, golden):
+    F.lib().fnft_errwarn_setprintf(None)
+    q = golden["refrun/scatter_bo/q"]
+    ret, a, ap, b = F.nse_scatter_bound_states(q, None, [-12, 12], golden["refrun/scatter_bo/lam"],
+                                               F.NSE_BO)
+    assert ret == 0
+    assert rel_err(a, golden["refrun/scatter_bo/a"]) < 1e-11
+    assert rel_err(ap, golden["refrun/scatter_bo/ap"]) < 1e-11
+    assert rel_err(b, golden["refrun/scatter_bo/b"]) < 1e-9
+    for disc in (11, 21):
+        o = F.nsev_default_opts()
+        o.discretization = disc
+        o.bound_state_localization = F.BSLOC_NEWTON
+        o.discspec_type = F.DSTYPE_BOTH
+        ret, cs, K, bs, nc = F.nsev(golden[f"refrun/bound/{disc}/q"], [-12, 12], 0, None, 1, o, K=4,
+                                    bound_states=golden[f"refrun/bound/{disc}/guesses"],
+                                    want_contspec=False)
+        ref_bs = golden[f"refrun/bound/{disc}/bs"]
+        assert ret == 0 and K == len(ref_bs)
+        assert (np.abs(bs - ref_bs) <= 1e-9 * np.abs(ref_bs)).all()
+        ref_nc = golden[f"refrun/bound/{disc}/nc"]
+        assert (np.abs(nc[:2 * K] - ref_nc) <= 1e-9 * np.abs(ref_nc)).all()
+
+
+# ------------------------------------------------------------------ oracle, larger sizes
+@pytest.mark.parametrize("disc", [11, 4])
+@pytest.mark.parametrize("D", [2, 3, 127, 1024, 4097, 16384])
+def test_fscatter_vs_oracle(F, disc, D):
+    T = (-8.0, 8.0)
+    q = sech_chirp(D, T, 2.3, 0.2)
+    eps_t = (T[1] - T[0]) / max(D - 1, 1)
+    ret, tm, deg, W = F.nse_fscatter(q, eps_t, 1, disc)
+    tmo, dego, Wo = O.nse_fscatter(q, eps_t, 1, disc)
+    assert ret == 0 and deg == dego
+    for e in range(4):
+        assert rel_err(tm[e] * 2.0 ** W, tmo[e] * 2.0 ** Wo) < 1e-10, (disc, D, e)
+
+
+@pytest.mark.parametrize("D,M", [(126, 40), (1024, 1024), (4096, 4000), (16384, 16384)])
+@pytest.mark.parametrize("kappa", [+1, -1])
+def test_nsev_contspec_vs_oracle(F, D, M, kappa):
+    T, XI = (-32.0, 32.0), (-10.0, 10.0)
+    t = np.linspace(T[0], T[1], D)
+    q = 1.7 / np.cosh(t) * np.exp(-3j * t + 0.4j * np.sin(t))
+    o = F.nsev_default_opts()
+    o.contspec_type = F.CSTYPE_BOTH
+    ret, cs, *_ = F.nsev(q, T, M, XI, kappa, o)
+    ref = O.nsev_contspec(q, T, M, XI, kappa, O.NSE_2SPLIT4B, cstype=2)
+    assert ret == 0
+    for part in range(3):
+        assert max(parity_contract(cs[part * M:(part + 1) * M], ref[part * M:(part + 1) * M])) < 1, part
+
+
+def test_nsev_4split4b_vs_oracle(F):
+    F.lib().fnft_errwarn_setprintf(None)
+    D, M = 2048, 512
+    T, XI = (-20.0, 20.0), (-6.0, 6.0)
+    q = sech_chirp(D, T, 1.4, 0.05)
+    o = F.nsev_default_opts()
+    o.discretization = F.NSE_4SPLIT4B
+    ret, cs, *_ = F.nsev(q, T, M, XI, 1, o)
+    ref = O.nsev_contspec(q, T, M, XI, 1, O.NSE_4SPLIT4B, cstype=0)
+    assert ret == 0 and max(parity_contract(cs, ref)) < 1
+
+
+def test_kdvv_vs_oracle_config4_shape(F):
+    # BASELINE config 4 shape at a size the oracle finishes in seconds
+    D = M = 8192
+    T, XI = (-16.0, 15.0), (-3.55, 3.95)
+    t = np.linspace(T[0], T[1], D)
+    u = 1.3 / np.cosh((t - 0.5) / 1.1) ** 2
+    o = F.kdvv_default_opts()
+    o.discretization = F.KDV_4SPLIT4B
+    ret, cs = F.kdvv(u, T, M, XI, o)
+    ref = O.kdvv(u, T, M, XI, O.KDV_4SPLIT4B)
+    assert ret == 0 and max(parity_contract(cs, ref)) < 1
+
+
+def test_newton_bound_states_vs_oracle(F):
+    D = 512
+    T = (-14.0, 14.0)
+    t = np.linspace(T[0], T[1], D)
+    q = 3.3 / np.cosh(t) * np.exp(0.2j * t)
+    g = np.array([0.7j, 1.9j - 0.1, 2.9j - 0.12, 0.72j + 0.01])
+    o = F.nsev_default_opts()
+    o.bound_state_localization = F.BSLOC_NEWTON
+    o.discspec_type = F.DSTYPE_BOTH
+    ret, cs, K, bs, nc = F.nsev(q, T, 0, None, 1, o, K=4, bound_states=g, want_contspec=False)
+    bo, no = O.nsev_bound_states_newton(q, T, g, O.NSE_2SPLIT4B, 10, 2, 2)
+    assert ret == 0 and K == len(bo)
+    assert (np.abs(bs - bo) <= 1e-9 * np.abs(bo)).all()
+    assert (np.abs(nc[:2 * K] - no) <= 1e-9 * np.abs(no)).all()
+
+
+# ------------------------------------------------------------------ batch API / properties
+def test_batch_matches_single_and_ragged_batch(F):
+    rng = np.random.default_rng(7)
+    B, D, M = 37, 1000, 333   # non-power-of-two everything
+    T, XI = (-10.0, 10.0), (-4.0, 5.0)
+    t = np.linspace(T[0], T[1], D)
+    Q = (rng.uniform(0.5, 3, (B, 1)) / np.cosh(t)[None] *
+         np.exp(1j * rng.uniform(-2, 2, (B, 1)) * t[None]))
+    ret, cs, _, _, _, rcs = F.nsev_batch(Q, T, M, XI, 1)
+    assert ret == 0 and (rcs == 0).all()
+    for b in (0, 17, 36):
+        r1, c1, *_ = F.nsev(Q[b], T, M, XI, 1)
+        assert r1 == 0 and np.array_equal(c1, cs[b])          # bit-identical: same kernels
+        assert max(parity_contract(cs[b], O.nsev_contspec(Q[b], T, M, XI, 1))) < 1
+
+
+def test_full_size_properties_config2(F):
+    """BASELINE config 2 size (D = M = 16384): properties that need no oracle run.
+    q -> q*exp(i*phi) leaves a unchanged and turns b into b*exp(-i*phi) (the leaves are
+    conjugated by a constant diagonal matrix); results must be deterministic."""
+    D = M = 16384
+    T, XI = (-32.0, 32.0), (-10.0, 10.0)
+    t = np.linspace(T[0], T[1], D)
+    q = 4.1 / np.cosh(t) * np.exp(-2j * 1.3 * t)
+    o = F.nsev_default_opts()
+    o.contspec_type = F.CSTYPE_AB
+    phi = 0.73
+    r0, c0, *_ = F.nsev(q, T, M, XI, 1, o)
+    r1, c1, *_ = F.nsev(q * np.exp(1j * phi), T, M, XI, 1, o)
+    r2, c2, *_ = F.nsev(q, T, M, XI, 1, o)
+    assert r0 == r1 == r2 == 0
+    assert np.array_equal(c0, c2)
+    a0, b0, a1, b1 = c0[:M], c0[M:], c1[:M], c1[M:]
+    assert rel_err(a1, a0) < 1e-11
+    assert rel_err(b1, b0 * np.exp(-1j * phi)) < 1e-11
+
+
+def test_against_reference_library_if_present(F):
+    """oracle/_ref/libfnft_ref.so is built in the build container and travels with the
+    snapshot; when present compare at the full config-2 size."""
+    if not R.available():
+        pytest.skip("oracle/_ref not present on this box")
+    D = M = 16384
+    T, XI = (-32.0, 32.0), (-10.0, 10.0)
+    t = np.linspace(T[0], T[1], D)
+    rng = np.random.default_rng(16384)
+    th = sum(rng.normal(0, 0.5) * np.sin(2 * np.pi * (k + 1) * t / 64 + rng.uniform(0, 6.28))
+             for k in range(8))
+    for q in (5.4 / np.cosh(t) * np.exp(-6j * t), 2.0 / np.cosh(t / 1.5) * np.exp(1j * th)):
+        r0, c0, *_ = R.nsev(q, T, M, XI, 1, None)
+        r1, c1, *_ = F.nsev(q, T, M, XI, 1, None)
+        assert r0 == 0 and r1 == 0
+        assert max(parity_contract(c1, c0)) < 1
+
+
+def test_invalid_and_edge_inputs(F):
+    F.lib().fnft_errwarn_setprintf(None)
+    # D = 2 (smallest allowed), M = 2
+    ret, cs, *_ = F.nsev(np.array([0.3 + 0.1j, -0.2j]), (0.0, 1.0), 2, (-1.0, 1.0), 1)
+    ref = O.nsev_contspec(np.array([0.3 + 0.1j, -0.2j]), (0.0, 1.0), 2, (-1.0, 1.0), 1)
+    assert ret == 0 and rel_err(cs, ref) < 1e-12
+    # all-zero signal: rho = 0, a = 1 up to the boundary phase
+    o = F.nsev_default_opts()
+    o.contspec_type = F.CSTYPE_BOTH
+    ret, cs, *_ = F.nsev(np.zeros(64), (-1.0, 1.0), 8, (-2.0, 2.0), 1, o)
+    assert ret == 0 and np.abs(cs[:8]).max() == 0.0 and np.allclose(np.abs(cs[8:16]), 1.0, atol=1e-13)
+    # Newton guess outside the bounding box is filtered away -> K = 0
+    o = F.nsev_default_opts()
+    o.bound_state_localization = F.BSLOC_NEWTON
+    ret, cs, K, bs, nc = F.nsev(sech_chirp(256, (-10, 10), 0.2, 0.0), (-10, 10), 0, None, 1, o, K=1,
+                                bound_states=np.array([-0.5j]), want_contspec=False)
+    assert ret == 0 and K == 0
+
+
+def test_nsep_gridsearch_vs_reference_if_present(F):
+    if not R.available():
+        pytest.skip("oracle/_ref not present on this box")
+    R.lib().fnft_errwarn_setprintf(None)
+    F.lib().fnft_errwarn_setprintf(None)
+    D = 256
+    T = (0.0, 2 * np.pi)
+    t = T[0] + (T[1] - T[0]) / D * np.arange(D)
+    q = 1.2 * np.exp(2j * t) * (1 + 0.2 * np.cos(3 * t + 0.4))
+    for disc in (F.NSE_2SPLIT2A, F.NSE_2SPLIT4B):
+        o0 = R.lib().fnft_nsep_default_opts()
+        o1 = F.nsep_default_opts()
+        for o in (o0, o1):
+            o.localization = 1
+            o.filtering = 1
+            o.bounding_box[0], o.bounding_box[1], o.bounding_box[2], o.bounding_box[3] = -10, 10, -10, 10
+            o.discretization = disc
+        r0, m0, a0 = R.nsep(q, T, 1, o0)
+        r1, m1, a1 = F.nsep(q, T, 1, o1)
+        assert r0 == 0 and r1 == 0
+        assert len(m0) == len(m1) and len(a0) == len(a1)
+        assert np.abs(m1 - m0).max() <= 1e-9 * max(1.0, np.abs(m0).max())
+        assert np.abs(a1 - a0).max() <= 1e-9 * max(1.0, np.abs(a0).max())

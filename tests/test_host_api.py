@@ -1,0 +1,174 @@
+"""CPU-only checks of the drop-in boundary: the shared library loads, exports every
+symbol include/fnft_b200.h declares, keeps the reference's struct layouts / defaults /
+argument checks, and fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import ROOT, ensure_lib
+
+pytestmark = []
+
+
+@pytest.fixture(scope="module")
+def F():
+    ensure_lib()
+    import fnft_b200
+    fnft_b200.lib()
+    return fnft_b200
+
+
+def test_library_exports_every_declared_symbol(F):
+    L = F.lib()
+    header = open(os.path.join(ROOT, "include", "fnft_b200.h")).read()
+    declared = set(re.findall(r"\b(fnft_[a-z0-9_]*|fnft__[a-z0-9_]*)\s*\(", header))
+    declared -= {"fnft_printf_ptr_t"}
+    assert declared, "no declarations parsed"
+    assert set(F.EXPORTED_SYMBOLS) >= declared
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"symbols declared in include/fnft_b200.h but not exported: {missing}"
+
+
+def test_struct_layouts_match_reference():
+    import fnft_b200 as F
+    # LP64 layouts verified against the reference with offsetof
+    assert C.sizeof(F.NsevOpts) == 48
+    assert [getattr(F.NsevOpts, f).offset for f, _ in F.NsevOpts._fields_] == [0, 4, 8, 16, 24, 28, 32, 36, 40]
+    assert C.sizeof(F.KdvvOpts) == 4
+    assert C.sizeof(F.NsepOpts) == 96
+    assert [getattr(F.NsepOpts, f).offset for f, _ in F.NsepOpts._fields_] == [0, 4, 8, 40, 48, 52, 56, 72, 80, 88]
+
+
+def test_default_options_match_reference(F):
+    o = F.nsev_default_opts()            # src/fnft_nsev.c:26-36
+    assert (o.bound_state_filtering, o.bound_state_localization, o.niter, o.Dsub) == (2, 2, 10, 0)
+    assert (o.discspec_type, o.contspec_type, o.normalization_flag) == (0, 0, 1)
+    assert (o.discretization, o.richardson_extrapolation_flag) == (11, 0)
+    k = F.kdvv_default_opts()            # src/fnft_kdvv.c:34-36 (2SPLIT8B = 17)
+    assert k.discretization == 17
+    n = F.nsep_default_opts()            # src/fnft_nsep.c:27-41
+    assert (n.localization, n.filtering, n.max_evals, n.discretization) == (2, 2, 20, 4)
+    assert (n.normalization_flag, n.points_per_spine, n.Dsub, n.tol) == (1, 2, 0, -1.0)
+    assert list(n.floquet_range) == [-1.0, 1.0]
+    assert list(n.bounding_box) == [-np.inf, np.inf, -np.inf, np.inf]
+    assert F.lib().fnft_nsev_max_K(100, None) == 200  # degree 2 * D
+
+
+def test_numel_helpers(F):
+    L = F.lib()
+    # 4*(deg+1)*nextpow2(n), src/private/fnft__poly_fmult.c:40-43
+    assert L.fnft__poly_fmult2x2_numel(2, 5) == 4 * 3 * 8
+    assert L.fnft__nse_fscatter_numel(100, F.NSE_2SPLIT4B) == 4 * 3 * 128
+    assert L.fnft__nse_fscatter_numel(100, F.NSE_BO) == 0          # slow scheme: no polynomial
+    assert L.fnft__kdv_fscatter_numel(64, F.KDV_4SPLIT4B) == 4 * 3 * 64
+    assert L.fnft__akns_fscatter_numel(64, F.AKNS_2SPLIT2A) == 4 * 2 * 64
+
+
+def test_version(F):
+    L = F.lib()
+    a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    s = C.create_string_buffer(9)
+    assert L.fnft_version(C.byref(a), C.byref(b), C.byref(c), s) == 0
+    assert (a.value, b.value, c.value, s.value) == (0, 4, 1, b"")
+
+
+def _call_nsev(F, D=16, q=True, T=(-1.0, 1.0), M=8, XI=(-2.0, 2.0), kappa=1, cs=True, opts=None):
+    L = F.lib()
+    qa = np.ones(max(D, 1), dtype=np.complex128)
+    Ta = np.array(T, dtype=np.float64)
+    Xa = np.array(XI, dtype=np.float64)
+    out = np.zeros(3 * M, dtype=np.complex128)
+    return L.fnft_nsev(D, qa.ctypes.data if q else None, Ta.ctypes.data, M,
+                       out.ctypes.data if cs else None, Xa.ctypes.data, None, None, None, kappa,
+                       C.addressof(opts) if opts is not None else None)
+
+
+def test_argument_checks_mirror_reference(F):
+    F.lib().fnft_errwarn_setprintf(None)
+    EC_INVALID = 2
+    # src/fnft_nsev.c:163-174
+    assert _call_nsev(F, D=1) == EC_INVALID
+    assert _call_nsev(F, q=False) == EC_INVALID
+    assert _call_nsev(F, T=(1.0, -1.0)) == EC_INVALID
+    assert _call_nsev(F, XI=(2.0, -2.0)) == EC_INVALID
+    assert _call_nsev(F, kappa=0) == EC_INVALID
+    o = F.nsev_default_opts()
+    o.discretization = 99
+    assert _call_nsev(F, opts=o) == EC_INVALID
+    # src/fnft_kdvv.c:74-92
+    L = F.lib()
+    u = np.ones(16, dtype=np.complex128)
+    Ta = np.array([-1.0, 1.0])
+    Xa = np.array([-2.0, 2.0])
+    out = np.zeros(8, dtype=np.complex128)
+    K = C.c_size_t(1)
+    assert L.fnft_kdvv(16, u.ctypes.data, Ta.ctypes.data, 8, None, Xa.ctypes.data, None, None, None, None) == EC_INVALID
+    assert L.fnft_kdvv(16, u.ctypes.data, Ta.ctypes.data, 8, out.ctypes.data, Xa.ctypes.data,
+                       C.addressof(K), None, None, None) == 6  # NOT_YET_IMPLEMENTED, like the reference
+
+
+def test_not_yet_implemented_paths_are_loud(F):
+    F.lib().fnft_errwarn_setprintf(None)
+    o = F.nsev_default_opts()
+    o.discretization = 1  # BO: slow scheme, out of scope of the GPU hot path
+    assert _call_nsev(F, opts=o) == 6
+    o = F.nsev_default_opts()
+    o.discretization = 7  # 2SPLIT3A: no leaf kernel yet
+    assert _call_nsev(F, opts=o) == 6
+
+
+def test_no_cpu_fallback_without_gpu(F):
+    """On a box without a usable GPU every transform must fail (FNFT_EC_OTHER), never
+    silently compute on the CPU."""
+    if F.device_count() > 0:
+        pytest.skip("a GPU is present")
+    msgs = []
+    CB = C.CFUNCTYPE(C.c_int32, C.c_char_p)
+
+    F.lib().fnft_errwarn_setprintf(None)
+    assert _call_nsev(F) == 5
+    u = np.ones(16, dtype=np.complex128)
+    ret, tm, deg, W = F.nse_fscatter(u, 0.1, 1, F.NSE_2SPLIT4B)
+    assert ret == 5
+    ret, out = F.poly_chirpz(np.ones(4), 0.9, np.exp(0.1j), 4)
+    assert ret == 5
+
+
+def test_filter_and_merge_host_logic(F):
+    """misc_filter / misc_merge restatements used by the discrete-spectrum driver."""
+    from oracle import fnft_oracle as O
+    L = F.lib()
+    rng = np.random.default_rng(5)
+    vals = (rng.uniform(-2, 2, 40) + 1j * rng.uniform(-1, 3, 40)).astype(np.complex128)
+    vals[7] = vals[3] + 1e-9
+    vals[21] = vals[3] - 1e-10j
+    vals[30] = complex(np.nan, 1.0)
+    box = np.array([-1.5, 1.5, 0.0, 2.5])
+    want = O.misc_merge(O.misc_filter(list(vals), box), np.sqrt(np.finfo(float).eps))
+    buf = vals.copy()
+    n = C.c_size_t(len(buf))
+    L.fnftb__filter_box(C.byref(n), buf.ctypes.data_as(C.c_void_p), box.ctypes.data_as(C.c_void_p))
+    L.fnftb__merge.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    L.fnftb__merge(C.byref(n), buf.ctypes.data_as(C.c_void_p), float(np.sqrt(np.finfo(float).eps)))
+    assert n.value == len(want)
+    assert np.array_equal(buf[:n.value], np.array(want))
+
+
+def test_logpolar_resolves_unit_circle_defect(F):
+    """ln|z| must resolve |z|-1 of a rounded unit-modulus number (needed because the
+    chirp-z kernels scale it by n^2/2 ~ 1e9)."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    L = F.lib()
+    L.fnftb__logpolar.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    for th in [4.8e-6, 0.3, 1.2345, 3.0, -2.2]:
+        z = complex(np.exp(1j * th))
+        lr, li = C.c_double(), C.c_double()
+        L.fnftb__logpolar(z.real, z.imag, C.byref(lr), C.byref(li))
+        x, y = Decimal(z.real), Decimal(z.imag)
+        exact = float((x * x + y * y).ln() / 2)
+        assert abs(lr.value - exact) <= 1e-30 + 1e-12 * abs(exact)
+        assert abs(li.value - th) < 1e-15

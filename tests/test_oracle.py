@@ -1,0 +1,98 @@
+"""Pins the oracle (oracle/fnft_oracle.py) against the reference's own golden vectors
+and against recorded outputs of the unmodified reference library (tests/golden)."""
+import numpy as np
+import pytest
+
+from common import (AKNS_TEST_SCHEMES, CHIRPZ_TEST_A, CHIRPZ_TEST_P, CHIRPZ_TEST_W,
+                    akns_fscatter_test_input, eval_tm, fmult2x2_test_input, rel_err)
+from oracle import fnft_oracle as O
+
+EPS = np.finfo(float).eps
+
+
+@pytest.mark.parametrize("n,key", [(4, "fmult2x2_pow2"), (5, "fmult2x2_nopow2")])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_fmult2x2_reference_golden(golden, n, key, normalize):
+    # test/fnft__poly/fnft__poly_fmult2x2_test_n_is_(no_)power_of_2.c, bound 100*eps (:105)
+    res, deg, W = O.poly_fmult2x2(fmult2x2_test_input(n), normalize)
+    exact = golden["reftest/" + key]
+    assert deg == exact.size // 4 - 1
+    if normalize:
+        assert W != 0
+    assert rel_err((res * 2.0 ** W).reshape(-1), exact) <= 100 * EPS
+
+
+@pytest.mark.parametrize("M", [3, 6])
+def test_chirpz_reference_golden(golden, M):
+    # test/fnft__poly/fnft__poly_chirpz_test.c:24-70, bound 100*eps
+    out = O.poly_chirpz(CHIRPZ_TEST_P, CHIRPZ_TEST_A, CHIRPZ_TEST_W, M)
+    assert rel_err(out, golden[f"reftest/chirpz_M{M}"]) <= 100 * EPS
+
+
+@pytest.mark.parametrize("name", sorted(AKNS_TEST_SCHEMES))
+@pytest.mark.parametrize("normalize", [False, True])
+def test_akns_fscatter_reference_golden(golden, name, normalize):
+    # test/fnft__akns_fscatter/fnft__akns_fscatter_test_<scheme>.c, bound 100*eps
+    q, r, eps_t, z = akns_fscatter_test_input()
+    tm, deg, W = O.akns_fscatter(q, r, eps_t, AKNS_TEST_SCHEMES[name], normalize)
+    got = eval_tm(tm * 2.0 ** W, z)
+    assert rel_err(got, golden[f"reftest/akns_fscatter_{name}"]) <= 100 * EPS
+
+
+def _keys(golden, prefix):
+    return sorted({k[len(prefix):].rsplit("/", 1)[0] for k in golden.files if k.startswith(prefix)})
+
+
+def test_fscatter_vs_reference_runs(golden):
+    for case in _keys(golden, "refrun/fscatter/"):
+        disc, D = map(int, case.split("/"))
+        q = golden[f"refrun/fscatter/{case}/q"]
+        eps = float(golden[f"refrun/fscatter/{case}/eps"])
+        tm, deg, W = O.nse_fscatter(q, eps, 1, disc)
+        ref = golden[f"refrun/fscatter/{case}/tm"]
+        for e in range(4):
+            if np.abs(ref[e]).sum() > 0:
+                assert rel_err(tm[e] * 2.0 ** W, ref[e]) < 1e-12, case
+
+
+def test_nsev_contspec_vs_reference_runs(golden):
+    for case in _keys(golden, "refrun/nsev/"):
+        disc, D, kappa = map(int, case.split("/"))
+        q = golden[f"refrun/nsev/{case}/q"]
+        cs = O.nsev_contspec(q, [-6, 6], 32, [-3.5, 2.75], kappa, disc, cstype=2)
+        ref = golden[f"refrun/nsev/{case}/cs"]
+        for part in range(3):
+            assert rel_err(cs[part * 32:(part + 1) * 32], ref[part * 32:(part + 1) * 32]) < 1e-11, case
+
+
+def test_kdvv_vs_reference_runs(golden):
+    for case in _keys(golden, "refrun/kdvv/"):
+        disc, D = map(int, case.split("/"))
+        u = golden[f"refrun/kdvv/{case}/u"]
+        cs = O.kdvv(u, [-16, 15], 32, [-3.55, 3.95], disc)
+        assert rel_err(cs, golden[f"refrun/kdvv/{case}/cs"]) < 1e-11, case
+
+
+def test_chirpz_and_general_tree_vs_reference_runs(golden):
+    A, W = golden["refrun/chirpz/AW"]
+    out = O.poly_chirpz(golden["refrun/chirpz/p"], A, W, 25)
+    assert rel_err(out, golden["refrun/chirpz/out"]) < 1e-12
+    res, deg, Wn = O.poly_fmult2x2(golden["refrun/fmult2x2_deg3_n5/p"])
+    assert deg == 15
+    assert rel_err((res * 2.0 ** Wn).reshape(-1), golden["refrun/fmult2x2_deg3_n5/res"].reshape(-1)) < 1e-13
+
+
+def test_bound_states_vs_reference_runs(golden):
+    a, ap, b = O.nse_scatter_bound_states(golden["refrun/scatter_bo/q"], [-12, 12],
+                                          golden["refrun/scatter_bo/lam"], 1)
+    assert rel_err(a, golden["refrun/scatter_bo/a"]) < 1e-12
+    assert rel_err(ap, golden["refrun/scatter_bo/ap"]) < 1e-12
+    assert rel_err(b, golden["refrun/scatter_bo/b"]) < 1e-10
+    for disc in (11, 21):
+        q = golden[f"refrun/bound/{disc}/q"]
+        bs, nc = O.nsev_bound_states_newton(q, [-12, 12], golden[f"refrun/bound/{disc}/guesses"],
+                                            disc, niter=10, bsfilt=2, dstype=2)
+        ref_bs = golden[f"refrun/bound/{disc}/bs"]
+        assert len(bs) == len(ref_bs) == 3          # two guesses merge into one eigenvalue
+        assert np.abs(bs - ref_bs).max() < 1e-12
+        assert rel_err(nc, golden[f"refrun/bound/{disc}/nc"]) < 1e-9
