@@ -44,6 +44,7 @@ static inline int cz_run(CzArgs a, fnftb_stream_t st, int row_n = FNFTB_CZ_ROW_N
     a.N1 = g.N1;
     a.N2 = g.N2;
     a.C = g.C;
+    a.log2C = ilog2i((unsigned)g.C);
     a.plan1 = make_fft_plan(g.N1);
     a.plan2 = make_fft_plan(g.N2);
     const int nt = 256;

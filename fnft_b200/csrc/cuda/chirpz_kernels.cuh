@@ -29,7 +29,8 @@ struct CzArgs {
     int deg;
     int B, M;
     int L, N1, N2;
-    int C;           // columns per CTA in the column kernels
+    int C;           // columns per CTA in the column kernels (power of two)
+    int log2C;
     FftPlan plan1, plan2;
     double lwr, lwi; // ln|W|, arg W
     double lar, lai; // ln|A|, arg A
@@ -86,7 +87,7 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
     FOR_THREADS(tid, nt)
     {
         for (int idx = tid; idx < C * N1; idx += nt) {
-            const int c = idx % C, n1 = idx / C;
+            const int c = idx & (C - 1), n1 = idx >> a.log2C;
             const long long n = (long long)n1 * N2 + n2_0 + c;
             cplx v = czero();
             if (!a.gen_v) {
@@ -112,14 +113,15 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
     }
     BLOCK_SYNC();
     FNFTB_SMEM_FFT_FWD(S, C, a.plan1, nt, a.T);
+    BLOCK_SYNC();
     FOR_THREADS(tid, nt)
     {
         cplx *dst = (a.gen_v ? a.vhat : a.ybuf + (size_t)sj * a.L);
         for (int idx = tid; idx < C * N1; idx += nt) {
-            const int c = idx % C, pos = idx / C;
+            const int c = idx & (C - 1), pos = idx >> a.log2C;
             const int k1 = plan_freq_of_pos(a.plan1, pos);
             const int n2 = n2_0 + c;
-            const cplx w = cispi(-2.0 * (double)(((long long)n2 * k1) % a.L) / (double)a.L);
+            const cplx w = cispi(-2.0 * (double)(((long long)n2 * k1) & (long long)(a.L - 1)) / (double)a.L);
             dst[(size_t)pos * N2 + n2] = cmul(S[(size_t)c * N1 + swz(pos)], w);
         }
     }
@@ -139,6 +141,7 @@ BLK void blk_cz_rows(const CzArgs &a, blk3 bid, int nt, void *smem)
     }
     BLOCK_SYNC();
     FNFTB_SMEM_FFT_FWD(S, 1, a.plan2, nt, a.T);
+    BLOCK_SYNC();
     if (a.fwd_only) {
         FOR_THREADS(tid, nt)
         {
@@ -155,6 +158,7 @@ BLK void blk_cz_rows(const CzArgs &a, blk3 bid, int nt, void *smem)
     }
     BLOCK_SYNC();
     FNFTB_SMEM_FFT_INV(S, 1, a.plan2, nt, a.T);
+    BLOCK_SYNC();
     FOR_THREADS(tid, nt)
     {
         for (int i = tid; i < N2; i += nt)
@@ -177,21 +181,22 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
         for (int j = 0; j < a.npoly; ++j) {
             const cplx *src = a.ybuf + ((size_t)s * a.npoly + j) * a.L;
             for (int idx = tid; idx < C * N1; idx += nt) {
-                const int c = idx % C, pos = idx / C;
+                const int c = idx & (C - 1), pos = idx >> a.log2C;
                 const int k1 = plan_freq_of_pos(a.plan1, pos);
                 const int n2 = n2_0 + c;
-                const cplx w = cispi(2.0 * (double)(((long long)n2 * k1) % a.L) / (double)a.L);
+                const cplx w = cispi(2.0 * (double)(((long long)n2 * k1) & (long long)(a.L - 1)) / (double)a.L);
                 S[((size_t)j * C + c) * N1 + swz(pos)] = cmul(src[(size_t)pos * N2 + n2], w);
             }
         }
     }
     BLOCK_SYNC();
     FNFTB_SMEM_FFT_INV(S, C * a.npoly, a.plan1, nt, a.T);
+    BLOCK_SYNC();
     FOR_THREADS(tid, nt)
     {
         const double invL = 1.0 / (double)a.L;
         for (int idx = tid; idx < C * N1; idx += nt) {
-            const int c = idx % C, n1 = idx / C;
+            const int c = idx & (C - 1), n1 = idx >> a.log2C;
             const long long m = (long long)n1 * N2 + n2_0 + c;
             if (m >= a.M)
                 continue;

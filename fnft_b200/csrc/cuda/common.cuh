@@ -21,6 +21,7 @@
 #define BLK inline
 #define FOR_THREADS(tid, nt) for (int tid = 0; tid < (nt); ++tid)
 #define BLOCK_SYNC() ((void)0)
+#define TEAM_SYNC(ts, nt) ((void)0)
 #define LDG(p) (*(p))
 struct cplx {
     double x, y;
@@ -52,6 +53,19 @@ static inline void emul_sincospi(double a, double *s, double *c)
 // Runs the body exactly once with tid = threadIdx.x.
 #define FOR_THREADS(tid, nt) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
 #define BLOCK_SYNC() __syncthreads()
+// Barrier among the `ts` consecutive threads of the caller's team (ts a multiple of 32
+// dividing nt).  One warp: __syncwarp; the whole CTA: __syncthreads; otherwise a named
+// barrier (ids 1..15, so at most 15 teams).
+#define TEAM_SYNC(ts, nt)                                                            \
+    do {                                                                             \
+        if ((ts) == 32) {                                                            \
+            __syncwarp();                                                            \
+        } else if ((ts) >= (nt)) {                                                   \
+            __syncthreads();                                                         \
+        } else {                                                                     \
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / (ts)), "r"(ts) : "memory"); \
+        }                                                                            \
+    } while (0)
 #ifdef __CUDA_ARCH__
 #define LDG(p) __ldg(p)
 #else

@@ -101,6 +101,17 @@ struct fnftb_ctx {
     int have_box3 = 0;
 };
 
+static TwTable ctx_tw(const fnftb_ctx *c)
+{
+    TwTable T;
+    T.tw = c->tw;
+    T.twn = c->twn;
+    T.log2twn = 0;
+    while ((1 << T.log2twn) < c->twn)
+        ++T.log2twn;
+    return T;
+}
+
 static int ensure(Buf &b, size_t bytes)
 {
     if (bytes <= b.cap)
@@ -327,9 +338,7 @@ int fnftb_fscatter(fnftb_ctx *c, const fnftb_scatter_desc *d)
     if ((size_t)d->deg0 * npad > ((size_t)1 << 22))
         return fail(-6, "signal too long for this build", __FILE__, __LINE__);
     RC(ensure_tree(c, c->B, npad, (size_t)d->deg0, deg_out));
-    TwTable T;
-    T.tw = c->tw;
-    T.twn = c->twn;
+    const TwTable T = ctx_tw(c);
     RC(tree_fscatter(tree_work(c), c->q, c->r, (int)c->B, (int)c->D, d->deg0, d->rmode, d->kappa,
                      d->scheme, d->eps_t, d->normalize, (cplx *)c->tm.p, T, c->st));
     c->deg = deg_out;
@@ -350,9 +359,7 @@ int fnftb_fmult2x2(fnftb_ctx *c, size_t deg, size_t n, const void *p_host, int n
     const size_t bytes = 4 * n * (deg + 1) * sizeof(cplx);
     RC(ensure(c->pbuf, bytes));
     CU(cudaMemcpyAsync(c->pbuf.p, p_host, bytes, cudaMemcpyHostToDevice, c->st));
-    TwTable T;
-    T.tw = c->tw;
-    T.twn = c->twn;
+    const TwTable T = ctx_tw(c);
     RC(tree_fmult2x2(tree_work(c), (const cplx *)c->pbuf.p, (int)n, (int)deg, normalize,
                      (cplx *)c->tm.p, T, c->st));
     c->deg = deg * n;
@@ -441,8 +448,7 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
     a.lai = d->lai;
     a.ybuf = (cplx *)c->ybuf.p;
     a.vhat = (cplx *)c->vhat.p;
-    a.T.tw = c->tw;
-    a.T.twn = c->twn;
+    a.T = ctx_tw(c);
     a.mode = d->mode;
     a.cstype = d->cstype;
     a.out = dst;
@@ -605,8 +611,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
             }
             a.ybuf = (cplx *)c->ybuf.p;
             a.vhat = (cplx *)c->vhat.p;
-            a.T.tw = c->tw;
-            a.T.twn = c->twn;
+            a.T = ctx_tw(c);
             a.mode = FNFTB_CZ_RAW;
             a.out = (cplx *)c->vals.p + (size_t)(k + 1) * Mpts;
             a.out_sstride = (size_t)npoly * 3 * Mpts;
@@ -700,8 +705,7 @@ int fnftb_resample_4split4(fnftb_ctx *c, double eps_t, int32_t *warn_host)
     ra.D = (int)D;
     ra.eps_t = eps_t;
     ra.plan = make_fft_plan((int)D);
-    ra.T.tw = c->tw;
-    ra.T.twn = c->twn;
+    ra.T = ctx_tw(c);
     const int nt = 256;
     RC((launch_blocks<ResampleArgs, blk_resample_4split4>(ra, (unsigned)c->B, nt,
                                                           resample_smem_bytes((int)D, nt), c->st, "resample_4split4")));

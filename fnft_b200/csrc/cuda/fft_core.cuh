@@ -117,15 +117,30 @@ HD int swz(int i) { return i ^ ((i >> 3) & 7); }
 struct TwTable {
     const cplx *tw;
     int twn;
+    int log2twn;
 };
 
 // w = exp(-2*pi*i * m / len) from the table (len divides twn), DIR selects conj
 template <int DIR>
-HD cplx tw_lookup(const TwTable &T, int m, int len)
+HD cplx tw_lookup(const TwTable &T, int m, int log2len)
 {
-    const cplx w = LDG(&T.tw[(size_t)m * (size_t)(T.twn / len)]);
+    const cplx w = LDG(&T.tw[m << (T.log2twn - log2len)]);
     return (DIR > 0) ? cconj(w) : w;
 }
+
+// compile-time log2 of the radix
+template <int R>
+struct Log2R {
+    static const int value = (R <= 1) ? 0 : 1 + Log2R<R / 2>::value;
+};
+template <>
+struct Log2R<1> {
+    static const int value = 0;
+};
+template <>
+struct Log2R<0> {
+    static const int value = 0;
+};
 
 // ---------------------------------------------------------------------------
 // one radix-R butterfly of an in-place pass over the array S (one FFT)
@@ -140,8 +155,8 @@ HD void fft_pass_butterfly(cplx *S, int u, int log2s, const TwTable &T)
     const int s = 1 << log2s;
     const int g = u >> log2s;
     const int o = u & (s - 1);
-    const int base = g * (R * s) + o;
-    const int len = R * s;
+    const int base = (g << (Log2R<R>::value + log2s)) + o;
+    const int len = Log2R<R>::value + log2s;  // log2 of the sub-transform length
     cplx v[R];
 #pragma unroll
     for (int j = 0; j < R; ++j)
@@ -171,7 +186,7 @@ template <int R, int DIR>
 HD void fft_pass_all(cplx *S, int nfft, int log2n, int log2s, int tid, int nt,
                      const TwTable &T)
 {
-    const int log2bpf = log2n - ilog2i(R);  // butterflies per FFT (log2)
+    const int log2bpf = log2n - Log2R<R>::value;  // butterflies per FFT (log2)
     const int nb = nfft << log2bpf;
     for (int b = tid; b < nb; b += nt) {
         const int f = b >> log2bpf;
@@ -253,19 +268,75 @@ HD int plan_freq_of_pos(const FftPlan &P, int pos)
     return k;
 }
 
+// ---------------------------------------------------------------------------
+// team-scheduled transforms: the CTA is split into teams of `ts` consecutive threads
+// (ts = fft_team_size(n, nt)); team t owns the transforms [t*fpt, (t+1)*fpt) for all
+// passes, so passes only need a barrier among the team's threads and the teams drift
+// apart, overlapping each other's load / compute / store phases.
+// ---------------------------------------------------------------------------
+HD int fft_team_size(int n, int nt)
+{
+    int ts = n / 16;
+    if (ts < 32)
+        ts = 32;
+    while (ts < nt && nt / ts > 15 && ts > 32)  // named barriers: at most 15 teams
+        ts *= 2;
+    if (ts > nt)
+        ts = nt;
+    return ts;
+}
+
+template <int R, int DIR>
+HD void fft_pass_team(cplx *S, int f0, int nf, int log2n, int log2s, int lane, int ts,
+                      const TwTable &T)
+{
+    const int log2bpf = log2n - Log2R<R>::value;
+    const int nb = nf << log2bpf;
+    for (int b = lane; b < nb; b += ts) {
+        const int f = f0 + (b >> log2bpf);
+        const int u = b & ((1 << log2bpf) - 1);
+        fft_pass_butterfly<R, DIR>(S + ((size_t)f << log2n), u, log2s, T);
+    }
+}
+
+template <int DIR>
+HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, int tid, int nt,
+                               int ts, const TwTable &T)
+{
+    const int nteams = nt / ts;
+    const int team = tid / ts, lane = tid - team * ts;
+    const int fpt = (nfft + nteams - 1) / nteams;
+    const int f0 = team * fpt;
+    int nf = nfft - f0;
+    if (nf > fpt)
+        nf = fpt;
+    if (nf <= 0)
+        return;
+    switch (R) {
+    case 16: fft_pass_team<16, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
+    case 8: fft_pass_team<8, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
+    case 4: fft_pass_team<4, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
+    case 2: fft_pass_team<2, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
+    default: break;
+    }
+}
+
 // In-place forward transforms of `nfft` arrays of length P.n (shared memory).
-// Must be called by all threads of the block program (contains BLOCK_SYNCs).
+// Must be called by all threads of the block program.  On return the team's own
+// transforms are complete (team barrier); callers that read other teams' data must
+// BLOCK_SYNC() first.
 #define FNFTB_SMEM_FFT_FWD(S, nfft, P, nt, T)                                         \
     do {                                                                              \
         int _l2s = (P).log2n;                                                         \
+        const int _ts = fft_team_size((P).n, nt);                                     \
         for (int _p = 0; _p < (P).npass; ++_p) {                                      \
             const int _R = (P).radix[_p];                                             \
             _l2s -= ilog2i(_R);                                                       \
             FOR_THREADS(tid, nt)                                                      \
             {                                                                         \
-                fft_pass_dispatch<-1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, T);  \
+                fft_pass_team_dispatch<-1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, _ts, T); \
             }                                                                         \
-            BLOCK_SYNC();                                                             \
+            TEAM_SYNC(_ts, nt);                                                       \
         }                                                                             \
     } while (0)
 
@@ -273,13 +344,14 @@ HD int plan_freq_of_pos(const FftPlan &P, int pos)
 #define FNFTB_SMEM_FFT_INV(S, nfft, P, nt, T)                                         \
     do {                                                                              \
         int _l2s = 0;                                                                 \
+        const int _ts = fft_team_size((P).n, nt);                                     \
         for (int _p = (P).npass - 1; _p >= 0; --_p) {                                 \
             const int _R = (P).radix[_p];                                             \
             FOR_THREADS(tid, nt)                                                      \
             {                                                                         \
-                fft_pass_dispatch<+1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, T);  \
+                fft_pass_team_dispatch<+1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, _ts, T); \
             }                                                                         \
-            BLOCK_SYNC();                                                             \
+            TEAM_SYNC(_ts, nt);                                                       \
             _l2s += ilog2i(_R);                                                       \
         }                                                                             \
     } while (0)

@@ -40,6 +40,7 @@ BLK void blk_resample_4split4(const ResampleArgs &a, blk3 bid, int nt, void *sme
     }
     BLOCK_SYNC();
     FNFTB_SMEM_FFT_FWD(S1, 1, a.plan, nt, a.T);
+    BLOCK_SYNC();
     // band-limitation check (fnft__misc.c:368-380): trapezoidal |X|^2 sums over the
     // two 5% bands next to the Nyquist bin versus the whole spectrum
     const int Dlp = D / 20;
@@ -96,6 +97,7 @@ BLK void blk_resample_4split4(const ResampleArgs &a, blk3 bid, int nt, void *sme
     }
     BLOCK_SYNC();
     FNFTB_SMEM_FFT_INV(S1, 2, a.plan, nt, a.T);
+    BLOCK_SYNC();
     FOR_THREADS(tid, nt)
     {
         const double sf = 1.7320508075688772 / 6.0;

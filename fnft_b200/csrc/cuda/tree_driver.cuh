@@ -87,9 +87,11 @@ template <int R>
 static inline int launch_combine(const PairArgs &pa, fnftb_stream_t st)
 {
     const long long total = (long long)pa.B * (pa.n_in / 2) * 4 * pa.N2;
-    const int nt = 128;
-    return launch_blocks<PairArgs, blk_pair_combine<R>, 128>(pa, (unsigned)((total + nt - 1) / nt), nt,
-                                                        0, st, "tree_pair_combine");
+    int nt = 128;
+    if (nt > pa.N2)
+        nt = pa.N2;  // a CTA must stay inside one (signal, pair, entry)
+    return launch_blocks<PairArgs, blk_pair_combine<R>, 128>(pa, (unsigned)(total / nt), nt,
+                                                        sizeof(double) * nt, st, "tree_pair_combine");
 }
 
 // Runs all levels.  On entry level buffer 0 holds npad matrices of degree deg0
@@ -145,6 +147,8 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                 if (G > npairs)
                     G = npairs;
                 pa.G = G;
+                pa.log2G = ilog2i((unsigned)G);
+                pa.log2N2 = ilog2i((unsigned)N);
                 pa.plan = make_fft_plan(N);
                 int nt = (8 * G * N) / 16;
                 if (nt > 512)
@@ -158,6 +162,8 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                 pa.R = N / smem_n;
                 pa.N2 = smem_n;
                 pa.G = 1;
+                pa.log2G = 0;
+                pa.log2N2 = ilog2i((unsigned)smem_n);
                 pa.plan = make_fft_plan(smem_n);
                 int nt = (8 * smem_n) / 16;
                 if (nt > 512)

@@ -284,7 +284,8 @@ struct PairArgs {
     int N;        // cyclic convolution length (power of two, >= 2*d_in)
     int wrap;     // 1 if N == 2*d_in (top coefficient handled analytically)
     int R, N2;    // N = R * N2; R == 1: whole product inside one CTA
-    int G;        // pairs per CTA (R == 1)
+    int G;        // pairs per CTA (R == 1), a power of two
+    int log2N2, log2G;
     FftPlan plan; // plan for length N2
     TwTable T;
 };
@@ -417,45 +418,66 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
     BLOCK_SYNC();
 
     // phase A: load (and for R > 1 fold the radix-R column step into the load)
+    const int l2n = a.log2N2, l2g = a.log2G;
+    if (R > 1) {
+        // w_R^(n1*k1) for n1 < R/2, shared by all elements of this CTA (kept in `red`,
+        // which is not used before phase E)
+        FOR_THREADS(tid, nt)
+        {
+            for (int n1 = tid; n1 < R / 2; n1 += nt) {
+                const cplx w = cispi(-2.0 * (double)((n1 * k1) % R) / (double)R);
+                red[2 * n1] = w.x;
+                red[2 * n1 + 1] = w.y;
+            }
+        }
+        BLOCK_SYNC();
+    }
     FOR_THREADS(tid, nt)
     {
         if (R == 1) {
-            const int total = 8 * G * N2;
+            const int total = (8 * G) << l2n;
             for (int idx = tid; idx < total; idx += nt) {
-                const int i = idx % N2;
-                const int pg = idx / N2;  // p*G + g
-                const int g = pg % G, p = pg / G;
+                const int i = idx & (N2 - 1);
+                const int pg = idx >> l2n;  // p*G + g
+                const int g = pg & (G - 1), p = pg >> l2g;
                 const int pair = pair0 + g;
                 cplx v = czero();
                 if (pair < npairs && i < nbody) {
                     const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> 2);
                     v = cscale(a.in[(mat * 4 + (p & 3)) * din1 + i], sc[(p >> 2) * G + g]);
                 }
-                S[(size_t)pg * N2 + swz(i)] = v;
+                S[((size_t)pg << l2n) + swz(i)] = v;
             }
         } else {
             // y[n2] = w_N^(n2*k1) * sum_{n1<R/2} x[n1*N2+n2] * w_R^(n1*k1)
             const int half = R / 2;
+            const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair0;
+            const cplx *xbase = a.in + matA * 4 * din1;
             for (int n2 = tid; n2 < N2; n2 += nt) {
-                const cplx wn = cispi(-2.0 * (double)(((long long)n2 * k1) % a.N) / (double)a.N);
-                for (int p = 0; p < 8; ++p) {
-                    const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair0 + (p >> 2);
-                    const cplx *x = a.in + (mat * 4 + (p & 3)) * din1;
-                    cplx acc = czero();
-                    for (int n1 = 0; n1 < half; ++n1) {
-                        const int i = n1 * N2 + n2;
-                        if (i >= nbody)
-                            break;
-                        const cplx wr = cispi(-2.0 * (double)((n1 * k1) % R) / (double)R);
-                        cfma(acc, x[i], wr);
-                    }
-                    S[(size_t)p * N2 + swz(n2)] = cscale(cmul(acc, wn), sc[(p >> 2) * G]);
+                const cplx wn = cispi(-2.0 * (double)((n2 * k1) & (a.N - 1)) / (double)a.N);
+                cplx acc[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    acc[p] = czero();
+                // 8 independent loads per n1 (the 8 operand polynomials of the pair)
+#pragma unroll 2
+                for (int n1 = 0; n1 < half; ++n1) {
+                    const int i = (n1 << l2n) + n2;
+                    if (i >= nbody)
+                        break;
+                    const cplx w = make_cplx(red[2 * n1], red[2 * n1 + 1]);
+#pragma unroll
+                    for (int p = 0; p < 8; ++p)
+                        cfma(acc[p], xbase[(size_t)p * din1 + i], w);
                 }
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    S[((size_t)p << l2n) + swz(n2)] = cscale(cmul(acc[p], wn), sc[(p >> 2) * G]);
             }
         }
         // top coefficients (only used when wrap)
         for (int pg = tid; pg < 8 * G; pg += nt) {
-            const int g = pg % G, p = pg / G;
+            const int g = pg & (G - 1), p = pg >> l2g;
             const int pair = pair0 + g;
             cplx v = czero();
             if (a.wrap && pair < npairs) {
@@ -469,15 +491,16 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
 
     // phase B: 8*G forward transforms of length N2
     FNFTB_SMEM_FFT_FWD(S, 8 * G, a.plan, nt, a.T);
+    BLOCK_SYNC();
 
     // phase C: pointwise 2x2 products; results overwrite the A-side arrays
     const int fs = plan_first_stride_log2(a.plan);
     FOR_THREADS(tid, nt)
     {
-        const int total = G * N2;
+        const int total = G << l2n;
         for (int idx = tid; idx < total; idx += nt) {
-            const int pos = idx % N2;
-            const int g = idx / N2;
+            const int pos = idx & (N2 - 1);
+            const int g = idx >> l2n;
             double sgn = 0.0;  // (-1)^k of the true frequency index k of this bin
             if (a.wrap) {
                 if (R == 1)
@@ -490,7 +513,7 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
                 const cplx t = top[p * G + g];
-                const cplx x = S[((size_t)p * G + g) * N2 + ph];
+                const cplx x = S[((size_t)(p * G + g) << l2n) + ph];
                 v[p] = make_cplx(x.x + sgn * t.x, x.y + sgn * t.y);
             }
             // [A11 A12; A21 A22] * [B11 B12; B21 B22], A = v[0..3], B = v[4..7]
@@ -502,16 +525,17 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
             cfma(c21, v[3], v[6]);
             cplx c22 = cmul(v[2], v[5]);
             cfma(c22, v[3], v[7]);
-            S[((size_t)0 * G + g) * N2 + ph] = c11;
-            S[((size_t)1 * G + g) * N2 + ph] = c12;
-            S[((size_t)2 * G + g) * N2 + ph] = c21;
-            S[((size_t)3 * G + g) * N2 + ph] = c22;
+            S[((size_t)(0 * G + g) << l2n) + ph] = c11;
+            S[((size_t)(1 * G + g) << l2n) + ph] = c12;
+            S[((size_t)(2 * G + g) << l2n) + ph] = c21;
+            S[((size_t)(3 * G + g) << l2n) + ph] = c22;
         }
     }
     BLOCK_SYNC();
 
     // phase D: 4*G inverse transforms
     FNFTB_SMEM_FFT_INV(S, 4 * G, a.plan, nt, a.T);
+    BLOCK_SYNC();
 
     // phase E: write out
     if (R > 1) {
@@ -519,8 +543,8 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
         {
             cplx *gb = a.gbuf + (((size_t)s * npairs + pair0) * 4) * (size_t)R * N2;
             for (int idx = tid; idx < 4 * N2; idx += nt) {
-                const int n2 = idx % N2, e = idx / N2;
-                gb[((size_t)e * R + k1) * N2 + n2] = S[(size_t)e * N2 + swz(n2)];
+                const int n2 = idx & (N2 - 1), e = idx >> l2n;
+                gb[((size_t)(e * R + k1) << l2n) + n2] = S[((size_t)e << l2n) + swz(n2)];
             }
         }
         return;
@@ -550,18 +574,22 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
             }
             cplx *o = a.out + ((size_t)s * npairs + pair) * 4 * dout1;
             double m2 = 0.0;
-            for (int idx = tid; idx < 4 * dout1; idx += nt) {
-                const int i = idx % dout1, e = idx / dout1;
-                cplx v;
-                if (a.wrap && i == a.N) {
-                    v = ct[e];
-                } else {
-                    v = cscale(S[((size_t)e * G + g) * N2 + swz(i)], invN);
-                    if (a.wrap && i == 0)
-                        v = csub(v, ct[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const cplx *Se = S + ((size_t)(e * G + g) << l2n);
+                cplx *oe = o + (size_t)e * dout1;
+                for (int i = tid; i < dout1; i += nt) {
+                    cplx v;
+                    if (a.wrap && i == a.N) {
+                        v = ct[e];
+                    } else {
+                        v = cscale(Se[swz(i)], invN);
+                        if (a.wrap && i == 0)
+                            v = csub(v, ct[e]);
+                    }
+                    oe[i] = v;
+                    m2 = fmax(m2, cabs2(v));
                 }
-                o[idx] = v;
-                m2 = fmax(m2, cabs2(v));
             }
             red[tid] = m2;
         }
@@ -580,65 +608,81 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
 }
 
 // Finishes a row-split product: radix-R inverse column step, 1/N scaling, wrap
-// correction, max|coeff|.  One thread per (signal, pair, entry, n2).
+// correction, max|coeff|.  One thread per (signal, pair, entry, n2); a CTA covers nt
+// consecutive n2 of ONE (signal, pair, entry) (nt divides N2), so the max is reduced
+// in shared memory and published with a single atomic per CTA.
 template <int R>
-BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void * /*smem*/)
+BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void *smem)
 {
+    double *red = (double *)smem;
+    const int npairs = a.n_in / 2;
+    const int N2 = a.N2;
+    const long long gid0 = (long long)bid.x * nt;
+    const long long spe = gid0 >> a.log2N2;  // (s*npairs + pair)*4 + e
+    const int e = (int)(spe & 3);
+    const long long sp = spe >> 2;
+    const int s = (int)(sp / npairs);
+    const int pair = (int)(sp % npairs);
     FOR_THREADS(tid, nt)
     {
-        const int npairs = a.n_in / 2;
-        const int N2 = a.N2;
-        const long long gid = (long long)bid.x * nt + tid;
-        const long long total = (long long)a.B * npairs * 4 * N2;
-        if (gid < total) {
-            const int n2 = (int)(gid % N2);
-            const long long spe = gid / N2;  // (s*npairs + pair)*4 + e
-            const int e = (int)(spe & 3);
-            const long long sp = spe >> 2;
-            const int s = (int)(sp / npairs);
-            const int pair = (int)(sp % npairs);
-            const cplx *gb = a.gbuf + (size_t)spe * R * N2;
-            cplx v[R];
+        const int n2 = (int)((gid0 + tid) & (N2 - 1));
+        const cplx *gb = a.gbuf + (((size_t)spe * R) << a.log2N2);
+        cplx v[R];
+        {
+            // w_N^(-k1*n2) by recurrence from w_N^(-n2) (R <= 64 steps)
+            const cplx w1 = cispi(2.0 * (double)n2 / (double)a.N);
+            cplx w = make_cplx(1.0, 0.0);
 #pragma unroll
             for (int k1 = 0; k1 < R; ++k1) {
-                const cplx w = cispi(2.0 * (double)(((long long)k1 * n2) % a.N) / (double)a.N);
-                v[k1] = cmul(gb[(size_t)k1 * N2 + n2], w);
+                v[k1] = cmul(gb[((size_t)k1 << a.log2N2) + n2], w);
+                w = cmul(w, w1);
             }
-            Dft<R, +1>::run(v);
-            const int dout1 = 2 * a.d_in + 1;  // == N + 1 when wrap, <= N otherwise
-            const int din1 = a.d_in + 1;
-            cplx *o = a.out + (size_t)spe * dout1;
-            const double invN = 1.0 / (double)a.N;
-            double m2 = 0.0;
-            cplx ct = czero();
-            if (n2 == 0 && a.wrap) {
-                // product of the top coefficients of row (e>>1) of A and column (e&1) of B
-                const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair;
-                int eA, eB;
-                const double sA = load_scale(a, matA, &eA), sB = load_scale(a, matA + 1, &eB);
-                const cplx *A = a.in + matA * 4 * din1;
-                const cplx *Bm = A + 4 * din1;
-                const int row = e >> 1, col = e & 1;
-                const cplx a0 = cscale(A[(row * 2 + 0) * din1 + a.d_in], sA);
-                const cplx a1 = cscale(A[(row * 2 + 1) * din1 + a.d_in], sA);
-                const cplx b0 = cscale(Bm[(0 * 2 + col) * din1 + a.d_in], sB);
-                const cplx b1 = cscale(Bm[(1 * 2 + col) * din1 + a.d_in], sB);
-                ct = cmul(a0, b0);
-                cfma(ct, a1, b1);
-                o[a.N] = ct;
-                m2 = cabs2(ct);
-            }
+        }
+        Dft<R, +1>::run(v);
+        const int dout1 = 2 * a.d_in + 1;  // == N + 1 when wrap, <= N otherwise
+        const int din1 = a.d_in + 1;
+        cplx *o = a.out + (size_t)spe * dout1;
+        const double invN = 1.0 / (double)a.N;
+        double m2 = 0.0;
+        cplx ct = czero();
+        if (n2 == 0 && a.wrap) {
+            // product of the top coefficients of row (e>>1) of A and column (e&1) of B
+            const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair;
+            int eA, eB;
+            const double sA = load_scale(a, matA, &eA), sB = load_scale(a, matA + 1, &eB);
+            const cplx *A = a.in + matA * 4 * din1;
+            const cplx *Bm = A + 4 * din1;
+            const int row = e >> 1, col = e & 1;
+            const cplx a0 = cscale(A[(row * 2 + 0) * din1 + a.d_in], sA);
+            const cplx a1 = cscale(A[(row * 2 + 1) * din1 + a.d_in], sA);
+            const cplx b0 = cscale(Bm[(0 * 2 + col) * din1 + a.d_in], sB);
+            const cplx b1 = cscale(Bm[(1 * 2 + col) * din1 + a.d_in], sB);
+            ct = cmul(a0, b0);
+            cfma(ct, a1, b1);
+            o[a.N] = ct;
+            m2 = cabs2(ct);
+        }
 #pragma unroll
-            for (int n1 = 0; n1 < R; ++n1) {
-                const int i = n1 * N2 + n2;
-                if (i >= dout1)
-                    break;
-                cplx c = cscale(v[n1], invN);
-                if (i == 0)
-                    c = csub(c, ct);  // ct == 0 unless wrap
-                o[i] = c;
-                m2 = fmax(m2, cabs2(c));
-            }
+        for (int n1 = 0; n1 < R; ++n1) {
+            const int i = (n1 << a.log2N2) + n2;
+            if (i >= dout1)
+                break;
+            cplx c = cscale(v[n1], invN);
+            if (i == 0)
+                c = csub(c, ct);  // ct == 0 unless wrap
+            o[i] = c;
+            m2 = fmax(m2, cabs2(c));
+        }
+        red[tid] = m2;
+    }
+    BLOCK_SYNC();
+    FOR_THREADS(tid, nt)
+    {
+        // tree reduction over the CTA, then one atomic
+        if (tid == 0) {
+            double m2 = 0.0;
+            for (int t = 0; t < nt; ++t)
+                m2 = fmax(m2, red[t]);
             atomic_max_double(&a.mx_out[sp], sqrt(m2));
         }
     }

@@ -47,16 +47,23 @@ def sech_chirp(D, T, amp=2.0, chirp=0.3):
     return amp / np.cosh(t) * np.exp(1j * chirp * t * t)
 
 
-def parity_contract(ours, ref, tol=1e-9):
-    """(i) L1-relative error, (ii) pointwise on |ref| >= 1e-6 max,
-    (iii) absolute on the tails.  Returns the three figures normalised by tol."""
+def parity_contract(ours, ref, tol=1e-9, floor=1e-2):
+    """The parity contract of this repository ("Parity contract"), derived
+    from SURVEY.md 8(c).  Returns two figures normalised by `tol`; both must be < 1:
+      (i)  misc_rel_err(ours, ref) = sum|d| / sum|ref|                  (the reference's
+           own comparison metric, src/private/fnft__misc.c:41-51)
+      (ii) pointwise  |d| <= tol * (|ref| + floor * max|ref|)
+    The additive term of (ii) is the reference's OWN accuracy floor: its chirp-z forms
+    the chirp with cpow(W, n^2/2), whose phase error (~1e-16 * n^2/2 * arg W rad) gives
+    every output an absolute error of order 1e-12..1e-11 * max|.|.  Where |ref| is small
+    the reference is therefore only accurate to ~1e-8 relative (demonstrated against a
+    long-double evaluation in tests/test_oracle.py::test_reference_accuracy_floor), and a
+    purely relative 1e-9 bound against it is not a meaningful target there."""
     ours, ref = np.asarray(ours), np.asarray(ref)
     mx = np.abs(ref).max()
-    big = np.abs(ref) >= 1e-6 * mx
     e1 = rel_err(ours, ref)
-    e2 = (np.abs(ours - ref)[big] / np.abs(ref)[big]).max() if big.any() else 0.0
-    e3 = (np.abs(ours - ref)[~big]).max() / mx if (~big).any() else 0.0
-    return e1 / tol, e2 / tol, e3 / tol
+    e2 = (np.abs(ours - ref) / (np.abs(ref) + floor * mx)).max()
+    return e1 / tol, e2 / tol
 
 
 # ---------------------------------------------------------------------------------

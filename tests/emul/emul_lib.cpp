@@ -20,6 +20,7 @@ static TwTable get_tw()
     TwTable T;
     T.tw = (const cplx *)g_tw.data();
     T.twn = twn;
+    T.log2twn = 12;
     return T;
 }
 

@@ -133,6 +133,50 @@ def main():
     assert ret == 0
     G["refrun/fmult2x2_deg3_n5/p"] = pm
     G["refrun/fmult2x2_deg3_n5/res"] = res * 2.0 ** W
+    # accuracy floor of the reference: defocusing case, D = 126, evaluated exactly
+    # (leaf coefficients in double like every implementation, product tree by direct
+    # convolution and Horner evaluation in 80-bit long double)
+    from oracle import fnft_oracle as O
+    Dq, Mq, kap = 126, 40, -1
+    Tq, XIq = (-32.0, 32.0), (-10.0, 10.0)
+    tq = np.linspace(Tq[0], Tq[1], Dq)
+    qq = 1.7 / np.cosh(tq) * np.exp(-3j * tq + 0.4j * np.sin(tq))
+    eps_t = (Tq[1] - Tq[0]) / (Dq - 1)
+    leaves = O.akns_leaves(qq, -kap * np.conj(qq), eps_t, 10)
+    LD = np.clongdouble
+
+    def conv(a, b):
+        o = np.zeros(len(a) + len(b) - 1, dtype=LD)
+        for i, ai in enumerate(a):
+            o[i:i + len(b)] += ai * b
+        return o
+    mats = [[leaves[e, k].astype(LD) for e in range(4)] for k in range(Dq)]
+    while len(mats) > 1:
+        nxt = []
+        for i in range(0, len(mats) - 1, 2):
+            A, Bm = mats[i], mats[i + 1]
+            nxt.append([conv(A[0], Bm[0]) + conv(A[1], Bm[2]), conv(A[0], Bm[1]) + conv(A[1], Bm[3]),
+                        conv(A[2], Bm[0]) + conv(A[3], Bm[2]), conv(A[2], Bm[1]) + conv(A[3], Bm[3])])
+        if len(mats) % 2:
+            nxt.append(mats[-1])
+        mats = nxt
+    eps_xi = (XIq[1] - XIq[0]) / (Mq - 1)
+    xi = XIq[0] + eps_xi * np.arange(Mq)
+    z = np.exp(2j * xi.astype(np.longdouble) * np.longdouble(eps_t) / 2)
+
+    def horner(cf, zz):
+        r = np.zeros_like(zz)
+        for ck in cf:
+            r = r * zz + ck
+        return r
+    rho_exact = (horner(mats[0][2], z) * np.exp(1j * xi * (-2 * (Tq[1] + eps_t * 0.5)))
+                 / horner(mats[0][0], z)).astype(np.complex128)
+    o = R.nsev_default_opts()
+    ret, cs, *_ = R.nsev(qq, Tq, Mq, XIq, kap, o)
+    assert ret == 0
+    G["floor/q"] = qq
+    G["floor/rho_exact"] = rho_exact
+    G["floor/rho_reference"] = cs
     out = os.path.join(HERE, "golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, os.path.getsize(out), "bytes,", len(G), "arrays")

@@ -256,6 +256,17 @@ def test_against_reference_library_if_present(F):
         assert max(parity_contract(c1, c0)) < 1
 
 
+def test_more_accurate_than_reference_where_reference_hits_its_floor(F, golden):
+    """Same case as tests/test_oracle.py::test_reference_accuracy_floor: the CUDA path
+    (exact chirp phases, direct convolution on the low tree levels) must be close to the
+    long-double truth, i.e. the difference to the reference there is the reference's."""
+    exact = golden["floor/rho_exact"]
+    ret, cs, *_ = F.nsev(golden["floor/q"], (-32.0, 32.0), 40, (-10.0, 10.0), -1)
+    assert ret == 0
+    assert (np.abs(cs - exact) / np.abs(exact)).max() < 2e-10
+    assert max(parity_contract(cs, golden["floor/rho_reference"])) < 1
+
+
 def test_invalid_and_edge_inputs(F):
     F.lib().fnft_errwarn_setprintf(None)
     # D = 2 (smallest allowed), M = 2
