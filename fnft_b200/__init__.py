@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfnft_b200.so")
+LIB_PATH = os.environ.get("FNFT_B200_LIB") or os.path.join(_HERE, "lib", "libfnft_b200.so")
 
 # enum values (include/fnft_b200.h)
 NSE_2SPLIT2_MODAL, NSE_BO, NSE_2SPLIT1A, NSE_2SPLIT1B, NSE_2SPLIT2A, NSE_2SPLIT2B, NSE_2SPLIT2S = range(7)

@@ -53,6 +53,9 @@ static inline void emul_sincospi(double a, double *s, double *c)
 // Runs the body exactly once with tid = threadIdx.x.
 #define FOR_THREADS(tid, nt) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
 #define BLOCK_SYNC() __syncthreads()
+#ifndef FNFTB_NO_NAMED_BARRIERS
+#define FNFTB_NO_NAMED_BARRIERS 0
+#endif
 // Barrier among the `ts` consecutive threads of the caller's team (ts a multiple of 32
 // dividing nt).  One warp: __syncwarp; the whole CTA: __syncthreads; otherwise a named
 // barrier (ids 1..15, so at most 15 teams).
@@ -60,7 +63,7 @@ static inline void emul_sincospi(double a, double *s, double *c)
     do {                                                                             \
         if ((ts) == 32) {                                                            \
             __syncwarp();                                                            \
-        } else if ((ts) >= (nt)) {                                                   \
+        } else if ((ts) >= (nt) || FNFTB_NO_NAMED_BARRIERS) {                        \
             __syncthreads();                                                         \
         } else {                                                                     \
             asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / (ts)), "r"(ts) : "memory"); \

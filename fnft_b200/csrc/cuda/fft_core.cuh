@@ -211,18 +211,30 @@ HD void fft_pass_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, int ti
 // Radix plan: as many radix-16 passes as possible, the remainder (8/4/2) LAST so
 // that every earlier pass has stride >= 8 elements (bank-conflict-free together
 // with swz()).  n = 1 gives an empty plan.
-static inline FftPlan make_fft_plan(int n)
+HD FftPlan make_fft_plan(int n, int max_radix = 16)
 {
     FftPlan P;
-    memset(&P, 0, sizeof(P));
     P.n = n;
     P.log2n = 0;
+    P.npass = 0;
+    for (int i = 0; i < FNFTB_MAX_PASSES; ++i)
+        P.radix[i] = 0;
     while ((1 << P.log2n) < n)
         ++P.log2n;
     int rem = P.log2n;
-    int tail = rem % 4;  // log2 of the last radix (0 => none)
-    // avoid a trailing radix-2 after radix-16s when a 8+4 / 8+8 split is nicer
+    if (max_radix < 16) {
+        // radix-8 passes with the remainder (4/2) last
+        while (rem >= 3) {
+            P.radix[P.npass++] = 8;
+            rem -= 3;
+        }
+        if (rem)
+            P.radix[P.npass++] = 1 << rem;
+        return P;
+    }
+    const int tail = rem % 4;  // log2 of the last radix (0 => none)
     int n16 = rem / 4;
+    // avoid a trailing radix-2 / radix-4 after radix-16s when 8*4 / 8*8 is nicer
     if (tail == 1 && n16 >= 1) {  // 16*2 -> 8*4
         n16 -= 1;
         for (int i = 0; i < n16; ++i)
@@ -299,7 +311,7 @@ HD void fft_pass_team(cplx *S, int f0, int nf, int log2n, int log2s, int lane, i
     }
 }
 
-template <int DIR>
+template <int DIR, int MAXR = 16>
 HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, int tid, int nt,
                                int ts, const TwTable &T)
 {
@@ -313,7 +325,10 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
     if (nf <= 0)
         return;
     switch (R) {
-    case 16: fft_pass_team<16, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
+    case 16:
+        if constexpr (MAXR >= 16)
+            fft_pass_team<16, DIR>(S, f0, nf, log2n, log2s, lane, ts, T);
+        break;
     case 8: fft_pass_team<8, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
     case 4: fft_pass_team<4, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
     case 2: fft_pass_team<2, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
@@ -325,7 +340,9 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
 // Must be called by all threads of the block program.  On return the team's own
 // transforms are complete (team barrier); callers that read other teams' data must
 // BLOCK_SYNC() first.
-#define FNFTB_SMEM_FFT_FWD(S, nfft, P, nt, T)                                         \
+#define FNFTB_SMEM_FFT_FWD(S, nfft, P, nt, T) FNFTB_SMEM_FFT_FWD_R(S, nfft, P, nt, T, 16)
+#define FNFTB_SMEM_FFT_INV(S, nfft, P, nt, T) FNFTB_SMEM_FFT_INV_R(S, nfft, P, nt, T, 16)
+#define FNFTB_SMEM_FFT_FWD_R(S, nfft, P, nt, T, MAXR)                                 \
     do {                                                                              \
         int _l2s = (P).log2n;                                                         \
         const int _ts = fft_team_size((P).n, nt);                                     \
@@ -334,14 +351,14 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
             _l2s -= ilog2i(_R);                                                       \
             FOR_THREADS(tid, nt)                                                      \
             {                                                                         \
-                fft_pass_team_dispatch<-1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, _ts, T); \
+                fft_pass_team_dispatch<-1, MAXR>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, _ts, T); \
             }                                                                         \
             TEAM_SYNC(_ts, nt);                                                       \
         }                                                                             \
     } while (0)
 
 // In-place inverse (unnormalised) transforms, consuming the forward's ordering.
-#define FNFTB_SMEM_FFT_INV(S, nfft, P, nt, T)                                         \
+#define FNFTB_SMEM_FFT_INV_R(S, nfft, P, nt, T, MAXR)                                 \
     do {                                                                              \
         int _l2s = 0;                                                                 \
         const int _ts = fft_team_size((P).n, nt);                                     \
@@ -349,7 +366,7 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
             const int _R = (P).radix[_p];                                             \
             FOR_THREADS(tid, nt)                                                      \
             {                                                                         \
-                fft_pass_team_dispatch<+1>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, _ts, T); \
+                fft_pass_team_dispatch<+1, MAXR>(_R, (S), (nfft), (P).log2n, _l2s, tid, nt, _ts, T); \
             }                                                                         \
             TEAM_SYNC(_ts, nt);                                                       \
             _l2s += ilog2i(_R);                                                       \

@@ -6,7 +6,7 @@
 
 #ifdef FNFTB_EMUL
 typedef void *fnftb_stream_t;
-template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256>
+template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256, int MINB = 1>
 static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t smem_bytes,
                                 fnftb_stream_t /*st*/, const char * /*name*/ = "")
 {
@@ -23,8 +23,8 @@ static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t sme
 }
 #else
 typedef cudaStream_t fnftb_stream_t;
-template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT>
-__global__ void __launch_bounds__(MAXT) fnftb_kernel(const Args a)
+template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) fnftb_kernel(const Args a)
 {
     extern __shared__ double2 fnftb_smem[];
     F(a, blockIdx, (int)blockDim.x, (void *)fnftb_smem);
@@ -37,7 +37,7 @@ void fnftb_profile_begin(const char *name, cudaStream_t st);
 void fnftb_profile_end(cudaStream_t st);
 extern int g_fnftb_profile_on;
 
-template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256>
+template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256, int MINB = 1>
 static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t smem_bytes,
                                 fnftb_stream_t st, const char *name = "")
 {
@@ -46,7 +46,7 @@ static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t sme
     if (nt > MAXT)
         return -77;
     if (smem_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fnftb_kernel<Args, F, MAXT>,
+        cudaError_t e = cudaFuncSetAttribute(fnftb_kernel<Args, F, MAXT, MINB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_bytes);
         if (e != cudaSuccess)
@@ -54,7 +54,7 @@ static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t sme
     }
     if (g_fnftb_profile_on)
         fnftb_profile_begin(name, st);
-    fnftb_kernel<Args, F, MAXT><<<grid, nt, smem_bytes, st>>>(a);
+    fnftb_kernel<Args, F, MAXT, MINB><<<grid, nt, smem_bytes, st>>>(a);
     if (g_fnftb_profile_on)
         fnftb_profile_end(st);
     ++g_fnftb_launch_count;

@@ -4,6 +4,7 @@
 #pragma once
 #include "launch.cuh"
 #include "tree_kernels.cuh"
+#include "tree_low_kernel.cuh"
 
 #ifdef FNFTB_EMUL
 static inline void dev_memset0(void *p, size_t bytes, fnftb_stream_t) { memset(p, 0, bytes); }
@@ -75,35 +76,94 @@ BLK void blk_import(const ImportArgs &a, blk3 bid, int nt, void *)
 }
 
 template <int DIN>
-static inline int launch_direct(const PairArgs &pa, fnftb_stream_t st)
+static inline int launch_direct(const PairArgs &pa, int sym, fnftb_stream_t st)
 {
-    const long long total = (long long)pa.B * (pa.n_in / 2) * 4;
+    const long long total = (long long)pa.B * (pa.n_in / 2) * (sym ? 2 : 4);
     const int nt = 128;
-    return launch_blocks<PairArgs, blk_pair_direct<DIN>, 128>(pa, (unsigned)((total + nt - 1) / nt), nt,
-                                                         0, st, "tree_pair_direct");
+    const unsigned grid = (unsigned)((total + nt - 1) / nt);
+    if (sym)
+        return launch_blocks<PairArgs, blk_pair_direct<DIN, true>, 128>(pa, grid, nt, 0, st,
+                                                                        "tree_pair_direct");
+    return launch_blocks<PairArgs, blk_pair_direct<DIN, false>, 128>(pa, grid, nt, 0, st,
+                                                                     "tree_pair_direct");
 }
 
 template <int R>
-static inline int launch_combine(const PairArgs &pa, fnftb_stream_t st)
+static inline int launch_combine(const PairArgs &pa, int sym, fnftb_stream_t st)
 {
-    const long long total = (long long)pa.B * (pa.n_in / 2) * 4 * pa.N2;
+    const long long total = (long long)pa.B * (pa.n_in / 2) * (sym ? 2 : 4) * pa.N2;
     int nt = 128;
     if (nt > pa.N2)
         nt = pa.N2;  // a CTA must stay inside one (signal, pair, entry)
-    return launch_blocks<PairArgs, blk_pair_combine<R>, 128>(pa, (unsigned)(total / nt), nt,
-                                                        sizeof(double) * nt, st, "tree_pair_combine");
+    const unsigned grid = (unsigned)(total / nt);
+    if (sym)
+        return launch_blocks<PairArgs, blk_pair_combine<R, true>, 128>(
+            pa, grid, nt, sizeof(double) * nt, st, "tree_pair_combine");
+    return launch_blocks<PairArgs, blk_pair_combine<R, false>, 128>(
+        pa, grid, nt, sizeof(double) * nt, st, "tree_pair_combine");
 }
 
 // Runs all levels.  On entry level buffer 0 holds npad matrices of degree deg0
 // per signal (and mx[0] their max, normally 1.0).  On return *cur_out tells which
 // level buffer holds the single product matrix (degree deg0*npad, pending scale in
 // mx[*cur_out]).  use_direct=0 forces the FFT path on every level (testing).
+// tuning knobs (environment, read once): FNFT_B200_TREE_SMEM_N (row length of the
+// in-shared-memory pair product), FNFT_B200_MAX_RADIX (16 or 8)
+static inline int tree_knob(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+static inline const char *level_name(const char *base, int log2n, int R)
+{
+    // stable storage for "base_N<len>[_R<r>]" strings (names are compared by content)
+    static char names[2][32][8][40];
+    const int b = (base[10] == 'f' && base[13] == '_') ? 1 : 0;  // "tree_pair_fft_rows" vs "tree_pair_fft"
+    int r = 0;
+    while ((1 << r) < R)
+        ++r;
+    char *s = names[b][log2n & 31][r & 7];
+    if (!s[0])
+        snprintf(s, 40, "%s_N%d_R%d", base, 1 << log2n, R);
+    return s;
+}
+
+static inline int launch_pair_fft(const PairArgs &pa, unsigned grid, int nt, size_t smem,
+                                  fnftb_stream_t st, const char *name, int max_radix, int sym)
+{
+    if (sym) {
+        if (max_radix < 16) {
+            if (nt <= 256)
+                return launch_blocks<PairArgs, blk_pair_fft_sym_r8, 256, 4>(pa, grid, nt, smem, st, name);
+            return launch_blocks<PairArgs, blk_pair_fft_sym_r8, 512, 2>(pa, grid, nt, smem, st, name);
+        }
+        if (nt <= 256)
+            return launch_blocks<PairArgs, blk_pair_fft_sym, 256, 2>(pa, grid, nt, smem, st, name);
+        return launch_blocks<PairArgs, blk_pair_fft_sym, 512>(pa, grid, nt, smem, st, name);
+    }
+    if (max_radix < 16) {
+        if (nt <= 256)
+            return launch_blocks<PairArgs, blk_pair_fft_r8, 256, 4>(pa, grid, nt, smem, st, name);
+        return launch_blocks<PairArgs, blk_pair_fft_r8, 512, 2>(pa, grid, nt, smem, st, name);
+    }
+    if (nt <= 256)
+        return launch_blocks<PairArgs, blk_pair_fft, 256, 2>(pa, grid, nt, smem, st, name);
+    return launch_blocks<PairArgs, blk_pair_fft, 512>(pa, grid, nt, smem, st, name);
+}
+
 static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int normalize,
                               const TwTable &T, fnftb_stream_t st, int *cur_out,
-                              int use_direct = 1, int smem_n = FNFTB_TREE_SMEM_N)
+                              int use_direct = 1, int smem_n = FNFTB_TREE_SMEM_N, int sym = 0,
+                              int kappa = 0)
 {
+    static const int knob_smem_n = tree_knob("FNFT_B200_TREE_SMEM_N", 0);
+    static const int max_radix = tree_knob("FNFT_B200_MAX_RADIX", 16);
+    static const int knob_cta_elems = tree_knob("FNFT_B200_TREE_CTA_ELEMS", 0);
+    if (knob_smem_n > 0 && smem_n == FNFTB_TREE_SMEM_N)
+        smem_n = knob_smem_n;
     int cur = 0;
-    int n = npad, d = deg0;
+    int n = npad, d = deg0;  // (callers may pass an intermediate level: n matrices of degree d)
     int rc = 0;
     while (n >= 2) {
         PairArgs pa;
@@ -118,19 +178,21 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
         pa.n_in = n;
         pa.d_in = d;
         pa.normalize = normalize;
+        pa.kappa = kappa;
         pa.T = T;
         const int npairs = n / 2;
+        const int NA = sym ? 4 : 8;  // operand arrays per pair
         const bool direct =
             use_direct && (d == 1 || d == 2 || d == 3 || d == 4 || d == 6 || d == 8);
         if (direct) {
             dev_memset0(pa.mx_out, sizeof(double) * (size_t)B * npairs, st);
             switch (d) {
-            case 1: rc = launch_direct<1>(pa, st); break;
-            case 2: rc = launch_direct<2>(pa, st); break;
-            case 3: rc = launch_direct<3>(pa, st); break;
-            case 4: rc = launch_direct<4>(pa, st); break;
-            case 6: rc = launch_direct<6>(pa, st); break;
-            default: rc = launch_direct<8>(pa, st); break;
+            case 1: rc = launch_direct<1>(pa, sym, st); break;
+            case 2: rc = launch_direct<2>(pa, sym, st); break;
+            case 3: rc = launch_direct<3>(pa, sym, st); break;
+            case 4: rc = launch_direct<4>(pa, sym, st); break;
+            case 6: rc = launch_direct<6>(pa, sym, st); break;
+            default: rc = launch_direct<8>(pa, sym, st); break;
             }
         } else {
             int N = (int)next_pow2_sz((size_t)2 * d);
@@ -141,7 +203,7 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
             if (N <= smem_n) {
                 pa.R = 1;
                 pa.N2 = N;
-                int G = smem_n / (2 * N);  // half of the big-CTA footprint per CTA
+                int G = (knob_cta_elems > 0 ? knob_cta_elems / NA : 4 * smem_n / NA) / N;
                 if (G < 1)
                     G = 1;
                 if (G > npairs)
@@ -149,41 +211,40 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                 pa.G = G;
                 pa.log2G = ilog2i((unsigned)G);
                 pa.log2N2 = ilog2i((unsigned)N);
-                pa.plan = make_fft_plan(N);
-                int nt = (8 * G * N) / 16;
+                pa.plan = make_fft_plan(N, max_radix);
+                int nt = (NA * G * N) / 16;
                 if (nt > 512)
                     nt = 512;
                 if (nt < 64)
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)((npairs + G - 1) / G);
-                rc = launch_blocks<PairArgs, blk_pair_fft, 512>(pa, grid, nt, pair_smem_bytes(G, N, nt),
-                                                           st, "tree_pair_fft");
+                rc = launch_pair_fft(pa, grid, nt, pair_smem_bytes(G, N, nt, sym), st,
+                                     level_name("tree_pair_fft", pa.log2N2, 1), max_radix, sym);
             } else {
                 pa.R = N / smem_n;
                 pa.N2 = smem_n;
                 pa.G = 1;
                 pa.log2G = 0;
                 pa.log2N2 = ilog2i((unsigned)smem_n);
-                pa.plan = make_fft_plan(smem_n);
-                int nt = (8 * smem_n) / 16;
+                pa.plan = make_fft_plan(smem_n, max_radix);
+                int nt = (NA * smem_n) / 16;
                 if (nt > 512)
                     nt = 512;
                 if (nt < 64)
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)npairs * (unsigned)pa.R;
-                rc = launch_blocks<PairArgs, blk_pair_fft, 512>(pa, grid, nt,
-                                                           pair_smem_bytes(1, smem_n, nt), st,
-                                                           "tree_pair_fft_rows");
+                rc = launch_pair_fft(pa, grid, nt, pair_smem_bytes(1, smem_n, nt, sym), st,
+                                     level_name("tree_pair_fft_rows", pa.log2N2, pa.R), max_radix, sym);
                 if (rc)
                     return rc;
                 dev_memset0(pa.mx_out, sizeof(double) * (size_t)B * npairs, st);
                 switch (pa.R) {
-                case 2: rc = launch_combine<2>(pa, st); break;
-                case 4: rc = launch_combine<4>(pa, st); break;
-                case 8: rc = launch_combine<8>(pa, st); break;
-                case 16: rc = launch_combine<16>(pa, st); break;
-                case 32: rc = launch_combine<32>(pa, st); break;
-                case 64: rc = launch_combine<64>(pa, st); break;
+                case 2: rc = launch_combine<2>(pa, sym, st); break;
+                case 4: rc = launch_combine<4>(pa, sym, st); break;
+                case 8: rc = launch_combine<8>(pa, sym, st); break;
+                case 16: rc = launch_combine<16>(pa, sym, st); break;
+                case 32: rc = launch_combine<32>(pa, sym, st); break;
+                case 64: rc = launch_combine<64>(pa, sym, st); break;
                 default: return -1000 - pa.R;  // transform too long for this build
                 }
             }
@@ -199,7 +260,7 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
 }
 
 static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, int deg_out,
-                                int normalize, cplx *tm, fnftb_stream_t st)
+                                int normalize, cplx *tm, fnftb_stream_t st, int sym = 0, int kappa = 0)
 {
     FinalArgs fa;
     fa.in = w.lev[cur];
@@ -210,6 +271,8 @@ static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, i
     fa.d_full = d_full;
     fa.deg_out = deg_out;
     fa.normalize = normalize;
+    fa.sym = sym;
+    fa.kappa = kappa;
     const long long tot = (long long)B * 4 * (deg_out + 1);
     return launch_blocks<FinalArgs, blk_tree_final>(fa, (unsigned)((tot + 255) / 256), 256, 0, st,
                                                     "tree_final");
@@ -224,31 +287,86 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
     const int npad = (int)next_pow2_sz((size_t)D);
     dev_memset0(w.W, sizeof(int) * (size_t)B, st);
     dev_memset0(w.status, sizeof(int) * (size_t)B, st);
-    LeafArgs la;
-    memset(&la, 0, sizeof(la));
-    la.q = q;
-    la.r = r;
-    la.out = w.lev[0];
-    la.mx = w.mx[0];
-    la.B = B;
-    la.D = D;
-    la.npad = npad;
-    la.deg0 = deg0;
-    la.rmode = rmode;
-    la.kappa = kappa;
-    la.scheme = scheme;
-    la.eps_t = eps_t;
-    la.status = w.status;
-    const long long total = (long long)B * npad;
-    int rc = launch_blocks<LeafArgs, blk_leaf>(la, (unsigned)((total + 127) / 128), 128, 0, st,
+    // first-row-only mode: NSE structure, and every level must be a wrap level
+    // (degree a power of two) once the FFT path is reached
+    static const int knob_sym = tree_knob("FNFT_B200_TREE_SYM", 1);
+    const int sym = (knob_sym && rmode == FNFTB_R_NSE && (deg0 == 1 || deg0 == 2)) ? 1 : 0;
+    static const int knob_low = tree_knob("FNFT_B200_TREE_LOW", 1);
+    static const int knob_low_s = tree_knob("FNFT_B200_TREE_LOW_S", 0);
+    static const int max_radix_low = tree_knob("FNFT_B200_MAX_RADIX", 16);
+    int rc;
+    int n_start = npad, d_start = deg0;
+    if (knob_low && (deg0 == 1 || deg0 == 2) && use_direct) {
+        // fused low levels: blocks of S samples -> one matrix of degree deg0*S per block
+        int S = knob_low_s > 0 ? knob_low_s : (sym ? 256 : 128);
+        if (S > npad)
+            S = npad;
+        LowArgs lo;
+        memset(&lo, 0, sizeof(lo));
+        lo.q = q;
+        lo.r = r;
+        lo.out = w.lev[0];
+        lo.mx_out = w.mx[0];
+        lo.W = w.W;
+        lo.status = w.status;
+        lo.B = B;
+        lo.D = D;
+        lo.npad = npad;
+        lo.deg0 = deg0;
+        lo.rmode = rmode;
+        lo.kappa = kappa;
+        lo.scheme = scheme;
+        lo.normalize = normalize;
+        lo.S = S;
+        lo.log2S = ilog2i((unsigned)S);
+        lo.eps_t = eps_t;
+        lo.T = T;
+        const unsigned grid = (unsigned)B * (unsigned)(npad / S);
+        const size_t smem = low_smem_bytes(sym, S, deg0);
+        const int nt = 128;
+        if (sym) {
+            if (max_radix_low < 16)
+                rc = launch_blocks<LowArgs, blk_tree_low_sym_r8, 128, 4>(lo, grid, nt, smem, st, "tree_low");
+            else
+                rc = launch_blocks<LowArgs, blk_tree_low_sym, 128, 3>(lo, grid, nt, smem, st, "tree_low");
+        } else {
+            if (max_radix_low < 16)
+                rc = launch_blocks<LowArgs, blk_tree_low_gen_r8, 128, 4>(lo, grid, nt, smem, st, "tree_low");
+            else
+                rc = launch_blocks<LowArgs, blk_tree_low_gen, 128, 3>(lo, grid, nt, smem, st, "tree_low");
+        }
+        if (rc)
+            return rc;
+        n_start = npad / S;
+        d_start = deg0 * S;
+    } else {
+        LeafArgs la;
+        memset(&la, 0, sizeof(la));
+        la.q = q;
+        la.r = r;
+        la.out = w.lev[0];
+        la.mx = w.mx[0];
+        la.B = B;
+        la.D = D;
+        la.npad = npad;
+        la.deg0 = deg0;
+        la.rmode = rmode;
+        la.kappa = kappa;
+        la.scheme = scheme;
+        la.sym = sym;
+        la.eps_t = eps_t;
+        la.status = w.status;
+        const long long total = (long long)B * npad;
+        rc = launch_blocks<LeafArgs, blk_leaf>(la, (unsigned)((total + 127) / 128), 128, 0, st,
                                                "tree_leaf");
-    if (rc)
-        return rc;
+        if (rc)
+            return rc;
+    }
     int cur = 0;
-    rc = tree_levels(w, B, npad, deg0, normalize, T, st, &cur, use_direct, smem_n);
+    rc = tree_levels(w, B, n_start, d_start, normalize, T, st, &cur, use_direct, smem_n, sym, kappa);
     if (rc)
         return rc;
-    return tree_finalize(w, cur, B, deg0 * npad, deg0 * D, normalize, tm, st);
+    return tree_finalize(w, cur, B, deg0 * npad, deg0 * D, normalize, tm, st, sym, kappa);
 }
 
 // Product of n given matrices (one "signal"), reference layout in and out.

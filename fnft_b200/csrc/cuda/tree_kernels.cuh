@@ -91,6 +91,19 @@ HD void zero_freq_expm(cplx *M, double h, cplx q, cplx r)
 }
 
 // ---------------------------------------------------------------------------
+// Symmetric ("SYM") mode.  For the NSE (r = -kappa*conj(q)) every leaf, and hence every
+// partial product, has the structure
+//        M(z) = [  a(z)          b(z)   ]      f#(z) = z^d * conj(f(1/conj(z)))
+//               [ -kappa*b#(z)   a#(z)  ]      (coefficients reversed and conjugated)
+// so only the first row (a, b) is stored and multiplied: 4 forward + 2 inverse
+// transforms per pair instead of 8 + 4, half the shared memory and half the HBM
+// traffic.  On the unit circle at the N = 2d roots of unity  F#[k] = (-1)^k conj(F[k]).
+// Level buffers then hold E = 2 entries (11, 12) per matrix.  Padding matrices are
+// diag(z^d, 1) (they have the structure, z^d*I does not); the final kernel undoes the
+// resulting shift of the second column and rebuilds the second row.
+// ---------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------
 // leaf kernel: one thread per (signal, level-0 matrix)
 // ---------------------------------------------------------------------------
 struct LeafArgs {
@@ -100,6 +113,7 @@ struct LeafArgs {
     double *mx;      // [B][npad]  (set to 1.0: leaves are not rescaled)
     int B, D, npad, deg0;
     int rmode, kappa, scheme;
+    int sym;         // 1: store only the first row (entries 11, 12)
     double eps_t;
     int *status;     // per-signal status (nonzero = error), may be NULL
 };
@@ -217,6 +231,7 @@ BLK void blk_leaf(const LeafArgs &a, blk3 bid, int nt, void * /*smem*/)
         if (gid < total) {
             const int s = (int)(gid / a.npad);
             const int m = (int)(gid % a.npad);
+            const int d1 = a.deg0 + 1;
             cplx p[4 * 3];  // deg0 <= 2 for every scheme implemented here
             int err = 0;
             if (m < a.D) {
@@ -231,14 +246,15 @@ BLK void blk_leaf(const LeafArgs &a, blk3 bid, int nt, void * /*smem*/)
                     r = a.r[idx];
                 leaf_matrix(p, a.scheme, a.deg0, a.eps_t, q, r, &err);
             } else {
-                // padding with z^deg * I  (fnft__poly_fmult.c:422-438)
-                for (int i = 0; i < 4 * (a.deg0 + 1); ++i)
+                // padding: z^deg * I (fnft__poly_fmult.c:422-438); diag(z^deg, 1) in SYM mode
+                for (int i = 0; i < 4 * d1; ++i)
                     p[i] = czero();
                 p[0] = make_cplx(1.0, 0.0);
-                p[3 * (a.deg0 + 1)] = make_cplx(1.0, 0.0);
+                p[3 * d1] = make_cplx(1.0, 0.0);
             }
-            cplx *o = a.out + (size_t)gid * 4 * (a.deg0 + 1);
-            for (int i = 0; i < 4 * (a.deg0 + 1); ++i)
+            const int E = a.sym ? 2 : 4;
+            cplx *o = a.out + (size_t)gid * E * d1;
+            for (int i = 0; i < E * d1; ++i)
                 o[i] = p[i];
             a.mx[gid] = 1.0;
             if (err && a.status)
@@ -278,9 +294,10 @@ struct PairArgs {
     const double *mx_in;  // [B][n_in]
     double *mx_out;       // [B][n_in/2]  (must be zeroed when atomics are used)
     int *W;               // [B]
-    cplx *gbuf;           // [B][pairs][4][R][N2] partial row results (R > 1)
+    cplx *gbuf;           // [B][pairs][E][R][N2] partial row results (R > 1)
     int B, n_in, d_in;
     int normalize;
+    int kappa;    // SYM mode only
     int N;        // cyclic convolution length (power of two, >= 2*d_in)
     int wrap;     // 1 if N == 2*d_in (top coefficient handled analytically)
     int R, N2;    // N = R * N2; R == 1: whole product inside one CTA
@@ -302,42 +319,60 @@ HD double load_scale(const PairArgs &a, size_t mat /* s*n_in + m */, int *expo)
 }
 
 // Small-degree pair products by direct convolution: one thread per
-// (signal, pair, output entry).  d_in is a template parameter so that the
+// (signal, pair, stored output entry).  d_in is a template parameter so that the
 // accumulators stay in registers.
-template <int DIN>
+template <int DIN, bool SYM>
 BLK void blk_pair_direct(const PairArgs &a, blk3 bid, int nt, void * /*smem*/)
 {
+    constexpr int E = SYM ? 2 : 4;
     FOR_THREADS(tid, nt)
     {
         const int npairs = a.n_in / 2;
         const long long gid = (long long)bid.x * nt + tid;
-        const long long total = (long long)a.B * npairs * 4;
+        const long long total = (long long)a.B * npairs * E;
         if (gid < total) {
-            const int e = (int)(gid & 3);
-            const long long sp = gid >> 2;  // s*npairs + pair
-            const int pair = (int)(sp % npairs);
+            const int e = (int)(gid % E);
+            const long long sp = gid / E;  // s*npairs + pair
             const int s = (int)(sp / npairs);
-            const int row = e >> 1, col = e & 1;
-            const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair;
+            const int row = SYM ? 0 : (e >> 1), col = SYM ? e : (e & 1);
+            const size_t matA = (size_t)sp * 2;
             int eA, eB;
             const double sA = load_scale(a, matA, &eA);
             const double sB = load_scale(a, matA + 1, &eB);
-            const cplx *A = a.in + matA * 4 * (DIN + 1);
-            const cplx *Bm = A + 4 * (DIN + 1);
-            const cplx *Ar0 = A + (row * 2 + 0) * (DIN + 1);
-            const cplx *Ar1 = A + (row * 2 + 1) * (DIN + 1);
-            const cplx *B0c = Bm + (0 * 2 + col) * (DIN + 1);
-            const cplx *B1c = Bm + (1 * 2 + col) * (DIN + 1);
+            const cplx *A = a.in + matA * E * (DIN + 1);
+            const cplx *Bm = A + E * (DIN + 1);
+            const cplx *Ar0 = A + (SYM ? 0 : (row * 2 + 0)) * (DIN + 1);
+            const cplx *Ar1 = A + (SYM ? 1 : (row * 2 + 1)) * (DIN + 1);
+            cplx b0[DIN + 1], b1[DIN + 1];
+            if (SYM) {
+                // column c of B: (B11, B21) or (B12, B22) with B21 = -kappa*rc(B12),
+                // B22 = rc(B11), rc = reverse + conjugate
+                const cplx *B11 = Bm, *B12 = Bm + (DIN + 1);
+#pragma unroll
+                for (int j = 0; j <= DIN; ++j) {
+                    if (col == 0) {
+                        b0[j] = cscale(B11[j], sB);
+                        const cplx t = B12[DIN - j];
+                        b1[j] = cscale(make_cplx(t.x, -t.y), -(double)a.kappa * sB);
+                    } else {
+                        b0[j] = cscale(B12[j], sB);
+                        const cplx t = B11[DIN - j];
+                        b1[j] = cscale(make_cplx(t.x, -t.y), sB);
+                    }
+                }
+            } else {
+                const cplx *B0c = Bm + (0 * 2 + col) * (DIN + 1);
+                const cplx *B1c = Bm + (1 * 2 + col) * (DIN + 1);
+#pragma unroll
+                for (int j = 0; j <= DIN; ++j) {
+                    b0[j] = cscale(B0c[j], sB);
+                    b1[j] = cscale(B1c[j], sB);
+                }
+            }
             cplx acc[2 * DIN + 1];
 #pragma unroll
             for (int k = 0; k < 2 * DIN + 1; ++k)
                 acc[k] = czero();
-            cplx b0[DIN + 1], b1[DIN + 1];
-#pragma unroll
-            for (int j = 0; j <= DIN; ++j) {
-                b0[j] = cscale(B0c[j], sB);
-                b1[j] = cscale(B1c[j], sB);
-            }
 #pragma unroll
             for (int i = 0; i <= DIN; ++i) {
                 const cplx a0 = cscale(Ar0[i], sA), a1 = cscale(Ar1[i], sA);
@@ -347,7 +382,7 @@ BLK void blk_pair_direct(const PairArgs &a, blk3 bid, int nt, void * /*smem*/)
                     cfma(acc[i + j], a1, b1[j]);
                 }
             }
-            cplx *o = a.out + ((size_t)sp * 4 + e) * (2 * DIN + 1);
+            cplx *o = a.out + ((size_t)sp * E + e) * (2 * DIN + 1);
             double m2 = 0.0;
 #pragma unroll
             for (int k = 0; k < 2 * DIN + 1; ++k) {
@@ -368,21 +403,28 @@ BLK void blk_pair_direct(const PairArgs &a, blk3 bid, int nt, void * /*smem*/)
 //            cyclic product from length-N2 transforms and writes the length-N2
 //            inverse transform of those bins to gbuf; blk_pair_combine finishes.
 //            grid.x = B * npairs * R
-// Shared memory: cplx S[8][G][N2] followed by cplx top[8][G], double sc[2][G],
-// double red[nt].
-HD size_t pair_smem_bytes(int G, int N2, int nt)
+// NA = 8 (4 in SYM mode) operand arrays and NO = 4 (2) result arrays per pair.
+// Shared memory: cplx S[NA][G][N2], cplx top[NA][G], cplx bot[NA][G] (SYM: index-0
+// coefficients), double sc[2][G], double red[nt].
+HD size_t pair_smem_bytes(int G, int N2, int nt, int sym)
 {
-    return sizeof(cplx) * ((size_t)8 * G * N2 + 8 * G) + sizeof(double) * (2 * G + nt);
+    const size_t NA = sym ? 4 : 8;
+    return sizeof(cplx) * (NA * G * N2 + 2 * NA * G) + sizeof(double) * (2 * G + nt);
 }
 
-BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
+template <int MAXR, bool SYM>
+BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
 {
+    constexpr int E = SYM ? 2 : 4;    // stored entries per matrix
+    constexpr int NA = 2 * E;         // operand arrays per pair
+    constexpr int L2E = SYM ? 1 : 2;  // log2(E)
     const int npairs = a.n_in / 2;
     const int G = a.G, N2 = a.N2, R = a.R;
     const int din1 = a.d_in + 1;
     cplx *S = (cplx *)smem;
-    cplx *top = S + (size_t)8 * G * N2;
-    double *sc = (double *)(top + 8 * G);
+    cplx *top = S + (size_t)NA * G * N2;
+    cplx *bot = top + NA * G;
+    double *sc = (double *)(bot + NA * G);
     double *red = sc + 2 * G;
 
     int s, pair0, k1;
@@ -398,8 +440,9 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
         s = sp / npairs;
     }
     const int nbody = a.wrap ? a.d_in : din1;  // coefficients that enter the FFT
+    const int l2n = a.log2N2, l2g = a.log2G;
 
-    // phase 0: per-matrix scale factors, exponent bookkeeping
+    // phase 0: per-matrix scale factors, exponent bookkeeping; R > 1: w_R^(n1*k1)
     FOR_THREADS(tid, nt)
     {
         for (int t2 = tid; t2 < 2 * G; t2 += nt) {
@@ -414,28 +457,21 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
             }
             sc[side * G + g] = scale;
         }
-    }
-    BLOCK_SYNC();
-
-    // phase A: load (and for R > 1 fold the radix-R column step into the load)
-    const int l2n = a.log2N2, l2g = a.log2G;
-    if (R > 1) {
-        // w_R^(n1*k1) for n1 < R/2, shared by all elements of this CTA (kept in `red`,
-        // which is not used before phase E)
-        FOR_THREADS(tid, nt)
-        {
+        if (R > 1) {
             for (int n1 = tid; n1 < R / 2; n1 += nt) {
                 const cplx w = cispi(-2.0 * (double)((n1 * k1) % R) / (double)R);
                 red[2 * n1] = w.x;
                 red[2 * n1 + 1] = w.y;
             }
         }
-        BLOCK_SYNC();
     }
+    BLOCK_SYNC();
+
+    // phase A: load (and for R > 1 fold the radix-R column step into the load)
     FOR_THREADS(tid, nt)
     {
         if (R == 1) {
-            const int total = (8 * G) << l2n;
+            const int total = (NA * G) << l2n;
             for (int idx = tid; idx < total; idx += nt) {
                 const int i = idx & (N2 - 1);
                 const int pg = idx >> l2n;  // p*G + g
@@ -443,8 +479,8 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
                 const int pair = pair0 + g;
                 cplx v = czero();
                 if (pair < npairs && i < nbody) {
-                    const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> 2);
-                    v = cscale(a.in[(mat * 4 + (p & 3)) * din1 + i], sc[(p >> 2) * G + g]);
+                    const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> L2E);
+                    v = cscale(a.in[(mat * E + (p & (E - 1))) * din1 + i], sc[(p >> L2E) * G + g]);
                 }
                 S[((size_t)pg << l2n) + swz(i)] = v;
             }
@@ -452,14 +488,14 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
             // y[n2] = w_N^(n2*k1) * sum_{n1<R/2} x[n1*N2+n2] * w_R^(n1*k1)
             const int half = R / 2;
             const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair0;
-            const cplx *xbase = a.in + matA * 4 * din1;
+            const cplx *xbase = a.in + matA * E * din1;
             for (int n2 = tid; n2 < N2; n2 += nt) {
                 const cplx wn = cispi(-2.0 * (double)((n2 * k1) & (a.N - 1)) / (double)a.N);
-                cplx acc[8];
+                cplx acc[NA];
 #pragma unroll
-                for (int p = 0; p < 8; ++p)
+                for (int p = 0; p < NA; ++p)
                     acc[p] = czero();
-                // 8 independent loads per n1 (the 8 operand polynomials of the pair)
+                // NA independent loads per n1 (the operand polynomials of the pair)
 #pragma unroll 2
                 for (int n1 = 0; n1 < half; ++n1) {
                     const int i = (n1 << l2n) + n2;
@@ -467,30 +503,33 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
                         break;
                     const cplx w = make_cplx(red[2 * n1], red[2 * n1 + 1]);
 #pragma unroll
-                    for (int p = 0; p < 8; ++p)
+                    for (int p = 0; p < NA; ++p)
                         cfma(acc[p], xbase[(size_t)p * din1 + i], w);
                 }
 #pragma unroll
-                for (int p = 0; p < 8; ++p)
-                    S[((size_t)p << l2n) + swz(n2)] = cscale(cmul(acc[p], wn), sc[(p >> 2) * G]);
+                for (int p = 0; p < NA; ++p)
+                    S[((size_t)p << l2n) + swz(n2)] = cscale(cmul(acc[p], wn), sc[(p >> L2E) * G]);
             }
         }
-        // top coefficients (only used when wrap)
-        for (int pg = tid; pg < 8 * G; pg += nt) {
+        // top coefficients (only used when wrap) and, in SYM mode, the index-0 ones
+        for (int pg = tid; pg < NA * G; pg += nt) {
             const int g = pg & (G - 1), p = pg >> l2g;
             const int pair = pair0 + g;
-            cplx v = czero();
+            cplx v = czero(), v0 = czero();
             if (a.wrap && pair < npairs) {
-                const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> 2);
-                v = cscale(a.in[(mat * 4 + (p & 3)) * din1 + a.d_in], sc[(p >> 2) * G + g]);
+                const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> L2E);
+                const cplx *x = a.in + (mat * E + (p & (E - 1))) * din1;
+                v = cscale(x[a.d_in], sc[(p >> L2E) * G + g]);
+                v0 = cscale(x[0], sc[(p >> L2E) * G + g]);
             }
             top[pg] = v;
+            bot[pg] = v0;
         }
     }
     BLOCK_SYNC();
 
-    // phase B: 8*G forward transforms of length N2
-    FNFTB_SMEM_FFT_FWD(S, 8 * G, a.plan, nt, a.T);
+    // phase B: NA*G forward transforms of length N2
+    FNFTB_SMEM_FFT_FWD_R(S, NA * G, a.plan, nt, a.T, MAXR);
     BLOCK_SYNC();
 
     // phase C: pointwise 2x2 products; results overwrite the A-side arrays
@@ -501,48 +540,63 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
         for (int idx = tid; idx < total; idx += nt) {
             const int pos = idx & (N2 - 1);
             const int g = idx >> l2n;
-            double sgn = 0.0;  // (-1)^k of the true frequency index k of this bin
-            if (a.wrap) {
-                if (R == 1)
-                    sgn = ((pos >> fs) & 1) ? -1.0 : 1.0;
-                else
-                    sgn = (k1 & 1) ? -1.0 : 1.0;
-            }
+            double sgn = 0.0;   // (-1)^k of the true frequency index k of this bin
+            double sgnk = 1.0;  // same, but also defined without wrap (SYM needs wrap)
+            if (R == 1)
+                sgnk = ((pos >> fs) & 1) ? -1.0 : 1.0;
+            else
+                sgnk = (k1 & 1) ? -1.0 : 1.0;
+            if (a.wrap)
+                sgn = sgnk;
             const int ph = swz(pos);
-            cplx v[8];
+            cplx v[NA];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
+            for (int p = 0; p < NA; ++p) {
                 const cplx t = top[p * G + g];
                 const cplx x = S[((size_t)(p * G + g) << l2n) + ph];
                 v[p] = make_cplx(x.x + sgn * t.x, x.y + sgn * t.y);
             }
-            // [A11 A12; A21 A22] * [B11 B12; B21 B22], A = v[0..3], B = v[4..7]
-            cplx c11 = cmul(v[0], v[4]);
-            cfma(c11, v[1], v[6]);
-            cplx c12 = cmul(v[0], v[5]);
-            cfma(c12, v[1], v[7]);
-            cplx c21 = cmul(v[2], v[4]);
-            cfma(c21, v[3], v[6]);
-            cplx c22 = cmul(v[2], v[5]);
-            cfma(c22, v[3], v[7]);
-            S[((size_t)(0 * G + g) << l2n) + ph] = c11;
-            S[((size_t)(1 * G + g) << l2n) + ph] = c12;
-            S[((size_t)(2 * G + g) << l2n) + ph] = c21;
-            S[((size_t)(3 * G + g) << l2n) + ph] = c22;
+            if (SYM) {
+                // A = (A11, A12) = v[0..1], B = (B11, B12) = v[2..3];
+                // B21 = -kappa*(-1)^k conj(B12), B22 = (-1)^k conj(B11)
+                const cplx b21 = cscale(cconj(v[3]), -(double)a.kappa * sgnk);
+                const cplx b22 = cscale(cconj(v[2]), sgnk);
+                cplx c11 = cmul(v[0], v[2]);
+                cfma(c11, v[1], b21);
+                cplx c12 = cmul(v[0], v[3]);
+                cfma(c12, v[1], b22);
+                S[((size_t)(0 * G + g) << l2n) + ph] = c11;
+                S[((size_t)(1 * G + g) << l2n) + ph] = c12;
+            } else {
+                // [A11 A12; A21 A22] * [B11 B12; B21 B22], A = v[0..3], B = v[4..7]
+                constexpr int b = SYM ? 0 : 4;
+                cplx c11 = cmul(v[0], v[b + 0]);
+                cfma(c11, v[1], v[b + 2]);
+                cplx c12 = cmul(v[0], v[b + 1]);
+                cfma(c12, v[1], v[b + 3]);
+                cplx c21 = cmul(v[2], v[b + 0]);
+                cfma(c21, v[3], v[b + 2]);
+                cplx c22 = cmul(v[2], v[b + 1]);
+                cfma(c22, v[3], v[b + 3]);
+                S[((size_t)(0 * G + g) << l2n) + ph] = c11;
+                S[((size_t)(1 * G + g) << l2n) + ph] = c12;
+                S[((size_t)(2 * G + g) << l2n) + ph] = c21;
+                S[((size_t)(3 * G + g) << l2n) + ph] = c22;
+            }
         }
     }
     BLOCK_SYNC();
 
-    // phase D: 4*G inverse transforms
-    FNFTB_SMEM_FFT_INV(S, 4 * G, a.plan, nt, a.T);
+    // phase D: E*G inverse transforms
+    FNFTB_SMEM_FFT_INV_R(S, E * G, a.plan, nt, a.T, MAXR);
     BLOCK_SYNC();
 
     // phase E: write out
     if (R > 1) {
         FOR_THREADS(tid, nt)
         {
-            cplx *gb = a.gbuf + (((size_t)s * npairs + pair0) * 4) * (size_t)R * N2;
-            for (int idx = tid; idx < 4 * N2; idx += nt) {
+            cplx *gb = a.gbuf + (((size_t)s * npairs + pair0) * E) * (size_t)R * N2;
+            for (int idx = tid; idx < E * N2; idx += nt) {
                 const int n2 = idx & (N2 - 1), e = idx >> l2n;
                 gb[((size_t)(e * R + k1) << l2n) + n2] = S[((size_t)e << l2n) + swz(n2)];
             }
@@ -557,25 +611,36 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
             break;
         FOR_THREADS(tid, nt)
         {
-            cplx ct[4];
-            {
-                const cplx tA11 = top[0 * G + g], tA12 = top[1 * G + g], tA21 = top[2 * G + g],
-                           tA22 = top[3 * G + g];
-                const cplx tB11 = top[4 * G + g], tB12 = top[5 * G + g], tB21 = top[6 * G + g],
-                           tB22 = top[7 * G + g];
+            cplx ct[E];
+            if (SYM) {
+                const cplx tA11 = top[0 * G + g], tA12 = top[1 * G + g];
+                const cplx tB11 = top[2 * G + g], tB12 = top[3 * G + g];
+                // top of B21 = -kappa*conj(B12[0]), top of B22 = conj(B11[0])
+                const cplx tB21 = cscale(cconj(bot[3 * G + g]), -(double)a.kappa);
+                const cplx tB22 = cconj(bot[2 * G + g]);
                 ct[0] = cmul(tA11, tB11);
                 cfma(ct[0], tA12, tB21);
                 ct[1] = cmul(tA11, tB12);
                 cfma(ct[1], tA12, tB22);
-                ct[2] = cmul(tA21, tB11);
-                cfma(ct[2], tA22, tB21);
-                ct[3] = cmul(tA21, tB12);
-                cfma(ct[3], tA22, tB22);
+            } else {
+                constexpr int b = SYM ? 0 : 4;
+                const cplx tA11 = top[0 * G + g], tA12 = top[1 * G + g], tA21 = top[2 * G + g],
+                           tA22 = top[3 * G + g];
+                const cplx tB11 = top[(b + 0) * G + g], tB12 = top[(b + 1) * G + g],
+                           tB21 = top[(b + 2) * G + g], tB22 = top[(b + 3) * G + g];
+                ct[0] = cmul(tA11, tB11);
+                cfma(ct[0], tA12, tB21);
+                ct[1] = cmul(tA11, tB12);
+                cfma(ct[1], tA12, tB22);
+                ct[E - 2] = cmul(tA21, tB11);
+                cfma(ct[E - 2], tA22, tB21);
+                ct[E - 1] = cmul(tA21, tB12);
+                cfma(ct[E - 1], tA22, tB22);
             }
-            cplx *o = a.out + ((size_t)s * npairs + pair) * 4 * dout1;
+            cplx *o = a.out + ((size_t)s * npairs + pair) * E * dout1;
             double m2 = 0.0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < E; ++e) {
                 const cplx *Se = S + ((size_t)(e * G + g) << l2n);
                 cplx *oe = o + (size_t)e * dout1;
                 for (int i = tid; i < dout1; i += nt) {
@@ -607,20 +672,38 @@ BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
     }
 }
 
+BLK void blk_pair_fft(const PairArgs &a, blk3 bid, int nt, void *smem)
+{
+    blk_pair_fft_t<16, false>(a, bid, nt, smem);
+}
+BLK void blk_pair_fft_r8(const PairArgs &a, blk3 bid, int nt, void *smem)
+{
+    blk_pair_fft_t<8, false>(a, bid, nt, smem);
+}
+BLK void blk_pair_fft_sym(const PairArgs &a, blk3 bid, int nt, void *smem)
+{
+    blk_pair_fft_t<16, true>(a, bid, nt, smem);
+}
+BLK void blk_pair_fft_sym_r8(const PairArgs &a, blk3 bid, int nt, void *smem)
+{
+    blk_pair_fft_t<8, true>(a, bid, nt, smem);
+}
+
 // Finishes a row-split product: radix-R inverse column step, 1/N scaling, wrap
 // correction, max|coeff|.  One thread per (signal, pair, entry, n2); a CTA covers nt
 // consecutive n2 of ONE (signal, pair, entry) (nt divides N2), so the max is reduced
 // in shared memory and published with a single atomic per CTA.
-template <int R>
+template <int R, bool SYM>
 BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void *smem)
 {
+    constexpr int E = SYM ? 2 : 4;
     double *red = (double *)smem;
     const int npairs = a.n_in / 2;
     const int N2 = a.N2;
     const long long gid0 = (long long)bid.x * nt;
-    const long long spe = gid0 >> a.log2N2;  // (s*npairs + pair)*4 + e
-    const int e = (int)(spe & 3);
-    const long long sp = spe >> 2;
+    const long long spe = gid0 >> a.log2N2;  // (s*npairs + pair)*E + e
+    const int e = (int)(spe % E);
+    const long long sp = spe / E;
     const int s = (int)(sp / npairs);
     const int pair = (int)(sp % npairs);
     FOR_THREADS(tid, nt)
@@ -650,13 +733,26 @@ BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void *smem)
             const size_t matA = (size_t)s * a.n_in + 2 * (size_t)pair;
             int eA, eB;
             const double sA = load_scale(a, matA, &eA), sB = load_scale(a, matA + 1, &eB);
-            const cplx *A = a.in + matA * 4 * din1;
-            const cplx *Bm = A + 4 * din1;
-            const int row = e >> 1, col = e & 1;
-            const cplx a0 = cscale(A[(row * 2 + 0) * din1 + a.d_in], sA);
-            const cplx a1 = cscale(A[(row * 2 + 1) * din1 + a.d_in], sA);
-            const cplx b0 = cscale(Bm[(0 * 2 + col) * din1 + a.d_in], sB);
-            const cplx b1 = cscale(Bm[(1 * 2 + col) * din1 + a.d_in], sB);
+            const cplx *A = a.in + matA * E * din1;
+            const cplx *Bm = A + E * din1;
+            cplx a0, a1, b0, b1;
+            if (SYM) {
+                a0 = cscale(A[0 * din1 + a.d_in], sA);
+                a1 = cscale(A[1 * din1 + a.d_in], sA);
+                if (e == 0) {
+                    b0 = cscale(Bm[0 * din1 + a.d_in], sB);
+                    b1 = cscale(cconj(Bm[1 * din1 + 0]), -(double)a.kappa * sB);
+                } else {
+                    b0 = cscale(Bm[1 * din1 + a.d_in], sB);
+                    b1 = cscale(cconj(Bm[0 * din1 + 0]), sB);
+                }
+            } else {
+                const int row = e >> 1, col = e & 1;
+                a0 = cscale(A[(row * 2 + 0) * din1 + a.d_in], sA);
+                a1 = cscale(A[(row * 2 + 1) * din1 + a.d_in], sA);
+                b0 = cscale(Bm[(0 * 2 + col) * din1 + a.d_in], sB);
+                b1 = cscale(Bm[(1 * 2 + col) * din1 + a.d_in], sB);
+            }
             ct = cmul(a0, b0);
             cfma(ct, a1, b1);
             o[a.N] = ct;
@@ -678,7 +774,6 @@ BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void *smem)
     BLOCK_SYNC();
     FOR_THREADS(tid, nt)
     {
-        // tree reduction over the CTA, then one atomic
         if (tid == 0) {
             double m2 = 0.0;
             for (int t = 0; t < nt; ++t)
@@ -689,13 +784,16 @@ BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void *smem)
 }
 
 // Final step: apply the pending scale of the single remaining matrix, strip the
-// padding-induced trailing coefficients and emit [B][4][deg_out+1] plus W.
+// padding-induced coefficients and emit [B][4][deg_out+1] plus W.  In SYM mode the
+// second row is rebuilt from the first: T21 = -kappa*T12#, T22 = T11#, and the second
+// column of the padded product is taken from the trailing coefficients.
 struct FinalArgs {
     const cplx *in;      // level buffer with 1 matrix per signal, degree d_full
     const double *mx_in; // [B]
     cplx *tm;            // [B][4][deg_out+1]
     int *W;              // [B]
     int B, d_full, deg_out, normalize;
+    int sym, kappa;
 };
 
 BLK void blk_tree_final(const FinalArgs &a, blk3 bid, int nt, void * /*smem*/)
@@ -715,7 +813,26 @@ BLK void blk_tree_final(const FinalArgs &a, blk3 bid, int nt, void * /*smem*/)
                 ex = rescale_exponent(a.mx_in[s]);
                 scale = ldexp(1.0, -ex);
             }
-            a.tm[gid] = cscale(a.in[((size_t)s * 4 + e) * (a.d_full + 1) + i], scale);
+            cplx v;
+            if (!a.sym) {
+                v = a.in[((size_t)s * 4 + e) * (a.d_full + 1) + i];
+            } else {
+                const cplx *r11 = a.in + ((size_t)s * 2 + 0) * (a.d_full + 1);
+                const cplx *r12 = r11 + (a.d_full + 1);
+                const int shift = a.d_full - a.deg_out;  // padding shifts column 2
+                if (e == 0) {
+                    v = r11[i];
+                } else if (e == 1) {
+                    v = r12[shift + i];
+                } else if (e == 2) {
+                    const cplx t = r12[shift + a.deg_out - i];
+                    v = cscale(make_cplx(t.x, -t.y), -(double)a.kappa);
+                } else {
+                    const cplx t = r11[a.deg_out - i];
+                    v = make_cplx(t.x, -t.y);
+                }
+            }
+            a.tm[gid] = cscale(v, scale);
             if (rem == 0 && a.normalize)
                 a.W[s] += ex;  // the tree kernels of this signal have all finished
         }

@@ -97,3 +97,34 @@ def test_chirpz_four_step_vs_oracle(E, deg, M, row_n):
     z = 1.0 / (A * W ** (-np.arange(M)))
     exact = np.polyval(p, z)
     assert rel_err(out, exact) < 1e-9
+
+
+@pytest.mark.parametrize("D", [2, 5, 64, 130, 300])
+@pytest.mark.parametrize("use_direct,smem_n", [(1, 1024), (0, 16), (1, 32)])
+def test_tree_kernels_general_mode_vs_oracle(E, D, use_direct, smem_n):
+    """KdV (r = -1) and explicit-r inputs take the general 4-entry path (no symmetry)."""
+    rng = np.random.default_rng(1000 + D)
+    t = np.linspace(-6, 6, D)
+    eps_t = 12.0 / max(D - 1, 1)
+    u = np.stack([1.5 / np.cosh(t) ** 2 + 0j, rng.standard_normal(D) * 0.7 + 0j])
+    for scheme in (10, 3):
+        d0 = O.akns_degree(scheme)
+        tm = np.zeros((2, 4, d0 * D + 1), dtype=np.complex128)
+        W = np.zeros(2, dtype=np.int32)
+        assert E.emul_fscatter(np.ascontiguousarray(u), None, 2, D, d0, 1, 0, scheme, eps_t, 1, tm, W,
+                               use_direct, smem_n) == 0
+        for s in range(2):
+            tmo, dego, Wo = O.akns_fscatter(u[s], -np.ones(D), eps_t, scheme)
+            for e in range(4):
+                if np.abs(tmo[e]).sum() > 0:
+                    assert rel_err(tm[s, e] * 2.0 ** W[s], tmo[e] * 2.0 ** Wo) < 1e-12
+    # explicit r
+    q = (rng.standard_normal((1, D)) + 1j * rng.standard_normal((1, D))) * 0.6
+    r = (rng.standard_normal((1, D)) + 1j * rng.standard_normal((1, D))) * 0.6
+    tm = np.zeros((1, 4, 2 * D + 1), dtype=np.complex128)
+    W = np.zeros(1, dtype=np.int32)
+    assert E.emul_fscatter(np.ascontiguousarray(q), r.ctypes.data_as(C.c_void_p), 1, D, 2, 2, 0, 10,
+                           eps_t, 1, tm, W, use_direct, smem_n) == 0
+    tmo, dego, Wo = O.akns_fscatter(q[0], r[0], eps_t, 10)
+    for e in range(4):
+        assert rel_err(tm[0, e] * 2.0 ** W[0], tmo[e] * 2.0 ** Wo) < 1e-12
