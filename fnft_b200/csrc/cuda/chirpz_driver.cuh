@@ -32,12 +32,19 @@ static inline CzGeom cz_geometry(int deg, int M, int row_n = FNFTB_CZ_ROW_N)
     return g;
 }
 
+// elements of the signal-independent tables (tab_y | tab_out | tab_ph | tab_tw)
+static inline size_t cz_table_elems(const CzGeom &g, int deg, int M)
+{
+    return (size_t)(deg + 1) + (size_t)M + 3 * (size_t)M + (size_t)g.L + 8;
+}
+
 // elements needed in ybuf for B signals / in vhat
 static inline size_t cz_ybuf_elems(const CzGeom &g, size_t B, int npoly) { return B * npoly * (size_t)g.L; }
 
 // Fills geometry/plans in `a` (a.deg, a.M, a.B, a.npoly must be set) and runs the
 // whole evaluation: vhat, forward columns, rows, inverse columns + epilogue.
-static inline int cz_run(CzArgs a, fnftb_stream_t st, int row_n = FNFTB_CZ_ROW_N)
+// `tables` must provide cz_table_elems() elements of device scratch.
+static inline int cz_run(CzArgs a, cplx *tables, fnftb_stream_t st, int row_n = FNFTB_CZ_ROW_N)
 {
     const CzGeom g = cz_geometry(a.deg, a.M, row_n);
     a.L = g.L;
@@ -49,6 +56,22 @@ static inline int cz_run(CzArgs a, fnftb_stream_t st, int row_n = FNFTB_CZ_ROW_N
     a.plan2 = make_fft_plan(g.N2);
     const int nt = 256;
     int rc;
+    a.tab_y = tables;
+    a.tab_out = a.tab_y + (a.deg + 1);
+    a.tab_ph = a.tab_out + a.M;
+    a.tab_tw = a.tab_ph + 3 * (size_t)a.M;
+    // 0. signal-independent tables (chirps, four-step twiddles, epilogue phases)
+    {
+        long long tot = a.deg + 1;
+        if (a.M > tot)
+            tot = a.M;
+        if (g.L > tot)
+            tot = g.L;
+        rc = launch_blocks<CzArgs, blk_cz_tables>(a, (unsigned)((tot + nt - 1) / nt), nt, 0, st,
+                                                  "cz_filter");
+        if (rc)
+            return rc;
+    }
     // 1. spectrum of the chirp filter
     {
         CzArgs v = a;

@@ -36,6 +36,12 @@ struct CzArgs {
     double lar, lai; // ln|A|, arg A
     cplx *ybuf;      // [B][npoly][N1][N2]
     cplx *vhat;      // [N1][N2]
+    // signal-independent tables, filled once per call by blk_cz_tables:
+    cplx *tab_y;     // [deg+1]  A^-n W^(n^2/2)
+    cplx *tab_out;   // [M]      W^(m^2/2) / L
+    cplx *tab_tw;    // [N1][N2] four-step twiddle w_L^(n2*k1(pos)), row index = storage position
+    cplx *tab_ph;    // [3][M]   epilogue phases exp(i*xi*ph_rho), exp(i*xi*ph_a), exp(i*xi*ph_b)
+                     //          (KDVV: [0] = exp(2i*xi*kdv_ph), [1] = exp(i*xi*kdv_sqrtz))
     TwTable T;
     int gen_v;       // cz_cols_fwd: 1 = generate the chirp filter v instead of y
     int fwd_only;    // cz_rows: 1 = forward transform only (used for vhat)
@@ -71,6 +77,46 @@ HD cplx chirp_factor(double mag_arg, double li1, double h1, double li2, double h
     return r;
 }
 
+// fills the signal-independent tables; grid covers max(deg+1, M, L) elements
+BLK void blk_cz_tables(const CzArgs &a, blk3 bid, int nt, void *)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long i = (long long)bid.x * nt + tid;
+        if (i <= a.deg) {
+            const double dn = (double)i;
+            a.tab_y[i] = chirp_factor(-a.lar * dn + a.lwr * (0.5 * dn * dn), a.lwi, 0.5 * dn * dn,
+                                      -a.lai, dn);
+        }
+        if (i < a.M) {
+            const double dm = (double)i;
+            a.tab_out[i] = cscale(chirp_factor(a.lwr * (0.5 * dm * dm), a.lwi, 0.5 * dm * dm, 0.0, 0.0),
+                                  1.0 / (double)a.L);
+            double sn, cs;
+            if (a.mode == FNFTB_CZ_NSEV) {
+                const double xi = a.xi0 + a.eps_xi * dm;
+                SINCOS(xi * a.ph_rho, &sn, &cs);
+                a.tab_ph[i] = make_cplx(cs, sn);
+                SINCOS(xi * a.ph_a, &sn, &cs);
+                a.tab_ph[a.M + i] = make_cplx(cs, sn);
+                SINCOS(xi * a.ph_b, &sn, &cs);
+                a.tab_ph[2 * (size_t)a.M + i] = make_cplx(cs, sn);
+            } else if (a.mode == FNFTB_CZ_KDVV) {
+                const double xi = -a.xi0 - dm * a.eps_xi;
+                SINCOS(2.0 * xi * a.kdv_ph, &sn, &cs);
+                a.tab_ph[i] = make_cplx(cs, sn);
+                SINCOS(xi * a.kdv_sqrtz, &sn, &cs);
+                a.tab_ph[a.M + i] = make_cplx(cs, sn);
+            }
+        }
+        if (i < a.L) {
+            const int pos = (int)(i >> ilog2i((unsigned)a.N2)), n2 = (int)(i & (a.N2 - 1));
+            const int k1 = plan_freq_of_pos(a.plan1, pos);
+            a.tab_tw[i] = cispi(-2.0 * (double)(((long long)n2 * k1) & (long long)(a.L - 1)) / (double)a.L);
+        }
+    }
+}
+
 HD size_t cz_cols_smem_bytes(int C, int N1, int npoly) { return sizeof(cplx) * (size_t)C * N1 * npoly; }
 
 // grid.x = B * npoly * (N2 / C)   (gen_v: B = npoly = 1)
@@ -93,10 +139,7 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
             if (!a.gen_v) {
                 if (n < Np) {
                     const cplx p = a.tm[(size_t)s * a.tm_sstride + (size_t)a.ent[j] * Np + (a.deg - n)];
-                    const double dn = (double)n;
-                    const cplx ch = chirp_factor(-a.lar * dn + a.lwr * (0.5 * dn * dn), a.lwi,
-                                                 0.5 * dn * dn, -a.lai, dn);
-                    v = cmul(p, ch);
+                    v = cmul(p, a.tab_y[n]);
                 }
             } else {
                 // fnft__poly_chirpz.c:76-82
@@ -119,9 +162,8 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
         cplx *dst = (a.gen_v ? a.vhat : a.ybuf + (size_t)sj * a.L);
         for (int idx = tid; idx < C * N1; idx += nt) {
             const int c = idx & (C - 1), pos = idx >> a.log2C;
-            const int k1 = plan_freq_of_pos(a.plan1, pos);
             const int n2 = n2_0 + c;
-            const cplx w = cispi(-2.0 * (double)(((long long)n2 * k1) & (long long)(a.L - 1)) / (double)a.L);
+            const cplx w = a.tab_tw[(size_t)pos * N2 + n2];
             dst[(size_t)pos * N2 + n2] = cmul(S[(size_t)c * N1 + swz(pos)], w);
         }
     }
@@ -182,9 +224,8 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
             const cplx *src = a.ybuf + ((size_t)s * a.npoly + j) * a.L;
             for (int idx = tid; idx < C * N1; idx += nt) {
                 const int c = idx & (C - 1), pos = idx >> a.log2C;
-                const int k1 = plan_freq_of_pos(a.plan1, pos);
                 const int n2 = n2_0 + c;
-                const cplx w = cispi(2.0 * (double)(((long long)n2 * k1) & (long long)(a.L - 1)) / (double)a.L);
+                const cplx w = cconj(a.tab_tw[(size_t)pos * N2 + n2]);
                 S[((size_t)j * C + c) * N1 + swz(pos)] = cmul(src[(size_t)pos * N2 + n2], w);
             }
         }
@@ -194,14 +235,12 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
     BLOCK_SYNC();
     FOR_THREADS(tid, nt)
     {
-        const double invL = 1.0 / (double)a.L;
         for (int idx = tid; idx < C * N1; idx += nt) {
             const int c = idx & (C - 1), n1 = idx >> a.log2C;
             const long long m = (long long)n1 * N2 + n2_0 + c;
             if (m >= a.M)
                 continue;
-            const double dm = (double)m;
-            const cplx ch = cscale(chirp_factor(a.lwr * (0.5 * dm * dm), a.lwi, 0.5 * dm * dm, 0.0, 0.0), invL);
+            const cplx ch = a.tab_out[m];
             cplx H[2];
             H[1] = czero();
             for (int j = 0; j < a.npoly; ++j)
@@ -212,8 +251,8 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
                 for (int j = 0; j < a.npoly; ++j)
                     o[(size_t)j * js + m] = H[j];
             } else if (a.mode == FNFTB_CZ_NSEV) {
-                // src/fnft_nsev.c:846-876; H[0] = H11 (a-poly), H[1] = H21 (b-poly)
-                const double xi = a.xi0 + a.eps_xi * dm;
+                // src/fnft_nsev.c:846-876; H[0] = H11 (a-poly), H[1] = H21 (b-poly); the
+                // phases exp(i*xi*phi) come from tab_ph
                 size_t off = 0;
                 if (a.cstype == 0 || a.cstype == 2) {
                     if (H[0].x == 0.0 && H[0].y == 0.0) {
@@ -221,32 +260,22 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
                             a.status[s] = 3;
                         o[m] = make_cplx(NAN, NAN);
                     } else {
-                        double sn, cs;
-                        SINCOS(xi * a.ph_rho, &sn, &cs);
-                        o[m] = cdiv(cmul(H[1], make_cplx(cs, sn)), H[0]);
+                        o[m] = cdiv(cmul(H[1], a.tab_ph[m]), H[0]);
                     }
                     off = a.M;
                 }
                 if (a.cstype == 1 || a.cstype == 2) {
                     const double scale = ldexp(1.0, a.W ? a.W[s] : 0);
-                    double sn, cs;
-                    SINCOS(xi * a.ph_a, &sn, &cs);
-                    o[off + m] = cmul(cscale(H[0], scale), make_cplx(cs, sn));
-                    SINCOS(xi * a.ph_b, &sn, &cs);
-                    o[off + a.M + m] = cmul(cscale(H[1], scale), make_cplx(cs, sn));
+                    o[off + m] = cmul(cscale(H[0], scale), a.tab_ph[a.M + m]);
+                    o[off + a.M + m] = cmul(cscale(H[1], scale), a.tab_ph[2 * (size_t)a.M + m]);
                 }
             } else {
                 // src/fnft_kdvv.c:186-203; H[0] = H12, H[1] = H22, xi grid negated
-                const double xi = -a.xi0 - dm * a.eps_xi;
+                const double xi = -a.xi0 - (double)m * a.eps_xi;
                 cplx h12 = H[0];
-                if (a.kdv_sqrtz != 0.0) {
-                    double sn, cs;
-                    SINCOS(xi * a.kdv_sqrtz, &sn, &cs);
-                    h12 = cdiv(h12, make_cplx(cs, sn));
-                }
-                double sn, cs;
-                SINCOS(2.0 * xi * a.kdv_ph, &sn, &cs);
-                const cplx num = cmul(make_cplx(cs, sn), h12);
+                if (a.kdv_sqrtz != 0.0)
+                    h12 = cdiv(h12, a.tab_ph[a.M + m]);
+                const cplx num = cmul(a.tab_ph[m], h12);
                 // 2*i*xi*H22 - H12
                 const cplx den = make_cplx(-2.0 * xi * H[1].y - h12.x, 2.0 * xi * H[1].x - h12.y);
                 o[m] = cdiv(num, den);

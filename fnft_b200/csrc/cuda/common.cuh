@@ -22,6 +22,7 @@
 #define FOR_THREADS(tid, nt) for (int tid = 0; tid < (nt); ++tid)
 #define BLOCK_SYNC() ((void)0)
 #define TEAM_SYNC(ts, nt) ((void)0)
+#define WARP_MAX(v) (v)
 #define LDG(p) (*(p))
 struct cplx {
     double x, y;
@@ -69,6 +70,15 @@ static inline void emul_sincospi(double a, double *s, double *c)
             asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / (ts)), "r"(ts) : "memory"); \
         }                                                                            \
     } while (0)
+// max over the lanes of a (fully active) warp; the emulation build keeps per-lane values
+#define WARP_MAX(v) fnftb_warp_max(v)
+static __device__ __forceinline__ double fnftb_warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 #ifdef __CUDA_ARCH__
 #define LDG(p) __ldg(p)
 #else

@@ -93,7 +93,7 @@ struct fnftb_ctx {
     size_t tmB = 0;        // number of matrices held
     size_t tm_entries = 4; // 4 for matrices, 1 for a standalone polynomial
     // chirp-z workspace
-    Buf ybuf, vhat, outbuf, pbuf;
+    Buf ybuf, vhat, outbuf, pbuf, cztab;
     // bound-state workspace
     Buf box3, lam, kcnt, flag, aout, apout, bout, phi;
     // nsep workspace
@@ -215,7 +215,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->W,
-                  &c->status, &c->tm, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf,
+                  &c->status, &c->tm, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept};
     for (Buf *b : all)
@@ -427,6 +427,7 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
     const CzGeom g = cz_geometry((int)c->deg, (int)d->M);
     RC(ensure(c->ybuf, cz_ybuf_elems(g, B, d->npoly) * sizeof(cplx)));
     RC(ensure(c->vhat, (size_t)g.L * sizeof(cplx)));
+    RC(ensure(c->cztab, cz_table_elems(g, (int)c->deg, (int)d->M) * sizeof(cplx)));
     cplx *dst = (cplx *)out;
     if (!on_device) {
         RC(ensure(c->outbuf, B * out_sstride * sizeof(cplx)));
@@ -462,7 +463,7 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
     a.kdv_ph = d->kdv_ph;
     a.kdv_sqrtz = d->kdv_sqrtz;
     a.status = (int *)c->status.p;
-    RC(cz_run(a, c->st));
+    RC(cz_run(a, (cplx *)c->cztab.p, c->st));
     if (!on_device) {
         CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     }
@@ -560,6 +561,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
     RC(ensure(c->ybuf, B * 2 * (size_t)g.L * sizeof(cplx)));
     RC(ensure(c->vhat, (size_t)g.L * sizeof(cplx)));
     RC(ensure(c->vals, B * 2 * 3 * Mpts * sizeof(cplx)));
+    RC(ensure(c->cztab, cz_table_elems(g, (int)deg, (int)Mpts) * sizeof(cplx)));
     const size_t cap = deg;  // more than deg roots is an error anyway
     RC(ensure(c->roots, B * 2 * cap * sizeof(cplx)));
     RC(ensure(c->nraw, B * 2 * sizeof(int)));
@@ -617,7 +619,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
             a.out_sstride = (size_t)npoly * 3 * Mpts;
             a.out_jstride = 3 * Mpts;
             a.status = (int *)c->status.p;
-            RC(cz_run(a, c->st));
+            RC(cz_run(a, (cplx *)c->cztab.p, c->st));
         }
         ScanArgs sa;
         memset(&sa, 0, sizeof(sa));

@@ -246,24 +246,22 @@ BLK void blk_tree_low_t(const LowArgs &a, blk3 bid, int nt, void *smem)
         BLOCK_SYNC();
         FOR_THREADS(tid, nt)
         {
-            // operand arrays: index (p*npairs + pair), p = side*E + entry
-            const int total = (NA * npairs) << l2n;
-            for (int idx = tid; idx < total; idx += nt) {
-                const int i = idx & (N - 1);
-                const int pg = idx >> l2n;
-                const int pair = pg % npairs, p = pg / npairs;
-                const int mat = 2 * pair + (p >> L2E);
-                cplx v = czero();
-                if (i < d)
-                    v = cscale(cur[((size_t)mat * E + (p & (E - 1))) * din1 + i], sc[mat]);
-                Y[((size_t)pg << l2n) + swz(i)] = v;
-            }
-            for (int pg = tid; pg < NA * npairs; pg += nt) {
-                const int pair = pg % npairs, p = pg / npairs;
+            // operand arrays: index pg = p*npairs + pair, p = side*E + entry; one warp per
+            // array, lanes run over the coefficients (no divisions in the inner loop)
+            const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+            const int l2p = ilog2i((unsigned)npairs);
+            for (int pg = warp; pg < NA * npairs; pg += nwarps) {
+                const int pair = pg & (npairs - 1), p = pg >> l2p;
                 const int mat = 2 * pair + (p >> L2E);
                 const cplx *x = cur + ((size_t)mat * E + (p & (E - 1))) * din1;
-                top[pg] = cscale(x[d], sc[mat]);
-                bot[pg] = cscale(x[0], sc[mat]);
+                const double scl = sc[mat];
+                cplx *dst = Y + ((size_t)pg << l2n);
+                for (int i = lane; i < N; i += 32)
+                    dst[swz(i)] = (i < d) ? cscale(x[i], scl) : czero();
+                if (lane == 0) {
+                    top[pg] = cscale(x[d], scl);
+                    bot[pg] = cscale(x[0], scl);
+                }
             }
             for (int pidx = tid; pidx < npairs; pidx += nt)
                 mxo[pidx] = 0.0;
@@ -280,22 +278,24 @@ BLK void blk_tree_low_t(const LowArgs &a, blk3 bid, int nt, void *smem)
                 const int pair = idx >> l2n;
                 const double sgn = ((pos >> fs) & 1) ? -1.0 : 1.0;
                 const int ph = swz(pos);
+                cplx *Yb = Y + ((size_t)pair << l2n) + ph;
+                const size_t astr = (size_t)npairs << l2n;  // distance between operand arrays
                 cplx v[NA];
 #pragma unroll
                 for (int p = 0; p < NA; ++p) {
                     const cplx t = top[p * npairs + pair];
-                    const cplx x = Y[((size_t)(p * npairs + pair) << l2n) + ph];
+                    const cplx x = Yb[p * astr];
                     v[p] = make_cplx(x.x + sgn * t.x, x.y + sgn * t.y);
                 }
                 if (SYM) {
-                    const cplx b21 = cscale(cconj(v[3]), -(double)a.kappa * sgn);
-                    const cplx b22 = cscale(cconj(v[2]), sgn);
+                    const double ks = -(double)a.kappa * sgn;
+                    // b21 = ks*conj(v3), b22 = sgn*conj(v2)
                     cplx c11 = cmul(v[0], v[2]);
-                    cfma(c11, v[1], b21);
+                    cfma(c11, v[1], make_cplx(ks * v[3].x, -ks * v[3].y));
                     cplx c12 = cmul(v[0], v[3]);
-                    cfma(c12, v[1], b22);
-                    Y[((size_t)(0 * npairs + pair) << l2n) + ph] = c11;
-                    Y[((size_t)(1 * npairs + pair) << l2n) + ph] = c12;
+                    cfma(c12, v[1], make_cplx(sgn * v[2].x, -sgn * v[2].y));
+                    Yb[0] = c11;
+                    Yb[astr] = c12;
                 } else {
                     constexpr int b = SYM ? 0 : 4;
                     cplx c11 = cmul(v[0], v[b + 0]);
@@ -306,25 +306,25 @@ BLK void blk_tree_low_t(const LowArgs &a, blk3 bid, int nt, void *smem)
                     cfma(c21, v[3], v[b + 2]);
                     cplx c22 = cmul(v[2], v[b + 1]);
                     cfma(c22, v[3], v[b + 3]);
-                    Y[((size_t)(0 * npairs + pair) << l2n) + ph] = c11;
-                    Y[((size_t)(1 * npairs + pair) << l2n) + ph] = c12;
-                    Y[((size_t)(2 * npairs + pair) << l2n) + ph] = c21;
-                    Y[((size_t)(3 * npairs + pair) << l2n) + ph] = c22;
+                    Yb[0] = c11;
+                    Yb[astr] = c12;
+                    Yb[2 * astr] = c21;
+                    Yb[3 * astr] = c22;
                 }
             }
         }
         BLOCK_SYNC();
         FNFTB_SMEM_FFT_INV_R(Y, E * npairs, plan, nt, a.T, MAXR);
         BLOCK_SYNC();
-        // finalize into the (dead) input region: next level's data, n/2 matrices of degree 2d
+        // finalize into the (dead) input region: next level's data, n/2 matrices of degree
+        // 2d.  One warp per (pair, entry): lanes run over the coefficients, the max is
+        // reduced per warp in registers and published with one shared-memory atomic.
         FOR_THREADS(tid, nt)
         {
             const double invN = 1.0 / (double)N;
-            const int per = E * dout1;
-            for (int idx = tid; idx < npairs * per; idx += nt) {
-                const int pair = idx / per, rem = idx - pair * per;
-                const int e = rem / dout1, i = rem - e * dout1;
-                // product of the top coefficients for entry e
+            const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+            for (int pe = warp; pe < npairs * E; pe += nwarps) {
+                const int pair = pe >> L2E, e = pe & (E - 1);
                 cplx ct;
                 if (SYM) {
                     const cplx tA11 = top[0 * npairs + pair], tA12 = top[1 * npairs + pair];
@@ -341,34 +341,32 @@ BLK void blk_tree_low_t(const LowArgs &a, blk3 bid, int nt, void *smem)
                     ct = cmul(top[(row * 2 + 0) * npairs + pair], top[(b + col) * npairs + pair]);
                     cfma(ct, top[(row * 2 + 1) * npairs + pair], top[(b + 2 + col) * npairs + pair]);
                 }
-                cplx v;
-                if (i == N) {
-                    v = ct;
-                } else {
-                    v = cscale(Y[((size_t)(e * npairs + pair) << l2n) + swz(i)], invN);
+                const cplx *src = Y + ((size_t)(e * npairs + pair) << l2n);
+                cplx *dst = cur + (size_t)pe * dout1;  // layout (pair*E + e)*dout1 + i
+                double m2 = 0.0;
+                for (int i = lane; i < N; i += 32) {
+                    cplx v = cscale(src[swz(i)], invN);
                     if (i == 0)
                         v = csub(v, ct);
+                    dst[i] = v;
+                    m2 = fmax(m2, cabs2(v));
                 }
-                cur[idx] = v;  // layout ((pair*E + e)*dout1 + i) == idx
+                if (lane == 0) {
+                    dst[N] = ct;
+                    m2 = fmax(m2, cabs2(ct));
+                }
+                m2 = WARP_MAX(m2);
+#ifndef FNFTB_EMUL
+                if (lane == 0)
+#endif
+                    atomic_max_double(&mxo[pair], m2);  // squared; sqrt taken below
             }
         }
         BLOCK_SYNC();
         FOR_THREADS(tid, nt)
         {
-            // per-pair max|coeff|: 8 chunks per pair, one shared-memory atomic each
-            const int per = E * dout1;
-            const int chunk = (per + 7) / 8;
-            for (int idx = tid; idx < npairs * 8; idx += nt) {
-                const int pair = idx >> 3, c = idx & 7;
-                const cplx *v = cur + (size_t)pair * per;
-                int i1 = (c + 1) * chunk;
-                if (i1 > per)
-                    i1 = per;
-                double m2 = 0.0;
-                for (int i = c * chunk; i < i1; ++i)
-                    m2 = fmax(m2, cabs2(v[i]));
-                atomic_max_double(&mxo[pair], sqrt(m2));
-            }
+            for (int pidx = tid; pidx < npairs; pidx += nt)
+                mxo[pidx] = sqrt(mxo[pidx]);
         }
         BLOCK_SYNC();
         double *tm = mxc;

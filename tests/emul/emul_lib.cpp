@@ -151,7 +151,8 @@ int emul_chirpz(const double *tm, long tm_sstride, int ent0, int ent1, int npoly
     std::vector<cplx> ybuf(cz_ybuf_elems(g, (size_t)B, npoly)), vhat((size_t)g.L);
     a.ybuf = ybuf.data();
     a.vhat = vhat.data();
-    return cz_run(a, NULL, row_n);
+    std::vector<cplx> tables(cz_table_elems(g, deg, M));
+    return cz_run(a, tables.data(), NULL, row_n);
 }
 
 }  // extern "C"
