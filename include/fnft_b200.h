@@ -45,6 +45,37 @@ typedef size_t FNFT_UINT;
 #define FNFT_NAN NAN
 #define FNFT_INF INFINITY
 #define FNFT_PI acos(-1.0)
+/* thin aliases of the C math / complex functions (include/fnft_numtypes.h:64-110), kept
+ * so that sources written against the reference headers compile unchanged */
+#define FNFT_FABS(X) fabs(X)
+#define FNFT_SQRT(X) sqrt(X)
+#define FNFT_COS(X) cos(X)
+#define FNFT_SIN(X) sin(X)
+#define FNFT_SINH(X) sinh(X)
+#define FNFT_COSH(X) cosh(X)
+#define FNFT_ATAN(X) atan(X)
+#define FNFT_ATANH(X) atanh(X)
+#define FNFT_LOG(X) log(X)
+#define FNFT_LOG2(X) log2(X)
+#define FNFT_POW(X, Y) pow(X, Y)
+#define FNFT_GAMMA(X) tgamma(X)
+#define FNFT_FLOOR(X) floor(X)
+#define FNFT_ROUND(X) round(X)
+#define FNFT_CEIL(X) ceil(X)
+#define FNFT_HYPOT(X, Y) hypot(X, Y)
+#define FNFT_CREAL(X) creal(X)
+#define FNFT_CIMAG(X) cimag(X)
+#define FNFT_CABS(X) cabs(X)
+#define FNFT_CARG(X) carg(X)
+#define FNFT_CONJ(X) conj(X)
+#define FNFT_CPOW(X, Y) cpow(X, Y)
+#define FNFT_CEXP(X) cexp(X)
+#define FNFT_CLOG(X) clog(X)
+#define FNFT_CSQRT(X) csqrt(X)
+#define FNFT_CSINH(X) csinh(X)
+#define FNFT_CCOSH(X) ccosh(X)
+#define FNFT_CSIN(X) csin(X)
+#define FNFT_CCOS(X) ccos(X)
 
 /* ---- error codes and message channel: include/fnft_errwarn.h:44-108 ------------ */
 typedef FNFT_INT (*fnft_printf_ptr_t)(const char *, ...);

@@ -1,0 +1,6 @@
+/* Forwarder: programs written against FNFT's `fnft_nsev.h` compile unchanged against
+ * the fnft_b200 drop-in library -- every declaration lives in fnft_b200.h. */
+#ifndef FNFT_B200_SHIM_FNFT_NSEV_H
+#define FNFT_B200_SHIM_FNFT_NSEV_H
+#include "fnft_b200.h"
+#endif

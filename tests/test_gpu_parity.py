@@ -309,3 +309,17 @@ def test_nsep_gridsearch_vs_reference_if_present(F):
         assert len(m0) == len(m1) and len(a0) == len(a1)
         assert np.abs(m1 - m0).max() <= 1e-9 * max(1.0, np.abs(m0).max())
         assert np.abs(a1 - a0).max() <= 1e-9 * max(1.0, np.abs(a0).max())
+
+
+def test_c_example_program_runs(F, tmp_path):
+    """Builds and runs examples/nsev_batch_example.c against the library on the GPU."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "nsev_batch_example")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "nsev_batch_example.c"),
+                           "-L" + os.path.join(root, "fnft_b200", "lib"), "-lfnft_b200",
+                           "-Wl,-rpath," + os.path.join(root, "fnft_b200", "lib"), "-lm", "-o", exe])
+    out = subprocess.check_output([exe]).decode()
+    assert "single: rho" in out and out.count("batch") == 4

@@ -172,3 +172,15 @@ def test_logpolar_resolves_unit_circle_defect(F):
         exact = float((x * x + y * y).ln() / 2)
         assert abs(lr.value - exact) <= 1e-30 + 1e-12 * abs(exact)
         assert abs(li.value - th) < 1e-15
+
+
+def test_c_caller_compiles_and_links_against_the_drop_in_headers(F, tmp_path):
+    """A C program using only the reference's public names builds against include/ and
+    links against libfnft_b200.so (the drop-in claim at the source level)."""
+    import subprocess
+    exe = str(tmp_path / "nsev_batch_example")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "nsev_batch_example.c"),
+                           "-L" + os.path.join(ROOT, "fnft_b200", "lib"), "-lfnft_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "fnft_b200", "lib"), "-lm", "-o", exe])
+    assert os.path.exists(exe)
