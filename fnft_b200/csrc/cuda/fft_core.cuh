@@ -211,6 +211,11 @@ HD void fft_pass_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, int ti
 // Radix plan: as many radix-16 passes as possible, the remainder (8/4/2) LAST so
 // that every earlier pass has stride >= 8 elements (bank-conflict-free together
 // with swz()).  n = 1 gives an empty plan.
+// Radix plan.  The LAST pass always has radix 4 (n >= 4): at stride 1 a pass carries no
+// twiddles, which lets the convolution kernels fuse "last forward pass + pointwise
+// product + first inverse pass" in registers (see fused_pointwise_* in the tree
+// kernels).  The bits before it are covered by radix-16 passes plus one 8/4/2 pass
+// (radix-8 passes only if max_radix < 16).
 HD FftPlan make_fft_plan(int n, int max_radix = 16)
 {
     FftPlan P;
@@ -221,40 +226,37 @@ HD FftPlan make_fft_plan(int n, int max_radix = 16)
         P.radix[i] = 0;
     while ((1 << P.log2n) < n)
         ++P.log2n;
-    int rem = P.log2n;
+    if (P.log2n == 0)
+        return P;
+    if (P.log2n == 1) {
+        P.radix[P.npass++] = 2;
+        return P;
+    }
+    int rem = P.log2n - 2;
     if (max_radix < 16) {
-        // radix-8 passes with the remainder (4/2) last
         while (rem >= 3) {
             P.radix[P.npass++] = 8;
             rem -= 3;
         }
-        if (rem)
-            P.radix[P.npass++] = 1 << rem;
-        return P;
-    }
-    const int tail = rem % 4;  // log2 of the last radix (0 => none)
-    int n16 = rem / 4;
-    // avoid a trailing radix-2 / radix-4 after radix-16s when 8*4 / 8*8 is nicer
-    if (tail == 1 && n16 >= 1) {  // 16*2 -> 8*4
-        n16 -= 1;
-        for (int i = 0; i < n16; ++i)
+    } else {
+        // 16 * 2 -> 8 * 4 so that no radix-2 pass appears next to radix-16 ones
+        while (rem >= 4 && rem != 5 && rem != 6) {
             P.radix[P.npass++] = 16;
-        P.radix[P.npass++] = 8;
-        P.radix[P.npass++] = 4;
-        return P;
+            rem -= 4;
+        }
+        if (rem == 6) {  // 16 * 4 -> 8 * 8 (a radix-4 pass at stride 4 has bank conflicts)
+            P.radix[P.npass++] = 8;
+            P.radix[P.npass++] = 8;
+            rem = 0;
+        }
+        if (rem == 5) {
+            P.radix[P.npass++] = 8;
+            rem -= 3;
+        }
     }
-    if (tail == 2 && n16 >= 1) {  // 16*4 -> 8*8
-        n16 -= 1;
-        for (int i = 0; i < n16; ++i)
-            P.radix[P.npass++] = 16;
-        P.radix[P.npass++] = 8;
-        P.radix[P.npass++] = 8;
-        return P;
-    }
-    for (int i = 0; i < n16; ++i)
-        P.radix[P.npass++] = 16;
-    if (tail)
-        P.radix[P.npass++] = 1 << tail;
+    if (rem)
+        P.radix[P.npass++] = 1 << rem;
+    P.radix[P.npass++] = 4;
     return P;
 }
 
@@ -342,11 +344,17 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
 // BLOCK_SYNC() first.
 #define FNFTB_SMEM_FFT_FWD(S, nfft, P, nt, T) FNFTB_SMEM_FFT_FWD_R(S, nfft, P, nt, T, 16)
 #define FNFTB_SMEM_FFT_INV(S, nfft, P, nt, T) FNFTB_SMEM_FFT_INV_R(S, nfft, P, nt, T, 16)
-#define FNFTB_SMEM_FFT_FWD_R(S, nfft, P, nt, T, MAXR)                                 \
+#define FNFTB_SMEM_FFT_FWD_R(S, nfft, P, nt, T, MAXR) \
+    FNFTB_SMEM_FFT_FWD_SKIP(S, nfft, P, nt, T, MAXR, 0)
+#define FNFTB_SMEM_FFT_INV_R(S, nfft, P, nt, T, MAXR) \
+    FNFTB_SMEM_FFT_INV_SKIP(S, nfft, P, nt, T, MAXR, 0)
+// SKIP = 1 leaves out the stride-1 pass (the last forward / first inverse pass), which the
+// caller then performs itself fused with its pointwise work.
+#define FNFTB_SMEM_FFT_FWD_SKIP(S, nfft, P, nt, T, MAXR, SKIP)                        \
     do {                                                                              \
         int _l2s = (P).log2n;                                                         \
         const int _ts = fft_team_size((P).n, nt);                                     \
-        for (int _p = 0; _p < (P).npass; ++_p) {                                      \
+        for (int _p = 0; _p < (P).npass - (SKIP); ++_p) {                                      \
             const int _R = (P).radix[_p];                                             \
             _l2s -= ilog2i(_R);                                                       \
             FOR_THREADS(tid, nt)                                                      \
@@ -358,11 +366,11 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
     } while (0)
 
 // In-place inverse (unnormalised) transforms, consuming the forward's ordering.
-#define FNFTB_SMEM_FFT_INV_R(S, nfft, P, nt, T, MAXR)                                 \
+#define FNFTB_SMEM_FFT_INV_SKIP(S, nfft, P, nt, T, MAXR, SKIP)                        \
     do {                                                                              \
-        int _l2s = 0;                                                                 \
+        int _l2s = (SKIP) ? ilog2i((P).radix[(P).npass - 1]) : 0;                     \
         const int _ts = fft_team_size((P).n, nt);                                     \
-        for (int _p = (P).npass - 1; _p >= 0; --_p) {                                 \
+        for (int _p = (P).npass - 1 - (SKIP); _p >= 0; --_p) {                                 \
             const int _R = (P).radix[_p];                                             \
             FOR_THREADS(tid, nt)                                                      \
             {                                                                         \

@@ -288,6 +288,118 @@ DEV void atomic_max_double(double *p, double v)
 DEV void atomic_add_int(int *p, int v) { atomicAdd(p, v); }
 #endif
 
+// ---------------------------------------------------------------------------
+// Fused "last forward pass + pointwise 2x2 product + first inverse pass" for plans whose
+// stride-1 pass has radix 4 (no twiddles at stride 1).  One call handles the 4 consecutive
+// storage positions [pos0, pos0+4) of all operand arrays of ONE pair:
+//   arr0   : operand array 0 of the pair; operand array p is at arr0 + p*astr
+//   top    : top coefficient of operand array p at top[p*tstr]   (zero if no wrap)
+//   sgn(j) : (-1)^k of the bin at position pos0+j = sgn_base for rows mode, else from
+//            the first-pass digit (pos >> fs) & 1
+// Results (E arrays) overwrite operand arrays 0..E-1 at the same positions, ready for the
+// remaining inverse passes.
+// ---------------------------------------------------------------------------
+template <bool SYM>
+HD void fused_pointwise4(cplx *arr0, size_t astr, int pos0, const cplx *top, int tstr, int wrap,
+                         int fs, int rows_mode, double sgn_rows, int kappa)
+{
+    int ph[4];
+    double sg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ph[j] = swz(pos0 + j);
+        sg[j] = rows_mode ? sgn_rows : ((((pos0 + j) >> fs) & 1) ? -1.0 : 1.0);
+    }
+    if (SYM) {
+        cplx v[4][4];  // [operand][position]
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[p][j] = arr0[p * astr + ph[j]];
+            Dft<4, -1>::run(v[p]);
+            if (wrap) {
+                const cplx t = top[p * tstr];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[p][j].x += sg[j] * t.x;
+                    v[p][j].y += sg[j] * t.y;
+                }
+            }
+        }
+        cplx c0[4], c1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // B21 = -kappa*(-1)^k conj(B12), B22 = (-1)^k conj(B11)
+            const double ks = -(double)kappa * sg[j];
+            c0[j] = cmul(v[0][j], v[2][j]);
+            cfma(c0[j], v[1][j], make_cplx(ks * v[3][j].x, -ks * v[3][j].y));
+            c1[j] = cmul(v[0][j], v[3][j]);
+            cfma(c1[j], v[1][j], make_cplx(sg[j] * v[2][j].x, -sg[j] * v[2][j].y));
+        }
+        Dft<4, +1>::run(c0);
+        Dft<4, +1>::run(c1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            arr0[ph[j]] = c0[j];
+            arr0[astr + ph[j]] = c1[j];
+        }
+    } else {
+        cplx A[4][4];  // A11, A12, A21, A22
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                A[p][j] = arr0[p * astr + ph[j]];
+            Dft<4, -1>::run(A[p]);
+            if (wrap) {
+                const cplx t = top[p * tstr];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    A[p][j].x += sg[j] * t.x;
+                    A[p][j].y += sg[j] * t.y;
+                }
+            }
+        }
+        cplx out[4][4];
+#pragma unroll
+        for (int col = 0; col < 2; ++col) {
+            cplx B1[4], B2[4];  // B1c, B2c
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                B1[j] = arr0[(4 + col) * astr + ph[j]];
+                B2[j] = arr0[(6 + col) * astr + ph[j]];
+            }
+            Dft<4, -1>::run(B1);
+            Dft<4, -1>::run(B2);
+            if (wrap) {
+                const cplx t1 = top[(4 + col) * tstr], t2 = top[(6 + col) * tstr];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    B1[j].x += sg[j] * t1.x;
+                    B1[j].y += sg[j] * t1.y;
+                    B2[j].x += sg[j] * t2.x;
+                    B2[j].y += sg[j] * t2.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                out[col][j] = cmul(A[0][j], B1[j]);       // C1c = A11*B1c + A12*B2c
+                cfma(out[col][j], A[1][j], B2[j]);
+                out[2 + col][j] = cmul(A[2][j], B1[j]);   // C2c = A21*B1c + A22*B2c
+                cfma(out[2 + col][j], A[3][j], B2[j]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            Dft<4, +1>::run(out[e]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                arr0[e * astr + ph[j]] = out[e][j];
+        }
+    }
+}
+
 struct PairArgs {
     const cplx *in;       // level buffer, n_in matrices of degree d_in per signal
     cplx *out;            // level buffer, n_in/2 matrices of degree 2*d_in
@@ -528,12 +640,26 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
     }
     BLOCK_SYNC();
 
-    // phase B: NA*G forward transforms of length N2
-    FNFTB_SMEM_FFT_FWD_R(S, NA * G, a.plan, nt, a.T, MAXR);
+    // phase B: NA*G forward transforms of length N2 (without the stride-1 pass if fused)
+    const int fs = plan_first_stride_log2(a.plan);
+    const int fuse = (a.plan.npass >= 1 && a.plan.radix[a.plan.npass - 1] == 4) ? 1 : 0;
+    FNFTB_SMEM_FFT_FWD_SKIP(S, NA * G, a.plan, nt, a.T, MAXR, fuse);
     BLOCK_SYNC();
 
     // phase C: pointwise 2x2 products; results overwrite the A-side arrays
-    const int fs = plan_first_stride_log2(a.plan);
+    if (fuse) {
+        FOR_THREADS(tid, nt)
+        {
+            const int l2q = l2n - 2;  // position groups per array (log2)
+            const int total = G << l2q;
+            for (int idx = tid; idx < total; idx += nt) {
+                const int grp = idx & ((1 << l2q) - 1);
+                const int g = idx >> l2q;
+                fused_pointwise4<SYM>(S + ((size_t)g << l2n), (size_t)G << l2n, grp * 4, top + g, G,
+                                      a.wrap, fs, R > 1, (k1 & 1) ? -1.0 : 1.0, a.kappa);
+            }
+        }
+    } else {
     FOR_THREADS(tid, nt)
     {
         const int total = G << l2n;
@@ -557,8 +683,6 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
                 v[p] = make_cplx(x.x + sgn * t.x, x.y + sgn * t.y);
             }
             if (SYM) {
-                // A = (A11, A12) = v[0..1], B = (B11, B12) = v[2..3];
-                // B21 = -kappa*(-1)^k conj(B12), B22 = (-1)^k conj(B11)
                 const cplx b21 = cscale(cconj(v[3]), -(double)a.kappa * sgnk);
                 const cplx b22 = cscale(cconj(v[2]), sgnk);
                 cplx c11 = cmul(v[0], v[2]);
@@ -568,7 +692,6 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
                 S[((size_t)(0 * G + g) << l2n) + ph] = c11;
                 S[((size_t)(1 * G + g) << l2n) + ph] = c12;
             } else {
-                // [A11 A12; A21 A22] * [B11 B12; B21 B22], A = v[0..3], B = v[4..7]
                 constexpr int b = SYM ? 0 : 4;
                 cplx c11 = cmul(v[0], v[b + 0]);
                 cfma(c11, v[1], v[b + 2]);
@@ -585,10 +708,11 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
             }
         }
     }
+    }
     BLOCK_SYNC();
 
-    // phase D: E*G inverse transforms
-    FNFTB_SMEM_FFT_INV_R(S, E * G, a.plan, nt, a.T, MAXR);
+    // phase D: E*G inverse transforms (the stride-1 pass is already done if fused)
+    FNFTB_SMEM_FFT_INV_SKIP(S, E * G, a.plan, nt, a.T, MAXR, fuse);
     BLOCK_SYNC();
 
     // phase E: write out

@@ -267,54 +267,25 @@ BLK void blk_tree_low_t(const LowArgs &a, blk3 bid, int nt, void *smem)
                 mxo[pidx] = 0.0;
         }
         BLOCK_SYNC();
-        FNFTB_SMEM_FFT_FWD_R(Y, NA * npairs, plan, nt, a.T, MAXR);
+        // forward transforms without the stride-1 pass, fused pointwise + first inverse
+        // pass, remaining inverse passes (every FFT level here has N >= 32, so the plan
+        // ends with the radix-4 pass)
+        FNFTB_SMEM_FFT_FWD_SKIP(Y, NA * npairs, plan, nt, a.T, MAXR, 1);
         BLOCK_SYNC();
         const int fs = plan_first_stride_log2(plan);
         FOR_THREADS(tid, nt)
         {
-            const int total = npairs << l2n;
+            const int l2q = l2n - 2;
+            const int total = npairs << l2q;
             for (int idx = tid; idx < total; idx += nt) {
-                const int pos = idx & (N - 1);
-                const int pair = idx >> l2n;
-                const double sgn = ((pos >> fs) & 1) ? -1.0 : 1.0;
-                const int ph = swz(pos);
-                cplx *Yb = Y + ((size_t)pair << l2n) + ph;
-                const size_t astr = (size_t)npairs << l2n;  // distance between operand arrays
-                cplx v[NA];
-#pragma unroll
-                for (int p = 0; p < NA; ++p) {
-                    const cplx t = top[p * npairs + pair];
-                    const cplx x = Yb[p * astr];
-                    v[p] = make_cplx(x.x + sgn * t.x, x.y + sgn * t.y);
-                }
-                if (SYM) {
-                    const double ks = -(double)a.kappa * sgn;
-                    // b21 = ks*conj(v3), b22 = sgn*conj(v2)
-                    cplx c11 = cmul(v[0], v[2]);
-                    cfma(c11, v[1], make_cplx(ks * v[3].x, -ks * v[3].y));
-                    cplx c12 = cmul(v[0], v[3]);
-                    cfma(c12, v[1], make_cplx(sgn * v[2].x, -sgn * v[2].y));
-                    Yb[0] = c11;
-                    Yb[astr] = c12;
-                } else {
-                    constexpr int b = SYM ? 0 : 4;
-                    cplx c11 = cmul(v[0], v[b + 0]);
-                    cfma(c11, v[1], v[b + 2]);
-                    cplx c12 = cmul(v[0], v[b + 1]);
-                    cfma(c12, v[1], v[b + 3]);
-                    cplx c21 = cmul(v[2], v[b + 0]);
-                    cfma(c21, v[3], v[b + 2]);
-                    cplx c22 = cmul(v[2], v[b + 1]);
-                    cfma(c22, v[3], v[b + 3]);
-                    Yb[0] = c11;
-                    Yb[astr] = c12;
-                    Yb[2 * astr] = c21;
-                    Yb[3 * astr] = c22;
-                }
+                const int grp = idx & ((1 << l2q) - 1);
+                const int pair = idx >> l2q;
+                fused_pointwise4<SYM>(Y + ((size_t)pair << l2n), (size_t)npairs << l2n, grp * 4,
+                                      top + pair, npairs, 1, fs, 0, 1.0, a.kappa);
             }
         }
         BLOCK_SYNC();
-        FNFTB_SMEM_FFT_INV_R(Y, E * npairs, plan, nt, a.T, MAXR);
+        FNFTB_SMEM_FFT_INV_SKIP(Y, E * npairs, plan, nt, a.T, MAXR, 1);
         BLOCK_SYNC();
         // finalize into the (dead) input region: next level's data, n/2 matrices of degree
         // 2d.  One warp per (pair, entry): lanes run over the coefficients, the max is

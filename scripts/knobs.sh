@@ -10,8 +10,5 @@ for l in sys.stdin:
 "
 }
 run A=1
-run FNFT_B200_TREE_LOW_S=128
-run FNFT_B200_TREE_LOW_S=64
-run FNFT_B200_TREE_LOW_S=128 FNFT_B200_TREE_SMEM_N=512
+run FNFT_B200_TREE_SMEM_N=512
 run FNFT_B200_MAX_RADIX=8
-run FNFT_B200_TREE_LOW=0
