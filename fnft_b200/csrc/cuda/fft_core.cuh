@@ -233,7 +233,12 @@ HD FftPlan make_fft_plan(int n, int max_radix = 16)
         return P;
     }
     int rem = P.log2n - 2;
-    if (max_radix < 16) {
+    if (max_radix < 8) {
+        while (rem >= 2) {
+            P.radix[P.npass++] = 4;
+            rem -= 2;
+        }
+    } else if (max_radix < 16) {
         while (rem >= 3) {
             P.radix[P.npass++] = 8;
             rem -= 3;
@@ -331,7 +336,10 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
         if constexpr (MAXR >= 16)
             fft_pass_team<16, DIR>(S, f0, nf, log2n, log2s, lane, ts, T);
         break;
-    case 8: fft_pass_team<8, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
+    case 8:
+        if constexpr (MAXR >= 8)
+            fft_pass_team<8, DIR>(S, f0, nf, log2n, log2s, lane, ts, T);
+        break;
     case 4: fft_pass_team<4, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
     case 2: fft_pass_team<2, DIR>(S, f0, nf, log2n, log2s, lane, ts, T); break;
     default: break;

@@ -133,6 +133,11 @@ static inline int launch_pair_fft(const PairArgs &pa, unsigned grid, int nt, siz
                                   fnftb_stream_t st, const char *name, int max_radix, int sym)
 {
     if (sym) {
+        if (max_radix < 8) {
+            if (nt <= 256)
+                return launch_blocks<PairArgs, blk_pair_fft_sym_r4, 256, 6>(pa, grid, nt, smem, st, name);
+            return launch_blocks<PairArgs, blk_pair_fft_sym_r4, 1024, 1>(pa, grid, nt, smem, st, name);
+        }
         if (max_radix < 16) {
             if (nt <= 256)
                 return launch_blocks<PairArgs, blk_pair_fft_sym_r8, 256, 4>(pa, grid, nt, smem, st, name);
@@ -212,9 +217,10 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                 pa.log2G = ilog2i((unsigned)G);
                 pa.log2N2 = ilog2i((unsigned)N);
                 pa.plan = make_fft_plan(N, max_radix);
-                int nt = (NA * G * N) / 16;
-                if (nt > 512)
-                    nt = 512;
+                static const int knob_tpb = tree_knob("FNFT_B200_PAIR_DIV", 16);
+                int nt = (NA * G * N) / knob_tpb;
+                if (nt > (knob_tpb < 16 ? 1024 : 512))
+                    nt = (knob_tpb < 16 ? 1024 : 512);
                 if (nt < 64)
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)((npairs + G - 1) / G);
@@ -227,9 +233,10 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                 pa.log2G = 0;
                 pa.log2N2 = ilog2i((unsigned)smem_n);
                 pa.plan = make_fft_plan(smem_n, max_radix);
-                int nt = (NA * smem_n) / 16;
-                if (nt > 512)
-                    nt = 512;
+                static const int knob_tpb2 = tree_knob("FNFT_B200_PAIR_DIV", 16);
+                int nt = (NA * smem_n) / knob_tpb2;
+                if (nt > (knob_tpb2 < 16 ? 1024 : 512))
+                    nt = (knob_tpb2 < 16 ? 1024 : 512);
                 if (nt < 64)
                     nt = 64;
                 const unsigned grid = (unsigned)B * (unsigned)npairs * (unsigned)pa.R;
@@ -323,8 +330,11 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
         lo.T = T;
         const unsigned grid = (unsigned)B * (unsigned)(npad / S);
         const size_t smem = low_smem_bytes(sym, S, deg0);
-        const int nt = 128;
-        if (sym) {
+        static const int knob_low_nt = tree_knob("FNFT_B200_LOW_NT", 128);
+        const int nt = knob_low_nt;
+        if (sym && max_radix_low < 8) {
+            rc = launch_blocks<LowArgs, blk_tree_low_sym_r4, 512, 2>(lo, grid, nt, smem, st, "tree_low");
+        } else if (sym) {
             if (max_radix_low < 16)
                 rc = launch_blocks<LowArgs, blk_tree_low_sym_r8, 128, 4>(lo, grid, nt, smem, st, "tree_low");
             else

@@ -521,7 +521,7 @@ BLK void blk_pair_direct(const PairArgs &a, blk3 bid, int nt, void * /*smem*/)
 HD size_t pair_smem_bytes(int G, int N2, int nt, int sym)
 {
     const size_t NA = sym ? 4 : 8;
-    return sizeof(cplx) * (NA * G * N2 + 2 * NA * G) + sizeof(double) * (2 * G + nt);
+    return sizeof(cplx) * (NA * G * N2 + 2 * NA * G) + sizeof(double) * (2 * G + (nt > G ? nt : G));
 }
 
 template <int MAXR, bool SYM>
@@ -583,18 +583,22 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
     FOR_THREADS(tid, nt)
     {
         if (R == 1) {
-            const int total = (NA * G) << l2n;
-            for (int idx = tid; idx < total; idx += nt) {
-                const int i = idx & (N2 - 1);
-                const int pg = idx >> l2n;  // p*G + g
+            // one warp per operand array pg = p*G + g, lanes over the coefficients
+            const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+            for (int pg = warp; pg < NA * G; pg += nwarps) {
                 const int g = pg & (G - 1), p = pg >> l2g;
                 const int pair = pair0 + g;
-                cplx v = czero();
-                if (pair < npairs && i < nbody) {
+                cplx *dst = S + ((size_t)pg << l2n);
+                if (pair < npairs) {
                     const size_t mat = (size_t)s * a.n_in + 2 * (size_t)pair + (p >> L2E);
-                    v = cscale(a.in[(mat * E + (p & (E - 1))) * din1 + i], sc[(p >> L2E) * G + g]);
+                    const cplx *x = a.in + (mat * E + (p & (E - 1))) * din1;
+                    const double scl = sc[(p >> L2E) * G + g];
+                    for (int i = lane; i < N2; i += 32)
+                        dst[swz(i)] = (i < nbody) ? cscale(x[i], scl) : czero();
+                } else {
+                    for (int i = lane; i < N2; i += 32)
+                        dst[swz(i)] = czero();
                 }
-                S[((size_t)pg << l2n) + swz(i)] = v;
             }
         } else {
             // y[n2] = w_N^(n2*k1) * sum_{n1<R/2} x[n1*N2+n2] * w_R^(n1*k1)
@@ -729,70 +733,70 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
     }
     const int dout1 = 2 * a.d_in + 1;
     const double invN = 1.0 / (double)a.N;
-    for (int g = 0; g < G; ++g) {
-        const int pair = pair0 + g;
-        if (pair >= npairs)
-            break;
-        FOR_THREADS(tid, nt)
-        {
-            cplx ct[E];
-            if (SYM) {
-                const cplx tA11 = top[0 * G + g], tA12 = top[1 * G + g];
-                const cplx tB11 = top[2 * G + g], tB12 = top[3 * G + g];
-                // top of B21 = -kappa*conj(B12[0]), top of B22 = conj(B11[0])
-                const cplx tB21 = cscale(cconj(bot[3 * G + g]), -(double)a.kappa);
-                const cplx tB22 = cconj(bot[2 * G + g]);
-                ct[0] = cmul(tA11, tB11);
-                cfma(ct[0], tA12, tB21);
-                ct[1] = cmul(tA11, tB12);
-                cfma(ct[1], tA12, tB22);
-            } else {
-                constexpr int b = SYM ? 0 : 4;
-                const cplx tA11 = top[0 * G + g], tA12 = top[1 * G + g], tA21 = top[2 * G + g],
-                           tA22 = top[3 * G + g];
-                const cplx tB11 = top[(b + 0) * G + g], tB12 = top[(b + 1) * G + g],
-                           tB21 = top[(b + 2) * G + g], tB22 = top[(b + 3) * G + g];
-                ct[0] = cmul(tA11, tB11);
-                cfma(ct[0], tA12, tB21);
-                ct[1] = cmul(tA11, tB12);
-                cfma(ct[1], tA12, tB22);
-                ct[E - 2] = cmul(tA21, tB11);
-                cfma(ct[E - 2], tA22, tB21);
-                ct[E - 1] = cmul(tA21, tB12);
-                cfma(ct[E - 1], tA22, tB22);
-            }
-            cplx *o = a.out + ((size_t)s * npairs + pair) * E * dout1;
-            double m2 = 0.0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const cplx *Se = S + ((size_t)(e * G + g) << l2n);
-                cplx *oe = o + (size_t)e * dout1;
-                for (int i = tid; i < dout1; i += nt) {
-                    cplx v;
-                    if (a.wrap && i == a.N) {
-                        v = ct[e];
+    // red[g] collects max |c|^2 of pair g (G <= nt entries of red are free here)
+    FOR_THREADS(tid, nt)
+    {
+        for (int g = tid; g < G; g += nt)
+            red[g] = 0.0;
+    }
+    BLOCK_SYNC();
+    FOR_THREADS(tid, nt)
+    {
+        // one warp per (pair g, entry e): lanes run over the coefficients
+        const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+        for (int ge = warp; ge < G * E; ge += nwarps) {
+            const int g = ge >> L2E, e = ge & (E - 1);
+            const int pair = pair0 + g;
+            if (pair >= npairs)
+                continue;
+            cplx ct = czero();
+            if (a.wrap) {
+                if (SYM) {
+                    const cplx tA11 = top[0 * G + g], tA12 = top[1 * G + g];
+                    if (e == 0) {
+                        // top of B21 = -kappa*conj(B12[0])
+                        ct = cmul(tA11, top[2 * G + g]);
+                        cfma(ct, tA12, cscale(cconj(bot[3 * G + g]), -(double)a.kappa));
                     } else {
-                        v = cscale(Se[swz(i)], invN);
-                        if (a.wrap && i == 0)
-                            v = csub(v, ct[e]);
+                        // top of B22 = conj(B11[0])
+                        ct = cmul(tA11, top[3 * G + g]);
+                        cfma(ct, tA12, cconj(bot[2 * G + g]));
                     }
-                    oe[i] = v;
-                    m2 = fmax(m2, cabs2(v));
+                } else {
+                    constexpr int b = SYM ? 0 : 4;
+                    const int row = e >> 1, col = e & 1;
+                    ct = cmul(top[(row * 2 + 0) * G + g], top[(b + col) * G + g]);
+                    cfma(ct, top[(row * 2 + 1) * G + g], top[(b + 2 + col) * G + g]);
                 }
             }
-            red[tid] = m2;
-        }
-        BLOCK_SYNC();
-        FOR_THREADS(tid, nt)
-        {
-            if (tid == 0) {
-                double m2 = 0.0;
-                for (int t = 0; t < nt; ++t)
-                    m2 = fmax(m2, red[t]);
-                a.mx_out[(size_t)s * npairs + pair] = sqrt(m2);
+            const cplx *Se = S + ((size_t)(e * G + g) << l2n);
+            cplx *oe = a.out + (((size_t)s * npairs + pair) * E + e) * dout1;
+            double m2 = 0.0;
+            const int nfft_out = a.wrap ? a.N : dout1;  // coefficients taken from the transform
+            for (int i = lane; i < nfft_out; i += 32) {
+                cplx v = cscale(Se[swz(i)], invN);
+                if (i == 0)
+                    v = csub(v, ct);  // ct == 0 unless wrap
+                oe[i] = v;
+                m2 = fmax(m2, cabs2(v));
             }
+            if (a.wrap && lane == 0) {
+                oe[a.N] = ct;
+                m2 = fmax(m2, cabs2(ct));
+            }
+            m2 = WARP_MAX(m2);
+#ifndef FNFTB_EMUL
+            if (lane == 0)
+#endif
+                atomic_max_double(&red[g], m2);
         }
-        BLOCK_SYNC();
+    }
+    BLOCK_SYNC();
+    FOR_THREADS(tid, nt)
+    {
+        for (int g = tid; g < G; g += nt)
+            if (pair0 + g < npairs)
+                a.mx_out[(size_t)s * npairs + pair0 + g] = sqrt(red[g]);
     }
 }
 
@@ -811,6 +815,11 @@ BLK void blk_pair_fft_sym(const PairArgs &a, blk3 bid, int nt, void *smem)
 BLK void blk_pair_fft_sym_r8(const PairArgs &a, blk3 bid, int nt, void *smem)
 {
     blk_pair_fft_t<8, true>(a, bid, nt, smem);
+}
+
+BLK void blk_pair_fft_sym_r4(const PairArgs &a, blk3 bid, int nt, void *smem)
+{
+    blk_pair_fft_t<4, true>(a, bid, nt, smem);
 }
 
 // Finishes a row-split product: radix-R inverse column step, 1/N scaling, wrap
@@ -893,18 +902,14 @@ BLK void blk_pair_combine(const PairArgs &a, blk3 bid, int nt, void *smem)
             o[i] = c;
             m2 = fmax(m2, cabs2(c));
         }
-        red[tid] = m2;
-    }
-    BLOCK_SYNC();
-    FOR_THREADS(tid, nt)
-    {
-        if (tid == 0) {
-            double m2 = 0.0;
-            for (int t = 0; t < nt; ++t)
-                m2 = fmax(m2, red[t]);
+        // one atomic per warp (all lanes of a warp belong to the same pair)
+        m2 = WARP_MAX(m2);
+#ifndef FNFTB_EMUL
+        if ((tid & 31) == 0)
+#endif
             atomic_max_double(&a.mx_out[sp], sqrt(m2));
-        }
     }
+    (void)red;
 }
 
 // Final step: apply the pending scale of the single remaining matrix, strip the

@@ -378,3 +378,7 @@ BLK void blk_tree_low_gen_r8(const LowArgs &a, blk3 bid, int nt, void *smem)
 {
     blk_tree_low_t<8, false>(a, bid, nt, smem);
 }
+BLK void blk_tree_low_sym_r4(const LowArgs &a, blk3 bid, int nt, void *smem)
+{
+    blk_tree_low_t<4, true>(a, bid, nt, smem);
+}
