@@ -87,7 +87,7 @@ struct fnftb_ctx {
     const cplx *q = nullptr, *r = nullptr;
     Buf qbuf, rbuf, qpre, warn;
     // tree workspace
-    Buf lev0, lev1, mx0, mx1, gbuf, W, status, tm;
+    Buf lev0, lev1, mx0, mx1, gbuf, colbuf, W, status, tm;
     // result description
     size_t deg = 0;        // degree of the transfer matrices held in tm
     size_t tmB = 0;        // number of matrices held
@@ -214,7 +214,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
         return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
-    Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->W,
+    Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->colbuf, &c->W,
                   &c->status, &c->tm, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept};
@@ -244,7 +244,7 @@ static size_t per_signal_bytes(size_t D, int deg0, size_t M, int npoly)
     size_t b = 0;
     b += 2 * tree_lev_elems(1, npad, (size_t)deg0) * sizeof(cplx);
     b += 2 * npad * sizeof(double);
-    b += tree_gbuf_elems(1, npad, (size_t)deg0) * sizeof(cplx);
+    b += 2 * tree_gbuf_elems(1, npad, (size_t)deg0) * sizeof(cplx);
     b += 4 * ((size_t)deg0 * D + 1) * sizeof(cplx);
     if (M > 0) {
         const CzGeom g = cz_geometry((int)((size_t)deg0 * D), (int)M);
@@ -305,6 +305,7 @@ static int ensure_tree(fnftb_ctx *c, size_t B, size_t npad, size_t deg0, size_t 
     RC(ensure(c->mx0, B * npad * sizeof(double)));
     RC(ensure(c->mx1, B * npad * sizeof(double)));
     RC(ensure(c->gbuf, tree_gbuf_elems(B, npad, deg0) * sizeof(cplx)));
+    RC(ensure(c->colbuf, tree_gbuf_elems(B, npad, deg0) * sizeof(cplx)));
     RC(ensure(c->W, B * sizeof(int)));
     RC(ensure(c->status, B * sizeof(int)));
     RC(ensure(c->tm, B * 4 * (deg_out + 1) * sizeof(cplx)));
@@ -319,6 +320,7 @@ static TreeWork tree_work(fnftb_ctx *c)
     w.mx[0] = (double *)c->mx0.p;
     w.mx[1] = (double *)c->mx1.p;
     w.gbuf = (cplx *)c->gbuf.p;
+    w.colbuf = (cplx *)c->colbuf.p;
     w.W = (int *)c->W.p;
     w.status = (int *)c->status.p;
     return w;

@@ -216,9 +216,9 @@ HD void fft_pass_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, int ti
 // product + first inverse pass" in registers (see fused_pointwise_* in the tree
 // kernels).  The bits before it are covered by radix-16 passes plus one 8/4/2 pass
 // (radix-8 passes only if max_radix < 16).
-HD FftPlan make_fft_plan(int n, int max_radix = 16)
+HD constexpr FftPlan make_fft_plan(int n, int max_radix = 16)
 {
-    FftPlan P;
+    FftPlan P{};
     P.n = n;
     P.log2n = 0;
     P.npass = 0;
@@ -386,5 +386,119 @@ HD void fft_pass_team_dispatch(int R, cplx *S, int nfft, int log2n, int log2s, i
             }                                                                         \
             TEAM_SYNC(_ts, nt);                                                       \
             _l2s += ilog2i(_R);                                                       \
+        }                                                                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Compile-time specialised transforms (length 2^LOG2N, default radix plan): every stride,
+// shift and twiddle step is a constant, so the address arithmetic of a pass folds into
+// immediates.  Used by the product-tree kernels for the lengths they actually run
+// (32 ... 1024); other lengths use the run-time-plan macros above.
+// ---------------------------------------------------------------------------
+HD constexpr int plan_log2_prefix(const FftPlan &P, int npasses)
+{
+    int s = 0;
+    for (int i = 0; i < npasses; ++i) {
+        int r = P.radix[i], l = 0;
+        while ((1 << l) < r)
+            ++l;
+        s += l;
+    }
+    return s;
+}
+
+template <int R, int DIR, int LOG2N, int LOG2S>
+HD void fft_pass_butterfly_ct(cplx *S, int u, const TwTable &T)
+{
+    constexpr int s = 1 << LOG2S;
+    constexpr int LR = Log2R<R>::value;
+    const int g = u >> LOG2S;
+    const int o = u & (s - 1);
+    const int base = (g << (LR + LOG2S)) + o;
+    constexpr int log2len = LR + LOG2S;
+    cplx v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        v[j] = S[swz(base + j * s)];
+    if constexpr (DIR > 0 && LOG2S > 0) {
+        if (o != 0) {
+#pragma unroll
+            for (int j = 1; j < R; ++j)
+                v[j] = cmul(v[j], tw_lookup<+1>(T, j * o, log2len));
+        }
+    }
+    Dft<R, DIR>::run(v);
+    if constexpr (DIR < 0 && LOG2S > 0) {
+        if (o != 0) {
+#pragma unroll
+            for (int j = 1; j < R; ++j)
+                v[j] = cmul(v[j], tw_lookup<-1>(T, j * o, log2len));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        S[swz(base + j * s)] = v[j];
+}
+
+template <int R, int DIR, int LOG2N, int LOG2S>
+HD void fft_pass_team_ct(cplx *S, int nfft, int tid, int nt, int ts, const TwTable &T)
+{
+    constexpr int log2bpf = LOG2N - Log2R<R>::value;
+    const int nteams = nt / ts;
+    const int team = tid / ts, lane = tid - team * ts;
+    const int fpt = (nfft + nteams - 1) / nteams;
+    const int f0 = team * fpt;
+    int nf = nfft - f0;
+    if (nf > fpt)
+        nf = fpt;
+    if (nf <= 0)
+        return;
+    const int nb = nf << log2bpf;
+    for (int b = lane; b < nb; b += ts) {
+        const int f = f0 + (b >> log2bpf);
+        const int u = b & ((1 << log2bpf) - 1);
+        fft_pass_butterfly_ct<R, DIR, LOG2N, LOG2S>(S + ((size_t)f << LOG2N), u, T);
+    }
+}
+
+template <int LOG2N, int DIR, int SKIP, int PASS>
+struct FftRunnerCt {
+    BLK static void run(cplx *S, int nfft, int nt, const TwTable &T)
+    {
+        constexpr FftPlan P = make_fft_plan(1 << LOG2N, 16);
+        constexpr int NP = P.npass - SKIP;
+        if constexpr (PASS < NP) {
+            constexpr int p = (DIR < 0) ? PASS : (NP - 1 - PASS);
+            constexpr int R = P.radix[p];
+            constexpr int L2S = LOG2N - plan_log2_prefix(P, p + 1);
+            const int ts = fft_team_size(1 << LOG2N, nt);
+            FOR_THREADS(tid, nt)
+            {
+                fft_pass_team_ct<R, DIR, LOG2N, L2S>(S, nfft, tid, nt, ts, T);
+            }
+            TEAM_SYNC(ts, nt);
+            FftRunnerCt<LOG2N, DIR, SKIP, PASS + 1>::run(S, nfft, nt, T);
+        }
+    }
+};
+
+// Dispatch on the run-time length: specialised code for 32..1024, generic otherwise.
+// (Same contract as FNFTB_SMEM_FFT_{FWD,INV}_SKIP with the default radix-16 plan.)
+#define FNFTB_SMEM_FFT_CT(DIR, S, nfft, P, nt, T, SKIP)                               \
+    do {                                                                              \
+        switch ((P).log2n) {                                                          \
+        case 5: FftRunnerCt<5, DIR, SKIP, 0>::run((S), (nfft), (nt), (T)); break;     \
+        case 6: FftRunnerCt<6, DIR, SKIP, 0>::run((S), (nfft), (nt), (T)); break;     \
+        case 7: FftRunnerCt<7, DIR, SKIP, 0>::run((S), (nfft), (nt), (T)); break;     \
+        case 8: FftRunnerCt<8, DIR, SKIP, 0>::run((S), (nfft), (nt), (T)); break;     \
+        case 9: FftRunnerCt<9, DIR, SKIP, 0>::run((S), (nfft), (nt), (T)); break;     \
+        case 10: FftRunnerCt<10, DIR, SKIP, 0>::run((S), (nfft), (nt), (T)); break;   \
+        default:                                                                      \
+            if ((DIR) < 0) {                                                          \
+                FNFTB_SMEM_FFT_FWD_SKIP(S, nfft, P, nt, T, 16, SKIP);                 \
+            } else {                                                                  \
+                FNFTB_SMEM_FFT_INV_SKIP(S, nfft, P, nt, T, 16, SKIP);                 \
+            }                                                                         \
+            break;                                                                    \
         }                                                                             \
     } while (0)

@@ -32,6 +32,7 @@ struct TreeWork {
     cplx *lev[2];    // level buffers, each >= B*4*npad*(deg0+1) cplx
     double *mx[2];   // per-matrix max|coeff|, each >= B*npad doubles
     cplx *gbuf;      // >= B*8*npad*deg0 cplx (row-split partial results)
+    cplx *colbuf;    // same size (column-transformed operands of the row-split levels)
     int *W;          // [B]
     int *status;     // [B]
 };
@@ -86,6 +87,19 @@ static inline int launch_direct(const PairArgs &pa, int sym, fnftb_stream_t st)
                                                                         "tree_pair_direct");
     return launch_blocks<PairArgs, blk_pair_direct<DIN, false>, 128>(pa, grid, nt, 0, st,
                                                                      "tree_pair_direct");
+}
+
+template <int R>
+static inline int launch_cols(const PairArgs &pa, int sym, fnftb_stream_t st)
+{
+    const long long total = (long long)pa.B * (pa.n_in / 2) * (sym ? 4 : 8) * pa.N2;
+    const int nt = 128;
+    const unsigned grid = (unsigned)((total + nt - 1) / nt);
+    if (sym)
+        return launch_blocks<PairArgs, blk_pair_cols<R, true>, 128>(pa, grid, nt, 0, st,
+                                                                    "tree_pair_cols");
+    return launch_blocks<PairArgs, blk_pair_cols<R, false>, 128>(pa, grid, nt, 0, st,
+                                                                 "tree_pair_cols");
 }
 
 template <int R>
@@ -179,6 +193,7 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
         pa.mx_out = w.mx[1 - cur];
         pa.W = w.W;
         pa.gbuf = w.gbuf;
+        pa.colbuf = w.colbuf;
         pa.B = B;
         pa.n_in = n;
         pa.d_in = d;
@@ -239,6 +254,21 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
                     nt = (knob_tpb2 < 16 ? 1024 : 512);
                 if (nt < 64)
                     nt = 64;
+                // column step as its own streaming kernel for R >= knob (default 4); for
+                // small R the R/2-term fold inside the rows kernel's load is cheaper
+                static const int knob_col_r = tree_knob("FNFT_B200_TREE_COL_R", 4);
+                pa.use_col = (w.colbuf != nullptr && pa.wrap && pa.R >= knob_col_r && pa.R <= 32) ? 1 : 0;
+                if (pa.use_col) {
+                    switch (pa.R) {
+                    case 2: rc = launch_cols<2>(pa, sym, st); break;
+                    case 4: rc = launch_cols<4>(pa, sym, st); break;
+                    case 8: rc = launch_cols<8>(pa, sym, st); break;
+                    case 16: rc = launch_cols<16>(pa, sym, st); break;
+                    default: rc = launch_cols<32>(pa, sym, st); break;
+                    }
+                    if (rc)
+                        return rc;
+                }
                 const unsigned grid = (unsigned)B * (unsigned)npairs * (unsigned)pa.R;
                 rc = launch_pair_fft(pa, grid, nt, pair_smem_bytes(1, smem_n, nt, sym), st,
                                      level_name("tree_pair_fft_rows", pa.log2N2, pa.R), max_radix, sym);

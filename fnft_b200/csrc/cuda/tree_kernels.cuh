@@ -407,6 +407,8 @@ struct PairArgs {
     double *mx_out;       // [B][n_in/2]  (must be zeroed when atomics are used)
     int *W;               // [B]
     cplx *gbuf;           // [B][pairs][E][R][N2] partial row results (R > 1)
+    cplx *colbuf;         // [B][pairs][NA][R][N2] column-transformed operands (R > 1, use_col)
+    int use_col;          // 1: blk_pair_cols ran before the rows kernel
     int B, n_in, d_in;
     int normalize;
     int kappa;    // SYM mode only
@@ -600,6 +602,16 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
                         dst[swz(i)] = czero();
                 }
             }
+        } else if (a.use_col) {
+            // operands were column-transformed (and scaled) by blk_pair_cols: plain row load
+            const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+            const cplx *cb = a.colbuf + ((((size_t)s * npairs + pair0) * NA) * (size_t)R << l2n);
+            for (int p = warp; p < NA; p += nwarps) {
+                const cplx *x = cb + (((size_t)p * R + k1) << l2n);
+                cplx *dst = S + ((size_t)p << l2n);
+                for (int i = lane; i < N2; i += 32)
+                    dst[swz(i)] = x[i];
+            }
         } else {
             // y[n2] = w_N^(n2*k1) * sum_{n1<R/2} x[n1*N2+n2] * w_R^(n1*k1)
             const int half = R / 2;
@@ -647,7 +659,11 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
     // phase B: NA*G forward transforms of length N2 (without the stride-1 pass if fused)
     const int fs = plan_first_stride_log2(a.plan);
     const int fuse = (a.plan.npass >= 1 && a.plan.radix[a.plan.npass - 1] == 4) ? 1 : 0;
-    FNFTB_SMEM_FFT_FWD_SKIP(S, NA * G, a.plan, nt, a.T, MAXR, fuse);
+    if (MAXR == 16 && fuse) {
+        FNFTB_SMEM_FFT_CT(-1, S, NA * G, a.plan, nt, a.T, 1);
+    } else {
+        FNFTB_SMEM_FFT_FWD_SKIP(S, NA * G, a.plan, nt, a.T, MAXR, fuse);
+    }
     BLOCK_SYNC();
 
     // phase C: pointwise 2x2 products; results overwrite the A-side arrays
@@ -716,7 +732,11 @@ BLK void blk_pair_fft_t(const PairArgs &a, blk3 bid, int nt, void *smem)
     BLOCK_SYNC();
 
     // phase D: E*G inverse transforms (the stride-1 pass is already done if fused)
-    FNFTB_SMEM_FFT_INV_SKIP(S, E * G, a.plan, nt, a.T, MAXR, fuse);
+    if (MAXR == 16 && fuse) {
+        FNFTB_SMEM_FFT_CT(+1, S, E * G, a.plan, nt, a.T, 1);
+    } else {
+        FNFTB_SMEM_FFT_INV_SKIP(S, E * G, a.plan, nt, a.T, MAXR, fuse);
+    }
     BLOCK_SYNC();
 
     // phase E: write out
@@ -820,6 +840,52 @@ BLK void blk_pair_fft_sym_r8(const PairArgs &a, blk3 bid, int nt, void *smem)
 BLK void blk_pair_fft_sym_r4(const PairArgs &a, blk3 bid, int nt, void *smem)
 {
     blk_pair_fft_t<4, true>(a, bid, nt, smem);
+}
+
+// Column step of the four-step transform for the row-split levels: for every operand
+// array (signal, pair, p) and column n2 the R-point DFT over n1 of x[n1*N2 + n2] (upper
+// half of the inputs is zero), times w_N^(n2*k1), times the pending power-of-two scale.
+// One thread per (array, n2); loads and stores are coalesced across n2.
+// grid.x * nt = B * npairs * NA * N2
+template <int R, bool SYM>
+BLK void blk_pair_cols(const PairArgs &a, blk3 bid, int nt, void *)
+{
+    constexpr int E = SYM ? 2 : 4;
+    constexpr int NA = 2 * E;
+    constexpr int L2E = SYM ? 1 : 2;
+    FOR_THREADS(tid, nt)
+    {
+        const int npairs = a.n_in / 2;
+        const int N2 = a.N2, l2n = a.log2N2;
+        const long long gid = (long long)bid.x * nt + tid;
+        const int n2 = (int)(gid & (N2 - 1));
+        const long long arr = gid >> l2n;  // (s*npairs + pair)*NA + p
+        if (arr < (long long)a.B * npairs * NA) {
+            const int p = (int)(arr % NA);
+            const long long sp = arr / NA;
+            const size_t mat = (size_t)sp * 2 + (p >> L2E);  // s*n_in + 2*pair + side
+            const int din1 = a.d_in + 1;
+            const int nbody = a.wrap ? a.d_in : din1;
+            const cplx *x = a.in + (mat * E + (p & (E - 1))) * din1;
+            int ex;
+            const double scl = load_scale(a, mat, &ex);
+            cplx v[R];
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) {
+                const int i = (n1 << l2n) + n2;
+                v[n1] = (n1 < R / 2 && i < nbody) ? cscale(x[i], scl) : czero();
+            }
+            Dft<R, -1>::run(v);
+            const cplx w1 = cispi(-2.0 * (double)n2 / (double)a.N);
+            cplx w = make_cplx(1.0, 0.0);
+            cplx *o = a.colbuf + (((size_t)arr * R) << l2n) + n2;
+#pragma unroll
+            for (int k1 = 0; k1 < R; ++k1) {
+                o[(size_t)k1 << l2n] = cmul(v[k1], w);
+                w = cmul(w, w1);
+            }
+        }
+    }
 }
 
 // Finishes a row-split product: radix-R inverse column step, 1/N scaling, wrap

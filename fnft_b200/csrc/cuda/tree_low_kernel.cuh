@@ -270,7 +270,11 @@ BLK void blk_tree_low_t(const LowArgs &a, blk3 bid, int nt, void *smem)
         // forward transforms without the stride-1 pass, fused pointwise + first inverse
         // pass, remaining inverse passes (every FFT level here has N >= 32, so the plan
         // ends with the radix-4 pass)
-        FNFTB_SMEM_FFT_FWD_SKIP(Y, NA * npairs, plan, nt, a.T, MAXR, 1);
+        if constexpr (MAXR == 16) {
+            FNFTB_SMEM_FFT_CT(-1, Y, NA * npairs, plan, nt, a.T, 1);
+        } else {
+            FNFTB_SMEM_FFT_FWD_SKIP(Y, NA * npairs, plan, nt, a.T, MAXR, 1);
+        }
         BLOCK_SYNC();
         const int fs = plan_first_stride_log2(plan);
         FOR_THREADS(tid, nt)
@@ -285,7 +289,11 @@ BLK void blk_tree_low_t(const LowArgs &a, blk3 bid, int nt, void *smem)
             }
         }
         BLOCK_SYNC();
-        FNFTB_SMEM_FFT_INV_SKIP(Y, E * npairs, plan, nt, a.T, MAXR, 1);
+        if constexpr (MAXR == 16) {
+            FNFTB_SMEM_FFT_CT(+1, Y, E * npairs, plan, nt, a.T, 1);
+        } else {
+            FNFTB_SMEM_FFT_INV_SKIP(Y, E * npairs, plan, nt, a.T, MAXR, 1);
+        }
         BLOCK_SYNC();
         // finalize into the (dead) input region: next level's data, n/2 matrices of degree
         // 2d.  One warp per (pair, entry): lanes run over the coefficients, the max is

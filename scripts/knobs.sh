@@ -10,7 +10,4 @@ for l in sys.stdin:
 "
 }
 run A=1
-run FNFT_B200_LOW_NT=256
-run FNFT_B200_MAX_RADIX=4 FNFT_B200_LOW_NT=256 FNFT_B200_PAIR_DIV=8
-run FNFT_B200_MAX_RADIX=4 FNFT_B200_LOW_NT=512 FNFT_B200_PAIR_DIV=4
-run FNFT_B200_MAX_RADIX=8 FNFT_B200_LOW_NT=256 FNFT_B200_PAIR_DIV=8
+run A=2

@@ -25,19 +25,20 @@ static TwTable get_tw()
 }
 
 struct Work {
-    std::vector<cplx> lev0, lev1, gbuf;
+    std::vector<cplx> lev0, lev1, gbuf, colbuf;
     std::vector<double> mx0, mx1;
     std::vector<int> W, status;
     TreeWork w;
     Work(size_t B, size_t npad, size_t deg0)
         : lev0(tree_lev_elems(B, npad, deg0)), lev1(tree_lev_elems(B, npad, deg0)),
-          gbuf(tree_gbuf_elems(B, npad, deg0)), mx0(B * npad), mx1(B * npad), W(B), status(B)
+          gbuf(tree_gbuf_elems(B, npad, deg0)), colbuf(tree_gbuf_elems(B, npad, deg0)), mx0(B * npad), mx1(B * npad), W(B), status(B)
     {
         w.lev[0] = lev0.data();
         w.lev[1] = lev1.data();
         w.mx[0] = mx0.data();
         w.mx[1] = mx1.data();
         w.gbuf = gbuf.data();
+        w.colbuf = colbuf.data();
         w.W = W.data();
         w.status = status.data();
     }
