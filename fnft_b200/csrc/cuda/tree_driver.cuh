@@ -5,6 +5,7 @@
 #include "launch.cuh"
 #include "tree_kernels.cuh"
 #include "tree_low_kernel.cuh"
+#include "tree_low2.cuh"
 
 #ifdef FNFTB_EMUL
 static inline void dev_memset0(void *p, size_t bytes, fnftb_stream_t) { memset(p, 0, bytes); }
@@ -333,6 +334,42 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
     static const int max_radix_low = tree_knob("FNFT_B200_MAX_RADIX", 16);
     int rc;
     int n_start = npad, d_start = deg0;
+#ifndef FNFTB_EMUL
+    // spectrum-carry kernel (tree_low2.cuh): first-row-only mode, M*8/deg0 samples per CTA
+    static const int knob_low2 = tree_knob("FNFT_B200_TREE_LOW2", 7);  // 0 off, 6 or 7 = log2(M)
+    bool low2_done = false;
+    if (knob_low && knob_low2 && sym && use_direct && T.log2twn == 12 && r == nullptr) {
+        int log2m = (knob_low2 == 6) ? 6 : 7;
+        if (low2_samples(log2m, deg0) > npad)
+            log2m = 6;
+        const int S2 = low2_samples(log2m, deg0);
+        if (S2 <= npad) {
+            Low2Args lo;
+            memset(&lo, 0, sizeof(lo));
+            lo.q = q;
+            lo.out = w.lev[0];
+            lo.mx_out = w.mx[0];
+            lo.W = w.W;
+            lo.status = w.status;
+            lo.tw = T.tw;
+            lo.B = B;
+            lo.D = D;
+            lo.npad = npad;
+            lo.kappa = kappa;
+            lo.scheme = scheme;
+            lo.normalize = normalize;
+            lo.eps_t = eps_t;
+            rc = low2_launch(lo, log2m, deg0, st);
+            if (rc)
+                return rc;
+            n_start = npad / S2;
+            d_start = deg0 * S2;
+            low2_done = true;
+        }
+    }
+    if (low2_done) {
+    } else
+#endif
     if (knob_low && (deg0 == 1 || deg0 == 2) && use_direct) {
         // fused low levels: blocks of S samples -> one matrix of degree deg0*S per block
         int S = knob_low_s > 0 ? knob_low_s : (sym ? 256 : 128);
