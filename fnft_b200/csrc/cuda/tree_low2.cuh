@@ -94,18 +94,76 @@ DEV void sym_prod(const cplx *a1, const cplx *b1, const cplx *a2, const cplx *b2
     }
 }
 
+// generic leaf (any scheme the leaf switch knows): kept out of line, it is large
+template <int DEG0>
+__device__ __noinline__ void low2_leaf_generic(int scheme, double eps_t, double qx, double qy, double kap,
+                                               cplx *AB /* [2][DEG0+1] */, int *err)
+{
+    const cplx q = make_cplx(qx, qy);
+    const cplx r = (kap > 0.0) ? make_cplx(-qx, qy) : make_cplx(qx, -qy);
+    cplx p[4 * (DEG0 + 1)];
+    leaf_matrix(p, scheme, DEG0, eps_t, q, r, err);
+#pragma unroll
+    for (int i = 0; i < 2 * (DEG0 + 1); ++i)
+        AB[i] = p[i];
+}
+
+// 2SPLIT4B / 4SPLIT4B leaf for r = -kappa*conj(q) (fnft__akns_fscatter.c:402-433 with
+// -q*r = kappa*|q|^2 real): Delta = h*|q| (kappa = +1) or i*h*|q| (kappa = -1), so the
+// zero-frequency exponentials E(h) = (cos D, q*h*sinc D, r*h*sinc D) need one real
+// sincos / sinh-cosh of x = eps*|q|/4 and the double-angle formulas for 2x.  With
+// a_1 a_2 = -kappa*alpha^2*|q|^2 the entry p11 has real coefficients and p12 = q * real.
+DEV void low2_leaf_4b(double eps_t, cplx q, double kap, cplx *A, cplx *B)
+{
+    const double m2 = q.x * q.x + q.y * q.y;
+    const double m = sqrt(m2);
+    const double ha = 0.25 * eps_t, hb = 0.5 * eps_t;
+    const double x = ha * m;
+    double c1, c2, sa, sb;  // cos D_a, cos D_b, sinc D_a, sinc D_b
+    if (kap > 0.0) {
+        double sn, cs;
+        sincos(x, &sn, &cs);
+        c1 = cs;
+        c2 = 1.0 - 2.0 * sn * sn;
+        const double s2 = 2.0 * sn * cs;
+        sa = (x >= 1.0e-8) ? sn / x : 1.0;            // misc_CSINC threshold (fnft__misc.c:306-314)
+        sb = (2.0 * x >= 1.0e-8) ? s2 / (2.0 * x) : 1.0;
+    } else {
+        const double sh = sinh(x), ch = cosh(x);
+        c1 = ch;
+        c2 = 1.0 + 2.0 * sh * sh;
+        const double s2 = 2.0 * sh * ch;
+        sa = (x >= 1.0e-8) ? sh / x : 1.0;
+        sb = (2.0 * x >= 1.0e-8) ? s2 / (2.0 * x) : 1.0;
+    }
+    const double al = ha * sa, be = hb * sb;           // a_1 = q*al, a_2 = r*al, b_1 = q*be, b_2 = r*be
+    const double qr = -kap * m2;                       // q*r
+    const double third = 1.0 / 3.0;
+    A[0] = make_cplx((4.0 * c2 * al * al - be * be) * qr * third, 0.0);
+    A[1] = make_cplx(8.0 * c1 * al * be * qr * third, 0.0);
+    A[2] = make_cplx(c2 * (4.0 * c1 * c1 - c2) * third, 0.0);
+    const double g0 = c2 * (4.0 * c1 * al - be) * third;
+    const double g1 = 4.0 * be * (c1 * c1 + al * al * qr) * third;
+    B[0] = make_cplx(q.x * g0, q.y * g0);
+    B[1] = make_cplx(q.x * g1, q.y * g1);
+    B[2] = B[0];
+}
+
 template <int DEG0>
 DEV void low2_leaf(const Low2Args &a, int s, int mg, cplx *A, cplx *B, int *err)
 {
     if (mg < a.D) {
         const cplx q = a.q[(size_t)s * a.D + (size_t)(a.D - 1 - mg)];
-        const cplx r = (a.kappa == 1) ? make_cplx(-q.x, q.y) : make_cplx(q.x, -q.y);
-        cplx p[4 * (DEG0 + 1)];
-        leaf_matrix(p, a.scheme, DEG0, a.eps_t, q, r, err);
+        if (DEG0 == 2 && (a.scheme == FNFTB_AKNS_2SPLIT4B || a.scheme == FNFTB_AKNS_4SPLIT4B)) {
+            low2_leaf_4b(a.eps_t, q, (double)a.kappa, A, B);
+        } else {
+            cplx AB[2 * (DEG0 + 1)];
+            low2_leaf_generic<DEG0>(a.scheme, a.eps_t, q.x, q.y, (double)a.kappa, AB, err);
 #pragma unroll
-        for (int i = 0; i <= DEG0; ++i) {
-            A[i] = p[i];
-            B[i] = p[DEG0 + 1 + i];
+            for (int i = 0; i <= DEG0; ++i) {
+                A[i] = AB[i];
+                B[i] = AB[DEG0 + 1 + i];
+            }
         }
     } else {  // padding diag(z^deg, 1) keeps the structure (tree_kernels.cuh header)
 #pragma unroll
