@@ -87,7 +87,8 @@ struct fnftb_ctx {
     const cplx *q = nullptr, *r = nullptr;
     Buf qbuf, rbuf, qpre, warn;
     // tree workspace
-    Buf lev0, lev1, mx0, mx1, gbuf, colbuf, W, status, tm;
+    Buf lev0, lev1, mx0, mx1, gbuf, colbuf, W, status, tm, tt0, tt1, twmem;
+    TwSet tws;
     // result description
     size_t deg = 0;        // degree of the transfer matrices held in tm
     size_t tmB = 0;        // number of matrices held
@@ -204,6 +205,14 @@ int fnftb_ctx_create(fnftb_ctx **out, int device)
     fnftb_fill_twiddles(tw.data(), (size_t)c->twn);
     CU(cudaMalloc((void **)&c->tw, sizeof(cplx) * c->twn));
     CU(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * c->twn, cudaMemcpyHostToDevice));
+    {
+        // pass-major twiddle tables of the spectrum-carry tree kernels (tw_tables.cuh)
+        TwSet tmp;
+        const size_t n = twset_layout(&tmp);
+        RC(ensure(c->twmem, n * sizeof(cplx)));
+        RC(twset_build(&c->tws, (cplx *)c->twmem.p, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
     *out = c;
     return 0;
 }
@@ -215,7 +224,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->colbuf, &c->W,
-                  &c->status, &c->tm, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
+                  &c->status, &c->tm, &c->tt0, &c->tt1, &c->twmem, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept};
     for (Buf *b : all)
@@ -309,6 +318,8 @@ static int ensure_tree(fnftb_ctx *c, size_t B, size_t npad, size_t deg0, size_t 
     RC(ensure(c->W, B * sizeof(int)));
     RC(ensure(c->status, B * sizeof(int)));
     RC(ensure(c->tm, B * 4 * (deg_out + 1) * sizeof(cplx)));
+    RC(ensure(c->tt0, (B * npad / 256 + 1) * 4 * sizeof(cplx)));
+    RC(ensure(c->tt1, (B * npad / 256 + 1) * 4 * sizeof(cplx)));
     return 0;
 }
 
@@ -323,6 +334,9 @@ static TreeWork tree_work(fnftb_ctx *c)
     w.colbuf = (cplx *)c->colbuf.p;
     w.W = (int *)c->W.p;
     w.status = (int *)c->status.p;
+    w.tt[0] = c->tt0.p;
+    w.tt[1] = c->tt1.p;
+    w.tws = &c->tws;
     return w;
 }
 

@@ -6,6 +6,7 @@
 #include "tree_kernels.cuh"
 #include "tree_low_kernel.cuh"
 #include "tree_low2.cuh"
+#include "tree_up.cuh"
 
 #ifdef FNFTB_EMUL
 static inline void dev_memset0(void *p, size_t bytes, fnftb_stream_t) { memset(p, 0, bytes); }
@@ -36,6 +37,8 @@ struct TreeWork {
     cplx *colbuf;    // same size (column-transformed operands of the row-split levels)
     int *W;          // [B]
     int *status;     // [B]
+    void *tt[2];     // spectrum path: top/bottom coefficients per matrix (Low2Tops), ping-pong
+    const void *tws; // spectrum path: TwSet (tw_tables.cuh), NULL disables the path
 };
 
 // workspace sizes (elements) for B signals of npad matrices of degree deg0
@@ -335,15 +338,24 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
     int rc;
     int n_start = npad, d_start = deg0;
 #ifndef FNFTB_EMUL
-    // spectrum-carry kernel (tree_low2.cuh): first-row-only mode, M*8/deg0 samples per CTA
+    // spectrum-carry path (tree_low2.cuh + tree_up.cuh): first-row-only mode; the low kernel
+    // handles M*8/deg0 samples per CTA, the upper levels stay in "values at the roots of
+    // unity" form until the last one
     static const int knob_low2 = tree_knob("FNFT_B200_TREE_LOW2", 7);  // 0 off, 6 or 7 = log2(M)
+    static const int knob_up = tree_knob("FNFT_B200_TREE_UP", 1);      // 0: old upper levels
+    static const int knob_up_smem = tree_knob("FNFT_B200_UP_SMEM_L2", 13);
     bool low2_done = false;
-    if (knob_low && knob_low2 && sym && use_direct && T.log2twn == 12 && r == nullptr) {
+    if (knob_low && knob_low2 && sym && use_direct && w.tws != nullptr && r == nullptr) {
         int log2m = (knob_low2 == 6) ? 6 : 7;
         if (low2_samples(log2m, deg0) > npad)
             log2m = 6;
         const int S2 = low2_samples(log2m, deg0);
         if (S2 <= npad) {
+            const int n_low = npad / S2;
+            int l2n0 = ilog2i((unsigned)(2 * deg0 * S2));  // operand length of the first upper level
+            bool spec = knob_up && n_low >= 2 && w.tt[0] != nullptr;
+            for (int n = n_low, l = l2n0; spec && n >= 2; n /= 2, ++l)
+                spec = up_supported(l, knob_up_smem);
             Low2Args lo;
             memset(&lo, 0, sizeof(lo));
             lo.q = q;
@@ -351,7 +363,9 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
             lo.mx_out = w.mx[0];
             lo.W = w.W;
             lo.status = w.status;
-            lo.tw = T.tw;
+            lo.tw = *(const TwSet *)w.tws;
+            lo.tt_out = (Low2Tops *)w.tt[0];
+            lo.spec_out = spec ? 1 : 0;
             lo.B = B;
             lo.D = D;
             lo.npad = npad;
@@ -362,9 +376,36 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
             rc = low2_launch(lo, log2m, deg0, st);
             if (rc)
                 return rc;
-            n_start = npad / S2;
+            n_start = n_low;
             d_start = deg0 * S2;
             low2_done = true;
+            if (spec) {
+                int cur = 0;
+                for (int n = n_low, l = l2n0; n >= 2; n /= 2, ++l) {
+                    UpArgs ua;
+                    memset(&ua, 0, sizeof(ua));
+                    ua.in = w.lev[cur];
+                    ua.out = w.lev[1 - cur];
+                    ua.tt_in = (const Low2Tops *)w.tt[cur];
+                    ua.tt_out = (Low2Tops *)w.tt[1 - cur];
+                    ua.mx_in = w.mx[cur];
+                    ua.mx_out = w.mx[1 - cur];
+                    ua.W = w.W;
+                    ua.ws = w.gbuf;
+                    ua.B = B;
+                    ua.n_in = n;
+                    ua.l2n = l;
+                    ua.normalize = normalize;
+                    ua.kappa = kappa;
+                    ua.last = (n == 2) ? 1 : 0;
+                    ua.tw = *(const TwSet *)w.tws;
+                    rc = up_level(ua, knob_up_smem, st);
+                    if (rc)
+                        return rc;
+                    cur = 1 - cur;
+                }
+                return tree_finalize(w, cur, B, deg0 * npad, deg0 * D, normalize, tm, st, sym, kappa);
+            }
         }
     }
     if (low2_done) {

@@ -32,6 +32,11 @@
 #pragma once
 #ifndef FNFTB_EMUL
 #include "tree_kernels.cuh"
+#include "tw_tables.cuh"
+
+struct Low2Tops {
+    cplx ta, tb, ba, bb;  // top (index d) and bottom (index 0) coefficients of a and b
+};
 
 struct Low2Args {
     const cplx *q;   // [B][D]
@@ -39,7 +44,10 @@ struct Low2Args {
     double *mx_out;  // [B][npad/S]
     int *W;          // [B]
     int *status;     // [B]
-    const cplx *tw;  // tw[k] = exp(-2*pi*i*k/4096)
+    TwSet tw;        // pass-major twiddle tables (tw_tables.cuh)
+    Low2Tops *tt_out;  // [B][npad/S] tops of the results (spec_out only)
+    int spec_out;    // 1: write the result as values at the 2*deg roots of unity (bit-reversed),
+                     //    layout [a: 2N][b: 2N] per matrix, for tree_up.cuh; 0: coefficients
     int B, D, npad;
     int kappa, scheme, normalize;
     double eps_t;
@@ -222,10 +230,6 @@ DEV void low2_front_fft16(const cplx *x, cplx *S, int base)
     }
 }
 
-struct Low2Tops {
-    cplx ta, tb, ba, bb;  // top (index d) and bottom (index 0) coefficients of a and b
-};
-
 // tops of the pair product A*B (fnft__poly_fmult.c pair product restricted to the extreme
 // coefficients), times the pending factor f
 DEV Low2Tops low2_pair_tops(const Low2Tops &A, const Low2Tops &B, double kap, double f)
@@ -253,7 +257,8 @@ DEV Low2Tops low2_pair_tops(const Low2Tops &A, const Low2Tops &B, double kap, do
 // values are only needed as the input of the inverse transform.
 // ---------------------------------------------------------------------------------------
 template <int LOG2M>
-DEV void low2_x_stage(cplx *S, const Low2Tops *TTc, int t, int l2n, bool first, bool last, double kap)
+DEV void low2_x_stage(cplx *S, const Low2Tops *TTc, int t, int l2n, bool first, bool last, double kap,
+                          cplx *gout)
 {
     const int N = 1 << l2n;
     const int l2g = l2n - 3;
@@ -305,6 +310,12 @@ DEV void low2_x_stage(cplx *S, const Low2Tops *TTc, int t, int l2n, bool first, 
                 S[ad[0] ^ j] = ca[j];
                 S[ad[2] ^ j] = cb[j];
             }
+        } else if (gout) {  // even bins of the result spectrum (single pair: p == 0)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                gout[4 * g + j] = ca[j];
+                gout[(2 << l2n) + 4 * g + j] = cb[j];
+            }
         }
         // first inverse pass (radix 4, stride 1, bit-reversed input)
         cplx t1 = ca[1];
@@ -334,12 +345,13 @@ DEV int low2_wbase(int p, int which, int l2n)
 // input), DIR = -1: forward (DIF, bit-reversed output).
 // ---------------------------------------------------------------------------------------
 template <int LOG2M, int R, int DIR>
-DEV void low2_p_pass(cplx *S, const cplx *tw, int t, int l2n, int sb)
+DEV void low2_p_pass(cplx *S, const TwSet &tw, int t, int l2n, int sb)
 {
     constexpr int M = 1 << LOG2M;
     constexpr int LR = Log2R<R>::value;
     constexpr int PER = 16 / R;  // items per thread
     const int l2gr = l2n - 2 - LR;  // groups per array (log2)
+    const cplx *pt = tw.base + tw.pass_off[LR + 2][LR];  // [q-1][o], o < 4
 #pragma unroll 1
     for (int k = 0; k < PER; ++k) {
         const int idx = swapbit2(t + k * M, sb);
@@ -355,7 +367,7 @@ DEV void low2_p_pass(cplx *S, const cplx *tw, int t, int l2n, int sb)
                 v[q] = S[swz2(base + 4 * brev_c(q, LR))];
 #pragma unroll
             for (int q = 1; q < R; ++q)
-                v[q] = cmulc(v[q], __ldg(&tw[(q * o) << (10 - LR)]));
+                v[q] = cmulc(v[q], __ldg(&pt[(q - 1) * 4 + o]));
             Dft<R, +1>::run(v);
 #pragma unroll
             for (int n = 0; n < R; ++n)
@@ -367,7 +379,7 @@ DEV void low2_p_pass(cplx *S, const cplx *tw, int t, int l2n, int sb)
             Dft<R, -1>::run(v);
 #pragma unroll
             for (int q = 1; q < R; ++q)
-                v[q] = cmul(v[q], __ldg(&tw[(q * o) << (10 - LR)]));
+                v[q] = cmul(v[q], __ldg(&pt[(q - 1) * 4 + o]));
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 S[swz2(base + 4 * brev_c(q, LR))] = v[q];
@@ -380,7 +392,7 @@ DEV void low2_p_pass(cplx *S, const cplx *tw, int t, int l2n, int sb)
 // w_2N^i / N, first forward pass -- all on one register set.
 // ---------------------------------------------------------------------------------------
 template <int LOG2M, int R>
-DEV void low2_m_stage(cplx *S, const cplx *tw, const Low2Tops *TTn, int t, int l2n, int sb)
+DEV double low2_m_stage(cplx *S, const TwSet &tw, const Low2Tops *TTn, int t, int l2n, int sb, bool want_max)
 {
     constexpr int M = 1 << LOG2M;
     constexpr int LR = Log2R<R>::value;
@@ -388,6 +400,9 @@ DEV void low2_m_stage(cplx *S, const cplx *tw, const Low2Tops *TTn, int t, int l
     const int l2s = l2n - LR;
     const int s = 1 << l2s;
     const double invN = 1.0 / (double)(1 << l2n);
+    const cplx *pt = tw.base + tw.pass_off[l2n][LR];  // [q-1][o], o < s
+    const cplx *tt = tw.base + tw.twist_off[l2n];     // w_2N^i
+    double m2 = 0.0;
 #pragma unroll 1
     for (int k = 0; k < PER; ++k) {
         int idx = t + k * M;
@@ -403,29 +418,63 @@ DEV void low2_m_stage(cplx *S, const cplx *tw, const Low2Tops *TTn, int t, int l
             v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
 #pragma unroll
         for (int q = 1; q < R; ++q)
-            v[q] = cmulc(v[q], __ldg(&tw[(q * o) << (12 - l2n)]));
+            v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
         Dft<R, +1>::run(v);
         // v[n] = N * c[o + n*s]
 #pragma unroll
-        for (int n = 0; n < R; ++n) {
-            const cplx w = __ldg(&tw[(o + (n << l2s)) << (11 - l2n)]);
-            v[n] = cmul(v[n], cscale(w, invN));
-        }
+        for (int n = 0; n < R; ++n)
+            v[n] = cscale(v[n], invN);
         if (o == 0)
             v[0] = which ? TTn[p].bb : TTn[p].ba;
+        if (want_max) {
+#pragma unroll
+            for (int n = 0; n < R; ++n)
+                m2 = fmax(m2, cabs2(v[n]));
+        }
+#pragma unroll
+        for (int n = 0; n < R; ++n)
+            v[n] = cmul(v[n], __ldg(&tt[o + (n << l2s)]));
         Dft<R, -1>::run(v);
 #pragma unroll
         for (int q = 1; q < R; ++q)
-            v[q] = cmul(v[q], __ldg(&tw[(q * o) << (12 - l2n)]));
+            v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
 #pragma unroll
         for (int q = 0; q < R; ++q)
             S[swz2(base + (brev_c(q, LR) << l2s))] = v[q];
+    }
+    return m2;
+}
+
+// spec_out: last forward pass (radix 4, stride 1) of the two workspace arrays of the single
+// remaining pair, "- c_N", store the odd bins of the result spectrum
+template <int LOG2M>
+DEV void low2_final_stage(const cplx *S, const Low2Tops &Tn, int t, int l2n, cplx *gout)
+{
+    constexpr int M = 1 << LOG2M;
+    const int N = 1 << l2n;
+    const int items = N >> 1;  // 2 arrays * N/4 groups
+#pragma unroll 1
+    for (int it = t; it < items; it += M) {
+        const int which = it >> (l2n - 2);
+        const int g = it & ((N >> 2) - 1);
+        const int ad = swz2(low2_wbase(0, which, l2n) + 4 * g);
+        cplx v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            v[j] = S[ad ^ j];
+        Dft<4, -1>::run(v);
+        const cplx ct = which ? Tn.tb : Tn.ta;
+        cplx *dst = gout + (size_t)which * (2 * N) + N + 4 * g;
+        dst[0] = csub(v[0], ct);
+        dst[1] = csub(v[2], ct);
+        dst[2] = csub(v[1], ct);
+        dst[3] = csub(v[3], ct);
     }
 }
 
 // last level: final inverse pass (radix 16), 1/N, write the coefficients; returns max |c|^2
 template <int LOG2M>
-DEV double low2_out_stage(const cplx *S, const cplx *tw, const Low2Tops &Tn, int t, int l2n, cplx *out)
+DEV double low2_out_stage(const cplx *S, const TwSet &tw, const Low2Tops &Tn, int t, int l2n, cplx *out)
 {
     constexpr int R = 16, LR = 4;
     const int l2s = l2n - LR;
@@ -435,13 +484,14 @@ DEV double low2_out_stage(const cplx *S, const cplx *tw, const Low2Tops &Tn, int
     const int o = t & (s - 1);
     const int which = t >> l2s;  // M threads == 2 arrays * s items
     const int base = low2_wbase(0, which, l2n) + o;
+    const cplx *pt = tw.base + tw.pass_off[l2n][LR];
     cplx v[R];
 #pragma unroll
     for (int q = 0; q < R; ++q)
         v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
 #pragma unroll
     for (int q = 1; q < R; ++q)
-        v[q] = cmulc(v[q], __ldg(&tw[(q * o) << (12 - l2n)]));
+        v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
     Dft<R, +1>::run(v);
     cplx *dst = out + (size_t)which * (N + 1);
     double m2 = 0.0;
@@ -551,6 +601,9 @@ __global__ void __launch_bounds__(1 << LOG2M, (LOG2M == 6) ? 6 : 3) k_tree_low2(
 
     // ---- levels: operand length 16, 32, ..., 8*M ---------------------------------------
     Low2Tops *TTc = TT1, *TTn = TT0;  // TTn: tops of the matrices being produced
+    const size_t mo = (size_t)s * nblk + blk;
+    cplx *gspec = a.spec_out ? a.out + mo * (size_t)(32 * M) : nullptr;  // [a: 16M][b: 16M]
+    double m2 = 0.0;
 #pragma unroll 1
     for (int L = 0; L < LOG2M; ++L) {
         const int l2n = 4 + L;
@@ -559,7 +612,7 @@ __global__ void __launch_bounds__(1 << LOG2M, (LOG2M == 6) ? 6 : 3) k_tree_low2(
         low2_plan(l2n, &rp, &rm, &sbp, &sbm);
         if (L > 0 && t < (M >> (L + 1)))
             TTn[t] = low2_pair_tops(TTc[2 * t], TTc[2 * t + 1], kap, 1.0);
-        low2_x_stage<LOG2M>(S, TTc, t, l2n, L == 0, last, kap);
+        low2_x_stage<LOG2M>(S, TTc, t, l2n, L == 0, last, kap, gspec);
         __syncthreads();
         switch (rp) {
         case 4: low2_p_pass<LOG2M, 4, +1>(S, a.tw, t, l2n, sbp); __syncthreads(); break;
@@ -572,37 +625,54 @@ __global__ void __launch_bounds__(1 << LOG2M, (LOG2M == 6) ? 6 : 3) k_tree_low2(
             break;
         default: break;
         }
-        if (last) {
-            const size_t mo = (size_t)s * nblk + blk;
-            double m2 = low2_out_stage<LOG2M>(S, a.tw, TTn[0], t, l2n, a.out + mo * 2 * ((8 * M) + 1));
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1)
-                m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, off));
-            if ((t & 31) == 0)
-                red[t >> 5] = m2;
-            __syncthreads();
-            if (t == 0) {
-                double m = red[0];
-                for (int w = 1; w < M / 32; ++w)
-                    m = fmax(m, red[w]);
-                a.mx_out[mo] = sqrt(m);
-            }
+        if (last && !a.spec_out) {
+            m2 = low2_out_stage<LOG2M>(S, a.tw, TTn[0], t, l2n, a.out + mo * 2 * ((8 * M) + 1));
             break;
         }
+        const bool want_max = last;
+        double mm;
         switch (rm) {
-        case 4: low2_m_stage<LOG2M, 4>(S, a.tw, TTn, t, l2n, sbm); break;
-        case 8: low2_m_stage<LOG2M, 8>(S, a.tw, TTn, t, l2n, sbm); break;
-        default: low2_m_stage<LOG2M, 16>(S, a.tw, TTn, t, l2n, sbm); break;
+        case 4: mm = low2_m_stage<LOG2M, 4>(S, a.tw, TTn, t, l2n, sbm, want_max); break;
+        case 8: mm = low2_m_stage<LOG2M, 8>(S, a.tw, TTn, t, l2n, sbm, want_max); break;
+        default: mm = low2_m_stage<LOG2M, 16>(S, a.tw, TTn, t, l2n, sbm, want_max); break;
         }
+        m2 = fmax(m2, mm);
         __syncthreads();
         switch (rp) {
         case 4: low2_p_pass<LOG2M, 4, -1>(S, a.tw, t, l2n, sbp); __syncthreads(); break;
         case 8: low2_p_pass<LOG2M, 8, -1>(S, a.tw, t, l2n, sbp); __syncthreads(); break;
+        case 16:
+            if constexpr (LOG2M > 6) {
+                low2_p_pass<LOG2M, 16, -1>(S, a.tw, t, l2n, sbp);
+                __syncthreads();
+            }
+            break;
         default: break;
+        }
+        if (last) {  // spec_out: odd bins of the result
+            low2_final_stage<LOG2M>(S, TTn[0], t, l2n, gspec);
+            if (t == 0) {
+                a.tt_out[mo] = TTn[0];
+                m2 = fmax(m2, fmax(cabs2(TTn[0].ta), cabs2(TTn[0].tb)));
+            }
+            break;
         }
         Low2Tops *tmp = TTc;
         TTc = TTn;
         TTn = tmp;
+    }
+    // max |c| of the result for the lazy normalisation of the next level
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, off));
+    if ((t & 31) == 0)
+        red[t >> 5] = m2;
+    __syncthreads();
+    if (t == 0) {
+        double m = red[0];
+        for (int w = 1; w < M / 32; ++w)
+            m = fmax(m, red[w]);
+        a.mx_out[mo] = sqrt(m);
     }
 }
 

@@ -1,0 +1,527 @@
+// fnft_b200 -- UPPER levels of the product tree in the first-row-only (NSE) mode, in the
+// "spectrum carry" representation of tree_low2.cuh: a level holds its matrices (a, b) as
+// VALUES at the N-th roots of unity (N = 2 * degree, bit-reversed order); a pair product
+// (fnft__poly_fmult.c:239-328) is a pointwise 2x2 product giving the even bins of the next
+// level's length-2N spectrum, and the odd bins are FFT_N(c_i * w_2N^i) - c_N with
+// c = IFFT_N(product values).  Coefficients only exist in registers, where max|c| is
+// taken for the lazy power-of-two normalisation (fnft__poly_fmult.c:330-374, see
+// tree_kernels.cuh header).
+//
+//  k_up_smem   : N <= 8192.  CTA = (signal, pair, output polynomial): pointwise product
+//                straight from HBM (+ store of the even bins), IFFT_N / twist / FFT_N in
+//                shared memory, store of the odd bins.  4N cplx read (the pair's two CTAs
+//                share them through L2), 2N written.
+//  k_up_rows_a / k_up_cols / k_up_rows_c : longer N = R * N2 (N2 = 4096).  (a) pointwise
+//                product + the inverse passes inside rows of N2 contiguous positions, (cols)
+//                radix-R inverse pass across rows + coefficient fix-up + twist + radix-R
+//                forward pass (streaming), (c) forward passes inside rows + odd-bin store.
+//  last level  : the twist / forward half is replaced by writing the coefficients (level
+//                buffer layout of tree_kernels.cuh, E = 2) for blk_tree_final.
+#pragma once
+#ifndef FNFTB_EMUL
+#include "tree_low2.cuh"
+
+struct UpArgs {
+    const cplx *in;         // [B][n_in][2][N]
+    cplx *out;              // [B][n_in/2][2][2N], or coefficients [B][n_in/2][2][N+1] (last)
+    const Low2Tops *tt_in;  // [B][n_in]
+    Low2Tops *tt_out;       // [B][n_in/2]
+    const double *mx_in;    // [B][n_in]
+    double *mx_out;         // [B][n_in/2], zeroed before the level
+    int *W;                 // [B]
+    cplx *ws;               // [B][n_in/2][2][N] (row-split levels)
+    int B, n_in, l2n;
+    int normalize, kappa, last;
+    int l2row;              // row-split: log2(N2)
+    TwSet tw;
+};
+
+struct UpPair {
+    Low2Tops Tn;  // tops of the product (already scaled)
+    double sc;    // 2^-(eA+eB)
+};
+
+// per-CTA prologue: scale of the pair, tops of the product; the `leader` CTA publishes them
+DEV UpPair up_pair_setup(const UpArgs &a, size_t sp, int s, bool leader)
+{
+    UpPair r;
+    const size_t mA = 2 * sp, mB = 2 * sp + 1;
+    int e = 0;
+    if (a.normalize)
+        e = rescale_exponent(a.mx_in[mA]) + rescale_exponent(a.mx_in[mB]);
+    r.sc = ldexp(1.0, -e);
+    const Low2Tops TA = a.tt_in[mA], TB = a.tt_in[mB];
+    r.Tn = low2_pair_tops(TA, TB, (double)a.kappa, r.sc);
+    if (leader && threadIdx.x == 0) {
+        a.tt_out[sp] = r.Tn;
+        if (e != 0)
+            atomicAdd(&a.W[s], e);
+    }
+    return r;
+}
+
+// pointwise product of RX consecutive positions for output polynomial `which`, operands in
+// HBM; c[] in natural position order.
+template <int RX>
+DEV void up_pointwise(const cplx *aA, const cplx *bA, const cplx *aB, const cplx *bB, int pos0, int which,
+                      double sg, double kap, double sc, cplx *c)
+{
+#pragma unroll
+    for (int j0 = 0; j0 < RX; j0 += 4) {
+        cplx x[4], y[4], z[4];
+        // which = 0: c = aA*aB + (-kap*sg*bA)*conj(bB);  which = 1: c = aA*bB + (sg*bA)*conj(aB)
+        const cplx *pz = which ? bB : aB;
+        const cplx *pw = which ? aB : bB;
+        cplx w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            x[j] = __ldg(&aA[pos0 + j0 + j]);
+            y[j] = __ldg(&bA[pos0 + j0 + j]);
+            z[j] = __ldg(&pz[pos0 + j0 + j]);
+            w[j] = __ldg(&pw[pos0 + j0 + j]);
+        }
+        const double f = which ? sg * sc : -kap * sg * sc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const cplx xs = cscale(x[j], sc);
+            cplx r = cmul(xs, z[j]);
+            cfmac(r, cscale(y[j], f), w[j]);
+            c[j0 + j] = r;
+        }
+    }
+}
+
+// generic radix-R pass at stride 1 << l2s over an array of n elements in shared memory
+template <int R, int DIR>
+DEV void up_p_pass(cplx *S, int n, int l2s, const TwSet &tw, int tid, int nt)
+{
+    constexpr int LR = Log2R<R>::value;
+    const int s = 1 << l2s;
+    const cplx *pt = tw.base + tw.pass_off[l2s + LR][LR];
+#pragma unroll 1
+    for (int idx = tid; idx < (n >> LR); idx += nt) {
+        const int o = idx & (s - 1);
+        const int g = idx >> l2s;
+        const int base = (g << (l2s + LR)) + o;
+        cplx v[R];
+        if (DIR > 0) {
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
+#pragma unroll
+            for (int q = 1; q < R; ++q)
+                v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+            Dft<R, +1>::run(v);
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2)
+                S[swz2(base + (n2 << l2s))] = v[n2];
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2)
+                v[n2] = S[swz2(base + (n2 << l2s))];
+            Dft<R, -1>::run(v);
+#pragma unroll
+            for (int q = 1; q < R; ++q)
+                v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                S[swz2(base + (brev_c(q, LR) << l2s))] = v[q];
+        }
+    }
+}
+
+// X stage: pointwise product of the CTA's positions [p0, p0 + n) (global), store of the even
+// bins, first inverse pass (radix RX, stride 1) into shared memory (local index 0..n)
+template <int RX>
+DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n, double sg, const UpPair &P,
+                    cplx *S, int tid, int nt)
+{
+    constexpr int LR = Log2R<RX>::value;
+    const int N = 1 << a.l2n;
+    const cplx *aA = a.in + (4 * sp) * (size_t)N;
+    const cplx *bA = aA + N, *aB = bA + N, *bB = aB + N;
+    cplx *ge = a.last ? nullptr : a.out + (2 * sp + which) * (size_t)(2 * N);
+#pragma unroll 1
+    for (int g = tid; g < (n >> LR); g += nt) {
+        cplx c[RX];
+        up_pointwise<RX>(aA, bA, aB, bB, p0 + RX * g, which, sg, (double)a.kappa, P.sc, c);
+        if (ge) {
+#pragma unroll
+            for (int j = 0; j < RX; ++j)
+                ge[p0 + RX * g + j] = c[j];
+        }
+        cplx v[RX];
+#pragma unroll
+        for (int q = 0; q < RX; ++q)
+            v[q] = c[brev_c(q, LR)];
+        Dft<RX, +1>::run(v);
+        const int ad = swz2(l0 + RX * g);  // l0 + RX*g is a multiple of 8
+#pragma unroll
+        for (int j = 0; j < RX; ++j)
+            S[(RX <= 8) ? (ad ^ j) : swz2(l0 + RX * g + j)] = v[j];
+    }
+}
+
+// F stage: last forward pass (radix RX, stride 1) of the CTA's n local elements, "- c_N",
+// store to the odd-bin region starting at godd
+template <int RX>
+DEV void up_f_stage(const cplx *S, int n, cplx ct, cplx *godd, int tid, int nt)
+{
+    constexpr int LR = Log2R<RX>::value;
+#pragma unroll 1
+    for (int g = tid; g < (n >> LR); g += nt) {
+        cplx v[RX];
+#pragma unroll
+        for (int j = 0; j < RX; ++j)
+            v[j] = S[swz2(RX * g + j)];
+        Dft<RX, -1>::run(v);
+#pragma unroll
+        for (int j = 0; j < RX; ++j)
+            godd[RX * g + j] = csub(v[brev_c(j, LR)], ct);
+    }
+}
+
+// M stage (radix 16, stride N/16) on a whole length-N array in shared memory; `last` writes
+// the coefficients to gcoef instead of twisting and transforming forward.  Returns max|c|^2.
+DEV double up_m_stage(cplx *S, int l2n, const TwSet &tw, const UpPair &P, int which, bool last, cplx *gcoef,
+                      int tid, int nt)
+{
+    constexpr int R = 16, LR = 4;
+    const int l2s = l2n - LR;
+    const int s = 1 << l2s;
+    const int N = 1 << l2n;
+    const double invN = 1.0 / (double)N;
+    const cplx *pt = tw.base + tw.pass_off[l2n][LR];
+    const cplx *tt = tw.base + tw.twist_off[l2n];
+    double m2 = 0.0;
+#pragma unroll 1
+    for (int o = tid; o < s; o += nt) {
+        cplx v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+            v[q] = S[swz2(o + (brev_c(q, LR) << l2s))];
+#pragma unroll
+        for (int q = 1; q < R; ++q)
+            v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        Dft<R, +1>::run(v);
+#pragma unroll
+        for (int n = 0; n < R; ++n)
+            v[n] = cscale(v[n], invN);
+        if (o == 0)
+            v[0] = which ? P.Tn.bb : P.Tn.ba;
+#pragma unroll
+        for (int n = 0; n < R; ++n)
+            m2 = fmax(m2, cabs2(v[n]));
+        if (last) {
+#pragma unroll
+            for (int n = 0; n < R; ++n)
+                gcoef[o + (n << l2s)] = v[n];
+            if (o == 0)
+                gcoef[N] = which ? P.Tn.tb : P.Tn.ta;
+            continue;
+        }
+#pragma unroll
+        for (int n = 0; n < R; ++n)
+            v[n] = cmul(v[n], __ldg(&tt[o + (n << l2s)]));
+        Dft<R, -1>::run(v);
+#pragma unroll
+        for (int q = 1; q < R; ++q)
+            v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+            S[swz2(o + (brev_c(q, LR) << l2s))] = v[q];
+    }
+    return m2;
+}
+
+// publishes max(|c|) of a CTA: warp shuffle, shared memory, one atomic
+DEV void up_publish_max(double m2, double *red, double *dst, int tid, int nt)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, off));
+    if ((tid & 31) == 0)
+        red[tid >> 5] = m2;
+    __syncthreads();
+    if (tid == 0) {
+        double m = red[0];
+        for (int w = 1; w < nt / 32; ++w)
+            m = fmax(m, red[w]);
+        atomic_max_double(dst, sqrt(m));
+    }
+}
+
+// inverse / forward row passes between the stride-1 stage (radix RX) and length 1 << l2len
+//   l2len 11: RX = 8,  P16(s=8)            [+ M16 at s=128]
+//   l2len 12: RX = 16, P16(s=16)           [+ M16 at s=256]
+//   l2len 13: RX = 8,  P8(s=8), P8(s=64)   [+ M16 at s=512]
+// with_top: rows of a longer transform also run the pass that the M stage replaces
+template <int DIR>
+DEV void up_row_passes(cplx *S, int l2len, bool with_top, const TwSet &tw, int tid, int nt)
+{
+    const int n = 1 << l2len;
+    if (DIR > 0) {
+        if (l2len == 12) {
+            up_p_pass<16, +1>(S, n, 4, tw, tid, nt);
+            __syncthreads();
+        } else if (l2len == 11) {
+            up_p_pass<16, +1>(S, n, 3, tw, tid, nt);
+            __syncthreads();
+        } else {
+            up_p_pass<8, +1>(S, n, 3, tw, tid, nt);
+            __syncthreads();
+            up_p_pass<8, +1>(S, n, 6, tw, tid, nt);
+            __syncthreads();
+        }
+        if (with_top) {
+            up_p_pass<16, +1>(S, n, l2len - 4, tw, tid, nt);
+            __syncthreads();
+        }
+    } else {
+        if (with_top) {
+            up_p_pass<16, -1>(S, n, l2len - 4, tw, tid, nt);
+            __syncthreads();
+        }
+        if (l2len == 12) {
+            up_p_pass<16, -1>(S, n, 4, tw, tid, nt);
+            __syncthreads();
+        } else if (l2len == 11) {
+            up_p_pass<16, -1>(S, n, 3, tw, tid, nt);
+            __syncthreads();
+        } else {
+            up_p_pass<8, -1>(S, n, 6, tw, tid, nt);
+            __syncthreads();
+            up_p_pass<8, -1>(S, n, 3, tw, tid, nt);
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// whole level in shared memory: grid.x = B * npairs * 2, blockDim.x = N / 32
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT <= 64) ? 6 : ((NT <= 128) ? 3 : 1)) k_up_smem(const UpArgs a)
+{
+    extern __shared__ double2 fnftb_smem_up[];
+    cplx *S = (cplx *)fnftb_smem_up;
+    const int l2n = a.l2n, N = 1 << l2n;
+    double *red = (double *)(S + N);
+    const int tid = threadIdx.x;
+    const int which = blockIdx.x & 1;
+    const size_t sp = blockIdx.x >> 1;
+    const int npairs = a.n_in >> 1;
+    const int s = (int)(sp / npairs);
+    const UpPair P = up_pair_setup(a, sp, s, which == 0);
+
+    // X stage: the two half regions carry (-1)^k = +1 / -1
+    if (l2n == 12) {
+        up_x_stage<16>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
+        up_x_stage<16>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
+    } else {
+        up_x_stage<8>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
+        up_x_stage<8>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
+    }
+    __syncthreads();
+    up_row_passes<+1>(S, l2n, false, a.tw, tid, NT);
+    cplx *gcoef = a.last ? a.out + (2 * sp + which) * (size_t)(N + 1) : nullptr;
+    const double m2 = up_m_stage(S, l2n, a.tw, P, which, a.last != 0, gcoef, tid, NT);
+    __syncthreads();
+    if (!a.last) {
+        up_row_passes<-1>(S, l2n, false, a.tw, tid, NT);
+        cplx *godd = a.out + (2 * sp + which) * (size_t)(2 * N) + N;
+        const cplx ct = which ? P.Tn.tb : P.Tn.ta;
+        if (l2n == 12)
+            up_f_stage<16>(S, N, ct, godd, tid, NT);
+        else
+            up_f_stage<8>(S, N, ct, godd, tid, NT);
+    }
+    double mm = m2;
+    if (tid == 0)
+        mm = fmax(mm, cabs2(which ? P.Tn.tb : P.Tn.ta));
+    up_publish_max(mm, red, &a.mx_out[sp], tid, NT);
+}
+
+// ---------------------------------------------------------------------------------------
+// row-split levels, N = R * N2
+// (a) grid.x = B * npairs * 2 * R: pointwise product + inverse passes inside row r
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
+{
+    extern __shared__ double2 fnftb_smem_up[];
+    cplx *S = (cplx *)fnftb_smem_up;
+    const int l2n = a.l2n, l2row = a.l2row, N2 = 1 << l2row;
+    const int l2R = l2n - l2row;
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x & ((1 << l2R) - 1);
+    const size_t arr = blockIdx.x >> l2R;
+    const int which = (int)(arr & 1);
+    const size_t sp = arr >> 1;
+    const int npairs = a.n_in >> 1;
+    const int s = (int)(sp / npairs);
+    const UpPair P = up_pair_setup(a, sp, s, which == 0 && row == 0);
+    const double sg = (row >> (l2R - 1)) ? -1.0 : 1.0;
+    // X stage over positions [row*N2, (row+1)*N2): local index = position - row*N2
+    up_x_stage<16>(a, sp, which, row << l2row, 0, N2, sg, P, S, tid, NT);
+    __syncthreads();
+    up_row_passes<+1>(S, l2row, true, a.tw, tid, NT);
+    cplx *dst = a.ws + arr * ((size_t)1 << l2n) + ((size_t)row << l2row);
+    for (int i = tid; i < N2; i += NT)
+        dst[i] = S[swz2(i)];
+}
+
+// (cols) one thread per (array, o < N2): radix-R inverse pass across the rows, coefficient
+// fix-up and max, then twist + radix-R forward pass (or the coefficient output when last)
+template <int R>
+__global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
+{
+    constexpr int LR = Log2R<R>::value;
+    __shared__ double red[8];
+    const int l2n = a.l2n, l2row = l2n - LR;
+    const int N = 1 << l2n;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = (int)(gid & ((1 << l2row) - 1));
+    const size_t arr = (size_t)(gid >> l2row);  // a CTA stays inside one array (256 | N2)
+    const int which = (int)(arr & 1);
+    const size_t sp = arr >> 1;
+    const Low2Tops Tn = a.tt_out[sp];
+    cplx *w = a.ws + arr * (size_t)N;
+    const cplx *pt = a.tw.base + a.tw.pass_off[l2n][LR];
+    const cplx *tt = a.tw.base + a.tw.twist_off[l2n];
+    const double invN = 1.0 / (double)N;
+    cplx v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+        v[q] = w[o + ((size_t)brev_c(q, LR) << l2row)];
+#pragma unroll
+    for (int q = 1; q < R; ++q)
+        v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2row) + o]));
+    Dft<R, +1>::run(v);
+#pragma unroll
+    for (int n = 0; n < R; ++n)
+        v[n] = cscale(v[n], invN);
+    if (o == 0)
+        v[0] = which ? Tn.bb : Tn.ba;
+    double m2 = 0.0;
+#pragma unroll
+    for (int n = 0; n < R; ++n)
+        m2 = fmax(m2, cabs2(v[n]));
+    if (a.last) {
+        cplx *gcoef = a.out + arr * (size_t)(N + 1);
+#pragma unroll
+        for (int n = 0; n < R; ++n)
+            gcoef[o + ((size_t)n << l2row)] = v[n];
+        if (o == 0) {
+            const cplx ct = which ? Tn.tb : Tn.ta;
+            gcoef[N] = ct;
+            m2 = fmax(m2, cabs2(ct));
+        }
+    } else {
+        if (o == 0)
+            m2 = fmax(m2, cabs2(which ? Tn.tb : Tn.ta));
+#pragma unroll
+        for (int n = 0; n < R; ++n)
+            v[n] = cmul(v[n], __ldg(&tt[o + (n << l2row)]));
+        Dft<R, -1>::run(v);
+#pragma unroll
+        for (int q = 1; q < R; ++q)
+            v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2row) + o]));
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+            w[o + ((size_t)brev_c(q, LR) << l2row)] = v[q];
+    }
+    up_publish_max(m2, red, &a.mx_out[sp], threadIdx.x, blockDim.x);
+}
+
+// (c) grid.x = B * npairs * 2 * R: forward passes inside row `row` of the workspace, odd bins
+template <int NT>
+__global__ void __launch_bounds__(NT, 3) k_up_rows_c(const UpArgs a)
+{
+    extern __shared__ double2 fnftb_smem_up[];
+    cplx *S = (cplx *)fnftb_smem_up;
+    const int l2n = a.l2n, l2row = a.l2row, N2 = 1 << l2row;
+    const int l2R = l2n - l2row;
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x & ((1 << l2R) - 1);
+    const size_t arr = blockIdx.x >> l2R;
+    const int which = (int)(arr & 1);
+    const size_t sp = arr >> 1;
+    const Low2Tops Tn = a.tt_out[sp];
+    const cplx *src = a.ws + arr * ((size_t)1 << l2n) + ((size_t)row << l2row);
+    for (int i = tid; i < N2; i += NT)
+        S[swz2(i)] = src[i];
+    __syncthreads();
+    up_row_passes<-1>(S, l2row, true, a.tw, tid, NT);
+    cplx *godd = a.out + arr * ((size_t)2 << l2n) + ((size_t)1 << l2n) + ((size_t)row << l2row);
+    up_f_stage<16>(S, N2, which ? Tn.tb : Tn.ta, godd, tid, NT);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+#define FNFTB_UP_ROW_L2 12  // rows of 4096
+
+template <class K>
+static inline int up_launch(K kernel, const UpArgs &a, unsigned grid, int nt, size_t smem, cudaStream_t st,
+                            const char *name)
+{
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return (int)e;
+    }
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin(name, st);
+    kernel<<<grid, nt, smem, st>>>(a);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(st);
+    ++g_fnftb_launch_count;
+    return (int)cudaGetLastError();
+}
+
+// can this level (operand length 1 << l2n) run on the spectrum path?
+static inline bool up_supported(int l2n, int l2smem_max)
+{
+    if (l2n < 11 || l2n > FNFTB_TW_MAXL)
+        return false;
+    if (l2n <= l2smem_max)
+        return true;
+    const int l2R = l2n - FNFTB_UP_ROW_L2;
+    return l2R >= 1 && l2R <= 4;
+}
+
+static inline int up_level(UpArgs a, int l2smem_max, cudaStream_t st)
+{
+    const int npairs = a.n_in / 2;
+    const int N = 1 << a.l2n;
+    cudaMemsetAsync(a.mx_out, 0, sizeof(double) * (size_t)a.B * npairs, st);
+    static const char *names_s[3] = {"tree_up_smem_N2048", "tree_up_smem_N4096", "tree_up_smem_N8192"};
+    if (a.l2n <= l2smem_max) {
+        const unsigned grid = (unsigned)a.B * (unsigned)npairs * 2u;
+        const size_t smem = sizeof(cplx) * N + 64 * sizeof(double);
+        switch (a.l2n) {
+        case 11: return up_launch(k_up_smem<64>, a, grid, 64, smem, st, names_s[0]);
+        case 12: return up_launch(k_up_smem<128>, a, grid, 128, smem, st, names_s[1]);
+        default: return up_launch(k_up_smem<256>, a, grid, 256, smem, st, names_s[2]);
+        }
+    }
+    a.l2row = FNFTB_UP_ROW_L2;
+    const int l2R = a.l2n - a.l2row;
+    const unsigned grid_rows = (unsigned)a.B * (unsigned)npairs * 2u << l2R;
+    const size_t smem = sizeof(cplx) << a.l2row;
+    int rc = up_launch(k_up_rows_a<128>, a, grid_rows, 128, smem, st, "tree_up_rows_a");
+    if (rc)
+        return rc;
+    const unsigned grid_cols = (unsigned)(((size_t)a.B * npairs * 2 << a.l2row) / 256);
+    switch (l2R) {
+    case 1: rc = up_launch(k_up_cols<2>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    case 2: rc = up_launch(k_up_cols<4>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    case 3: rc = up_launch(k_up_cols<8>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    default: rc = up_launch(k_up_cols<16>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    }
+    if (rc || a.last)
+        return rc;
+    return up_launch(k_up_rows_c<128>, a, grid_rows, 128, smem, st, "tree_up_rows_c");
+}
+#endif  // !FNFTB_EMUL

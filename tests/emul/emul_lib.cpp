@@ -41,6 +41,8 @@ struct Work {
         w.colbuf = colbuf.data();
         w.W = W.data();
         w.status = status.data();
+        w.tt[0] = w.tt[1] = nullptr;
+        w.tws = nullptr;
     }
 };
 
