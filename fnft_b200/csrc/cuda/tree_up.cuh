@@ -21,6 +21,8 @@
 #ifndef FNFTB_EMUL
 #include "tree_low2.cuh"
 
+#define FNFTB_UP_ROW_L2 12  // row-split levels use rows of 4096 positions
+
 struct UpArgs {
     const cplx *in;         // [B][n_in][2][N]
     cplx *out;              // [B][n_in/2][2][2N], or coefficients [B][n_in/2][2][N+1] (last)
@@ -58,37 +60,6 @@ DEV UpPair up_pair_setup(const UpArgs &a, size_t sp, int s, bool leader)
             atomicAdd(&a.W[s], e);
     }
     return r;
-}
-
-// pointwise product of RX consecutive positions for output polynomial `which`, operands in
-// HBM; c[] in natural position order.
-template <int RX>
-DEV void up_pointwise(const cplx *aA, const cplx *bA, const cplx *aB, const cplx *bB, int pos0, int which,
-                      double sg, double kap, double sc, cplx *c)
-{
-#pragma unroll
-    for (int j0 = 0; j0 < RX; j0 += 4) {
-        cplx x[4], y[4], z[4];
-        // which = 0: c = aA*aB + (-kap*sg*bA)*conj(bB);  which = 1: c = aA*bB + (sg*bA)*conj(aB)
-        const cplx *pz = which ? bB : aB;
-        const cplx *pw = which ? aB : bB;
-        cplx w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            x[j] = __ldg(&aA[pos0 + j0 + j]);
-            y[j] = __ldg(&bA[pos0 + j0 + j]);
-            z[j] = __ldg(&pz[pos0 + j0 + j]);
-            w[j] = __ldg(&pw[pos0 + j0 + j]);
-        }
-        const double f = which ? sg * sc : -kap * sg * sc;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const cplx xs = cscale(x[j], sc);
-            cplx r = cmul(xs, z[j]);
-            cfmac(r, cscale(y[j], f), w[j]);
-            c[j0 + j] = r;
-        }
-    }
 }
 
 // generic radix-R pass at stride 1 << l2s over an array of n elements in shared memory
@@ -131,7 +102,11 @@ DEV void up_p_pass(cplx *S, int n, int l2s, const TwSet &tw, int tid, int nt)
 }
 
 // X stage: pointwise product of the CTA's positions [p0, p0 + n) (global), store of the even
-// bins, first inverse pass (radix RX, stride 1) into shared memory (local index 0..n)
+// bins, first inverse pass (radix RX, stride 1) into shared memory (local index l0..l0+n).
+// A warp owns chunks of 32*RX consecutive positions: lanes run over consecutive positions for
+// the global loads / stores (512 contiguous bytes per access) and park the product values in
+// shared memory; after a __syncwarp each lane takes its RX consecutive positions for the
+// stride-1 pass.
 template <int RX>
 DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n, double sg, const UpPair &P,
                     cplx *S, int tid, int nt)
@@ -139,45 +114,74 @@ DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n
     constexpr int LR = Log2R<RX>::value;
     const int N = 1 << a.l2n;
     const cplx *aA = a.in + (4 * sp) * (size_t)N;
-    const cplx *bA = aA + N, *aB = bA + N, *bB = aB + N;
+    const cplx *bA = aA + N;
+    const cplx *pz = aA + (which ? 3 : 2) * (size_t)N;  // which = 0: aB, 1: bB
+    const cplx *pw = aA + (which ? 2 : 3) * (size_t)N;  // which = 0: bB, 1: aB
     cplx *ge = a.last ? nullptr : a.out + (2 * sp + which) * (size_t)(2 * N);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const double sc = P.sc;
+    // which = 0: c = aA*aB + (-kap*sg*bA)*conj(bB);  which = 1: c = aA*bB + (sg*bA)*conj(aB)
+    const double f = which ? sg * sc : -(double)a.kappa * sg * sc;
 #pragma unroll 1
-    for (int g = tid; g < (n >> LR); g += nt) {
-        cplx c[RX];
-        up_pointwise<RX>(aA, bA, aB, bB, p0 + RX * g, which, sg, (double)a.kappa, P.sc, c);
-        if (ge) {
+    for (int cb = warp * (32 * RX); cb < n; cb += nwarps * (32 * RX)) {
 #pragma unroll
-            for (int j = 0; j < RX; ++j)
-                ge[p0 + RX * g + j] = c[j];
+        for (int i0 = 0; i0 < RX; i0 += 4) {
+            cplx x[4], y[4], z[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pos = p0 + cb + 32 * (i0 + i) + lane;
+                x[i] = __ldg(&aA[pos]);
+                y[i] = __ldg(&bA[pos]);
+                z[i] = __ldg(&pz[pos]);
+                w[i] = __ldg(&pw[pos]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int loc = cb + 32 * (i0 + i) + lane;
+                cplx r = cmul(cscale(x[i], sc), z[i]);
+                cfmac(r, cscale(y[i], f), w[i]);
+                if (ge)
+                    ge[p0 + loc] = r;
+                S[swz2(l0 + loc)] = r;
+            }
         }
+        __syncwarp();
+        const int b = l0 + cb + RX * lane;
         cplx v[RX];
 #pragma unroll
         for (int q = 0; q < RX; ++q)
-            v[q] = c[brev_c(q, LR)];
+            v[q] = S[swz2(b + brev_c(q, LR))];
         Dft<RX, +1>::run(v);
-        const int ad = swz2(l0 + RX * g);  // l0 + RX*g is a multiple of 8
 #pragma unroll
         for (int j = 0; j < RX; ++j)
-            S[(RX <= 8) ? (ad ^ j) : swz2(l0 + RX * g + j)] = v[j];
+            S[swz2(b + j)] = v[j];
     }
 }
 
 // F stage: last forward pass (radix RX, stride 1) of the CTA's n local elements, "- c_N",
-// store to the odd-bin region starting at godd
+// coalesced store to the odd-bin region starting at godd (same warp-chunk scheme)
 template <int RX>
-DEV void up_f_stage(const cplx *S, int n, cplx ct, cplx *godd, int tid, int nt)
+DEV void up_f_stage(cplx *S, int n, cplx ct, cplx *godd, int tid, int nt)
 {
     constexpr int LR = Log2R<RX>::value;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 #pragma unroll 1
-    for (int g = tid; g < (n >> LR); g += nt) {
+    for (int cb = warp * (32 * RX); cb < n; cb += nwarps * (32 * RX)) {
+        const int b = cb + RX * lane;
         cplx v[RX];
 #pragma unroll
         for (int j = 0; j < RX; ++j)
-            v[j] = S[swz2(RX * g + j)];
+            v[j] = S[swz2(b + j)];
         Dft<RX, -1>::run(v);
 #pragma unroll
-        for (int j = 0; j < RX; ++j)
-            godd[RX * g + j] = csub(v[brev_c(j, LR)], ct);
+        for (int q = 0; q < RX; ++q)
+            S[swz2(b + brev_c(q, LR))] = v[q];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < RX; ++i) {
+            const int loc = cb + 32 * i + lane;
+            godd[loc] = csub(S[swz2(loc)], ct);
+        }
     }
 }
 
@@ -256,15 +260,15 @@ DEV void up_publish_max(double m2, double *red, double *dst, int tid, int nt)
 //   l2len 12: RX = 16, P16(s=16)           [+ M16 at s=256]
 //   l2len 13: RX = 8,  P8(s=8), P8(s=64)   [+ M16 at s=512]
 // with_top: rows of a longer transform also run the pass that the M stage replaces
-template <int DIR>
-DEV void up_row_passes(cplx *S, int l2len, bool with_top, const TwSet &tw, int tid, int nt)
+template <int DIR, int L2LEN, bool WITH_TOP>
+DEV void up_row_passes(cplx *S, const TwSet &tw, int tid, int nt)
 {
-    const int n = 1 << l2len;
-    if (DIR > 0) {
-        if (l2len == 12) {
+    constexpr int n = 1 << L2LEN;
+    if constexpr (DIR > 0) {
+        if constexpr (L2LEN == 12) {
             up_p_pass<16, +1>(S, n, 4, tw, tid, nt);
             __syncthreads();
-        } else if (l2len == 11) {
+        } else if constexpr (L2LEN == 11) {
             up_p_pass<16, +1>(S, n, 3, tw, tid, nt);
             __syncthreads();
         } else {
@@ -273,19 +277,19 @@ DEV void up_row_passes(cplx *S, int l2len, bool with_top, const TwSet &tw, int t
             up_p_pass<8, +1>(S, n, 6, tw, tid, nt);
             __syncthreads();
         }
-        if (with_top) {
-            up_p_pass<16, +1>(S, n, l2len - 4, tw, tid, nt);
+        if constexpr (WITH_TOP) {
+            up_p_pass<16, +1>(S, n, L2LEN - 4, tw, tid, nt);
             __syncthreads();
         }
     } else {
-        if (with_top) {
-            up_p_pass<16, -1>(S, n, l2len - 4, tw, tid, nt);
+        if constexpr (WITH_TOP) {
+            up_p_pass<16, -1>(S, n, L2LEN - 4, tw, tid, nt);
             __syncthreads();
         }
-        if (l2len == 12) {
+        if constexpr (L2LEN == 12) {
             up_p_pass<16, -1>(S, n, 4, tw, tid, nt);
             __syncthreads();
-        } else if (l2len == 11) {
+        } else if constexpr (L2LEN == 11) {
             up_p_pass<16, -1>(S, n, 3, tw, tid, nt);
             __syncthreads();
         } else {
@@ -300,12 +304,13 @@ DEV void up_row_passes(cplx *S, int l2len, bool with_top, const TwSet &tw, int t
 // ---------------------------------------------------------------------------------------
 // whole level in shared memory: grid.x = B * npairs * 2, blockDim.x = N / 32
 // ---------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(NT, (NT <= 64) ? 6 : ((NT <= 128) ? 3 : 1)) k_up_smem(const UpArgs a)
+template <int L2N>
+__global__ void __launch_bounds__(1 << (L2N - 5), (L2N == 11) ? 6 : ((L2N == 12) ? 3 : 1)) k_up_smem(const UpArgs a)
 {
+    constexpr int N = 1 << L2N, NT = N / 32;
+    constexpr int RX = (L2N == 12) ? 16 : 8;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
-    const int l2n = a.l2n, N = 1 << l2n;
     double *red = (double *)(S + N);
     const int tid = threadIdx.x;
     const int which = blockIdx.x & 1;
@@ -315,26 +320,17 @@ __global__ void __launch_bounds__(NT, (NT <= 64) ? 6 : ((NT <= 128) ? 3 : 1)) k_
     const UpPair P = up_pair_setup(a, sp, s, which == 0);
 
     // X stage: the two half regions carry (-1)^k = +1 / -1
-    if (l2n == 12) {
-        up_x_stage<16>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
-        up_x_stage<16>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
-    } else {
-        up_x_stage<8>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
-        up_x_stage<8>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
-    }
+    up_x_stage<RX>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
+    up_x_stage<RX>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
     __syncthreads();
-    up_row_passes<+1>(S, l2n, false, a.tw, tid, NT);
+    up_row_passes<+1, L2N, false>(S, a.tw, tid, NT);
     cplx *gcoef = a.last ? a.out + (2 * sp + which) * (size_t)(N + 1) : nullptr;
-    const double m2 = up_m_stage(S, l2n, a.tw, P, which, a.last != 0, gcoef, tid, NT);
+    const double m2 = up_m_stage(S, L2N, a.tw, P, which, a.last != 0, gcoef, tid, NT);
     __syncthreads();
     if (!a.last) {
-        up_row_passes<-1>(S, l2n, false, a.tw, tid, NT);
+        up_row_passes<-1, L2N, false>(S, a.tw, tid, NT);
         cplx *godd = a.out + (2 * sp + which) * (size_t)(2 * N) + N;
-        const cplx ct = which ? P.Tn.tb : P.Tn.ta;
-        if (l2n == 12)
-            up_f_stage<16>(S, N, ct, godd, tid, NT);
-        else
-            up_f_stage<8>(S, N, ct, godd, tid, NT);
+        up_f_stage<RX>(S, N, which ? P.Tn.tb : P.Tn.ta, godd, tid, NT);
     }
     double mm = m2;
     if (tid == 0)
@@ -365,7 +361,7 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
     // X stage over positions [row*N2, (row+1)*N2): local index = position - row*N2
     up_x_stage<16>(a, sp, which, row << l2row, 0, N2, sg, P, S, tid, NT);
     __syncthreads();
-    up_row_passes<+1>(S, l2row, true, a.tw, tid, NT);
+    up_row_passes<+1, FNFTB_UP_ROW_L2, true>(S, a.tw, tid, NT);
     cplx *dst = a.ws + arr * ((size_t)1 << l2n) + ((size_t)row << l2row);
     for (int i = tid; i < N2; i += NT)
         dst[i] = S[swz2(i)];
@@ -452,7 +448,7 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_c(const UpArgs a)
     for (int i = tid; i < N2; i += NT)
         S[swz2(i)] = src[i];
     __syncthreads();
-    up_row_passes<-1>(S, l2row, true, a.tw, tid, NT);
+    up_row_passes<-1, FNFTB_UP_ROW_L2, true>(S, a.tw, tid, NT);
     cplx *godd = a.out + arr * ((size_t)2 << l2n) + ((size_t)1 << l2n) + ((size_t)row << l2row);
     up_f_stage<16>(S, N2, which ? Tn.tb : Tn.ta, godd, tid, NT);
 }
@@ -460,7 +456,6 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_c(const UpArgs a)
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-#define FNFTB_UP_ROW_L2 12  // rows of 4096
 
 template <class K>
 static inline int up_launch(K kernel, const UpArgs &a, unsigned grid, int nt, size_t smem, cudaStream_t st,
@@ -501,9 +496,9 @@ static inline int up_level(UpArgs a, int l2smem_max, cudaStream_t st)
         const unsigned grid = (unsigned)a.B * (unsigned)npairs * 2u;
         const size_t smem = sizeof(cplx) * N + 64 * sizeof(double);
         switch (a.l2n) {
-        case 11: return up_launch(k_up_smem<64>, a, grid, 64, smem, st, names_s[0]);
-        case 12: return up_launch(k_up_smem<128>, a, grid, 128, smem, st, names_s[1]);
-        default: return up_launch(k_up_smem<256>, a, grid, 256, smem, st, names_s[2]);
+        case 11: return up_launch(k_up_smem<11>, a, grid, 64, smem, st, names_s[0]);
+        case 12: return up_launch(k_up_smem<12>, a, grid, 128, smem, st, names_s[1]);
+        default: return up_launch(k_up_smem<13>, a, grid, 256, smem, st, names_s[2]);
         }
     }
     a.l2row = FNFTB_UP_ROW_L2;
