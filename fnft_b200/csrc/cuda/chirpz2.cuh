@@ -1,0 +1,329 @@
+// fnft_b200 -- fast path of the batched chirp-z evaluation (fnft__poly_chirpz.c:33-105)
+// for Bluestein lengths L = R * 4096, R in {2, 4, 8, 16}: same algorithm and tables as
+// chirpz_kernels.cuh, but the two length-L transforms are organised like the tree kernels
+// (tree_up.cuh): bit-reversed DIF forward / DIT inverse, pass-major twiddle tables, and
+//
+//   cz2_cols_fwd : y_n = p[deg-n]*tab_y[n] on the fly, radix-R DIF pass across the rows
+//                  (stride 4096), streaming, one thread per column
+//   cz2_rows     : per row of 4096: [global -> radix-16 (s=256)] [radix-16 (s=16)]
+//                  [radix-16 (s=1) * FFT(v) * inverse radix-16 (s=1), in registers]
+//                  [inverse radix-16 (s=16)] [inverse radix-16 (s=256) -> global]
+//   cz2_cols_inv : radix-R DIT pass across the rows, only outputs m < M, * W^(m^2/2)/L,
+//                  continuous-spectrum epilogue (src/fnft_nsev.c:846-876,
+//                  src/fnft_kdvv.c:186-203) for both polynomials of a signal at once
+//
+// FFT(v) is stored pre-permuted ([row][q][g], value at row position 16*g + brev4(q)) so that
+// the register-fused stage reads it with unit stride across the lanes.
+#pragma once
+#ifndef FNFTB_EMUL
+#include "chirpz_kernels.cuh"
+#include "tree_up.cuh"
+
+#define FNFTB_CZ2_ROW_L2 12
+
+struct Cz2Args {
+    CzArgs c;     // polynomials, tables (tab_y, tab_out, tab_ph), epilogue description
+    TwSet tw;
+    cplx *vperm;  // [L] permuted FFT(v)
+    int l2L;
+    int gen_v;    // cols_fwd: generate the chirp filter; rows: forward half only -> vperm
+};
+
+// grid.x * 256 threads = narr * 4096 ; narr = B*npoly (or 1 for gen_v)
+template <int R>
+__global__ void __launch_bounds__(256) k_cz2_cols_fwd(const Cz2Args a)
+{
+    constexpr int LR = Log2R<R>::value;
+    constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
+    const CzArgs &c = a.c;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = (int)(gid & (N2 - 1));
+    const size_t arr = (size_t)(gid >> FNFTB_CZ2_ROW_L2);
+    const int Np = c.deg + 1;
+    const int L = 1 << a.l2L;
+    cplx v[R];
+    if (!a.gen_v) {
+        const int j = (int)(arr % c.npoly);
+        const size_t s = arr / c.npoly;
+        const cplx *p = c.tm + s * c.tm_sstride + (size_t)c.ent[j] * Np;
+#pragma unroll
+        for (int n1 = 0; n1 < R; ++n1) {
+            const int n = o + n1 * N2;
+            v[n1] = (n < Np) ? cmul(p[c.deg - n], __ldg(&c.tab_y[n])) : czero();
+        }
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < R; ++n1) {
+            const int n = o + n1 * N2;
+            // fnft__poly_chirpz.c:76-82
+            double dn = -1.0;
+            if (n < c.M)
+                dn = (double)n;
+            else if (n > L - Np)
+                dn = (double)(L - n);
+            v[n1] = (dn >= 0.0) ? chirp_factor(-c.lwr * (0.5 * dn * dn), -c.lwi, 0.5 * dn * dn, 0.0, 0.0)
+                                : czero();
+        }
+    }
+    Dft<R, -1>::run(v);
+    const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][LR];
+    cplx *dst = c.ybuf + arr * (size_t)L;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        cplx y = v[q];
+        if (q > 0)
+            y = cmul(y, __ldg(&pt[((q - 1) << FNFTB_CZ2_ROW_L2) + o]));
+        dst[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o] = y;
+    }
+}
+
+// grid.x = narr * R rows, 128 threads, 64 KiB shared memory
+__global__ void __launch_bounds__(128, 3) k_cz2_rows(const Cz2Args a)
+{
+    constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
+    constexpr int NT = 128;
+    extern __shared__ double2 fnftb_smem_cz2[];
+    cplx *S = (cplx *)fnftb_smem_cz2;
+    const int tid = threadIdx.x;
+    const int l2R = a.l2L - FNFTB_CZ2_ROW_L2;
+    const int row = blockIdx.x & ((1 << l2R) - 1);
+    cplx *g = a.c.ybuf + (size_t)blockIdx.x * N2;  // rows are contiguous: arr*L + row*N2
+    const cplx *pt12 = a.tw.base + a.tw.pass_off[12][4];  // len 4096, radix 16, s = 256
+    // global -> forward radix-16 at stride 256 -> shared
+#pragma unroll 1
+    for (int o = tid; o < 256; o += NT) {
+        cplx v[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+            v[n] = g[o + (n << 8)];
+        Dft<16, -1>::run(v);
+#pragma unroll
+        for (int q = 1; q < 16; ++q)
+            v[q] = cmul(v[q], __ldg(&pt12[((q - 1) << 8) + o]));
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            S[swz2(o + (brev_c(q, 4) << 8))] = v[q];
+    }
+    __syncthreads();
+    up_p_pass<16, -1>(S, N2, 4, a.tw, tid, NT);
+    __syncthreads();
+    // stride-1 forward pass, * FFT(v), stride-1 inverse pass (registers)
+    const cplx *vp = a.vperm + ((size_t)row << FNFTB_CZ2_ROW_L2);
+#pragma unroll 1
+    for (int gi = tid; gi < 256; gi += NT) {
+        cplx v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[j] = S[swz2(16 * gi + j)];
+        Dft<16, -1>::run(v);
+        if (a.gen_v) {
+            cplx *vo = a.vperm + ((size_t)row << FNFTB_CZ2_ROW_L2);
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                vo[(q << 8) + gi] = v[q];
+            continue;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            v[q] = cmul(v[q], __ldg(&vp[(q << 8) + gi]));
+        Dft<16, +1>::run(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            S[swz2(16 * gi + j)] = v[j];
+    }
+    if (a.gen_v)
+        return;
+    __syncthreads();
+    up_p_pass<16, +1>(S, N2, 4, a.tw, tid, NT);
+    __syncthreads();
+    // shared -> inverse radix-16 at stride 256 -> global
+#pragma unroll 1
+    for (int o = tid; o < 256; o += NT) {
+        cplx v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            v[q] = S[swz2(o + (brev_c(q, 4) << 8))];
+#pragma unroll
+        for (int q = 1; q < 16; ++q)
+            v[q] = cmulc(v[q], __ldg(&pt12[((q - 1) << 8) + o]));
+        Dft<16, +1>::run(v);
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+            g[o + (n << 8)] = v[n];
+    }
+}
+
+// grid.x * 256 threads = B * 4096
+template <int R>
+__global__ void __launch_bounds__(256) k_cz2_cols_inv(const Cz2Args a)
+{
+    constexpr int LR = Log2R<R>::value;
+    constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
+    const CzArgs &c = a.c;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = (int)(gid & (N2 - 1));
+    const size_t s = (size_t)(gid >> FNFTB_CZ2_ROW_L2);
+    if (o >= c.M)
+        return;
+    const int L = 1 << a.l2L;
+    const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][LR];
+    cplx H[2][R];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (j < c.npoly) {
+            const cplx *src = c.ybuf + (s * c.npoly + j) * (size_t)L;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                cplx y = src[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o];
+                if (q > 0)
+                    y = cmulc(y, __ldg(&pt[((q - 1) << FNFTB_CZ2_ROW_L2) + o]));
+                H[j][q] = y;
+            }
+            Dft<R, +1>::run(H[j]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                H[j][q] = czero();
+        }
+    }
+    cplx *out = c.out + s * c.out_sstride;
+#pragma unroll
+    for (int n = 0; n < R; ++n) {
+        const int m = o + n * N2;
+        if (m >= c.M)
+            break;
+        const cplx ch = __ldg(&c.tab_out[m]);
+        const cplx H0 = cmul(H[0][n], ch), H1 = cmul(H[1][n], ch);
+        if (c.mode == FNFTB_CZ_RAW) {
+            const size_t js = c.out_jstride ? c.out_jstride : (size_t)c.M;
+            out[m] = H0;
+            if (c.npoly > 1)
+                out[js + m] = H1;
+        } else if (c.mode == FNFTB_CZ_NSEV) {
+            // src/fnft_nsev.c:846-876; H0 = H11 (a-poly), H1 = H21 (b-poly)
+            size_t off = 0;
+            if (c.cstype == 0 || c.cstype == 2) {
+                if (H0.x == 0.0 && H0.y == 0.0) {
+                    if (c.status)
+                        c.status[s] = 3;
+                    out[m] = make_cplx(NAN, NAN);
+                } else {
+                    out[m] = cdiv(cmul(H1, __ldg(&c.tab_ph[m])), H0);
+                }
+                off = c.M;
+            }
+            if (c.cstype == 1 || c.cstype == 2) {
+                const double scale = ldexp(1.0, c.W ? c.W[s] : 0);
+                out[off + m] = cmul(cscale(H0, scale), __ldg(&c.tab_ph[c.M + m]));
+                out[off + c.M + m] = cmul(cscale(H1, scale), __ldg(&c.tab_ph[2 * (size_t)c.M + m]));
+            }
+        } else {
+            // src/fnft_kdvv.c:186-203; H0 = H12, H1 = H22, xi grid negated
+            const double xi = -c.xi0 - (double)m * c.eps_xi;
+            cplx h12 = H0;
+            if (c.kdv_sqrtz != 0.0)
+                h12 = cdiv(h12, __ldg(&c.tab_ph[c.M + m]));
+            const cplx num = cmul(__ldg(&c.tab_ph[m]), h12);
+            const cplx den = make_cplx(-2.0 * xi * H1.y - h12.x, 2.0 * xi * H1.x - h12.y);
+            out[m] = cdiv(num, den);
+        }
+    }
+}
+
+template <class K>
+static inline int cz2_launch(K kernel, const Cz2Args &a, unsigned grid, int nt, size_t smem, cudaStream_t st,
+                             const char *name)
+{
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return (int)e;
+    }
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin(name, st);
+    kernel<<<grid, nt, smem, st>>>(a);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(st);
+    ++g_fnftb_launch_count;
+    return (int)cudaGetLastError();
+}
+
+static inline bool cz2_supported(int deg, int M)
+{
+    size_t need = (size_t)deg + (size_t)M, L = 1;
+    int l2 = 0;
+    while (L < need) {
+        L *= 2;
+        ++l2;
+    }
+    return l2 >= FNFTB_CZ2_ROW_L2 + 1 && l2 <= FNFTB_CZ2_ROW_L2 + 4 && l2 <= FNFTB_TW_MAXL;
+}
+
+// Same contract as cz_run (chirpz_driver.cuh); a.vhat doubles as the permuted FFT(v).
+static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st)
+{
+    size_t need = (size_t)c.deg + (size_t)c.M, L = 1;
+    int l2L = 0;
+    while (L < need) {
+        L *= 2;
+        ++l2L;
+    }
+    const int l2R = l2L - FNFTB_CZ2_ROW_L2;
+    c.L = (int)L;
+    c.N2 = 1 << FNFTB_CZ2_ROW_L2;
+    c.N1 = 1 << l2R;
+    c.plan1 = make_fft_plan(c.N1);  // only used by the table kernel's (unused) twiddle table
+    c.tab_y = tables;
+    c.tab_out = c.tab_y + (c.deg + 1);
+    c.tab_ph = c.tab_out + c.M;
+    c.tab_tw = c.tab_ph + 3 * (size_t)c.M;
+    int rc;
+    {
+        long long tot = c.deg + 1;
+        if (c.M > tot)
+            tot = c.M;
+        if ((long long)L > tot)
+            tot = (long long)L;
+        rc = launch_blocks<CzArgs, blk_cz_tables>(c, (unsigned)((tot + 255) / 256), 256, 0, st, "cz_filter");
+        if (rc)
+            return rc;
+    }
+    Cz2Args a;
+    a.c = c;
+    a.tw = tw;
+    a.vperm = c.vhat;
+    a.l2L = l2L;
+    const size_t smem = sizeof(cplx) << FNFTB_CZ2_ROW_L2;
+    const unsigned cols1 = (unsigned)((size_t)1 << FNFTB_CZ2_ROW_L2) / 256;
+    const size_t narr = (size_t)c.B * c.npoly;
+#define CZ2_BY_R(KERNEL, ARGS, GRID, NAME)                                                     \
+    switch (l2R) {                                                                             \
+    case 1: rc = cz2_launch(KERNEL<2>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    case 2: rc = cz2_launch(KERNEL<4>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    case 3: rc = cz2_launch(KERNEL<8>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    default: rc = cz2_launch(KERNEL<16>, ARGS, GRID, 256, 0, st, NAME); break;                 \
+    }
+    // spectrum of the chirp filter (signal independent)
+    {
+        Cz2Args v = a;
+        v.gen_v = 1;
+        v.c.ybuf = c.ybuf;  // array 0 of the workspace as scratch
+        CZ2_BY_R(k_cz2_cols_fwd, v, cols1, "cz_filter");
+        if (rc)
+            return rc;
+        rc = cz2_launch(k_cz2_rows, v, 1u << l2R, 128, smem, st, "cz_filter");
+        if (rc)
+            return rc;
+    }
+    a.gen_v = 0;
+    CZ2_BY_R(k_cz2_cols_fwd, a, (unsigned)(narr * cols1), "cz_cols_fwd");
+    if (rc)
+        return rc;
+    rc = cz2_launch(k_cz2_rows, a, (unsigned)(narr << l2R), 128, smem, st, "cz_rows");
+    if (rc)
+        return rc;
+    CZ2_BY_R(k_cz2_cols_inv, a, (unsigned)((size_t)c.B * cols1), "cz_cols_inv");
+#undef CZ2_BY_R
+    return rc;
+}
+#endif  // !FNFTB_EMUL

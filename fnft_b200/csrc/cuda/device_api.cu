@@ -4,6 +4,7 @@
 
 #include "bound_kernels.cuh"
 #include "chirpz_driver.cuh"
+#include "chirpz2.cuh"
 #include "nsep_kernels.cuh"
 #include "resample_kernels.cuh"
 #include "tree_driver.cuh"
@@ -479,7 +480,13 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
     a.kdv_ph = d->kdv_ph;
     a.kdv_sqrtz = d->kdv_sqrtz;
     a.status = (int *)c->status.p;
-    RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+    {
+        static const int knob_cz2 = tree_knob("FNFT_B200_CZ2", 1);
+        if (knob_cz2 && cz2_supported((int)c->deg, (int)d->M))
+            RC(cz2_run(a, (cplx *)c->cztab.p, c->tws, c->st));
+        else
+            RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+    }
     if (!on_device) {
         CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     }
