@@ -232,7 +232,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        nsig = args.ref_signals or max(2 * cores, 16)
+        nsig = args.ref_signals or max(8 * cores, 64)
         for _ in range(max(args.warmup, 0) and 1):
             run_reference_sample(min(nsig, cores), cores)
         t_tot, n_tot = 0.0, 0
@@ -264,7 +264,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import ref_lib as R
         if R.available():
-            nsig = max(cores, 8)
+            nsig = min(args.batch, max(8 * cores, 64))  # ~20 core-seconds of reference work
             rate, wall, ref_out = run_reference_sample(nsig, cores, P_all)
             cpu_baseline = {"value": rate, "unit": "signals/s", "cores": cores, "kind": "reference",
                             "sample": "first %d signals of the batch, one signal per task over %d "

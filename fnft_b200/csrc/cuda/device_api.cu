@@ -50,6 +50,50 @@ void fnftb_profile_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st);
 
 static thread_local std::string g_err;
 
+// optional timeline of the pipelined mode (env FNFT_B200_PIPE_TRACE=1): timed events at the
+// start / end of every copy-in, compute and copy-out, printed by fnftb_pipeline_end
+struct TraceRec {
+    const char *what;
+    int chunk;
+    cudaEvent_t ev;
+};
+static std::vector<TraceRec> g_trace;
+static int trace_on()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("FNFT_B200_PIPE_TRACE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+static void trace_mark(const char *what, int chunk, cudaStream_t st)
+{
+    if (!trace_on())
+        return;
+    TraceRec r;
+    r.what = what;
+    r.chunk = chunk;
+    cudaEventCreate(&r.ev);
+    cudaEventRecord(r.ev, st);
+    g_trace.push_back(r);
+}
+static void trace_dump()
+{
+    if (!trace_on() || g_trace.empty())
+        return;
+    cudaDeviceSynchronize();
+    for (size_t i = 0; i < g_trace.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_trace[0].ev, g_trace[i].ev);
+        fprintf(stderr, "[pipe] chunk %2d %-10s %8.3f ms\n", g_trace[i].chunk, g_trace[i].what, ms);
+    }
+    for (auto &r : g_trace)
+        cudaEventDestroy(r.ev);
+    g_trace.clear();
+}
+static int g_trace_chunk = 0;
+
 static int fail(int code, const char *what, const char *file, int line)
 {
     char buf[512];
@@ -101,6 +145,14 @@ struct fnftb_ctx {
     // nsep workspace
     Buf fpoly, vals, roots, nraw, nkept;
     int have_box3 = 0;
+    // pipelined host transfers (fnftb_pipeline_begin): two slots, copy streams, events
+    int pipe_on = 0, slot = 0;
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    int comp_valid[2] = {0, 0}, d2h_valid[2] = {0, 0};
+    Buf qslot[2], outslot[2], stslot[2];
+    int32_t *st_pinned[2] = {nullptr, nullptr};  // pinned host copies of the per-chunk status
+    size_t st_pinned_cap[2] = {0, 0};
 };
 
 static TwTable ctx_tw(const fnftb_ctx *c)
@@ -227,9 +279,24 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
     Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->colbuf, &c->W,
                   &c->status, &c->tm, &c->tt0, &c->tt1, &c->twmem, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
-                  &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept};
+                  &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept,
+                  &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1]};
     for (Buf *b : all)
         release(*b);
+    if (c->st_h2d)
+        cudaStreamDestroy(c->st_h2d);
+    if (c->st_d2h)
+        cudaStreamDestroy(c->st_d2h);
+    for (int i = 0; i < 2; ++i) {
+        if (c->st_pinned[i])
+            cudaFreeHost(c->st_pinned[i]);
+        if (c->ev_h2d[i])
+            cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_comp[i])
+            cudaEventDestroy(c->ev_comp[i]);
+        if (c->ev_d2h[i])
+            cudaEventDestroy(c->ev_d2h[i]);
+    }
     if (c->tw)
         cudaFree(c->tw);
     if (c->st)
@@ -247,6 +314,61 @@ int fnftb_ctx_sync(fnftb_ctx *c)
 }
 
 void *fnftb_ctx_stream(fnftb_ctx *c) { return (void *)c->st; }
+
+// ---------------------------------------------------------------------------
+// Pipelined host transfers.  Between begin and end, fnftb_set_signals (host q) copies on
+// its own stream into one of two input slots and fnftb_contspec (host out) returns
+// without waiting: the device->host copy of the results runs on a third stream.  The
+// caller alternates slots 0, 1, 0, ... with its chunks and calls fnftb_pipeline_wait(slot)
+// before it reads the outputs / status of the chunk that used that slot.
+// ---------------------------------------------------------------------------
+int fnftb_pipeline_begin(fnftb_ctx *c)
+{
+    if (!c)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    if (!c->st_h2d) {
+        CU(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    CU(cudaStreamSynchronize(c->st));
+    c->pipe_on = 1;
+    c->slot = 0;
+    c->comp_valid[0] = c->comp_valid[1] = 0;
+    c->d2h_valid[0] = c->d2h_valid[1] = 0;
+    return 0;
+}
+
+int fnftb_pipeline_wait(fnftb_ctx *c, int slot, const int32_t **status)
+{
+    if (!c || slot < 0 || slot > 1)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    if (c->d2h_valid[slot])
+        CU(cudaEventSynchronize(c->ev_d2h[slot]));
+    if (status)
+        *status = c->st_pinned[slot];
+    return 0;
+}
+
+int fnftb_pipeline_end(fnftb_ctx *c)
+{
+    if (!c)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    c->pipe_on = 0;
+    trace_dump();
+    g_trace_chunk = 0;
+    if (c->st_h2d) {
+        CU(cudaStreamSynchronize(c->st_h2d));
+        CU(cudaStreamSynchronize(c->st));
+        CU(cudaStreamSynchronize(c->st_d2h));
+    }
+    return 0;
+}
 
 static size_t per_signal_bytes(size_t D, int deg0, size_t M, int npoly)
 {
@@ -296,6 +418,21 @@ int fnftb_set_signals(fnftb_ctx *c, size_t B, size_t D, const void *q, const voi
         return 0;
     }
     const size_t bytes = B * D * sizeof(cplx);
+    if (c->pipe_on && !r) {
+        const int sl = c->slot;
+        RC(ensure(c->qslot[sl], bytes));
+        if (c->comp_valid[sl])  // the chunk that used this slot before has finished computing
+            CU(cudaStreamWaitEvent(c->st_h2d, c->ev_comp[sl], 0));
+        trace_mark("h2d_start", g_trace_chunk, c->st_h2d);
+        CU(cudaMemcpyAsync(c->qslot[sl].p, q, bytes, cudaMemcpyHostToDevice, c->st_h2d));
+        trace_mark("h2d_end", g_trace_chunk, c->st_h2d);
+        CU(cudaEventRecord(c->ev_h2d[sl], c->st_h2d));
+        CU(cudaStreamWaitEvent(c->st, c->ev_h2d[sl], 0));
+        trace_mark("comp_start", g_trace_chunk, c->st);
+        c->q = (const cplx *)c->qslot[sl].p;
+        c->r = nullptr;
+        return 0;
+    }
     RC(ensure(c->qbuf, bytes));
     CU(cudaMemcpyAsync(c->qbuf.p, q, bytes, cudaMemcpyHostToDevice, c->st));
     c->q = (const cplx *)c->qbuf.p;
@@ -446,7 +583,23 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
     RC(ensure(c->vhat, (size_t)g.L * sizeof(cplx)));
     RC(ensure(c->cztab, cz_table_elems(g, (int)c->deg, (int)d->M) * sizeof(cplx)));
     cplx *dst = (cplx *)out;
-    if (!on_device) {
+    const bool piped = c->pipe_on && !on_device;
+    const int sl = c->slot;
+    if (piped) {
+        RC(ensure(c->outslot[sl], B * out_sstride * sizeof(cplx)));
+        RC(ensure(c->stslot[sl], B * sizeof(int)));
+        if (c->st_pinned_cap[sl] < B) {  // a pageable destination would make the copy synchronous
+            if (c->st_pinned[sl])
+                CU(cudaFreeHost(c->st_pinned[sl]));
+            c->st_pinned[sl] = nullptr;
+            c->st_pinned_cap[sl] = 0;
+            CU(cudaMallocHost((void **)&c->st_pinned[sl], B * sizeof(int32_t)));
+            c->st_pinned_cap[sl] = B;
+        }
+        if (c->d2h_valid[sl])  // results of the previous user of this slot have left the device
+            CU(cudaStreamWaitEvent(c->st, c->ev_d2h[sl], 0));
+        dst = (cplx *)c->outslot[sl].p;
+    } else if (!on_device) {
         RC(ensure(c->outbuf, B * out_sstride * sizeof(cplx)));
         dst = (cplx *)c->outbuf.p;
     }
@@ -486,6 +639,22 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
             RC(cz2_run(a, (cplx *)c->cztab.p, c->tws, c->st));
         else
             RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+    }
+    if (piped) {
+        CU(cudaMemcpyAsync(c->stslot[sl].p, c->status.p, B * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+        CU(cudaEventRecord(c->ev_comp[sl], c->st));
+        trace_mark("comp_end", g_trace_chunk, c->st);
+        c->comp_valid[sl] = 1;
+        CU(cudaStreamWaitEvent(c->st_d2h, c->ev_comp[sl], 0));
+        trace_mark("d2h_start", g_trace_chunk, c->st_d2h);
+        CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st_d2h));
+        CU(cudaMemcpyAsync(c->st_pinned[sl], c->stslot[sl].p, B * sizeof(int), cudaMemcpyDeviceToHost,
+                           c->st_d2h));
+        CU(cudaEventRecord(c->ev_d2h[sl], c->st_d2h));
+        trace_mark("d2h_end", g_trace_chunk++, c->st_d2h);
+        c->d2h_valid[sl] = 1;
+        c->slot ^= 1;
+        return 0;
     }
     if (!on_device) {
         CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));

@@ -65,6 +65,16 @@ int fnftb_ctx_sync(fnftb_ctx *ctx);
 /* the context's stream as a cudaStream_t cast to void* (for event timing) */
 void *fnftb_ctx_stream(fnftb_ctx *ctx);
 
+/* Pipelined host transfers: between begin and end, fnftb_set_signals (host q) and
+ * fnftb_contspec (host out) run their copies on separate streams and do not wait; the
+ * caller alternates slots 0, 1, 0, ... with its chunks and calls fnftb_pipeline_wait(slot)
+ * before reading the outputs of the chunk that used that slot; the per-signal status of
+ * that chunk is returned in a pinned buffer owned by the context (the status_host argument
+ * of fnftb_contspec is ignored in this mode: a pageable destination would serialise). */
+int fnftb_pipeline_begin(fnftb_ctx *ctx);
+int fnftb_pipeline_wait(fnftb_ctx *ctx, int slot, const int32_t **status);
+int fnftb_pipeline_end(fnftb_ctx *ctx);
+
 /* Largest number of signals one fscatter+contspec pass may hold given the
  * workspace budget (bytes; 0 = default budget). */
 size_t fnftb_max_chunk(const fnftb_ctx *ctx, size_t D, int deg0, size_t M, int npoly,

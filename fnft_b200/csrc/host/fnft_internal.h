@@ -38,6 +38,7 @@ FNFT_INT fnftb__device_error(const char *func, const FNFT_INT line);
 fnftb_ctx *fnftb__ctx(void);          /* NULL (after printing why) if no GPU */
 int fnftb__device_pointers(void);     /* flag set by fnft_b200_set_device_pointers */
 size_t fnftb__workspace_limit(void);
+int fnftb__pipe_chunks(void);
 
 /* ln|z| and arg z of a complex double, accurate to far below one ulp of |z|-1 */
 void fnftb__logpolar(FNFT_COMPLEX z, double *ln_abs, double *arg);

@@ -95,15 +95,29 @@ FNFT_INT fnft_kdvv_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
         for (FNFT_UINT b = 0; b < B; b++)
             ret_codes[b] = FNFT_SUCCESS;
 
-    for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
-        const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
-        if (fnftb_set_signals(ctx, nb, D, u + b0 * D, NULL, devptr) != 0)
-            return E_DEVICE;
-        if (fnftb_fscatter(ctx, &sd) != 0)
-            return E_DEVICE;
-        if (fnftb_contspec(ctx, &cd, contspec + b0 * M, M, devptr, NULL) != 0)
+    /* host buffers: overlap the copies of neighbouring chunks with the kernels */
+    const int piped = (!devptr && B >= 16 && fnftb__pipe_chunks() > 0);
+    if (piped) {
+        const size_t nch = (size_t)fnftb__pipe_chunks();
+        size_t c8 = (B + nch - 1) / nch;
+        if (c8 < 64)
+            c8 = 64;
+        if (chunk > c8)
+            chunk = c8;
+        if (fnftb_pipeline_begin(ctx) != 0)
             return E_DEVICE;
     }
+    for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
+        const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        if (fnftb_set_signals(ctx, nb, D, u + b0 * D, NULL, devptr) != 0 ||
+            fnftb_fscatter(ctx, &sd) != 0 ||
+            fnftb_contspec(ctx, &cd, contspec + b0 * M, M, devptr, NULL) != 0) {
+            ret_code = E_DEVICE;
+            break;
+        }
+    }
+    if (piped && fnftb_pipeline_end(ctx) != 0 && ret_code == FNFT_SUCCESS)
+        ret_code = E_DEVICE;
     return ret_code;
 }
 

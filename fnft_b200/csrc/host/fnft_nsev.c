@@ -161,8 +161,20 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
                                    fnftb__workspace_limit());
     if (chunk > B)
         chunk = B;
+    /* Continuous spectrum only, host buffers: overlap the host<->device copies of
+     * neighbouring chunks with the kernels (fnftb_pipeline_*); at least 8 chunks for
+     * large batches so that only a small first copy-in / last copy-out stay exposed. */
+    const int piped = (!devptr && want_contspec && !want_discspec && B >= 16 && fnftb__pipe_chunks() > 0);
+    if (piped) {
+        const size_t nch = (size_t)fnftb__pipe_chunks();
+        size_t c8 = (B + nch - 1) / nch;
+        if (c8 < 64)
+            c8 = 64;
+        if (chunk > c8)
+            chunk = c8;
+    }
     if (!devptr) {
-        status = malloc(chunk * sizeof(int32_t));
+        status = malloc(2 * chunk * sizeof(int32_t));
         if (status == NULL)
             return E_NOMEM;
     }
@@ -179,60 +191,80 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     sd.normalize = opts->normalization_flag ? 1 : 0;
     sd.eps_t = eps_t;
 
-    for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
-        const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
-
-        /* preprocessing (src/fnft_nsev.c:272): plain copy for upsampling 1; the
-         * 4SPLIT4 schemes resample on the device */
-        if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, devptr) != 0) {
-            ret_code = E_DEVICE;
-            goto leave_fun;
-        }
-        if (upsampling == 2) {
-            int32_t *warn = devptr ? NULL : malloc(nb * sizeof(int32_t));
-            if (fnftb_resample_4split4(ctx, eps_t, warn) != 0) {
-                free(warn);
+    if (piped && fnftb_pipeline_begin(ctx) != 0) {
+        ret_code = E_DEVICE;
+        goto leave_fun;
+    }
+    FNFT_UINT prev_b0 = 0, prev_nb = 0; /* chunk whose results are still in flight */
+    int slot = 0;
+    for (FNFT_UINT b0 = 0; b0 < B || prev_nb > 0; b0 += chunk) {
+        const FNFT_UINT nb = (b0 >= B) ? 0 : ((B - b0 < chunk) ? (B - b0) : chunk);
+        int32_t *st_cur = status ? status + (size_t)slot * chunk : NULL;
+        if (nb > 0) {
+            /* preprocessing (src/fnft_nsev.c:272): plain copy for upsampling 1; the
+             * 4SPLIT4 schemes resample on the device */
+            if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, devptr) != 0) {
                 ret_code = E_DEVICE;
                 goto leave_fun;
             }
-            if (warn != NULL) {
-                for (FNFT_UINT b = 0; b < nb; b++) {
-                    if (warn[b]) { /* src/private/fnft__misc.c:379-380 */
-                        WARN("Signal does not appear to be bandlimited. Interpolation step may be inaccurate. Try to reduce the step size, or switch to a discretization that does not require interpolation");
-                        break;
-                    }
-                }
-                free(warn);
-            }
-        }
-
-        /* transfer matrix: nse_fscatter (src/fnft_nsev.c:527).  The Newton path never
-         * reads it, so it is only built when a continuous spectrum is wanted. */
-        if (want_contspec) {
-            if (fnftb_fscatter(ctx, &sd) != 0) {
-                ret_code = E_DEVICE;
-                goto leave_fun;
-            }
-        }
-
-        if (want_contspec) {
-            ret_code = nsev_contspec_chunk(ctx, D, T, M, XI, opts, contspec + b0 * cs_len, devptr,
-                                           devptr ? NULL : status);
-            CHECK_RETCODE(ret_code, leave_fun);
-            if (!devptr) {
-                for (FNFT_UINT b = 0; b < nb; b++) {
-                    if (status[b] == FNFT_EC_DIV_BY_ZERO) {
-                        const FNFT_INT ec = E_DIV_BY_ZERO; /* src/fnft_nsev.c:850-852 */
-                        if (ret_codes != NULL)
-                            ret_codes[b0 + b] = ec;
-                        if (ret_code == FNFT_SUCCESS)
-                            ret_code = ec;
-                    }
-                }
-                if (ret_code != FNFT_SUCCESS && ret_codes == NULL)
+            if (upsampling == 2) {
+                int32_t *warn = devptr ? NULL : malloc(nb * sizeof(int32_t));
+                if (fnftb_resample_4split4(ctx, eps_t, warn) != 0) {
+                    free(warn);
+                    ret_code = E_DEVICE;
                     goto leave_fun;
+                }
+                if (warn != NULL) {
+                    for (FNFT_UINT b = 0; b < nb; b++) {
+                        if (warn[b]) { /* src/private/fnft__misc.c:379-380 */
+                            WARN("Signal does not appear to be bandlimited. Interpolation step may be inaccurate. Try to reduce the step size, or switch to a discretization that does not require interpolation");
+                            break;
+                        }
+                    }
+                    free(warn);
+                }
+            }
+
+            /* transfer matrix: nse_fscatter (src/fnft_nsev.c:527).  The Newton path never
+             * reads it, so it is only built when a continuous spectrum is wanted. */
+            if (want_contspec) {
+                if (fnftb_fscatter(ctx, &sd) != 0) {
+                    ret_code = E_DEVICE;
+                    goto leave_fun;
+                }
+                ret_code = nsev_contspec_chunk(ctx, D, T, M, XI, opts, contspec + b0 * cs_len, devptr,
+                                               st_cur);
+                CHECK_RETCODE(ret_code, leave_fun);
             }
         }
+        /* status of the chunk whose results are complete: the current one, or in
+         * pipelined mode the previous one (its copy-out overlapped this chunk's kernels) */
+        if (want_contspec && !devptr) {
+            const FNFT_UINT cb0 = piped ? prev_b0 : b0, cnb = piped ? prev_nb : nb;
+            const int32_t *st_chk = st_cur;
+            if (piped && cnb > 0 && fnftb_pipeline_wait(ctx, slot ^ 1, &st_chk) != 0) {
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+            for (FNFT_UINT b = 0; b < cnb; b++) {
+                if (st_chk[b] == FNFT_EC_DIV_BY_ZERO) {
+                    const FNFT_INT ec = E_DIV_BY_ZERO; /* src/fnft_nsev.c:850-852 */
+                    if (ret_codes != NULL)
+                        ret_codes[cb0 + b] = ec;
+                    if (ret_code == FNFT_SUCCESS)
+                        ret_code = ec;
+                }
+            }
+            if (ret_code != FNFT_SUCCESS && ret_codes == NULL)
+                goto leave_fun;
+        }
+        if (piped) {
+            prev_b0 = b0;
+            prev_nb = nb;
+            slot ^= 1;
+        }
+        if (nb == 0)
+            break;
 
         if (want_discspec) {
             FNFT_INT rc2 = fnftb__nsev_discrete_chunk(ctx, nb, D_eff, D, T, eps_t, K + b0, Kmax,
@@ -254,6 +286,8 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     }
 
 leave_fun:
+    if (piped)
+        (void)fnftb_pipeline_end(ctx);
     free(status);
     return ret_code;
 }

@@ -4,6 +4,7 @@
  * workspaces); contexts are created lazily on first use.
  */
 #include "fnft_internal.h"
+#include <stdlib.h>
 #include <stdio.h>
 
 static __thread fnftb_ctx *tl_ctx = NULL;
@@ -36,6 +37,20 @@ fnftb_ctx *fnftb__ctx(void)
 
 int fnftb__device_pointers(void) { return tl_devptr; }
 size_t fnftb__workspace_limit(void) { return tl_limit; }
+
+/* number of chunks the pipelined batch loops aim for (env FNFT_B200_PIPE, 0 = no
+ * pipelining, default 16) */
+int fnftb__pipe_chunks(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("FNFT_B200_PIPE");
+        v = (e && e[0]) ? atoi(e) : 16;
+        if (v < 0)
+            v = 0;
+    }
+    return v;
+}
 
 FNFT_INT fnft_b200_device_count(void) { return (FNFT_INT)fnftb_device_count(); }
 
