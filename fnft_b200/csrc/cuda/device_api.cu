@@ -3,6 +3,7 @@
 #include "fnftb_device.h"
 
 #include "bound_kernels.cuh"
+#include "bound_warp.cuh"
 #include "chirpz_driver.cuh"
 #include "chirpz2.cuh"
 #include "nsep_kernels.cuh"
@@ -990,7 +991,19 @@ int fnftb_newton(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_host,
     RC(stage_eigs(c, d, K_host, lam_host));
     const size_t n = c->B * (size_t)d->Kmax;
     BoundArgs a = bound_args(c, d);
-    RC((launch_blocks<BoundArgs, blk_newton, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st, "bound_newton")));
+    static const int knob_warp = tree_knob("FNFT_B200_BOUND_WARP", 1);
+    if (knob_warp) {
+        // one eigenvalue per warp (bound_warp.cuh)
+        if (g_fnftb_profile_on)
+            fnftb_profile_begin("bound_newton_warp", c->st);
+        k_newton_warp<<<(unsigned)((n + 3) / 4), 128, 0, c->st>>>(a);
+        if (g_fnftb_profile_on)
+            fnftb_profile_end(c->st);
+        ++g_fnftb_launch_count;
+        CU(cudaGetLastError());
+    } else {
+        RC((launch_blocks<BoundArgs, blk_newton, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st, "bound_newton")));
+    }
     CU(cudaMemcpyAsync(lam_host, c->lam.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     if (flag_host)
         CU(cudaMemcpyAsync(flag_host, c->flag.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -1015,7 +1028,18 @@ int fnftb_normconsts(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_h
     CU(cudaMemsetAsync(c->apout.p, 0, n * sizeof(cplx), c->st));
     CU(cudaMemsetAsync(c->bout.p, 0, n * sizeof(cplx), c->st));
     BoundArgs a = bound_args(c, d);
-    RC((launch_blocks<BoundArgs, blk_normconsts, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st, "bound_normconsts")));
+    static const int knob_warp = tree_knob("FNFT_B200_BOUND_WARP", 1);
+    if (knob_warp) {
+        if (g_fnftb_profile_on)
+            fnftb_profile_begin("bound_normconsts_warp", c->st);
+        k_normconsts_warp<<<(unsigned)((n + 3) / 4), 128, 0, c->st>>>(a);
+        if (g_fnftb_profile_on)
+            fnftb_profile_end(c->st);
+        ++g_fnftb_launch_count;
+        CU(cudaGetLastError());
+    } else {
+        RC((launch_blocks<BoundArgs, blk_normconsts, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st, "bound_normconsts")));
+    }
     if (a_host)
         CU(cudaMemcpyAsync(a_host, c->aout.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     if (ap_host)
