@@ -357,9 +357,21 @@ def main():
     peak, peak_src = measured_hbm_peak()
     bts = tree_bytes_per_signal()
     achieved = bts * B / (tree_ms * 1e-3) / 1e9
+    # physical DRAM traffic of the tree kernels: per-signal bytes from the committed ncu capture
+    # (profiles/tree_dram_bytes.json, dram__bytes_read.sum + dram__bytes_write.sum), times the
+    # signals of one step -- "per launch set" like `achieved`
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "tree_dram_bytes.json")) as f:
+            tj = json.load(f)
+        traffic = float(tj["tree_bytes_per_signal"]) * B
+        traffic_src = tj.get("source")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "fmult2x2 product tree (all tree_* launches of one step)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                "physical_gbs": (traffic / (tree_ms * 1e-3) / 1e9) if traffic else None,
                 "algorithmic_bytes_per_signal": bts, "tree_ms_per_step": tree_ms,
                 "tree_launches_per_step": tree_launches, "tree_share_of_step": tree_ms / total_ms,
                 "kernel_ms_per_step": {k: round(ms, 4) for k, (n, ms) in sorted(rep.items())}}
