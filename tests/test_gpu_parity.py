@@ -145,6 +145,81 @@ def test_fscatter_vs_oracle(F, disc, D):
         assert rel_err(tm[e] * 2.0 ** W, tmo[e] * 2.0 ** Wo) < 1e-10, (disc, D, e)
 
 
+@pytest.mark.parametrize("kappa", [+1, -1])
+@pytest.mark.parametrize("normalize", [True, False])
+def test_spectrum_carry_tree_normalisation_and_kappa(F, kappa, normalize):
+    """tree_low2 / tree_up: strong potential so that the power-of-two exponents of
+    the thread phase and of the upper levels are exercised (kappa = -1 grows like cosh), with and
+    without normalisation; result * 2^W must agree with the oracle's."""
+    D = 2048 if not normalize else 8192
+    T = (-10.0, 10.0)
+    amp = 6.0 if normalize else 2.0
+    q = sech_chirp(D, T, amp, 0.4) + 0.3 * amp * np.exp(-((np.linspace(T[0], T[1], D) - 3.0) / 0.7) ** 2)
+    eps_t = (T[1] - T[0]) / (D - 1)
+    ret, tm, deg, W = F.nse_fscatter(q, eps_t, kappa, 11, normalize)
+    tmo, dego, Wo = O.nse_fscatter(q, eps_t, kappa, 11, normalize)
+    assert ret == 0 and deg == dego
+    if not normalize:
+        assert W == 0
+    for e in range(4):
+        assert rel_err(tm[e] * 2.0 ** W, tmo[e] * 2.0 ** Wo) < 1e-10, (kappa, normalize, e)
+
+
+def test_spectrum_carry_padded_lengths_and_modal_scheme(F):
+    """non-power-of-two D (padding matrices diag(z^d, 1)) on the spectrum path, generic leaf
+    (2SPLIT2_MODAL, out-of-line leaf call of tree_low2) and the deg0 = 1 build"""
+    for disc, D in ((0, 3000), (5, 5000), (11, 6001)):
+        T = (-9.0, 9.0)
+        q = 0.6 * sech_chirp(D, T, 1.9, -0.3)
+        eps_t = (T[1] - T[0]) / (D - 1)
+        ret, tm, deg, W = F.nse_fscatter(q, eps_t, 1, disc)
+        tmo, dego, Wo = O.nse_fscatter(q, eps_t, 1, disc)
+        assert ret == 0 and deg == dego
+        for e in range(4):
+            assert rel_err(tm[e] * 2.0 ** W, tmo[e] * 2.0 ** Wo) < 1e-10, (disc, D, e)
+
+
+def test_pipelined_batch_equals_single_calls_config2_shape(F):
+    """fnft_nsev_batch with host buffers runs its chunks through the copy/compute pipeline
+    (DESIGN 7); every signal must be bit-identical to the single-signal call."""
+    rng = np.random.default_rng(5)
+    B, D, M = 70, 4096, 2048
+    T, XI = (-32.0, 32.0), (-10.0, 10.0)
+    t = np.linspace(T[0], T[1], D)
+    Q = (rng.uniform(0.5, 5.4, (B, 1)) / np.cosh(t)[None] *
+         np.exp(-2j * rng.uniform(-3, 3, (B, 1)) * t[None]))
+    ret, cs, _, _, _, rcs = F.nsev_batch(Q, T, M, XI, 1)
+    assert ret == 0 and (rcs == 0).all()
+    for b in (0, 1, 33, 64, 69):
+        r1, c1, *_ = F.nsev(Q[b], T, M, XI, 1)
+        assert r1 == 0 and np.array_equal(c1, cs[b])
+
+
+def test_newton_warp_kernels_many_eigenvalues(F):
+    """bound_warp.cuh at a size where every lane owns a long chunk, D not a multiple of 32,
+    both BO (2SPLIT4B) and CF4_2 (4SPLIT4B, power-of-two D).  The potential is deliberately
+    asymmetric: on a symmetric one the reference's error metric for the choice of b
+    (fnft__nse_scatter_bound_states.c:642-654) has mirror-image minima that are equal up to
+    rounding, so WHICH sample point wins -- and with it b -- is decided by noise."""
+    F.lib().fnft_errwarn_setprintf(None)
+    for disc, D in ((11, 1500), (21, 1024)):
+        T = (-16.0, 16.0)
+        t = np.linspace(T[0], T[1], D)
+        q = 2.6 / np.cosh(t - 1.5) * np.exp(0.3j * t) + 1.7 / np.cosh((t + 2.0) / 0.8) * np.exp(-0.2j * t)
+        g = np.array([-0.075 + 1.20j, 0.06 + 1.30j, -0.15 + 2.15j, -0.035 + 0.35j]) + (0.01 + 0.01j)
+        o = F.nsev_default_opts()
+        o.discretization = disc
+        o.bound_state_localization = F.BSLOC_NEWTON
+        o.discspec_type = F.DSTYPE_BOTH
+        ret, cs, K, bs, nc = F.nsev(q, T, 0, None, 1, o, K=len(g), bound_states=g, want_contspec=False)
+        bo, no = O.nsev_bound_states_newton(q, T, g, disc, 10, 2, 2)
+        assert ret == 0 and K == len(bo) == 4, (disc, K, len(bo))
+        order = [int(np.argmin(np.abs(bs - b))) for b in bo]
+        assert (np.abs(bs[order] - bo) <= 1e-9 * np.abs(bo)).all()
+        assert (np.abs(nc[:K][order] - no[:K]) <= 1e-9 * np.abs(no[:K])).all()
+        assert (np.abs(nc[K:2 * K][order] - no[K:2 * K]) <= 1e-9 * np.abs(no[K:2 * K])).all()
+
+
 @pytest.mark.parametrize("D,M", [(126, 40), (1024, 1024), (4096, 4000), (16384, 16384)])
 @pytest.mark.parametrize("kappa", [+1, -1])
 def test_nsev_contspec_vs_oracle(F, D, M, kappa):
