@@ -457,8 +457,8 @@ static int ensure_tree(fnftb_ctx *c, size_t B, size_t npad, size_t deg0, size_t 
     RC(ensure(c->W, B * sizeof(int)));
     RC(ensure(c->status, B * sizeof(int)));
     RC(ensure(c->tm, B * 4 * (deg_out + 1) * sizeof(cplx)));
-    RC(ensure(c->tt0, (B * npad / 256 + 1) * 4 * sizeof(cplx)));
-    RC(ensure(c->tt1, (B * npad / 256 + 1) * 4 * sizeof(cplx)));
+    RC(ensure(c->tt0, (B * npad / 256 + 1) * 8 * sizeof(cplx)));
+    RC(ensure(c->tt1, (B * npad / 256 + 1) * 8 * sizeof(cplx)));
     return 0;
 }
 

@@ -44,7 +44,10 @@ struct TreeWork {
 // workspace sizes (elements) for B signals of npad matrices of degree deg0
 static inline size_t tree_lev_elems(size_t B, size_t npad, size_t deg0)
 {
-    return B * 4 * npad * (deg0 + 1);
+    // coefficient form: 4 entries of degree deg0 per level-0 matrix; spectrum form of the general
+    // 2x2 path (tree_low2g / tree_up): 4 entries * 2*degree values per matrix = 8*npad*deg0
+    const size_t coef = 4 * npad * (deg0 + 1), spec = 8 * npad * deg0;
+    return B * (coef > spec ? coef : spec) + 64;
 }
 static inline size_t tree_gbuf_elems(size_t B, size_t npad, size_t deg0)
 {
@@ -386,8 +389,8 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
                     memset(&ua, 0, sizeof(ua));
                     ua.in = w.lev[cur];
                     ua.out = w.lev[1 - cur];
-                    ua.tt_in = (const Low2Tops *)w.tt[cur];
-                    ua.tt_out = (Low2Tops *)w.tt[1 - cur];
+                    ua.tt_in = w.tt[cur];
+                    ua.tt_out = w.tt[1 - cur];
                     ua.mx_in = w.mx[cur];
                     ua.mx_out = w.mx[1 - cur];
                     ua.W = w.W;
@@ -405,6 +408,69 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
                     cur = 1 - cur;
                 }
                 return tree_finalize(w, cur, B, deg0 * npad, deg0 * D, normalize, tm, st, sym, kappa);
+            }
+        }
+    }
+    // general 2x2 spectrum-carry path (tree_low2g.cuh + tree_up.cuh with E = 4): KdV, explicit r
+    static const int knob_gen = tree_knob("FNFT_B200_TREE_GEN2", 1);
+    if (!low2_done && !sym && knob_low && knob_gen && use_direct && w.tws != nullptr && w.tt[0] != nullptr &&
+        (deg0 == 1 || deg0 == 2)) {
+        const int log2m = 8;
+        const int S2 = low2g_samples(log2m, deg0);
+        if (S2 <= npad) {
+            const int n_low = npad / S2;
+            const int l2n0 = ilog2i((unsigned)(2 * deg0 * S2));
+            bool spec = n_low >= 2;
+            for (int n = n_low, l = l2n0; spec && n >= 2; n /= 2, ++l)
+                spec = up_supported(l, knob_up_smem);
+            if (spec || n_low == 1) {
+                Low2gArgs lo;
+                memset(&lo, 0, sizeof(lo));
+                lo.q = q;
+                lo.r = r;
+                lo.out = w.lev[0];
+                lo.mx_out = w.mx[0];
+                lo.W = w.W;
+                lo.status = w.status;
+                lo.tt_out = (GenTops *)w.tt[0];
+                lo.tw = *(const TwSet *)w.tws;
+                lo.spec_out = spec ? 1 : 0;
+                lo.B = B;
+                lo.D = D;
+                lo.npad = npad;
+                lo.rmode = rmode;
+                lo.kappa = kappa;
+                lo.scheme = scheme;
+                lo.normalize = normalize;
+                lo.eps_t = eps_t;
+                rc = (deg0 == 2) ? low2g_launch_t<8, 2>(lo, st) : low2g_launch_t<8, 1>(lo, st);
+                if (rc)
+                    return rc;
+                int cur = 0;
+                for (int n = n_low, l = l2n0; spec && n >= 2; n /= 2, ++l) {
+                    UpArgs ua;
+                    memset(&ua, 0, sizeof(ua));
+                    ua.in = w.lev[cur];
+                    ua.out = w.lev[1 - cur];
+                    ua.tt_in = w.tt[cur];
+                    ua.tt_out = w.tt[1 - cur];
+                    ua.mx_in = w.mx[cur];
+                    ua.mx_out = w.mx[1 - cur];
+                    ua.W = w.W;
+                    ua.ws = w.gbuf;
+                    ua.B = B;
+                    ua.n_in = n;
+                    ua.l2n = l;
+                    ua.normalize = normalize;
+                    ua.kappa = kappa;
+                    ua.last = (n == 2) ? 1 : 0;
+                    ua.tw = *(const TwSet *)w.tws;
+                    rc = up_level(ua, knob_up_smem, st, false);
+                    if (rc)
+                        return rc;
+                    cur = 1 - cur;
+                }
+                return tree_finalize(w, cur, B, deg0 * npad, deg0 * D, normalize, tm, st, 0, kappa);
             }
         }
     }

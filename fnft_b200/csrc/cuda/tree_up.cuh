@@ -20,14 +20,15 @@
 #pragma once
 #ifndef FNFTB_EMUL
 #include "tree_low2.cuh"
+#include "tree_low2g.cuh"
 
 #define FNFTB_UP_ROW_L2 12  // row-split levels use rows of 4096 positions
 
 struct UpArgs {
-    const cplx *in;         // [B][n_in][2][N]
-    cplx *out;              // [B][n_in/2][2][2N], or coefficients [B][n_in/2][2][N+1] (last)
-    const Low2Tops *tt_in;  // [B][n_in]
-    Low2Tops *tt_out;       // [B][n_in/2]
+    const cplx *in;         // [B][n_in][E][N]      (E = 2 first-row-only, 4 general)
+    cplx *out;              // [B][n_in/2][E][2N], or coefficients [B][n_in/2][E][N+1] (last)
+    const void *tt_in;      // [B][n_in]   Low2Tops (E = 2) or GenTops (E = 4)
+    void *tt_out;           // [B][n_in/2]
     const double *mx_in;    // [B][n_in]
     double *mx_out;         // [B][n_in/2], zeroed before the level
     int *W;                 // [B]
@@ -38,24 +39,51 @@ struct UpArgs {
     TwSet tw;
 };
 
+// SYM = first-row-only NSE mode (2 stored entries, conj symmetry), !SYM = general 2x2
+template <bool SYM>
+struct UpT {
+    typedef Low2Tops Tops;
+    static constexpr int E = 2;
+};
+template <>
+struct UpT<false> {
+    typedef GenTops Tops;
+    static constexpr int E = 4;
+};
+DEV cplx up_top(const Low2Tops &T, int which) { return which ? T.tb : T.ta; }
+DEV cplx up_bot(const Low2Tops &T, int which) { return which ? T.bb : T.ba; }
+DEV cplx up_top(const GenTops &T, int which) { return T.t[which]; }
+DEV cplx up_bot(const GenTops &T, int which) { return T.b[which]; }
+DEV Low2Tops up_tops_product(const Low2Tops &A, const Low2Tops &B, double kap, double f)
+{
+    return low2_pair_tops(A, B, kap, f);
+}
+DEV GenTops up_tops_product(const GenTops &A, const GenTops &B, double, double f)
+{
+    return gen_tops_scaled(gen_pair_tops(A, B), f);
+}
+
+template <bool SYM>
 struct UpPair {
-    Low2Tops Tn;  // tops of the product (already scaled)
-    double sc;    // 2^-(eA+eB)
+    typename UpT<SYM>::Tops Tn;  // tops of the product (already scaled)
+    double sc;                   // 2^-(eA+eB)
 };
 
 // per-CTA prologue: scale of the pair, tops of the product; the `leader` CTA publishes them
-DEV UpPair up_pair_setup(const UpArgs &a, size_t sp, int s, bool leader)
+template <bool SYM>
+DEV UpPair<SYM> up_pair_setup(const UpArgs &a, size_t sp, int s, bool leader)
 {
-    UpPair r;
+    typedef typename UpT<SYM>::Tops Tops;
+    UpPair<SYM> r;
     const size_t mA = 2 * sp, mB = 2 * sp + 1;
     int e = 0;
     if (a.normalize)
         e = rescale_exponent(a.mx_in[mA]) + rescale_exponent(a.mx_in[mB]);
     r.sc = ldexp(1.0, -e);
-    const Low2Tops TA = a.tt_in[mA], TB = a.tt_in[mB];
-    r.Tn = low2_pair_tops(TA, TB, (double)a.kappa, r.sc);
+    const Tops TA = ((const Tops *)a.tt_in)[mA], TB = ((const Tops *)a.tt_in)[mB];
+    r.Tn = up_tops_product(TA, TB, (double)a.kappa, r.sc);
     if (leader && threadIdx.x == 0) {
-        a.tt_out[sp] = r.Tn;
+        ((Tops *)a.tt_out)[sp] = r.Tn;
         if (e != 0)
             atomicAdd(&a.W[s], e);
     }
@@ -107,21 +135,25 @@ DEV void up_p_pass(cplx *S, int n, int l2s, const TwSet &tw, int tid, int nt)
 // the global loads / stores (512 contiguous bytes per access) and park the product values in
 // shared memory; after a __syncwarp each lane takes its RX consecutive positions for the
 // stride-1 pass.
-template <int RX>
-DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n, double sg, const UpPair &P,
-                    cplx *S, int tid, int nt)
+template <int RX, bool SYM>
+DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n, double sg,
+                    const UpPair<SYM> &P, cplx *S, int tid, int nt)
 {
     constexpr int LR = Log2R<RX>::value;
+    constexpr int E = UpT<SYM>::E;
     const int N = 1 << a.l2n;
-    const cplx *aA = a.in + (4 * sp) * (size_t)N;
+    const cplx *mA = a.in + (2 * E * sp) * (size_t)N;  // matrix A, then matrix B
+    const cplx *mB = mA + (size_t)E * N;
+    // SYM:  which = 0: c = aA*aB + (-kap*sg*bA)*conj(bB);  which = 1: c = aA*bB + (sg*bA)*conj(aB)
+    // !SYM: c(row, col) = A(row,1)*B(1,col) + A(row,2)*B(2,col)
+    const cplx *aA = SYM ? mA : mA + (size_t)(2 * (which >> 1)) * N;
     const cplx *bA = aA + N;
-    const cplx *pz = aA + (which ? 3 : 2) * (size_t)N;  // which = 0: aB, 1: bB
-    const cplx *pw = aA + (which ? 2 : 3) * (size_t)N;  // which = 0: bB, 1: aB
-    cplx *ge = a.last ? nullptr : a.out + (2 * sp + which) * (size_t)(2 * N);
+    const cplx *pz = SYM ? mB + (which ? 1 : 0) * (size_t)N : mB + (size_t)(which & 1) * N;
+    const cplx *pw = SYM ? mB + (which ? 0 : 1) * (size_t)N : mB + (size_t)(2 + (which & 1)) * N;
+    cplx *ge = a.last ? nullptr : a.out + (E * sp + which) * (size_t)(2 * N);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const double sc = P.sc;
-    // which = 0: c = aA*aB + (-kap*sg*bA)*conj(bB);  which = 1: c = aA*bB + (sg*bA)*conj(aB)
-    const double f = which ? sg * sc : -(double)a.kappa * sg * sc;
+    const double f = SYM ? (which ? sg * sc : -(double)a.kappa * sg * sc) : sc;
 #pragma unroll 1
     for (int cb = warp * (32 * RX); cb < n; cb += nwarps * (32 * RX)) {
 #pragma unroll
@@ -139,7 +171,10 @@ DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n
             for (int i = 0; i < 4; ++i) {
                 const int loc = cb + 32 * (i0 + i) + lane;
                 cplx r = cmul(cscale(x[i], sc), z[i]);
-                cfmac(r, cscale(y[i], f), w[i]);
+                if (SYM)
+                    cfmac(r, cscale(y[i], f), w[i]);
+                else
+                    cfma(r, cscale(y[i], f), w[i]);
                 if (ge)
                     ge[p0 + loc] = r;
                 S[swz2(l0 + loc)] = r;
@@ -187,8 +222,9 @@ DEV void up_f_stage(cplx *S, int n, cplx ct, cplx *godd, int tid, int nt)
 
 // M stage (radix 16, stride N/16) on a whole length-N array in shared memory; `last` writes
 // the coefficients to gcoef instead of twisting and transforming forward.  Returns max|c|^2.
-DEV double up_m_stage(cplx *S, int l2n, const TwSet &tw, const UpPair &P, int which, bool last, cplx *gcoef,
-                      int tid, int nt)
+template <bool SYM>
+DEV double up_m_stage(cplx *S, int l2n, const TwSet &tw, const UpPair<SYM> &P, int which, bool last,
+                      cplx *gcoef, int tid, int nt)
 {
     constexpr int R = 16, LR = 4;
     const int l2s = l2n - LR;
@@ -212,7 +248,7 @@ DEV double up_m_stage(cplx *S, int l2n, const TwSet &tw, const UpPair &P, int wh
         for (int n = 0; n < R; ++n)
             v[n] = cscale(v[n], invN);
         if (o == 0)
-            v[0] = which ? P.Tn.bb : P.Tn.ba;
+            v[0] = up_bot(P.Tn, which);
 #pragma unroll
         for (int n = 0; n < R; ++n)
             m2 = fmax(m2, cabs2(v[n]));
@@ -221,7 +257,7 @@ DEV double up_m_stage(cplx *S, int l2n, const TwSet &tw, const UpPair &P, int wh
             for (int n = 0; n < R; ++n)
                 gcoef[o + (n << l2s)] = v[n];
             if (o == 0)
-                gcoef[N] = which ? P.Tn.tb : P.Tn.ta;
+                gcoef[N] = up_top(P.Tn, which);
             continue;
         }
 #pragma unroll
@@ -304,37 +340,38 @@ DEV void up_row_passes(cplx *S, const TwSet &tw, int tid, int nt)
 // ---------------------------------------------------------------------------------------
 // whole level in shared memory: grid.x = B * npairs * 2, blockDim.x = N / 32
 // ---------------------------------------------------------------------------------------
-template <int L2N>
+template <int L2N, bool SYM>
 __global__ void __launch_bounds__(1 << (L2N - 5), (L2N == 11) ? 6 : ((L2N == 12) ? 3 : 1)) k_up_smem(const UpArgs a)
 {
+    constexpr int E = UpT<SYM>::E;
     constexpr int N = 1 << L2N, NT = N / 32;
     constexpr int RX = (L2N == 12) ? 16 : 8;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
     double *red = (double *)(S + N);
     const int tid = threadIdx.x;
-    const int which = blockIdx.x & 1;
-    const size_t sp = blockIdx.x >> 1;
+    const int which = blockIdx.x % E;
+    const size_t sp = blockIdx.x / E;
     const int npairs = a.n_in >> 1;
     const int s = (int)(sp / npairs);
-    const UpPair P = up_pair_setup(a, sp, s, which == 0);
+    const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0);
 
     // X stage: the two half regions carry (-1)^k = +1 / -1
-    up_x_stage<RX>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
-    up_x_stage<RX>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
+    up_x_stage<RX, SYM>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
+    up_x_stage<RX, SYM>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
     __syncthreads();
     up_row_passes<+1, L2N, false>(S, a.tw, tid, NT);
-    cplx *gcoef = a.last ? a.out + (2 * sp + which) * (size_t)(N + 1) : nullptr;
-    const double m2 = up_m_stage(S, L2N, a.tw, P, which, a.last != 0, gcoef, tid, NT);
+    cplx *gcoef = a.last ? a.out + (E * sp + which) * (size_t)(N + 1) : nullptr;
+    const double m2 = up_m_stage<SYM>(S, L2N, a.tw, P, which, a.last != 0, gcoef, tid, NT);
     __syncthreads();
     if (!a.last) {
         up_row_passes<-1, L2N, false>(S, a.tw, tid, NT);
-        cplx *godd = a.out + (2 * sp + which) * (size_t)(2 * N) + N;
-        up_f_stage<RX>(S, N, which ? P.Tn.tb : P.Tn.ta, godd, tid, NT);
+        cplx *godd = a.out + (E * sp + which) * (size_t)(2 * N) + N;
+        up_f_stage<RX>(S, N, up_top(P.Tn, which), godd, tid, NT);
     }
     double mm = m2;
     if (tid == 0)
-        mm = fmax(mm, cabs2(which ? P.Tn.tb : P.Tn.ta));
+        mm = fmax(mm, cabs2(up_top(P.Tn, which)));
     up_publish_max(mm, red, &a.mx_out[sp], tid, NT);
 }
 
@@ -342,9 +379,10 @@ __global__ void __launch_bounds__(1 << (L2N - 5), (L2N == 11) ? 6 : ((L2N == 12)
 // row-split levels, N = R * N2
 // (a) grid.x = B * npairs * 2 * R: pointwise product + inverse passes inside row r
 // ---------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, bool SYM>
 __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
 {
+    constexpr int E = UpT<SYM>::E;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
     const int l2n = a.l2n, l2row = a.l2row, N2 = 1 << l2row;
@@ -352,14 +390,14 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
     const int tid = threadIdx.x;
     const int row = blockIdx.x & ((1 << l2R) - 1);
     const size_t arr = blockIdx.x >> l2R;
-    const int which = (int)(arr & 1);
-    const size_t sp = arr >> 1;
+    const int which = (int)(arr % E);
+    const size_t sp = arr / E;
     const int npairs = a.n_in >> 1;
     const int s = (int)(sp / npairs);
-    const UpPair P = up_pair_setup(a, sp, s, which == 0 && row == 0);
+    const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0 && row == 0);
     const double sg = (row >> (l2R - 1)) ? -1.0 : 1.0;
     // X stage over positions [row*N2, (row+1)*N2): local index = position - row*N2
-    up_x_stage<16>(a, sp, which, row << l2row, 0, N2, sg, P, S, tid, NT);
+    up_x_stage<16, SYM>(a, sp, which, row << l2row, 0, N2, sg, P, S, tid, NT);
     __syncthreads();
     up_row_passes<+1, FNFTB_UP_ROW_L2, true>(S, a.tw, tid, NT);
     cplx *dst = a.ws + arr * ((size_t)1 << l2n) + ((size_t)row << l2row);
@@ -369,9 +407,11 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
 
 // (cols) one thread per (array, o < N2): radix-R inverse pass across the rows, coefficient
 // fix-up and max, then twist + radix-R forward pass (or the coefficient output when last)
-template <int R>
+template <int R, bool SYM>
 __global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
 {
+    typedef typename UpT<SYM>::Tops Tops;
+    constexpr int E = UpT<SYM>::E;
     constexpr int LR = Log2R<R>::value;
     __shared__ double red[8];
     const int l2n = a.l2n, l2row = l2n - LR;
@@ -379,9 +419,9 @@ __global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int o = (int)(gid & ((1 << l2row) - 1));
     const size_t arr = (size_t)(gid >> l2row);  // a CTA stays inside one array (256 | N2)
-    const int which = (int)(arr & 1);
-    const size_t sp = arr >> 1;
-    const Low2Tops Tn = a.tt_out[sp];
+    const int which = (int)(arr % E);
+    const size_t sp = arr / E;
+    const Tops Tn = ((const Tops *)a.tt_out)[sp];
     cplx *w = a.ws + arr * (size_t)N;
     const cplx *pt = a.tw.base + a.tw.pass_off[l2n][LR];
     const cplx *tt = a.tw.base + a.tw.twist_off[l2n];
@@ -398,7 +438,7 @@ __global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
     for (int n = 0; n < R; ++n)
         v[n] = cscale(v[n], invN);
     if (o == 0)
-        v[0] = which ? Tn.bb : Tn.ba;
+        v[0] = up_bot(Tn, which);
     double m2 = 0.0;
 #pragma unroll
     for (int n = 0; n < R; ++n)
@@ -409,13 +449,13 @@ __global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
         for (int n = 0; n < R; ++n)
             gcoef[o + ((size_t)n << l2row)] = v[n];
         if (o == 0) {
-            const cplx ct = which ? Tn.tb : Tn.ta;
+            const cplx ct = up_top(Tn, which);
             gcoef[N] = ct;
             m2 = fmax(m2, cabs2(ct));
         }
     } else {
         if (o == 0)
-            m2 = fmax(m2, cabs2(which ? Tn.tb : Tn.ta));
+            m2 = fmax(m2, cabs2(up_top(Tn, which)));
 #pragma unroll
         for (int n = 0; n < R; ++n)
             v[n] = cmul(v[n], __ldg(&tt[o + (n << l2row)]));
@@ -431,9 +471,11 @@ __global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
 }
 
 // (c) grid.x = B * npairs * 2 * R: forward passes inside row `row` of the workspace, odd bins
-template <int NT>
+template <int NT, bool SYM>
 __global__ void __launch_bounds__(NT, 3) k_up_rows_c(const UpArgs a)
 {
+    typedef typename UpT<SYM>::Tops Tops;
+    constexpr int E = UpT<SYM>::E;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
     const int l2n = a.l2n, l2row = a.l2row, N2 = 1 << l2row;
@@ -441,16 +483,16 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_c(const UpArgs a)
     const int tid = threadIdx.x;
     const int row = blockIdx.x & ((1 << l2R) - 1);
     const size_t arr = blockIdx.x >> l2R;
-    const int which = (int)(arr & 1);
-    const size_t sp = arr >> 1;
-    const Low2Tops Tn = a.tt_out[sp];
+    const int which = (int)(arr % E);
+    const size_t sp = arr / E;
+    const Tops Tn = ((const Tops *)a.tt_out)[sp];
     const cplx *src = a.ws + arr * ((size_t)1 << l2n) + ((size_t)row << l2row);
     for (int i = tid; i < N2; i += NT)
         S[swz2(i)] = src[i];
     __syncthreads();
     up_row_passes<-1, FNFTB_UP_ROW_L2, true>(S, a.tw, tid, NT);
     cplx *godd = a.out + arr * ((size_t)2 << l2n) + ((size_t)1 << l2n) + ((size_t)row << l2row);
-    up_f_stage<16>(S, N2, which ? Tn.tb : Tn.ta, godd, tid, NT);
+    up_f_stage<16>(S, N2, up_top(Tn, which), godd, tid, NT);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -486,37 +528,44 @@ static inline bool up_supported(int l2n, int l2smem_max)
     return l2R >= 1 && l2R <= 4;
 }
 
-static inline int up_level(UpArgs a, int l2smem_max, cudaStream_t st)
+template <bool SYM>
+static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
 {
+    constexpr int E = UpT<SYM>::E;
     const int npairs = a.n_in / 2;
     const int N = 1 << a.l2n;
     cudaMemsetAsync(a.mx_out, 0, sizeof(double) * (size_t)a.B * npairs, st);
     static const char *names_s[3] = {"tree_up_smem_N2048", "tree_up_smem_N4096", "tree_up_smem_N8192"};
     if (a.l2n <= l2smem_max) {
-        const unsigned grid = (unsigned)a.B * (unsigned)npairs * 2u;
+        const unsigned grid = (unsigned)a.B * (unsigned)npairs * (unsigned)E;
         const size_t smem = sizeof(cplx) * N + 64 * sizeof(double);
         switch (a.l2n) {
-        case 11: return up_launch(k_up_smem<11>, a, grid, 64, smem, st, names_s[0]);
-        case 12: return up_launch(k_up_smem<12>, a, grid, 128, smem, st, names_s[1]);
-        default: return up_launch(k_up_smem<13>, a, grid, 256, smem, st, names_s[2]);
+        case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 64, smem, st, names_s[0]);
+        case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 128, smem, st, names_s[1]);
+        default: return up_launch(k_up_smem<13, SYM>, a, grid, 256, smem, st, names_s[2]);
         }
     }
     a.l2row = FNFTB_UP_ROW_L2;
     const int l2R = a.l2n - a.l2row;
-    const unsigned grid_rows = (unsigned)a.B * (unsigned)npairs * 2u << l2R;
+    const unsigned grid_rows = (unsigned)a.B * (unsigned)npairs * (unsigned)E << l2R;
     const size_t smem = sizeof(cplx) << a.l2row;
-    int rc = up_launch(k_up_rows_a<128>, a, grid_rows, 128, smem, st, "tree_up_rows_a");
+    int rc = up_launch(k_up_rows_a<128, SYM>, a, grid_rows, 128, smem, st, "tree_up_rows_a");
     if (rc)
         return rc;
-    const unsigned grid_cols = (unsigned)(((size_t)a.B * npairs * 2 << a.l2row) / 256);
+    const unsigned grid_cols = (unsigned)(((size_t)a.B * npairs * E << a.l2row) / 256);
     switch (l2R) {
-    case 1: rc = up_launch(k_up_cols<2>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    case 2: rc = up_launch(k_up_cols<4>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    case 3: rc = up_launch(k_up_cols<8>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    default: rc = up_launch(k_up_cols<16>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    case 1: rc = up_launch(k_up_cols<2, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    case 2: rc = up_launch(k_up_cols<4, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    case 3: rc = up_launch(k_up_cols<8, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    default: rc = up_launch(k_up_cols<16, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
     }
     if (rc || a.last)
         return rc;
-    return up_launch(k_up_rows_c<128>, a, grid_rows, 128, smem, st, "tree_up_rows_c");
+    return up_launch(k_up_rows_c<128, SYM>, a, grid_rows, 128, smem, st, "tree_up_rows_c");
+}
+
+static inline int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym = true)
+{
+    return sym ? up_level_t<true>(a, l2smem_max, st) : up_level_t<false>(a, l2smem_max, st);
 }
 #endif  // !FNFTB_EMUL

@@ -12,7 +12,7 @@
 #ifndef FNFTB_EMUL
 #include "common.cuh"
 
-#define FNFTB_TW_MINL 4
+#define FNFTB_TW_MINL 3
 #define FNFTB_TW_MAXL 16  // tables for lengths 2^4 .. 2^16
 
 struct TwSet {

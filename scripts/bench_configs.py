@@ -238,8 +238,25 @@ def main():
             o = F.kdvv_default_opts()
             o.discretization = F.KDV_4SPLIT4B
 
-            def run():
-                return F.kdvv_batch(U, T, M, XI, o)
+            # pinned host buffers (as a production caller would use) when torch is available
+            try:
+                import torch
+                Uh = torch.empty((B, U.shape[1]), dtype=torch.complex128, pin_memory=True)
+                Uh.copy_(torch.from_numpy(U))
+                csh = torch.empty((B, M), dtype=torch.complex128, pin_memory=True)
+                rch = np.zeros(B, dtype=np.int32)
+                Ta, XIa = np.array(T), np.array(XI)
+                Lb = F.lib()
+
+                def run():
+                    r = Lb.fnft_kdvv_batch(B, U.shape[1], Uh.data_ptr(), Ta.ctypes.data, M, csh.data_ptr(),
+                                           XIa.ctypes.data, C.addressof(o), rch.ctypes.data)
+                    return r, csh.numpy(), rch
+                line["host_buffers"] = "pinned"
+            except ImportError:
+                def run():
+                    return F.kdvv_batch(U, T, M, XI, o)
+                line["host_buffers"] = "pageable"
             run()
             dt, (ret, cs, rcs) = best_of(run, args.reps)
             line.update(workload="fnft_kdvv reflection coefficient, 4SPLIT4B, D=M=8192, B=%d" % B,

@@ -165,6 +165,30 @@ def test_spectrum_carry_tree_normalisation_and_kappa(F, kappa, normalize):
         assert rel_err(tm[e] * 2.0 ** W, tmo[e] * 2.0 ** Wo) < 1e-10, (kappa, normalize, e)
 
 
+def test_general_spectrum_carry_tree_kdv_and_explicit_r(F):
+    """tree_low2g / tree_up with E = 4 (general 2x2 case): KdV (real-arithmetic leaf),
+    explicit complex r (generic leaf), padded and power-of-two lengths, deg0 = 1 and 2"""
+    rng = np.random.default_rng(11)
+    for D in (1024, 3000, 8192):
+        T = (-12.0, 12.0)
+        t = np.linspace(T[0], T[1], D)
+        eps_t = (T[1] - T[0]) / (D - 1)
+        u = 2.1 / np.cosh(t - 0.3) ** 2 - 0.4 * np.exp(-((t + 3.0) / 0.8) ** 2)   # changes sign
+        for disc in (F.KDV_4SPLIT4B, F.KDV_2SPLIT2A):
+            ret, tm, deg, W = F.kdv_fscatter(u, eps_t, disc)
+            tmo, dego, Wo = O.kdv_fscatter(u, eps_t, disc)
+            assert ret == 0 and deg == dego
+            for e in range(4):
+                assert rel_err(tm[e] * 2.0 ** W, tmo[e] * 2.0 ** Wo) < 1e-10, ("kdv", D, disc, e)
+        q = sech_chirp(D, T, 1.7, 0.3)
+        r = -0.8 * np.conj(q) * np.exp(0.2j) + 0.05 * rng.normal(size=D)
+        ret, tm, deg, W = F.akns_fscatter(q, r, eps_t, 10)   # akns 2SPLIT4B
+        tmo, dego, Wo = O.akns_fscatter(q, r, eps_t, 10)
+        assert ret == 0 and deg == dego
+        for e in range(4):
+            assert rel_err(tm[e] * 2.0 ** W, tmo[e] * 2.0 ** Wo) < 1e-10, ("akns", D, e)
+
+
 def test_spectrum_carry_padded_lengths_and_modal_scheme(F):
     """non-power-of-two D (padding matrices diag(z^d, 1)) on the spectrum path, generic leaf
     (2SPLIT2_MODAL, out-of-line leaf call of tree_low2) and the deg0 = 1 build"""
