@@ -67,14 +67,11 @@ __global__ void __launch_bounds__(256) k_cz2_cols_fwd(const Cz2Args a)
     }
     Dft<R, -1>::run(v);
     const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][LR];
+    up_twiddle_mul<R, false>(v, pt, N2, o);
     cplx *dst = c.ybuf + arr * (size_t)L;
 #pragma unroll
-    for (int q = 0; q < R; ++q) {
-        cplx y = v[q];
-        if (q > 0)
-            y = cmul(y, __ldg(&pt[((q - 1) << FNFTB_CZ2_ROW_L2) + o]));
-        dst[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o] = y;
-    }
+    for (int q = 0; q < R; ++q)
+        dst[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o] = v[q];
 }
 
 // grid.x = narr * R rows, 128 threads, 64 KiB shared memory
@@ -97,9 +94,7 @@ __global__ void __launch_bounds__(128, 3) k_cz2_rows(const Cz2Args a)
         for (int n = 0; n < 16; ++n)
             v[n] = g[o + (n << 8)];
         Dft<16, -1>::run(v);
-#pragma unroll
-        for (int q = 1; q < 16; ++q)
-            v[q] = cmul(v[q], __ldg(&pt12[((q - 1) << 8) + o]));
+        up_twiddle_mul<16, false>(v, pt12, 256, o);
 #pragma unroll
         for (int q = 0; q < 16; ++q)
             S[swz2(o + (brev_c(q, 4) << 8))] = v[q];
@@ -143,9 +138,7 @@ __global__ void __launch_bounds__(128, 3) k_cz2_rows(const Cz2Args a)
 #pragma unroll
         for (int q = 0; q < 16; ++q)
             v[q] = S[swz2(o + (brev_c(q, 4) << 8))];
-#pragma unroll
-        for (int q = 1; q < 16; ++q)
-            v[q] = cmulc(v[q], __ldg(&pt12[((q - 1) << 8) + o]));
+        up_twiddle_mul<16, true>(v, pt12, 256, o);
         Dft<16, +1>::run(v);
 #pragma unroll
         for (int n = 0; n < 16; ++n)
@@ -173,12 +166,9 @@ __global__ void __launch_bounds__(256) k_cz2_cols_inv(const Cz2Args a)
         if (j < c.npoly) {
             const cplx *src = c.ybuf + (s * c.npoly + j) * (size_t)L;
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                cplx y = src[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o];
-                if (q > 0)
-                    y = cmulc(y, __ldg(&pt[((q - 1) << FNFTB_CZ2_ROW_L2) + o]));
-                H[j][q] = y;
-            }
+            for (int q = 0; q < R; ++q)
+                H[j][q] = src[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o];
+            up_twiddle_mul<R, true>(H[j], pt, N2, o);
             Dft<R, +1>::run(H[j]);
         } else {
 #pragma unroll

@@ -102,6 +102,82 @@ DEV void sym_prod(const cplx *a1, const cplx *b1, const cplx *a2, const cplx *b2
     }
 }
 
+// v[q] *= w^q (CONJ: conj(w)^q), q = 1 .. R-1, where w = tw[o] is the first row of the pass
+// table: the powers are derived in registers (squarings / products of depth <= 4, a few ulp)
+// instead of loading R-1 table rows.  ptxas serialises load -> use -> load under register
+// pressure, so every one of the 15 L2 latencies of a radix-16 butterfly was exposed
+// (long_scoreboard 40-58 % of the stalls, profiles/r01h_kernels_ncu.md); FP64 had headroom.
+#ifndef FNFTB_TW_DERIVE
+#define FNFTB_TW_DERIVE 1
+#endif
+DEV cplx csq(cplx a) { return make_cplx(a.x * a.x - a.y * a.y, 2.0 * a.x * a.y); }
+template <int R, bool CONJ>
+DEV void up_twiddle_mul(cplx *v, const cplx *pt, int stride, int o)
+{
+#if FNFTB_TW_DERIVE
+    cplx w1 = __ldg(&pt[o]);
+    if (CONJ)
+        w1 = cconj(w1);
+    v[1] = cmul(v[1], w1);
+    if constexpr (R > 2) {
+        const cplx w2 = csq(w1);
+        v[2] = cmul(v[2], w2);
+        const cplx w3 = cmul(w2, w1);
+        v[3] = cmul(v[3], w3);
+        if constexpr (R > 4) {
+            const cplx w4 = csq(w2);
+            v[4] = cmul(v[4], w4);
+            const cplx w5 = cmul(w4, w1);
+            v[5] = cmul(v[5], w5);
+            const cplx w6 = csq(w3);
+            v[6] = cmul(v[6], w6);
+            const cplx w7 = cmul(w4, w3);
+            v[7] = cmul(v[7], w7);
+            if constexpr (R > 8) {
+                const cplx w8 = csq(w4);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], csq(w5));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                v[12] = cmul(v[12], csq(w6));
+                v[13] = cmul(v[13], cmul(w8, w5));
+                v[14] = cmul(v[14], csq(w7));
+                v[15] = cmul(v[15], cmul(w8, w7));
+                static_assert(R <= 16, "radix");
+            }
+        }
+    }
+    (void)stride;
+#else
+    constexpr int BATCH = (R > 8) ? 8 : R - 1;
+#pragma unroll
+    for (int q0 = 1; q0 < R; q0 += BATCH) {
+        cplx w[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+            if (q0 + j < R)
+                w[j] = __ldg(&pt[(size_t)(q0 + j - 1) * stride + o]);
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+            if (q0 + j < R)
+                v[q0 + j] = CONJ ? cmulc(v[q0 + j], w[j]) : cmul(v[q0 + j], w[j]);
+    }
+#endif
+}
+
+// v[n] *= t0 * w_2R^n: the twist w_2N^(o + n*N/R) with t0 = w_2N^o loaded once
+template <int R, int N_>
+struct UpTwist {
+    DEV static void run(cplx *v, cplx t0)
+    {
+        if constexpr (N_ < R) {
+            v[N_] = cmul(mul_root<2 * R, N_, -1>(v[N_]), t0);
+            UpTwist<R, N_ + 1>::run(v, t0);
+        }
+    }
+};
+DEV void up_twist16(cplx *v, cplx t0) { UpTwist<16, 0>::run(v, t0); }
+
 // generic leaf (any scheme the leaf switch knows): kept out of line, it is large
 template <int DEG0>
 __device__ __noinline__ void low2_leaf_generic(int scheme, double eps_t, double qx, double qy, double kap,
@@ -365,9 +441,7 @@ DEV void low2_p_pass(cplx *S, const TwSet &tw, int t, int l2n, int sb)
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 v[q] = S[swz2(base + 4 * brev_c(q, LR))];
-#pragma unroll
-            for (int q = 1; q < R; ++q)
-                v[q] = cmulc(v[q], __ldg(&pt[(q - 1) * 4 + o]));
+            up_twiddle_mul<R, true>(v, pt, 4, o);
             Dft<R, +1>::run(v);
 #pragma unroll
             for (int n = 0; n < R; ++n)
@@ -377,9 +451,7 @@ DEV void low2_p_pass(cplx *S, const TwSet &tw, int t, int l2n, int sb)
             for (int n = 0; n < R; ++n)
                 v[n] = S[swz2(base + 4 * n)];
             Dft<R, -1>::run(v);
-#pragma unroll
-            for (int q = 1; q < R; ++q)
-                v[q] = cmul(v[q], __ldg(&pt[(q - 1) * 4 + o]));
+            up_twiddle_mul<R, false>(v, pt, 4, o);
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 S[swz2(base + 4 * brev_c(q, LR))] = v[q];
@@ -416,9 +488,7 @@ DEV double low2_m_stage(cplx *S, const TwSet &tw, const Low2Tops *TTn, int t, in
 #pragma unroll
         for (int q = 0; q < R; ++q)
             v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        up_twiddle_mul<R, true>(v, pt, s, o);
         Dft<R, +1>::run(v);
         // v[n] = N * c[o + n*s]
 #pragma unroll
@@ -431,13 +501,9 @@ DEV double low2_m_stage(cplx *S, const TwSet &tw, const Low2Tops *TTn, int t, in
             for (int n = 0; n < R; ++n)
                 m2 = fmax(m2, cabs2(v[n]));
         }
-#pragma unroll
-        for (int n = 0; n < R; ++n)
-            v[n] = cmul(v[n], __ldg(&tt[o + (n << l2s)]));
+        UpTwist<R, 0>::run(v, __ldg(&tt[o]));
         Dft<R, -1>::run(v);
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        up_twiddle_mul<R, false>(v, pt, s, o);
 #pragma unroll
         for (int q = 0; q < R; ++q)
             S[swz2(base + (brev_c(q, LR) << l2s))] = v[q];
@@ -489,9 +555,7 @@ DEV double low2_out_stage(const cplx *S, const TwSet &tw, const Low2Tops &Tn, in
 #pragma unroll
     for (int q = 0; q < R; ++q)
         v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
-#pragma unroll
-    for (int q = 1; q < R; ++q)
-        v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+    up_twiddle_mul<R, true>(v, pt, s, o);
     Dft<R, +1>::run(v);
     cplx *dst = out + (size_t)which * (N + 1);
     double m2 = 0.0;

@@ -313,9 +313,7 @@ DEV double low2g_m_stage(cplx *S, const TwSet &tw, const GenTops *TTn, int t, in
 #pragma unroll
         for (int q = 0; q < R; ++q)
             v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        up_twiddle_mul<R, true>(v, pt, s, o);
         Dft<R, +1>::run(v);
 #pragma unroll
         for (int n = 0; n < R; ++n)
@@ -327,13 +325,9 @@ DEV double low2g_m_stage(cplx *S, const TwSet &tw, const GenTops *TTn, int t, in
             for (int n = 0; n < R; ++n)
                 m2 = fmax(m2, cabs2(v[n]));
         }
-#pragma unroll
-        for (int n = 0; n < R; ++n)
-            v[n] = cmul(v[n], __ldg(&tt[o + (n << l2s)]));
+        UpTwist<R, 0>::run(v, __ldg(&tt[o]));
         Dft<R, -1>::run(v);
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        up_twiddle_mul<R, false>(v, pt, s, o);
 #pragma unroll
         for (int q = 0; q < R; ++q)
             S[swz2(base + (brev_c(q, LR) << l2s))] = v[q];
@@ -362,9 +356,7 @@ DEV double low2g_out_stage(const cplx *S, const TwSet &tw, const GenTops &Tn, in
 #pragma unroll
         for (int q = 0; q < R; ++q)
             v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        up_twiddle_mul<R, true>(v, pt, s, o);
         Dft<R, +1>::run(v);
         cplx *dst = out + (size_t)e * (N + 1);
 #pragma unroll

@@ -107,9 +107,7 @@ DEV void up_p_pass(cplx *S, int n, int l2s, const TwSet &tw, int tid, int nt)
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 v[q] = S[swz2(base + (brev_c(q, LR) << l2s))];
-#pragma unroll
-            for (int q = 1; q < R; ++q)
-                v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+            up_twiddle_mul<R, true>(v, pt, s, o);
             Dft<R, +1>::run(v);
 #pragma unroll
             for (int n2 = 0; n2 < R; ++n2)
@@ -119,9 +117,7 @@ DEV void up_p_pass(cplx *S, int n, int l2s, const TwSet &tw, int tid, int nt)
             for (int n2 = 0; n2 < R; ++n2)
                 v[n2] = S[swz2(base + (n2 << l2s))];
             Dft<R, -1>::run(v);
-#pragma unroll
-            for (int q = 1; q < R; ++q)
-                v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+            up_twiddle_mul<R, false>(v, pt, s, o);
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 S[swz2(base + (brev_c(q, LR) << l2s))] = v[q];
@@ -240,9 +236,7 @@ DEV double up_m_stage(cplx *S, int l2n, const TwSet &tw, const UpPair<SYM> &P, i
 #pragma unroll
         for (int q = 0; q < R; ++q)
             v[q] = S[swz2(o + (brev_c(q, LR) << l2s))];
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        up_twiddle_mul<R, true>(v, pt, s, o);
         Dft<R, +1>::run(v);
 #pragma unroll
         for (int n = 0; n < R; ++n)
@@ -260,13 +254,26 @@ DEV double up_m_stage(cplx *S, int l2n, const TwSet &tw, const UpPair<SYM> &P, i
                 gcoef[N] = up_top(P.Tn, which);
             continue;
         }
+#if FNFTB_TW_DERIVE
+        {
+            // twist w_2N^(o + n*s) = w_2N^o * w_2R^n: one load, the second factor is a constant
+            const cplx t0 = __ldg(&tt[o]);
+            up_twist16(v, t0);
+        }
+#else
 #pragma unroll
-        for (int n = 0; n < R; ++n)
-            v[n] = cmul(v[n], __ldg(&tt[o + (n << l2s)]));
+        for (int n0 = 0; n0 < R; n0 += 8) {
+            cplx w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                w[j] = __ldg(&tt[o + ((n0 + j) << l2s)]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[n0 + j] = cmul(v[n0 + j], w[j]);
+        }
+#endif
         Dft<R, -1>::run(v);
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2s) + o]));
+        up_twiddle_mul<R, false>(v, pt, s, o);
 #pragma unroll
         for (int q = 0; q < R; ++q)
             S[swz2(o + (brev_c(q, LR) << l2s))] = v[q];
@@ -430,9 +437,7 @@ __global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
 #pragma unroll
     for (int q = 0; q < R; ++q)
         v[q] = w[o + ((size_t)brev_c(q, LR) << l2row)];
-#pragma unroll
-    for (int q = 1; q < R; ++q)
-        v[q] = cmulc(v[q], __ldg(&pt[((q - 1) << l2row) + o]));
+    up_twiddle_mul<R, true>(v, pt, 1 << l2row, o);
     Dft<R, +1>::run(v);
 #pragma unroll
     for (int n = 0; n < R; ++n)
@@ -456,13 +461,9 @@ __global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
     } else {
         if (o == 0)
             m2 = fmax(m2, cabs2(up_top(Tn, which)));
-#pragma unroll
-        for (int n = 0; n < R; ++n)
-            v[n] = cmul(v[n], __ldg(&tt[o + (n << l2row)]));
+        UpTwist<R, 0>::run(v, __ldg(&tt[o]));
         Dft<R, -1>::run(v);
-#pragma unroll
-        for (int q = 1; q < R; ++q)
-            v[q] = cmul(v[q], __ldg(&pt[((q - 1) << l2row) + o]));
+        up_twiddle_mul<R, false>(v, pt, 1 << l2row, o);
 #pragma unroll
         for (int q = 0; q < R; ++q)
             w[o + ((size_t)brev_c(q, LR) << l2row)] = v[q];
