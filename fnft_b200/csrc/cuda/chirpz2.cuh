@@ -21,8 +21,18 @@
 
 #define FNFTB_CZ2_ROW_L2 12
 
+// first-row-only tree result as polynomial source (instead of the finalised transfer matrix):
+// level buffer layout of tree_kernels.cuh with E = 2, one matrix per signal of degree d_full
+struct Cz2SymSrc {
+    const cplx *lev;   // NULL: read c.tm
+    const double *mx;  // [B] max|coeff| -> pending power-of-two scale
+    int *W;            // [B] the exponent of that scale is added here (what blk_tree_final does)
+    int d_full, kappa, normalize;
+};
+
 struct Cz2Args {
     CzArgs c;     // polynomials, tables (tab_y, tab_out, tab_ph), epilogue description
+    Cz2SymSrc src;
     TwSet tw;
     cplx *vperm;  // [L] permuted FFT(v)
     int l2L;
@@ -42,7 +52,34 @@ __global__ void __launch_bounds__(256) k_cz2_cols_fwd(const Cz2Args a)
     const int Np = c.deg + 1;
     const int L = 1 << a.l2L;
     cplx v[R];
-    if (!a.gen_v) {
+    if (!a.gen_v && a.src.lev) {
+        // H11[deg-n] = scale * a[deg-n];  H21[deg-n] = -kappa * scale * conj(b[shift + n])
+        // (blk_tree_final: T21 = -kappa * T12#, second column shifted by the padding)
+        const int j = (int)(arr & 1);
+        const size_t s = arr >> 1;
+        int ex = 0;
+        double scale = 1.0;
+        if (a.src.normalize) {
+            ex = rescale_exponent(a.src.mx[s]);
+            scale = ldexp(1.0, -ex);
+        }
+        if (j == 0 && o == 0 && ex != 0)
+            a.src.W[s] += ex;  // this signal's tree kernels have all finished
+        const cplx *pl = a.src.lev + (s * 2 + j) * (size_t)(a.src.d_full + 1);
+        const int shift = a.src.d_full - c.deg;
+        const double f = j ? -(double)a.src.kappa * scale : scale;
+#pragma unroll
+        for (int n1 = 0; n1 < R; ++n1) {
+            const int n = o + n1 * N2;
+            if (n < Np) {
+                cplx x = j ? pl[shift + n] : pl[c.deg - n];
+                x = make_cplx(x.x * f, j ? -x.y * f : x.y * f);
+                v[n1] = cmul(x, __ldg(&c.tab_y[n]));
+            } else {
+                v[n1] = czero();
+            }
+        }
+    } else if (!a.gen_v) {
         const int j = (int)(arr % c.npoly);
         const size_t s = arr / c.npoly;
         const cplx *p = c.tm + s * c.tm_sstride + (size_t)c.ent[j] * Np;
@@ -250,7 +287,8 @@ static inline bool cz2_supported(int deg, int M)
 }
 
 // Same contract as cz_run (chirpz_driver.cuh); a.vhat doubles as the permuted FFT(v).
-static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st)
+static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st,
+                          const Cz2SymSrc *src = nullptr)
 {
     size_t need = (size_t)c.deg + (size_t)c.M, L = 1;
     int l2L = 0;
@@ -280,6 +318,9 @@ static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t 
     }
     Cz2Args a;
     a.c = c;
+    memset(&a.src, 0, sizeof(a.src));
+    if (src)
+        a.src = *src;
     a.tw = tw;
     a.vperm = c.vhat;
     a.l2L = l2L;

@@ -135,6 +135,7 @@ struct fnftb_ctx {
     // tree workspace
     Buf lev0, lev1, mx0, mx1, gbuf, colbuf, W, status, tm, tt0, tt1, twmem;
     TwSet tws;
+    TreeDeferred deferred = {0, 0, 0, 0, 0, 0, 0, 0};  // pending blk_tree_final (see ctx_finalize)
     // result description
     size_t deg = 0;        // degree of the transfer matrices held in tm
     size_t tmB = 0;        // number of matrices held
@@ -479,6 +480,18 @@ static TreeWork tree_work(fnftb_ctx *c)
     return w;
 }
 
+// runs the deferred blk_tree_final, for consumers that need the full transfer matrix
+static int ctx_finalize(fnftb_ctx *c)
+{
+    if (!c->deferred.valid)
+        return 0;
+    const TreeDeferred &f = c->deferred;
+    RC(tree_finalize(tree_work(c), f.cur, f.B, f.d_full, f.deg_out, f.normalize, (cplx *)c->tm.p, c->st,
+                     f.sym, f.kappa));
+    c->deferred.valid = 0;
+    return 0;
+}
+
 int fnftb_fscatter(fnftb_ctx *c, const fnftb_scatter_desc *d)
 {
     if (!c || !d || !c->q)
@@ -494,8 +507,12 @@ int fnftb_fscatter(fnftb_ctx *c, const fnftb_scatter_desc *d)
         return fail(-6, "signal too long for this build", __FILE__, __LINE__);
     RC(ensure_tree(c, c->B, npad, (size_t)d->deg0, deg_out));
     const TwTable T = ctx_tw(c);
+    static const int knob_defer = tree_knob("FNFT_B200_DEFER_FINAL", 1);
     RC(tree_fscatter(tree_work(c), c->q, c->r, (int)c->B, (int)c->D, d->deg0, d->rmode, d->kappa,
-                     d->scheme, d->eps_t, d->normalize, (cplx *)c->tm.p, T, c->st));
+                     d->scheme, d->eps_t, d->normalize, (cplx *)c->tm.p, T, c->st, 1, FNFTB_TREE_SMEM_N,
+                     (knob_defer && d->defer_final) ? &c->deferred : nullptr));
+    if (!(knob_defer && d->defer_final))
+        c->deferred.valid = 0;
     c->deg = deg_out;
     c->tmB = c->B;
     c->tm_entries = 4;
@@ -517,6 +534,7 @@ int fnftb_fmult2x2(fnftb_ctx *c, size_t deg, size_t n, const void *p_host, int n
     const TwTable T = ctx_tw(c);
     RC(tree_fmult2x2(tree_work(c), (const cplx *)c->pbuf.p, (int)n, (int)deg, normalize,
                      (cplx *)c->tm.p, T, c->st));
+    c->deferred.valid = 0;
     c->deg = deg * n;
     c->tmB = 1;
     c->tm_entries = 4;
@@ -530,6 +548,7 @@ int fnftb_get_transfer_matrix(fnftb_ctx *c, void *tm_host, int32_t *W_host)
     if (!c || c->tmB == 0)
         return fail(-2, "no result held", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
+    RC(ctx_finalize(c));
     if (tm_host)
         CU(cudaMemcpyAsync(tm_host, c->tm.p, c->tmB * c->tm_entries * (c->deg + 1) * sizeof(cplx),
                            cudaMemcpyDeviceToHost, c->st));
@@ -561,6 +580,7 @@ int fnftb_set_polynomial(fnftb_ctx *c, size_t deg, const void *p_host)
     CU(cudaMemcpyAsync(c->tm.p, p_host, (deg + 1) * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
     CU(cudaMemsetAsync(c->W.p, 0, sizeof(int), c->st));
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->st));
+    c->deferred.valid = 0;
     c->deg = deg;
     c->tmB = 1;
     c->tm_entries = 1;
@@ -636,8 +656,27 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
     a.status = (int *)c->status.p;
     {
         static const int knob_cz2 = tree_knob("FNFT_B200_CZ2", 1);
-        if (knob_cz2 && cz2_supported((int)c->deg, (int)d->M))
-            RC(cz2_run(a, (cplx *)c->cztab.p, c->tws, c->st));
+        const bool fast = knob_cz2 && cz2_supported((int)c->deg, (int)d->M);
+        Cz2SymSrc src;
+        memset(&src, 0, sizeof(src));
+        if (c->deferred.valid) {
+            const TreeDeferred &f = c->deferred;
+            if (fast && f.sym && d->mode == FNFTB_MODE_NSEV && d->npoly == 2 && d->ent[0] == 0 && d->ent[1] == 2) {
+                // polynomials straight from the level buffer: H11 = a, H21 = -kappa * b#
+                const TreeWork w = tree_work(c);
+                src.lev = w.lev[f.cur];
+                src.mx = w.mx[f.cur];
+                src.W = (int *)c->W.p;
+                src.d_full = f.d_full;
+                src.kappa = f.kappa;
+                src.normalize = f.normalize;
+                c->deferred.valid = 0;  // the exponent of the last matrix is added to W by the kernel
+            } else {
+                RC(ctx_finalize(c));
+            }
+        }
+        if (fast)
+            RC(cz2_run(a, (cplx *)c->cztab.p, c->tws, c->st, src.lev ? &src : nullptr));
         else
             RC(cz_run(a, (cplx *)c->cztab.p, c->st));
     }
@@ -742,6 +781,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
     if (!c || !d || c->tmB == 0 || c->tm_entries != 4)
         return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
+    RC(ctx_finalize(c));
     const size_t B = c->tmB, deg = c->deg, d1 = deg + 1;
     if (deg < 2)
         return fail(-2, "degree too small", __FILE__, __LINE__);

@@ -36,6 +36,8 @@ typedef struct {
     int deg0;       /* polynomial degree of one step */
     int normalize;  /* 1: power-of-two rescaling with exponent W */
     double eps_t;   /* step size entering the leaves */
+    int defer_final; /* 1: the caller only wants fnftb_contspec next; the [B][4][deg+1] transfer
+                      * matrix is then built lazily (or never, on the chirp-z fast path) */
 } fnftb_scatter_desc;
 
 typedef struct {

@@ -303,6 +303,15 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
     return 0;
 }
 
+// What blk_tree_final would consume: lets a caller that only needs the continuous spectrum of
+// the first-row-only (NSE) mode skip the [B][4][deg+1] transfer matrix altogether -- the
+// chirp-z fast path reads (a, b) from the level buffer directly (chirpz2.cuh, sym source).
+struct TreeDeferred {
+    int valid;          // 1: finalisation pending, fields below describe it
+    int cur;            // level buffer holding the single matrix per signal
+    int B, d_full, deg_out, normalize, sym, kappa;
+};
+
 static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, int deg_out,
                                 int normalize, cplx *tm, fnftb_stream_t st, int sym = 0, int kappa = 0)
 {
@@ -326,9 +335,12 @@ static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, i
 static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r, int B, int D,
                                 int deg0, int rmode, int kappa, int scheme, double eps_t,
                                 int normalize, cplx *tm, const TwTable &T, fnftb_stream_t st,
-                                int use_direct = 1, int smem_n = FNFTB_TREE_SMEM_N)
+                                int use_direct = 1, int smem_n = FNFTB_TREE_SMEM_N,
+                                TreeDeferred *defer = nullptr)
 {
     const int npad = (int)next_pow2_sz((size_t)D);
+    if (defer)
+        defer->valid = 0;
     dev_memset0(w.W, sizeof(int) * (size_t)B, st);
     dev_memset0(w.status, sizeof(int) * (size_t)B, st);
     // first-row-only mode: NSE structure, and every level must be a wrap level
@@ -406,6 +418,17 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
                     if (rc)
                         return rc;
                     cur = 1 - cur;
+                }
+                if (defer) {  // first-row-only result stays in the level buffer
+                    defer->valid = 1;
+                    defer->cur = cur;
+                    defer->B = B;
+                    defer->d_full = deg0 * npad;
+                    defer->deg_out = deg0 * D;
+                    defer->normalize = normalize;
+                    defer->sym = sym;
+                    defer->kappa = kappa;
+                    return 0;
                 }
                 return tree_finalize(w, cur, B, deg0 * npad, deg0 * D, normalize, tm, st, sym, kappa);
             }

@@ -190,6 +190,7 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     sd.deg0 = (int)deg0;
     sd.normalize = opts->normalization_flag ? 1 : 0;
     sd.eps_t = eps_t;
+    sd.defer_final = 1; /* only fnftb_contspec consumes the scattering result here */
 
     if (piped && fnftb_pipeline_begin(ctx) != 0) {
         ret_code = E_DEVICE;
