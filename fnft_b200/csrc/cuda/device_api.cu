@@ -375,10 +375,11 @@ int fnftb_pipeline_end(fnftb_ctx *c)
 static size_t per_signal_bytes(size_t D, int deg0, size_t M, int npoly)
 {
     const size_t npad = next_pow2_sz(D);
+    const size_t dtree = deg0 <= 2 ? (size_t)deg0 : next_pow2_sz((size_t)deg0);  // tree_leaf_degree
     size_t b = 0;
-    b += 2 * tree_lev_elems(1, npad, (size_t)deg0) * sizeof(cplx);
+    b += 2 * tree_lev_elems(1, npad, dtree) * sizeof(cplx);
     b += 2 * npad * sizeof(double);
-    b += 2 * tree_gbuf_elems(1, npad, (size_t)deg0) * sizeof(cplx);
+    b += 2 * tree_gbuf_elems(1, npad, dtree) * sizeof(cplx);
     b += 4 * ((size_t)deg0 * D + 1) * sizeof(cplx);
     if (M > 0) {
         const CzGeom g = cz_geometry((int)((size_t)deg0 * D), (int)M);
@@ -498,14 +499,16 @@ int fnftb_fscatter(fnftb_ctx *c, const fnftb_scatter_desc *d)
         return fail(-2, "invalid argument / no signals staged", __FILE__, __LINE__);
     if (d->rmode == FNFTB_RMODE_EXPLICIT && !c->r)
         return fail(-2, "explicit r requested but not staged", __FILE__, __LINE__);
-    if (d->deg0 < 1 || d->deg0 > 2)
+    if (d->deg0 < 1 || d->deg0 > 105)
         return fail(-5, "discretization not implemented on the GPU path", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
     const size_t npad = next_pow2_sz(c->D);
     const size_t deg_out = (size_t)d->deg0 * c->D;
-    if ((size_t)d->deg0 * npad > ((size_t)1 << 22))
+    const size_t dtree = (size_t)tree_leaf_degree(d->scheme, d->deg0);
+    // longest pair product: cyclic length dtree*npad <= 2^16 rows of <= 64 * 1024 (tree_driver.cuh)
+    if ((d->deg0 <= 2) ? ((size_t)d->deg0 * npad > ((size_t)1 << 22)) : (dtree * npad > ((size_t)1 << 16)))
         return fail(-6, "signal too long for this build", __FILE__, __LINE__);
-    RC(ensure_tree(c, c->B, npad, (size_t)d->deg0, deg_out));
+    RC(ensure_tree(c, c->B, npad, dtree, deg_out));
     const TwTable T = ctx_tw(c);
     static const int knob_defer = tree_knob("FNFT_B200_DEFER_FINAL", 1);
     RC(tree_fscatter(tree_work(c), c->q, c->r, (int)c->B, (int)c->D, d->deg0, d->rmode, d->kappa,

@@ -4,6 +4,7 @@
 #pragma once
 #include "launch.cuh"
 #include "tree_kernels.cuh"
+#include "leaf_chain.cuh"
 #include "tree_low_kernel.cuh"
 #include "tree_low2.cuh"
 #include "tree_up.cuh"
@@ -331,6 +332,14 @@ static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, i
                                                     "tree_final");
 }
 
+// Degree the level-0 matrices are stored with (> deg0 for the chain schemes of
+// leaf_chain.cuh, whose leaves are padded to a power-of-two degree); workspaces are sized by it.
+static inline int tree_leaf_degree(int scheme, int deg0)
+{
+    ChainScheme cs;
+    return chain_scheme_for(scheme, &cs) ? chain_padded_degree(deg0) : deg0;
+}
+
 // Full fast scattering for a batch: leaves -> tree -> [B][4][deg_out+1] + W[B].
 static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r, int B, int D,
                                 int deg0, int rmode, int kappa, int scheme, double eps_t,
@@ -352,6 +361,7 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
     static const int max_radix_low = tree_knob("FNFT_B200_MAX_RADIX", 16);
     int rc;
     int n_start = npad, d_start = deg0;
+    const int dtree = tree_leaf_degree(scheme, deg0);
 #ifndef FNFTB_EMUL
     // spectrum-carry path (tree_low2.cuh + tree_up.cuh): first-row-only mode; the low kernel
     // handles M*8/deg0 samples per CTA, the upper levels stay in "values at the roots of
@@ -564,8 +574,20 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
         la.eps_t = eps_t;
         la.status = w.status;
         const long long total = (long long)B * npad;
-        rc = launch_blocks<LeafArgs, blk_leaf>(la, (unsigned)((total + 127) / 128), 128, 0, st,
-                                               "tree_leaf");
+        LeafChainArgs ca;
+        if (chain_scheme_for(scheme, &ca.cs)) {
+            // higher-order splittings (degree >= 3): generated from their chains, stored with
+            // a power-of-two degree (leaf_chain.cuh)
+            if (ca.cs.deg != deg0)
+                return -78;
+            ca.la = la;
+            ca.dpad = dtree;
+            d_start = dtree;
+            rc = launch_blocks<LeafChainArgs, blk_leaf_chain>(ca, (unsigned)((total + 127) / 128), 128,
+                                                              0, st, "tree_leaf_chain");
+        } else
+            rc = launch_blocks<LeafArgs, blk_leaf>(la, (unsigned)((total + 127) / 128), 128, 0, st,
+                                                   "tree_leaf");
         if (rc)
             return rc;
     }
@@ -573,7 +595,7 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
     rc = tree_levels(w, B, n_start, d_start, normalize, T, st, &cur, use_direct, smem_n, sym, kappa);
     if (rc)
         return rc;
-    return tree_finalize(w, cur, B, deg0 * npad, deg0 * D, normalize, tm, st, sym, kappa);
+    return tree_finalize(w, cur, B, dtree * npad, deg0 * D, normalize, tm, st, sym, kappa);
 }
 
 // Product of n given matrices (one "signal"), reference layout in and out.

@@ -193,6 +193,25 @@ HD void leaf_matrix(cplx *p /*[4][deg0+1]*/, int scheme, int deg0, double eps_t,
         p22[1] = Z;
         break;
     }
+    case FNFTB_AKNS_2SPLIT3S: {  // :331-360 (Burstein-Mirin; see leaf_chain.cuh for the chains)
+        cplx a[3], b[3];
+        zero_freq_expm(a, eps_t / deg0, q, r);
+        zero_freq_expm(b, 2.0 * eps_t / deg0, q, r);
+        const double third = 1.0 / 3.0, sixth = 1.0 / 6.0;
+        p11[0] = cscale(cscale(cmul(a[1], a[2]), 2.0), third);
+        p11[1] = Z;
+        p11[2] = cscale(cadd(cscale(cmul(a[0], a[0]), 2.0), b[0]), third);
+        p12[0] = cscale(csub(cscale(cmul(a[0], a[1]), 4.0), b[1]), sixth);
+        p12[1] = cscale(cscale(b[1], 2.0), third);
+        p12[2] = p12[0];
+        p21[0] = cscale(csub(cscale(cmul(a[0], a[2]), 4.0), b[2]), sixth);
+        p21[1] = cscale(cscale(b[2], 2.0), third);
+        p21[2] = p21[0];
+        p22[0] = p11[2];
+        p22[1] = Z;
+        p22[2] = p11[0];
+        break;
+    }
     case FNFTB_AKNS_2SPLIT4B:
     case FNFTB_AKNS_4SPLIT4B: {  // :402-433
         cplx a[3], b[3];

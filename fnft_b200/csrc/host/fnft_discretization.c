@@ -23,21 +23,21 @@ static const struct {
     /* 2SPLIT2A */ {1, 1, 2, 1},
     /* 2SPLIT2B */ {1, 1, 2, 1},
     /* 2SPLIT2S */ {1, 1, 2, 1},
-    /* 2SPLIT3A */ {3, 1, 2, 0},
-    /* 2SPLIT3B */ {3, 1, 2, 0},
-    /* 2SPLIT3S */ {2, 1, 2, 0},
-    /* 2SPLIT4A */ {4, 1, 2, 0},
+    /* 2SPLIT3A */ {3, 1, 2, 1},
+    /* 2SPLIT3B */ {3, 1, 2, 1},
+    /* 2SPLIT3S */ {2, 1, 2, 1},
+    /* 2SPLIT4A */ {4, 1, 2, 1},
     /* 2SPLIT4B */ {2, 1, 2, 1},
-    /* 2SPLIT5A */ {15, 1, 2, 0},
-    /* 2SPLIT5B */ {15, 1, 2, 0},
-    /* 2SPLIT6A */ {12, 1, 2, 0},
-    /* 2SPLIT6B */ {6, 1, 2, 0},
-    /* 2SPLIT7A */ {105, 1, 2, 0},
-    /* 2SPLIT7B */ {105, 1, 2, 0},
-    /* 2SPLIT8A */ {24, 1, 2, 0},
-    /* 2SPLIT8B */ {12, 1, 2, 0},
+    /* 2SPLIT5A */ {15, 1, 2, 1},
+    /* 2SPLIT5B */ {15, 1, 2, 1},
+    /* 2SPLIT6A */ {12, 1, 2, 1},
+    /* 2SPLIT6B */ {6, 1, 2, 1},
+    /* 2SPLIT7A */ {105, 1, 2, 1},
+    /* 2SPLIT7B */ {105, 1, 2, 1},
+    /* 2SPLIT8A */ {24, 1, 2, 1},
+    /* 2SPLIT8B */ {12, 1, 2, 1},
     /* BO */ {0, 1, 2, 0},
-    /* 4SPLIT4A */ {4, 2, 4, 0},
+    /* 4SPLIT4A */ {4, 2, 4, 1},
     /* 4SPLIT4B */ {2, 2, 4, 1},
     /* CF4_2 */ {0, 2, 4, 0},
     /* CF4_3 */ {0, 3, 4, 0},

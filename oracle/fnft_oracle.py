@@ -22,8 +22,35 @@ EPS = np.finfo(np.float64).eps
 
 # values of fnft__akns_discretization_t (include/private/fnft__akns_discretization_t.h:43-72)
 AKNS_2SPLIT2_MODAL, AKNS_2SPLIT1A, AKNS_2SPLIT1B, AKNS_2SPLIT2A, AKNS_2SPLIT2B, AKNS_2SPLIT2S = range(6)
-AKNS_2SPLIT4B = 10
+AKNS_2SPLIT3A, AKNS_2SPLIT3B, AKNS_2SPLIT3S, AKNS_2SPLIT4A, AKNS_2SPLIT4B = 6, 7, 8, 9, 10
+AKNS_2SPLIT5A, AKNS_2SPLIT5B, AKNS_2SPLIT6A, AKNS_2SPLIT6B = 11, 12, 13, 14
+AKNS_2SPLIT7A, AKNS_2SPLIT7B, AKNS_2SPLIT8A, AKNS_2SPLIT8B = 15, 16, 17, 18
+AKNS_4SPLIT4A = 20
 AKNS_4SPLIT4B = 21
+
+# Higher-order splittings as weighted sums of chains (the MATLAB recipes quoted in
+# test/fnft__akns_fscatter/fnft__akns_fscatter_test_2split{3A..8B}.c, e.g. _2split6B.c:47-49;
+# src/private/fnft__akns_fscatter.c:256-400,435-912 spells the same sums out per coefficient).
+# Entry: scheme -> (degree, [(weight, m, leftmost)]) where the chain has m+1 alternating
+# factors exp(A.), exp(B.) of sizes 1,2,...,2,1 (in units of eps_t/m), leftmost 'A' or 'B'.
+def _richardson(ms):
+    return [np.prod([mk * mk / (mk * mk - mj * mj) for mj in ms if mj != mk]) for mk in ms]
+
+
+def _chain_scheme(order, left, deg):
+    ms = list(range(1, order + 1, 2)) if order % 2 else list(range(2, order + 1, 2))
+    return deg, [(c, m, left) for c, m in zip(_richardson(ms), ms)]
+
+
+_CHAINS = {
+    AKNS_2SPLIT3A: _chain_scheme(3, 'A', 3), AKNS_2SPLIT3B: _chain_scheme(3, 'B', 3),
+    AKNS_2SPLIT3S: (2, [(2 / 3, 2, 'A'), (2 / 3, 2, 'B'), (-1 / 6, 1, 'A'), (-1 / 6, 1, 'B')]),
+    AKNS_2SPLIT4A: _chain_scheme(4, 'A', 4), AKNS_4SPLIT4A: _chain_scheme(4, 'A', 4),
+    AKNS_2SPLIT5A: _chain_scheme(5, 'A', 15), AKNS_2SPLIT5B: _chain_scheme(5, 'B', 15),
+    AKNS_2SPLIT6A: _chain_scheme(6, 'A', 12), AKNS_2SPLIT6B: _chain_scheme(6, 'B', 6),
+    AKNS_2SPLIT7A: _chain_scheme(7, 'A', 105), AKNS_2SPLIT7B: _chain_scheme(7, 'B', 105),
+    AKNS_2SPLIT8A: _chain_scheme(8, 'A', 24), AKNS_2SPLIT8B: _chain_scheme(8, 'B', 12),
+}
 # values of fnft_nse_discretization_t (include/fnft_nse_discretization_t.h:104-133)
 NSE_2SPLIT2_MODAL, NSE_BO, NSE_2SPLIT1A, NSE_2SPLIT1B, NSE_2SPLIT2A, NSE_2SPLIT2B, NSE_2SPLIT2S = range(7)
 NSE_2SPLIT4B = 11
@@ -34,22 +61,25 @@ KDV_2SPLIT1A, KDV_2SPLIT1B, KDV_2SPLIT2A, KDV_2SPLIT2B, KDV_2SPLIT2S = range(5)
 KDV_2SPLIT4B = 9
 KDV_4SPLIT4B = 19
 
-_NSE2AKNS = {NSE_2SPLIT2_MODAL: AKNS_2SPLIT2_MODAL, NSE_2SPLIT1A: AKNS_2SPLIT1A,
-             NSE_2SPLIT1B: AKNS_2SPLIT1B, NSE_2SPLIT2A: AKNS_2SPLIT2A, NSE_2SPLIT2B: AKNS_2SPLIT2B,
-             NSE_2SPLIT2S: AKNS_2SPLIT2S, NSE_2SPLIT4B: AKNS_2SPLIT4B, NSE_4SPLIT4B: AKNS_4SPLIT4B}
-_KDV2AKNS = {KDV_2SPLIT1A: AKNS_2SPLIT1A, KDV_2SPLIT1B: AKNS_2SPLIT1B, KDV_2SPLIT2A: AKNS_2SPLIT2A,
-             KDV_2SPLIT2B: AKNS_2SPLIT2B, KDV_2SPLIT2S: AKNS_2SPLIT2S, KDV_2SPLIT4B: AKNS_2SPLIT4B,
-             KDV_4SPLIT4B: AKNS_4SPLIT4B}
+# enum -> akns scheme (src/private/fnft__nse_discretization.c:109-202,
+# src/private/fnft__kdv_discretization.c:98-193): the polynomial schemes keep their order
+_NSE2AKNS = {NSE_2SPLIT2_MODAL: AKNS_2SPLIT2_MODAL}
+_NSE2AKNS.update({2 + i: 1 + i for i in range(18)})        # 2SPLIT1A .. 2SPLIT8B
+_NSE2AKNS.update({20: AKNS_4SPLIT4A, NSE_4SPLIT4B: AKNS_4SPLIT4B})
+_KDV2AKNS = {i: 1 + i for i in range(18)}                  # 2SPLIT1A .. 2SPLIT8B
+_KDV2AKNS.update({18: AKNS_4SPLIT4A, KDV_4SPLIT4B: AKNS_4SPLIT4B})
 
 
 def akns_degree(scheme):
     """src/private/fnft__akns_discretization.c:29-67 (schemes restated here)."""
+    if scheme in _CHAINS:
+        return _CHAINS[scheme][0]
     return 2 if scheme in (AKNS_2SPLIT4B, AKNS_4SPLIT4B) else 1
 
 
 def akns_upsampling(scheme):
     """src/private/fnft__akns_discretization.c:114-154."""
-    return 2 if scheme == AKNS_4SPLIT4B else 1
+    return 2 if scheme in (AKNS_4SPLIT4A, AKNS_4SPLIT4B) else 1
 
 
 def next_fast_size(n):
@@ -144,9 +174,41 @@ def akns_leaves(q, r, eps_t, scheme):
         p[3, :, 0] = p[0, :, 2]
         p[3, :, 1] = p[0, :, 1]
         p[3, :, 2] = p[0, :, 0]
+    elif scheme in _CHAINS:
+        for c, m, left in _CHAINS[scheme][1]:
+            p += c * _chain_polys(q, r, eps_t, deg, m, left)
     else:
         raise ValueError("scheme not restated in the oracle")
     return p
+
+
+def _chain_polys(q, r, eps_t, deg, m, left):
+    """One chain as a 2x2 matrix of polynomials in z (dense polynomial products, highest power
+    first): exp(A f eps_t) = diag(1, z^(f deg)) up to a scalar, exp(B f eps_t) from
+    zero_freq_expm (src/private/fnft__akns_fscatter.c:46-59)."""
+    D = q.shape[0]
+    # P[i][j]: coefficient arrays [D, deg+1] in ASCENDING powers while multiplying
+    P = [[np.zeros((D, deg + 1), dtype=np.complex128) for _ in range(2)] for _ in range(2)]
+    P[0][0][:, 0] = 1.0
+    P[1][1][:, 0] = 1.0
+    for i in range(m + 1):
+        size = 1 if i in (0, m) else 2
+        is_a = (i % 2 == 0) == (left == 'A')
+        if is_a:  # right-multiply by diag(1, z^k): shifts column 1
+            k = size * deg // m
+            assert size * deg % m == 0
+            for row in range(2):
+                P[row][1] = np.concatenate([np.zeros((D, k), dtype=np.complex128), P[row][1][:, :deg + 1 - k]], axis=1)
+        else:
+            c, sq, sr = zero_freq_expm(size * eps_t / m, q, r)
+            E = [[c, sq], [sr, c]]
+            P = [[P[row][0] * E[0][col][:, None] + P[row][1] * E[1][col][:, None] for col in range(2)]
+                 for row in range(2)]
+    out = np.empty((4, D, deg + 1), dtype=np.complex128)
+    for row in range(2):
+        for col in range(2):
+            out[2 * row + col] = P[row][col][:, ::-1]
+    return out
 
 
 def poly_fmult2x2(p, normalize=True):
@@ -243,7 +305,7 @@ def preprocess_signal(q, eps_t, kappa, nse_disc):
     """nse_discretization_preprocess_signal without subsampling,
     src/private/fnft__nse_discretization.c:386-656 (:467-473 copy, :474-503 4SPLIT4)."""
     q = np.asarray(q, dtype=np.complex128)
-    if nse_disc in (NSE_4SPLIT4B, NSE_CF4_2):
+    if nse_disc in (20, NSE_4SPLIT4B, NSE_CF4_2):   # 4SPLIT4A, 4SPLIT4B, CF4_2
         s = np.sqrt(3.0) / 6.0
         q1 = resample(q, eps_t, -eps_t * s)
         q2 = resample(q, eps_t, +eps_t * s)
@@ -255,10 +317,13 @@ def preprocess_signal(q, eps_t, kappa, nse_disc):
     return q.copy()
 
 
-def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normalize=True):
+def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normalize=True,
+                  evaluate=None):
     """Continuous spectrum of fnft_nsev for the fast discretizations:
     src/fnft_nsev.c:133-314 (driver), :458-542 (base), :744-891 (contspec).
-    cstype 0: rho[M]; 1: [a | b]; 2: [rho | a | b]."""
+    cstype 0: rho[M]; 1: [a | b]; 2: [rho | a | b].
+    evaluate(p, xi) -> p(z(xi)), if given, replaces the chirp-z evaluation (used by
+    tests/golden/make_golden.py to evaluate the same polynomials in long double)."""
     q = np.asarray(q, dtype=np.complex128)
     D = q.shape[0]
     scheme = _NSE2AKNS[nse_disc]
@@ -269,8 +334,11 @@ def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normal
     xi = XI[0] + eps_xi * np.arange(M)
     V = lambda_to_z(eps_xi, eps_t, scheme)     # :822-827
     A = lambda_to_z(-XI[0], eps_t, scheme)
-    H11 = poly_chirpz(tm[0], A, V, M)
-    H21 = poly_chirpz(tm[2], A, V, M)
+    if evaluate is None:
+        H11 = poly_chirpz(tm[0], A, V, M)
+        H21 = poly_chirpz(tm[2], A, V, M)
+    else:
+        H11, H21 = evaluate(tm[0], xi), evaluate(tm[2], xi)
     bc = 0.5
     d1 = akns_degree(scheme)
     extra = eps_t / d1 if nse_disc in (NSE_2SPLIT2A, NSE_2SPLIT2_MODAL) else 0.0
@@ -287,8 +355,9 @@ def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normal
     return np.concatenate(out)
 
 
-def kdvv(u, T, M, XI, kdv_disc=KDV_2SPLIT4B):
-    """fnft_kdvv, src/fnft_kdvv.c:59-209 (no preprocessing; xi grid negated)."""
+def kdvv(u, T, M, XI, kdv_disc=KDV_2SPLIT4B, evaluate=None):
+    """fnft_kdvv, src/fnft_kdvv.c:59-209 (no preprocessing; xi grid negated).
+    evaluate: see nsev_contspec."""
     u = np.asarray(u, dtype=np.complex128)
     D = u.shape[0]
     scheme = _KDV2AKNS[kdv_disc]
@@ -298,9 +367,12 @@ def kdvv(u, T, M, XI, kdv_disc=KDV_2SPLIT4B):
     tm, deg, _ = akns_fscatter(u, -np.ones_like(u), eps_t, scheme, normalize=False)
     V = np.exp(-2j * eps_xi * eps_t / deg1)      # :169-170
     A = np.exp(2j * XI[0] * eps_t / deg1)
-    H12 = poly_chirpz(tm[1], A, V, M)
-    H22 = poly_chirpz(tm[3], A, V, M)
     xi = -XI[0] - np.arange(M) * eps_xi
+    if evaluate is None:
+        H12 = poly_chirpz(tm[1], A, V, M)
+        H22 = poly_chirpz(tm[3], A, V, M)
+    else:
+        H12, H22 = evaluate(tm[1], xi), evaluate(tm[3], xi)
     if kdv_disc == KDV_2SPLIT2A:                 # :186-195
         H12 = H12 / np.exp(1j * xi * eps_t / deg1)
     return np.exp(2j * xi * (T[1] + 0.5 * eps_t)) * H12 / (2j * xi * H22 - H12)  # :198-203

@@ -29,7 +29,12 @@ def akns_fscatter_test_input():
 
 
 AKNS_TEST_SCHEMES = {"2split4B": 10, "2split2A": 3, "2split1A": 1, "2split1B": 2, "2split2B": 4,
-                     "2split2S": 5, "2split2_modal": 0}
+                     "2split2S": 5, "2split2_modal": 0, "2split3A": 6, "2split3B": 7, "2split3S": 8,
+                     "2split4A": 9, "2split5A": 11, "2split5B": 12, "2split6A": 13, "2split6B": 14,
+                     "2split7A": 15, "2split7B": 16, "2split8A": 17, "2split8B": 18}
+# error bounds of the reference tests in units of eps (err_bnd in the files named above)
+AKNS_TEST_BOUND = {"2split6A": 291, "2split6B": 250, "2split7A": 250, "2split7B": 250,
+                   "2split8A": 250, "2split8B": 250}
 
 
 def eval_tm(tm, z):

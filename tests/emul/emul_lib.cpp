@@ -92,7 +92,7 @@ int emul_fscatter(const double *q, const double *r, int B, int D, int deg0, int 
                   int smem_n)
 {
     const size_t npad = next_pow2_sz((size_t)D);
-    Work wk((size_t)B, npad, (size_t)deg0);
+    Work wk((size_t)B, npad, (size_t)tree_leaf_degree(scheme, deg0));
     int rc = tree_fscatter(wk.w, (const cplx *)q, (const cplx *)r, B, D, deg0, rmode, kappa, scheme,
                            eps_t, normalize, (cplx *)tm, get_tw(), NULL, use_direct, smem_n);
     for (int s = 0; s < B; ++s) {

@@ -53,7 +53,9 @@ def main():
         os.path.join(t, "fnft__poly/fnft__poly_chirpz_test.c"), "result_exactM3")
     G["reftest/chirpz_M6"] = parse_complex_array(
         os.path.join(t, "fnft__poly/fnft__poly_chirpz_test.c"), "result_exactM6")
-    for nm in ["2split4B", "2split2A", "2split1A", "2split1B", "2split2B", "2split2S", "2split2_modal"]:
+    for nm in ["2split4B", "2split2A", "2split1A", "2split1B", "2split2B", "2split2S", "2split2_modal",
+               "2split3A", "2split3B", "2split3S", "2split4A", "2split5A", "2split5B", "2split6A",
+               "2split6B", "2split7A", "2split7B", "2split8A", "2split8B"]:
         G[f"reftest/akns_fscatter_{nm}"] = parse_complex_array(
             os.path.join(t, f"fnft__akns_fscatter/fnft__akns_fscatter_test_{nm}.c"), "result_exact")
 
@@ -133,6 +135,51 @@ def main():
     assert ret == 0
     G["refrun/fmult2x2_deg3_n5/p"] = pm
     G["refrun/fmult2x2_deg3_n5/res"] = res * 2.0 ** W
+    # every polynomial splitting scheme end to end: nsev (a, b, rho) and kdvv (R).  The
+    # reference's chirp-z loses accuracy where sum|coeff| >> |p(z)| (high-degree schemes,
+    # kappa = -1), so next to its output ("cs") the same quantities are recorded with the
+    # oracle's polynomials (pinned to the reference's to 1e-14) evaluated by Horner's rule in
+    # 80-bit long double ("exact").
+    from oracle import fnft_oracle as O
+
+    def ld_eval(eps_t, step_div):
+        def ev(p, xi):
+            zz = np.exp(2j * xi.astype(np.longdouble) * np.longdouble(eps_t) / step_div)
+            r = np.zeros_like(zz)
+            for ck in p.astype(np.clongdouble):
+                r = r * zz + ck
+            return r
+        return ev
+
+    for disc in (2, 3, 5, 6, 7, 8, 9, 10, 12, 13, 14, 15, 16, 17, 18, 19, 20):   # nse enum values
+        D = 64 if disc == 20 else 50
+        tt = np.linspace(-6, 6, D)
+        q = 1.6 / np.cosh(tt) * np.exp(0.25j * tt * tt - 0.4j * tt)
+        for kappa in (1, -1):
+            o = R.nsev_default_opts()
+            o.discretization = disc
+            o.contspec_type = 2
+            ret, cs, *_ = R.nsev(q, [-6, 6], 24, [-2.5, 3.25], kappa, o)
+            assert ret == 0, (disc, ret)
+            G[f"refrun/schemes_nsev/{disc}/{kappa}/q"] = q
+            G[f"refrun/schemes_nsev/{disc}/{kappa}/cs"] = cs
+            sch = O._NSE2AKNS[disc]
+            G[f"refrun/schemes_nsev/{disc}/{kappa}/exact"] = O.nsev_contspec(
+                q, [-6, 6], 24, [-2.5, 3.25], kappa, disc, cstype=2,
+                evaluate=ld_eval(12.0 / (D - 1), O.akns_degree(sch) * O.akns_upsampling(sch))).astype(np.complex128)
+    for disc in range(0, 19):   # kdv enum values 1A ... 4SPLIT4A (4SPLIT4B = 19 is above)
+        D = 64 if disc == 18 else 50
+        tt = np.linspace(-16, 15, D)
+        u = 1.3 / np.cosh(tt) ** 2 + 0.25 * np.exp(-(tt + 2) ** 2)
+        o = R.lib().fnft_kdvv_default_opts()
+        o.discretization = disc
+        ret, cs = R.kdvv(u, [-16, 15], 24, [-3.55, 3.95], o)
+        assert ret == 0, (disc, ret)
+        G[f"refrun/schemes_kdvv/{disc}/u"] = u.astype(np.complex128)
+        G[f"refrun/schemes_kdvv/{disc}/cs"] = cs
+        G[f"refrun/schemes_kdvv/{disc}/exact"] = O.kdvv(
+            u, [-16, 15], 24, [-3.55, 3.95], disc,
+            evaluate=ld_eval(31.0 / (D - 1), O.akns_degree(O._KDV2AKNS[disc]))).astype(np.complex128)
     # accuracy floor of the reference: defocusing case, D = 126, evaluated exactly
     # (leaf coefficients in double like every implementation, product tree by direct
     # convolution and Horner evaluation in 80-bit long double)

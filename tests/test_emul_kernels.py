@@ -8,11 +8,13 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import ensure_emul, rel_err
+from common import (AKNS_TEST_BOUND, AKNS_TEST_SCHEMES, akns_fscatter_test_input, ensure_emul, eval_tm,
+                    rel_err)
 from oracle import fnft_oracle as O
 
 dp = np.ctypeslib.ndpointer(dtype=np.complex128, flags="C_CONTIGUOUS")
 ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+EPS = np.finfo(float).eps
 
 
 @pytest.fixture(scope="module")
@@ -128,3 +130,42 @@ def test_tree_kernels_general_mode_vs_oracle(E, D, use_direct, smem_n):
     tmo, dego, Wo = O.akns_fscatter(q[0], r[0], eps_t, 10)
     for e in range(4):
         assert rel_err(tm[0, e] * 2.0 ** W[0], tmo[e] * 2.0 ** Wo) < 1e-12
+
+
+@pytest.mark.parametrize("name", sorted(AKNS_TEST_SCHEMES))
+@pytest.mark.parametrize("use_direct", [1, 0])
+def test_leaf_kernels_all_schemes_reference_golden(E, golden, name, use_direct):
+    # the CUDA leaf + tree block programs (host emulation) on the input of
+    # test/fnft__akns_fscatter/fnft__akns_fscatter_test_<scheme>.c, explicit r
+    q, r, eps_t, z = akns_fscatter_test_input()
+    ak = AKNS_TEST_SCHEMES[name]
+    d0 = O.akns_degree(ak)
+    tm = np.zeros((1, 4, d0 * 8 + 1), dtype=np.complex128)
+    W = np.zeros(1, dtype=np.int32)
+    r = np.ascontiguousarray(r)
+    rc = E.emul_fscatter(np.ascontiguousarray(q), r.ctypes.data, 1, 8, d0, 2, 0, ak, eps_t, 1,
+                         tm, W, use_direct, 1024)
+    assert rc == 0
+    got = eval_tm(tm[0] * 2.0 ** W[0], z)
+    assert rel_err(got, golden[f"reftest/akns_fscatter_{name}"]) <= AKNS_TEST_BOUND.get(name, 100) * EPS
+
+
+@pytest.mark.parametrize("ak", [6, 8, 9, 12, 14, 18])
+@pytest.mark.parametrize("D", [3, 37])
+def test_chain_leaves_nse_and_kdv_modes_vs_oracle(E, ak, D):
+    rng = np.random.default_rng(ak * 100 + D)
+    t = np.linspace(-5, 5, D)
+    eps_t = 10.0 / (D - 1)
+    q = np.stack([1.3 / np.cosh(t) * np.exp(0.7j * t),
+                  (rng.standard_normal(D) + 1j * rng.standard_normal(D)) * 0.5])
+    d0 = O.akns_degree(ak)
+    for rmode, kappa in ((0, 1), (0, -1), (1, 0)):
+        tm = np.zeros((2, 4, d0 * D + 1), dtype=np.complex128)
+        W = np.zeros(2, dtype=np.int32)
+        assert E.emul_fscatter(np.ascontiguousarray(q), None, 2, D, d0, rmode, kappa, ak, eps_t, 1, tm, W,
+                               1, 1024) == 0
+        for s in range(2):
+            r = -kappa * np.conj(q[s]) if rmode == 0 else -np.ones(D)
+            tmo, dego, Wo = O.akns_fscatter(q[s], r, eps_t, ak)
+            for e in range(4):
+                assert rel_err(tm[s, e] * 2.0 ** W[s], tmo[e] * 2.0 ** Wo) < 1e-11

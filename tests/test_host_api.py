@@ -116,7 +116,7 @@ def test_not_yet_implemented_paths_are_loud(F):
     o.discretization = 1  # BO: slow scheme, out of scope of the GPU hot path
     assert _call_nsev(F, opts=o) == 6
     o = F.nsev_default_opts()
-    o.discretization = 7  # 2SPLIT3A: no leaf kernel yet
+    o.discretization = 23  # CF4_3: slow scheme as well
     assert _call_nsev(F, opts=o) == 6
 
 
