@@ -99,11 +99,14 @@ def test_all_splitting_schemes_vs_reference_runs(F, golden):
     #      sum|coeff| >> |p(z)| (degree >= 12 schemes with kappa = -1).
     F.lib().fnft_errwarn_setprintf(None)
 
-    def check(ours, ref, exact, n, case):
+    def check(ours, ref, exact, n, case, cond=1.0):
+        # cond = sum|coeff of a| / min|a(xi)|: no double-precision evaluation of the polynomial can
+        # be better than ~eps*cond (1.3e7 for 2SPLIT8A with kappa = -1, < 1e5 everywhere else)
+        tol = max(1e-9, 8 * EPS * cond)
         for part in range(ours.size // n):
             sl = slice(part * n, (part + 1) * n)
-            assert max(parity_contract(ours[sl], exact[sl])) < 1, (case, part, "vs long double")
-            slack = 1 + 2 * max(parity_contract(ref[sl], exact[sl]))
+            assert max(parity_contract(ours[sl], exact[sl], tol=tol)) < 1, (case, part, "vs long double")
+            slack = tol / 1e-9 + 2 * max(parity_contract(ref[sl], exact[sl]))
             assert max(parity_contract(ours[sl], ref[sl])) < slack, (case, part, "vs reference")
 
     for case in _keys(golden, "refrun/schemes_nsev/"):
@@ -113,7 +116,12 @@ def test_all_splitting_schemes_vs_reference_runs(F, golden):
         o.contspec_type = F.CSTYPE_BOTH
         ret, cs, *_ = F.nsev(golden[f"refrun/schemes_nsev/{case}/q"], [-6, 6], 24, [-2.5, 3.25], kappa, o)
         assert ret == 0, case
-        check(cs, golden[f"refrun/schemes_nsev/{case}/cs"], golden[f"refrun/schemes_nsev/{case}/exact"], 24, case)
+        q = golden[f"refrun/schemes_nsev/{case}/q"]
+        exact = golden[f"refrun/schemes_nsev/{case}/exact"]
+        qp = O.preprocess_signal(q, 12.0 / (q.size - 1), kappa, disc)
+        tm, _, W = O.akns_fscatter(qp, -kappa * np.conj(qp), 12.0 / (q.size - 1), O._NSE2AKNS[disc])
+        cond = np.abs(tm[0]).sum() * 2.0 ** W / np.abs(exact[24:48]).min()
+        check(cs, golden[f"refrun/schemes_nsev/{case}/cs"], exact, 24, case, cond)
     for case in _keys(golden, "refrun/schemes_kdvv/"):
         o = F.kdvv_default_opts()
         o.discretization = int(case)
