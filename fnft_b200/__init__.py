@@ -78,7 +78,7 @@ EXPORTED_SYMBOLS = [
     "fnft_nsev_default_opts", "fnft_nsev_max_K", "fnft_nsev",
     "fnft_kdvv_default_opts", "fnft_kdvv",
     "fnft_nsep_default_opts", "fnft_nsep",
-    "fnft__poly_fmult2x2_numel", "fnft__poly_fmult2x2", "fnft__poly_chirpz",
+    "fnft__poly_fmult2x2_numel", "fnft__poly_fmult2x2", "fnft__poly_chirpz", "fnft__poly_roots_fasteigen",
     "fnft__akns_fscatter_numel", "fnft__akns_fscatter",
     "fnft__nse_fscatter_numel", "fnft__nse_fscatter",
     "fnft__kdv_fscatter_numel", "fnft__kdv_fscatter",
@@ -126,6 +126,8 @@ def lib():
     L.fnft__poly_fmult2x2_numel.argtypes = [sz, sz]
     L.fnft__poly_fmult2x2.restype = i32
     L.fnft__poly_fmult2x2.argtypes = [vp, sz, vp, vp, vp]
+    L.fnft__poly_roots_fasteigen.restype = i32
+    L.fnft__poly_roots_fasteigen.argtypes = [sz, vp, vp]
     L.fnft__poly_chirpz.restype = i32
     L.fnft__poly_chirpz.argtypes = [sz, vp, Cplx, Cplx, sz, vp]
     L.fnft__akns_fscatter_numel.restype = sz
@@ -389,6 +391,16 @@ def poly_chirpz(p, A, W, M):
     ret = L.fnft__poly_chirpz(p.shape[0] - 1, _p(p), Cplx(A.real, A.imag), Cplx(W.real, W.imag), M,
                               _p(out))
     return ret, out
+
+
+def poly_roots_fasteigen(p):
+    """fnft__poly_roots_fasteigen.  p: deg+1 coefficients, highest power first.
+    Returns (ret, roots[deg])."""
+    L = lib()
+    p = _c128(p)
+    roots = np.zeros(p.shape[0] - 1, dtype=np.complex128)
+    ret = L.fnft__poly_roots_fasteigen(p.shape[0] - 1, _p(p), _p(roots))
+    return ret, roots
 
 
 def nse_scatter_bound_states(q, r, T, lam, discretization, skip_b=False):

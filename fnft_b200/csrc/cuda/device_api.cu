@@ -7,6 +7,7 @@
 #include "chirpz_driver.cuh"
 #include "chirpz2.cuh"
 #include "nsep_kernels.cuh"
+#include "poly_roots.cuh"
 #include "resample_kernels.cuh"
 #include "tree_driver.cuh"
 #include "twiddle.h"
@@ -146,6 +147,8 @@ struct fnftb_ctx {
     Buf box3, lam, kcnt, flag, aout, apout, bout, phi;
     // nsep workspace
     Buf fpoly, vals, roots, nraw, nkept;
+    // root-finder workspace
+    Buf rt_roots, rt_absc, rt_lg, rt_hull, rt_info;
     int have_box3 = 0;
     // pipelined host transfers (fnftb_pipeline_begin): two slots, copy streams, events
     int pipe_on = 0, slot = 0;
@@ -282,6 +285,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
                   &c->status, &c->tm, &c->tt0, &c->tt1, &c->twmem, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept,
+                  &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info,
                   &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1]};
     for (Buf *b : all)
         release(*b);
@@ -925,14 +929,46 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
 // ---------------------------------------------------------------------------
 int fnftb_resample_4split4(fnftb_ctx *c, double eps_t, int32_t *warn_host)
 {
+    return fnftb_resample_4split4_sub(c, eps_t, 1, c ? c->D : 0, warn_host);
+}
+
+int fnftb_subsample(fnftb_ctx *c, size_t nskip, size_t Dsub)
+{
     if (!c || !c->q)
         return fail(-2, "no signals staged", __FILE__, __LINE__);
+    if (nskip < 1 || Dsub < 1 || (Dsub - 1) * nskip >= c->D)
+        return fail(-2, "invalid subsampling", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure(c->qpre, c->B * Dsub * sizeof(cplx)));
+    SubsampleArgs sa;
+    sa.q = c->q;
+    sa.out = (cplx *)c->qpre.p;
+    sa.B = (int)c->B;
+    sa.D = (int)c->D;
+    sa.nskip = (int)nskip;
+    sa.Dsub = (int)Dsub;
+    const long long total = (long long)c->B * (long long)Dsub;
+    RC((launch_blocks<SubsampleArgs, blk_subsample>(sa, (unsigned)((total + 255) / 256), 256, 0, c->st,
+                                                    "subsample")));
+    c->q = (const cplx *)c->qpre.p;
+    c->r = nullptr;
+    c->D = Dsub;
+    c->have_box3 = 0;
+    return 0;
+}
+
+int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host)
+{
+    if (!c || !c->q)
+        return fail(-2, "no signals staged", __FILE__, __LINE__);
+    if (nskip < 1 || Dsub < 1 || (Dsub - 1) * nskip >= c->D)
+        return fail(-2, "invalid subsampling", __FILE__, __LINE__);
     const size_t D = c->D;
     if ((D & (D - 1)) != 0 || D < 4 || D > 4096)
         return fail(-6, "GPU resampling needs a power-of-two number of samples between 4 and 4096",
                     __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
-    RC(ensure(c->qpre, c->B * 2 * D * sizeof(cplx)));
+    RC(ensure(c->qpre, c->B * 2 * Dsub * sizeof(cplx)));
     RC(ensure(c->warn, c->B * sizeof(int)));
     ResampleArgs ra;
     memset(&ra, 0, sizeof(ra));
@@ -941,6 +977,8 @@ int fnftb_resample_4split4(fnftb_ctx *c, double eps_t, int32_t *warn_host)
     ra.warn = (int *)c->warn.p;
     ra.B = (int)c->B;
     ra.D = (int)D;
+    ra.nskip = (int)nskip;
+    ra.Dsub = (int)Dsub;
     ra.eps_t = eps_t;
     ra.plan = make_fft_plan((int)D);
     ra.T = ctx_tw(c);
@@ -949,11 +987,54 @@ int fnftb_resample_4split4(fnftb_ctx *c, double eps_t, int32_t *warn_host)
                                                           resample_smem_bytes((int)D, nt), c->st, "resample_4split4")));
     c->q = (const cplx *)c->qpre.p;
     c->r = nullptr;
-    c->D = 2 * D;
+    c->D = 2 * Dsub;
+    c->have_box3 = 0;
     if (warn_host) {
         CU(cudaMemcpyAsync(warn_host, c->warn.p, c->B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// polynomial roots (poly_roots.cuh)
+// ---------------------------------------------------------------------------
+int fnftb_poly_roots(fnftb_ctx *c, int ent, void *roots_host, int32_t *info_host)
+{
+    if (!c || !roots_host || c->tmB == 0 || c->deg < 1 || ent < 0 || ent >= (int)c->tm_entries)
+        return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ctx_finalize(c));
+    const size_t B = c->tmB, n = c->deg;
+    RC(ensure(c->rt_roots, B * n * sizeof(cplx)));
+    RC(ensure(c->rt_absc, B * (n + 1) * sizeof(double)));
+    RC(ensure(c->rt_lg, B * (n + 1) * sizeof(double)));
+    RC(ensure(c->rt_hull, B * (n + 2) * sizeof(int)));
+    RC(ensure(c->rt_info, B * 4 * sizeof(int)));
+    RootsArgs ra;
+    ra.coef = (const cplx *)c->tm.p + (size_t)ent * (n + 1);
+    ra.cstride = (long long)(c->tm_entries * (n + 1));
+    ra.n = (int)n;
+    ra.roots = (cplx *)c->rt_roots.p;
+    ra.absc = (double *)c->rt_absc.p;
+    ra.lg = (double *)c->rt_lg.p;
+    ra.hull = (int *)c->rt_hull.p;
+    ra.info = (int *)c->rt_info.p;
+    static const int knob_maxit = tree_knob("FNFT_B200_ROOTS_MAXIT", 200);
+    ra.maxit = knob_maxit;
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin("poly_roots", c->st);
+    const int rc = roots_launch(ra, (int)B, c->st);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(c->st);
+    if (rc == -6)
+        return fail(-6, "polynomial degree too large for the GPU root finder (max 8192)", __FILE__, __LINE__);
+    if (rc)
+        return fail(rc, "root finder launch failed", __FILE__, __LINE__);
+    CU(cudaMemcpyAsync(roots_host, c->rt_roots.p, B * n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    if (info_host)
+        CU(cudaMemcpyAsync(info_host, c->rt_info.p, B * 4 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
     return 0;
 }
 

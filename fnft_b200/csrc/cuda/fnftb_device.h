@@ -92,6 +92,20 @@ int fnftb_set_signals(fnftb_ctx *ctx, size_t B, size_t D, const void *q, const v
  * signal does not look band-limited. */
 int fnftb_resample_4split4(fnftb_ctx *ctx, double eps_t, int32_t *warn_host);
 
+/* Same with subsampling (src/private/fnft__nse_discretization.c:428-431,483-500): the shifts
+ * are scaled by nskip and only the samples 0, nskip, 2*nskip, ... (Dsub of them) are kept. */
+int fnftb_resample_4split4_sub(fnftb_ctx *ctx, double eps_t, size_t nskip, size_t Dsub,
+                               int32_t *warn_host);
+/* Plain subsampling of the staged signals (fnft__nse_discretization.c:463-470): keeps the
+ * samples 0, nskip, ..., (Dsub-1)*nskip (device resident). */
+int fnftb_subsample(fnftb_ctx *ctx, size_t nskip, size_t Dsub);
+
+/* All roots of entry `ent` (0 = a(z)) of every transfer matrix held in the context
+ * (fnft__poly_roots_fasteigen, src/private/fnft__poly_roots_fasteigen.c:29-48; Aberth-Ehrlich
+ * iteration on the device, poly_roots.cuh).  roots_host: [B][deg]; info_host (may be NULL):
+ * [B][4] = {leading zeros, effective degree, sweeps, roots that did not converge}. */
+int fnftb_poly_roots(fnftb_ctx *ctx, int ent, void *roots_host, int32_t *info_host);
+
 /* leaves + product tree for the staged signals */
 int fnftb_fscatter(fnftb_ctx *ctx, const fnftb_scatter_desc *desc);
 

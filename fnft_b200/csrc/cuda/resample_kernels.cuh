@@ -18,6 +18,7 @@ struct ResampleArgs {
     cplx *out;      // [B][2*D]
     int *warn;      // [B] 1 if the spectrum does not look band-limited
     int B, D;
+    int nskip, Dsub;  // keep the samples 0, nskip, ..., (Dsub-1)*nskip; shifts scaled by nskip
     double eps_t;
     FftPlan plan;
     TwTable T;
@@ -84,7 +85,7 @@ BLK void blk_resample_4split4(const ResampleArgs &a, blk3 bid, int nt, void *sme
     FOR_THREADS(tid, nt)
     {
         const double scl = (double)D * a.eps_t;
-        const double delta = a.eps_t * (1.7320508075688772 / 6.0);
+        const double delta = a.eps_t * (1.7320508075688772 / 6.0) * (double)a.nskip;
         for (int pos = tid; pos < D; pos += nt) {
             const int k = plan_freq_of_pos(a.plan, pos);
             const double freq = (k < D / 2) ? (double)k / scl : ((double)k - (double)D) / scl;
@@ -103,11 +104,31 @@ BLK void blk_resample_4split4(const ResampleArgs &a, blk3 bid, int nt, void *sme
         const double sf = 1.7320508075688772 / 6.0;
         const double w0 = 0.25 + sf, w1 = 0.25 - sf;
         const double invD = 1.0 / (double)D;
-        cplx *o = a.out + (size_t)s * 2 * D;
-        for (int i = tid; i < D; i += nt) {
+        cplx *o = a.out + (size_t)s * 2 * a.Dsub;
+        for (int isub = tid; isub < a.Dsub; isub += nt) {
+            const int i = isub * a.nskip;
             const cplx q1 = cscale(S1[swz(i)], invD), q2 = cscale(S2[swz(i)], invD);
-            o[2 * i] = make_cplx(w0 * q1.x + w1 * q2.x, w0 * q1.y + w1 * q2.y);
-            o[2 * i + 1] = make_cplx(w1 * q1.x + w0 * q2.x, w1 * q1.y + w0 * q2.y);
+            o[2 * isub] = make_cplx(w0 * q1.x + w1 * q2.x, w0 * q1.y + w1 * q2.y);
+            o[2 * isub + 1] = make_cplx(w1 * q1.x + w0 * q2.x, w1 * q1.y + w0 * q2.y);
+        }
+    }
+}
+
+// plain subsampling (fnft__nse_discretization.c:463-470)
+struct SubsampleArgs {
+    const cplx *q;  // [B][D]
+    cplx *out;      // [B][Dsub]
+    int B, D, nskip, Dsub;
+};
+
+BLK void blk_subsample(const SubsampleArgs &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        if (gid < (long long)a.B * a.Dsub) {
+            const int s = (int)(gid / a.Dsub), isub = (int)(gid % a.Dsub);
+            a.out[gid] = a.q[(size_t)s * a.D + (size_t)isub * a.nskip];
         }
     }
 }

@@ -142,9 +142,10 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
         return E_NOT_YET_IMPLEMENTED(D, The GPU resampling step of the 4SPLIT4 schemes needs a power-of-two number of samples.);
     const int want_contspec = (contspec != NULL && M > 0);
     const int want_discspec = (kappa == +1 && bound_states != NULL);
-    if (want_discspec && opts->bound_state_localization != fnft_nsev_bsloc_NEWTON)
-        return E_NOT_YET_IMPLEMENTED(opts->bound_state_localization,
-                                     The GPU build localizes bound states with fnft_nsev_bsloc_NEWTON only.);
+    const fnft_nsev_bsloc_t bsloc = opts->bound_state_localization;
+    if (want_discspec && bsloc != fnft_nsev_bsloc_NEWTON && bsloc != fnft_nsev_bsloc_FAST_EIGENVALUE &&
+        bsloc != fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE)
+        return E_INVALID_ARGUMENT(opts->bound_state_localization);
     if (want_discspec && Kmax == 0)
         return E_INVALID_ARGUMENT(Kmax);
 
@@ -201,6 +202,33 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     for (FNFT_UINT b0 = 0; b0 < B || prev_nb > 0; b0 += chunk) {
         const FNFT_UINT nb = (b0 >= B) ? 0 : ((B - b0 < chunk) ? (B - b0) : chunk);
         int32_t *st_cur = status ? status + (size_t)slot * chunk : NULL;
+        if (nb > 0 && want_discspec && bsloc == fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE) {
+            /* First step of the mixed method (src/fnft_nsev.c:276-296): initial guesses from
+             * the fast eigenvalue method on a subsampled signal. */
+            FNFT_UINT Dsub = opts->Dsub;
+            if (Dsub == 0) /* the user wants us to determine Dsub */
+                Dsub = (FNFT_UINT)sqrt(D * log2(D) * log2(D));
+            if (Dsub < 2) /* src/private/fnft__nse_discretization.c:424-431 */
+                Dsub = 2;
+            if (Dsub > D)
+                Dsub = D;
+            const FNFT_UINT nskip = (FNFT_UINT)round((FNFT_REAL)D / Dsub);
+            Dsub = (FNFT_UINT)round((FNFT_REAL)D / nskip);
+            if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, devptr) != 0) {
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+            const int rc_sub = (upsampling == 2) ? fnftb_resample_4split4_sub(ctx, eps_t, nskip, Dsub, NULL)
+                                                 : fnftb_subsample(ctx, nskip, Dsub);
+            if (rc_sub != 0) {
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+            const FNFT_REAL Tsub[2] = {T[0], T[0] + ((Dsub - 1) * nskip) * eps_t}; /* :290-291 */
+            ret_code = fnftb__nsev_fasteig_chunk(ctx, nb, Dsub * upsampling, Dsub, Tsub, kappa, 0, K + b0,
+                                                 Kmax, bound_states + b0 * Kmax, opts);
+            CHECK_RETCODE(ret_code, leave_fun);
+        }
         if (nb > 0) {
             /* preprocessing (src/fnft_nsev.c:272): plain copy for upsampling 1; the
              * 4SPLIT4 schemes resample on the device */
@@ -268,6 +296,12 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
             break;
 
         if (want_discspec) {
+            const int fast = (bsloc == fnft_nsev_bsloc_FAST_EIGENVALUE);
+            if (fast) { /* src/fnft_nsev.c:687-711; the transfer matrix of this chunk is reused */
+                ret_code = fnftb__nsev_fasteig_chunk(ctx, nb, D_eff, D, T, kappa, want_contspec, K + b0,
+                                                     Kmax, bound_states + b0 * Kmax, opts);
+                CHECK_RETCODE(ret_code, leave_fun);
+            }
             FNFT_INT rc2 = fnftb__nsev_discrete_chunk(ctx, nb, D_eff, D, T, eps_t, K + b0, Kmax,
                                                       bound_states + b0 * Kmax,
                                                       normconsts_or_residues == NULL
@@ -275,7 +309,7 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
                                                           : normconsts_or_residues +
                                                                 b0 * Kmax *
                                                                     (opts->discspec_type == fnft_nsev_dstype_BOTH ? 2 : 1),
-                                                      opts, ret_codes ? ret_codes + b0 : NULL);
+                                                      opts, ret_codes ? ret_codes + b0 : NULL, fast);
             if (rc2 != FNFT_SUCCESS && ret_code == FNFT_SUCCESS)
                 ret_code = rc2;
             if (rc2 != FNFT_SUCCESS && ret_codes == NULL)

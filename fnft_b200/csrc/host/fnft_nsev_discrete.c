@@ -42,11 +42,116 @@ void fnftb__merge(FNFT_UINT *N, FNFT_COMPLEX *vals, FNFT_REAL tol)
     *N = kept;
 }
 
+/* bounding box of src/fnft_nsev.c:628-659: box[0..2] common, box3[b] per signal */
+static FNFT_INT nsev_bounding_boxes(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT upsampling, FNFT_REAL const *T,
+                                    FNFT_REAL eps_t, fnft_nsev_opts_t const *opts, double *box,
+                                    double *box3, int *use_box3)
+{
+    const FNFT_REAL degree1step = (FNFT_REAL)fnftb__nse_degree(opts->discretization);
+    const FNFT_REAL map_coeff = (degree1step != 0) ? 2 / degree1step : 2.0;
+    *use_box3 = 0;
+    if (opts->bound_state_filtering == fnft_nsev_bsfilt_FULL) {
+        box[1] = 0.9 * FNFT_PI / fabs(map_coeff * eps_t);
+        box[0] = -box[1];
+        box[2] = 0.0;
+        *use_box3 = 1;
+        if (fnftb_imbound(ctx, (int)upsampling, T[0], T[1], box3) != 0)
+            return E_DEVICE;
+    } else if (opts->bound_state_filtering == fnft_nsev_bsfilt_BASIC) {
+        box[0] = -INFINITY;
+        box[1] = INFINITY;
+        box[2] = 0.0;
+        for (FNFT_UINT b = 0; b < nb; b++)
+            box3[b] = INFINITY;
+    } else {
+        box[0] = -INFINITY;
+        box[1] = INFINITY;
+        box[2] = -INFINITY;
+        for (FNFT_UINT b = 0; b < nb; b++)
+            box3[b] = INFINITY;
+    }
+    return FNFT_SUCCESS;
+}
+
+FNFT_INT fnftb__nsev_fasteig_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D_eff, FNFT_UINT D_given,
+                                   FNFT_REAL const *T, FNFT_INT kappa, int have_tm, FNFT_UINT *K,
+                                   FNFT_UINT Kmax, FNFT_COMPLEX *bound_states,
+                                   fnft_nsev_opts_t const *opts)
+{
+    FNFT_INT ret_code = FNFT_SUCCESS;
+    FNFT_COMPLEX *roots = NULL;
+    int32_t *info = NULL;
+    double *box3 = NULL;
+    const FNFT_UINT upsampling = D_eff / D_given;
+    const FNFT_REAL eps_t = (T[1] - T[0]) / (D_given - 1);
+    fnft__akns_discretization_t akns;
+    if (fnftb__nse_to_akns(opts->discretization, &akns) != FNFT_SUCCESS)
+        return E_INVALID_ARGUMENT(opts->discretization);
+    const FNFT_UINT deg0 = fnftb__akns_degree(akns);
+    if (deg0 == 0) /* slow discretizations only support Newton (include/fnft_nse_discretization_t.h) */
+        return E_INVALID_ARGUMENT(opts->bound_state_localization);
+    const FNFT_UINT deg = deg0 * D_eff;
+
+    if (!have_tm) { /* nse_fscatter of fnft_nsev_base, src/fnft_nsev.c:527 */
+        fnftb_scatter_desc sd;
+        memset(&sd, 0, sizeof(sd));
+        sd.rmode = FNFTB_RMODE_NSE;
+        sd.kappa = kappa;
+        sd.scheme = (int)akns;
+        sd.deg0 = (int)deg0;
+        sd.normalize = opts->normalization_flag ? 1 : 0;
+        sd.eps_t = eps_t;
+        if (fnftb_fscatter(ctx, &sd) != 0)
+            return E_DEVICE;
+    }
+    roots = malloc(nb * deg * sizeof(FNFT_COMPLEX));
+    info = malloc(nb * 4 * sizeof(int32_t));
+    box3 = malloc(nb * sizeof(double));
+    if (roots == NULL || info == NULL || box3 == NULL) {
+        ret_code = E_NOMEM;
+        goto leave_fun;
+    }
+    /* poly_roots_fasteigen(deg, transfer_matrix, buffer), :702 */
+    if (fnftb_poly_roots(ctx, 0, roots, info) != 0) {
+        ret_code = E_DEVICE;
+        goto leave_fun;
+    }
+    double box[4];
+    int use_box3;
+    ret_code = nsev_bounding_boxes(ctx, nb, upsampling, T, eps_t, opts, box, box3, &use_box3);
+    CHECK_RETCODE(ret_code, leave_fun);
+    /* z -> lambda (src/private/fnft__akns_discretization.c:225-240), filter, merge (:717-724) */
+    const FNFT_REAL degree1step = (FNFT_REAL)(deg0 * upsampling);
+    for (FNFT_UINT b = 0; b < nb; b++) {
+        FNFT_COMPLEX *buf = roots + b * deg;
+        FNFT_UINT Kb = (FNFT_UINT)info[4 * b + 1]; /* roots of the zero-stripped polynomial */
+        for (FNFT_UINT i = 0; i < Kb; i++)
+            buf[i] = clog(buf[i]) / (2 * I * eps_t / degree1step);
+        if (opts->bound_state_filtering != fnft_nsev_bsfilt_NONE) {
+            box[3] = box3[b];
+            fnftb__filter_box(&Kb, buf, box);
+            fnftb__merge(&Kb, buf, sqrt(FNFT_EPSILON));
+        }
+        if (Kb > Kmax) { /* :728-731 */
+            WARN("Found more than *K_ptr bound states. Returning as many as possible.");
+            Kb = Kmax;
+        }
+        memcpy(bound_states + b * Kmax, buf, Kb * sizeof(FNFT_COMPLEX));
+        K[b] = Kb;
+    }
+
+leave_fun:
+    free(roots);
+    free(info);
+    free(box3);
+    return ret_code;
+}
+
 FNFT_INT fnftb__nsev_discrete_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D_eff, FNFT_UINT D_given,
                                     FNFT_REAL const *T, FNFT_REAL eps_t, FNFT_UINT *K,
                                     FNFT_UINT Kmax, FNFT_COMPLEX *bound_states,
                                     FNFT_COMPLEX *normconsts_or_residues,
-                                    fnft_nsev_opts_t const *opts, FNFT_INT *ret_codes)
+                                    fnft_nsev_opts_t const *opts, FNFT_INT *ret_codes, int skip_newton)
 {
     FNFT_INT ret_code = FNFT_SUCCESS;
     int32_t *Kc = NULL, *flag = NULL;
@@ -110,7 +215,7 @@ FNFT_INT fnftb__nsev_discrete_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D_ef
     }
 
     /* Newton refinement (skipped like the reference when niter == 0, :992) */
-    if (opts->niter > 0) {
+    if (opts->niter > 0 && !skip_newton) {
         if (fnftb_newton(ctx, &bd, Kc, bound_states, flag) != 0) {
             ret_code = E_DEVICE;
             goto leave_fun;
@@ -126,7 +231,7 @@ FNFT_INT fnftb__nsev_discrete_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D_ef
         for (FNFT_UINT i = 0; i < Kb; i++)
             if (flag[b * Kmax + i] == FNFT_EC_DIV_BY_ZERO)
                 rc_b = E_DIV_BY_ZERO; /* :1020-1021 */
-        if (rc_b == FNFT_SUCCESS && opts->bound_state_filtering != fnft_nsev_bsfilt_NONE) {
+        if (rc_b == FNFT_SUCCESS && opts->bound_state_filtering != fnft_nsev_bsfilt_NONE && !skip_newton) {
             const FNFT_REAL box[4] = {bd.box0, bd.box1, bd.box2, box3[b]};
             fnftb__filter_box(&Kb, bound_states + b * Kmax, box);
             fnftb__merge(&Kb, bound_states + b * Kmax, sqrt(FNFT_EPSILON));

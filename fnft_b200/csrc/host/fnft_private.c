@@ -84,6 +84,29 @@ FNFT_INT fnft__poly_chirpz(const FNFT_UINT deg, FNFT_COMPLEX const *const p,
     return FNFT_SUCCESS;
 }
 
+/* src/private/fnft__poly_roots_fasteigen.c:29-48 */
+FNFT_INT fnft__poly_roots_fasteigen(const FNFT_UINT deg, FNFT_COMPLEX const *const p,
+                                    FNFT_COMPLEX *const roots)
+{
+    if (p == NULL)
+        return E_INVALID_ARGUMENT(p);
+    if (roots == NULL)
+        return E_INVALID_ARGUMENT(roots);
+    if (deg == 0)
+        return FNFT_SUCCESS;
+    fnftb_ctx *ctx = ctx_or_error();
+    if (ctx == NULL)
+        return FNFT_EC_OTHER;
+    if (fnftb_set_polynomial(ctx, deg, p) != 0)
+        return E_DEVICE;
+    int32_t info[4];
+    if (fnftb_poly_roots(ctx, 0, roots, info) != 0)
+        return E_DEVICE;
+    if (info[3] != 0) /* eiscor's info != 0 (:44-47) */
+        return E_SUBROUTINE(FNFT_EC_OTHER);
+    return FNFT_SUCCESS;
+}
+
 /* src/private/fnft__akns_fscatter.c:33-41 */
 FNFT_UINT fnft__akns_fscatter_numel(FNFT_UINT D, fnft__akns_discretization_t discretization)
 {

@@ -289,6 +289,12 @@ FNFT_INT fnft_nsep(const FNFT_UINT D, FNFT_COMPLEX const *const q, FNFT_REAL con
 FNFT_UINT fnft__poly_fmult2x2_numel(FNFT_UINT deg, FNFT_UINT n);
 FNFT_INT fnft__poly_fmult2x2(FNFT_UINT *const d, FNFT_UINT n, FNFT_COMPLEX *const p,
                              FNFT_COMPLEX *const result, FNFT_INT *const W_ptr);
+/* include/private/fnft__poly_roots_fasteigen.h:45, src/private/fnft__poly_roots_fasteigen.c:29-48:
+ * all deg roots of p (deg+1 coefficients, highest power first).  The reference calls eiscor's
+ * companion-pencil QR; this library runs an Aberth-Ehrlich iteration on the GPU. */
+FNFT_INT fnft__poly_roots_fasteigen(const FNFT_UINT deg, FNFT_COMPLEX const *const p,
+                                    FNFT_COMPLEX *const roots);
+
 /* include/private/fnft__poly_chirpz.h:66, src/private/fnft__poly_chirpz.c:33 */
 FNFT_INT fnft__poly_chirpz(const FNFT_UINT deg, FNFT_COMPLEX const *const p,
                            const FNFT_COMPLEX A, const FNFT_COMPLEX W, const FNFT_UINT M,

@@ -180,6 +180,40 @@ def main():
         G[f"refrun/schemes_kdvv/{disc}/exact"] = O.kdvv(
             u, [-16, 15], 24, [-3.55, 3.95], disc,
             evaluate=ld_eval(31.0 / (D - 1), O.akns_degree(O._KDV2AKNS[disc]))).astype(np.complex128)
+    # default options (SUBSAMPLE_AND_REFINE) and FAST_EIGENVALUE: the reference with eiscor replaced
+    # by the oracle-only companion-matrix shim (oracle/eiscor_shim.c)
+    def bs_case(key, q, T, M, XI, disc, bsloc, dstype=2):
+        o = R.nsev_default_opts()
+        o.discretization = disc
+        o.bound_state_localization = bsloc
+        o.discspec_type = dstype
+        ret, cs, K, bs, nc = R.nsev(q, T, M, XI, 1, o, K=2 * len(q))
+        assert ret == 0, (key, ret)
+        G[f"refrun/defaults/{key}/q"] = np.asarray(q, dtype=np.complex128)
+        G[f"refrun/defaults/{key}/par"] = np.array([T[0], T[1], M, XI[0], XI[1], disc, bsloc, dstype], dtype=np.float64)
+        G[f"refrun/defaults/{key}/cs"] = cs
+        G[f"refrun/defaults/{key}/bs"] = bs[:K]
+        G[f"refrun/defaults/{key}/nc"] = nc[:2 * K if dstype == 2 else K]
+    # BASELINE config 1: examples/fnft_nsev_example.c as shipped (rectangular pulse, :34-76)
+    bs_case("example", np.full(256, 2.0 + 0j), [-1, 1], 8, [-2, 2], 11, 2, 0)
+    for D in (256, 500, 1024):
+        tt = np.linspace(-10, 10, D)
+        qs = 2.7 / np.cosh(tt) * np.exp(0.4j * tt)
+        bs_case(f"sech{D}_sub", qs, [-10, 10], 16, [-2, 2], 11, 2)
+        bs_case(f"sech{D}_fast", qs, [-10, 10], 16, [-2, 2], 11, 0)
+    tt = np.linspace(-10, 10, 256)
+    qs = 2.7 / np.cosh(tt) * np.exp(0.4j * tt)
+    bs_case("sech256_4split4b_sub", qs, [-10, 10], 16, [-2, 2], 21, 2)
+    bs_case("sech256_2split2a_sub", qs, [-10, 10], 16, [-2, 2], 4, 2)
+    bs_case("sech256_2split6b_fast", qs, [-10, 10], 16, [-2, 2], 15, 0)
+    pr = rng.standard_normal(60) + 1j * rng.standard_normal(60)
+    G["refrun/roots/p"] = pr
+    ret = R.lib().fnft__poly_roots_fasteigen
+    rts = np.zeros(59, dtype=np.complex128)
+    assert ret(59, pr.ctypes.data, rts.ctypes.data) == 0
+    G["refrun/roots/roots"] = rts
+    G["reftest/roots_fasteigen"] = parse_complex_array(
+        os.path.join(t, "fnft__poly/fnft__poly_roots_fasteigen_test.c"), "roots_exact")
     # accuracy floor of the reference: defocusing case, D = 126, evaluated exactly
     # (leaf coefficients in double like every implementation, product tree by direct
     # convolution and Horner evaluation in 80-bit long double)

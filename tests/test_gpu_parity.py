@@ -131,6 +131,125 @@ def test_all_splitting_schemes_vs_reference_runs(F, golden):
               "kdvv " + case)
 
 
+def _match_sets(ours, ref):
+    """Pairs every reference value with the nearest of ours (like nsev_compare_nfs,
+    src/private/fnft__nsev_testcases.c:664-705); returns the index list."""
+    assert len(ours) == len(ref), (ours, ref)
+    idx = [int(np.argmin(np.abs(ours - r))) for r in ref]
+    assert sorted(idx) == list(range(len(ref))), "not a one-to-one match"
+    return idx
+
+
+def test_poly_roots_fasteigen_reference_golden(F, golden):
+    # test/fnft__poly/fnft__poly_roots_fasteigen_test.c:24-40 (Hausdorff distance <= 100 eps)
+    p = np.array([1.0 - 2.0j, 0.3 + 0.4j, -2.0 - 2.0j, -3.0 + 4.0j])
+    ret, roots = F.poly_roots_fasteigen(p)
+    assert ret == 0
+    exact = golden["reftest/roots_fasteigen"]
+    d = np.abs(roots[:, None] - exact[None, :])
+    assert max(d.min(axis=0).max(), d.min(axis=1).max()) <= 100 * EPS
+    # recorded run of the reference (companion-matrix QR) on a random polynomial of degree 59
+    ret, roots = F.poly_roots_fasteigen(golden["refrun/roots/p"])
+    ref = golden["refrun/roots/roots"]
+    idx = _match_sets(roots, ref)
+    assert ret == 0 and np.abs(roots[idx] - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 1024, 1025, 3640, 8192])
+def test_poly_roots_residuals_and_vieta(F, n):
+    # size-independent properties: every returned value is a root to working precision
+    # (|p(z)| <= 16 n eps sum|c_k||z|^k, evaluated in long double) and the roots add up to
+    # -c_1/c_0.  Roots of modulus 0.6 ... 1.4 around the unit circle, like a(z) of a signal.
+    rng = np.random.default_rng(n)
+    p = (rng.standard_normal(n + 1) + 1j * rng.standard_normal(n + 1)) * np.exp(-0.5 * rng.random(n + 1))
+    ret, roots = F.poly_roots_fasteigen(p)
+    assert ret == 0
+    z = roots.astype(np.clongdouble)
+    big = np.abs(z) > 1
+    w = np.where(big, 1 / z, z)
+    val = np.zeros(n, dtype=np.clongdouble)
+    bnd = np.zeros(n, dtype=np.longdouble)
+    for k in range(n + 1):
+        ck = np.where(big, p[n - k], p[k])
+        val = val * w + ck
+        bnd = bnd * np.abs(w) + np.abs(ck)
+    assert (np.abs(val) <= 16 * n * EPS * bnd).all()
+    assert abs(roots.sum() + p[1] / p[0]) <= 1e-9 * max(1.0, np.abs(roots).sum())
+    if n > 1:  # all distinct
+        srt = np.sort_complex(roots)
+        assert np.abs(np.diff(srt)).min() > 0
+
+
+def test_poly_roots_zero_leading_and_trailing_coefficients(F):
+    p = np.array([0, 0, 1.0, -3.0, 2.0, 0, 0], dtype=np.complex128)   # z^2 (z-1)(z-2), degree "6"
+    ret, roots = F.poly_roots_fasteigen(p)
+    assert ret == 0
+    nz = roots[np.abs(roots) > 0]
+    assert len(nz) == 2 and np.allclose(np.sort(nz.real), [1.0, 2.0], atol=1e-14) and np.abs(nz.imag).max() < 1e-14
+
+
+def test_nsev_default_options_and_fast_eigenvalue_vs_reference_runs(F, golden):
+    # fnft_nsev with the DEFAULT options (bsloc_SUBSAMPLE_AND_REFINE), including BASELINE config 1
+    # (examples/fnft_nsev_example.c as shipped), and bsloc_FAST_EIGENVALUE, against recorded runs
+    # of the reference (its Fortran root finder replaced by a LAPACK companion-matrix solve).
+    F.lib().fnft_errwarn_setprintf(None)
+    for case in _keys(golden, "refrun/defaults/"):
+        q = golden[f"refrun/defaults/{case}/q"]
+        T0, T1, M, X0, X1, disc, bsloc, dstype = golden[f"refrun/defaults/{case}/par"]
+        o = F.nsev_default_opts()
+        assert o.bound_state_localization == 2
+        o.discretization, o.bound_state_localization, o.discspec_type = int(disc), int(bsloc), int(dstype)
+        ret, cs, K, bs, nc = F.nsev(q, [T0, T1], int(M), [X0, X1], 1, o, K=2 * q.size)
+        assert ret == 0, case
+        rbs, rnc = golden[f"refrun/defaults/{case}/bs"], golden[f"refrun/defaults/{case}/nc"]
+        assert K == rbs.size, (case, K, bs[:K], rbs)
+        assert max(parity_contract(cs, golden[f"refrun/defaults/{case}/cs"])) < 1, case
+        idx = _match_sets(bs[:K], rbs)
+        # refined values: 1e-9 relative; raw polynomial roots (FAST_EIGENVALUE): limited by the
+        # conditioning of the roots of a(z), both root finders are backward stable only
+        # (the stand-in's dense QR is accurate to ~1e-7 only: checked separately below)
+        tol = 1e-9 if bsloc == 2 else 1e-6
+        scale = np.maximum(np.abs(rbs), 1.0) if case == "example" else np.abs(rbs)
+        assert (np.abs(bs[:K][idx] - rbs) <= tol * scale).all(), (case, bs[:K][idx] - rbs)
+        if bsloc == 0:
+            # FAST_EIGENVALUE returns roots of a(z): one Newton step in long double on the oracle's
+            # polynomial (pinned to the reference's) must not move them by more than 1e-12
+            eps_t = (T1 - T0) / (q.size - 1)
+            sch = O._NSE2AKNS[int(disc)]
+            tm, _, _ = O.nse_fscatter(q, eps_t, 1, int(disc))
+            z = np.exp(2j * bs[:K].astype(np.clongdouble) * eps_t / (O.akns_degree(sch) * O.akns_upsampling(sch)))
+            pv, dv = np.zeros(K, dtype=np.clongdouble), np.zeros(K, dtype=np.clongdouble)
+            for ck in tm[0].astype(np.clongdouble):
+                dv = dv * z + pv
+                pv = pv * z + ck
+            assert (np.abs(pv / dv) <= 1e-12 * np.abs(z)).all(), (case, np.abs(pv / dv))
+        nparts = 2 if dstype == 2 else 1
+        for part in range(nparts):
+            ours, ref = nc[part * K:(part + 1) * K][idx], rnc[part * K:(part + 1) * K]
+            assert (np.abs(ours - ref) <= (1e-9 if bsloc == 2 else 1e-5) * np.abs(ref)).all(), (case, part, ours, ref)
+
+
+def test_nsev_batch_default_options_matches_single_calls(F):
+    D, B = 512, 6
+    t = np.linspace(-10, 10, D)
+    amps = np.array([0.4, 1.3, 2.2, 2.7, 3.4, 1.8])
+    q = amps[:, None] / np.cosh(t)[None, :] * np.exp(0.3j * t)[None, :]
+    o = F.nsev_default_opts()
+    o.discspec_type = 2
+    ret, cs, K, bs, nc, rcs = F.nsev_batch(q, [-10, 10], 32, [-2, 2], 1, o, K=np.zeros(B), Kmax=16,
+                                           bound_states=np.zeros((B, 16), dtype=np.complex128))
+    assert ret == 0 and not rcs.any()
+    assert list(K) == [0, 1, 2, 3, 3, 2]      # sech amplitude A has floor(A + 1/2) bound states
+    for b in range(B):
+        r1, cs1, K1, bs1, nc1 = F.nsev(q[b], [-10, 10], 32, [-2, 2], 1, o, K=16)
+        assert r1 == 0 and K1 == K[b]
+        assert np.array_equal(bs1[:K1], bs[b, :K1]) and np.array_equal(cs1, cs[b])
+        assert np.array_equal(nc1[:2 * K1], nc[b, :2 * K1])
+        # eigenvalues of A sech(t) exp(i c t): -c/2 + i (A - k - 1/2)
+        want = -0.15 + 1j * (amps[b] - 0.5 - np.arange(K1))
+        assert K1 == 0 or np.abs(np.sort_complex(bs1[:K1]) - np.sort_complex(want)).max() < 5e-3
+
+
 def test_kdvv_default_options_vs_oracle(F):
     # fnft_kdvv(opts = NULL) uses 2SPLIT8B (degree 12, src/fnft_kdvv.c:34-36)
     D, M = 300, 64
