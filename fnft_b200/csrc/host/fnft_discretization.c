@@ -110,6 +110,11 @@ FNFT_UINT fnftb__nse_upsampling(fnft_nse_discretization_t d)
 {
     return ((int)d >= 0 && (int)d < NSE_COUNT) ? fnftb__akns_upsampling(nse_map[d]) : 0;
 }
+/* src/private/fnft__nse_discretization.c (method_order via the akns table, :158-198) */
+FNFT_UINT fnftb__nse_method_order(fnft_nse_discretization_t d)
+{
+    return ((int)d >= 0 && (int)d < NSE_COUNT) ? fnftb__akns_method_order(nse_map[d]) : 0;
+}
 FNFT_REAL fnftb__nse_boundary_coeff(fnft_nse_discretization_t d)
 {
     return ((int)d >= 0 && (int)d < NSE_COUNT) ? 0.5 : NAN;

@@ -54,6 +54,7 @@ FNFT_INT fnftb__kdv_to_akns(fnft_kdv_discretization_t d, fnft__akns_discretizati
 int fnftb__akns_on_gpu(fnft__akns_discretization_t d);
 FNFT_UINT fnftb__nse_degree(fnft_nse_discretization_t d);
 FNFT_UINT fnftb__nse_upsampling(fnft_nse_discretization_t d);
+FNFT_UINT fnftb__nse_method_order(fnft_nse_discretization_t d);
 FNFT_REAL fnftb__nse_boundary_coeff(fnft_nse_discretization_t d);
 FNFT_INT fnftb__nse_phase_factor_rho(FNFT_REAL eps_t, FNFT_REAL T1, FNFT_REAL *out,
                                      fnft_nse_discretization_t d);

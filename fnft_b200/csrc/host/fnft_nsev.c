@@ -86,12 +86,19 @@ static FNFT_INT nsev_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL
     return FNFT_SUCCESS;
 }
 
-FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
-                         FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
-                         FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
-                         FNFT_COMPLEX *const bound_states,
-                         FNFT_COMPLEX *const normconsts_or_residues, const FNFT_INT kappa,
-                         fnft_nsev_opts_t const *opts, FNFT_INT *const ret_codes)
+/*
+ * One pass of fnft_nsev over a batch: preprocessing + fnft_nsev_base (src/fnft_nsev.c:266-309,
+ * 458-565).  Dsub_req != 0 asks for the pass on the subsampled signals
+ * (nse_discretization_preprocess_signal with *Dsub_ptr = Dsub_req; second pass of the
+ * Richardson extrapolation, :374-391); the time window and step size follow (:382-384).
+ */
+static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
+                          FNFT_REAL const *const T_full, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                          FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
+                          FNFT_COMPLEX *const bound_states,
+                          FNFT_COMPLEX *const normconsts_or_residues, const FNFT_INT kappa,
+                          fnft_nsev_opts_t const *opts, FNFT_INT *const ret_codes,
+                          const FNFT_UINT Dsub_req, FNFT_REAL *const eps_t_pass)
 {
     FNFT_INT ret_code = FNFT_SUCCESS;
     int32_t *status = NULL;
@@ -103,7 +110,7 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
         return E_INVALID_ARGUMENT(D);
     if (q == NULL)
         return E_INVALID_ARGUMENT(q);
-    if (T == NULL || T[0] >= T[1])
+    if (T_full == NULL || T_full[0] >= T_full[1])
         return E_INVALID_ARGUMENT(T);
     if (contspec != NULL) {
         if (XI == NULL || XI[0] >= XI[1])
@@ -133,9 +140,6 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     if (!fnftb__akns_on_gpu(akns))
         return E_NOT_YET_IMPLEMENTED(opts->discretization,
                                      This splitting scheme has no GPU leaf kernel yet.);
-    if (opts->richardson_extrapolation_flag)
-        return E_NOT_YET_IMPLEMENTED(opts->richardson_extrapolation_flag,
-                                     Richardson extrapolation is not available in the GPU build.);
     if (upsampling > 2)
         return E_NOT_YET_IMPLEMENTED(opts->discretization, Unsupported upsampling factor.);
     if (upsampling == 2 && (D & (D - 1)) != 0)
@@ -154,8 +158,19 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
         return E_OTHER("No usable CUDA device: the fnft_b200 hot path has no CPU fallback.");
     const int devptr = fnftb__device_pointers();
 
-    const FNFT_REAL eps_t = (T[1] - T[0]) / (D - 1); /* src/fnft_nsev.c:237 */
-    const FNFT_UINT D_eff = D * upsampling;
+    const FNFT_REAL eps_t_full = (T_full[1] - T_full[0]) / (D - 1); /* src/fnft_nsev.c:237 */
+    /* subsampled pass: src/private/fnft__nse_discretization.c:424-431,623-625 */
+    FNFT_UINT D_given = D, nskip_pass = 1;
+    if (Dsub_req != 0) {
+        FNFT_UINT Dsub = Dsub_req < 2 ? 2 : (Dsub_req > D ? D : Dsub_req);
+        nskip_pass = (FNFT_UINT)round((FNFT_REAL)D / Dsub);
+        D_given = (FNFT_UINT)round((FNFT_REAL)D / nskip_pass);
+    }
+    const FNFT_REAL T[2] = {T_full[0], Dsub_req != 0 ? T_full[0] + ((D_given - 1) * nskip_pass) * eps_t_full : T_full[1]};
+    const FNFT_REAL eps_t = (Dsub_req != 0) ? (T[1] - T[0]) / (D_given - 1) : eps_t_full;
+    if (eps_t_pass != NULL)
+        *eps_t_pass = eps_t;
+    const FNFT_UINT D_eff = D_given * upsampling;
     const FNFT_UINT cs_len = want_contspec ? contspec_len(opts->contspec_type, M) : 0;
 
     size_t chunk = fnftb_max_chunk(ctx, D_eff, (int)deg0, want_contspec ? M : 0, 2,
@@ -165,7 +180,8 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     /* Continuous spectrum only, host buffers: overlap the host<->device copies of
      * neighbouring chunks with the kernels (fnftb_pipeline_*); at least 8 chunks for
      * large batches so that only a small first copy-in / last copy-out stay exposed. */
-    const int piped = (!devptr && want_contspec && !want_discspec && B >= 16 && fnftb__pipe_chunks() > 0);
+    const int piped = (!devptr && want_contspec && !want_discspec && B >= 16 && fnftb__pipe_chunks() > 0 &&
+                       Dsub_req == 0);
     if (piped) {
         const size_t nch = (size_t)fnftb__pipe_chunks();
         size_t c8 = (B + nch - 1) / nch;
@@ -202,7 +218,7 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     for (FNFT_UINT b0 = 0; b0 < B || prev_nb > 0; b0 += chunk) {
         const FNFT_UINT nb = (b0 >= B) ? 0 : ((B - b0 < chunk) ? (B - b0) : chunk);
         int32_t *st_cur = status ? status + (size_t)slot * chunk : NULL;
-        if (nb > 0 && want_discspec && bsloc == fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE) {
+        if (nb > 0 && want_discspec && bsloc == fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE && Dsub_req == 0) {
             /* First step of the mixed method (src/fnft_nsev.c:276-296): initial guesses from
              * the fast eigenvalue method on a subsampled signal. */
             FNFT_UINT Dsub = opts->Dsub;
@@ -218,13 +234,13 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
                 ret_code = E_DEVICE;
                 goto leave_fun;
             }
-            const int rc_sub = (upsampling == 2) ? fnftb_resample_4split4_sub(ctx, eps_t, nskip, Dsub, NULL)
+            const int rc_sub = (upsampling == 2) ? fnftb_resample_4split4_sub(ctx, eps_t_full, nskip, Dsub, NULL)
                                                  : fnftb_subsample(ctx, nskip, Dsub);
             if (rc_sub != 0) {
                 ret_code = E_DEVICE;
                 goto leave_fun;
             }
-            const FNFT_REAL Tsub[2] = {T[0], T[0] + ((Dsub - 1) * nskip) * eps_t}; /* :290-291 */
+            const FNFT_REAL Tsub[2] = {T[0], T[0] + ((Dsub - 1) * nskip) * eps_t_full}; /* :290-291 */
             ret_code = fnftb__nsev_fasteig_chunk(ctx, nb, Dsub * upsampling, Dsub, Tsub, kappa, 0, K + b0,
                                                  Kmax, bound_states + b0 * Kmax, opts);
             CHECK_RETCODE(ret_code, leave_fun);
@@ -236,9 +252,15 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
                 ret_code = E_DEVICE;
                 goto leave_fun;
             }
+            if (upsampling == 1 && Dsub_req != 0) {
+                if (fnftb_subsample(ctx, nskip_pass, D_given) != 0) {
+                    ret_code = E_DEVICE;
+                    goto leave_fun;
+                }
+            }
             if (upsampling == 2) {
                 int32_t *warn = devptr ? NULL : malloc(nb * sizeof(int32_t));
-                if (fnftb_resample_4split4(ctx, eps_t, warn) != 0) {
+                if (fnftb_resample_4split4_sub(ctx, eps_t_full, nskip_pass, D_given, warn) != 0) {
                     free(warn);
                     ret_code = E_DEVICE;
                     goto leave_fun;
@@ -261,7 +283,7 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
                     ret_code = E_DEVICE;
                     goto leave_fun;
                 }
-                ret_code = nsev_contspec_chunk(ctx, D, T, M, XI, opts, contspec + b0 * cs_len, devptr,
+                ret_code = nsev_contspec_chunk(ctx, D_given, T, M, XI, opts, contspec + b0 * cs_len, devptr,
                                                st_cur);
                 CHECK_RETCODE(ret_code, leave_fun);
             }
@@ -298,11 +320,11 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
         if (want_discspec) {
             const int fast = (bsloc == fnft_nsev_bsloc_FAST_EIGENVALUE);
             if (fast) { /* src/fnft_nsev.c:687-711; the transfer matrix of this chunk is reused */
-                ret_code = fnftb__nsev_fasteig_chunk(ctx, nb, D_eff, D, T, kappa, want_contspec, K + b0,
+                ret_code = fnftb__nsev_fasteig_chunk(ctx, nb, D_eff, D_given, T, kappa, want_contspec, K + b0,
                                                      Kmax, bound_states + b0 * Kmax, opts);
                 CHECK_RETCODE(ret_code, leave_fun);
             }
-            FNFT_INT rc2 = fnftb__nsev_discrete_chunk(ctx, nb, D_eff, D, T, eps_t, K + b0, Kmax,
+            FNFT_INT rc2 = fnftb__nsev_discrete_chunk(ctx, nb, D_eff, D_given, T, eps_t, K + b0, Kmax,
                                                       bound_states + b0 * Kmax,
                                                       normconsts_or_residues == NULL
                                                           ? NULL
@@ -324,6 +346,141 @@ leave_fun:
     if (piped)
         (void)fnftb_pipeline_end(ctx);
     free(status);
+    return ret_code;
+}
+
+FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
+                         FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                         FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
+                         FNFT_COMPLEX *const bound_states,
+                         FNFT_COMPLEX *const normconsts_or_residues, const FNFT_INT kappa,
+                         fnft_nsev_opts_t const *opts, FNFT_INT *const ret_codes)
+{
+    if (opts == NULL)
+        opts = &nsev_defaults;
+    if (opts->richardson_extrapolation_flag != 1)
+        return nsev_pass(B, D, q, T, M, contspec, XI, K, Kmax, bound_states, normconsts_or_residues, kappa,
+                         opts, ret_codes, 0, NULL);
+
+    /*
+     * Richardson extrapolation (src/fnft_nsev.c:250-263, 316-442): a second approximation from
+     * every other sample, bound states refined by Newton from the first pass's values, then
+     * (scl*first - second)/(scl - 1) with scl = (eps_t_sub/eps_t)^order.  The two passes run on
+     * the GPU; the O(M + K^2) combination is done here like in the reference.
+     */
+    FNFT_INT ret_code = FNFT_SUCCESS;
+    FNFT_COMPLEX *cs_sub = NULL, *bs_sub = NULL, *nc_sub = NULL, *nc_res = NULL;
+    FNFT_UINT *K_sub = NULL;
+    if (fnftb__device_pointers())
+        return E_NOT_YET_IMPLEMENTED(richardson_extrapolation_flag, Richardson extrapolation needs host buffers.);
+    const int want_cs = (contspec != NULL && M > 0);
+    const int want_ds = (kappa == +1 && bound_states != NULL);
+    const FNFT_UINT cs_len = want_cs ? contspec_len(opts->contspec_type, M) : 0;
+    if (want_cs && cs_len == 0)
+        return E_INVALID_ARGUMENT(opts->contspec_type);
+    fnft_nsev_opts_t o = *opts;
+    const fnft_nsev_dstype_t ds_type_opt = opts->discspec_type;
+    FNFT_COMPLEX *nc_main = normconsts_or_residues;
+    if (want_ds && normconsts_or_residues != NULL && ds_type_opt == fnft_nsev_dstype_RESIDUES) {
+        /* a' is extrapolated, so norming constants and residues are both needed (:252-262) */
+        o.discspec_type = fnft_nsev_dstype_BOTH;
+        nc_res = malloc(B * 2 * Kmax * sizeof(FNFT_COMPLEX));
+        if (nc_res == NULL)
+            return E_NOMEM;
+        nc_main = nc_res;
+    }
+    const FNFT_UINT nc_stride = (o.discspec_type == fnft_nsev_dstype_BOTH) ? 2 * Kmax : Kmax;
+    FNFT_REAL eps_t = 0, eps_t_sub = 0;
+    ret_code = nsev_pass(B, D, q, T, M, contspec, XI, K, Kmax, bound_states, nc_main, kappa, &o, ret_codes, 0,
+                         &eps_t);
+    CHECK_RETCODE(ret_code, leave_fun);
+
+    const FNFT_UINT method_order = fnftb__nse_method_order(opts->discretization);
+    if (method_order == 0) {
+        ret_code = E_INVALID_ARGUMENT(discretization);
+        goto leave_fun;
+    }
+    if (want_cs) {
+        cs_sub = malloc(B * cs_len * sizeof(FNFT_COMPLEX));
+        if (cs_sub == NULL) {
+            ret_code = E_NOMEM;
+            goto leave_fun;
+        }
+    }
+    int any_bs = 0;
+    if (want_ds) {
+        K_sub = malloc(B * sizeof(FNFT_UINT));
+        bs_sub = malloc(B * Kmax * sizeof(FNFT_COMPLEX));
+        nc_sub = (normconsts_or_residues != NULL) ? malloc(B * nc_stride * sizeof(FNFT_COMPLEX)) : NULL;
+        if (K_sub == NULL || bs_sub == NULL || (normconsts_or_residues != NULL && nc_sub == NULL)) {
+            ret_code = E_NOMEM;
+            goto leave_fun;
+        }
+        for (FNFT_UINT b = 0; b < B; b++) {
+            K_sub[b] = K[b];
+            any_bs |= (K[b] != 0);
+            memcpy(bs_sub + b * Kmax, bound_states + b * Kmax, K[b] * sizeof(FNFT_COMPLEX));
+        }
+    }
+    o.bound_state_localization = fnft_nsev_bsloc_NEWTON; /* :387-388 */
+    ret_code = nsev_pass(B, D, q, T, M, cs_sub, XI, (want_ds && any_bs) ? K_sub : NULL, Kmax,
+                         (want_ds && any_bs) ? bs_sub : NULL, (want_ds && any_bs) ? nc_sub : NULL, kappa, &o,
+                         NULL, D / 2 /* Dsub = CEIL(D/2) with the integer quotient, :374 */, &eps_t_sub);
+    CHECK_RETCODE(ret_code, leave_fun);
+
+    const FNFT_REAL scl_num = pow(eps_t_sub / eps_t, (FNFT_REAL)method_order);
+    const FNFT_REAL scl_den = scl_num - 1.0;
+    if (want_cs) { /* :398-407 */
+        const FNFT_REAL dxi = (XI[1] - XI[0]) / (M - 1);
+        for (FNFT_UINT b = 0; b < B; b++) {
+            FNFT_COMPLEX *c1 = contspec + b * cs_len;
+            FNFT_COMPLEX const *c2 = cs_sub + b * cs_len;
+            for (FNFT_UINT i = 0; i < M; i++)
+                if (fabs(XI[0] + dxi * i) < 0.9 * FNFT_PI / (2.0 * eps_t_sub))
+                    for (FNFT_UINT j = 0; j < cs_len; j += M)
+                        c1[i + j] = (scl_num * c1[i + j] - c2[i + j]) / scl_den;
+        }
+    }
+    if (want_ds && any_bs) { /* :409-441 */
+        for (FNFT_UINT b = 0; b < B; b++) {
+            const FNFT_UINT Kb = K[b], Ks = K_sub[b];
+            FNFT_COMPLEX *bs1 = bound_states + b * Kmax;
+            FNFT_COMPLEX const *bs2 = bs_sub + b * Kmax;
+            FNFT_COMPLEX *n1 = nc_main ? nc_main + b * nc_stride : NULL;
+            FNFT_COMPLEX *n2 = nc_sub ? nc_sub + b * nc_stride : NULL;
+            for (FNFT_UINT i = 0; i < Kb && Ks != 0; i++) {
+                FNFT_UINT loc = Ks;
+                FNFT_REAL thres = eps_t;
+                for (FNFT_UINT j = 0; j < Ks; j++) {
+                    const FNFT_REAL err = cabs(bs1[i] - bs2[j]) / cabs(bs1[i]);
+                    if (err < thres) {
+                        thres = err;
+                        loc = j;
+                    }
+                }
+                if (loc < Ks) {
+                    bs1[i] = (scl_num * bs1[i] - bs2[loc]) / scl_den;
+                    if (n1 != NULL && (ds_type_opt == fnft_nsev_dstype_RESIDUES ||
+                                       ds_type_opt == fnft_nsev_dstype_BOTH)) {
+                        /* a' = b / residue on both grids, Richardson step on a', new residue */
+                        n1[Kb + i] = n1[i] / n1[Kb + i];
+                        n2[Ks + loc] = n2[loc] / n2[Ks + loc];
+                        n1[Kb + i] = (scl_num * n1[Kb + i] - n2[loc + Ks]) / scl_den;
+                        n1[Kb + i] = n1[i] / n1[Kb + i];
+                    }
+                }
+            }
+            if (n1 != NULL && ds_type_opt == fnft_nsev_dstype_RESIDUES)
+                memcpy(normconsts_or_residues + b * Kmax, n1 + Kb, Kb * sizeof(FNFT_COMPLEX));
+        }
+    }
+
+leave_fun:
+    free(cs_sub);
+    free(bs_sub);
+    free(nc_sub);
+    free(nc_res);
+    free(K_sub);
     return ret_code;
 }
 

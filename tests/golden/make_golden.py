@@ -206,6 +206,34 @@ def main():
     bs_case("sech256_4split4b_sub", qs, [-10, 10], 16, [-2, 2], 21, 2)
     bs_case("sech256_2split2a_sub", qs, [-10, 10], 16, [-2, 2], 4, 2)
     bs_case("sech256_2split6b_fast", qs, [-10, 10], 16, [-2, 2], 15, 0)
+    # Richardson extrapolation (src/fnft_nsev.c:316-442)
+    def re_case(key, q, T, M, XI, disc, bsloc, dstype, cstype, guesses=None):
+        o = R.nsev_default_opts()
+        o.discretization, o.bound_state_localization, o.discspec_type = disc, bsloc, dstype
+        o.contspec_type, o.richardson_extrapolation_flag = cstype, 1
+        if guesses is None:
+            ret, cs, K, bs, nc = R.nsev(q, T, M, XI, 1, o, K=2 * len(q))
+        else:
+            ret, cs, K, bs, nc = R.nsev(q, T, M, XI, 1, o, K=len(guesses), bound_states=guesses)
+        assert ret == 0, (key, ret)
+        G[f"refrun/richardson/{key}/q"] = np.asarray(q, dtype=np.complex128)
+        G[f"refrun/richardson/{key}/par"] = np.array([T[0], T[1], M, XI[0], XI[1], disc, bsloc, dstype, cstype], dtype=np.float64)
+        G[f"refrun/richardson/{key}/guesses"] = np.zeros(0, dtype=np.complex128) if guesses is None else guesses
+        G[f"refrun/richardson/{key}/cs"] = cs
+        G[f"refrun/richardson/{key}/bs"] = bs[:K]
+        G[f"refrun/richardson/{key}/nc"] = nc[:2 * K if dstype == 2 else K]
+    gs = np.array([0.2j - 0.2, 1.2j - 0.21, 2.19j - 0.2])
+    for D in (256, 301):
+        tt = np.linspace(-10, 10, D)
+        qs = 2.7 / np.cosh(tt) * np.exp(0.4j * tt)
+        re_case(f"sech{D}_newton_both", qs, [-10, 10], 16, [-2, 2], 11, 1, 2, 2, gs)
+        re_case(f"sech{D}_newton_res", qs, [-10, 10], 16, [-2, 2], 11, 1, 1, 0, gs)
+        re_case(f"sech{D}_sub_nc", qs, [-10, 10], 16, [-2, 2], 11, 2, 0, 1)
+        re_case(f"sech{D}_sub_res", qs, [-10, 10], 16, [-2, 2], 11, 2, 1, 0)
+        re_case(f"sech{D}_2a_sub", qs, [-10, 10], 16, [-2, 2], 4, 2, 2, 2)
+    tt = np.linspace(-10, 10, 256)
+    qs = 2.7 / np.cosh(tt) * np.exp(0.4j * tt)
+    re_case("sech256_4split4b", qs, [-10, 10], 16, [-2, 2], 21, 1, 2, 2, gs)
     pr = rng.standard_normal(60) + 1j * rng.standard_normal(60)
     G["refrun/roots/p"] = pr
     ret = R.lib().fnft__poly_roots_fasteigen

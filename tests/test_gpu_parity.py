@@ -229,6 +229,40 @@ def test_nsev_default_options_and_fast_eigenvalue_vs_reference_runs(F, golden):
             assert (np.abs(ours - ref) <= (1e-9 if bsloc == 2 else 1e-5) * np.abs(ref)).all(), (case, part, ours, ref)
 
 
+def test_nsev_richardson_extrapolation_vs_reference_runs(F, golden):
+    # opts->richardson_extrapolation_flag = 1 (src/fnft_nsev.c:316-442): both passes on the GPU
+    F.lib().fnft_errwarn_setprintf(None)
+    for case in _keys(golden, "refrun/richardson/"):
+        q = golden[f"refrun/richardson/{case}/q"]
+        T0, T1, M, X0, X1, disc, bsloc, dstype, cstype = golden[f"refrun/richardson/{case}/par"]
+        g = golden[f"refrun/richardson/{case}/guesses"]
+        o = F.nsev_default_opts()
+        o.discretization, o.bound_state_localization, o.discspec_type = int(disc), int(bsloc), int(dstype)
+        o.contspec_type, o.richardson_extrapolation_flag = int(cstype), 1
+        if g.size:
+            ret, cs, K, bs, nc = F.nsev(q, [T0, T1], int(M), [X0, X1], 1, o, K=g.size, bound_states=g)
+        else:
+            ret, cs, K, bs, nc = F.nsev(q, [T0, T1], int(M), [X0, X1], 1, o, K=2 * q.size)
+        assert ret == 0, case
+        rbs, rnc, rcs = (golden[f"refrun/richardson/{case}/{k}"] for k in ("bs", "nc", "cs"))
+        assert K == rbs.size, (case, K, rbs)
+        n = int(M)
+        for part in range(rcs.size // n):
+            assert max(parity_contract(cs[part * n:(part + 1) * n], rcs[part * n:(part + 1) * n])) < 1, case
+        idx = _match_sets(bs[:K], rbs)
+        assert (np.abs(bs[:K][idx] - rbs) <= 1e-9 * np.abs(rbs)).all(), (case, bs[:K][idx] - rbs)
+        if case.endswith("_newton_res"):
+            # Reference bug: with bsloc_NEWTON + dstype_RESIDUES the first pass writes norming
+            # constants AND residues into the caller's array instead of the reserve array
+            # (src/fnft_nsev.c:311-312 vs :304-305), and the result is copied from the never
+            # initialised reserve array (:438).  Expected values: the residues of the BOTH run.
+            rK = rbs.size
+            rnc = golden[f"refrun/richardson/{case[:-4]}_both/nc"][rK:2 * rK]
+        for part in range(2 if dstype == 2 else 1):
+            ours, ref = nc[part * K:(part + 1) * K][idx], rnc[part * K:(part + 1) * K]
+            assert (np.abs(ours - ref) <= 1e-9 * np.abs(ref)).all(), (case, part, ours, ref)
+
+
 def test_nsev_batch_default_options_matches_single_calls(F):
     D, B = 512, 6
     t = np.linspace(-10, 10, D)
