@@ -149,6 +149,8 @@ struct fnftb_ctx {
     Buf fpoly, vals, roots, nraw, nkept;
     // root-finder workspace
     Buf rt_roots, rt_absc, rt_lg, rt_hull, rt_info;
+    // general-length resampling workspace
+    Buf rs_a, rs_b;
     int have_box3 = 0;
     // pipelined host transfers (fnftb_pipeline_begin): two slots, copy streams, events
     int pipe_on = 0, slot = 0;
@@ -285,7 +287,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
                   &c->status, &c->tm, &c->tt0, &c->tt1, &c->twmem, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept,
-                  &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info,
+                  &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info, &c->rs_a, &c->rs_b,
                   &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1]};
     for (Buf *b : all)
         release(*b);
@@ -957,6 +959,88 @@ int fnftb_subsample(fnftb_ctx *c, size_t nskip, size_t Dsub)
     return 0;
 }
 
+// 4SPLIT4 preprocessing for any number of samples: length-D DFTs as chirp-z transforms
+// (resample_kernels.cuh, second half)
+static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host)
+{
+    const size_t B = c->B, D = c->D;
+    if (2 * D > ((size_t)1 << 24))
+        return fail(-6, "signal too long for the GPU resampling step", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure(c->rs_a, B * 2 * D * sizeof(cplx)));
+    RC(ensure(c->rs_b, B * 2 * D * sizeof(cplx)));
+    RC(ensure(c->qpre, B * 2 * Dsub * sizeof(cplx)));
+    RC(ensure(c->warn, B * sizeof(int)));
+    RC(ensure(c->status, B * sizeof(int)));
+    const CzGeom g = cz_geometry((int)D - 1, (int)D);
+    RC(ensure(c->ybuf, cz_ybuf_elems(g, B, 2) * sizeof(cplx)));
+    RC(ensure(c->vhat, (size_t)g.L * sizeof(cplx)));
+    RC(ensure(c->cztab, cz_table_elems(g, (int)D - 1, (int)D) * sizeof(cplx)));
+    RsArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.B = (int)B;
+    ra.D = (int)D;
+    ra.nskip = (int)nskip;
+    ra.Dsub = (int)Dsub;
+    ra.eps_t = eps_t;
+    ra.warn = (int *)c->warn.p;
+    const long long tot = (long long)B * (long long)D;
+    // 1. q reversed -> rs_a[B][D]
+    ra.in = c->q;
+    ra.out = (cplx *)c->rs_a.p;
+    RC((launch_blocks<RsArgs, blk_rs_reverse>(ra, (unsigned)((tot + 255) / 256), 256, 0, c->st, "resample_reverse")));
+    // 2. X = DFT_D(q) -> rs_b[B][D]
+    CzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tm = (const cplx *)c->rs_a.p;
+    a.tm_sstride = D;
+    a.ent[0] = 0;
+    a.ent[1] = 0;
+    a.npoly = 1;
+    a.deg = (int)D - 1;
+    a.B = (int)B;
+    a.M = (int)D;
+    a.lwr = 0.0;
+    a.lwi = -2.0 * 3.14159265358979323846 / (double)D;  // W = exp(-2 pi i / D), A = 1
+    a.ybuf = (cplx *)c->ybuf.p;
+    a.vhat = (cplx *)c->vhat.p;
+    a.T = ctx_tw(c);
+    a.mode = FNFTB_CZ_RAW;
+    a.out = (cplx *)c->rs_b.p;
+    a.out_sstride = D;
+    a.status = (int *)c->status.p;
+    RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+    // 3. band-limit check, the two phase ramps -> rs_a[B][2][D] (reversed)
+    ra.in = (const cplx *)c->rs_b.p;
+    ra.out = (cplx *)c->rs_a.p;
+    RC((launch_blocks<RsArgs, blk_rs_shift>(ra, (unsigned)B, 256, 3 * 256 * sizeof(double), c->st, "resample_shift")));
+    // 4. the two inverse DFTs (unnormalised) -> rs_b[B][2][D]
+    a.tm = (const cplx *)c->rs_a.p;
+    a.tm_sstride = 2 * D;
+    a.ent[0] = 0;
+    a.ent[1] = 1;
+    a.npoly = 2;
+    a.lwi = 2.0 * 3.14159265358979323846 / (double)D;
+    a.out = (cplx *)c->rs_b.p;
+    a.out_sstride = 2 * D;
+    a.out_jstride = D;
+    RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+    // 5. weights + subsampling -> qpre[B][2*Dsub]
+    ra.in = (const cplx *)c->rs_b.p;
+    ra.out = (cplx *)c->qpre.p;
+    const long long tot2 = (long long)B * (long long)Dsub;
+    RC((launch_blocks<RsArgs, blk_rs_weights>(ra, (unsigned)((tot2 + 255) / 256), 256, 0, c->st, "resample_weights")));
+    c->q = (const cplx *)c->qpre.p;
+    c->r = nullptr;
+    c->D = 2 * Dsub;
+    c->have_box3 = 0;
+    if (warn_host) {
+        CU(cudaMemcpyAsync(warn_host, c->warn.p, B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    return 0;
+}
+
 int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host)
 {
     if (!c || !c->q)
@@ -964,9 +1048,10 @@ int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t 
     if (nskip < 1 || Dsub < 1 || (Dsub - 1) * nskip >= c->D)
         return fail(-2, "invalid subsampling", __FILE__, __LINE__);
     const size_t D = c->D;
-    if ((D & (D - 1)) != 0 || D < 4 || D > 4096)
-        return fail(-6, "GPU resampling needs a power-of-two number of samples between 4 and 4096",
-                    __FILE__, __LINE__);
+    if (D < 4)
+        return fail(-6, "resampling needs at least 4 samples", __FILE__, __LINE__);
+    if ((D & (D - 1)) != 0 || D > 4096)
+        return resample_general(c, eps_t, nskip, Dsub, warn_host);
     CU(cudaSetDevice(c->device));
     RC(ensure(c->qpre, c->B * 2 * Dsub * sizeof(cplx)));
     RC(ensure(c->warn, c->B * sizeof(int)));

@@ -132,3 +132,106 @@ BLK void blk_subsample(const SubsampleArgs &a, blk3 bid, int nt, void * /*smem*/
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// General lengths (any D >= 4, not limited by shared memory): the length-D transforms are
+// evaluated as chirp-z transforms with the batched Bluestein machinery of chirpz_driver.cuh
+// (X_k = sum_n q_n w^(nk) is the polynomial sum_n q_n z^n at z = w^k), so the arithmetic is
+// again power-of-two FFTs while the result is the length-D DFT the reference computes with
+// Kiss FFT's mixed radices (fnft__misc.c:358-397).  Kernels around the two chirp-z calls:
+//   blk_rs_reverse : coefficients highest power first, as the chirp-z kernels read them
+//   blk_rs_shift   : band-limitation check (:368-380) and the two phase ramps (:382-392)
+//   blk_rs_weights : 1/D, Gauss weights, subsampling (fnft__nse_discretization.c:483-500)
+// ---------------------------------------------------------------------------------------------
+struct RsArgs {
+    const cplx *in;
+    cplx *out;
+    int *warn;
+    int B, D, nskip, Dsub;
+    double eps_t;
+};
+
+BLK void blk_rs_reverse(const RsArgs &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        if (gid < (long long)a.B * a.D) {
+            const int s = (int)(gid / a.D), i = (int)(gid % a.D);
+            a.out[gid] = a.in[(size_t)s * a.D + (size_t)(a.D - 1 - i)];
+        }
+    }
+}
+
+// in: X [B][D] (natural order); out: [B][2][D], entry j = spectrum shifted by -/+ delta, stored
+// reversed (highest "power" first) for the inverse chirp-z.  One CTA per signal.
+BLK void blk_rs_shift(const RsArgs &a, blk3 bid, int nt, void *smem)
+{
+    const int D = a.D, s = bid.x;
+    double *red = (double *)smem;
+    const cplx *X = a.in + (size_t)s * D;
+    cplx *Y = a.out + (size_t)s * 2 * D;
+    const int Dlp = D / 20;
+    FOR_THREADS(tid, nt)
+    {
+        double lo = 0.0, hi = 0.0, all = 0.0;
+        const double scl = (double)D * a.eps_t;
+        const double delta = a.eps_t * (1.7320508075688772 / 6.0) * (double)a.nskip;
+        for (int k = tid; k < D; k += nt) {
+            const cplx x = X[k];
+            const double m2 = cabs2(x);
+            all += ((k == 0 || k == D - 1) ? 0.5 : 1.0) * m2;
+            if (Dlp >= 2) {
+                const int j1 = k - (D / 2 - 1 - Dlp);
+                if (j1 >= 0 && j1 < Dlp)
+                    lo += ((j1 == 0 || j1 == Dlp - 1) ? 0.5 : 1.0) * m2;
+                const int j2 = k - (D / 2 + 1);
+                if (j2 >= 0 && j2 < Dlp)
+                    hi += ((j2 == 0 || j2 == Dlp - 1) ? 0.5 : 1.0) * m2;
+            }
+            const double freq = (k < D / 2) ? (double)k / scl : ((double)k - (double)D) / scl;
+            double sn, cs;
+            SINCOS(2.0 * 3.141592653589793 * delta * freq, &sn, &cs);
+            Y[D - 1 - k] = cmul(x, make_cplx(cs, -sn));      // shift by -delta
+            Y[D + D - 1 - k] = cmul(x, make_cplx(cs, sn));   // shift by +delta
+        }
+        red[tid] = lo;
+        red[nt + tid] = hi;
+        red[2 * nt + tid] = all;
+    }
+    BLOCK_SYNC();
+    FOR_THREADS(tid, nt)
+    {
+        if (tid == 0) {
+            double lo = 0.0, hi = 0.0, all = 0.0;
+            for (int t = 0; t < nt; ++t) {
+                lo += red[t];
+                hi += red[nt + t];
+                all += red[2 * nt + t];
+            }
+            const double ratio = sqrt(lo + hi) / sqrt(all);
+            a.warn[s] = (Dlp >= 2 && ratio > 1.4901161193847656e-08 /* sqrt(eps) */) ? 1 : 0;
+        }
+    }
+}
+
+// in: [B][2][D] unnormalised inverse transforms; out: [B][2*Dsub]
+BLK void blk_rs_weights(const RsArgs &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        if (gid < (long long)a.B * a.Dsub) {
+            const int s = (int)(gid / a.Dsub), isub = (int)(gid % a.Dsub);
+            const int i = isub * a.nskip;
+            const double sf = 1.7320508075688772 / 6.0;
+            const double w0 = 0.25 + sf, w1 = 0.25 - sf;
+            const double invD = 1.0 / (double)a.D;
+            const cplx q1 = cscale(a.in[(size_t)s * 2 * a.D + i], invD);
+            const cplx q2 = cscale(a.in[(size_t)s * 2 * a.D + a.D + i], invD);
+            cplx *o = a.out + (size_t)s * 2 * a.Dsub + 2 * (size_t)isub;
+            o[0] = make_cplx(w0 * q1.x + w1 * q2.x, w0 * q1.y + w1 * q2.y);
+            o[1] = make_cplx(w1 * q1.x + w0 * q2.x, w1 * q1.y + w0 * q2.y);
+        }
+    }
+}

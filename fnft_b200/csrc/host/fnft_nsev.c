@@ -142,8 +142,6 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                                      This splitting scheme has no GPU leaf kernel yet.);
     if (upsampling > 2)
         return E_NOT_YET_IMPLEMENTED(opts->discretization, Unsupported upsampling factor.);
-    if (upsampling == 2 && (D & (D - 1)) != 0)
-        return E_NOT_YET_IMPLEMENTED(D, The GPU resampling step of the 4SPLIT4 schemes needs a power-of-two number of samples.);
     const int want_contspec = (contspec != NULL && M > 0);
     const int want_discspec = (kappa == +1 && bound_states != NULL);
     const fnft_nsev_bsloc_t bsloc = opts->bound_state_localization;

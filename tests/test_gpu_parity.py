@@ -478,6 +478,24 @@ def test_nsev_4split4b_vs_oracle(F):
     assert ret == 0 and max(parity_contract(cs, ref)) < 1
 
 
+@pytest.mark.parametrize("disc", [21, 20])
+@pytest.mark.parametrize("D", [37, 300, 4100, 8192])
+def test_nsev_4split4_any_number_of_samples_vs_oracle(F, disc, D):
+    # the band-limited resampling of the 4SPLIT4 schemes (misc_resample, a length-D FFT in the
+    # reference) for lengths that are not powers of two / do not fit shared memory
+    F.lib().fnft_errwarn_setprintf(None)
+    T, XI, M = [-12.0, 12.0], [-3.0, 2.5], 48
+    q = sech_chirp(D, T, amp=1.9, chirp=0.15)
+    o = F.nsev_default_opts()
+    o.discretization = disc
+    o.contspec_type = F.CSTYPE_BOTH
+    ret, cs, *_ = F.nsev(q, T, M, XI, 1, o)
+    assert ret == 0
+    ref = O.nsev_contspec(q, T, M, XI, 1, disc, cstype=2)
+    for part in range(3):
+        assert max(parity_contract(cs[part * M:(part + 1) * M], ref[part * M:(part + 1) * M])) < 1
+
+
 def test_kdvv_vs_oracle_config4_shape(F):
     # BASELINE config 4 shape at a size the oracle finishes in seconds
     D = M = 8192
