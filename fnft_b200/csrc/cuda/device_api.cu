@@ -8,6 +8,7 @@
 #include "chirpz2.cuh"
 #include "nsep_kernels.cuh"
 #include "poly_roots.cuh"
+#include "nsep_refine.cuh"
 #include "resample_kernels.cuh"
 #include "tree_driver.cuh"
 #include "twiddle.h"
@@ -151,6 +152,10 @@ struct fnftb_ctx {
     Buf rt_roots, rt_absc, rt_lg, rt_hull, rt_info;
     // general-length resampling workspace
     Buf rs_a, rs_b;
+    // separate homes for the de-rotated (nsep) and the subsampled signals, and saved selections
+    Buf qrot, qsub;
+    const cplx *saved_q[2] = {nullptr, nullptr}, *saved_r[2] = {nullptr, nullptr};
+    size_t saved_D[2] = {0, 0};
     int have_box3 = 0;
     // pipelined host transfers (fnftb_pipeline_begin): two slots, copy streams, events
     int pipe_on = 0, slot = 0;
@@ -287,7 +292,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
                   &c->status, &c->tm, &c->tt0, &c->tt1, &c->twmem, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept,
-                  &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info, &c->rs_a, &c->rs_b,
+                  &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info, &c->rs_a, &c->rs_b, &c->qrot, &c->qsub,
                   &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1]};
     for (Buf *b : all)
         release(*b);
@@ -724,10 +729,10 @@ int fnftb_nsep_derotate(fnftb_ctx *c, double lam_shift, double T0, double eps_t)
     if (!c || !c->q)
         return fail(-2, "no signals staged", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
-    RC(ensure(c->qpre, c->B * c->D * sizeof(cplx)));
+    RC(ensure(c->qrot, c->B * c->D * sizeof(cplx)));  // (not qpre: the resampling step writes there)
     DerotArgs da;
     da.q = c->q;
-    da.out = (cplx *)c->qpre.p;
+    da.out = (cplx *)c->qrot.p;
     da.B = (int)c->B;
     da.D = (int)c->D;
     da.lam_shift = lam_shift;
@@ -736,7 +741,98 @@ int fnftb_nsep_derotate(fnftb_ctx *c, double lam_shift, double T0, double eps_t)
     const long long tot = (long long)c->B * c->D;
     RC((launch_blocks<DerotArgs, blk_nsep_derotate>(da, (unsigned)((tot + 255) / 256), 256, 0, c->st,
                                                      "nsep_derotate")));
-    c->q = (const cplx *)c->qpre.p;
+    c->q = (const cplx *)c->qrot.p;
+    return 0;
+}
+
+int fnftb_signals_save(fnftb_ctx *c, int slot)
+{
+    if (!c || !c->q || slot < 0 || slot > 1)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    c->saved_q[slot] = c->q;
+    c->saved_r[slot] = c->r;
+    c->saved_D[slot] = c->D;
+    return 0;
+}
+
+int fnftb_signals_restore(fnftb_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot > 1 || !c->saved_q[slot])
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    c->q = c->saved_q[slot];
+    c->r = c->saved_r[slot];
+    c->D = c->saved_D[slot];
+    c->have_box3 = 0;
+    return 0;
+}
+
+static int roots_run(fnftb_ctx *c, const cplx *coef, long long cstride, size_t B, size_t n, void *roots_host,
+                     int32_t *info_host);
+
+int fnftb_nsep_floquet_roots(fnftb_ctx *c, double rhs, void *roots_host, int32_t *info_host)
+{
+    if (!c || !roots_host || c->tmB == 0 || c->deg < 2 || c->tm_entries != 4)
+        return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ctx_finalize(c));
+    const size_t B = c->tmB, d1 = c->deg + 1;
+    RC(ensure(c->fpoly, B * 2 * d1 * sizeof(cplx)));
+    FloquetRhsArgs fa;
+    fa.tm = (const cplx *)c->tm.p;
+    fa.W = (const int *)c->W.p;
+    fa.P = (cplx *)c->fpoly.p;
+    fa.B = (int)B;
+    fa.deg = (int)c->deg;
+    fa.rhs = rhs;
+    const long long tot = (long long)B * (long long)d1;
+    k_nsep_floquet_rhs<<<(unsigned)((tot + 255) / 256), 256, 0, c->st>>>(fa);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    return roots_run(c, (const cplx *)c->fpoly.p, (long long)d1, B, c->deg, roots_host, info_host);
+}
+
+int fnftb_nsep_refine(fnftb_ctx *c, const fnftb_refine_desc *d, const int32_t *K_host, void *lam_host,
+                      int32_t *flag_host)
+{
+    if (!c || !d || !c->q || !K_host || !lam_host || d->Kstride < 1 || (d->upsampling != 1 && d->upsampling != 2))
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->B * (size_t)d->Kstride;
+    RC(ensure(c->lam, n * sizeof(cplx)));
+    RC(ensure(c->kcnt, c->B * sizeof(int)));
+    RC(ensure(c->flag, n * sizeof(int)));
+    CU(cudaMemcpyAsync(c->lam.p, lam_host, n * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->kcnt.p, K_host, c->B * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemsetAsync(c->flag.p, 0, n * sizeof(int), c->st));
+    NsepRefineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = c->q;
+    a.B = (int)c->B;
+    a.D = (int)c->D;
+    a.upsampling = d->upsampling;
+    a.kappa = d->kappa;
+    a.Kstride = d->Kstride;
+    a.K = (const int *)c->kcnt.p;
+    a.lam = (cplx *)c->lam.p;
+    a.flag = (int *)c->flag.p;
+    a.eps_t = d->eps_t;
+    a.lweight = (d->upsampling == 2) ? 0.5 : 1.0;  // sum of the CF4_2 weights of a node
+    a.scl = (d->upsampling == 2) ? 0.5 : 1.0;      // fnft__akns_scatter_matrix.c:113,121
+    a.rhs = d->rhs;
+    a.tol = d->tol;
+    a.max_evals = d->max_evals;
+    a.mode = d->mode;
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin("nsep_refine", c->st);
+    k_nsep_refine<<<(unsigned)((n + 3) / 4), 128, 0, c->st>>>(a);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(c->st);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(lam_host, c->lam.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    if (flag_host)
+        CU(cudaMemcpyAsync(flag_host, c->flag.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
     return 0;
 }
 
@@ -941,10 +1037,10 @@ int fnftb_subsample(fnftb_ctx *c, size_t nskip, size_t Dsub)
     if (nskip < 1 || Dsub < 1 || (Dsub - 1) * nskip >= c->D)
         return fail(-2, "invalid subsampling", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
-    RC(ensure(c->qpre, c->B * Dsub * sizeof(cplx)));
+    RC(ensure(c->qsub, c->B * Dsub * sizeof(cplx)));
     SubsampleArgs sa;
     sa.q = c->q;
-    sa.out = (cplx *)c->qpre.p;
+    sa.out = (cplx *)c->qsub.p;
     sa.B = (int)c->B;
     sa.D = (int)c->D;
     sa.nskip = (int)nskip;
@@ -952,7 +1048,7 @@ int fnftb_subsample(fnftb_ctx *c, size_t nskip, size_t Dsub)
     const long long total = (long long)c->B * (long long)Dsub;
     RC((launch_blocks<SubsampleArgs, blk_subsample>(sa, (unsigned)((total + 255) / 256), 256, 0, c->st,
                                                     "subsample")));
-    c->q = (const cplx *)c->qpre.p;
+    c->q = (const cplx *)c->qsub.p;
     c->r = nullptr;
     c->D = Dsub;
     c->have_box3 = 0;
@@ -969,7 +1065,8 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     CU(cudaSetDevice(c->device));
     RC(ensure(c->rs_a, B * 2 * D * sizeof(cplx)));
     RC(ensure(c->rs_b, B * 2 * D * sizeof(cplx)));
-    RC(ensure(c->qpre, B * 2 * Dsub * sizeof(cplx)));
+    Buf &dstbuf = (nskip > 1) ? c->qsub : c->qpre;  // a subsampled copy never replaces the full one
+    RC(ensure(dstbuf, B * 2 * Dsub * sizeof(cplx)));
     RC(ensure(c->warn, B * sizeof(int)));
     RC(ensure(c->status, B * sizeof(int)));
     const CzGeom g = cz_geometry((int)D - 1, (int)D);
@@ -1027,10 +1124,10 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     RC(cz_run(a, (cplx *)c->cztab.p, c->st));
     // 5. weights + subsampling -> qpre[B][2*Dsub]
     ra.in = (const cplx *)c->rs_b.p;
-    ra.out = (cplx *)c->qpre.p;
+    ra.out = (cplx *)dstbuf.p;
     const long long tot2 = (long long)B * (long long)Dsub;
     RC((launch_blocks<RsArgs, blk_rs_weights>(ra, (unsigned)((tot2 + 255) / 256), 256, 0, c->st, "resample_weights")));
-    c->q = (const cplx *)c->qpre.p;
+    c->q = (const cplx *)dstbuf.p;
     c->r = nullptr;
     c->D = 2 * Dsub;
     c->have_box3 = 0;
@@ -1053,12 +1150,13 @@ int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t 
     if ((D & (D - 1)) != 0 || D > 4096)
         return resample_general(c, eps_t, nskip, Dsub, warn_host);
     CU(cudaSetDevice(c->device));
-    RC(ensure(c->qpre, c->B * 2 * Dsub * sizeof(cplx)));
+    Buf &dstbuf = (nskip > 1) ? c->qsub : c->qpre;  // a subsampled copy never replaces the full one
+    RC(ensure(dstbuf, c->B * 2 * Dsub * sizeof(cplx)));
     RC(ensure(c->warn, c->B * sizeof(int)));
     ResampleArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.q = c->q;
-    ra.out = (cplx *)c->qpre.p;
+    ra.out = (cplx *)dstbuf.p;
     ra.warn = (int *)c->warn.p;
     ra.B = (int)c->B;
     ra.D = (int)D;
@@ -1070,7 +1168,7 @@ int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t 
     const int nt = 256;
     RC((launch_blocks<ResampleArgs, blk_resample_4split4>(ra, (unsigned)c->B, nt,
                                                           resample_smem_bytes((int)D, nt), c->st, "resample_4split4")));
-    c->q = (const cplx *)c->qpre.p;
+    c->q = (const cplx *)dstbuf.p;
     c->r = nullptr;
     c->D = 2 * Dsub;
     c->have_box3 = 0;
@@ -1084,21 +1182,17 @@ int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t 
 // ---------------------------------------------------------------------------
 // polynomial roots (poly_roots.cuh)
 // ---------------------------------------------------------------------------
-int fnftb_poly_roots(fnftb_ctx *c, int ent, void *roots_host, int32_t *info_host)
+static int roots_run(fnftb_ctx *c, const cplx *coef, long long cstride, size_t B, size_t n, void *roots_host,
+                     int32_t *info_host)
 {
-    if (!c || !roots_host || c->tmB == 0 || c->deg < 1 || ent < 0 || ent >= (int)c->tm_entries)
-        return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
-    CU(cudaSetDevice(c->device));
-    RC(ctx_finalize(c));
-    const size_t B = c->tmB, n = c->deg;
     RC(ensure(c->rt_roots, B * n * sizeof(cplx)));
     RC(ensure(c->rt_absc, B * (n + 1) * sizeof(double)));
     RC(ensure(c->rt_lg, B * (n + 1) * sizeof(double)));
     RC(ensure(c->rt_hull, B * (n + 2) * sizeof(int)));
     RC(ensure(c->rt_info, B * 4 * sizeof(int)));
     RootsArgs ra;
-    ra.coef = (const cplx *)c->tm.p + (size_t)ent * (n + 1);
-    ra.cstride = (long long)(c->tm_entries * (n + 1));
+    ra.coef = coef;
+    ra.cstride = cstride;
     ra.n = (int)n;
     ra.roots = (cplx *)c->rt_roots.p;
     ra.absc = (double *)c->rt_absc.p;
@@ -1121,6 +1215,17 @@ int fnftb_poly_roots(fnftb_ctx *c, int ent, void *roots_host, int32_t *info_host
         CU(cudaMemcpyAsync(info_host, c->rt_info.p, B * 4 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     return 0;
+}
+
+int fnftb_poly_roots(fnftb_ctx *c, int ent, void *roots_host, int32_t *info_host)
+{
+    if (!c || !roots_host || c->tmB == 0 || c->deg < 1 || ent < 0 || ent >= (int)c->tm_entries)
+        return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ctx_finalize(c));
+    const size_t n = c->deg;
+    return roots_run(c, (const cplx *)c->tm.p + (size_t)ent * (n + 1), (long long)(c->tm_entries * (n + 1)),
+                     c->tmB, n, roots_host, info_host);
 }
 
 // ---------------------------------------------------------------------------

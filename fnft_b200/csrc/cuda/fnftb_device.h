@@ -148,6 +148,28 @@ size_t fnftb_nsep_chunk(const fnftb_ctx *ctx, size_t D_eff, int deg0, size_t bud
 int fnftb_nsep_gridsearch(fnftb_ctx *ctx, const fnftb_nsep_desc *desc, uint64_t *K_host,
                           void *main_host, uint64_t *M_host, void *aux_host, int32_t *status_host);
 
+/* Remember / re-select the currently staged signals (pointer + length; slot 0 or 1), so that
+ * a subsampled copy can be scattered in between (fnft_nsep subsample-and-refine). */
+int fnftb_signals_save(fnftb_ctx *ctx, int slot);
+int fnftb_signals_restore(fnftb_ctx *ctx, int slot);
+
+/* Roots of the Floquet polynomial a(z) + a#(z) - rhs*2^-W of every transfer matrix held
+ * (src/fnft_nsep.c:561-586).  roots_host: [B][deg]; info_host as for fnftb_poly_roots. */
+int fnftb_nsep_floquet_roots(fnftb_ctx *ctx, double rhs, void *roots_host, int32_t *info_host);
+
+/* Newton refinement of main (mode 0: trace + rhs) or auxiliary (mode 1: b) spectrum points on
+ * the staged signals, src/fnft_nsep.c:708-835.  lam_host: [B][Kstride] in/out. */
+typedef struct {
+    int upsampling;   /* 1: BO, 2: CF4_2 */
+    int kappa;
+    int Kstride;
+    int mode;
+    int max_evals;
+    double eps_t, rhs, tol;
+} fnftb_refine_desc;
+int fnftb_nsep_refine(fnftb_ctx *ctx, const fnftb_refine_desc *desc, const int32_t *K_host,
+                      void *lam_host, int32_t *flag_host);
+
 /* ---- bound states (Newton on the BO / CF4_2 recurrence) ------------------------ */
 typedef struct {
     int upsampling;   /* 1: BO, 2: CF4_2 */

@@ -8,11 +8,15 @@
  * Floquet polynomials and the three grid searches (:319-326,355-360,400), coordinate
  * transform + filtering (:335-345) and the truncation warnings (:347-353,377-386).
  *
- * Only fnft_nsep_loc_GRIDSEARCH runs here.  SUBSAMPLE_AND_REFINE and MIXED (the
- * reference default) need the eiscor root finder and the slow scattering with
- * derivatives and return FNFT_EC_NOT_YET_IMPLEMENTED.
+ * fnft_nsep_loc_SUBSAMPLE_AND_REFINE and fnft_nsep_loc_MIXED (the reference default) mirror
+ * subsample_and_refine (:441-706): the roots of the Floquet polynomials of a subsampled signal
+ * come from the GPU root finder (poly_roots.cuh, in place of eiscor), refine_mainspec /
+ * refine_auxspec (:708-835) run as one-warp-per-point kernels on the full signal
+ * (nsep_refine.cuh); the order-dependent filtering and the assembly of the user arrays stay
+ * on the host like in the reference.
  */
 #include "fnft_internal.h"
+#include "fnft_nsev_discrete.h"
 
 static const fnft_nsep_opts_t nsep_defaults = {
     .localization = fnft_nsep_loc_MIXED,
@@ -28,6 +32,219 @@ static const fnft_nsep_opts_t nsep_defaults = {
 
 fnft_nsep_opts_t fnft_nsep_default_opts(void) { return nsep_defaults; }
 
+/* src/private/fnft__misc.c:205-226 */
+static void filter_nonreal(FNFT_UINT *N, FNFT_COMPLEX *vals, FNFT_REAL tol_im)
+{
+    FNFT_UINT kept = 0;
+    for (FNFT_UINT i = 0; i < *N; i++) {
+        if (!(fabs(cimag(vals[i])) > tol_im))
+            continue;
+        vals[kept++] = vals[i];
+    }
+    *N = kept;
+}
+
+/*
+ * subsample_and_refine (src/fnft_nsep.c:441-706) for the nb signals of a chunk.  On entry the
+ * de-rotated signals are saved in slot 1 of the context and the fully preprocessed ones in
+ * slot 0.  main_out / aux_out: host rows of stride Kmax / Mmax (NULL = not wanted); K1 / M1
+ * receive the numbers of points written.  box: bounding box (MANUAL: already shifted; AUTO:
+ * recomputed here from the subsampled step size, :548 and returned).
+ */
+static FNFT_INT nsep_subsample_refine_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D, FNFT_UINT upsampling,
+                                            FNFT_UINT deg0, fnft__akns_discretization_t akns,
+                                            FNFT_REAL eps_t, FNFT_INT kappa, fnft_nsep_opts_t const *opts,
+                                            FNFT_REAL *box, int skip_real, FNFT_COMPLEX *main_out,
+                                            FNFT_UINT Kmax, FNFT_UINT *K1, FNFT_COMPLEX *aux_out,
+                                            FNFT_UINT Mmax, FNFT_UINT *M1, FNFT_REAL Lam_shift,
+                                            int *warned, FNFT_INT *ret_codes)
+{
+    FNFT_INT ret_code = FNFT_SUCCESS;
+    FNFT_COMPLEX *roots = NULL;
+    int32_t *info = NULL, *Kn = NULL, *flag = NULL;
+    char *full = NULL;
+
+    /* number of samples of the subsampled signal, :485-497 and the clamps / rounding of
+     * nse_discretization_preprocess_signal (fnft__nse_discretization.c:424-431) */
+    FNFT_UINT Dsub = opts->Dsub;
+    if (Dsub == 0)
+        Dsub = (FNFT_UINT)pow(2.0, ceil(0.5 * log2(D * log2(D) * log2(D))));
+    else
+        Dsub = (FNFT_UINT)pow(2.0, round(log2(Dsub)));
+    if (Dsub < 2)
+        Dsub = 2;
+    if (Dsub > D)
+        Dsub = D;
+    const FNFT_UINT nskip = (FNFT_UINT)round((FNFT_REAL)D / Dsub);
+    Dsub = (FNFT_UINT)round((FNFT_REAL)D / nskip);
+    const FNFT_UINT nskip_per_step = D / Dsub;
+    if ((Dsub - 1) * nskip + nskip_per_step != D) /* :494-498 */
+        return E_ASSERTION_FAILED;
+
+    if (fnftb_signals_restore(ctx, 1) != 0)
+        return E_DEVICE;
+    if ((upsampling == 2 ? fnftb_resample_4split4_sub(ctx, eps_t, nskip, Dsub, NULL)
+                         : fnftb_subsample(ctx, nskip, Dsub)) != 0)
+        return E_DEVICE;
+    const FNFT_REAL eps_t_sub = nskip_per_step * eps_t; /* :525 */
+    fnftb_scatter_desc sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.rmode = FNFTB_RMODE_NSE;
+    sd.kappa = kappa;
+    sd.scheme = (int)akns;
+    sd.deg0 = (int)deg0;
+    sd.normalize = opts->normalization_flag ? 1 : 0;
+    sd.eps_t = eps_t_sub;
+    if (fnftb_fscatter(ctx, &sd) != 0)
+        return E_DEVICE;
+    const FNFT_UINT deg = deg0 * Dsub * upsampling;
+
+    const FNFT_REAL degree1step = (FNFT_REAL)deg0;
+    const FNFT_REAL map_coeff = 2 / degree1step;
+    if (opts->filtering == fnft_nsep_filt_AUTO) { /* update_bounding_box_if_auto(eps_t_sub, ...), :548 */
+        box[1] = 0.9 * FNFT_PI / (fabs(map_coeff) * eps_t_sub);
+        box[0] = -box[1];
+        box[3] = -log(0.1) / (fabs(map_coeff) * eps_t_sub);
+        box[2] = -box[3];
+    }
+    const FNFT_REAL tol_im = (box[1] - box[0]) / (32 * (D - 1));                 /* :549-550 */
+    const FNFT_REAL refine_tol = (opts->tol < 0) ? sqrt(FNFT_EPSILON) : opts->tol; /* :507-510 */
+    const FNFT_REAL lam_den = 2 * eps_t_sub / (degree1step * upsampling);
+
+    roots = malloc(nb * deg * sizeof(FNFT_COMPLEX));
+    info = malloc(nb * 4 * sizeof(int32_t));
+    Kn = malloc(nb * sizeof(int32_t));
+    flag = malloc(nb * deg * sizeof(int32_t));
+    full = calloc(nb, 1);
+    if (roots == NULL || info == NULL || Kn == NULL || flag == NULL || full == NULL) {
+        ret_code = E_NOMEM;
+        goto leave_fun;
+    }
+    fnftb_refine_desc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.upsampling = (int)upsampling; /* BO or CF4_2, :500-504 */
+    rd.kappa = kappa;
+    rd.Kstride = (int)deg;
+    rd.max_evals = (int)opts->max_evals;
+    rd.eps_t = eps_t;
+    rd.tol = refine_tol;
+
+#define NSEP_POSTPROCESS_ROOTS(do_nonreal)                                                   \
+    for (FNFT_UINT b = 0; b < nb; b++) {                                                      \
+        FNFT_COMPLEX *buf = roots + b * deg;                                                  \
+        FNFT_UINT Kb = (FNFT_UINT)info[4 * b + 1];                                            \
+        for (FNFT_UINT i = 0; i < Kb; i++) /* z_to_lambda, fnft__akns_discretization.c:225-240 */ \
+            buf[i] = clog(buf[i]) / (I * lam_den);                                            \
+        if (opts->filtering != fnft_nsep_filt_NONE)                                           \
+            fnftb__filter_box(&Kb, buf, box);                                                 \
+        if (do_nonreal)                                                                       \
+            filter_nonreal(&Kb, buf, tol_im);                                                 \
+        Kn[b] = (int32_t)Kb;                                                                  \
+    }
+#define NSEP_CHECK_FLAGS()                                                                   \
+    for (FNFT_UINT b = 0; b < nb; b++)                                                        \
+        for (FNFT_UINT i = 0; i < (FNFT_UINT)Kn[b]; i++)                                      \
+            if (flag[b * deg + i] == FNFT_EC_DIV_BY_ZERO) {                                   \
+                const FNFT_INT ec = E_DIV_BY_ZERO; /* :741-742, :820-821 */                   \
+                if (ret_codes != NULL)                                                        \
+                    ret_codes[b] = ec;                                                        \
+                if (ret_code == FNFT_SUCCESS)                                                 \
+                    ret_code = ec;                                                            \
+                Kn[b] = 0;                                                                    \
+                break;                                                                        \
+            }
+
+    if (main_out != NULL) { /* :553-640 */
+        const FNFT_REAL rhs_0 = opts->floquet_range[0], rhs_1 = opts->floquet_range[1];
+        const FNFT_UINT nvals = opts->points_per_spine;
+        FNFT_REAL rhs_step = rhs_1 - rhs_0;
+        if (nvals > 1)
+            rhs_step /= nvals - 1;
+        for (FNFT_UINT nval = 0; nval < nvals; nval++) {
+            const FNFT_REAL rhs = 2.0 * (rhs_0 + nval * rhs_step);
+            if (fnftb_nsep_floquet_roots(ctx, rhs, roots, info) != 0) {
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+            NSEP_POSTPROCESS_ROOTS(skip_real)
+            rd.mode = 0;
+            rd.rhs = -rhs;
+            if (fnftb_signals_restore(ctx, 0) != 0 || fnftb_nsep_refine(ctx, &rd, Kn, roots, flag) != 0) {
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+            NSEP_CHECK_FLAGS()
+            if (ret_code != FNFT_SUCCESS && ret_codes == NULL)
+                goto leave_fun;
+            for (FNFT_UINT b = 0; b < nb; b++) {
+                if (full[b])
+                    continue; /* user-provided array is full, :637-638 */
+                FNFT_COMPLEX *buf = roots + b * deg;
+                FNFT_UINT K_new = (FNFT_UINT)Kn[b];
+                if (opts->filtering != fnft_nsep_filt_NONE)
+                    fnftb__filter_box(&K_new, buf, box);
+                if (skip_real)
+                    filter_nonreal(&K_new, buf, tol_im);
+                if (K1[b] + K_new > Kmax) {
+                    if (!warned[0]) {
+                        WARN("Found more than *K_ptr main spectrum points. Returning as many as possible.");
+                        warned[0] = 1;
+                    }
+                    K_new = Kmax - K1[b];
+                    full[b] = 1;
+                }
+                for (FNFT_UINT i = 0; i < K_new; i++)
+                    main_out[b * Kmax + K1[b] + i] = buf[i] + Lam_shift;
+                K1[b] += K_new;
+            }
+        }
+    }
+    if (aux_out != NULL) { /* :642-691 */
+        if (fnftb_poly_roots(ctx, 1, roots, info) != 0) {
+            ret_code = E_DEVICE;
+            goto leave_fun;
+        }
+        NSEP_POSTPROCESS_ROOTS(0)
+        rd.mode = 1;
+        rd.rhs = 0.0;
+        if (fnftb_signals_restore(ctx, 0) != 0 || fnftb_nsep_refine(ctx, &rd, Kn, roots, flag) != 0) {
+            ret_code = E_DEVICE;
+            goto leave_fun;
+        }
+        NSEP_CHECK_FLAGS()
+        if (ret_code != FNFT_SUCCESS && ret_codes == NULL)
+            goto leave_fun;
+        for (FNFT_UINT b = 0; b < nb; b++) {
+            FNFT_COMPLEX *buf = roots + b * deg;
+            FNFT_UINT Mb = (FNFT_UINT)Kn[b];
+            if (opts->filtering != fnft_nsep_filt_NONE)
+                fnftb__filter_box(&Mb, buf, box);
+            if (skip_real)
+                filter_nonreal(&Mb, buf, tol_im);
+            if (Mb > Mmax) {
+                if (!warned[1]) {
+                    WARN("Found more than *M_ptr aux spectrum points. Returning as many as possible.");
+                    warned[1] = 1;
+                }
+                Mb = Mmax;
+            }
+            for (FNFT_UINT i = 0; i < Mb; i++)
+                aux_out[b * Mmax + i] = buf[i] + Lam_shift;
+            M1[b] = Mb;
+        }
+    }
+#undef NSEP_POSTPROCESS_ROOTS
+#undef NSEP_CHECK_FLAGS
+
+leave_fun:
+    free(roots);
+    free(info);
+    free(Kn);
+    free(flag);
+    free(full);
+    return ret_code;
+}
+
 /* shared by the single-signal and the batched entry point; box_out receives the
  * bounding box actually used (the reference writes it back into *opts) */
 static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
@@ -41,6 +258,8 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     FNFT_INT ret_code = FNFT_SUCCESS;
     int32_t *status = NULL;
     uint64_t *Kc = NULL, *Mc = NULL;
+    FNFT_UINT *K1 = NULL, *M1 = NULL;
+    FNFT_COMPLEX *main_tmp = NULL, *aux_tmp = NULL;
 
     if (B == 0)
         return E_INVALID_ARGUMENT(B);
@@ -60,9 +279,11 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         opts = &nsep_defaults;
     if (opts->filtering != fnft_nsep_filt_NONE && main_spec == NULL && aux_spec != NULL)
         return E_INVALID_ARGUMENT(main_spec.Filtering of the auxiliary spectrum is not possible if the main spectrum is not computed.);
-    if (opts->localization != fnft_nsep_loc_GRIDSEARCH)
-        return E_NOT_YET_IMPLEMENTED(opts->localization,
-                                     The GPU build implements fnft_nsep_loc_GRIDSEARCH only.);
+    const fnft_nsep_loc_t loc = opts->localization;
+    if (loc != fnft_nsep_loc_GRIDSEARCH && loc != fnft_nsep_loc_SUBSAMPLE_AND_REFINE &&
+        loc != fnft_nsep_loc_MIXED)
+        return E_INVALID_ARGUMENT(opts_ptr->discretization); /* sic, src/fnft_nsep.c:191 */
+    const int do_sub = (loc != fnft_nsep_loc_GRIDSEARCH), do_grid = (loc != fnft_nsep_loc_SUBSAMPLE_AND_REFINE);
 
     fnft__akns_discretization_t akns;
     ret_code = fnftb__nse_to_akns(opts->discretization, &akns);
@@ -105,7 +326,7 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         PHI[1] = tmp;
     }
     /* argument check of poly_roots_fftgridsearch (fftgridsearch.c:53-55) */
-    if (!(PHI[0] < PHI[1]) || PHI[0] == -INFINITY || PHI[1] == INFINITY)
+    if (do_grid && (!(PHI[0] < PHI[1]) || PHI[0] == -INFINITY || PHI[1] == INFINITY))
         return E_SUBROUTINE(E_INVALID_ARGUMENT(PHI));
 
     fnftb_scatter_desc sd;
@@ -139,10 +360,25 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         goto leave_fun;
     }
     int warned_main = 0, warned_aux = 0;
+    int warned_sub[2] = {0, 0};
+    K1 = calloc(chunk, sizeof(FNFT_UINT));
+    M1 = calloc(chunk, sizeof(FNFT_UINT));
+    if (K1 == NULL || M1 == NULL) {
+        ret_code = E_NOMEM;
+        goto leave_fun;
+    }
+    if (do_sub && do_grid) { /* MIXED: the grid search results are appended on the host */
+        main_tmp = main_spec ? malloc(chunk * Kmax * sizeof(FNFT_COMPLEX)) : NULL;
+        aux_tmp = aux_spec ? malloc(chunk * Mmax * sizeof(FNFT_COMPLEX)) : NULL;
+        if ((main_spec && main_tmp == NULL) || (aux_spec && aux_tmp == NULL)) {
+            ret_code = E_NOMEM;
+            goto leave_fun;
+        }
+    }
     for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
         const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
         if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, 0) != 0 ||
-            fnftb_nsep_derotate(ctx, Lam_shift, T[0], eps_t) != 0) {
+            fnftb_nsep_derotate(ctx, Lam_shift, T[0], eps_t) != 0 || fnftb_signals_save(ctx, 1) != 0) {
             ret_code = E_DEVICE;
             goto leave_fun;
         }
@@ -161,18 +397,77 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
             }
             free(warn);
         }
+        if (fnftb_signals_save(ctx, 0) != 0) {
+            ret_code = E_DEVICE;
+            goto leave_fun;
+        }
+        memset(K1, 0, nb * sizeof(FNFT_UINT));
+        memset(M1, 0, nb * sizeof(FNFT_UINT));
+        if (do_sub) {
+            /* MIXED computes only the non-real points here (skip_real_flag, :155-167); no non-real
+             * main spectrum exists in the defocusing case */
+            const int skip_real = do_grid;
+            FNFT_COMPLEX *main_dst = (main_spec != NULL && !(do_grid && kappa == -1)) ? main_spec + b0 * Kmax : NULL;
+            FNFT_REAL box_sub[4];
+            memcpy(box_sub, box, sizeof(box));
+            if (opts->filtering == fnft_nsep_filt_AUTO && !do_grid) {
+                /* nothing: recomputed inside from the subsampled step size */
+            }
+            ret_code = nsep_subsample_refine_chunk(ctx, nb, D, upsampling, deg0, akns, eps_t, kappa, opts, box_sub,
+                                                   skip_real, main_dst, Kmax, K1, aux_spec ? aux_spec + b0 * Mmax : NULL,
+                                                   Mmax, M1, Lam_shift, warned_sub, ret_codes ? ret_codes + b0 : NULL);
+            if (ret_code != FNFT_SUCCESS && ret_codes == NULL) {
+                ret_code = E_SUBROUTINE(ret_code);
+                goto leave_fun;
+            }
+            if (!do_grid) {
+                if (box_out != NULL)
+                    memcpy(box_out, box_sub, sizeof(box_sub));
+                for (FNFT_UINT b = 0; b < nb; b++) {
+                    K[b0 + b] = K1[b];
+                    Mcount[b0 + b] = M1[b];
+                }
+                continue;
+            }
+            if (fnftb_signals_restore(ctx, 0) != 0) {
+                ret_code = E_DEVICE;
+                goto leave_fun;
+            }
+        }
         if (fnftb_fscatter(ctx, &sd) != 0) {
             ret_code = E_DEVICE;
             goto leave_fun;
         }
         memset(Kc, 0, nb * sizeof(uint64_t));
         memset(Mc, 0, nb * sizeof(uint64_t));
-        if (fnftb_nsep_gridsearch(ctx, &nd, Kc, main_spec ? main_spec + b0 * Kmax : NULL, Mc,
-                                  aux_spec ? aux_spec + b0 * Mmax : NULL, status) != 0) {
+        FNFT_COMPLEX *gs_main = main_spec ? (do_sub ? main_tmp : main_spec + b0 * Kmax) : NULL;
+        FNFT_COMPLEX *gs_aux = aux_spec ? (do_sub ? aux_tmp : aux_spec + b0 * Mmax) : NULL;
+        if (fnftb_nsep_gridsearch(ctx, &nd, Kc, gs_main, Mc, gs_aux, status) != 0) {
             ret_code = E_DEVICE;
             goto leave_fun;
         }
         for (FNFT_UINT b = 0; b < nb; b++) {
+            if (do_sub) {
+                /* MIXED: real points from the grid search behind the non-real ones, in what is
+                 * left of the user arrays (:171-185) */
+                FNFT_UINT K2 = (FNFT_UINT)Kc[b], M2 = (FNFT_UINT)Mc[b];
+                if (main_spec != NULL) {
+                    if (K1[b] + K2 > Kmax) {
+                        K2 = Kmax - K1[b];
+                        status[b] |= 16;
+                    }
+                    memcpy(main_spec + (b0 + b) * Kmax + K1[b], main_tmp + b * Kmax, K2 * sizeof(FNFT_COMPLEX));
+                }
+                if (aux_spec != NULL) {
+                    if (M1[b] + M2 > Mmax) {
+                        M2 = Mmax - M1[b];
+                        status[b] |= 32;
+                    }
+                    memcpy(aux_spec + (b0 + b) * Mmax + M1[b], aux_tmp + b * Mmax, M2 * sizeof(FNFT_COMPLEX));
+                }
+                Kc[b] = K1[b] + K2;
+                Mc[b] = M1[b] + M2;
+            }
             K[b0 + b] = (FNFT_UINT)Kc[b];
             Mcount[b0 + b] = (FNFT_UINT)Mc[b];
             if (status[b] == 1) {
@@ -200,6 +495,10 @@ leave_fun:
     free(status);
     free(Kc);
     free(Mc);
+    free(K1);
+    free(M1);
+    free(main_tmp);
+    free(aux_tmp);
     return ret_code;
 }
 

@@ -234,6 +234,29 @@ def main():
     tt = np.linspace(-10, 10, 256)
     qs = 2.7 / np.cosh(tt) * np.exp(0.4j * tt)
     re_case("sech256_4split4b", qs, [-10, 10], 16, [-2, 2], 21, 1, 2, 2, gs)
+    # fnft_nsep with the default options (MIXED, 2SPLIT2A) and SUBSAMPLE_AND_REFINE: perturbed plane
+    # waves (the family of BASELINE config 5), reference with the companion-matrix stand-in for eiscor
+    def nsep_case(key, D, A, m, k, e, phi, kappa, loc, disc, phase_shift=0.0):
+        tt = 2 * np.pi * np.arange(D) / D
+        qq = A * np.exp(1j * m * tt) * (1 + e * np.cos(k * tt + phi))
+        if phase_shift != 0.0:
+            qq = qq * np.exp(1j * phase_shift * tt / (2 * np.pi))
+        o = R.lib().fnft_nsep_default_opts()
+        o.localization, o.discretization = loc, disc
+        ret, ms, au = R.nsep(qq, [0, 2 * np.pi], kappa, o, phase_shift=phase_shift)
+        assert ret == 0, (key, ret)
+        G[f"refrun/nsep_defaults/{key}/q"] = qq
+        G[f"refrun/nsep_defaults/{key}/par"] = np.array([kappa, loc, disc, phase_shift], dtype=np.float64)
+        G[f"refrun/nsep_defaults/{key}/main"] = ms
+        G[f"refrun/nsep_defaults/{key}/aux"] = au
+    nsep_case("mixed_2a", 256, 1.3, 1, 2, 0.2, 0.3, 1, 2, 4)
+    nsep_case("sub_2a", 256, 1.3, 1, 2, 0.2, 0.3, 1, 0, 4)
+    nsep_case("mixed_4b", 256, 0.9, 0, 1, 0.25, 1.1, 1, 2, 11)
+    nsep_case("sub_4b_defoc", 128, 0.9, 0, 1, 0.25, 1.1, -1, 0, 11)
+    nsep_case("mixed_2a_defoc", 128, 1.1, 2, 3, 0.1, 0.0, -1, 2, 4)
+    nsep_case("mixed_2a_shift", 256, 1.3, 1, 2, 0.2, 0.3, 1, 2, 4, phase_shift=0.8)
+    nsep_case("sub_4split4b", 128, 1.2, 0, 1, 0.2, 0.5, 1, 0, 21)
+    nsep_case("mixed_2a_1024", 1024, 1.6, 0, 2, 0.15, 0.4, 1, 2, 4)
     pr = rng.standard_normal(60) + 1j * rng.standard_normal(60)
     G["refrun/roots/p"] = pr
     ret = R.lib().fnft__poly_roots_fasteigen

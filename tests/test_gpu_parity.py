@@ -263,6 +263,54 @@ def test_nsev_richardson_extrapolation_vs_reference_runs(F, golden):
             assert (np.abs(ours - ref) <= 1e-9 * np.abs(ref)).all(), (case, part, ours, ref)
 
 
+def test_nsep_default_options_and_subsample_refine_vs_reference_runs(F, golden):
+    # fnft_nsep with localization MIXED (the default) and SUBSAMPLE_AND_REFINE against recorded
+    # runs of the reference (root finder: companion-matrix stand-in for eiscor).  Simple points
+    # of the spectra are refined to full precision by both; degenerate (double) points of the
+    # main spectrum are located only to ~sqrt(tol) by the damped Newton iteration -- the two
+    # members of such a pair differ by 1e-4 in the reference's own output -- hence two bounds.
+    F.lib().fnft_errwarn_setprintf(None)
+    for case in _keys(golden, "refrun/nsep_defaults/"):
+        q = golden[f"refrun/nsep_defaults/{case}/q"]
+        kappa, loc, disc, ps = golden[f"refrun/nsep_defaults/{case}/par"]
+        o = F.nsep_default_opts()
+        assert o.localization == 2 and o.discretization == 4
+        o.localization, o.discretization = int(loc), int(disc)
+        ret, ms, au = F.nsep(q, [0, 2 * np.pi], int(kappa), o, phase_shift=float(ps))
+        assert ret == 0, case
+        for ours, ref, nm in ((ms, golden[f"refrun/nsep_defaults/{case}/main"], "main"),
+                              (au, golden[f"refrun/nsep_defaults/{case}/aux"], "aux")):
+            assert ours.size == ref.size, (case, nm, ours.size, ref.size)
+            d = np.abs(ours[:, None] - ref[None, :])
+            haus = max(d.min(axis=0).max(), d.min(axis=1).max())
+            assert haus <= 2e-3, (case, nm, haus)
+            # non-degenerate points: isolated from every other point of the reference set
+            dr = np.abs(ref[:, None] - ref[None, :]) + 1e9 * np.eye(ref.size)
+            simple = dr.min(axis=1) > 0.05
+            assert simple.any()
+            assert d.min(axis=0)[simple].max() <= 1e-8 * max(1.0, np.abs(ref).max()), (case, nm)
+
+
+@pytest.mark.parametrize("disc,loc", [(4, 2), (21, 2), (11, 0), (21, 1)])
+def test_nsep_batch_matches_single_calls(F, disc, loc):
+    # batched periodic NFT (all localizations; 4SPLIT4B exercises the resampling of several
+    # signals at once) = the single-signal entry point, signal by signal
+    F.lib().fnft_errwarn_setprintf(None)
+    D, B = 128, 5
+    tt = 2 * np.pi * np.arange(D) / D
+    rng = np.random.default_rng(disc * 10 + loc)
+    q = np.stack([(0.8 + 0.3 * b) * np.exp(1j * (b % 3) * tt) * (1 + 0.2 * np.cos((1 + b % 2) * tt + rng.uniform(0, 6)))
+                  for b in range(B)])
+    o = F.nsep_default_opts()
+    o.localization, o.discretization = loc, disc
+    ret, Ka, main, Ma, aux, rcs = F.nsep_batch(q, [0, 2 * np.pi], 64 * D, 64 * D, 1, o)
+    assert ret == 0 and not rcs.any()
+    for b in range(B):
+        r1, ms, au = F.nsep(q[b], [0, 2 * np.pi], 1, o)
+        assert r1 == 0 and ms.size == Ka[b] and au.size == Ma[b]
+        assert np.array_equal(ms, main[b, :ms.size]) and np.array_equal(au, aux[b, :au.size])
+
+
 def test_nsev_batch_default_options_matches_single_calls(F):
     D, B = 512, 6
     t = np.linspace(-10, 10, D)
