@@ -4,6 +4,8 @@
   3  fnft_nsev bound states + norming constants (Newton), D = 4096, 8-soliton signals, B = 1024
   4  fnft_kdvv reflection coefficient, 4SPLIT4B, D = M = 8192, B = 2048
   5  fnft_nsep main + auxiliary spectrum (grid search), D = 4096, B = 1024
+  6  the same signals with fnft_nsep's default localization (MIXED)
+  7  config 3's signals through fnft_nsev with its default options (SUBSAMPLE_AND_REFINE)
 
 For each: throughput of the batched C-ABI call with host buffers (wall clock around the
 call, best of --reps), the reference library (oracle/_ref) on a bounded sample over all
@@ -170,12 +172,12 @@ def main():
     # reference legs first (fork before CUDA is initialised)
     ref = {}
     inputs = {}
-    if 3 in todo:
+    if 3 in todo or 7 in todo:
         B = max(16, int(1024 * args.scale))
         T = (-20.0, 20.0)
         Q, lam, G = config3_inputs(B) if have_ref else (None, None, None)
         inputs[3] = (Q, lam, G, T)
-        if have_ref:
+        if have_ref and 3 in todo:
             n = args.ref_signals or min(B, 4 * nc)
             ref[3] = run_pool(_ref3, [(Q[i], G[i], T) for i in range(n)])
     if 4 in todo:
@@ -185,11 +187,11 @@ def main():
         if have_ref:
             n = args.ref_signals or min(B, 4 * nc)
             ref[4] = run_pool(_ref4, [(U[i], (-16.0, 15.0), 8192, (-3.55, 3.95)) for i in range(n)])
-    if 5 in todo:
+    if 5 in todo or 6 in todo:
         B = max(16, int(1024 * args.scale))
         Q5 = config5_inputs(B)
         inputs[5] = Q5
-        if have_ref:
+        if have_ref and 5 in todo:
             n = args.ref_signals or min(B, nc)
             ref[5] = run_pool(_ref5, [(Q5[i], (0.0, 2 * np.pi)) for i in range(n)])
 
@@ -300,6 +302,53 @@ def main():
                     if len(a0):
                         err = max(err, float(np.abs(a1 - a0).max() / max(1.0, np.abs(a0).max())))
                 line["parity"] = {"same_counts": ok, "max_err": err, "bound": 1e-9, "signals": len(res)}
+        elif cfg == 6:
+            # config 5's signals with the reference's DEFAULT localization (MIXED: subsample-and-refine for
+            # the non-real points + grid search for the real ones); no CPU leg: the oracle's stand-in for
+            # eiscor is O(n^3) (minutes per signal at this size)
+            Q5 = inputs[5]
+            B, D = Q5.shape
+            T = (0.0, 2 * np.pi)
+            o = F.nsep_default_opts()
+            o.filtering = 1
+            o.bounding_box[0], o.bounding_box[1], o.bounding_box[2], o.bounding_box[3] = -10, 10, -10, 10
+            o.discretization = F.NSE_2SPLIT4B
+            Kmax = Mmax = 4 * 2 * D
+
+            def run():
+                return F.nsep_batch(Q5, T, Kmax, Mmax, 1, o)
+            run()
+            dt, (ret, Ka, main, Ma, aux, rcs) = best_of(run, args.reps)
+            line.update(workload="fnft_nsep default localization MIXED (main + auxiliary spectrum), 2SPLIT4B, "
+                                 "D=4096, B=%d" % B,
+                        value=B / dt, unit="signals/s", ms_per_call=dt * 1e3, ret=int(ret),
+                        mean_main_points=float(Ka.mean()), mean_aux_points=float(Ma.mean()))
+        elif cfg == 7:
+            # config 3's multi-soliton signals through fnft_nsev with its DEFAULT options
+            # (bsloc_SUBSAMPLE_AND_REFINE: GPU root finder on the subsampled signal + Newton), plus the
+            # reflection coefficient at M = D points
+            Q, lam, G, T = inputs[3]
+            if Q is None:
+                print(json.dumps({"config": 7, "unavailable": "oracle/_ref needed to synthesise the solitons"}))
+                continue
+            B, K = G.shape
+            D = Q.shape[1]
+            o = F.nsev_default_opts()
+            o.discspec_type = F.DSTYPE_BOTH
+            Kmax = 64
+
+            def run():
+                return F.nsev_batch(Q, T, D, (-4.0, 4.0), 1, o, K=np.zeros(B), Kmax=Kmax,
+                                    bound_states=np.zeros((B, Kmax), dtype=np.complex128))
+            run()
+            dt, (ret, cs, Ka, bs, ncs, rcs) = best_of(run, args.reps)
+            ok = 0
+            for i in range(B):  # every true eigenvalue found (BO-discretised, within 1e-3)
+                ok += all(np.abs(bs[i, :int(Ka[i])] - l).min() < 2e-3 for l in lam[i]) if Ka[i] else 0
+            line.update(workload="fnft_nsev default options (SUBSAMPLE_AND_REFINE bound states + residues + "
+                                 "reflection coefficient, M=D), D=4096, 8-soliton signals, B=%d" % B,
+                        value=B / dt, unit="signals/s", ms_per_call=dt * 1e3, ret=int(ret),
+                        mean_K=float(Ka.mean()), all_eigenvalues_found=ok / B)
         print(json.dumps(line), flush=True)
 
 
