@@ -39,6 +39,7 @@ fnftb_ctx *fnftb__ctx(void);          /* NULL (after printing why) if no GPU */
 int fnftb__device_pointers(void);     /* flag set by fnft_b200_set_device_pointers */
 size_t fnftb__workspace_limit(void);
 int fnftb__pipe_chunks(void);
+FNFT_UINT fnftb__pipe_step(FNFT_UINT b0, FNFT_UINT B, FNFT_UINT chunk);
 
 /* ln|z| and arg z of a complex double, accurate to far below one ulp of |z|-1 */
 void fnftb__logpolar(FNFT_COMPLEX z, double *ln_abs, double *arg);

@@ -107,8 +107,10 @@ FNFT_INT fnft_kdvv_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
         if (fnftb_pipeline_begin(ctx) != 0)
             return E_DEVICE;
     }
-    for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
-        const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    FNFT_UINT step = chunk;
+    for (FNFT_UINT b0 = 0; b0 < B; b0 += step) {
+        step = piped ? fnftb__pipe_step(b0, B, chunk) : chunk; /* tapered at both ends */
+        const FNFT_UINT nb = (B - b0 < step) ? (B - b0) : step;
         if (fnftb_set_signals(ctx, nb, D, u + b0 * D, NULL, devptr) != 0 ||
             fnftb_fscatter(ctx, &sd) != 0 ||
             fnftb_contspec(ctx, &cd, contspec + b0 * M, M, devptr, NULL) != 0) {

@@ -213,8 +213,10 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     }
     FNFT_UINT prev_b0 = 0, prev_nb = 0; /* chunk whose results are still in flight */
     int slot = 0;
-    for (FNFT_UINT b0 = 0; b0 < B || prev_nb > 0; b0 += chunk) {
-        const FNFT_UINT nb = (b0 >= B) ? 0 : ((B - b0 < chunk) ? (B - b0) : chunk);
+    FNFT_UINT step = chunk;
+    for (FNFT_UINT b0 = 0; b0 < B || prev_nb > 0; b0 += step) {
+        step = piped ? fnftb__pipe_step(b0, B, chunk) : chunk; /* tapered at both ends */
+        const FNFT_UINT nb = (b0 >= B) ? 0 : ((B - b0 < step) ? (B - b0) : step);
         int32_t *st_cur = status ? status + (size_t)slot * chunk : NULL;
         if (nb > 0 && want_discspec && bsloc == fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE && Dsub_req == 0) {
             /* First step of the mixed method (src/fnft_nsev.c:276-296): initial guesses from

@@ -27,8 +27,10 @@ for r in rows[2:]:
         if k in d: print('  %-75s %s' % (k, d[k]))
     st = []
     for k in hdr:
-        if 'issue_stalled' in k and k.endswith('_per_warp_active.pct') and 'not_issued' not in k:
+        if 'issue_stalled' in k and (k.endswith('_per_warp_active.pct') or k.endswith('_per_issue_active.ratio')) \
+                and 'not_issued' not in k:
             try: st.append((float(d[k].replace(',', '')), k))
             except ValueError: pass
-    for v, k in sorted(st, reverse=True)[:8]:
-        print('  stall %6.1f%%  %s' % (v, k.split('issue_stalled_')[1].split('_per_warp')[0]))
+    tot = sum(v for v, _ in st) or 1.0
+    for v, k in sorted(st, reverse=True)[:6]:
+        print('  stall %5.1f%% of the stalled warp-cycles  %s' % (100 * v / tot, k.split('issue_stalled_')[1].split('_per_')[0]))
