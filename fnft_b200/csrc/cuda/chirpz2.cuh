@@ -41,7 +41,7 @@ struct Cz2Args {
 
 // grid.x * 256 threads = narr * 4096 ; narr = B*npoly (or 1 for gen_v)
 template <int R>
-__global__ void __launch_bounds__(256) k_cz2_cols_fwd(const Cz2Args a)
+__global__ void __launch_bounds__(256, 3) k_cz2_cols_fwd(const Cz2Args a)
 {
     constexpr int LR = Log2R<R>::value;
     constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
@@ -183,6 +183,45 @@ __global__ void __launch_bounds__(128, 3) k_cz2_rows(const Cz2Args a)
     }
 }
 
+// continuous-spectrum epilogue of output point m (both polynomials evaluated): H0, H1 already
+// carry the factor W^(m^2/2)/L
+DEV void cz2_epilogue(const CzArgs &c, size_t s, int m, cplx H0, cplx H1, cplx *out)
+{
+    if (c.mode == FNFTB_CZ_RAW) {
+        const size_t js = c.out_jstride ? c.out_jstride : (size_t)c.M;
+        out[m] = H0;
+        if (c.npoly > 1)
+            out[js + m] = H1;
+    } else if (c.mode == FNFTB_CZ_NSEV) {
+        // src/fnft_nsev.c:846-876; H0 = H11 (a-poly), H1 = H21 (b-poly)
+        size_t off = 0;
+        if (c.cstype == 0 || c.cstype == 2) {
+            if (H0.x == 0.0 && H0.y == 0.0) {
+                if (c.status)
+                    c.status[s] = 3;
+                out[m] = make_cplx(NAN, NAN);
+            } else {
+                out[m] = cdiv(cmul(H1, __ldg(&c.tab_ph[m])), H0);
+            }
+            off = c.M;
+        }
+        if (c.cstype == 1 || c.cstype == 2) {
+            const double scale = ldexp(1.0, c.W ? c.W[s] : 0);
+            out[off + m] = cmul(cscale(H0, scale), __ldg(&c.tab_ph[c.M + m]));
+            out[off + c.M + m] = cmul(cscale(H1, scale), __ldg(&c.tab_ph[2 * (size_t)c.M + m]));
+        }
+    } else {
+        // src/fnft_kdvv.c:186-203; H0 = H12, H1 = H22, xi grid negated
+        const double xi = -c.xi0 - (double)m * c.eps_xi;
+        cplx h12 = H0;
+        if (c.kdv_sqrtz != 0.0)
+            h12 = cdiv(h12, __ldg(&c.tab_ph[c.M + m]));
+        const cplx num = cmul(__ldg(&c.tab_ph[m]), h12);
+        const cplx den = make_cplx(-2.0 * xi * H1.y - h12.x, 2.0 * xi * H1.x - h12.y);
+        out[m] = cdiv(num, den);
+    }
+}
+
 // grid.x * 256 threads = B * 4096
 template <int R>
 __global__ void __launch_bounds__(256) k_cz2_cols_inv(const Cz2Args a)
@@ -220,40 +259,103 @@ __global__ void __launch_bounds__(256) k_cz2_cols_inv(const Cz2Args a)
         if (m >= c.M)
             break;
         const cplx ch = __ldg(&c.tab_out[m]);
-        const cplx H0 = cmul(H[0][n], ch), H1 = cmul(H[1][n], ch);
-        if (c.mode == FNFTB_CZ_RAW) {
-            const size_t js = c.out_jstride ? c.out_jstride : (size_t)c.M;
-            out[m] = H0;
-            if (c.npoly > 1)
-                out[js + m] = H1;
-        } else if (c.mode == FNFTB_CZ_NSEV) {
-            // src/fnft_nsev.c:846-876; H0 = H11 (a-poly), H1 = H21 (b-poly)
-            size_t off = 0;
-            if (c.cstype == 0 || c.cstype == 2) {
-                if (H0.x == 0.0 && H0.y == 0.0) {
-                    if (c.status)
-                        c.status[s] = 3;
-                    out[m] = make_cplx(NAN, NAN);
-                } else {
-                    out[m] = cdiv(cmul(H1, __ldg(&c.tab_ph[m])), H0);
+        cz2_epilogue(c, s, m, cmul(H[0][n], ch), cmul(H[1][n], ch), out);
+    }
+}
+
+// exp(2 pi i k / 16), folded to constants once the callers' loops are unrolled
+DEV cplx unit_root16(int k)
+{
+    const double c1 = 0.9238795325112867, s1 = 0.3826834323650898, h = 0.7071067811865476;
+    switch (k & 15) {
+    case 0: return make_cplx(1.0, 0.0);
+    case 1: return make_cplx(c1, s1);
+    case 2: return make_cplx(h, h);
+    case 3: return make_cplx(s1, c1);
+    case 4: return make_cplx(0.0, 1.0);
+    case 5: return make_cplx(-s1, c1);
+    case 6: return make_cplx(-h, h);
+    case 7: return make_cplx(-c1, s1);
+    case 8: return make_cplx(-1.0, 0.0);
+    case 9: return make_cplx(-c1, -s1);
+    case 10: return make_cplx(-h, -h);
+    case 11: return make_cplx(-s1, -c1);
+    case 12: return make_cplx(0.0, -1.0);
+    case 13: return make_cplx(s1, -c1);
+    case 14: return make_cplx(h, -h);
+    default: return make_cplx(c1, -s1);
+    }
+}
+
+// Output-pruned variant: only the rows n < NOUT (m = o + n*4096 < M) of the radix-R inverse column
+// pass are wanted -- config 2 needs 4 of 16.  With q = s + S*t (S = R/NOUT):
+//   X[n] = sum_s w_R^(s n) * ( sum_t x[s + S t] w_NOUT^(t n) ),      n < NOUT,
+// i.e. S streamed NOUT-point transforms accumulated into NOUT values per polynomial: a fraction of
+// the registers of the full butterfly (the kernel is latency bound: 174 registers, 8 warps per SM),
+// so three times the warps are resident.
+template <int R, int NOUT>
+__global__ void __launch_bounds__(256, 3) k_cz2_cols_inv_p(const Cz2Args a)
+{
+    constexpr int LR = Log2R<R>::value;
+    constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
+    constexpr int S = R / NOUT;
+    const CzArgs &c = a.c;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = (int)(gid & (N2 - 1));
+    const size_t s = (size_t)(gid >> FNFTB_CZ2_ROW_L2);
+    if (o >= c.M)
+        return;
+    const int L = 1 << a.l2L;
+    const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][LR];
+    const cplx w1 = cconj(__ldg(&pt[o]));  // element q carries w1^q (up_twiddle_mul<R, true>)
+    cplx wS = w1;
+#pragma unroll
+    for (int i = 1; i < S; i <<= 1)
+        wS = csq(wS);
+    cplx acc[2][NOUT];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n)
+            acc[j][n] = czero();
+        if (j < c.npoly) {
+            const cplx *src = c.ybuf + (s * c.npoly + j) * (size_t)L;
+            cplx ws = make_cplx(1.0, 0.0);
+#pragma unroll
+            for (int sI = 0; sI < S; ++sI) {
+                cplx y[NOUT];
+#pragma unroll
+                for (int t = 0; t < NOUT; ++t)
+                    y[t] = src[((size_t)brev_c(sI + S * t, LR) << FNFTB_CZ2_ROW_L2) + o];
+                cplx tw = ws;
+#pragma unroll
+                for (int t = 0; t < NOUT; ++t) {
+                    if (sI + t > 0)
+                        y[t] = cmul(y[t], tw);
+                    tw = cmul(tw, wS);
                 }
-                off = c.M;
+                Dft<NOUT, +1>::run(y);
+#pragma unroll
+                for (int n = 0; n < NOUT; ++n) {
+                    const int k16 = (sI * n * (16 / R)) & 15;
+                    if (k16 == 0) {
+                        acc[j][n] = cadd(acc[j][n], y[n]);
+                    } else {
+                        cfma(acc[j][n], y[n], unit_root16(k16));
+                    }
+                }
+                ws = cmul(ws, w1);
             }
-            if (c.cstype == 1 || c.cstype == 2) {
-                const double scale = ldexp(1.0, c.W ? c.W[s] : 0);
-                out[off + m] = cmul(cscale(H0, scale), __ldg(&c.tab_ph[c.M + m]));
-                out[off + c.M + m] = cmul(cscale(H1, scale), __ldg(&c.tab_ph[2 * (size_t)c.M + m]));
-            }
-        } else {
-            // src/fnft_kdvv.c:186-203; H0 = H12, H1 = H22, xi grid negated
-            const double xi = -c.xi0 - (double)m * c.eps_xi;
-            cplx h12 = H0;
-            if (c.kdv_sqrtz != 0.0)
-                h12 = cdiv(h12, __ldg(&c.tab_ph[c.M + m]));
-            const cplx num = cmul(__ldg(&c.tab_ph[m]), h12);
-            const cplx den = make_cplx(-2.0 * xi * H1.y - h12.x, 2.0 * xi * H1.x - h12.y);
-            out[m] = cdiv(num, den);
         }
+    }
+    cplx *out = c.out + s * c.out_sstride;
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) {
+        const int m = o + n * N2;
+        if (m >= c.M)
+            break;
+        const cplx ch = __ldg(&c.tab_out[m]);
+        cz2_epilogue(c, s, m, cmul(acc[0][n], ch), cmul(acc[1][n], ch), out);
     }
 }
 
@@ -353,7 +455,35 @@ static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t 
     rc = cz2_launch(k_cz2_rows, a, (unsigned)(narr << l2R), 128, smem, st, "cz_rows");
     if (rc)
         return rc;
-    CZ2_BY_R(k_cz2_cols_inv, a, (unsigned)((size_t)c.B * cols1), "cz_cols_inv");
+    {
+        // rows of the last column pass that hold wanted outputs (m < M)
+        const int need = (c.M + (1 << FNFTB_CZ2_ROW_L2) - 1) >> FNFTB_CZ2_ROW_L2;
+        const unsigned grid = (unsigned)((size_t)c.B * cols1);
+        static const int knob_prune = [] {
+            const char *e = getenv("FNFT_B200_CZ2_PRUNE");
+            return (e && e[0]) ? atoi(e) : 1;
+        }();
+        const int R = 1 << l2R;
+        if (knob_prune && R >= 4 && need * 2 <= R) {
+            const bool quarter = (need * 4 <= R);
+            switch (l2R) {
+            case 2:
+                rc = quarter ? cz2_launch(k_cz2_cols_inv_p<4, 1>, a, grid, 256, 0, st, "cz_cols_inv")
+                             : cz2_launch(k_cz2_cols_inv_p<4, 2>, a, grid, 256, 0, st, "cz_cols_inv");
+                break;
+            case 3:
+                rc = quarter ? cz2_launch(k_cz2_cols_inv_p<8, 2>, a, grid, 256, 0, st, "cz_cols_inv")
+                             : cz2_launch(k_cz2_cols_inv_p<8, 4>, a, grid, 256, 0, st, "cz_cols_inv");
+                break;
+            default:
+                rc = quarter ? cz2_launch(k_cz2_cols_inv_p<16, 4>, a, grid, 256, 0, st, "cz_cols_inv")
+                             : cz2_launch(k_cz2_cols_inv_p<16, 8>, a, grid, 256, 0, st, "cz_cols_inv");
+                break;
+            }
+        } else {
+            CZ2_BY_R(k_cz2_cols_inv, a, grid, "cz_cols_inv");
+        }
+    }
 #undef CZ2_BY_R
     return rc;
 }

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
 // (cols) one thread per (array, o < N2): radix-R inverse pass across the rows, coefficient
 // fix-up and max, then twist + radix-R forward pass (or the coefficient output when last)
 template <int R, bool SYM>
-__global__ void __launch_bounds__(256) k_up_cols(const UpArgs a)
+__global__ void __launch_bounds__(256, (R >= 8) ? 3 : 4) k_up_cols(const UpArgs a)
 {
     typedef typename UpT<SYM>::Tops Tops;
     constexpr int E = UpT<SYM>::E;
