@@ -695,3 +695,27 @@ def test_c_example_program_runs(F, tmp_path):
                            "-Wl,-rpath," + os.path.join(root, "fnft_b200", "lib"), "-lm", "-o", exe])
     out = subprocess.check_output([exe]).decode()
     assert "single: rho" in out and out.count("batch") == 4
+
+
+def test_c_example_config1_default_options(F, golden, tmp_path):
+    """BASELINE config 1: examples/nsev_example.c (the scenario of the reference's
+    fnft_nsev_example.c, default options) built with gcc against include/ and run on the GPU;
+    its printed numbers against the recorded run of the reference."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "nsev_example")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "nsev_example.c"),
+                           "-L" + os.path.join(root, "fnft_b200", "lib"), "-lfnft_b200",
+                           "-Wl,-rpath," + os.path.join(root, "fnft_b200", "lib"), "-lm", "-o", exe])
+    out = subprocess.check_output([exe]).decode()
+    num = r"([-+]\d\.\d+e[-+]\d+)"
+    rho = np.array([complex(float(a), float(b)) for a, b in re.findall(r"rho = " + num + " " + num + "i", out)])
+    lam = [complex(float(a), float(b)) for a, b in re.findall(r"lambda = " + num + " " + num + "i", out)]
+    bb = [complex(float(a), float(b)) for a, b in re.findall(r"b = " + num + " " + num + "i", out)]
+    assert "K = 1" in out and len(lam) == 1
+    assert np.abs(rho - golden["refrun/defaults/example/cs"]).max() < 1e-8   # 10 printed digits
+    assert abs(lam[0] - golden["refrun/defaults/example/bs"][0]) < 1e-8
+    assert abs(bb[0] - golden["refrun/defaults/example/nc"][0]) < 1e-8
