@@ -207,7 +207,31 @@ def parse_report(txt):
     return out
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Rank 0 must print exactly ONE line on stdout.  Libraries write there too (NCCL prints its
+    version banner on stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr
+    for the rest of the run and the JSON line goes to a private duplicate of the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -253,7 +277,7 @@ def main():
                                           "gcc -O3 -march=x86-64-v3, Kiss FFT"},
                 "e2e": {"value": val, "unit": "signals/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     # ------------------------------------------------------------------ CPU baseline first
@@ -414,7 +438,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "parity": parity}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
