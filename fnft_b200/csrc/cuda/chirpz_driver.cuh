@@ -77,11 +77,11 @@ static inline int cz_run(CzArgs a, cplx *tables, fnftb_stream_t st, int row_n = 
         CzArgs v = a;
         v.gen_v = 1;
         v.fwd_only = 1;
-        rc = launch_blocks<CzArgs, blk_cz_cols_fwd>(v, (unsigned)(g.N2 / g.C), nt,
+        rc = launch_blocks<CzArgs, blk_cz_cols_fwd, 256, 3>(v, (unsigned)(g.N2 / g.C), nt,
                                                     cz_cols_smem_bytes(g.C, g.N1, 1), st, "cz_filter");
         if (rc)
             return rc;
-        rc = launch_blocks<CzArgs, blk_cz_rows>(v, (unsigned)g.N1, nt, sizeof(cplx) * (size_t)g.N2, st,
+        rc = launch_blocks<CzArgs, blk_cz_rows, 256, 2>(v, (unsigned)g.N1, nt, sizeof(cplx) * (size_t)g.N2, st,
                                                 "cz_filter");
         if (rc)
             return rc;
@@ -89,16 +89,16 @@ static inline int cz_run(CzArgs a, cplx *tables, fnftb_stream_t st, int row_n = 
     a.gen_v = 0;
     a.fwd_only = 0;
     // 2. forward columns of all polynomials
-    rc = launch_blocks<CzArgs, blk_cz_cols_fwd>(a, (unsigned)((size_t)a.B * a.npoly * (g.N2 / g.C)), nt,
+    rc = launch_blocks<CzArgs, blk_cz_cols_fwd, 256, 3>(a, (unsigned)((size_t)a.B * a.npoly * (g.N2 / g.C)), nt,
                                                 cz_cols_smem_bytes(g.C, g.N1, 1), st, "cz_cols_fwd");
     if (rc)
         return rc;
     // 3. rows: FFT, multiply, inverse FFT
-    rc = launch_blocks<CzArgs, blk_cz_rows>(a, (unsigned)((size_t)a.B * a.npoly * g.N1), nt,
+    rc = launch_blocks<CzArgs, blk_cz_rows, 256, 2>(a, (unsigned)((size_t)a.B * a.npoly * g.N1), nt,
                                             sizeof(cplx) * (size_t)g.N2, st, "cz_rows");
     if (rc)
         return rc;
     // 4. inverse columns + epilogue
-    return launch_blocks<CzArgs, blk_cz_cols_inv>(a, (unsigned)((size_t)a.B * (g.N2 / g.C)), nt,
+    return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / g.C)), nt,
                                                   cz_cols_smem_bytes(g.C, g.N1, a.npoly), st, "cz_cols_inv");
 }
