@@ -9,6 +9,7 @@
 #include "nsep_kernels.cuh"
 #include "poly_roots.cuh"
 #include "nsep_refine.cuh"
+#include "slow_scatter.cuh"
 #include "resample_kernels.cuh"
 #include "tree_driver.cuh"
 #include "twiddle.h"
@@ -720,6 +721,56 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
     return 0;
 }
 
+
+int fnftb_slow_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, int upsampling, int kappa, double eps_t,
+                        void *out, size_t out_sstride, int on_device, int32_t *status_host)
+{
+    if (!c || !d || !out || !c->q || d->M == 0 || (upsampling != 1 && upsampling != 2))
+        return fail(-2, "invalid argument / no signals staged", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->B;
+    RC(ensure(c->status, B * sizeof(int)));
+    CU(cudaMemsetAsync(c->status.p, 0, B * sizeof(int), c->st));
+    cplx *dst = (cplx *)out;
+    if (!on_device) {
+        RC(ensure(c->outbuf, B * out_sstride * sizeof(cplx)));
+        dst = (cplx *)c->outbuf.p;
+    }
+    SlowCsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = c->q;
+    a.B = (int)B;
+    a.D = (int)c->D;
+    a.upsampling = upsampling;
+    a.kappa = kappa;
+    a.M = (int)d->M;
+    a.cstype = d->cstype;
+    a.eps_t = eps_t;
+    a.lweight = (upsampling == 2) ? 0.5 : 1.0;
+    a.xi0 = d->xi0;
+    a.eps_xi = d->eps_xi;
+    a.ph_rho = d->ph_rho;
+    a.ph_a = d->ph_a;
+    a.ph_b = d->ph_b;
+    a.out = dst;
+    a.out_sstride = out_sstride;
+    a.status = (int *)c->status.p;
+    const size_t n = B * (size_t)d->M;
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin("slow_contspec", c->st);
+    k_slow_contspec<<<(unsigned)((n + 3) / 4), 128, 0, c->st>>>(a);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(c->st);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    if (!on_device)
+        CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    if (status_host)
+        CU(cudaMemcpyAsync(status_host, c->status.p, B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    if (!on_device || status_host)
+        CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
 
 // ---------------------------------------------------------------------------
 // periodic NFT: grid search

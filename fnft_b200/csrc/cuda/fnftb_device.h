@@ -132,6 +132,13 @@ int fnftb_set_polynomial(fnftb_ctx *ctx, size_t deg, const void *p_host);
 int fnftb_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, void *out,
                    size_t out_sstride, int on_device, int32_t *status_host);
 
+/* Continuous spectrum of the staged signals with the slow discretizations BO (upsampling 1) and
+ * CF4_2 (upsampling 2; the staged signals are the resampled ones): one product of D step matrices
+ * per spectral point, src/fnft_nsev.c:794-814 + epilogue :836-876.  Uses mode / cstype / M / xi0 /
+ * eps_xi / ph_* of the descriptor. */
+int fnftb_slow_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, int upsampling, int kappa,
+                        double eps_t, void *out, size_t out_sstride, int on_device, int32_t *status_host);
+
 /* ---- periodic NFT (grid search) --------------------------------------------------- */
 typedef struct {
     double PHI0, PHI1;   /* angular range of the search on the unit circle */

@@ -87,6 +87,40 @@ static FNFT_INT nsev_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL
 }
 
 /*
+ * Continuous spectrum of the staged signals for the slow discretizations BO / CF4_2
+ * (nsev_compute_contspec with deg == 0, src/fnft_nsev.c:794-814, epilogue :836-876).
+ */
+static FNFT_INT nsev_slow_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL const *T, FNFT_UINT M,
+                                         FNFT_REAL const *XI, FNFT_INT kappa, int upsampling,
+                                         fnft_nsev_opts_t const *opts, FNFT_COMPLEX *out, int on_device,
+                                         int32_t *status)
+{
+    const fnft_nse_discretization_t disc = opts->discretization;
+    const FNFT_REAL eps_t = (T[1] - T[0]) / (D_given - 1);
+    fnftb_contspec_desc cd;
+    memset(&cd, 0, sizeof(cd));
+    cd.mode = FNFTB_MODE_NSEV;
+    cd.cstype = (int)opts->contspec_type;
+    cd.M = M;
+    cd.xi0 = XI[0];
+    cd.eps_xi = (XI[1] - XI[0]) / (M - 1);
+    FNFT_INT ret_code;
+    ret_code = fnftb__nse_phase_factor_rho(eps_t, T[1], &cd.ph_rho, disc);
+    if (ret_code != FNFT_SUCCESS)
+        return E_SUBROUTINE(ret_code);
+    ret_code = fnftb__nse_phase_factor_a(eps_t, D_given, T, &cd.ph_a, disc);
+    if (ret_code != FNFT_SUCCESS)
+        return E_SUBROUTINE(ret_code);
+    ret_code = fnftb__nse_phase_factor_b(eps_t, D_given, T, &cd.ph_b, disc);
+    if (ret_code != FNFT_SUCCESS)
+        return E_SUBROUTINE(ret_code);
+    if (fnftb_slow_contspec(ctx, &cd, upsampling, kappa, eps_t, out, contspec_len(opts->contspec_type, M),
+                            on_device, status) != 0)
+        return E_DEVICE;
+    return FNFT_SUCCESS;
+}
+
+/*
  * One pass of fnft_nsev over a batch: preprocessing + fnft_nsev_base (src/fnft_nsev.c:266-309,
  * 458-565).  Dsub_req != 0 asks for the pass on the subsampled signals
  * (nse_discretization_preprocess_signal with *Dsub_ptr = Dsub_req; second pass of the
@@ -134,12 +168,18 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         return E_INVALID_ARGUMENT(opts->discretization);
     const FNFT_UINT deg0 = fnftb__akns_degree(akns);
     const FNFT_UINT upsampling = fnftb__akns_upsampling(akns);
-    if (deg0 == 0)
+    /* "slow" discretizations (no polynomial transfer matrix): BO and CF4_2 run on the GPU, the
+     * continuous spectrum as one product of step matrices per spectral point (slow_scatter.cuh) */
+    const int slow = (deg0 == 0);
+    if (slow && akns != fnft__akns_discretization_BO && akns != fnft__akns_discretization_CF4_2)
         return E_NOT_YET_IMPLEMENTED(opts->discretization,
-                                     Only the fast (polynomial) discretizations run on the GPU.);
-    if (!fnftb__akns_on_gpu(akns))
+                                     Of the slow discretizations only BO and CF4_2 run on the GPU.);
+    if (!slow && !fnftb__akns_on_gpu(akns))
         return E_NOT_YET_IMPLEMENTED(opts->discretization,
                                      This splitting scheme has no GPU leaf kernel yet.);
+    /* src/fnft_nsev.c:209-219: the slow discretizations only support Newton localization */
+    if (slow && kappa == +1 && opts->bound_state_localization != fnft_nsev_bsloc_NEWTON)
+        return E_INVALID_ARGUMENT(opts->bound_state_localization);
     if (upsampling > 2)
         return E_NOT_YET_IMPLEMENTED(opts->discretization, Unsupported upsampling factor.);
     const int want_contspec = (contspec != NULL && M > 0);
@@ -171,7 +211,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     const FNFT_UINT D_eff = D_given * upsampling;
     const FNFT_UINT cs_len = want_contspec ? contspec_len(opts->contspec_type, M) : 0;
 
-    size_t chunk = fnftb_max_chunk(ctx, D_eff, (int)deg0, want_contspec ? M : 0, 2,
+    size_t chunk = fnftb_max_chunk(ctx, D_eff, slow ? 1 : (int)deg0, (want_contspec && !slow) ? M : 0, 2,
                                    fnftb__workspace_limit());
     if (chunk > B)
         chunk = B;
@@ -179,7 +219,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
      * neighbouring chunks with the kernels (fnftb_pipeline_*); at least 8 chunks for
      * large batches so that only a small first copy-in / last copy-out stay exposed. */
     const int piped = (!devptr && want_contspec && !want_discspec && B >= 16 && fnftb__pipe_chunks() > 0 &&
-                       Dsub_req == 0);
+                       Dsub_req == 0 && !slow);
     if (piped) {
         const size_t nch = (size_t)fnftb__pipe_chunks();
         size_t c8 = (B + nch - 1) / nch;
@@ -278,7 +318,11 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
 
             /* transfer matrix: nse_fscatter (src/fnft_nsev.c:527).  The Newton path never
              * reads it, so it is only built when a continuous spectrum is wanted. */
-            if (want_contspec) {
+            if (want_contspec && slow) {
+                ret_code = nsev_slow_contspec_chunk(ctx, D_given, T, M, XI, kappa, (int)upsampling, opts,
+                                                    contspec + b0 * cs_len, devptr, st_cur);
+                CHECK_RETCODE(ret_code, leave_fun);
+            } else if (want_contspec) {
                 if (fnftb_fscatter(ctx, &sd) != 0) {
                     ret_code = E_DEVICE;
                     goto leave_fun;

@@ -355,6 +355,37 @@ def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normal
     return np.concatenate(out)
 
 
+def nsev_contspec_slow(q, T, M, XI, kappa=+1, nse_disc=NSE_BO, cstype=0):
+    """Continuous spectrum of fnft_nsev for the slow discretizations BO and CF4_2: one product of D
+    step matrices per spectral point (fnft__akns_scatter_matrix, src/private/fnft__akns_scatter_matrix.c:
+    112-126,206-232, derivative_flag 0), then the epilogue of src/fnft_nsev.c:836-876 with the phase
+    factors of the slow branch (src/private/fnft__nse_discretization.c:240-379)."""
+    q = np.asarray(q, dtype=np.complex128)
+    D = q.shape[0]
+    eps_t = (T[1] - T[0]) / (D - 1)
+    qp = preprocess_signal(q, eps_t, kappa, nse_disc)
+    lw = 0.5 if nse_disc == NSE_CF4_2 else 1.0
+    xi = XI[0] + (XI[1] - XI[0]) / (M - 1) * np.arange(M)
+    l = xi * lw + 0j
+    S11, S12 = np.ones(M, dtype=np.complex128), np.zeros(M, dtype=np.complex128)
+    S21, S22 = np.zeros(M, dtype=np.complex128), np.ones(M, dtype=np.complex128)
+    for n in range(qp.shape[0]):
+        (u11, u12, u21, u22), _ = _bo_step(qp[n], -kappa * np.conj(qp[n]), l, eps_t)
+        S11, S12, S21, S22 = (u11 * S11 + u12 * S21, u11 * S12 + u12 * S22,
+                              u21 * S11 + u22 * S21, u21 * S12 + u22 * S22)
+    bc = 0.5
+    ph_rho = -2.0 * (T[1] + eps_t * bc)
+    ph_a = (T[1] + eps_t * bc) - (T[0] - eps_t * bc)
+    ph_b = -(T[1] + eps_t * bc) - (T[0] - eps_t * bc)
+    out = []
+    if cstype in (0, 2):
+        out.append(S21 * np.exp(1j * xi * ph_rho) / S11)
+    if cstype in (1, 2):
+        out.append(S11 * np.exp(1j * xi * ph_a))
+        out.append(S21 * np.exp(1j * xi * ph_b))
+    return np.concatenate(out)
+
+
 def kdvv(u, T, M, XI, kdv_disc=KDV_2SPLIT4B, evaluate=None):
     """fnft_kdvv, src/fnft_kdvv.c:59-209 (no preprocessing; xi grid negated).
     evaluate: see nsev_contspec."""

@@ -257,6 +257,22 @@ def main():
     nsep_case("mixed_2a_shift", 256, 1.3, 1, 2, 0.2, 0.3, 1, 2, 4, phase_shift=0.8)
     nsep_case("sub_4split4b", 128, 1.2, 0, 1, 0.2, 0.5, 1, 0, 21)
     nsep_case("mixed_2a_1024", 1024, 1.6, 0, 2, 0.15, 0.4, 1, 2, 4)
+    # slow discretizations BO (1) and CF4_2 (22): continuous spectrum by nse_scatter_matrix + Newton
+    for disc in (1, 22):
+        for D, kappa in ((100, 1), (256, 1), (256, -1)):
+            tt = np.linspace(-10, 10, D)
+            qs = 2.7 / np.cosh(tt) * np.exp(0.4j * tt)
+            o = R.nsev_default_opts()
+            o.discretization, o.bound_state_localization, o.discspec_type, o.contspec_type = disc, 1, 2, 2
+            gs = np.array([0.2j - 0.2, 1.2j - 0.21, 2.19j - 0.2])
+            ret, cs, K, bs, nc = R.nsev(qs, [-10, 10], 20, [-2, 2.5], kappa, o, K=3, bound_states=gs)
+            assert ret == 0, (disc, D, kappa, ret)
+            key = f"refrun/slow/{disc}/{D}/{kappa}"
+            G[key + "/q"] = qs
+            G[key + "/guesses"] = gs
+            G[key + "/cs"] = cs
+            G[key + "/bs"] = bs[:K]
+            G[key + "/nc"] = nc[:2 * K]
     pr = rng.standard_normal(60) + 1j * rng.standard_normal(60)
     G["refrun/roots/p"] = pr
     ret = R.lib().fnft__poly_roots_fasteigen

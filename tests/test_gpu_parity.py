@@ -311,6 +311,40 @@ def test_nsep_batch_matches_single_calls(F, disc, loc):
         assert np.array_equal(ms, main[b, :ms.size]) and np.array_equal(au, aux[b, :au.size])
 
 
+def test_nsev_slow_discretizations_bo_cf4_2_vs_reference_runs(F, golden):
+    # fnft_nse_discretization_BO / _CF4_2 as the discretization of fnft_nsev (no polynomial transfer
+    # matrix): continuous spectrum (rho, a, b) and Newton-refined bound states with residues
+    F.lib().fnft_errwarn_setprintf(None)
+    for case in _keys(golden, "refrun/slow/"):
+        disc, D, kappa = map(int, case.split("/"))
+        q = golden[f"refrun/slow/{case}/q"]
+        g = golden[f"refrun/slow/{case}/guesses"]
+        o = F.nsev_default_opts()
+        o.discretization, o.bound_state_localization, o.discspec_type, o.contspec_type = disc, 1, 2, 2
+        ret, cs, K, bs, nc = F.nsev(q, [-10, 10], 20, [-2, 2.5], kappa, o, K=3, bound_states=g)
+        assert ret == 0, case
+        ref = golden[f"refrun/slow/{case}/cs"]
+        for part in range(3):
+            assert max(parity_contract(cs[part * 20:(part + 1) * 20], ref[part * 20:(part + 1) * 20])) < 1, case
+        rbs, rnc = golden[f"refrun/slow/{case}/bs"], golden[f"refrun/slow/{case}/nc"]
+        assert K == rbs.size
+        if K:
+            idx = _match_sets(bs[:K], rbs)
+            assert (np.abs(bs[:K][idx] - rbs) <= 1e-9 * np.abs(rbs)).all()
+            for part in range(2):
+                assert (np.abs(nc[part * K:(part + 1) * K][idx] - rnc[part * K:(part + 1) * K])
+                        <= 1e-9 * np.abs(rnc[part * K:(part + 1) * K])).all()
+    # the other slow discretizations are not implemented, and say so; default localization is
+    # rejected for slow discretizations like in the reference (src/fnft_nsev.c:209-219)
+    o = F.nsev_default_opts()
+    o.discretization = 23
+    o.bound_state_localization = 1
+    assert F.nsev(np.ones(16), [-1, 1], 4, [-1, 1], 1, o)[0] == 6
+    o.discretization = 1
+    o.bound_state_localization = 2
+    assert F.nsev(np.ones(16), [-1, 1], 4, [-1, 1], 1, o)[0] == 2
+
+
 def test_nsev_batch_default_options_matches_single_calls(F):
     D, B = 512, 6
     t = np.linspace(-10, 10, D)

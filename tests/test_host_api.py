@@ -113,11 +113,11 @@ def test_argument_checks_mirror_reference(F):
 def test_not_yet_implemented_paths_are_loud(F):
     F.lib().fnft_errwarn_setprintf(None)
     o = F.nsev_default_opts()
-    o.discretization = 1  # BO: slow scheme, out of scope of the GPU hot path
+    o.discretization = 23  # CF4_3: slow discretization without a GPU kernel
     assert _call_nsev(F, opts=o) == 6
     o = F.nsev_default_opts()
-    o.discretization = 23  # CF4_3: slow scheme as well
-    assert _call_nsev(F, opts=o) == 6
+    o.discretization = 1  # BO runs on the GPU, but only with Newton localization (src/fnft_nsev.c:209-219)
+    assert _call_nsev(F, opts=o) == 2
 
 
 def test_no_cpu_fallback_without_gpu(F):

@@ -126,3 +126,12 @@ def test_reference_accuracy_floor(golden):
     assert rel_err(ref, exact) < 1e-11      # ... while its L1 error is fine
     ours = O.nsev_contspec(golden["floor/q"], (-32.0, 32.0), 40, (-10.0, 10.0), -1)
     assert (np.abs(ours - ref) / np.abs(ref)).max() < 1e-9   # oracle tracks the reference
+
+
+def test_slow_discretizations_vs_reference_runs(golden):
+    # BO and CF4_2 as discretization of fnft_nsev: continuous spectrum through nse_scatter_matrix
+    for case in _keys(golden, "refrun/slow/"):
+        disc, D, kappa = map(int, case.split("/"))
+        q = golden[f"refrun/slow/{case}/q"]
+        cs = O.nsev_contspec_slow(q, [-10, 10], 20, [-2, 2.5], kappa, disc, cstype=2)
+        assert rel_err(cs, golden[f"refrun/slow/{case}/cs"]) < 1e-12, case
