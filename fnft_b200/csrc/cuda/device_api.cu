@@ -471,8 +471,11 @@ static int ensure_tree(fnftb_ctx *c, size_t B, size_t npad, size_t deg0, size_t 
     RC(ensure(c->W, B * sizeof(int)));
     RC(ensure(c->status, B * sizeof(int)));
     RC(ensure(c->tm, B * 4 * (deg_out + 1) * sizeof(cplx)));
-    RC(ensure(c->tt0, (B * npad / 256 + 1) * 8 * sizeof(cplx)));
-    RC(ensure(c->tt1, (B * npad / 256 + 1) * 8 * sizeof(cplx)));
+    // tops of the spectrum path: one per 256 samples (low kernels), or per degree-1024 matrix when a
+    // coefficient level is converted (tree_convert.cuh)
+    const size_t ntops = B * npad / 256 + B * npad * deg0 / 1024 + 1;
+    RC(ensure(c->tt0, ntops * 8 * sizeof(cplx)));
+    RC(ensure(c->tt1, ntops * 8 * sizeof(cplx)));
     return 0;
 }
 

@@ -8,6 +8,7 @@
 #include "tree_low_kernel.cuh"
 #include "tree_low2.cuh"
 #include "tree_up.cuh"
+#include "tree_convert.cuh"
 
 #ifdef FNFTB_EMUL
 static inline void dev_memset0(void *p, size_t bytes, fnftb_stream_t) { memset(p, 0, bytes); }
@@ -182,7 +183,7 @@ static inline int launch_pair_fft(const PairArgs &pa, unsigned grid, int nt, siz
 static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int normalize,
                               const TwTable &T, fnftb_stream_t st, int *cur_out,
                               int use_direct = 1, int smem_n = FNFTB_TREE_SMEM_N, int sym = 0,
-                              int kappa = 0)
+                              int kappa = 0, int n_stop = 1)
 {
     static const int knob_smem_n = tree_knob("FNFT_B200_TREE_SMEM_N", 0);
     static const int max_radix = tree_knob("FNFT_B200_MAX_RADIX", 16);
@@ -192,7 +193,7 @@ static inline int tree_levels(const TreeWork &w, int B, int npad, int deg0, int 
     int cur = 0;
     int n = npad, d = deg0;  // (callers may pass an intermediate level: n matrices of degree d)
     int rc = 0;
-    while (n >= 2) {
+    while (n >= 2 && n > n_stop) {
         PairArgs pa;
         memset(&pa, 0, sizeof(pa));
         pa.in = w.lev[cur];
@@ -592,6 +593,59 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
             return rc;
     }
     int cur = 0;
+#ifndef FNFTB_EMUL
+    // Long products of the general 2x2 path: coefficient levels up to degree 1024, then the
+    // spectrum-carry upper levels (tree_convert.cuh).  Needs a power-of-two degree at every level.
+    static const int knob_conv = tree_knob("FNFT_B200_TREE_CONVERT", 1);
+    const long long total_deg = (long long)dtree * npad;
+    if (knob_conv && !sym && use_direct && w.tws != nullptr && w.tt[0] != nullptr && (d_start & (d_start - 1)) == 0 &&
+        d_start <= 1024 && total_deg >= 4096 && total_deg <= (1LL << 16)) {
+        const int n_conv = (int)(total_deg / 1024);  // matrices of degree 1024 per signal
+        bool ok = true;
+        for (int n = n_conv, l = 11; ok && n >= 2; n /= 2, ++l)
+            ok = up_supported(l, 13);
+        if (ok) {
+            rc = tree_levels(w, B, n_start, d_start, normalize, T, st, &cur, use_direct, smem_n, 0, kappa, n_conv);
+            if (rc)
+                return rc;
+            ConvArgs ca;
+            ca.in = w.lev[cur];
+            ca.out = w.lev[1 - cur];
+            ca.tt_out = (GenTops *)w.tt[1 - cur];
+            ca.tw = *(const TwSet *)w.tws;
+            ca.nmat = (long long)B * n_conv;
+            rc = coef_to_spec2048(ca, st);
+            if (rc)
+                return rc;
+            cudaMemcpyAsync(w.mx[1 - cur], w.mx[cur], sizeof(double) * (size_t)B * n_conv, cudaMemcpyDeviceToDevice, st);
+            cur = 1 - cur;
+            for (int n = n_conv, l = 11; n >= 2; n /= 2, ++l) {
+                UpArgs ua;
+                memset(&ua, 0, sizeof(ua));
+                ua.in = w.lev[cur];
+                ua.out = w.lev[1 - cur];
+                ua.tt_in = w.tt[cur];
+                ua.tt_out = w.tt[1 - cur];
+                ua.mx_in = w.mx[cur];
+                ua.mx_out = w.mx[1 - cur];
+                ua.W = w.W;
+                ua.ws = w.gbuf;
+                ua.B = B;
+                ua.n_in = n;
+                ua.l2n = l;
+                ua.normalize = normalize;
+                ua.kappa = kappa;
+                ua.last = (n == 2) ? 1 : 0;
+                ua.tw = *(const TwSet *)w.tws;
+                rc = up_level(ua, 13, st, false);
+                if (rc)
+                    return rc;
+                cur = 1 - cur;
+            }
+            return tree_finalize(w, cur, B, dtree * npad, deg0 * D, normalize, tm, st, 0, kappa);
+        }
+    }
+#endif
     rc = tree_levels(w, B, n_start, d_start, normalize, T, st, &cur, use_direct, smem_n, sym, kappa);
     if (rc)
         return rc;

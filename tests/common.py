@@ -52,6 +52,19 @@ def sech_chirp(D, T, amp=2.0, chirp=0.3):
     return amp / np.cosh(t) * np.exp(1j * chirp * t * t)
 
 
+def ld_evaluator(eps_t, step_div):
+    """evaluate(p, xi) for oracle.nsev_contspec / oracle.kdvv: Horner's rule in 80-bit long double
+    at z = exp(2i xi eps_t / step_div) -- the exact value of the polynomial the double-precision
+    chirp-z implementations approximate (the reference's loses accuracy where sum|c| >> |p(z)|)."""
+    def ev(p, xi):
+        zz = np.exp(2j * xi.astype(np.longdouble) * np.longdouble(eps_t) / step_div)
+        r = np.zeros_like(zz)
+        for ck in p.astype(np.clongdouble):
+            r = r * zz + ck
+        return r
+    return ev
+
+
 def parity_contract(ours, ref, tol=1e-9, floor=1e-2):
     """The parity contract of this repository ("Parity contract"), derived
     from SURVEY.md 8(c).  Returns two figures normalised by `tol`; both must be < 1:

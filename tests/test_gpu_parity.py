@@ -9,7 +9,7 @@ otherwise the 1e-9 contract of SURVEY.md 8(c) (L1-relative / pointwise / tail)."
 import numpy as np
 import pytest
 
-from common import (AKNS_TEST_BOUND, AKNS_TEST_SCHEMES, CHIRPZ_TEST_A, CHIRPZ_TEST_P, CHIRPZ_TEST_W,
+from common import (AKNS_TEST_BOUND, AKNS_TEST_SCHEMES, ld_evaluator, CHIRPZ_TEST_A, CHIRPZ_TEST_P, CHIRPZ_TEST_W,
                     akns_fscatter_test_input, eval_tm, fmult2x2_test_input, parity_contract,
                     rel_err, sech_chirp)
 from oracle import fnft_oracle as O
@@ -375,6 +375,46 @@ def test_kdvv_default_options_vs_oracle(F):
     assert ret == 0 and not rcs.any()
     for b in range(2):
         assert max(parity_contract(cs[b], O.kdvv(u[b], [-16, 15], M, [-3.55, 3.95], 17))) < 1
+
+
+@pytest.mark.parametrize("D", [1024, 3000, 4096])
+def test_kdvv_default_options_long_signals_vs_oracle(F, D):
+    # 2SPLIT8B (degree 12, stored as 16): coefficient levels up to degree 1024, then the
+    # spectrum-carry upper levels (tree_convert.cuh); D = 4096 is the longest supported (16*4096 = 2^16)
+    M = 64
+    t = np.linspace(-16, 15, D)
+    u = 1.1 / np.cosh(t) ** 2 + 0.3 * np.exp(-(t - 2) ** 2)
+    ret, cs = F.kdvv(u, [-16, 15], M, [-3.55, 3.95], None)
+    assert ret == 0
+    # against the oracle's polynomials evaluated in long double (its double-precision chirp-z, like the
+    # reference's, is off by a few 1e-9 at these degrees)
+    exact = O.kdvv(u, [-16, 15], M, [-3.55, 3.95], 17, evaluate=ld_evaluator(31.0 / (D - 1), 12)).astype(np.complex128)
+    assert max(parity_contract(cs, exact)) < 1
+    assert max(parity_contract(cs, O.kdvv(u, [-16, 15], M, [-3.55, 3.95], 17), tol=1e-8)) < 1
+
+
+@pytest.mark.parametrize("disc,D", [(15, 2048), (13, 1000), (10, 4096), (20, 2048)])
+@pytest.mark.parametrize("kappa", [1, -1])
+def test_nsev_higher_order_schemes_long_signals_vs_oracle(F, disc, D, kappa):
+    # 2SPLIT6B / 2SPLIT5B / 2SPLIT4A / 4SPLIT4A at lengths where the tree switches from the
+    # coefficient kernels to the spectrum-carry levels
+    F.lib().fnft_errwarn_setprintf(None)
+    T, XI, M = [-12.0, 12.0], [-3.0, 2.5], 48
+    q = sech_chirp(D, T, amp=1.7, chirp=0.1)
+    o = F.nsev_default_opts()
+    o.discretization = disc
+    o.contspec_type = F.CSTYPE_BOTH
+    ret, cs, *_ = F.nsev(q, T, M, XI, kappa, o)
+    assert ret == 0
+    sch = O._NSE2AKNS[disc]
+    exact = O.nsev_contspec(q, T, M, XI, kappa, disc, cstype=2,
+                            evaluate=ld_evaluator(24.0 / (D - 1), O.akns_degree(sch) * O.akns_upsampling(sch)))
+    exact = exact.astype(np.complex128)
+    ref = O.nsev_contspec(q, T, M, XI, kappa, disc, cstype=2)
+    for part in range(3):
+        sl = slice(part * M, (part + 1) * M)
+        assert max(parity_contract(cs[sl], exact[sl])) < 1          # the polynomial's exact values
+        assert max(parity_contract(cs[sl], ref[sl], tol=1e-7)) < 1  # the reference algorithm (cpow chirp)
 
 
 def test_kdvv_vs_reference_runs(F, golden):
