@@ -5,7 +5,7 @@
 // 65536.  Once the matrices have degree 1024 this kernel turns every entry into its values at the
 // 2048-th roots of unity (bit-reversed order) plus the top / bottom coefficients, which is the
 // input format of the spectrum-carry upper levels (tree_up.cuh, E = 4): those cost a third less
-// arithmetic per level and never form coefficients in HBM again (same limit: final degree 65536).  The lazy normalisation carries over unchanged (values and tops are those of the
+// arithmetic per level and never form coefficients in HBM again, and reach final degree 131072.  The lazy normalisation carries over unchanged (values and tops are those of the
 // unscaled coefficients; mx[] keeps max|c|).
 //
 //   V[k] = sum_{i=0}^{d} c_i w_N^(ik),  N = 2d = 2048:  FFT_N of c_0..c_{d-1} (zero padded)

@@ -115,6 +115,22 @@ template <int R, bool CONJ>
 DEV void up_twiddle_mul(cplx *v, const cplx *pt, int stride, int o)
 {
 #if FNFTB_TW_DERIVE
+    if constexpr (R > 16) {
+        // radix 32 (last level of a degree-131072 product only): plain table rows [q-1][o]
+#pragma unroll
+        for (int q0 = 1; q0 < R; q0 += 8) {
+            cplx w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (q0 + j < R)
+                    w[j] = __ldg(&pt[(size_t)(q0 + j - 1) * stride + o]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (q0 + j < R)
+                    v[q0 + j] = CONJ ? cmulc(v[q0 + j], w[j]) : cmul(v[q0 + j], w[j]);
+        }
+        return;
+    }
     cplx w1 = __ldg(&pt[o]);
     if (CONJ)
         w1 = cconj(w1);
@@ -143,7 +159,7 @@ DEV void up_twiddle_mul(cplx *v, const cplx *pt, int stride, int o)
                 v[13] = cmul(v[13], cmul(w8, w5));
                 v[14] = cmul(v[14], csq(w7));
                 v[15] = cmul(v[15], cmul(w8, w7));
-                static_assert(R <= 16, "radix");
+                static_assert(R <= 32, "radix");
             }
         }
     }

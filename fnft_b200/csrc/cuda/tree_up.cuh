@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
 // (cols) one thread per (array, o < N2): radix-R inverse pass across the rows, coefficient
 // fix-up and max, then twist + radix-R forward pass (or the coefficient output when last)
 template <int R, bool SYM>
-__global__ void __launch_bounds__(256, (R >= 8) ? 3 : 4) k_up_cols(const UpArgs a)
+__global__ void __launch_bounds__(256, (R >= 32) ? 1 : ((R >= 8) ? 3 : 4)) k_up_cols(const UpArgs a)
 {
     typedef typename UpT<SYM>::Tops Tops;
     constexpr int E = UpT<SYM>::E;
@@ -526,7 +526,7 @@ static inline bool up_supported(int l2n, int l2smem_max)
     if (l2n <= l2smem_max)
         return true;
     const int l2R = l2n - FNFTB_UP_ROW_L2;
-    return l2R >= 1 && l2R <= 4;
+    return l2R >= 1 && l2R <= 5;  // radix 32 across the rows for operand length 2^17
 }
 
 template <bool SYM>
@@ -558,7 +558,8 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
     case 1: rc = up_launch(k_up_cols<2, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
     case 2: rc = up_launch(k_up_cols<4, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
     case 3: rc = up_launch(k_up_cols<8, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    default: rc = up_launch(k_up_cols<16, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    case 4: rc = up_launch(k_up_cols<16, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    default: rc = up_launch(k_up_cols<32, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
     }
     if (rc || a.last)
         return rc;

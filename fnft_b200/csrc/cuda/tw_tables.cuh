@@ -13,7 +13,7 @@
 #include "common.cuh"
 
 #define FNFTB_TW_MINL 3
-#define FNFTB_TW_MAXL 16  // tables for lengths 2^4 .. 2^16
+#define FNFTB_TW_MAXL 17  // tables for lengths 2^3 .. 2^17
 
 struct TwSet {
     const cplx *base;

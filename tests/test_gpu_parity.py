@@ -377,10 +377,10 @@ def test_kdvv_default_options_vs_oracle(F):
         assert max(parity_contract(cs[b], O.kdvv(u[b], [-16, 15], M, [-3.55, 3.95], 17))) < 1
 
 
-@pytest.mark.parametrize("D", [1024, 3000, 4096])
+@pytest.mark.parametrize("D", [1024, 3000, 8192])
 def test_kdvv_default_options_long_signals_vs_oracle(F, D):
     # 2SPLIT8B (degree 12, stored as 16): coefficient levels up to degree 1024, then the
-    # spectrum-carry upper levels (tree_convert.cuh); D = 4096 is the longest supported (16*4096 = 2^16)
+    # spectrum-carry upper levels (tree_convert.cuh); D = 8192 is the longest supported (16*8192 = 2^17)
     M = 64
     t = np.linspace(-16, 15, D)
     u = 1.1 / np.cosh(t) ** 2 + 0.3 * np.exp(-(t - 2) ** 2)
@@ -415,6 +415,20 @@ def test_nsev_higher_order_schemes_long_signals_vs_oracle(F, disc, D, kappa):
         sl = slice(part * M, (part + 1) * M)
         assert max(parity_contract(cs[sl], exact[sl])) < 1          # the polynomial's exact values
         assert max(parity_contract(cs[sl], ref[sl], tol=1e-7)) < 1  # the reference algorithm (cpow chirp)
+
+
+def test_nsev_longest_supported_signal_vs_oracle(F):
+    # D = 65536 samples, 2SPLIT4B: final degree 131072, the last tree level has operand length 2^17
+    # (radix-32 column pass); beyond that the library reports "signal too long" instead of computing
+    D, M = 65536, 32
+    T, XI = [-40.0, 40.0], [-4.0, 4.0]
+    q = sech_chirp(D, T, amp=2.2, chirp=0.02)
+    ret, cs, *_ = F.nsev(q, T, M, XI, 1, None)
+    assert ret == 0
+    assert max(parity_contract(cs, O.nsev_contspec(q, T, M, XI, 1))) < 1
+    F.lib().fnft_errwarn_setprintf(None)
+    ret, *_ = F.nsev(np.ones(2 * D + 2, dtype=np.complex128) * 0.01, T, M, XI, 1, None)
+    assert ret == 5   # FNFT_EC_OTHER from the device layer: loud, no fallback
 
 
 def test_kdvv_vs_reference_runs(F, golden):
