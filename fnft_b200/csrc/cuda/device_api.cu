@@ -166,6 +166,10 @@ struct fnftb_ctx {
     Buf qslot[2], outslot[2], stslot[2];
     int32_t *st_pinned[2] = {nullptr, nullptr};  // pinned host copies of the per-chunk status
     size_t st_pinned_cap[2] = {0, 0};
+    // fully asynchronous mode (fnftb_pipeline_begin with total > 0): one pinned status array for the whole
+    // batch, filled chunk by chunk; the host never waits inside the loop
+    int32_t *st_all = nullptr;
+    size_t st_all_cap = 0, st_all_off = 0, st_all_total = 0;
 };
 
 static TwTable ctx_tw(const fnftb_ctx *c)
@@ -304,6 +308,8 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
     for (int i = 0; i < 2; ++i) {
         if (c->st_pinned[i])
             cudaFreeHost(c->st_pinned[i]);
+        if (i == 0 && c->st_all)
+            cudaFreeHost(c->st_all);
         if (c->ev_h2d[i])
             cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_comp[i])
@@ -336,11 +342,21 @@ void *fnftb_ctx_stream(fnftb_ctx *c) { return (void *)c->st; }
 // caller alternates slots 0, 1, 0, ... with its chunks and calls fnftb_pipeline_wait(slot)
 // before it reads the outputs / status of the chunk that used that slot.
 // ---------------------------------------------------------------------------
-int fnftb_pipeline_begin(fnftb_ctx *c)
+int fnftb_pipeline_begin(fnftb_ctx *c, size_t total_signals)
 {
     if (!c)
         return fail(-2, "invalid argument", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
+    if (total_signals > c->st_all_cap) {
+        if (c->st_all)
+            CU(cudaFreeHost(c->st_all));
+        c->st_all = nullptr;
+        c->st_all_cap = 0;
+        CU(cudaMallocHost((void **)&c->st_all, total_signals * sizeof(int32_t)));
+        c->st_all_cap = total_signals;
+    }
+    c->st_all_total = total_signals;
+    c->st_all_off = 0;
     if (!c->st_h2d) {
         CU(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
@@ -369,10 +385,20 @@ int fnftb_pipeline_wait(fnftb_ctx *c, int slot, const int32_t **status)
     return 0;
 }
 
+int fnftb_pipeline_status(fnftb_ctx *c, const int32_t **status)
+{
+    if (!c || !status)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    *status = c->st_all;
+    return 0;
+}
+
 int fnftb_pipeline_end(fnftb_ctx *c)
 {
     if (!c)
         return fail(-2, "invalid argument", __FILE__, __LINE__);
+    if (!c->pipe_on)
+        return 0;
     c->pipe_on = 0;
     trace_dump();
     g_trace_chunk = 0;
@@ -707,8 +733,14 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
         CU(cudaStreamWaitEvent(c->st_d2h, c->ev_comp[sl], 0));
         trace_mark("d2h_start", g_trace_chunk, c->st_d2h);
         CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st_d2h));
-        CU(cudaMemcpyAsync(c->st_pinned[sl], c->stslot[sl].p, B * sizeof(int), cudaMemcpyDeviceToHost,
-                           c->st_d2h));
+        if (c->st_all_total > 0 && c->st_all_off + B <= c->st_all_total) {
+            CU(cudaMemcpyAsync(c->st_all + c->st_all_off, c->stslot[sl].p, B * sizeof(int), cudaMemcpyDeviceToHost,
+                               c->st_d2h));
+            c->st_all_off += B;
+        } else {
+            CU(cudaMemcpyAsync(c->st_pinned[sl], c->stslot[sl].p, B * sizeof(int), cudaMemcpyDeviceToHost,
+                               c->st_d2h));
+        }
         CU(cudaEventRecord(c->ev_d2h[sl], c->st_d2h));
         trace_mark("d2h_end", g_trace_chunk++, c->st_d2h);
         c->d2h_valid[sl] = 1;

@@ -73,9 +73,14 @@ void *fnftb_ctx_stream(fnftb_ctx *ctx);
  * before reading the outputs of the chunk that used that slot; the per-signal status of
  * that chunk is returned in a pinned buffer owned by the context (the status_host argument
  * of fnftb_contspec is ignored in this mode: a pageable destination would serialise). */
-int fnftb_pipeline_begin(fnftb_ctx *ctx);
+int fnftb_pipeline_begin(fnftb_ctx *ctx, size_t total_signals);
 int fnftb_pipeline_wait(fnftb_ctx *ctx, int slot, const int32_t **status);
 int fnftb_pipeline_end(fnftb_ctx *ctx);
+/* With total_signals > 0 the per-signal status of ALL chunks accumulates in one pinned array
+ * (chunk after chunk, in call order), so the host does not have to wait for a chunk before it
+ * issues the next ones: it enqueues the whole batch, calls fnftb_pipeline_end (which waits for the
+ * three streams) and then reads the array through fnftb_pipeline_status. */
+int fnftb_pipeline_status(fnftb_ctx *ctx, const int32_t **status);
 
 /* Largest number of signals one fscatter+contspec pass may hold given the
  * workspace budget (bytes; 0 = default budget). */

@@ -104,7 +104,7 @@ FNFT_INT fnft_kdvv_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
             c8 = 64;
         if (chunk > c8)
             chunk = c8;
-        if (fnftb_pipeline_begin(ctx) != 0)
+        if (fnftb_pipeline_begin(ctx, 0) != 0)
             return E_DEVICE;
     }
     FNFT_UINT step = chunk;

@@ -247,7 +247,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     sd.eps_t = eps_t;
     sd.defer_final = 1; /* only fnftb_contspec consumes the scattering result here */
 
-    if (piped && fnftb_pipeline_begin(ctx) != 0) {
+    if (piped && fnftb_pipeline_begin(ctx, B) != 0) {
         ret_code = E_DEVICE;
         goto leave_fun;
     }
@@ -334,13 +334,9 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         }
         /* status of the chunk whose results are complete: the current one, or in
          * pipelined mode the previous one (its copy-out overlapped this chunk's kernels) */
-        if (want_contspec && !devptr) {
-            const FNFT_UINT cb0 = piped ? prev_b0 : b0, cnb = piped ? prev_nb : nb;
+        if (want_contspec && !devptr && !piped) {
+            const FNFT_UINT cb0 = b0, cnb = nb;
             const int32_t *st_chk = st_cur;
-            if (piped && cnb > 0 && fnftb_pipeline_wait(ctx, slot ^ 1, &st_chk) != 0) {
-                ret_code = E_DEVICE;
-                goto leave_fun;
-            }
             for (FNFT_UINT b = 0; b < cnb; b++) {
                 if (st_chk[b] == FNFT_EC_DIV_BY_ZERO) {
                     const FNFT_INT ec = E_DIV_BY_ZERO; /* src/fnft_nsev.c:850-852 */
@@ -383,6 +379,25 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         } else if (K != NULL && !devptr) {
             for (FNFT_UINT b = 0; b < nb; b++)
                 K[b0 + b] = 0; /* src/fnft_nsev.c:558-560 */
+        }
+    }
+
+    if (piped) {
+        /* pipelined mode: the whole batch has been enqueued without a single host-side wait; now
+         * wait for the streams and look at the per-signal status of all chunks (src/fnft_nsev.c:850-852) */
+        const int32_t *st_all = NULL;
+        if (fnftb_pipeline_end(ctx) != 0 || fnftb_pipeline_status(ctx, &st_all) != 0 || st_all == NULL) {
+            ret_code = E_DEVICE;
+            goto leave_fun;
+        }
+        for (FNFT_UINT b = 0; b < B; b++) {
+            if (st_all[b] == FNFT_EC_DIV_BY_ZERO) {
+                const FNFT_INT ec = E_DIV_BY_ZERO;
+                if (ret_codes != NULL)
+                    ret_codes[b] = ec;
+                if (ret_code == FNFT_SUCCESS)
+                    ret_code = ec;
+            }
         }
     }
 
