@@ -130,6 +130,48 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
     const int j = sj % a.npoly, s = sj / a.npoly;
     const int n2_0 = tile * C;
     const int Np = a.deg + 1;
+    // Short polynomial, long transform (nsep rings: 8193 coefficients, L = 2^19): only the first
+    // nz = ceil(Np / N2) of the N1 rows are non-zero, so the N1-point column transforms are
+    // evaluated directly, X[k1] = sum_{n1 < nz} y[n1] w_N1^(n1 k1), instead of through the
+    // shared-memory FFT -- 3 terms per output at that size; the kernel becomes a pure stream of
+    // writes.
+    const int nz = (Np + N2 - 1) / N2;
+    if (!a.gen_v && nz <= 4 && N1 >= 32 && nz * (N1 + C) <= C * N1) {
+        cplx *Wt = S;            // [nz][N1]  w_N1^(n1 * k1(pos)), indexed by storage position
+        cplx *Y = S + nz * N1;   // [nz][C]
+        FOR_THREADS(tid, nt)
+        {
+            for (int idx = tid; idx < nz * N1; idx += nt) {
+                const int n1 = idx / N1, pos = idx - n1 * N1;
+                const int k1 = plan_freq_of_pos(a.plan1, pos);
+                Wt[idx] = cispi(-2.0 * (double)((n1 * k1) & (N1 - 1)) / (double)N1);
+            }
+            for (int idx = tid; idx < nz * C; idx += nt) {
+                const int n1 = idx >> a.log2C, c = idx & (C - 1);
+                const long long n = (long long)n1 * N2 + n2_0 + c;
+                cplx v = czero();
+                if (n < Np) {
+                    const cplx p = a.tm[(size_t)s * a.tm_sstride + (size_t)a.ent[j] * Np + (a.deg - n)];
+                    v = cmul(p, a.tab_y[n]);
+                }
+                Y[idx] = v;
+            }
+        }
+        BLOCK_SYNC();
+        FOR_THREADS(tid, nt)
+        {
+            cplx *dst = a.ybuf + (size_t)sj * a.L;
+            for (int idx = tid; idx < C * N1; idx += nt) {
+                const int c = idx & (C - 1), pos = idx >> a.log2C;
+                const int n2 = n2_0 + c;
+                cplx x = Y[c];  // n1 = 0: w = 1
+                for (int n1 = 1; n1 < nz; ++n1)
+                    cfma(x, Y[n1 * C + c], Wt[n1 * N1 + pos]);
+                dst[(size_t)pos * N2 + n2] = cmul(x, a.tab_tw[(size_t)pos * N2 + n2]);
+            }
+        }
+        return;
+    }
     FOR_THREADS(tid, nt)
     {
         for (int idx = tid; idx < C * N1; idx += nt) {

@@ -87,7 +87,9 @@ def test_general_fmult2x2_vs_oracle(E, deg, n, use_direct, smem_n):
 
 
 @pytest.mark.parametrize("deg,M,row_n", [(3, 3, 4096), (3, 6, 4096), (100, 57, 4096), (100, 57, 16),
-                                         (1000, 1500, 64), (2048, 700, 256)])
+                                         (1000, 1500, 64), (2048, 700, 256),
+                                         # short polynomial, long transform: direct column evaluation
+                                         (20, 1000, 16), (40, 3000, 16), (63, 900, 16)])
 def test_chirpz_four_step_vs_oracle(E, deg, M, row_n):
     rng = np.random.default_rng(deg + M)
     p = rng.standard_normal(deg + 1) + 1j * rng.standard_normal(deg + 1)
