@@ -487,4 +487,76 @@ static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t 
 #undef CZ2_BY_R
     return rc;
 }
+// General four-step chirp-z (any L = N1 * 4096, chirpz_driver.cuh) with the row stage of the fast
+// path: k_cz2_rows does "row FFT * FFT(v) * inverse row FFT" about three times faster than the
+// first-generation blk_cz_rows (register-fused stride-1 passes, derived twiddles).  Nothing else
+// changes: the row kernel is self-contained as long as the filter spectrum comes from the same
+// kernel (gen_v), which stores it in its own permuted order.
+static inline int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
+{
+    const CzGeom g = cz_geometry(a.deg, a.M);
+    if (g.N2 != (1 << FNFTB_CZ2_ROW_L2))
+        return cz_run(a, tables, st);
+    a.L = g.L;
+    a.N1 = g.N1;
+    a.N2 = g.N2;
+    a.C = g.C;
+    a.log2C = ilog2i((unsigned)g.C);
+    a.plan1 = make_fft_plan(g.N1);
+    a.plan2 = make_fft_plan(g.N2);
+    const int nt = 256;
+    int rc;
+    a.tab_y = tables;
+    a.tab_out = a.tab_y + (a.deg + 1);
+    a.tab_ph = a.tab_out + a.M;
+    a.tab_tw = a.tab_ph + 3 * (size_t)a.M;
+    {
+        long long tot = a.deg + 1;
+        if (a.M > tot)
+            tot = a.M;
+        if (g.L > tot)
+            tot = g.L;
+        rc = launch_blocks<CzArgs, blk_cz_tables>(a, (unsigned)((tot + nt - 1) / nt), nt, 0, st, "cz_filter");
+        if (rc)
+            return rc;
+    }
+    Cz2Args r;
+    memset(&r, 0, sizeof(r));
+    r.tw = tw;
+    r.vperm = a.vhat;
+    r.l2L = ilog2i((unsigned)g.L);
+    const size_t smem = sizeof(cplx) << FNFTB_CZ2_ROW_L2;
+    // 1. spectrum of the chirp filter: columns into array 0 of the workspace, rows -> vhat (permuted)
+    {
+        CzArgs v = a;
+        v.gen_v = 1;
+        v.fwd_only = 1;
+        v.vhat = a.ybuf;
+        rc = launch_blocks<CzArgs, blk_cz_cols_fwd, 256, 3>(v, (unsigned)(g.N2 / g.C), nt,
+                                                            cz_cols_smem_bytes(g.C, g.N1, 1), st, "cz_filter");
+        if (rc)
+            return rc;
+        r.c = a;
+        r.gen_v = 1;
+        rc = cz2_launch(k_cz2_rows, r, (unsigned)g.N1, 128, smem, st, "cz_filter");
+        if (rc)
+            return rc;
+    }
+    a.gen_v = 0;
+    a.fwd_only = 0;
+    // 2. forward columns of all polynomials
+    rc = launch_blocks<CzArgs, blk_cz_cols_fwd, 256, 3>(a, (unsigned)((size_t)a.B * a.npoly * (g.N2 / g.C)), nt,
+                                                        cz_cols_smem_bytes(g.C, g.N1, 1), st, "cz_cols_fwd");
+    if (rc)
+        return rc;
+    // 3. rows
+    r.c = a;
+    r.gen_v = 0;
+    rc = cz2_launch(k_cz2_rows, r, (unsigned)((size_t)a.B * a.npoly * g.N1), 128, smem, st, "cz_rows");
+    if (rc)
+        return rc;
+    // 4. inverse columns + epilogue
+    return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / g.C)), nt,
+                                                          cz_cols_smem_bytes(g.C, g.N1, a.npoly), st, "cz_cols_inv");
+}
 #endif  // !FNFTB_EMUL

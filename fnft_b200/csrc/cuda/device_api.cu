@@ -723,7 +723,7 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
         if (fast)
             RC(cz2_run(a, (cplx *)c->cztab.p, c->tws, c->st, src.lev ? &src : nullptr));
         else
-            RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+            RC(cz_run_fastrows(a, (cplx *)c->cztab.p, c->tws, c->st));
     }
     if (piped) {
         CU(cudaMemcpyAsync(c->stslot[sl].p, c->status.p, B * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
@@ -1044,7 +1044,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
             a.out_sstride = (size_t)npoly * 3 * Mpts;
             a.out_jstride = 3 * Mpts;
             a.status = (int *)c->status.p;
-            RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+            RC(cz_run_fastrows(a, (cplx *)c->cztab.p, c->tws, c->st));
         }
         ScanArgs sa;
         memset(&sa, 0, sizeof(sa));
@@ -1193,7 +1193,7 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     a.out = (cplx *)c->rs_b.p;
     a.out_sstride = D;
     a.status = (int *)c->status.p;
-    RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+    RC(cz_run_fastrows(a, (cplx *)c->cztab.p, c->tws, c->st));
     // 3. band-limit check, the two phase ramps -> rs_a[B][2][D] (reversed)
     ra.in = (const cplx *)c->rs_b.p;
     ra.out = (cplx *)c->rs_a.p;
@@ -1208,7 +1208,7 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     a.out = (cplx *)c->rs_b.p;
     a.out_sstride = 2 * D;
     a.out_jstride = D;
-    RC(cz_run(a, (cplx *)c->cztab.p, c->st));
+    RC(cz_run_fastrows(a, (cplx *)c->cztab.p, c->tws, c->st));
     // 5. weights + subsampling -> qpre[B][2*Dsub]
     ra.in = (const cplx *)c->rs_b.p;
     ra.out = (cplx *)dstbuf.p;
