@@ -1068,10 +1068,20 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
                                                    c->st, "nsep_scan")));
         CU(cudaMemcpyAsync(nraw.data(), c->nraw.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaMemcpyAsync(nkept.data(), c->nkept.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-        roots.resize(B * npoly * cap);
-        CU(cudaMemcpyAsync(roots.data(), c->roots.p, B * npoly * cap * sizeof(cplx),
-                           cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
+        // copy only as many values per row as the fullest row holds (typically tens of the `cap` slots)
+        size_t maxn = 0;
+        for (size_t i = 0; i < B * npoly; ++i) {
+            const size_t n = (size_t)nkept[i] > cap ? cap : (size_t)nkept[i];
+            if (n > maxn)
+                maxn = n;
+        }
+        roots.resize(B * npoly * maxn + 1);  // compact host copy: row pitch maxn
+        if (maxn > 0) {
+            CU(cudaMemcpy2DAsync(roots.data(), maxn * sizeof(cplx), c->roots.p, cap * sizeof(cplx),
+                                 maxn * sizeof(cplx), B * npoly, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+        }
         for (size_t b = 0; b < B; ++b) {
             if (pass == 0) {
                 cplx *dst = (cplx *)main_host + b * d->Kmax;
@@ -1088,7 +1098,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
                         status_host[b] |= 16;
                         n = (K < d->Kmax) ? d->Kmax - K : 0;
                     }
-                    memcpy(dst + K, roots.data() + (b * 2 + j) * cap, n * sizeof(cplx));
+                    memcpy(dst + K, roots.data() + (b * 2 + j) * maxn, n * sizeof(cplx));
                     K += n;
                 }
                 K_host[b] = (status_host[b] == 1) ? 0 : K;
@@ -1101,7 +1111,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
                     status_host[b] |= 32;
                     n = d->Mmax;
                 }
-                memcpy(dst, roots.data() + b * cap, n * sizeof(cplx));
+                memcpy(dst, roots.data() + b * maxn, n * sizeof(cplx));
                 M_host[b] = n;
             }
         }
