@@ -150,7 +150,8 @@ struct fnftb_ctx {
     // nsep workspace
     Buf fpoly, vals, roots, nraw, nkept;
     // root-finder workspace
-    Buf rt_roots, rt_absc, rt_lg, rt_hull, rt_info;
+    Buf rt_roots, rt_absc, rt_lg, rt_hull, rt_info, rt_lam, rt_cnt;
+    size_t rt_B = 0, rt_n = 0;  // polynomials / degree of the last root-finder call
     // general-length resampling workspace
     Buf rs_a, rs_b;
     // separate homes for the de-rotated (nsep) and the subsampled signals, and saved selections
@@ -297,7 +298,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
                   &c->status, &c->tm, &c->tt0, &c->tt1, &c->twmem, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept,
-                  &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info, &c->rs_a, &c->rs_b, &c->qrot, &c->qsub,
+                  &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info, &c->rt_lam, &c->rt_cnt, &c->rs_a, &c->rs_b, &c->qrot, &c->qsub,
                   &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1]};
     for (Buf *b : all)
         release(*b);
@@ -858,7 +859,7 @@ static int roots_run(fnftb_ctx *c, const cplx *coef, long long cstride, size_t B
 
 int fnftb_nsep_floquet_roots(fnftb_ctx *c, double rhs, void *roots_host, int32_t *info_host)
 {
-    if (!c || !roots_host || c->tmB == 0 || c->deg < 2 || c->tm_entries != 4)
+    if (!c || c->tmB == 0 || c->deg < 2 || c->tm_entries != 4)
         return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
     RC(ctx_finalize(c));
@@ -1307,16 +1308,61 @@ static int roots_run(fnftb_ctx *c, const cplx *coef, long long cstride, size_t B
         return fail(-6, "polynomial degree too large for the GPU root finder (max 8192)", __FILE__, __LINE__);
     if (rc)
         return fail(rc, "root finder launch failed", __FILE__, __LINE__);
-    CU(cudaMemcpyAsync(roots_host, c->rt_roots.p, B * n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+    c->rt_B = B;
+    c->rt_n = n;
+    if (roots_host)
+        CU(cudaMemcpyAsync(roots_host, c->rt_roots.p, B * n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     if (info_host)
         CU(cudaMemcpyAsync(info_host, c->rt_info.p, B * 4 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    if (roots_host || info_host)
+        CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int fnftb_roots_lambda(fnftb_ctx *c, double lam_den, const double *box, int use_box3, void *lam_host,
+                       size_t stride, int32_t *count_host)
+{
+    if (!c || !lam_host || !count_host || c->rt_B == 0 || stride == 0)
+        return fail(-2, "invalid argument / no roots held", __FILE__, __LINE__);
+    if (use_box3 && (!c->have_box3 || c->B != c->rt_B))
+        return fail(-2, "no per-signal bound available", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t B = c->rt_B, n = c->rt_n;
+    RC(ensure(c->rt_lam, B * n * sizeof(cplx)));
+    RC(ensure(c->rt_cnt, B * sizeof(int)));
+    RootsLamArgs a;
+    a.roots = (const cplx *)c->rt_roots.p;
+    a.info = (const int *)c->rt_info.p;
+    a.lam = (cplx *)c->rt_lam.p;
+    a.count = (int *)c->rt_cnt.p;
+    a.n = (int)n;
+    a.lam_den = lam_den;
+    a.filtering = box ? 1 : 0;
+    for (int i = 0; i < 4; ++i)
+        a.box[i] = box ? box[i] : 0.0;
+    a.box3 = use_box3 ? (const double *)c->box3.p : nullptr;
+    k_roots_lambda<<<(unsigned)B, 256, 0, c->st>>>(a);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(count_host, c->rt_cnt.p, B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    size_t maxn = 0;
+    for (size_t b = 0; b < B; ++b) {
+        const size_t k = (size_t)count_host[b] > stride ? stride : (size_t)count_host[b];
+        if (k > maxn)
+            maxn = k;
+    }
+    if (maxn > 0) {
+        CU(cudaMemcpy2DAsync(lam_host, stride * sizeof(cplx), c->rt_lam.p, n * sizeof(cplx), maxn * sizeof(cplx), B,
+                             cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
     return 0;
 }
 
 int fnftb_poly_roots(fnftb_ctx *c, int ent, void *roots_host, int32_t *info_host)
 {
-    if (!c || !roots_host || c->tmB == 0 || c->deg < 1 || ent < 0 || ent >= (int)c->tm_entries)
+    if (!c || c->tmB == 0 || c->deg < 1 || ent < 0 || ent >= (int)c->tm_entries)
         return fail(-2, "invalid argument / no transfer matrix held", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
     RC(ctx_finalize(c));

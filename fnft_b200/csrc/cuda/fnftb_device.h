@@ -111,6 +111,14 @@ int fnftb_subsample(fnftb_ctx *ctx, size_t nskip, size_t Dsub);
  * [B][4] = {leading zeros, effective degree, sweeps, roots that did not converge}. */
 int fnftb_poly_roots(fnftb_ctx *ctx, int ent, void *roots_host, int32_t *info_host);
 
+/* z -> lambda = log(z)/(i*lam_den) and box filter (order preserving) of the roots found by the LAST
+ * fnftb_poly_roots / fnftb_nsep_floquet_roots call, on the device; only the survivors are copied:
+ * lam_host[b*stride + i], i < count_host[b] (counts may exceed stride: then only stride values are
+ * stored).  box == NULL: no filtering.  use_box3: the upper imaginary bound of signal b is the value
+ * computed by the last fnftb_imbound call instead of box[3]. */
+int fnftb_roots_lambda(fnftb_ctx *ctx, double lam_den, const double *box, int use_box3, void *lam_host,
+                       size_t stride, int32_t *count_host);
+
 /* leaves + product tree for the staged signals */
 int fnftb_fscatter(fnftb_ctx *ctx, const fnftb_scatter_desc *desc);
 

@@ -305,3 +305,64 @@ static inline int roots_launch(const RootsArgs &a, int B, cudaStream_t st)
 }
 
 #endif  // FNFTB_EMUL
+
+#ifndef FNFTB_EMUL
+// ---- z -> lambda and bounding-box filter on the device ---------------------------------------
+// lambda = log(z) / (i * lam_den)   (fnft__akns_discretization_z_to_lambda,
+// src/private/fnft__akns_discretization.c:225-240) followed by misc_filter
+// (src/private/fnft__misc.c:114-157): order-preserving compaction of the values inside the box, so
+// that only the survivors (tens out of thousands of roots) travel to the host.
+struct RootsLamArgs {
+    const cplx *roots;   // [B][n]
+    const int *info;     // [B][4] (m = info[1] valid roots per polynomial)
+    cplx *lam;           // [B][n] compacted
+    int *count;          // [B]
+    int n;
+    double lam_den;
+    int filtering;       // 0: keep everything
+    double box[4];       // re_min, re_max, im_min, im_max
+    const double *box3;  // per-polynomial im_max (overrides box[3]) or NULL
+};
+
+__global__ void __launch_bounds__(256) k_roots_lambda(const RootsLamArgs a)
+{
+    __shared__ int cnt[256];
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int m = a.info[4 * b + 1];
+    const cplx *z = a.roots + (size_t)b * a.n;
+    cplx *out = a.lam + (size_t)b * a.n;
+    const double im_max = a.box3 ? a.box3[b] : a.box[3];
+    const int per = (m + nt - 1) / nt;
+    const int lo = min(tid * per, m), hi = min(lo + per, m);
+    const double f = 1.0 / a.lam_den;
+    // pass 1: count
+    int k = 0;
+    for (int i = lo; i < hi; ++i) {
+        const cplx zi = z[i];
+        const double re = atan2(zi.y, zi.x) * f, im = -log(hypot(zi.x, zi.y)) * f;
+        const bool keep = !a.filtering || (re >= a.box[0] && re <= a.box[1] && im >= a.box[2] && im <= im_max);
+        k += keep ? 1 : 0;
+    }
+    cnt[tid] = k;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t < nt; ++t) {
+            const int c = cnt[t];
+            cnt[t] = run;
+            run += c;
+        }
+        a.count[b] = run;
+    }
+    __syncthreads();
+    // pass 2: write in order
+    int w = cnt[tid];
+    for (int i = lo; i < hi; ++i) {
+        const cplx zi = z[i];
+        const double re = atan2(zi.y, zi.x) * f, im = -log(hypot(zi.x, zi.y)) * f;
+        const bool keep = !a.filtering || (re >= a.box[0] && re <= a.box[1] && im >= a.box[2] && im <= im_max);
+        if (keep)
+            out[w++] = make_cplx(re, im);
+    }
+}
+#endif

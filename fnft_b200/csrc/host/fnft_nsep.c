@@ -129,14 +129,17 @@ static FNFT_INT nsep_subsample_refine_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_U
     rd.eps_t = eps_t;
     rd.tol = refine_tol;
 
+/* z_to_lambda (fnft__akns_discretization.c:225-240) and the box filter on the device, only the
+ * survivors are copied (row stride deg); misc_filter_nonreal here */
 #define NSEP_POSTPROCESS_ROOTS(do_nonreal)                                                   \
+    if (fnftb_roots_lambda(ctx, lam_den, opts->filtering != fnft_nsep_filt_NONE ? box : NULL, 0, roots, deg, \
+                           Kn) != 0) {                                                        \
+        ret_code = E_DEVICE;                                                                  \
+        goto leave_fun;                                                                       \
+    }                                                                                         \
     for (FNFT_UINT b = 0; b < nb; b++) {                                                      \
         FNFT_COMPLEX *buf = roots + b * deg;                                                  \
-        FNFT_UINT Kb = (FNFT_UINT)info[4 * b + 1];                                            \
-        for (FNFT_UINT i = 0; i < Kb; i++) /* z_to_lambda, fnft__akns_discretization.c:225-240 */ \
-            buf[i] = clog(buf[i]) / (I * lam_den);                                            \
-        if (opts->filtering != fnft_nsep_filt_NONE)                                           \
-            fnftb__filter_box(&Kb, buf, box);                                                 \
+        FNFT_UINT Kb = (FNFT_UINT)Kn[b];                                                      \
         if (do_nonreal)                                                                       \
             filter_nonreal(&Kb, buf, tol_im);                                                 \
         Kn[b] = (int32_t)Kb;                                                                  \
@@ -162,7 +165,7 @@ static FNFT_INT nsep_subsample_refine_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_U
             rhs_step /= nvals - 1;
         for (FNFT_UINT nval = 0; nval < nvals; nval++) {
             const FNFT_REAL rhs = 2.0 * (rhs_0 + nval * rhs_step);
-            if (fnftb_nsep_floquet_roots(ctx, rhs, roots, info) != 0) {
+            if (fnftb_nsep_floquet_roots(ctx, rhs, NULL, NULL) != 0) {
                 ret_code = E_DEVICE;
                 goto leave_fun;
             }
@@ -200,7 +203,7 @@ static FNFT_INT nsep_subsample_refine_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_U
         }
     }
     if (aux_out != NULL) { /* :642-691 */
-        if (fnftb_poly_roots(ctx, 1, roots, info) != 0) {
+        if (fnftb_poly_roots(ctx, 1, NULL, NULL) != 0) {
             ret_code = E_DEVICE;
             goto leave_fun;
         }

@@ -251,13 +251,11 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         ret_code = E_DEVICE;
         goto leave_fun;
     }
-    FNFT_UINT prev_b0 = 0, prev_nb = 0; /* chunk whose results are still in flight */
-    int slot = 0;
     FNFT_UINT step = chunk;
-    for (FNFT_UINT b0 = 0; b0 < B || prev_nb > 0; b0 += step) {
+    for (FNFT_UINT b0 = 0; b0 < B; b0 += step) {
         step = piped ? fnftb__pipe_step(b0, B, chunk) : chunk; /* tapered at both ends */
-        const FNFT_UINT nb = (b0 >= B) ? 0 : ((B - b0 < step) ? (B - b0) : step);
-        int32_t *st_cur = status ? status + (size_t)slot * chunk : NULL;
+        const FNFT_UINT nb = (B - b0 < step) ? (B - b0) : step;
+        int32_t *st_cur = status;
         if (nb > 0 && want_discspec && bsloc == fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE && Dsub_req == 0) {
             /* First step of the mixed method (src/fnft_nsev.c:276-296): initial guesses from
              * the fast eigenvalue method on a subsampled signal. */
@@ -332,8 +330,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                 CHECK_RETCODE(ret_code, leave_fun);
             }
         }
-        /* status of the chunk whose results are complete: the current one, or in
-         * pipelined mode the previous one (its copy-out overlapped this chunk's kernels) */
+        /* status of this chunk (pipelined mode: all chunks at once after the loop) */
         if (want_contspec && !devptr && !piped) {
             const FNFT_UINT cb0 = b0, cnb = nb;
             const int32_t *st_chk = st_cur;
@@ -349,13 +346,6 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
             if (ret_code != FNFT_SUCCESS && ret_codes == NULL)
                 goto leave_fun;
         }
-        if (piped) {
-            prev_b0 = b0;
-            prev_nb = nb;
-            slot ^= 1;
-        }
-        if (nb == 0)
-            break;
 
         if (want_discspec) {
             const int fast = (bsloc == fnft_nsev_bsloc_FAST_EIGENVALUE);

@@ -104,32 +104,55 @@ FNFT_INT fnftb__nsev_fasteig_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D_eff
         if (fnftb_fscatter(ctx, &sd) != 0)
             return E_DEVICE;
     }
-    roots = malloc(nb * deg * sizeof(FNFT_COMPLEX));
-    info = malloc(nb * 4 * sizeof(int32_t));
+    /* poly_roots_fasteigen(deg, transfer_matrix, buffer), :702 -- the roots stay on the device */
+    if (fnftb_poly_roots(ctx, 0, NULL, NULL) != 0)
+        return E_DEVICE;
     box3 = malloc(nb * sizeof(double));
-    if (roots == NULL || info == NULL || box3 == NULL) {
+    info = malloc(nb * sizeof(int32_t));
+    if (box3 == NULL || info == NULL) {
         ret_code = E_NOMEM;
-        goto leave_fun;
-    }
-    /* poly_roots_fasteigen(deg, transfer_matrix, buffer), :702 */
-    if (fnftb_poly_roots(ctx, 0, roots, info) != 0) {
-        ret_code = E_DEVICE;
         goto leave_fun;
     }
     double box[4];
     int use_box3;
     ret_code = nsev_bounding_boxes(ctx, nb, upsampling, T, eps_t, opts, box, box3, &use_box3);
     CHECK_RETCODE(ret_code, leave_fun);
-    /* z -> lambda (src/private/fnft__akns_discretization.c:225-240), filter, merge (:717-724) */
+    /* z -> lambda (src/private/fnft__akns_discretization.c:225-240) and the box filter (:717-720) on
+     * the device; merge (order dependent, :721-723) here.  Room for every root is only needed when
+     * nothing is filtered. */
     const FNFT_REAL degree1step = (FNFT_REAL)(deg0 * upsampling);
+    const int filtering = (opts->bound_state_filtering != fnft_nsev_bsfilt_NONE);
+    FNFT_UINT stride = filtering ? (deg < 4096 ? deg : 4096) : deg;
+    box[3] = INFINITY; /* per-signal upper bounds come from box3 */
+    for (;;) {
+        roots = malloc(nb * stride * sizeof(FNFT_COMPLEX));
+        if (roots == NULL) {
+            ret_code = E_NOMEM;
+            goto leave_fun;
+        }
+        if (fnftb_roots_lambda(ctx, 2 * eps_t / degree1step, filtering ? box : NULL, filtering && use_box3,
+                               roots, stride, info) != 0) {
+            ret_code = E_DEVICE;
+            goto leave_fun;
+        }
+        FNFT_UINT mx = 0;
+        for (FNFT_UINT b = 0; b < nb; b++)
+            if ((FNFT_UINT)info[b] > mx)
+                mx = (FNFT_UINT)info[b];
+        if (mx <= stride)
+            break;
+        free(roots); /* more survivors than expected: once more with room for all of them */
+        roots = NULL;
+        stride = mx;
+    }
     for (FNFT_UINT b = 0; b < nb; b++) {
-        FNFT_COMPLEX *buf = roots + b * deg;
-        FNFT_UINT Kb = (FNFT_UINT)info[4 * b + 1]; /* roots of the zero-stripped polynomial */
-        for (FNFT_UINT i = 0; i < Kb; i++)
-            buf[i] = clog(buf[i]) / (2 * I * eps_t / degree1step);
-        if (opts->bound_state_filtering != fnft_nsev_bsfilt_NONE) {
-            box[3] = box3[b];
-            fnftb__filter_box(&Kb, buf, box);
+        FNFT_COMPLEX *buf = roots + b * stride;
+        FNFT_UINT Kb = (FNFT_UINT)info[b];
+        if (filtering) {
+            if (!use_box3) { /* BASIC: the common box only */
+                const FNFT_REAL bx[4] = {box[0], box[1], box[2], INFINITY};
+                fnftb__filter_box(&Kb, buf, bx);
+            }
             fnftb__merge(&Kb, buf, sqrt(FNFT_EPSILON));
         }
         if (Kb > Kmax) { /* :728-731 */
