@@ -1299,13 +1299,14 @@ static int roots_run(fnftb_ctx *c, const cplx *coef, long long cstride, size_t B
     ra.info = (int *)c->rt_info.p;
     static const int knob_maxit = tree_knob("FNFT_B200_ROOTS_MAXIT", 200);
     ra.maxit = knob_maxit;
+    ra.in_global = 0;
     if (g_fnftb_profile_on)
         fnftb_profile_begin("poly_roots", c->st);
     const int rc = roots_launch(ra, (int)B, c->st);
     if (g_fnftb_profile_on)
         fnftb_profile_end(c->st);
     if (rc == -6)
-        return fail(-6, "polynomial degree too large for the GPU root finder (max 8192)", __FILE__, __LINE__);
+        return fail(-6, "polynomial degree too large for the GPU root finder (max 32768)", __FILE__, __LINE__);
     if (rc)
         return fail(rc, "root finder launch failed", __FILE__, __LINE__);
     c->rt_B = B;

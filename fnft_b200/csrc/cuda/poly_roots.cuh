@@ -11,8 +11,8 @@
 //
 // (cubically convergent, embarrassingly parallel over i, O(n^2) per sweep).
 //
-//   * one CTA per polynomial, roots in shared memory (Jacobi sweeps: all updates of a sweep
-//     use the previous sweep's roots), coefficients read through the read-only path (all lanes
+//   * one CTA per polynomial, roots in shared memory (degree <= 8192; in the output array in global
+//     memory up to 32768), groups of roots updated Jacobi style, Gauss-Seidel from group to group, coefficients read through the read-only path (all lanes
 //     read the same address: broadcast);
 //   * p and p' by Horner's rule in double; for |z| > 1 on the reversed polynomial in w = 1/z
 //     (p(z) = z^n q(w),  N = z/(n - w q'(w)/q(w))), so nothing overflows;
@@ -43,6 +43,7 @@ struct RootsArgs {
     int *hull;          // [B][n+2] workspace: vertices of the upper convex hull
     int *info;          // [B][4]: lead, m (effective degree), sweeps used, roots not converged
     int maxit;
+    int in_global;      // 1: the sweeps work on `roots` in global memory (degree > 8192)
 };
 
 // ---- start values -------------------------------------------------------------------------
@@ -145,9 +146,13 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth(const RootsArgs a)
     const cplx *c = a.coef + (size_t)b * a.cstride + lead;
     const double *ac = a.absc + (size_t)b * (n + 1) + lead;
     cplx *groots = a.roots + (size_t)b * n;
-    cplx *z = (cplx *)fnftb_smem;  // [m]
-    for (int i = tid; i < m; i += nt)
-        z[i] = groots[i];
+    // working copy of the roots: shared memory up to degree 8192, else the output array itself
+    // (every access below is a broadcast read or a thread's own element; barriers order the sweeps)
+    cplx *z = a.in_global ? groots : (cplx *)fnftb_smem;  // [m]
+    if (!a.in_global) {
+        for (int i = tid; i < m; i += nt)
+            z[i] = groots[i];
+    }
     __syncthreads();
     const int G = (m + R * nt - 1) / (R * nt);  // <= 32 / R
     unsigned done = 0;  // bit g*R + r: that root has converged (or does not exist)
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth(const RootsArgs a)
             if (!((done >> q) & 1u)) {  // still moving after maxit sweeps: not a root, say so
                 ++notconv;
                 groots[i] = make_cplx(nan(""), nan(""));
-            } else {
+            } else if (!a.in_global) {
                 groots[i] = z[i];
             }
         }
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth(const RootsArgs a)
 template <int R, int MAXNT>
 static inline int roots_launch_r(const RootsArgs &a, int B, int nt, cudaStream_t st)
 {
-    const size_t smem = sizeof(cplx) * (size_t)a.n;
+    const size_t smem = a.in_global ? 0 : sizeof(cplx) * (size_t)a.n;
     auto kern = k_roots_aberth<R, MAXNT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -282,13 +287,15 @@ static inline int roots_launch_r(const RootsArgs &a, int B, int nt, cudaStream_t
 }
 
 // Launches both kernels for B polynomials of nominal degree n.  Returns 0, or -6 when n
-// exceeds what one CTA can hold (roots in shared memory: n <= 8192).
-static inline int roots_launch(const RootsArgs &a, int B, cudaStream_t st)
+// exceeds 32768 (roots in shared memory up to 8192, in global memory beyond).
+static inline int roots_launch(const RootsArgs &a_in, int B, cudaStream_t st)
 {
-    if (a.n < 1)
+    if (a_in.n < 1)
         return -2;
-    if (a.n > 8192)
+    if (a_in.n > 32768)  // 32 roots per thread (one bit each in `done`)
         return -6;
+    RootsArgs a = a_in;
+    a.in_global = (a.n > 8192) ? 1 : 0;
     k_roots_init<<<B, 256, 0, st>>>(a);
     ++g_fnftb_launch_count;
     // One root per group (R = 1) measured fastest on B200: converged roots drop out one by one,

@@ -155,7 +155,7 @@ def test_poly_roots_fasteigen_reference_golden(F, golden):
     assert ret == 0 and np.abs(roots[idx] - ref).max() <= 1e-11 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("n", [1, 2, 255, 1024, 1025, 3640, 8192])
+@pytest.mark.parametrize("n", [1, 2, 255, 1024, 1025, 3640, 8192, 13440])
 def test_poly_roots_residuals_and_vieta(F, n):
     # size-independent properties: every returned value is a root to working precision
     # (|p(z)| <= 16 n eps sum|c_k||z|^k, evaluated in long double) and the roots add up to
