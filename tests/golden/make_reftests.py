@@ -1,6 +1,6 @@
 """Generates tests/golden/reftests.npz + reftests.json -- run in the BUILD CONTAINER only.
 
-The reference's end-to-end tests (test/fnft_nsev/*.c, test/fnft_kdvv/*.c) all have the form
+The reference's end-to-end tests (test/fnft_nsev/*.c, test/fnft_kdvv/*.c, test/fnft_nsep/*.c) all have the form
     opts = defaults; opts.<field> = ...; <x>_testcases_test_fnft(tc, D, error_bounds, &opts); ...
 Each test file is compiled here UNCHANGED from /root/reference together with a stub of
 <x>_testcases_test_fnft that only records its arguments (test case, D, the six error bounds, the
@@ -34,6 +34,21 @@ STUB = r'''
 #include <stdio.h>
 #include "fnft_nsev.h"
 #include "fnft_kdvv.h"
+#include "fnft_nsep.h"
+FNFT_INT fnft__nsep_testcases_test_fnft(int tc, FNFT_UINT D, FNFT_REAL eb[3], fnft_nsep_opts_t *o)
+{
+    fnft_nsep_opts_t d = fnft_nsep_default_opts();
+    if (o == NULL)
+        o = &d;
+    printf("{\"fn\": \"nsep\", \"tc\": %d, \"D\": %zu, \"eb\": [%.17g, %.17g, %.17g], \"localization\": %d, "
+           "\"filtering\": %d, \"bounding_box\": [%.17g, %.17g, %.17g, %.17g], \"max_evals\": %zu, "
+           "\"discretization\": %d, \"normalization_flag\": %d, \"floquet_range\": [%.17g, %.17g], "
+           "\"points_per_spine\": %zu, \"Dsub\": %zu, \"tol\": %.17g}\n", tc, D, eb[0], eb[1], eb[2],
+           (int)o->localization, (int)o->filtering, o->bounding_box[0], o->bounding_box[1], o->bounding_box[2],
+           o->bounding_box[3], o->max_evals, (int)o->discretization, (int)o->normalization_flag,
+           o->floquet_range[0], o->floquet_range[1], o->points_per_spine, o->Dsub, o->tol);
+    return 0;
+}
 FNFT_INT fnft__nsev_testcases_test_fnft(int tc, FNFT_UINT D, const FNFT_REAL eb[6], fnft_nsev_opts_t *o)
 {
     printf("{\"fn\": \"nsev\", \"tc\": %d, \"D\": %zu, \"eb\": [%.17g, %.17g, %.17g, %.17g, %.17g, %.17g], "
@@ -59,7 +74,7 @@ def record_calls():
         open(stub, "w").write(STUB)
         inc = ["-I" + REFLIB_DIR, "-I" + os.path.join(REF, "include"), "-I" + os.path.join(REF, "include", "private"),
                "-I" + os.path.join(REF, "include", "3rd_party", "kiss_fft")]
-        for sub in ("fnft_nsev", "fnft_kdvv"):
+        for sub in ("fnft_nsev", "fnft_kdvv", "fnft_nsep"):
             for src in sorted(glob.glob(os.path.join(REF, "test", sub, "*.c"))):
                 exe = os.path.join(tmp, "t.out")
                 subprocess.check_call(["gcc", "-std=gnu99", "-w", "-O0"] + inc + [src, stub, "-L" + REFLIB_DIR,
@@ -112,6 +127,24 @@ def kdvv_case(tc, D):
     return dict(q=a(q, D), T=np.array(T[:]), XI=np.array(XI[:]), contspec=a(cs, Mv))
 
 
+def nsep_case(tc, D):
+    L = R.lib()
+    q, ms, au, sh = (C.c_void_p() for _ in range(4))
+    T, rb = (C.c_double * 2)(), (C.c_double * 4)()
+    ps = C.c_double()
+    K, M, kappa = C.c_size_t(), C.c_size_t(), C.c_int32()
+    f = L.fnft__nsep_testcases
+    f.restype = C.c_int32
+    f.argtypes = None
+    rc = f(C.c_int(tc), C.c_size_t(D), C.byref(q), T, C.byref(ps), C.byref(K), C.byref(ms), C.byref(M), C.byref(au),
+           C.byref(sh), C.byref(kappa), rb)
+    assert rc == 0
+    a = lambda p, n: (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128).copy()
+                      if p.value and n else np.zeros(0, dtype=np.complex128))
+    return dict(q=a(q, D), T=np.array(T[:]), phase_shift=np.array(ps.value), kappa=np.array(kappa.value),
+                mainspec=a(ms, K.value), auxspec=a(au, M.value), remove_box=np.array(rb[:]))
+
+
 def main():
     calls = record_calls()
     G = {}
@@ -119,7 +152,7 @@ def main():
         key = "%s/%d/%d" % (c["fn"], c["tc"], c["D"])
         if key + "/q" in G:
             continue
-        data = nsev_case(c["tc"], c["D"]) if c["fn"] == "nsev" else kdvv_case(c["tc"], c["D"])
+        data = {"nsev": nsev_case, "kdvv": kdvv_case, "nsep": nsep_case}[c["fn"]](c["tc"], c["D"])
         for k, v in data.items():
             G[key + "/" + k] = v
     np.savez_compressed(os.path.join(HERE, "reftests.npz"), **G)

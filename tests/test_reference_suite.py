@@ -1,7 +1,7 @@
 """The reference's own end-to-end test suite, replayed against libfnft_b200.so on the GPU.
 
 tests/golden/reftests.json lists every call <x>_testcases_test_fnft(test case, D, error_bounds, opts)
-that the 84 test programs under test/fnft_nsev and test/fnft_kdvv of the reference make (recorded by
+that the test programs under test/fnft_nsev, test/fnft_kdvv and test/fnft_nsep of the reference make (recorded by
 compiling those programs unchanged against a logging stub, tests/golden/make_reftests.py);
 tests/golden/reftests.npz holds the test cases produced by the reference's generators
 (src/private/fnft__nsev_testcases.c:32-594, fnft__kdvv_testcases.c:32-290): signal, exact spectra.
@@ -80,8 +80,47 @@ def _ids():
 def test_reference_suite_call(F, cases, call):
     key = "%s/%d/%d" % (call["fn"], call["tc"], call["D"])
     q = cases[key + "/q"]
-    T, XI = cases[key + "/T"], cases[key + "/XI"]
+    T = cases[key + "/T"]
+    XI = cases[key + "/XI"] if call["fn"] != "nsep" else None
     eb = np.array(call["eb"], dtype=np.float64)
+    if call["fn"] == "nsep":
+        # nsep_testcases_test_fnft, src/private/fnft__nsep_testcases.c:297-402
+        import ctypes as C
+        o = F.nsep_default_opts()
+        o.localization, o.filtering, o.max_evals = call["localization"], call["filtering"], call["max_evals"]
+        o.discretization, o.normalization_flag = call["discretization"], call["normalization_flag"]
+        o.points_per_spine, o.Dsub, o.tol = call["points_per_spine"], call["Dsub"], call["tol"]
+        for i in range(4):
+            o.bounding_box[i] = call["bounding_box"][i]
+        o.floquet_range[0], o.floquet_range[1] = call["floquet_range"]
+        deg = {0: 1, 4: 1, 10: 4, 11: 2, 20: 4, 21: 2}[call["discretization"]]      # nse_discretization_degree
+        K = 2 * deg * q.size + 1                                             # :326-327
+        ret, ms, au = F.nsep(q, T, int(cases[key + "/kappa"]), o, K=K, M=K,
+                             phase_shift=float(cases[key + "/phase_shift"]))
+        assert ret == 0, ret
+        box = np.array([o.bounding_box[i] for i in range(4)])                # as left behind by fnft_nsep
+        rb = cases[key + "/remove_box"]
+
+        def keep_in(v, b):      # misc_filter, fnft__misc.c:114-157
+            return v[(v.real >= b[0]) & (v.real <= b[1]) & (v.imag >= b[2]) & (v.imag <= b[3])]
+
+        def drop_in(v, b):      # misc_filter_inv, fnft__misc.c:159-203
+            inside = (v.real > b[0]) & (v.real < b[1]) & (v.imag > b[2]) & (v.imag < b[3])
+            return v[~inside]
+        ms_x = drop_in(keep_in(cases[key + "/mainspec"], box), rb)
+        au_x = drop_in(keep_in(cases[key + "/auxspec"], box), rb)
+        ms, au = drop_in(ms, rb), drop_in(au, rb)
+
+        def dist(a, b):         # nsep_compare_nfs, :252-295
+            if a.size == 0 and b.size == 0:
+                return 0.0
+            if a.size == 0 or b.size == 0:
+                return np.nan
+            return hausdorff(a, b)
+        errs = [dist(ms, ms_x), dist(au, au_x), 0.0]
+        for i in range(3):
+            assert errs[i] <= eb[i], "error %d: %.3e > bound %.3e (%s)" % (i, errs[i], eb[i], call["file"])
+        return
     if call["fn"] == "kdvv":
         exact = cases[key + "/contspec"]
         o = F.kdvv_default_opts()
