@@ -548,8 +548,8 @@ int fnftb_fscatter(fnftb_ctx *c, const fnftb_scatter_desc *d)
     const size_t deg_out = (size_t)d->deg0 * c->D;
     const size_t dtree = (size_t)tree_leaf_degree(d->scheme, d->deg0);
     // longest pair product: cyclic length dtree*npad <= 2^16 rows of <= 64 * 1024 (tree_driver.cuh)
-    // longest product: degree 2^17 (operand length 2^17 at the last level of the spectrum-carry path)
-    if (dtree * npad > ((size_t)1 << 17))
+    // longest product: degree 2^18 (operand length 2^18 at the last level of the spectrum-carry path)
+    if (dtree * npad > ((size_t)1 << 18))
         return fail(-6, "signal too long for this build", __FILE__, __LINE__);
     RC(ensure_tree(c, c->B, npad, dtree, deg_out));
     const TwTable T = ctx_tw(c);

@@ -599,7 +599,7 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
     static const int knob_conv = tree_knob("FNFT_B200_TREE_CONVERT", 1);
     const long long total_deg = (long long)dtree * npad;
     if (knob_conv && !sym && use_direct && w.tws != nullptr && w.tt[0] != nullptr && (d_start & (d_start - 1)) == 0 &&
-        d_start <= 1024 && total_deg >= 4096 && total_deg <= (1LL << 17)) {
+        d_start <= 1024 && total_deg >= 4096 && total_deg <= (1LL << 18)) {
         const int n_conv = (int)(total_deg / 1024);  // matrices of degree 1024 per signal
         bool ok = true;
         for (int n = n_conv, l = 11; ok && n >= 2; n /= 2, ++l)

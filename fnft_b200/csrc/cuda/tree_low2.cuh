@@ -116,7 +116,7 @@ DEV void up_twiddle_mul(cplx *v, const cplx *pt, int stride, int o)
 {
 #if FNFTB_TW_DERIVE
     if constexpr (R > 16) {
-        // radix 32 (last level of a degree-131072 product only): plain table rows [q-1][o]
+        // radix 32 / 64 (top levels of the longest products only): plain table rows [q-1][o]
 #pragma unroll
         for (int q0 = 1; q0 < R; q0 += 8) {
             cplx w[8];
@@ -159,7 +159,7 @@ DEV void up_twiddle_mul(cplx *v, const cplx *pt, int stride, int o)
                 v[13] = cmul(v[13], cmul(w8, w5));
                 v[14] = cmul(v[14], csq(w7));
                 v[15] = cmul(v[15], cmul(w8, w7));
-                static_assert(R <= 32, "radix");
+                static_assert(R <= 64, "radix");
             }
         }
     }

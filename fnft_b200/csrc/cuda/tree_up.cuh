@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
 // (cols) one thread per (array, o < N2): radix-R inverse pass across the rows, coefficient
 // fix-up and max, then twist + radix-R forward pass (or the coefficient output when last)
 template <int R, bool SYM>
-__global__ void __launch_bounds__(256, (R >= 32) ? 1 : ((R >= 8) ? 3 : 4)) k_up_cols(const UpArgs a)
+__global__ void __launch_bounds__((R >= 64) ? 128 : 256, (R >= 32) ? 1 : ((R >= 8) ? 3 : 4)) k_up_cols(const UpArgs a)
 {
     typedef typename UpT<SYM>::Tops Tops;
     constexpr int E = UpT<SYM>::E;
@@ -526,7 +526,7 @@ static inline bool up_supported(int l2n, int l2smem_max)
     if (l2n <= l2smem_max)
         return true;
     const int l2R = l2n - FNFTB_UP_ROW_L2;
-    return l2R >= 1 && l2R <= 5;  // radix 32 across the rows for operand length 2^17
+    return l2R >= 1 && l2R <= 6;  // radix 32 / 64 across the rows for operand lengths 2^17 / 2^18
 }
 
 template <bool SYM>
@@ -559,7 +559,12 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
     case 2: rc = up_launch(k_up_cols<4, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
     case 3: rc = up_launch(k_up_cols<8, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
     case 4: rc = up_launch(k_up_cols<16, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    default: rc = up_launch(k_up_cols<32, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    case 5: rc = up_launch(k_up_cols<32, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
+    default:
+        if (!a.last)
+            return -1064;  // radix 64 only exists for the last level (coefficient output)
+        rc = up_launch(k_up_cols<64, SYM>, a, grid_cols * 2, 128, 0, st, "tree_up_cols");
+        break;
     }
     if (rc || a.last)
         return rc;

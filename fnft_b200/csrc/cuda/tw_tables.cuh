@@ -13,12 +13,12 @@
 #include "common.cuh"
 
 #define FNFTB_TW_MINL 3
-#define FNFTB_TW_MAXL 17  // tables for lengths 2^3 .. 2^17
+#define FNFTB_TW_MAXL 18  // tables for lengths 2^3 .. 2^18
 
 struct TwSet {
     const cplx *base;
     int twist_off[FNFTB_TW_MAXL + 1];    // [log2 N]      -> w_2N^i, i < N
-    int pass_off[FNFTB_TW_MAXL + 1][6];  // [log2 len][log2 R] -> [q-1][o], o < len/R
+    int pass_off[FNFTB_TW_MAXL + 1][7];  // [log2 len][log2 R] -> [q-1][o], o < len/R (radix 64: longest length only)
 };
 
 __global__ void k_tw_fill_pass(cplx *dst, int l2len, int l2r)
@@ -51,13 +51,13 @@ static inline size_t twset_layout(TwSet *T)
     size_t off = 0;
     for (int l = 0; l <= FNFTB_TW_MAXL; ++l) {
         T->twist_off[l] = -1;
-        for (int r = 0; r < 6; ++r)
+        for (int r = 0; r < 7; ++r)
             T->pass_off[l][r] = -1;
     }
     for (int l = FNFTB_TW_MINL; l <= FNFTB_TW_MAXL; ++l) {
         T->twist_off[l] = (int)off;
         off += (size_t)1 << l;
-        for (int r = 1; r <= 5 && r <= l - 2; ++r) {
+        for (int r = 1; r <= (l == FNFTB_TW_MAXL ? 6 : 5) && r <= l - 2; ++r) {
             T->pass_off[l][r] = (int)off;
             off += (size_t)((1 << r) - 1) * ((size_t)1 << (l - r));
         }
@@ -72,7 +72,7 @@ static inline int twset_build(TwSet *T, cplx *mem, cudaStream_t st)
     for (int l = FNFTB_TW_MINL; l <= FNFTB_TW_MAXL; ++l) {
         const int N = 1 << l;
         k_tw_fill_twist<<<(N + 255) / 256, 256, 0, st>>>(mem + T->twist_off[l], l);
-        for (int r = 1; r <= 5 && r <= l - 2; ++r) {
+        for (int r = 1; r <= (l == FNFTB_TW_MAXL ? 6 : 5) && r <= l - 2; ++r) {
             const int total = ((1 << r) - 1) * (N >> r);
             k_tw_fill_pass<<<(total + 255) / 256, 256, 0, st>>>(mem + T->pass_off[l][r], l, r);
         }
