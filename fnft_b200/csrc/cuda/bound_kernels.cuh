@@ -68,16 +68,28 @@ HD void bo_step(cplx q, cplx r, cplx l, double h, cplx U[4], cplx Ud[4])
     }
 }
 
+// Spectral parameter of effective sample n.  BO and CF4_2 use one weight for every sample (passed
+// as `lweight`: 1 and 0.5); CF4_3 (upsampling 3, lweight = 1) weights the three exponentials of a
+// step with the row sums 11/40, 9/20, 11/40 of its weight matrix
+// (/root/reference/src/private/fnft__akns_scatter_matrix.c:101-109,131-144,
+//  /root/reference/src/private/fnft__akns_discretization.c:299-327).
+HD cplx bo_l_at(cplx l, int up, int n)
+{
+    if (up != 3)
+        return l;
+    return cscale(l, ((n % 3) == 1) ? 9.0 / 20.0 : 11.0 / 40.0);
+}
+
 struct BoundArgs {
     const cplx *q;     // [B][D] effective (preprocessed) samples, r = -conj(q)
     int B, D;          // D = number of effective samples
-    int upsampling;    // 1 (BO) or 2 (CF4_2)
+    int upsampling;    // 1 (BO), 2 (CF4_2) or 3 (CF4_3)
     int Kmax;          // stride of the per-signal eigenvalue arrays
     const int *K;      // [B] number of eigenvalues per signal
     cplx *lam;         // [B][Kmax] in/out
     double T0, T1, eps_t, bc;
-    double lweight;    // 1 for BO, 0.5 for CF4_2 (sum of the method weights)
-    double scl;        // factor of a' (1 or 0.5)
+    double lweight;    // 1 for BO, 0.5 for CF4_2 (sum of the method weights), 1 for CF4_3 (see bo_l_at)
+    double scl;        // factor of a' (1, 0.5 or 1/3)
     int niter;
     double box0, box1, box2;  // re_min, re_max, im_min
     const double *box3;       // [B] im_max per signal (NULL => +inf)
@@ -109,7 +121,7 @@ HD void bound_forward(const BoundArgs &a, const cplx *q, cplx lcur, cplx *phi_ou
         const cplx qn = q[n];
         const cplx rn = make_cplx(-qn.x, qn.y);
         cplx U[4], Ud[4];
-        bo_step<true>(qn, rn, l, a.eps_t, U, Ud);
+        bo_step<true>(qn, rn, bo_l_at(l, a.upsampling, n), a.eps_t, U, Ud);
         cplx c = cmul(Ud[0], phi1);
         cfma(c, Ud[1], phi2);
         cfma(c, U[0], d1);
@@ -228,7 +240,7 @@ BLK void blk_normconsts(const BoundArgs &a, blk3 bid, int nt, void *)
                     const cplx qn = q[n];
                     const cplx rn = make_cplx(-qn.x, qn.y);
                     cplx U[4], Ud[4];
-                    bo_step<false>(qn, rn, l, -a.eps_t, U, Ud);
+                    bo_step<false>(qn, rn, bo_l_at(l, a.upsampling, n), -a.eps_t, U, Ud);
                     cplx c = cmul(U[2], psi1);
                     cfma(c, U[3], psi2);
                     cplx d = cmul(U[0], psi1);
@@ -260,7 +272,7 @@ BLK void blk_normconsts(const BoundArgs &a, blk3 bid, int nt, void *)
 }
 
 // 1.5 * 0.25 * l2norm2(q)  (src/fnft_nsev.c:582-592, src/private/fnft__misc.c:90-112).
-// One CTA per signal.  q_given[i] = up * q[up*i + (up-1)] for upsampling up = 2
+// One CTA per signal.  q_given[i] = up * q[up*i + 1] for upsampling up > 1
 // (src/fnft_nsev.c:647-651), q itself for up = 1.
 struct NormArgs {
     const cplx *q;
@@ -278,7 +290,7 @@ BLK void blk_imbound(const NormArgs &a, blk3 bid, int nt, void *smem)
     {
         double acc = 0.0;
         for (int i = tid; i < Dg; i += nt) {
-            const cplx z = a.q[(size_t)s * a.D + (size_t)i * a.upsampling + (a.upsampling - 1)];
+            const cplx z = a.q[(size_t)s * a.D + (size_t)i * a.upsampling + (a.upsampling > 1 ? 1 : 0)];
             const double m = hypot(z.x, z.y) * a.upsampling;
             const double w = (i == 0 || i == Dg - 1) ? 0.5 * h : h;
             acc += w * m * m;

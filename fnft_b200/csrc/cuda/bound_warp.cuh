@@ -60,7 +60,7 @@ DEV cplx shfl_down_c(cplx v, int off)
 
 // product (with derivative) of the forward steps of samples [lo, hi)
 template <bool WITH_D>
-DEV BoMat bo_chunk(const cplx *q, int lo, int hi, cplx l, double h, bool descending)
+DEV BoMat bo_chunk(const cplx *q, int lo, int hi, cplx l, double h, bool descending, int up)
 {
     BoMat P;
     P.m[0] = make_cplx(1.0, 0.0);
@@ -75,7 +75,7 @@ DEV BoMat bo_chunk(const cplx *q, int lo, int hi, cplx l, double h, bool descend
         const cplx qn = __ldg(&q[n]);
         const cplx rn = make_cplx(-qn.x, qn.y);
         cplx U[4], Ud[4];
-        bo_step<WITH_D>(qn, rn, l, h, U, Ud);
+        bo_step<WITH_D>(qn, rn, bo_l_at(l, up, n), h, U, Ud);
         cplx t[4];
         if (WITH_D) {
             cplx td[4];
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) k_newton_warp(const BoundArgs a)
     int iter = 0, status = 0;
     while (true) {
         const cplx l = cscale(lam, a.lweight);
-        BoMat P = bo_chunk<true>(q, lo, hi, l, a.eps_t, false);
+        BoMat P = bo_chunk<true>(q, lo, hi, l, a.eps_t, false, a.upsampling);
         // ordered tree reduction: lane j ends up with P_(j+2^k-1) ... P_j
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
 
     // ---- forward: chunk products, ordered scan for the start vectors ------------------
     {
-        const BoMat P = bo_chunk<true>(q, lo, hi, l, a.eps_t, false);
+        const BoMat P = bo_chunk<true>(q, lo, hi, l, a.eps_t, false, a.upsampling);
         cplx v1 = c_exp(make_cplx(lcur.y * tb, -lcur.x * tb)), v2 = czero();
         cplx w1 = cmul(v1, make_cplx(0.0, -tb)), w2 = czero();
         cplx s1 = v1, s2 = v2;  // start vector of this lane's chunk
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
             const cplx qn = __ldg(&q[n]);
             const cplx rn = make_cplx(-qn.x, qn.y);
             cplx U[4], Ud[4];
-            bo_step<false>(qn, rn, l, a.eps_t, U, Ud);
+            bo_step<false>(qn, rn, bo_l_at(l, up, n), a.eps_t, U, Ud);
             cplx g = cmul(U[0], p1);
             cfma(g, U[1], p2);
             cplx f = cmul(U[2], p1);
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
     int best_n = 0x7fffffff;
     cplx bval = czero();
     {
-        const BoMat P = bo_chunk<false>(q, lo, hi, l, -a.eps_t, true);
+        const BoMat P = bo_chunk<false>(q, lo, hi, l, -a.eps_t, true, a.upsampling);
         cplx v1 = czero(), v2 = c_exp(make_cplx(-lcur.y * te, lcur.x * te));
         cplx s1 = v1, s2 = v2;
         for (int j = 31; j >= 0; --j) {
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
             const cplx qn = __ldg(&q[n]);
             const cplx rn = make_cplx(-qn.x, qn.y);
             cplx U[4], Ud[4];
-            bo_step<false>(qn, rn, l, -a.eps_t, U, Ud);
+            bo_step<false>(qn, rn, bo_l_at(l, up, n), -a.eps_t, U, Ud);
             cplx d = cmul(U[0], psi1);
             cfma(d, U[1], psi2);
             cplx c = cmul(U[2], psi1);

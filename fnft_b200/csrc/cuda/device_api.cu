@@ -762,7 +762,7 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
 int fnftb_slow_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, int upsampling, int kappa, double eps_t,
                         void *out, size_t out_sstride, int on_device, int32_t *status_host)
 {
-    if (!c || !d || !out || !c->q || d->M == 0 || (upsampling != 1 && upsampling != 2))
+    if (!c || !d || !out || !c->q || d->M == 0 || upsampling < 1 || upsampling > 3)
         return fail(-2, "invalid argument / no signals staged", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
     const size_t B = c->B;
@@ -783,7 +783,7 @@ int fnftb_slow_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, int upsampli
     a.M = (int)d->M;
     a.cstype = d->cstype;
     a.eps_t = eps_t;
-    a.lweight = (upsampling == 2) ? 0.5 : 1.0;
+    a.lweight = (upsampling == 2) ? 0.5 : 1.0;  // CF4_3: per-sample weights, see bo_l_at
     a.xi0 = d->xi0;
     a.eps_xi = d->eps_xi;
     a.ph_rho = d->ph_rho;
@@ -1155,7 +1155,7 @@ int fnftb_subsample(fnftb_ctx *c, size_t nskip, size_t Dsub)
 
 // 4SPLIT4 preprocessing for any number of samples: length-D DFTs as chirp-z transforms
 // (resample_kernels.cuh, second half)
-static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host)
+static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host, int up = 2)
 {
     const size_t B = c->B, D = c->D;
     if (2 * D > ((size_t)1 << 24))
@@ -1164,7 +1164,7 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     RC(ensure(c->rs_a, B * 2 * D * sizeof(cplx)));
     RC(ensure(c->rs_b, B * 2 * D * sizeof(cplx)));
     Buf &dstbuf = (nskip > 1) ? c->qsub : c->qpre;  // a subsampled copy never replaces the full one
-    RC(ensure(dstbuf, B * 2 * Dsub * sizeof(cplx)));
+    RC(ensure(dstbuf, B * (size_t)up * Dsub * sizeof(cplx)));
     RC(ensure(c->warn, B * sizeof(int)));
     RC(ensure(c->status, B * sizeof(int)));
     const CzGeom g = cz_geometry((int)D - 1, (int)D);
@@ -1179,6 +1179,26 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     ra.Dsub = (int)Dsub;
     ra.eps_t = eps_t;
     ra.warn = (int *)c->warn.p;
+    ra.up = up;
+    ra.q0 = c->q;
+    if (up == 3) {
+        // CF4_3 weights (/root/reference/src/private/fnft__akns_discretization.c:299-327): Legendre
+        // expansion of the coefficient table f at the three Gauss nodes
+        const double f[3][3] = {{11.0 / 40.0, 20.0 / 87.0, 7.0 / 50.0},
+                                {9.0 / 20.0, 0.0, -7.0 / 25.0},
+                                {11.0 / 40.0, -20.0 / 87.0, 7.0 / 50.0}};
+        const double wm[3] = {5.0 / 18.0, 4.0 / 9.0, 5.0 / 18.0};
+        const double xm[3] = {2.0 * sqrt(3.0 / 20.0), 0.0, -2.0 * sqrt(3.0 / 20.0)};
+        for (int m = 0; m < 3; ++m) {
+            const double P[3] = {1.0, xm[m], 0.5 * (3.0 * xm[m] * xm[m] - 1.0)};
+            for (int i = 0; i < 3; ++i) {
+                double w = 0.0;
+                for (int n = 0; n < 3; ++n)
+                    w += (2 * n + 1) * P[n] * f[i][n];
+                ra.w3[i * 3 + m] = w * wm[m];
+            }
+        }
+    }
     const long long tot = (long long)B * (long long)D;
     // 1. q reversed -> rs_a[B][D]
     ra.in = c->q;
@@ -1227,13 +1247,26 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     RC((launch_blocks<RsArgs, blk_rs_weights>(ra, (unsigned)((tot2 + 255) / 256), 256, 0, c->st, "resample_weights")));
     c->q = (const cplx *)dstbuf.p;
     c->r = nullptr;
-    c->D = 2 * Dsub;
+    c->D = (size_t)up * Dsub;
     c->have_box3 = 0;
     if (warn_host) {
         CU(cudaMemcpyAsync(warn_host, c->warn.p, B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
     }
     return 0;
+}
+
+// CF4_3 preprocessing (/root/reference/src/private/fnft__nse_discretization.c:505-531): always
+// through the general (chirp-z DFT) path; the staged signals become [B][3*Dsub]
+int fnftb_resample_cf4_3_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host)
+{
+    if (!c || !c->q)
+        return fail(-2, "no signals staged", __FILE__, __LINE__);
+    if (nskip < 1 || Dsub < 1 || (Dsub - 1) * nskip >= c->D)
+        return fail(-2, "invalid subsampling", __FILE__, __LINE__);
+    if (c->D < 4)
+        return fail(-6, "resampling needs at least 4 samples", __FILE__, __LINE__);
+    return resample_general(c, eps_t, nskip, Dsub, warn_host, 3);
 }
 
 int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host)

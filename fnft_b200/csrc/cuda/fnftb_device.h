@@ -101,6 +101,11 @@ int fnftb_resample_4split4(fnftb_ctx *ctx, double eps_t, int32_t *warn_host);
  * are scaled by nskip and only the samples 0, nskip, 2*nskip, ... (Dsub of them) are kept. */
 int fnftb_resample_4split4_sub(fnftb_ctx *ctx, double eps_t, size_t nskip, size_t Dsub,
                                int32_t *warn_host);
+/* CF4_3 preprocessing (src/private/fnft__nse_discretization.c:505-531): shifts by -/+ sqrt(3/20)*eps_t
+ * (scaled by nskip), the unshifted samples as middle node, 3x3 Gauss-node weights; the staged
+ * signals are replaced by the 3*Dsub weighted samples. */
+int fnftb_resample_cf4_3_sub(fnftb_ctx *ctx, double eps_t, size_t nskip, size_t Dsub,
+                             int32_t *warn_host);
 /* Plain subsampling of the staged signals (fnft__nse_discretization.c:463-470): keeps the
  * samples 0, nskip, ..., (Dsub-1)*nskip (device resident). */
 int fnftb_subsample(fnftb_ctx *ctx, size_t nskip, size_t Dsub);
@@ -145,8 +150,8 @@ int fnftb_set_polynomial(fnftb_ctx *ctx, size_t deg, const void *p_host);
 int fnftb_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, void *out,
                    size_t out_sstride, int on_device, int32_t *status_host);
 
-/* Continuous spectrum of the staged signals with the slow discretizations BO (upsampling 1) and
- * CF4_2 (upsampling 2; the staged signals are the resampled ones): one product of D step matrices
+/* Continuous spectrum of the staged signals with the slow discretizations BO (upsampling 1),
+ * CF4_2 and CF4_3 (upsampling 2 and 3; the staged signals are the resampled ones): one product of D step matrices
  * per spectral point, src/fnft_nsev.c:794-814 + epilogue :836-876.  Uses mode / cstype / M / xi0 /
  * eps_xi / ph_* of the descriptor. */
 int fnftb_slow_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, int upsampling, int kappa,
@@ -192,10 +197,10 @@ int fnftb_nsep_refine(fnftb_ctx *ctx, const fnftb_refine_desc *desc, const int32
 
 /* ---- bound states (Newton on the BO / CF4_2 recurrence) ------------------------ */
 typedef struct {
-    int upsampling;   /* 1: BO, 2: CF4_2 */
+    int upsampling;   /* 1: BO, 2: CF4_2, 3: CF4_3 */
     int Kmax;         /* stride of the per-signal eigenvalue arrays */
     double T0, T1, eps_t, bc;
-    double lweight;   /* 1 (BO) or 0.5 (CF4_2) */
+    double lweight;   /* 1 (BO), 0.5 (CF4_2), 1 (CF4_3: per-sample weights inside the kernels) */
     double scl;       /* factor of a' */
     int niter;
     double box0, box1, box2; /* re_min, re_max, im_min */

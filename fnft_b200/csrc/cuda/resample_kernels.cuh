@@ -149,6 +149,11 @@ struct RsArgs {
     int *warn;
     int B, D, nskip, Dsub;
     double eps_t;
+    // CF4_3 (up == 3, fnft__nse_discretization.c:505-531): shifts by -/+ sqrt(3/20)*eps_t, the
+    // unshifted samples q0 as middle node and the 3x3 weight matrix w3 (row-major, real)
+    int up;
+    const cplx *q0;  // [B][D]
+    double w3[9];
 };
 
 BLK void blk_rs_reverse(const RsArgs &a, blk3 bid, int nt, void * /*smem*/)
@@ -176,7 +181,7 @@ BLK void blk_rs_shift(const RsArgs &a, blk3 bid, int nt, void *smem)
     {
         double lo = 0.0, hi = 0.0, all = 0.0;
         const double scl = (double)D * a.eps_t;
-        const double delta = a.eps_t * (1.7320508075688772 / 6.0) * (double)a.nskip;
+        const double delta = a.eps_t * (a.up == 3 ? sqrt(3.0 / 20.0) : 1.7320508075688772 / 6.0) * (double)a.nskip;
         for (int k = tid; k < D; k += nt) {
             const cplx x = X[k];
             const double m2 = cabs2(x);
@@ -229,6 +234,15 @@ BLK void blk_rs_weights(const RsArgs &a, blk3 bid, int nt, void * /*smem*/)
             const double invD = 1.0 / (double)a.D;
             const cplx q1 = cscale(a.in[(size_t)s * 2 * a.D + i], invD);
             const cplx q2 = cscale(a.in[(size_t)s * 2 * a.D + a.D + i], invD);
+            if (a.up == 3) {
+                const cplx qm = a.q0[(size_t)s * a.D + i];
+                cplx *o3 = a.out + (size_t)s * 3 * a.Dsub + 3 * (size_t)isub;
+                for (int r = 0; r < 3; ++r) {
+                    const double *w = a.w3 + 3 * r;
+                    o3[r] = make_cplx(w[0] * q1.x + w[1] * qm.x + w[2] * q2.x, w[0] * q1.y + w[1] * qm.y + w[2] * q2.y);
+                }
+                continue;
+            }
             cplx *o = a.out + (size_t)s * 2 * a.Dsub + 2 * (size_t)isub;
             o[0] = make_cplx(w0 * q1.x + w1 * q2.x, w0 * q1.y + w1 * q2.y);
             o[1] = make_cplx(w1 * q1.x + w0 * q2.x, w1 * q1.y + w0 * q2.y);

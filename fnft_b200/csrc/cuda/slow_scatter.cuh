@@ -1,4 +1,4 @@
-// fnft_b200 -- continuous spectrum with the non-polynomial ("slow") discretizations BO and CF4_2.
+// fnft_b200 -- continuous spectrum with the non-polynomial ("slow") discretizations BO, CF4_2 and CF4_3.
 //
 // Replaces, for these two discretizations, the call of fnft__nse_scatter_matrix (derivative_flag 0)
 //   /root/reference/src/private/fnft__akns_scatter_matrix.c:112-126,206-232
@@ -25,7 +25,7 @@ struct SlowCsArgs {
 };
 
 // product of the steps of samples [lo, hi) without derivative, r = -kappa*conj(q)
-DEV void bo_chunk_plain(const cplx *q, int lo, int hi, cplx l, double h, int kappa, cplx *Pm)
+DEV void bo_chunk_plain(const cplx *q, int lo, int hi, cplx l, double h, int kappa, int up, cplx *Pm)
 {
     Pm[0] = make_cplx(1.0, 0.0);
     Pm[1] = czero();
@@ -36,7 +36,7 @@ DEV void bo_chunk_plain(const cplx *q, int lo, int hi, cplx l, double h, int kap
         const cplx qn = __ldg(&q[n]);
         const cplx rn = make_cplx(ks * qn.x, -ks * qn.y);
         cplx U[4], Ud[4], t[4];
-        bo_step<false>(qn, rn, l, h, U, Ud);
+        bo_step<false>(qn, rn, bo_l_at(l, up, n), h, U, Ud);
         bo_mm(U, Pm, t);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) k_slow_contspec(const SlowCsArgs a)
     bo_chunk_bounds(a.D, a.upsampling, lane, &lo, &hi);
     const double xi = a.xi0 + a.eps_xi * (double)m;
     cplx P[4];
-    bo_chunk_plain(q, lo, hi, make_cplx(xi * a.lweight, 0.0), a.eps_t, a.kappa, P);
+    bo_chunk_plain(q, lo, hi, make_cplx(xi * a.lweight, 0.0), a.eps_t, a.kappa, a.upsampling, P);
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         cplx H[4], t[4];

@@ -188,14 +188,14 @@ FNFT_INT fnftb__nsev_discrete_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D_ef
 
     fnftb_bound_desc bd;
     memset(&bd, 0, sizeof(bd));
-    bd.upsampling = (int)upsampling; /* BO for upsampling 1, CF4_2 for 2 (:675-680) */
+    bd.upsampling = (int)upsampling; /* BO for upsampling 1, CF4_2 for 2 (:675-680), CF4_3 itself for 3 */
     bd.Kmax = (int)Kmax;
     bd.T0 = T[0];
     bd.T1 = T[1];
     bd.eps_t = eps_t;
     bd.bc = 0.5;
     bd.lweight = (upsampling == 2) ? 0.5 : 1.0;
-    bd.scl = (upsampling == 2) ? 0.5 : 1.0;
+    bd.scl = 1.0 / upsampling; /* fnft__nse_scatter_bound_states.c:225,235,247 */
     bd.niter = (int)opts->niter;
 
     Kc = malloc(nb * sizeof(int32_t));

@@ -278,9 +278,11 @@ FNFT_INT fnft__nse_scatter_bound_states(const FNFT_UINT D, FNFT_COMPLEX const *c
         upsampling = 1;
     else if (discretization == fnft_nse_discretization_CF4_2)
         upsampling = 2;
+    else if (discretization == fnft_nse_discretization_CF4_3)
+        upsampling = 3;
     else
-        return E_NOT_YET_IMPLEMENTED(discretization, Only BO and CF4_2 run on the GPU.);
-    if (upsampling == 2 && D % 2 != 0)
+        return E_NOT_YET_IMPLEMENTED(discretization, Only BO CF4_2 and CF4_3 run on the GPU.);
+    if (D % upsampling != 0) /* fnft__nse_scatter_bound_states.c:231-246 */
         return E_ASSERTION_FAILED;
     if (r != NULL) {
         for (FNFT_UINT n = 0; n < D; n++)
@@ -302,7 +304,7 @@ FNFT_INT fnft__nse_scatter_bound_states(const FNFT_UINT D, FNFT_COMPLEX const *c
     bd.eps_t = (T[1] - T[0]) / (D_given - 1);
     bd.bc = 0.5;
     bd.lweight = (upsampling == 2) ? 0.5 : 1.0;
-    bd.scl = (upsampling == 2) ? 0.5 : 1.0;
+    bd.scl = 1.0 / upsampling;
     int32_t Kc = (int32_t)K;
     (void)skip_b_flag; /* b is cheap next to the sweeps; always computed */
     if (fnftb_normconsts(ctx, &bd, &Kc, bound_states, a_vals, aprime_vals, b) != 0)

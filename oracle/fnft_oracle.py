@@ -56,6 +56,7 @@ NSE_2SPLIT2_MODAL, NSE_BO, NSE_2SPLIT1A, NSE_2SPLIT1B, NSE_2SPLIT2A, NSE_2SPLIT2
 NSE_2SPLIT4B = 11
 NSE_4SPLIT4B = 21
 NSE_CF4_2 = 22
+NSE_CF4_3 = 23
 # fnft_kdv_discretization_t (include/fnft_kdv_discretization_t.h:96-122)
 KDV_2SPLIT1A, KDV_2SPLIT1B, KDV_2SPLIT2A, KDV_2SPLIT2B, KDV_2SPLIT2S = range(5)
 KDV_2SPLIT4B = 9
@@ -314,7 +315,43 @@ def preprocess_signal(q, eps_t, kappa, nse_disc):
         out[0::2] = w[0] * q1 + w[1] * q2
         out[1::2] = w[2] * q1 + w[3] * q2
         return out
+    if nse_disc == NSE_CF4_3:                       # :505-531
+        s = np.sqrt(3.0 / 20.0)
+        q1 = resample(q, eps_t, -eps_t * s)
+        q3 = resample(q, eps_t, +eps_t * s)
+        w = cf4_3_weights()
+        out = np.empty(3 * q.shape[0], dtype=np.complex128)
+        for i in range(3):
+            out[i::3] = w[i, 0] * q1 + w[i, 1] * q + w[i, 2] * q3
+        return out
     return q.copy()
+
+
+def cf4_3_weights():
+    """akns_discretization_method_weights for CF4_3, src/private/fnft__akns_discretization.c:299-327:
+    Legendre expansion of the coefficient table f at the three Gauss nodes.  Row sums (the weights of
+    the spectral parameter, fnft__akns_scatter_matrix.c:101-109): 11/40, 9/20, 11/40."""
+    f = np.array([[11.0 / 40.0, 20.0 / 87.0, 7.0 / 50.0],
+                  [9.0 / 20.0, 0.0, -7.0 / 25.0],
+                  [11.0 / 40.0, -20.0 / 87.0, 7.0 / 50.0]])
+    wm = np.array([5.0 / 18.0, 4.0 / 9.0, 5.0 / 18.0])
+    xm = np.array([2.0 * np.sqrt(3.0 / 20.0), 0.0, -2.0 * np.sqrt(3.0 / 20.0)])
+    P = np.stack([np.ones(3), xm, 0.5 * (3.0 * xm * xm - 1.0)])      # P[n, m]
+    w = np.zeros((3, 3))
+    for m in range(3):
+        for i in range(3):
+            w[i, m] = wm[m] * sum((2 * n + 1) * P[n, m] * f[i, n] for n in range(3))
+    return w
+
+
+def slow_lweights(upsampling):
+    """Weights of the spectral parameter per effective sample (period = upsampling),
+    src/private/fnft__akns_scatter_matrix.c:101-144: 1 (BO), 0.5 (CF4_2), row sums of the CF4_3 weights."""
+    if upsampling == 1:
+        return np.array([1.0])
+    if upsampling == 2:
+        return np.array([0.5])
+    return cf4_3_weights().sum(axis=1)
 
 
 def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normalize=True,
@@ -356,7 +393,7 @@ def nsev_contspec(q, T, M, XI, kappa=+1, nse_disc=NSE_2SPLIT4B, cstype=0, normal
 
 
 def nsev_contspec_slow(q, T, M, XI, kappa=+1, nse_disc=NSE_BO, cstype=0):
-    """Continuous spectrum of fnft_nsev for the slow discretizations BO and CF4_2: one product of D
+    """Continuous spectrum of fnft_nsev for the slow discretizations BO, CF4_2 and CF4_3: one product of D
     step matrices per spectral point (fnft__akns_scatter_matrix, src/private/fnft__akns_scatter_matrix.c:
     112-126,206-232, derivative_flag 0), then the epilogue of src/fnft_nsev.c:836-876 with the phase
     factors of the slow branch (src/private/fnft__nse_discretization.c:240-379)."""
@@ -364,12 +401,12 @@ def nsev_contspec_slow(q, T, M, XI, kappa=+1, nse_disc=NSE_BO, cstype=0):
     D = q.shape[0]
     eps_t = (T[1] - T[0]) / (D - 1)
     qp = preprocess_signal(q, eps_t, kappa, nse_disc)
-    lw = 0.5 if nse_disc == NSE_CF4_2 else 1.0
+    lws = slow_lweights({NSE_CF4_2: 2, NSE_CF4_3: 3}.get(nse_disc, 1))
     xi = XI[0] + (XI[1] - XI[0]) / (M - 1) * np.arange(M)
-    l = xi * lw + 0j
     S11, S12 = np.ones(M, dtype=np.complex128), np.zeros(M, dtype=np.complex128)
     S21, S22 = np.zeros(M, dtype=np.complex128), np.ones(M, dtype=np.complex128)
     for n in range(qp.shape[0]):
+        l = xi * lws[n % lws.size] + 0j
         (u11, u12, u21, u22), _ = _bo_step(qp[n], -kappa * np.conj(qp[n]), l, eps_t)
         S11, S12, S21, S22 = (u11 * S11 + u12 * S21, u11 * S12 + u12 * S22,
                               u21 * S11 + u22 * S21, u21 * S12 + u22 * S22)
@@ -431,7 +468,7 @@ def _bo_step(q, r, l, h):
 
 
 def nse_scatter_bound_states(q, T, lam, upsampling=1):
-    """fnft__nse_scatter_bound_states for BO (upsampling 1) and CF4_2 (upsampling 2),
+    """fnft__nse_scatter_bound_states for BO (upsampling 1), CF4_2 (upsampling 2) and CF4_3 (3),
     src/private/fnft__nse_scatter_bound_states.c:29-667.  q are the effective
     (preprocessed) samples, r = -conj(q).  Returns (a, aprime, b)."""
     q = np.asarray(q, dtype=np.complex128)
@@ -441,9 +478,8 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1):
     r = -np.conj(q)
     eps_t = (T[1] - T[0]) / (Dg - 1)
     bc = 0.5
-    lw = 0.5 if upsampling == 2 else 1.0       # sum of the CF4_2 weights (:214-221, 232-243)
-    scl = 0.5 if upsampling == 2 else 1.0
-    l = lam * lw
+    lws = slow_lweights(upsampling)            # sums of the method weights (:214-221, 232-268)
+    scl = 1.0 / upsampling                     # :225, 235, 247
     K = lam.shape[0]
     PHI = np.zeros((Dg + 1, 2, K), dtype=np.complex128)
     tb = T[0] - eps_t * bc
@@ -454,6 +490,7 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1):
     PHI[0, 0], PHI[0, 1] = phi1, phi2
     ng = 0
     for n in range(D):                          # :289-338
+        l = lam * lws[n % lws.size]
         U, Ud = _bo_step(q[n], r[n], l, eps_t)
         c = Ud[0] * phi1 + Ud[1] * phi2 + U[0] * d1 + U[1] * d2
         d2 = Ud[2] * phi1 + Ud[3] * phi2 + U[2] * d1 + U[3] * d2
@@ -475,6 +512,7 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1):
     PSI[Dg, 0], PSI[Dg, 1] = psi1, psi2
     ng = Dg
     for n in range(D - 1, -1, -1):
+        l = lam * lws[n % lws.size]
         U, _ = _bo_step(q[n], r[n], l, -eps_t)
         c = U[2] * psi1 + U[3] * psi2
         psi1 = U[0] * psi1 + U[1] * psi2
@@ -535,10 +573,10 @@ def nsev_bound_states_newton(q, T, guesses, nse_disc=NSE_2SPLIT4B, niter=10, bsf
     q = np.asarray(q, dtype=np.complex128)
     D = q.shape[0]
     eps_t = (T[1] - T[0]) / (D - 1)
-    up = 2 if nse_disc == NSE_4SPLIT4B else 1
+    up = {NSE_4SPLIT4B: 2, 20: 2, NSE_CF4_2: 2, NSE_CF4_3: 3}.get(nse_disc, 1)
     qp = preprocess_signal(q, eps_t, +1, nse_disc)
-    deg1 = akns_degree(_NSE2AKNS[nse_disc])
-    map_coeff = 2.0 / deg1
+    deg1 = 0 if nse_disc in (NSE_BO, NSE_CF4_2, NSE_CF4_3) else akns_degree(_NSE2AKNS[nse_disc])
+    map_coeff = 2.0 / deg1 if deg1 else 2.0     # src/fnft_nsev.c:612-616
     if bsfilt == 2:      # FULL :633-653
         re = 0.9 * np.pi / abs(map_coeff * eps_t)
         qg = qp if up == 1 else up * qp[1::up]

@@ -6,6 +6,8 @@ the C-ABI of libfnft_b200.so and compares with
   * the unmodified reference library itself when oracle/_ref travelled to the box.
 Tolerances: the reference's unit-test bound 100*eps where the reference states one;
 otherwise the 1e-9 contract of SURVEY.md 8(c) (L1-relative / pointwise / tail)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -337,12 +339,55 @@ def test_nsev_slow_discretizations_bo_cf4_2_vs_reference_runs(F, golden):
     # the other slow discretizations are not implemented, and say so; default localization is
     # rejected for slow discretizations like in the reference (src/fnft_nsev.c:209-219)
     o = F.nsev_default_opts()
-    o.discretization = 23
+    o.discretization = 24
     o.bound_state_localization = 1
     assert F.nsev(np.ones(16), [-1, 1], 4, [-1, 1], 1, o)[0] == 6
     o.discretization = 1
     o.bound_state_localization = 2
     assert F.nsev(np.ones(16), [-1, 1], 4, [-1, 1], 1, o)[0] == 2
+
+
+def test_nsev_cf4_3_vs_reference_runs(F):
+    # fnft_nse_discretization_CF4_3: resampling at -/+ sqrt(3/20) eps_t with the 3x3 Gauss-node weights,
+    # three step matrices per sample with their own spectral-parameter weights; continuous spectrum
+    # (rho, a, b), Newton bound states with norming constants and residues, Richardson extrapolation;
+    # D = 100, 255, 300 are not powers of two.  Reference outputs: tests/golden/make_golden_cf4_3.py
+    F.lib().fnft_errwarn_setprintf(None)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cf4_3.npz"))
+    cases = sorted({tuple(k.split("/")[1:5]) for k in g.files if k.startswith("refrun/slow")})
+    assert len(cases) == 7
+    for kind, disc, D, kappa in cases:
+        key = f"refrun/{kind}/{disc}/{D}/{kappa}"
+        q = g[f"refrun/slow/{disc}/{D}/{kappa}/q"]
+        gs = g[f"refrun/slow/{disc}/{D}/{kappa}/guesses"]
+        o = F.nsev_default_opts()
+        o.discretization, o.bound_state_localization, o.discspec_type, o.contspec_type = int(disc), 1, 2, 2
+        o.richardson_extrapolation_flag = 1 if kind == "slow_richardson" else 0
+        ret, cs, K, bs, nc = F.nsev(q, [-10, 10], 20, [-2, 2.5], int(kappa), o, K=3, bound_states=gs)
+        assert ret == 0, key
+        ref = g[key + "/cs"]
+        for part in range(3):
+            assert max(parity_contract(cs[part * 20:(part + 1) * 20], ref[part * 20:(part + 1) * 20])) < 1, key
+        rbs, rnc = g[key + "/bs"], g[key + "/nc"]
+        assert K == rbs.size, key
+        if K:
+            idx = _match_sets(bs[:K], rbs)
+            assert (np.abs(bs[:K][idx] - rbs) <= 1e-9 * np.abs(rbs)).all(), key
+            for part in range(2):
+                assert (np.abs(nc[part * K:(part + 1) * K][idx] - rnc[part * K:(part + 1) * K])
+                        <= 1e-9 * np.abs(rnc[part * K:(part + 1) * K])).all(), key
+    # a batch gives the same values as single calls
+    D = 256
+    t = np.linspace(-10, 10, D)
+    Q = np.stack([a / np.cosh(t) * np.exp(0.2j * a * t) for a in (0.8, 1.7, 2.6)])
+    o = F.nsev_default_opts()
+    o.discretization = 23
+    ret, csb, *_ = F.nsev_batch(Q, [-10, 10], 32, [-2, 2], -1, o)
+    assert ret == 0
+    for b in range(3):
+        r1, cs1, *_ = F.nsev(Q[b], [-10, 10], 32, [-2, 2], -1, o)
+        assert r1 == 0 and np.array_equal(cs1, csb[b])
+        assert O.misc_rel_err(cs1, O.nsev_contspec_slow(Q[b], [-10, 10], 32, [-2, 2], -1, 23, 0)) < 1e-9
 
 
 def test_nsev_batch_default_options_matches_single_calls(F):

@@ -135,3 +135,24 @@ def test_slow_discretizations_vs_reference_runs(golden):
         q = golden[f"refrun/slow/{case}/q"]
         cs = O.nsev_contspec_slow(q, [-10, 10], 20, [-2, 2.5], kappa, disc, cstype=2)
         assert rel_err(cs, golden[f"refrun/slow/{case}/cs"]) < 1e-12, case
+
+
+def test_cf4_3_vs_reference_runs():
+    # CF4_3 (three exponentials per step, 3x3 Gauss-node weights, fnft__nse_discretization.c:505-531):
+    # oracle against outputs of the unmodified reference (tests/golden/make_golden_cf4_3.py)
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cf4_3.npz"))
+    w = O.cf4_3_weights()
+    assert np.allclose(w.sum(axis=1), [11 / 40, 9 / 20, 11 / 40], rtol=0, atol=1e-15)
+    cases = sorted({"/".join(k.split("/")[2:5]) for k in g.files if k.startswith("refrun/slow/")})
+    assert len(cases) == 5
+    for case in cases:
+        disc, D, kappa = map(int, case.split("/"))
+        q = g[f"refrun/slow/{case}/q"]
+        cs = O.nsev_contspec_slow(q, [-10, 10], 20, [-2, 2.5], kappa, disc, cstype=2)
+        assert rel_err(cs, g[f"refrun/slow/{case}/cs"]) < 1e-12, case
+        if kappa == 1:
+            bs, nc = O.nsev_bound_states_newton(q, [-10, 10], g[f"refrun/slow/{case}/guesses"], disc, 10, 2, 2)
+            rbs, rnc = g[f"refrun/slow/{case}/bs"], g[f"refrun/slow/{case}/nc"]
+            assert bs.size == rbs.size
+            assert np.abs(bs - rbs).max() < 1e-11 and (np.abs(nc - rnc) <= 1e-9 * np.abs(rnc)).all(), case
