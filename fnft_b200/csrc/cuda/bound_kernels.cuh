@@ -68,22 +68,52 @@ HD void bo_step(cplx q, cplx r, cplx l, double h, cplx U[4], cplx Ud[4])
     }
 }
 
-// Spectral parameter of effective sample n.  BO and CF4_2 use one weight for every sample (passed
-// as `lweight`: 1 and 0.5); CF4_3 (upsampling 3, lweight = 1) weights the three exponentials of a
-// step with the row sums 11/40, 9/20, 11/40 of its weight matrix
-// (/root/reference/src/private/fnft__akns_scatter_matrix.c:101-109,131-144,
-//  /root/reference/src/private/fnft__akns_discretization.c:299-327).
-HD cplx bo_l_at(cplx l, int up, int n)
+// Weight matrices of the commutator-free schemes with complex weights
+// (/root/reference/src/private/fnft__akns_discretization.c:330-367): w[i][m], i = exponential of the step,
+// m = node (shifted by -delta, unshifted, shifted by +delta).  wsel 2: CF5_3 (3x3), wsel 3: CF6_4 (4x3).
+HD cplx bo_cf_w(int wsel, int i, int m)
 {
-    if (up != 3)
+    if (wsel == 2) {
+        const double s15 = 3.872983346207416885;  // sqrt(15)
+        const double w[5][2] = {{(145.0 + 37.0 * s15) / 900.0, (5.0 + 3.0 * s15) / 300.0},
+                                {-1.0 / 45.0, 1.0 / 15.0},
+                                {(145.0 - 37.0 * s15) / 900.0, (5.0 - 3.0 * s15) / 300.0},
+                                {-2.0 / 45.0, -s15 / 50.0},
+                                {22.0 / 45.0, 0.0}};
+        const int k = 3 * i + m;  // weights[5..8] = conj(weights[3..0])
+        return k <= 4 ? make_cplx(w[k][0], w[k][1]) : make_cplx(w[8 - k][0], -w[8 - k][1]);
+    }
+    const double w6[6][2] = {{0.245985577298764, 0.038734389227165},  {-0.046806149832549, 0.012442141491185},
+                             {0.010894359342569, -0.004575808769067}, {0.062868370946917, -0.048761268117765},
+                             {0.269028372054771, -0.012442141491185}, {-0.041970529810473, 0.014602687659668}};
+    const int k = 3 * i + m;      // weights[6..11] = weights[5..0]
+    const int kk = k <= 5 ? k : 11 - k;
+    return make_cplx(w6[kk][0], w6[kk][1]);
+}
+
+// Spectral parameter of effective sample n.  BO and CF4_2 use one weight for every sample (passed
+// as `lweight`: 1 and 0.5; wsel 0).  The schemes with more exponentials per step (lweight = 1) weight
+// them with the row sums of their weight matrix
+// (/root/reference/src/private/fnft__akns_scatter_matrix.c:101-109,131-160):
+// wsel 1: CF4_3, real sums 11/40, 9/20, 11/40 (fnft__akns_discretization.c:299-327);
+// wsel 2: CF5_3; wsel 3: CF6_4 (complex sums of bo_cf_w).
+HD cplx bo_l_at(cplx l, int wsel, int n)
+{
+    if (wsel == 0)
         return l;
-    return cscale(l, ((n % 3) == 1) ? 9.0 / 20.0 : 11.0 / 40.0);
+    if (wsel == 1)
+        return cscale(l, ((n % 3) == 1) ? 9.0 / 20.0 : 11.0 / 40.0);
+    const int i = (wsel == 2) ? (n % 3) : (n % 4);
+    const cplx w0 = bo_cf_w(wsel, i, 0), w1 = bo_cf_w(wsel, i, 1), w2 = bo_cf_w(wsel, i, 2);
+    return cmul(l, make_cplx(w0.x + w1.x + w2.x, w0.y + w1.y + w2.y));
 }
 
 struct BoundArgs {
     const cplx *q;     // [B][D] effective (preprocessed) samples, r = -conj(q)
     int B, D;          // D = number of effective samples
-    int upsampling;    // 1 (BO), 2 (CF4_2) or 3 (CF4_3)
+    int upsampling;    // 1 (BO), 2 (CF4_2), 3 (CF4_3, CF5_3), 4 (CF6_4)
+    int wsel;          // weights of the spectral parameter, see bo_l_at
+    const cplx *r;     // [B][D] explicit r samples (CF5_3 / CF6_4: r is not -conj(q)); NULL otherwise
     int Kmax;          // stride of the per-signal eigenvalue arrays
     const int *K;      // [B] number of eigenvalues per signal
     cplx *lam;         // [B][Kmax] in/out
@@ -117,11 +147,12 @@ HD void bound_forward(const BoundArgs &a, const cplx *q, cplx lcur, cplx *phi_ou
     }
     int count = a.upsampling - 1;
     size_t ng = 0;
+    const cplx *rs = a.r ? a.r + (q - a.q) : (const cplx *)0;
     for (int n = 0; n < a.D; ++n) {
         const cplx qn = q[n];
-        const cplx rn = make_cplx(-qn.x, qn.y);
+        const cplx rn = rs ? rs[n] : make_cplx(-qn.x, qn.y);
         cplx U[4], Ud[4];
-        bo_step<true>(qn, rn, bo_l_at(l, a.upsampling, n), a.eps_t, U, Ud);
+        bo_step<true>(qn, rn, bo_l_at(l, a.wsel, n), a.eps_t, U, Ud);
         cplx c = cmul(Ud[0], phi1);
         cfma(c, Ud[1], phi2);
         cfma(c, U[0], d1);
@@ -236,11 +267,12 @@ BLK void blk_normconsts(const BoundArgs &a, blk3 bid, int nt, void *)
                 int ng = Dg;
                 // candidate at n = D_given (PSI1 = 0 -> metric is inf/NaN, never chosen)
                 int count = a.upsampling - 1;
+                const cplx *rs = a.r ? a.r + (q - a.q) : (const cplx *)0;
                 for (int n = a.D - 1; n >= 0; --n) {
                     const cplx qn = q[n];
-                    const cplx rn = make_cplx(-qn.x, qn.y);
+                    const cplx rn = rs ? rs[n] : make_cplx(-qn.x, qn.y);
                     cplx U[4], Ud[4];
-                    bo_step<false>(qn, rn, bo_l_at(l, a.upsampling, n), -a.eps_t, U, Ud);
+                    bo_step<false>(qn, rn, bo_l_at(l, a.wsel, n), -a.eps_t, U, Ud);
                     cplx c = cmul(U[2], psi1);
                     cfma(c, U[3], psi2);
                     cplx d = cmul(U[0], psi1);

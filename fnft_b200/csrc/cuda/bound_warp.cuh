@@ -60,7 +60,7 @@ DEV cplx shfl_down_c(cplx v, int off)
 
 // product (with derivative) of the forward steps of samples [lo, hi)
 template <bool WITH_D>
-DEV BoMat bo_chunk(const cplx *q, int lo, int hi, cplx l, double h, bool descending, int up)
+DEV BoMat bo_chunk(const cplx *q, const cplx *r, int lo, int hi, cplx l, double h, bool descending, int wsel)
 {
     BoMat P;
     P.m[0] = make_cplx(1.0, 0.0);
@@ -73,9 +73,9 @@ DEV BoMat bo_chunk(const cplx *q, int lo, int hi, cplx l, double h, bool descend
     for (int k = lo; k < hi; ++k) {
         const int n = descending ? (hi - 1 - (k - lo)) : k;
         const cplx qn = __ldg(&q[n]);
-        const cplx rn = make_cplx(-qn.x, qn.y);
+        const cplx rn = r ? __ldg(&r[n]) : make_cplx(-qn.x, qn.y);
         cplx U[4], Ud[4];
-        bo_step<WITH_D>(qn, rn, bo_l_at(l, up, n), h, U, Ud);
+        bo_step<WITH_D>(qn, rn, bo_l_at(l, wsel, n), h, U, Ud);
         cplx t[4];
         if (WITH_D) {
             cplx td[4];
@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(128) k_newton_warp(const BoundArgs a)
     if (i >= a.K[s])
         return;
     const cplx *q = a.q + (size_t)s * a.D;
+    const cplx *rs = a.r ? a.r + (size_t)s * a.D : (const cplx *)0;
     int lo, hi;
     bo_chunk_bounds(a.D, a.upsampling, lane, &lo, &hi);
     cplx lam = a.lam[gid];
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(128) k_newton_warp(const BoundArgs a)
     int iter = 0, status = 0;
     while (true) {
         const cplx l = cscale(lam, a.lweight);
-        BoMat P = bo_chunk<true>(q, lo, hi, l, a.eps_t, false, a.upsampling);
+        BoMat P = bo_chunk<true>(q, rs, lo, hi, l, a.eps_t, false, a.wsel);
         // ordered tree reduction: lane j ends up with P_(j+2^k-1) ... P_j
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
     if (i >= a.K[s])
         return;
     const cplx *q = a.q + (size_t)s * a.D;
+    const cplx *rs = a.r ? a.r + (size_t)s * a.D : (const cplx *)0;
     const int up = a.upsampling;
     const int Dg = a.D / up;
     int lo, hi;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
 
     // ---- forward: chunk products, ordered scan for the start vectors ------------------
     {
-        const BoMat P = bo_chunk<true>(q, lo, hi, l, a.eps_t, false, a.upsampling);
+        const BoMat P = bo_chunk<true>(q, rs, lo, hi, l, a.eps_t, false, a.wsel);
         cplx v1 = c_exp(make_cplx(lcur.y * tb, -lcur.x * tb)), v2 = czero();
         cplx w1 = cmul(v1, make_cplx(0.0, -tb)), w2 = czero();
         cplx s1 = v1, s2 = v2;  // start vector of this lane's chunk
@@ -242,9 +244,9 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
         cplx p1 = s1, p2 = s2;
         for (int n = lo; n < hi; ++n) {
             const cplx qn = __ldg(&q[n]);
-            const cplx rn = make_cplx(-qn.x, qn.y);
+            const cplx rn = rs ? __ldg(&rs[n]) : make_cplx(-qn.x, qn.y);
             cplx U[4], Ud[4];
-            bo_step<false>(qn, rn, bo_l_at(l, up, n), a.eps_t, U, Ud);
+            bo_step<false>(qn, rn, bo_l_at(l, a.wsel, n), a.eps_t, U, Ud);
             cplx g = cmul(U[0], p1);
             cfma(g, U[1], p2);
             cplx f = cmul(U[2], p1);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
     int best_n = 0x7fffffff;
     cplx bval = czero();
     {
-        const BoMat P = bo_chunk<false>(q, lo, hi, l, -a.eps_t, true, a.upsampling);
+        const BoMat P = bo_chunk<false>(q, rs, lo, hi, l, -a.eps_t, true, a.wsel);
         cplx v1 = czero(), v2 = c_exp(make_cplx(-lcur.y * te, lcur.x * te));
         cplx s1 = v1, s2 = v2;
         for (int j = 31; j >= 0; --j) {
@@ -286,9 +288,9 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
         cplx psi1 = s1, psi2 = s2;
         for (int n = hi - 1; n >= lo; --n) {
             const cplx qn = __ldg(&q[n]);
-            const cplx rn = make_cplx(-qn.x, qn.y);
+            const cplx rn = rs ? __ldg(&rs[n]) : make_cplx(-qn.x, qn.y);
             cplx U[4], Ud[4];
-            bo_step<false>(qn, rn, bo_l_at(l, up, n), -a.eps_t, U, Ud);
+            bo_step<false>(qn, rn, bo_l_at(l, a.wsel, n), -a.eps_t, U, Ud);
             cplx d = cmul(U[0], psi1);
             cfma(d, U[1], psi2);
             cplx c = cmul(U[2], psi1);

@@ -159,6 +159,11 @@ struct fnftb_ctx {
     const cplx *saved_q[2] = {nullptr, nullptr}, *saved_r[2] = {nullptr, nullptr};
     size_t saved_D[2] = {0, 0};
     int have_box3 = 0;
+    // slow discretizations with several exponentials per step (set by the CF resampling, reset whenever
+    // other signals are staged): weight selector of bo_l_at and, for CF5_3 / CF6_4, the explicit r samples
+    int slow_wsel = 0;
+    const cplx *rpre = nullptr;
+    Buf rprebuf;
     // pipelined host transfers (fnftb_pipeline_begin): two slots, copy streams, events
     int pipe_on = 0, slot = 0;
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
@@ -454,6 +459,8 @@ int fnftb_set_signals(fnftb_ctx *c, size_t B, size_t D, const void *q, const voi
     c->B = B;
     c->D = D;
     c->have_box3 = 0;
+    c->slow_wsel = 0;
+    c->rpre = nullptr;
     if (on_device) {
         c->q = (const cplx *)q;
         c->r = (const cplx *)r;
@@ -762,7 +769,7 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
 int fnftb_slow_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, int upsampling, int kappa, double eps_t,
                         void *out, size_t out_sstride, int on_device, int32_t *status_host)
 {
-    if (!c || !d || !out || !c->q || d->M == 0 || upsampling < 1 || upsampling > 3)
+    if (!c || !d || !out || !c->q || d->M == 0 || upsampling < 1 || upsampling > 4)
         return fail(-2, "invalid argument / no signals staged", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
     const size_t B = c->B;
@@ -776,6 +783,8 @@ int fnftb_slow_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, int upsampli
     SlowCsArgs a;
     memset(&a, 0, sizeof(a));
     a.q = c->q;
+    a.r = c->rpre;
+    a.wsel = c->slow_wsel;
     a.B = (int)B;
     a.D = (int)c->D;
     a.upsampling = upsampling;
@@ -1150,12 +1159,15 @@ int fnftb_subsample(fnftb_ctx *c, size_t nskip, size_t Dsub)
     c->r = nullptr;
     c->D = Dsub;
     c->have_box3 = 0;
+    c->slow_wsel = 0;
+    c->rpre = nullptr;
     return 0;
 }
 
 // 4SPLIT4 preprocessing for any number of samples: length-D DFTs as chirp-z transforms
 // (resample_kernels.cuh, second half)
-static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host, int up = 2)
+static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host, int up = 2,
+                            int wsel = 0, int kappa = 1)
 {
     const size_t B = c->B, D = c->D;
     if (2 * D > ((size_t)1 << 24))
@@ -1181,6 +1193,12 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     ra.warn = (int *)c->warn.p;
     ra.up = up;
     ra.q0 = c->q;
+    ra.wsel = wsel;
+    ra.kappa = kappa;
+    if (wsel >= 2) {
+        RC(ensure(c->rprebuf, B * (size_t)up * Dsub * sizeof(cplx)));
+        ra.rout = (cplx *)c->rprebuf.p;
+    }
     if (up == 3) {
         // CF4_3 weights (/root/reference/src/private/fnft__akns_discretization.c:299-327): Legendre
         // expansion of the coefficient table f at the three Gauss nodes
@@ -1249,6 +1267,8 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     c->r = nullptr;
     c->D = (size_t)up * Dsub;
     c->have_box3 = 0;
+    c->slow_wsel = wsel;
+    c->rpre = (wsel >= 2) ? (const cplx *)c->rprebuf.p : nullptr;
     if (warn_host) {
         CU(cudaMemcpyAsync(warn_host, c->warn.p, B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
@@ -1266,7 +1286,32 @@ int fnftb_resample_cf4_3_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t Ds
         return fail(-2, "invalid subsampling", __FILE__, __LINE__);
     if (c->D < 4)
         return fail(-6, "resampling needs at least 4 samples", __FILE__, __LINE__);
-    return resample_general(c, eps_t, nskip, Dsub, warn_host, 3);
+    return resample_general(c, eps_t, nskip, Dsub, warn_host, 3, 1, 1);
+}
+
+// CF5_3 (wsel 2) and CF6_4 (wsel 3) preprocessing (:532-604): complex weights, explicit r samples
+int fnftb_resample_cf_sub(fnftb_ctx *c, int wsel, int kappa, double eps_t, size_t nskip, size_t Dsub,
+                          int32_t *warn_host)
+{
+    if (wsel == 1)
+        return fnftb_resample_cf4_3_sub(c, eps_t, nskip, Dsub, warn_host);
+    if (!c || !c->q || (wsel != 2 && wsel != 3) || (kappa != 1 && kappa != -1))
+        return fail(-2, "invalid argument / no signals staged", __FILE__, __LINE__);
+    if (nskip < 1 || Dsub < 1 || (Dsub - 1) * nskip >= c->D)
+        return fail(-2, "invalid subsampling", __FILE__, __LINE__);
+    if (c->D < 4)
+        return fail(-6, "resampling needs at least 4 samples", __FILE__, __LINE__);
+    return resample_general(c, eps_t, nskip, Dsub, warn_host, wsel == 2 ? 3 : 4, wsel, kappa);
+}
+
+// The staged signals are CF4_3-preprocessed samples supplied by the caller (private API)
+int fnftb_set_slow_weights(fnftb_ctx *c, int wsel)
+{
+    if (!c || wsel < 0 || wsel > 1)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    c->slow_wsel = wsel;
+    c->rpre = nullptr;
+    return 0;
 }
 
 int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsub, int32_t *warn_host)
@@ -1303,6 +1348,8 @@ int fnftb_resample_4split4_sub(fnftb_ctx *c, double eps_t, size_t nskip, size_t 
     c->r = nullptr;
     c->D = 2 * Dsub;
     c->have_box3 = 0;
+    c->slow_wsel = 0;
+    c->rpre = nullptr;
     if (warn_host) {
         CU(cudaMemcpyAsync(warn_host, c->warn.p, c->B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
@@ -1416,6 +1463,8 @@ static BoundArgs bound_args(fnftb_ctx *c, const fnftb_bound_desc *d)
     a.B = (int)c->B;
     a.D = (int)c->D;
     a.upsampling = d->upsampling;
+    a.wsel = c->slow_wsel;
+    a.r = c->rpre;
     a.Kmax = d->Kmax;
     a.K = (const int *)c->kcnt.p;
     a.lam = (cplx *)c->lam.p;

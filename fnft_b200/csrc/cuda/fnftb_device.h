@@ -106,6 +106,14 @@ int fnftb_resample_4split4_sub(fnftb_ctx *ctx, double eps_t, size_t nskip, size_
  * signals are replaced by the 3*Dsub weighted samples. */
 int fnftb_resample_cf4_3_sub(fnftb_ctx *ctx, double eps_t, size_t nskip, size_t Dsub,
                              int32_t *warn_host);
+/* CF5_3 (wsel 2, 3 exponentials per step) and CF6_4 (wsel 3, 4 per step), :532-604: shifts by
+ * -/+ sqrt(15)/10*eps_t, complex weights applied to q and (unconjugated) to r = -kappa*conj(q); the
+ * explicit r samples stay on the device next to the weighted q.  wsel 1 = CF4_3. */
+int fnftb_resample_cf_sub(fnftb_ctx *ctx, int wsel, int kappa, double eps_t, size_t nskip, size_t Dsub,
+                          int32_t *warn_host);
+/* Declares the staged signals to be CF4_3-preprocessed samples (wsel 1; 0 = BO / CF4_2), for callers
+ * of the private API that pass preprocessed samples themselves. */
+int fnftb_set_slow_weights(fnftb_ctx *ctx, int wsel);
 /* Plain subsampling of the staged signals (fnft__nse_discretization.c:463-470): keeps the
  * samples 0, nskip, ..., (Dsub-1)*nskip (device resident). */
 int fnftb_subsample(fnftb_ctx *ctx, size_t nskip, size_t Dsub);

@@ -154,6 +154,11 @@ struct RsArgs {
     int up;
     const cplx *q0;  // [B][D]
     double w3[9];
+    // CF5_3 (wsel 2, up 3) and CF6_4 (wsel 3, up 4), :532-604: shifts by -/+ sqrt(15)/10*eps_t, complex
+    // weights bo_cf_w applied to q and, unconjugated, to r = -kappa*conj(q): r is no longer
+    // -kappa*conj(q_preprocessed) and is written to rout [B][up*Dsub]
+    int wsel, kappa;
+    cplx *rout;
 };
 
 BLK void blk_rs_reverse(const RsArgs &a, blk3 bid, int nt, void * /*smem*/)
@@ -181,7 +186,8 @@ BLK void blk_rs_shift(const RsArgs &a, blk3 bid, int nt, void *smem)
     {
         double lo = 0.0, hi = 0.0, all = 0.0;
         const double scl = (double)D * a.eps_t;
-        const double delta = a.eps_t * (a.up == 3 ? sqrt(3.0 / 20.0) : 1.7320508075688772 / 6.0) * (double)a.nskip;
+        const double delta = a.eps_t * (double)a.nskip *
+                             (a.wsel >= 2 ? sqrt(15.0) / 10.0 : (a.up == 3 ? sqrt(3.0 / 20.0) : 1.7320508075688772 / 6.0));
         for (int k = tid; k < D; k += nt) {
             const cplx x = X[k];
             const double m2 = cabs2(x);
@@ -234,6 +240,23 @@ BLK void blk_rs_weights(const RsArgs &a, blk3 bid, int nt, void * /*smem*/)
             const double invD = 1.0 / (double)a.D;
             const cplx q1 = cscale(a.in[(size_t)s * 2 * a.D + i], invD);
             const cplx q2 = cscale(a.in[(size_t)s * 2 * a.D + a.D + i], invD);
+            if (a.wsel >= 2) {
+                const cplx qn[3] = {q1, a.q0[(size_t)s * a.D + i], q2};
+                const double ks = -(double)a.kappa;
+                cplx *oq = a.out + ((size_t)s * a.Dsub + (size_t)isub) * a.up;
+                cplx *orr = a.rout + ((size_t)s * a.Dsub + (size_t)isub) * a.up;
+                for (int r = 0; r < a.up; ++r) {
+                    cplx accq = czero(), accr = czero();
+                    for (int m = 0; m < 3; ++m) {
+                        const cplx w = bo_cf_w(a.wsel, r, m);
+                        cfma(accq, w, qn[m]);
+                        cfma(accr, w, make_cplx(ks * qn[m].x, -ks * qn[m].y));
+                    }
+                    oq[r] = accq;
+                    orr[r] = accr;
+                }
+                continue;
+            }
             if (a.up == 3) {
                 const cplx qm = a.q0[(size_t)s * a.D + i];
                 cplx *o3 = a.out + (size_t)s * 3 * a.Dsub + 3 * (size_t)isub;

@@ -1,4 +1,4 @@
-// fnft_b200 -- continuous spectrum with the non-polynomial ("slow") discretizations BO, CF4_2 and CF4_3.
+// fnft_b200 -- continuous spectrum with the non-polynomial ("slow") discretizations BO, CF4_2, CF4_3, CF5_3 and CF6_4.
 //
 // Replaces, for these two discretizations, the call of fnft__nse_scatter_matrix (derivative_flag 0)
 //   /root/reference/src/private/fnft__akns_scatter_matrix.c:112-126,206-232
@@ -14,6 +14,8 @@
 
 struct SlowCsArgs {
     const cplx *q;   // [B][D] effective (preprocessed) samples
+    const cplx *r;   // [B][D] explicit r (CF5_3 / CF6_4), NULL: r = -kappa*conj(q)
+    int wsel;        // weights of the spectral parameter, see bo_l_at
     int B, D, upsampling, kappa;
     int M, cstype;   // 0: rho, 1: a and b, 2: rho, a, b
     double eps_t, lweight;
@@ -25,7 +27,7 @@ struct SlowCsArgs {
 };
 
 // product of the steps of samples [lo, hi) without derivative, r = -kappa*conj(q)
-DEV void bo_chunk_plain(const cplx *q, int lo, int hi, cplx l, double h, int kappa, int up, cplx *Pm)
+DEV void bo_chunk_plain(const cplx *q, const cplx *r, int lo, int hi, cplx l, double h, int kappa, int wsel, cplx *Pm)
 {
     Pm[0] = make_cplx(1.0, 0.0);
     Pm[1] = czero();
@@ -34,9 +36,9 @@ DEV void bo_chunk_plain(const cplx *q, int lo, int hi, cplx l, double h, int kap
     const double ks = -(double)kappa;
     for (int n = lo; n < hi; ++n) {
         const cplx qn = __ldg(&q[n]);
-        const cplx rn = make_cplx(ks * qn.x, -ks * qn.y);
+        const cplx rn = r ? __ldg(&r[n]) : make_cplx(ks * qn.x, -ks * qn.y);
         cplx U[4], Ud[4], t[4];
-        bo_step<false>(qn, rn, bo_l_at(l, up, n), h, U, Ud);
+        bo_step<false>(qn, rn, bo_l_at(l, wsel, n), h, U, Ud);
         bo_mm(U, Pm, t);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -56,7 +58,8 @@ __global__ void __launch_bounds__(128) k_slow_contspec(const SlowCsArgs a)
     bo_chunk_bounds(a.D, a.upsampling, lane, &lo, &hi);
     const double xi = a.xi0 + a.eps_xi * (double)m;
     cplx P[4];
-    bo_chunk_plain(q, lo, hi, make_cplx(xi * a.lweight, 0.0), a.eps_t, a.kappa, a.upsampling, P);
+    bo_chunk_plain(q, a.r ? a.r + (size_t)s * a.D : (const cplx *)0, lo, hi, make_cplx(xi * a.lweight, 0.0), a.eps_t,
+                   a.kappa, a.wsel, P);
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         cplx H[4], t[4];

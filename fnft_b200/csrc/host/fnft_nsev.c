@@ -171,17 +171,21 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     /* "slow" discretizations (no polynomial transfer matrix): BO and CF4_2 run on the GPU, the
      * continuous spectrum as one product of step matrices per spectral point (slow_scatter.cuh) */
     const int slow = (deg0 == 0);
-    if (slow && akns != fnft__akns_discretization_BO && akns != fnft__akns_discretization_CF4_2 &&
-        akns != fnft__akns_discretization_CF4_3)
+    /* weight selector of the commutator-free schemes with more than two exponentials (bo_l_at) */
+    const int cf_wsel = (akns == fnft__akns_discretization_CF4_3)   ? 1
+                        : (akns == fnft__akns_discretization_CF5_3) ? 2
+                        : (akns == fnft__akns_discretization_CF6_4) ? 3
+                                                                    : 0;
+    if (slow && akns != fnft__akns_discretization_BO && akns != fnft__akns_discretization_CF4_2 && cf_wsel == 0)
         return E_NOT_YET_IMPLEMENTED(opts->discretization,
-                                     Of the slow discretizations only BO CF4_2 and CF4_3 run on the GPU.);
+                                     Of the slow discretizations ES4 and TES4 do not run on the GPU.);
     if (!slow && !fnftb__akns_on_gpu(akns))
         return E_NOT_YET_IMPLEMENTED(opts->discretization,
                                      This splitting scheme has no GPU leaf kernel yet.);
     /* src/fnft_nsev.c:209-219: the slow discretizations only support Newton localization */
     if (slow && kappa == +1 && opts->bound_state_localization != fnft_nsev_bsloc_NEWTON)
         return E_INVALID_ARGUMENT(opts->bound_state_localization);
-    if (upsampling > 3)
+    if (upsampling > 4 || (upsampling > 2 && cf_wsel == 0))
         return E_NOT_YET_IMPLEMENTED(opts->discretization, Unsupported upsampling factor.);
     const int want_contspec = (contspec != NULL && M > 0);
     const int want_discspec = (kappa == +1 && bound_states != NULL);
@@ -274,7 +278,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                 goto leave_fun;
             }
             const int rc_sub = (upsampling == 2)   ? fnftb_resample_4split4_sub(ctx, eps_t_full, nskip, Dsub, NULL)
-                               : (upsampling == 3) ? fnftb_resample_cf4_3_sub(ctx, eps_t_full, nskip, Dsub, NULL)
+                               : (upsampling >= 3) ? fnftb_resample_cf_sub(ctx, cf_wsel, (int)kappa, eps_t_full, nskip, Dsub, NULL)
                                                    : fnftb_subsample(ctx, nskip, Dsub);
             if (rc_sub != 0) {
                 ret_code = E_DEVICE;
@@ -301,7 +305,8 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
             if (upsampling >= 2) {
                 int32_t *warn = devptr ? NULL : malloc(nb * sizeof(int32_t));
                 if ((upsampling == 2 ? fnftb_resample_4split4_sub(ctx, eps_t_full, nskip_pass, D_given, warn)
-                                     : fnftb_resample_cf4_3_sub(ctx, eps_t_full, nskip_pass, D_given, warn)) != 0) {
+                                     : fnftb_resample_cf_sub(ctx, cf_wsel, (int)kappa, eps_t_full, nskip_pass, D_given,
+                                                             warn)) != 0) {
                     free(warn);
                     ret_code = E_DEVICE;
                     goto leave_fun;

@@ -292,7 +292,7 @@ FNFT_INT fnft__nse_scatter_bound_states(const FNFT_UINT D, FNFT_COMPLEX const *c
     fnftb_ctx *ctx = ctx_or_error();
     if (ctx == NULL)
         return FNFT_EC_OTHER;
-    if (fnftb_set_signals(ctx, 1, D, q, NULL, 0) != 0)
+    if (fnftb_set_signals(ctx, 1, D, q, NULL, 0) != 0 || fnftb_set_slow_weights(ctx, upsampling == 3 ? 1 : 0) != 0)
         return E_DEVICE;
     const FNFT_UINT D_given = D / upsampling;
     fnftb_bound_desc bd;

@@ -57,6 +57,9 @@ NSE_2SPLIT4B = 11
 NSE_4SPLIT4B = 21
 NSE_CF4_2 = 22
 NSE_CF4_3 = 23
+NSE_CF5_3 = 24
+NSE_CF6_4 = 25
+_SLOW_UP = {NSE_CF4_2: 2, NSE_CF4_3: 3, NSE_CF5_3: 3, NSE_CF6_4: 4}   # upsampling factors of the slow schemes
 # fnft_kdv_discretization_t (include/fnft_kdv_discretization_t.h:96-122)
 KDV_2SPLIT1A, KDV_2SPLIT1B, KDV_2SPLIT2A, KDV_2SPLIT2B, KDV_2SPLIT2S = range(5)
 KDV_2SPLIT4B = 9
@@ -327,6 +330,46 @@ def preprocess_signal(q, eps_t, kappa, nse_disc):
     return q.copy()
 
 
+def cf_complex_weights(nse_disc):
+    """akns_discretization_method_weights for CF5_3 (3x3) and CF6_4 (4x3),
+    src/private/fnft__akns_discretization.c:330-367."""
+    if nse_disc == NSE_CF5_3:
+        s15 = np.sqrt(15.0)
+        w = np.zeros(9, dtype=np.complex128)
+        w[0] = ((145.0 + 37.0 * s15) / 900.0) + 1j * ((5.0 + 3.0 * s15) / 300.0)
+        w[1] = (-1.0 / 45.0) + 1j * (1.0 / 15.0)
+        w[2] = ((145.0 - 37.0 * s15) / 900.0) + 1j * ((5.0 - 3.0 * s15) / 300.0)
+        w[3] = (-2.0 / 45.0) + 1j * (-s15 / 50.0)
+        w[4] = 22.0 / 45.0
+        w[5:9] = np.conj(w[3::-1])
+        return w.reshape(3, 3)
+    h = np.array([0.245985577298764 + 0.038734389227165j, -0.046806149832549 + 0.012442141491185j,
+                  0.010894359342569 - 0.004575808769067j, 0.062868370946917 - 0.048761268117765j,
+                  0.269028372054771 - 0.012442141491185j, -0.041970529810473 + 0.014602687659668j])
+    return np.concatenate([h, h[::-1]]).reshape(4, 3)
+
+
+def preprocess_signal_qr(q, eps_t, kappa, nse_disc):
+    """(q_preprocessed, r_preprocessed) of nse_discretization_preprocess_signal.  For CF5_3 / CF6_4
+    (src/private/fnft__nse_discretization.c:532-604) the complex weights are applied to r = -kappa*conj(q)
+    unconjugated, so r_preprocessed is not -kappa*conj(q_preprocessed); for every other scheme it is."""
+    q = np.asarray(q, dtype=np.complex128)
+    if nse_disc in (NSE_CF5_3, NSE_CF6_4):
+        d = eps_t * np.sqrt(15.0) / 10.0
+        qs = (resample(q, eps_t, -d), q, resample(q, eps_t, +d))
+        rs = tuple(-kappa * np.conj(x) for x in qs)
+        w = cf_complex_weights(nse_disc)
+        up = w.shape[0]
+        qp = np.empty(up * q.shape[0], dtype=np.complex128)
+        rp = np.empty(up * q.shape[0], dtype=np.complex128)
+        for i in range(up):
+            qp[i::up] = w[i, 0] * qs[0] + w[i, 1] * qs[1] + w[i, 2] * qs[2]
+            rp[i::up] = w[i, 0] * rs[0] + w[i, 1] * rs[1] + w[i, 2] * rs[2]
+        return qp, rp
+    qp = preprocess_signal(q, eps_t, kappa, nse_disc)
+    return qp, -kappa * np.conj(qp)
+
+
 def cf4_3_weights():
     """akns_discretization_method_weights for CF4_3, src/private/fnft__akns_discretization.c:299-327:
     Legendre expansion of the coefficient table f at the three Gauss nodes.  Row sums (the weights of
@@ -344,9 +387,12 @@ def cf4_3_weights():
     return w
 
 
-def slow_lweights(upsampling):
+def slow_lweights(upsampling, nse_disc=None):
     """Weights of the spectral parameter per effective sample (period = upsampling),
-    src/private/fnft__akns_scatter_matrix.c:101-144: 1 (BO), 0.5 (CF4_2), row sums of the CF4_3 weights."""
+    src/private/fnft__akns_scatter_matrix.c:101-160: 1 (BO), 0.5 (CF4_2), row sums of the weight matrix
+    (CF4_3 real; CF5_3, CF6_4 complex)."""
+    if nse_disc in (NSE_CF5_3, NSE_CF6_4):
+        return cf_complex_weights(nse_disc).sum(axis=1)
     if upsampling == 1:
         return np.array([1.0])
     if upsampling == 2:
@@ -400,14 +446,14 @@ def nsev_contspec_slow(q, T, M, XI, kappa=+1, nse_disc=NSE_BO, cstype=0):
     q = np.asarray(q, dtype=np.complex128)
     D = q.shape[0]
     eps_t = (T[1] - T[0]) / (D - 1)
-    qp = preprocess_signal(q, eps_t, kappa, nse_disc)
-    lws = slow_lweights({NSE_CF4_2: 2, NSE_CF4_3: 3}.get(nse_disc, 1))
+    qp, rp = preprocess_signal_qr(q, eps_t, kappa, nse_disc)
+    lws = slow_lweights(_SLOW_UP.get(nse_disc, 1), nse_disc)
     xi = XI[0] + (XI[1] - XI[0]) / (M - 1) * np.arange(M)
     S11, S12 = np.ones(M, dtype=np.complex128), np.zeros(M, dtype=np.complex128)
     S21, S22 = np.zeros(M, dtype=np.complex128), np.ones(M, dtype=np.complex128)
     for n in range(qp.shape[0]):
         l = xi * lws[n % lws.size] + 0j
-        (u11, u12, u21, u22), _ = _bo_step(qp[n], -kappa * np.conj(qp[n]), l, eps_t)
+        (u11, u12, u21, u22), _ = _bo_step(qp[n], rp[n], l, eps_t)
         S11, S12, S21, S22 = (u11 * S11 + u12 * S21, u11 * S12 + u12 * S22,
                               u21 * S11 + u22 * S21, u21 * S12 + u22 * S22)
     bc = 0.5
@@ -467,7 +513,7 @@ def _bo_step(q, r, l, h):
     return U, Ud
 
 
-def nse_scatter_bound_states(q, T, lam, upsampling=1):
+def nse_scatter_bound_states(q, T, lam, upsampling=1, r=None, nse_disc=None):
     """fnft__nse_scatter_bound_states for BO (upsampling 1), CF4_2 (upsampling 2) and CF4_3 (3),
     src/private/fnft__nse_scatter_bound_states.c:29-667.  q are the effective
     (preprocessed) samples, r = -conj(q).  Returns (a, aprime, b)."""
@@ -475,10 +521,10 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1):
     lam = np.asarray(lam, dtype=np.complex128)
     D = q.shape[0]
     Dg = D // upsampling
-    r = -np.conj(q)
+    r = -np.conj(q) if r is None else np.asarray(r, dtype=np.complex128)   # CF5_3 / CF6_4: explicit r
     eps_t = (T[1] - T[0]) / (Dg - 1)
     bc = 0.5
-    lws = slow_lweights(upsampling)            # sums of the method weights (:214-221, 232-268)
+    lws = slow_lweights(upsampling, nse_disc)  # sums of the method weights (:214-221, 232-268)
     scl = 1.0 / upsampling                     # :225, 235, 247
     K = lam.shape[0]
     PHI = np.zeros((Dg + 1, 2, K), dtype=np.complex128)
@@ -573,9 +619,10 @@ def nsev_bound_states_newton(q, T, guesses, nse_disc=NSE_2SPLIT4B, niter=10, bsf
     q = np.asarray(q, dtype=np.complex128)
     D = q.shape[0]
     eps_t = (T[1] - T[0]) / (D - 1)
-    up = {NSE_4SPLIT4B: 2, 20: 2, NSE_CF4_2: 2, NSE_CF4_3: 3}.get(nse_disc, 1)
-    qp = preprocess_signal(q, eps_t, +1, nse_disc)
-    deg1 = 0 if nse_disc in (NSE_BO, NSE_CF4_2, NSE_CF4_3) else akns_degree(_NSE2AKNS[nse_disc])
+    up = {NSE_4SPLIT4B: 2, 20: 2, **_SLOW_UP}.get(nse_disc, 1)
+    qp, rp = preprocess_signal_qr(q, eps_t, +1, nse_disc)
+    wd = nse_disc if nse_disc in (NSE_CF5_3, NSE_CF6_4) else None
+    deg1 = 0 if nse_disc == NSE_BO or nse_disc in _SLOW_UP else akns_degree(_NSE2AKNS[nse_disc])
     map_coeff = 2.0 / deg1 if deg1 else 2.0     # src/fnft_nsev.c:612-616
     if bsfilt == 2:      # FULL :633-653
         re = 0.9 * np.pi / abs(map_coeff * eps_t)
@@ -589,7 +636,7 @@ def nsev_bound_states_newton(q, T, guesses, nse_disc=NSE_2SPLIT4B, niter=10, bsf
     for lam in np.asarray(guesses, dtype=np.complex128):
         it = 0
         while niter > 0:  # :1007-1034
-            a, ap, _ = nse_scatter_bound_states(qp, T, np.array([lam]), up)
+            a, ap, _ = nse_scatter_bound_states(qp, T, np.array([lam]), up, rp, wd)
             if a[0] == 0:
                 break
             err = a[0] / ap[0]
@@ -605,7 +652,7 @@ def nsev_bound_states_newton(q, T, guesses, nse_disc=NSE_2SPLIT4B, niter=10, bsf
     bs = np.array(out, dtype=np.complex128)
     if len(bs) == 0:
         return bs, np.zeros(0, dtype=np.complex128)
-    a, ap, b = nse_scatter_bound_states(qp, T, bs, up)
+    a, ap, b = nse_scatter_bound_states(qp, T, bs, up, rp, wd)
     if dstype == 0:
         nc = b
     elif dstype == 1:

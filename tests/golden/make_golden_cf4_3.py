@@ -1,4 +1,4 @@
-"""Golden vectors for fnft_nsev with discretization CF4_3 (fnft_nse_discretization_t 23), produced by the
+"""Golden vectors for fnft_nsev with the discretizations CF4_3, CF5_3, CF6_4 (fnft_nse_discretization_t 23-25), produced by the
 UNMODIFIED reference compiled into oracle/_ref (oracle/ref_lib.py) -- run in the build container:
     python tests/golden/make_golden_cf4_3.py
 Same layout as the "refrun/slow/" entries of make_golden.py; kept in a separate small file so that
@@ -13,8 +13,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_lib as R  # noqa: E402
 
 G = {}
-disc = 23
-for D, kappa in ((100, 1), (256, 1), (255, 1), (256, -1), (300, -1)):
+for disc, D, kappa in [(d, D, k) for d in (23, 24, 25) for D, k in ((100, 1), (256, 1), (255, 1), (256, -1), (300, -1))]:
     tt = np.linspace(-10, 10, D)
     qs = 2.7 / np.cosh(tt) * np.exp(0.4j * tt)
     o = R.nsev_default_opts()

@@ -137,15 +137,16 @@ def test_slow_discretizations_vs_reference_runs(golden):
         assert rel_err(cs, golden[f"refrun/slow/{case}/cs"]) < 1e-12, case
 
 
-def test_cf4_3_vs_reference_runs():
-    # CF4_3 (three exponentials per step, 3x3 Gauss-node weights, fnft__nse_discretization.c:505-531):
+def test_cf_schemes_vs_reference_runs():
+    # CF4_3 (three exponentials per step, 3x3 Gauss-node weights, fnft__nse_discretization.c:505-531), CF5_3 and
+    # CF6_4 (complex weights, explicit r, :532-604):
     # oracle against outputs of the unmodified reference (tests/golden/make_golden_cf4_3.py)
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cf4_3.npz"))
     w = O.cf4_3_weights()
     assert np.allclose(w.sum(axis=1), [11 / 40, 9 / 20, 11 / 40], rtol=0, atol=1e-15)
     cases = sorted({"/".join(k.split("/")[2:5]) for k in g.files if k.startswith("refrun/slow/")})
-    assert len(cases) == 5
+    assert len(cases) == 15
     for case in cases:
         disc, D, kappa = map(int, case.split("/"))
         q = g[f"refrun/slow/{case}/q"]

@@ -8,7 +8,7 @@ tests/golden/reftests.npz holds the test cases produced by the reference's gener
 Each call is repeated through the C-ABI with the same options, the result is compared with the exact
 spectra by a restatement of nsev_compare_nfs (fnft__nsev_testcases.c:596-712) / misc_rel_err and must
 meet the reference's OWN error bounds for that call.  Calls that use a discretization this library does
-not implement (CF5_3, CF6_4, ES4, TES4) are skipped and counted.
+not implement (ES4, TES4) are skipped and counted.
 """
 import json
 import os
@@ -19,7 +19,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 CALLS = json.load(open(os.path.join(HERE, "golden", "reftests.json")))
-UNSUPPORTED_NSE = {24: "CF5_3", 25: "CF6_4", 26: "ES4", 27: "TES4"}
+UNSUPPORTED_NSE = {26: "ES4", 27: "TES4"}
 
 
 @pytest.fixture(scope="module")
