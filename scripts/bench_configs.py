@@ -6,6 +6,7 @@
   5  fnft_nsep main + auxiliary spectrum (grid search), D = 4096, B = 1024
   6  the same signals with fnft_nsep's default localization (MIXED)
   7  config 3's signals through fnft_nsev with its default options (SUBSAMPLE_AND_REFINE)
+  8  fnft_nsev reflection coefficient with the slow discretizations CF4_3 / CF5_3 / CF6_4, D = M = 1024, B = 256
 
 For each: throughput of the batched C-ABI call with host buffers (wall clock around the
 call, best of --reps), the reference library (oracle/_ref) on a bounded sample over all
@@ -138,6 +139,18 @@ def _ref5(args):
     return time.perf_counter() - t0, ret, main, aux
 
 
+def _ref8(args):
+    from oracle import ref_lib as R
+    q, T, M, XI, disc = args
+    R.lib().fnft_errwarn_setprintf(None)
+    o = R.nsev_default_opts()
+    o.discretization = disc
+    o.bound_state_localization = 1
+    t0 = time.perf_counter()
+    ret, cs, *_ = R.nsev(q, T, M, XI, -1, o)
+    return time.perf_counter() - t0, ret, cs
+
+
 def run_pool(fn, tasks):
     nc = cores()
     with mp.Pool(nc) as pool:
@@ -194,6 +207,19 @@ def main():
         if have_ref and 5 in todo:
             n = args.ref_signals or min(B, nc)
             ref[5] = run_pool(_ref5, [(Q5[i], (0.0, 2 * np.pi)) for i in range(n)])
+
+    if 8 in todo:
+        B, D = max(int(256 * args.scale), 16), 1024
+        T8, XI8 = (-16.0, 16.0), (-6.0, 6.0)
+        t = np.linspace(T8[0], T8[1], D)
+        rng = np.random.default_rng(1024)
+        Q8 = np.stack([(0.5 + 2.0 * rng.random()) / np.cosh(t - rng.normal(0, 0.5)) *
+                       np.exp(1j * rng.normal(0, 0.4) * t) for _ in range(B)])
+        inputs[8] = Q8
+        if have_ref:
+            n = args.ref_signals or min(B, 2 * nc)
+            for disc in (23, 24, 25):
+                ref[(8, disc)] = run_pool(_ref8, [(Q8[i], T8, D, XI8, disc) for i in range(n)])
 
     import fnft_b200 as F
     F.lib().fnft_errwarn_setprintf(None)
@@ -349,6 +375,32 @@ def main():
                                  "reflection coefficient, M=D), D=4096, 8-soliton signals, B=%d" % B,
                         value=B / dt, unit="signals/s", ms_per_call=dt * 1e3, ret=int(ret),
                         mean_K=float(Ka.mean()), all_eigenvalues_found=ok / B)
+        elif cfg == 8:
+            # slow (O(D*M)) commutator-free schemes: one warp per spectral point, D products of 2x2 exponentials
+            Q, T, XI = inputs[8], T8, XI8
+            B, D = Q.shape
+            per = {}
+            for name, disc in (("CF4_3", 23), ("CF5_3", 24), ("CF6_4", 25)):
+                o = F.nsev_default_opts()
+                o.discretization = disc
+                o.bound_state_localization = 1
+
+                def run():
+                    return F.nsev_batch(Q, T, D, XI, -1, o)
+                run()
+                dt, out = best_of(run, args.reps)
+                ret, cs = out[0], out[1]
+                entry = {"signals_per_s": B / dt, "ms_per_call": dt * 1e3, "ret": int(ret)}
+                if (8, disc) in ref:
+                    res, wall = ref[(8, disc)]
+                    nref = len(res)
+                    entry["reference_signals_per_s"] = nref / wall
+                    entry["max_rel_err_vs_reference"] = max(
+                        float(np.abs(cs[i] - res[i][2]).sum() / np.abs(res[i][2]).sum()) for i in range(nref))
+                per[name] = entry
+            line.update(workload="fnft_nsev reflection coefficient, slow discretizations CF4_3 / CF5_3 / CF6_4, "
+                                 "D=M=1024, kappa=-1, B=%d" % B, unit="signals/s", value=per["CF4_3"]["signals_per_s"],
+                        per_scheme=per, cores=cores())
         print(json.dumps(line), flush=True)
 
 
