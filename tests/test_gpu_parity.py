@@ -392,6 +392,33 @@ def test_nsev_cf_schemes_vs_reference_runs(F):
             assert O.misc_rel_err(cs1, O.nsev_contspec_slow(Q[b], [-10, 10], 32, [-2, 2], -1, disc, 0)) < 1e-9
 
 
+def test_private_scatter_bound_states_cf4_3(F):
+    # fnft__nse_scatter_bound_states with discretization CF4_3 on samples the caller preprocessed
+    # (three exponentials per step, fnft__nse_scatter_bound_states.c:240-253): a, a' and b against the oracle and,
+    # when oracle/_ref travelled to the box, against the unmodified reference
+    F.lib().fnft_errwarn_setprintf(None)
+    D, T = 300, [-10.0, 10.0]
+    t = np.linspace(T[0], T[1], D)
+    q = 2.7 / np.cosh(t) * np.exp(0.4j * t)
+    qp = O.preprocess_signal(q, (T[1] - T[0]) / (D - 1), 1, 23)
+    lam = np.array([-0.2 + 0.2j, -0.2 + 1.2j, -0.2 + 2.2j, 0.3 + 0.7j])
+    ret, a, ap, b = F.nse_scatter_bound_states(qp, None, T, lam, 23)
+    assert ret == 0
+    ao, apo, bo = O.nse_scatter_bound_states(qp, T, lam, 3)
+    # b = PHI1/PSI1 at the sample minimising the error metric; the lam above are only close to eigenvalues, so b
+    # depends weakly on the chosen sample and neighbouring candidates differ by ~1e-9: 1e-8 for b, 1e-9 for a, a'
+    for ours, want, tol in ((a, ao, 1e-9), (ap, apo, 1e-9), (b, bo, 1e-8)):
+        assert (np.abs(ours - want) <= tol * np.maximum(np.abs(want), 1.0)).all()   # a ~ 1e-10 at the eigenvalues
+    if R.available():
+        R.lib().fnft_errwarn_setprintf(None)
+        ret, ar, apr, br = R.nse_scatter_bound_states(qp, -np.conj(qp), T, lam, 23)
+        assert ret == 0
+        for ours, want, tol in ((a, ar, 1e-9), (ap, apr, 1e-9), (b, br, 1e-8)):
+            assert (np.abs(ours - want) <= tol * np.maximum(np.abs(want), 1.0)).all()
+    # a length that is not a multiple of 3 is rejected like in the reference (E_ASSERTION_FAILED = 9 ... any error)
+    assert F.nse_scatter_bound_states(qp[:-1], None, T, lam, 23)[0] != 0
+
+
 def test_nsev_batch_default_options_matches_single_calls(F):
     D, B = 512, 6
     t = np.linspace(-10, 10, D)
