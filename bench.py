@@ -15,6 +15,18 @@ in HBM), `e2e` = through the C-ABI fnft_nsev_batch with pinned HOST buffers (H2D
 inside the timed region), `roofline` = product-tree algorithmic bytes / tree kernel
 time (CUDA events per launch) against the measured HBM copy bandwidth, `cpu_baseline` =
 the reference library timed on this box's host cores on a bounded sample.
+
+PARITY GATE: every rank compares outputs of its OWN shard -- the
+device-resident run and the host-buffer run -- with the unmodified reference
+(oracle/_ref) on the same signals, metric misc_rel_err (src/private/fnft__misc.c:41-51);
+the maximum over all ranks is printed as `parity` and the process exits with status 1
+when it exceeds its bound (also for the extra configurations below).  `--corrupt`
+perturbs one output value on the last rank to show that the gate trips.
+
+Extra keys (`--no-extras` skips them): `strong` = BASELINE config 2 as written, ONE batch
+of 4096 signals split over the ranks; `configs` = BASELINE configs 3, 4 and 5 (Newton bound
+states, fnft_kdvv 4SPLIT4B, fnft_nsep grid search), each ONE batch sharded over the ranks,
+timed through the batched C-ABI calls with host buffers and checked against the reference.
 """
 import argparse
 import ctypes as C
@@ -38,11 +50,23 @@ KAPPA = +1
 BATCH_PER_GPU = 4096
 SEED = 16384
 DEG0 = 2  # 2SPLIT4B
+PARITY_BOUND = 1e-9
 
 
 def tree_bytes_per_signal(d0=DEG0, dd=D):
     # one read + one write of every tree level
     return 16 * (8 * d0 * dd * int(math.log2(dd)) + 12 * dd - 12)
+
+
+def shard_range(B, rank, world):
+    base, extra = divmod(B, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def rel_err(a, b):
+    """misc_rel_err, src/private/fnft__misc.c:41-51"""
+    return float(np.abs(np.asarray(a) - np.asarray(b)).sum() / np.abs(np.asarray(b)).sum())
 
 
 # ----------------------------------------------------------------------------------
@@ -57,6 +81,8 @@ def signal_params(B, seed=SEED):
 
 
 def signals_numpy(P, idx):
+    """Signals with the GLOBAL indices idx of the parameter set P (the parity of the global
+    index selects the family)."""
     t = np.linspace(TT[0], TT[1], D)
     out = np.empty((len(idx), D), dtype=np.complex128)
     for o, b in enumerate(idx):
@@ -70,14 +96,16 @@ def signals_numpy(P, idx):
     return out
 
 
-def signals_torch(P, B, device):
+def signals_torch(P, g0, g1, device):
+    """Signals with the global indices g0 .. g1-1 of the parameter set P, on the GPU."""
     import torch
+    B = g1 - g0
     t = torch.linspace(TT[0], TT[1], D, dtype=torch.float64, device=device)[None, :]
     tt = lambda a: torch.as_tensor(a, dtype=torch.float64, device=device)
     q = torch.empty((B, D), dtype=torch.complex128, device=device)
     step = 512
-    for b0 in range(0, B, step):
-        b1 = min(B, b0 + step)
+    for b0 in range(g0, g1, step):
+        b1 = min(g1, b0 + step)
         A = tt(P["A"][b0:b1])[:, None]
         even = A / torch.cosh(t) * torch.exp(1j * (-2 * tt(P["lam0"][b0:b1])[:, None] * t
                                                   + tt(P["phi"][b0:b1])[:, None]))
@@ -87,14 +115,92 @@ def signals_torch(P, B, device):
                 2 * math.pi * (k + 1) * t / 64 + tt(P["psi"][b0:b1, k])[:, None])
         odd = A / torch.cosh(t / tt(P["w"][b0:b1])[:, None]) * torch.exp(1j * th)
         is_even = (torch.arange(b0, b1, device=device) % 2 == 0)[:, None]
-        q[b0:b1] = torch.where(is_even, even, odd)
+        q[b0 - g0:b1 - g0] = torch.where(is_even, even, odd)
     return q
 
 
 # ----------------------------------------------------------------------------------
-# CPU reference leg (oracle/_ref): process pool over the host cores
+# BASELINE configs 3, 4, 5: inputs by GLOBAL signal index, so that every
+# rank can build exactly its shard
 # ----------------------------------------------------------------------------------
-def _ref_worker(args):
+C3 = dict(B=1024, D=4096, K=8, T=(-20.0, 20.0), seed=4096)
+C4 = dict(B=2048, D=8192, M=8192, T=(-16.0, 15.0), XI=(-3.55, 3.95), seed=8192)
+C5 = dict(B=1024, D=4096, T=(0.0, 2 * math.pi), seed=40960)
+
+
+class InvOpts(C.Structure):  # include/fnft_nsev_inverse.h (oracle side only)
+    _fields_ = [("discretization", C.c_int), ("contspec_type", C.c_int),
+                ("contspec_inversion_method", C.c_int), ("discspec_type", C.c_int),
+                ("max_iter", C.c_size_t), ("oversampling_factor", C.c_size_t)]
+
+
+def _soliton_worker(args):
+    """exact multi-soliton by the reference's fnft_nsev_inverse (pure CDT), oracle/_ref"""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_lib as R
+    lam, b, Dn, T = args
+    L = R.lib()
+    L.fnft_nsev_inverse_default_opts.restype = InvOpts
+    o = L.fnft_nsev_inverse_default_opts()
+    o.discspec_type = 0  # norming constants
+    K = len(lam)
+    q = np.zeros(Dn, dtype=np.complex128)
+    Ta = np.array(T, dtype=np.float64)
+    XIz = np.zeros(2)
+    lam = np.ascontiguousarray(lam, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    L.fnft_nsev_inverse.argtypes = None
+    ret = L.fnft_nsev_inverse(C.c_size_t(0), None, XIz.ctypes.data_as(C.c_void_p), C.c_size_t(K),
+                              lam.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                              C.c_size_t(Dn), q.ctypes.data_as(C.c_void_p),
+                              Ta.ctypes.data_as(C.c_void_p), C.c_int32(1), C.byref(o))
+    if ret != 0:
+        raise RuntimeError("fnft_nsev_inverse returned %d" % ret)
+    return q
+
+
+def config3_params(B=C3["B"], K=C3["K"], seed=C3["seed"]):
+    rng = np.random.default_rng(seed)
+    lams = np.empty((B, K), dtype=np.complex128)
+    for i in range(B):
+        while True:
+            lam = rng.uniform(-2, 2, K) + 1j * rng.uniform(0.3, 2.3, K)
+            d = np.abs(lam[:, None] - lam[None, :]) + 10 * np.eye(K)
+            if d.min() >= 0.1:
+                break
+        lams[i] = lam
+    bn = np.exp(1j * rng.uniform(0, 2 * np.pi, (B, K)))
+    guesses = lams + 0.01 * (rng.normal(size=(B, K)) + 1j * rng.normal(size=(B, K)))
+    return lams, bn, guesses
+
+
+def config4_inputs(g0, g1):
+    rng = np.random.default_rng(C4["seed"])
+    B = C4["B"]
+    A, t0, w = rng.uniform(0.5, 3.2, B), rng.uniform(-2, 2, B), rng.uniform(0.7, 1.5, B)
+    t = np.linspace(C4["T"][0], C4["T"][1], C4["D"])[None, :]
+    s = slice(g0, g1)
+    return (A[s, None] / np.cosh((t - t0[s, None]) / w[s, None]) ** 2).astype(np.complex128)
+
+
+def config5_inputs(g0, g1):
+    rng = np.random.default_rng(C5["seed"])
+    B, Dn = C5["B"], C5["D"]
+    A = rng.uniform(0.5, 2.5, B)
+    m = rng.integers(0, 5, B)
+    k = rng.integers(1, 5, B)
+    e = rng.uniform(0, 0.3, B)
+    ph = rng.uniform(0, 2 * np.pi, B)
+    t = (2 * np.pi / Dn * np.arange(Dn))[None, :]
+    s = slice(g0, g1)
+    return A[s, None] * np.exp(1j * m[s, None] * t) * (1 + e[s, None] * np.cos(k[s, None] * t + ph[s, None]))
+
+
+# ----------------------------------------------------------------------------------
+# CPU reference legs (oracle/_ref): process pools over the host cores.  "fork" before CUDA
+# is initialised in this process, "spawn" afterwards.
+# ----------------------------------------------------------------------------------
+def _ref_worker(args):  # config 2
     sys.path.insert(0, ROOT)
     from oracle import ref_lib as R
     q, = args
@@ -104,6 +210,42 @@ def _ref_worker(args):
     return ret, time.perf_counter() - t0, cs
 
 
+def _ref3(args):
+    sys.path.insert(0, ROOT)
+    from oracle import ref_lib as R
+    q, g = args
+    R.lib().fnft_errwarn_setprintf(None)
+    o = R.nsev_default_opts()
+    o.bound_state_localization = 1  # NEWTON
+    o.discspec_type = 2             # BOTH
+    ret, cs, K, bs, nc = R.nsev(q, C3["T"], 0, None, 1, o, K=len(g), bound_states=g, want_contspec=False)
+    return ret, K, bs, nc
+
+
+def _ref4(args):
+    sys.path.insert(0, ROOT)
+    from oracle import ref_lib as R
+    u, = args
+    o = R.lib().fnft_kdvv_default_opts()
+    o.discretization = 19  # kdv 4SPLIT4B
+    ret, cs = R.kdvv(u, C4["T"], C4["M"], C4["XI"], o)
+    return ret, cs
+
+
+def _ref5(args):
+    sys.path.insert(0, ROOT)
+    from oracle import ref_lib as R
+    q, = args
+    R.lib().fnft_errwarn_setprintf(None)
+    o = R.lib().fnft_nsep_default_opts()
+    o.localization = 1  # GRIDSEARCH
+    o.filtering = 1     # MANUAL
+    o.bounding_box[0], o.bounding_box[1], o.bounding_box[2], o.bounding_box[3] = -10, 10, -10, 10
+    o.discretization = 11  # 2SPLIT4B
+    ret, main, aux = R.nsep(q, C5["T"], 1, o)
+    return ret, main, aux
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -111,22 +253,32 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_reference_sample(nsig, cores, P=None):
-    """Times the reference on `nsig` signals with `cores` worker processes.
-    Returns (signals_per_s, wall_s, outputs)."""
+def pool_map(fn, tasks, workers, method, warm=True):
+    """Maps fn over tasks in a process pool; returns (results, wall seconds of the timed map)."""
     import multiprocessing as mp
-    if P is None:
-        P = signal_params(max(nsig, 2))
-    q = signals_numpy(P, list(range(nsig)))
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_ref_worker, [(q[0],)] * min(cores, nsig))  # warm-up: load lib, page in
+    ctx = mp.get_context(method)
+    workers = max(1, min(workers, len(tasks)))
+    with ctx.Pool(workers) as pool:
+        if warm:
+            pool.map(fn, tasks[:workers])  # load the library, page in
         t0 = time.perf_counter()
-        res = pool.map(_ref_worker, [(q[i],) for i in range(nsig)], chunksize=1)
+        res = pool.map(fn, tasks, chunksize=1)
         wall = time.perf_counter() - t0
     if any(r[0] != 0 for r in res):
         raise RuntimeError("reference returned an error code")
-    return nsig / wall, wall, [r[2] for r in res]
+    return res, wall
+
+
+def run_reference_sample(nsig, cores, P=None, idx=None, method="fork"):
+    """Times the reference on signals idx (default: the first nsig) with `cores` worker
+    processes.  Returns (signals_per_s, wall_s, outputs)."""
+    if P is None:
+        P = signal_params(max(nsig, 2))
+    if idx is None:
+        idx = list(range(nsig))
+    q = signals_numpy(P, idx)
+    res, wall = pool_map(_ref_worker, [(q[i],) for i in range(len(idx))], cores, method)
+    return len(idx) / wall, wall, [r[2] for r in res]
 
 
 def cpu_model():
@@ -137,6 +289,12 @@ def cpu_model():
     except Exception:
         pass
     return "unknown"
+
+
+def spread(n_total, n_pick):
+    """n_pick indices spread over range(n_total), first and last included"""
+    n_pick = max(1, min(n_pick, n_total))
+    return sorted(set(int(round(i * (n_total - 1) / max(1, n_pick - 1))) for i in range(n_pick)))
 
 
 # ----------------------------------------------------------------------------------
@@ -191,7 +349,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------
-def measured_hbm_peak():
+def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -230,6 +388,41 @@ def _emit(line):
         os.write(_JSON_FD, data)
 
 
+def log(*a):
+    print("[bench rank %s]" % os.environ.get("RANK", "0"), *a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------
+# parity comparisons of the extra configurations
+# ----------------------------------------------------------------------------------
+def compare3(Ka, bs, ncs, ref, K):
+    """bound states / norming constants / residues against the reference, matched by nearest
+    eigenvalue like nsev_compare_nfs (src/private/fnft__nsev_testcases.c:664-705)"""
+    ret, Kr, bsr, ncr = ref
+    if int(Ka) != int(Kr):
+        return float("inf")
+    e = 0.0
+    for j in range(Kr):
+        jj = int(np.argmin(np.abs(bs[:Kr] - bsr[j])))
+        e = max(e, abs(bs[jj] - bsr[j]) / abs(bsr[j]))
+        e = max(e, abs(ncs[jj] - ncr[j]) / abs(ncr[j]))
+        e = max(e, abs(ncs[K + jj] - ncr[Kr + j]) / abs(ncr[Kr + j]))
+    return float(e)
+
+
+def compare5(Ka, main, Ma, aux, ref):
+    ret, m0, a0 = ref
+    m1, a1 = main[:int(Ka)], aux[:int(Ma)]
+    if len(m0) != len(m1) or len(a0) != len(a1):
+        return float("inf")
+    e = 0.0
+    if len(m0):
+        e = max(e, float(np.abs(m1 - m0).max() / max(1.0, np.abs(m0).max())))
+    if len(a0):
+        e = max(e, float(np.abs(a1 - a0).max() / max(1.0, np.abs(a0).max())))
+    return e
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -239,7 +432,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="signals per GPU per step")
     ap.add_argument("--ref-signals", type=int, default=0, help="signals per reference step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true",
+                    help="skip the timed reference leg AND the parity gate (profiling runs only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip `strong` and `configs`")
+    ap.add_argument("--parity-signals", type=int, default=16, help="signals per rank checked against the reference")
+    ap.add_argument("--corrupt", action="store_true", help="perturb one output on the last rank (gate self-test)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -280,20 +477,86 @@ def main():
         _emit(line)
         return 0
 
+    from oracle import ref_lib as R
+    have_ref = R.available() and not args.no_cpu_baseline
+    extras = not args.no_extras
+    B = args.batch
+    npar = args.parity_signals
+
+    # the workloads and this rank's shard of each (global signal indices)
+    P_weak = signal_params(B * world)          # weak run: rank r owns [r*B, (r+1)*B)
+    weak0 = rank * B
+    P_strong = signal_params(BATCH_PER_GPU)     # strong run: ONE batch of 4096 split over the ranks
+    s0, s1 = shard_range(BATCH_PER_GPU, rank, world)
+    g3 = shard_range(C3["B"], rank, world)
+    g4 = shard_range(C4["B"], rank, world)
+    g5 = shard_range(C5["B"], rank, world)
+    lam3, bn3, guess3 = config3_params()
+
+    # reference outputs for the parity gate: name -> (local indices, outputs)
+    refs, cpu_base, Q3 = {}, {}, None
+
+    def reference_phase(method, workers, timed):
+        """Runs the reference on samples of this rank's shards.  timed (rank 0, before CUDA is
+        initialised, all cores): larger samples whose wall time is the CPU baseline."""
+        nonlocal Q3
+        # config 2, weak run
+        n = min(B, max(8 * cores, 64)) if timed else min(B, npar)
+        idx = list(range(n)) if timed else spread(B, n)
+        rate, wall, outs = run_reference_sample(n, workers, P_weak, [weak0 + i for i in idx], method)
+        refs["weak"] = (idx, outs)
+        if timed:
+            cpu_base["weak"] = {"value": rate, "unit": "signals/s", "cores": workers, "kind": "reference",
+                                "sample": "first %d signals of the batch, one signal per task over %d "
+                                          "worker processes, %.1f s wall" % (n, workers, wall),
+                                "cpu": cpu_model()}
+        if not extras:
+            return
+        # config 2, strong run (at N = 1 it is the same batch as the weak run)
+        if world > 1 or B != BATCH_PER_GPU:
+            idx = spread(s1 - s0, min(npar, 8))
+            _, _, outs = run_reference_sample(len(idx), workers, P_strong, [s0 + i for i in idx], method)
+            refs["strong"] = (idx, outs)
+        else:
+            refs["strong"] = refs["weak"]
+        # config 3: this rank's solitons, then the reference's Newton run on a sample
+        tasks = [(lam3[i], bn3[i], C3["D"], C3["T"]) for i in range(g3[0], g3[1])]
+        import multiprocessing as mp
+        with mp.get_context(method).Pool(max(1, min(workers, len(tasks)))) as pool:
+            Q3 = np.array(pool.map(_soliton_worker, tasks, chunksize=4))
+        n = min(g3[1] - g3[0], 4 * cores) if timed else min(g3[1] - g3[0], 8)
+        idx = list(range(n)) if timed else spread(g3[1] - g3[0], n)
+        res, wall = pool_map(_ref3, [(Q3[i], guess3[g3[0] + i]) for i in idx], workers, method)
+        refs["c3"] = (idx, res)
+        if timed:
+            cpu_base["c3"] = {"value": n / wall, "unit": "signals/s", "cores": workers, "kind": "reference",
+                              "sample": "%d signals, %.1f s wall" % (n, wall)}
+        # config 4
+        n = min(g4[1] - g4[0], 4 * cores) if timed else min(g4[1] - g4[0], 8)
+        idx = list(range(n)) if timed else spread(g4[1] - g4[0], n)
+        U = config4_inputs(g4[0], g4[1])
+        res, wall = pool_map(_ref4, [(U[i],) for i in idx], workers, method)
+        refs["c4"] = (idx, res)
+        if timed:
+            cpu_base["c4"] = {"value": n / wall, "unit": "signals/s", "cores": workers, "kind": "reference",
+                              "sample": "%d signals, %.1f s wall" % (n, wall)}
+        # config 5
+        n = min(g5[1] - g5[0], cores) if timed else min(g5[1] - g5[0], 2)
+        idx = list(range(n)) if timed else spread(g5[1] - g5[0], n)
+        Q5 = config5_inputs(g5[0], g5[1])
+        res, wall = pool_map(_ref5, [(Q5[i],) for i in idx], workers, method, warm=False)
+        refs["c5"] = (idx, res)
+        if timed:
+            cpu_base["c5"] = {"value": n / wall, "unit": "signals/s", "cores": workers, "kind": "reference",
+                              "sample": "%d signals, %.1f s wall" % (n, wall)}
+
     # ------------------------------------------------------------------ CPU baseline first
-    # (before CUDA is initialised in this process: the pool is forked)
-    cpu_baseline = None
-    P_all = signal_params(args.batch)
-    ref_out = None
-    if rank == 0 and not args.no_cpu_baseline:
-        from oracle import ref_lib as R
-        if R.available():
-            nsig = min(args.batch, max(8 * cores, 64))  # ~20 core-seconds of reference work
-            rate, wall, ref_out = run_reference_sample(nsig, cores, P_all)
-            cpu_baseline = {"value": rate, "unit": "signals/s", "cores": cores, "kind": "reference",
-                            "sample": "first %d signals of the batch, one signal per task over %d "
-                                      "worker processes, %.1f s wall" % (nsig, cores, wall),
-                            "cpu": cpu_model()}
+    # (rank 0, before CUDA is initialised in this process: the pools are forked; the other ranks
+    # wait in the process-group rendezvous, so the timed reference has the host cores to itself)
+    if rank == 0 and have_ref:
+        t0 = time.perf_counter()
+        reference_phase("fork", cores, True)
+        log("reference phase (timed CPU baselines) %.1f s" % (time.perf_counter() - t0))
 
     # ------------------------------------------------------------------ GPU arm
     import torch
@@ -308,22 +571,6 @@ def main():
     L = F.lib()
     if L.fnft_b200_set_device(local_rank) != 0:
         raise SystemExit("fnft_b200_set_device failed")
-    B = args.batch
-    # every rank works on its own shard: signal parameters are offset by rank
-    P = signal_params(B * world)
-    P = {k: v[rank * B:(rank + 1) * B] for k, v in P.items()}
-    q_dev = signals_torch(P, B, dev)
-    out_dev = torch.zeros((B, M), dtype=torch.complex128, device=dev)
-    Tarr = np.array(TT, dtype=np.float64)
-    XIarr = np.array(XI, dtype=np.float64)
-    opts = L.fnft_nsev_default_opts()  # 2SPLIT4B, reflection coefficient, normalisation on
-    stream = torch.cuda.ExternalStream(L.fnft_b200_stream(), device=dev)
-
-    def step_device():
-        rc = L.fnft_nsev_batch(B, D, q_dev.data_ptr(), Tarr.ctypes.data, M, out_dev.data_ptr(),
-                               XIarr.ctypes.data, None, 0, None, None, KAPPA, C.addressof(opts), None)
-        if rc != 0:
-            raise SystemExit("fnft_nsev_batch (device pointers) failed with code %d" % rc)
 
     def barrier():
         if world > 1:
@@ -335,6 +582,36 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    barrier()
+    # the other ranks compute the references of their own shards now (spawned pools: CUDA is up),
+    # sharing the host cores among themselves while rank 0 idles
+    if rank != 0 and have_ref:
+        reference_phase("spawn", max(1, cores // max(1, world - 1)), False)
+    barrier()
+
+    q_dev = signals_torch(P_weak, weak0, weak0 + B, dev)
+    out_dev = torch.zeros((B, M), dtype=torch.complex128, device=dev)
+    Tarr = np.array(TT, dtype=np.float64)
+    XIarr = np.array(XI, dtype=np.float64)
+    opts = L.fnft_nsev_default_opts()  # 2SPLIT4B, reflection coefficient, normalisation on
+    stream = torch.cuda.ExternalStream(L.fnft_b200_stream(), device=dev)
+
+    def nsev_call(nb, qptr, outptr):
+        rc = L.fnft_nsev_batch(nb, D, qptr, Tarr.ctypes.data, M, outptr, XIarr.ctypes.data, None, 0, None, None,
+                               KAPPA, C.addressof(opts), None)
+        if rc != 0:
+            raise SystemExit("fnft_nsev_batch failed with code %d" % rc)
+
+    def step_device():
+        nsev_call(B, q_dev.data_ptr(), out_dev.data_ptr())
 
     # ---- device-resident throughput ("value")
     L.fnft_b200_set_device_pointers(1)
@@ -361,14 +638,20 @@ def main():
     ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
     value = world * B * args.steps / (ms_dev * 1e-3)
 
-    # ---- parity spot check against the reference outputs computed for the CPU baseline
-    parity = None
-    if ref_out is not None:
-        got = out_dev[:len(ref_out)].cpu().numpy()
-        errs = [float(np.abs(got[i] - ref_out[i]).sum() / np.abs(ref_out[i]).sum())
-                for i in range(len(ref_out))]
-        parity = {"metric": "misc_rel_err(ours, reference) per signal, max over the sample",
-                  "max": max(errs), "signals": len(errs), "bound": 1e-9}
+    # ---- parity gate, part 1: device-resident outputs of THIS rank's shard against the reference
+    parity_local = {}   # name -> max error on this rank
+    parity_count = {}
+
+    def gate(name, errs):
+        parity_local[name] = max([parity_local.get(name, 0.0)] + [float(e) for e in errs])
+        parity_count[name] = parity_count.get(name, 0) + len(errs)
+
+    if args.corrupt and rank == world - 1:
+        out_dev[0, M // 2] += 1.0
+    if "weak" in refs:
+        idx, outs = refs["weak"]
+        got = out_dev[idx].cpu().numpy()
+        gate("config2_device", [rel_err(got[i], outs[i]) for i in range(len(idx))])
 
     # ---- per-kernel timing (CUDA events around every launch) for the roofline
     L.fnft_b200_profile_enable(1)
@@ -378,7 +661,7 @@ def main():
     tree_ms = sum(ms for k, (n, ms) in rep.items() if k.startswith("tree_"))
     tree_launches = sum(n for k, (n, ms) in rep.items() if k.startswith("tree_"))
     total_ms = sum(ms for k, (n, ms) in rep.items())
-    peak, peak_src = measured_hbm_peak()
+    peak, peak_src = measured_peaks()
     bts = tree_bytes_per_signal()
     achieved = bts * B / (tree_ms * 1e-3) / 1e9
     # physical DRAM traffic of the tree kernels: per-signal bytes from the committed ncu capture
@@ -399,6 +682,10 @@ def main():
                 "algorithmic_bytes_per_signal": bts, "tree_ms_per_step": tree_ms,
                 "tree_launches_per_step": tree_launches, "tree_share_of_step": tree_ms / total_ms,
                 "kernel_ms_per_step": {k: round(ms, 4) for k, (n, ms) in sorted(rep.items())}}
+    # FP64 pipe: DFMA throughput of this GPU measured by the library's own probe kernel
+    if hasattr(L, "fnft_b200_probe_fp64_tflops"):
+        L.fnft_b200_probe_fp64_tflops.restype = C.c_double
+        roofline["fp64_peak_tflops_measured"] = float(L.fnft_b200_probe_fp64_tflops())
 
     # ---- end to end through the C-ABI with pinned host buffers ("e2e")
     L.fnft_b200_set_device_pointers(0)
@@ -407,10 +694,7 @@ def main():
     out_host = torch.empty((B, M), dtype=torch.complex128, pin_memory=True)
 
     def step_host():
-        rc = L.fnft_nsev_batch(B, D, q_host.data_ptr(), Tarr.ctypes.data, M, out_host.data_ptr(),
-                               XIarr.ctypes.data, None, 0, None, None, KAPPA, C.addressof(opts), None)
-        if rc != 0:
-            raise SystemExit("fnft_nsev_batch (host pointers) failed with code %d" % rc)
+        nsev_call(B, q_host.data_ptr(), out_host.data_ptr())
 
     out_host.zero_()  # touch the pinned pages before the first DMA
     for _ in range(args.warmup):
@@ -430,6 +714,161 @@ def main():
            "h2d_bytes_per_step": B * D * 16, "d2h_bytes_per_step": B * M * 16,
            "ms_per_step": ms_e2e / args.steps, "ms_each_step_rank0": step_ms,
            "api": "fnft_nsev_batch (C-ABI, libfnft_b200.so) with pinned host buffers"}
+    if "weak" in refs:  # parity gate, part 2: the host-buffer path
+        idx, outs = refs["weak"]
+        got = out_host[idx].numpy()
+        gate("config2_e2e", [rel_err(got[i], outs[i]) for i in range(len(idx))])
+
+    # ---- what the box can copy at all: every rank moves its step's bytes host->device and
+    # device->host concurrently (plain cudaMemcpyAsync on two streams, no kernels)
+    st_in, st_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    nrep = 3
+    for _ in range(nrep):
+        with torch.cuda.stream(st_in):
+            q_dev.copy_(q_host, non_blocking=True)
+        with torch.cuda.stream(st_out):
+            out_host.copy_(out_dev, non_blocking=True)
+    torch.cuda.synchronize()
+    ms_copy = max_over_ranks((time.perf_counter() - t0) * 1e3) / nrep
+    barrier()
+    bytes_step = B * D * 16 + B * M * 16
+    e2e["copy_only_ms_per_step"] = ms_copy
+    e2e["copy_ceiling_gbs_all_ranks"] = world * bytes_step / (ms_copy * 1e-3) / 1e9
+    e2e["copy_ceiling_signals_per_s"] = world * B / (ms_copy * 1e-3)
+    e2e["frac_of_copy_ceiling"] = e2e["value"] / e2e["copy_ceiling_signals_per_s"]
+
+    # ------------------------------------------------------------------ extras
+    strong, cfgs = None, None
+    if extras:
+        def timed_call(fn, reps=3):
+            """best of reps of: barrier, wall clock around fn() + synchronize, max over ranks"""
+            best, out = None, None
+            for rep in range(reps + 1):  # the first one warms up and does not count
+                torch.cuda.synchronize()
+                barrier()
+                t0 = time.perf_counter()
+                out = fn()
+                L.fnft_b200_synchronize()
+                dt = max_over_ranks(time.perf_counter() - t0)
+                if rep > 0:
+                    best = dt if best is None else min(best, dt)
+            return best, out
+
+        # --- strong scaling of config 2: ONE batch of 4096 signals, shard [s0, s1) here
+        nb = s1 - s0
+        qs_dev = signals_torch(P_strong, s0, s1, dev)
+        L.fnft_b200_set_device_pointers(1)
+        dt_dev, _ = timed_call(lambda: nsev_call(nb, qs_dev.data_ptr(), out_dev.data_ptr()))
+        L.fnft_b200_set_device_pointers(0)
+        q_host[:nb].copy_(qs_dev)
+        torch.cuda.synchronize()
+        dt_e2e, _ = timed_call(lambda: nsev_call(nb, q_host.data_ptr(), out_host.data_ptr()))
+        strong = {"workload": "BASELINE config 2 as written: one batch of %d signals split over %d GPU(s) "
+                              "(%d per GPU)" % (BATCH_PER_GPU, world, nb),
+                  "scaling": "strong", "value": BATCH_PER_GPU / dt_dev, "unit": "signals/s",
+                  "ms_per_batch": dt_dev * 1e3,
+                  "e2e": {"value": BATCH_PER_GPU / dt_e2e, "unit": "signals/s", "ms_per_batch": dt_e2e * 1e3}}
+        if "strong" in refs:
+            idx, outs = refs["strong"]
+            got = out_host[idx].numpy()
+            gate("config2_strong", [rel_err(got[i], outs[i]) for i in range(len(idx))])
+        del qs_dev
+
+        cfgs = {}
+        L.fnft_errwarn_setprintf(None)
+        # --- config 3: Newton bound states + norming constants and residues
+        if Q3 is not None:
+            n3, K3 = g3[1] - g3[0], C3["K"]
+            o3 = F.nsev_default_opts()
+            o3.bound_state_localization = F.BSLOC_NEWTON
+            o3.discspec_type = F.DSTYPE_BOTH
+            G3 = guess3[g3[0]:g3[1]]
+            dt, (ret, cs, Ka, bs, ncs, rcs) = timed_call(
+                lambda: F.nsev_batch(Q3, C3["T"], 0, None, 1, o3, K=np.full(n3, K3), Kmax=K3, bound_states=G3))
+            if ret != 0:
+                raise SystemExit("config 3: fnft_nsev_batch returned %d" % ret)
+            L.fnft_b200_profile_enable(1)
+            F.nsev_batch(Q3, C3["T"], 0, None, 1, o3, K=np.full(n3, K3), Kmax=K3, bound_states=G3)
+            rep3 = parse_report(L.fnft_b200_profile_report())
+            L.fnft_b200_profile_enable(0)
+            cfgs["3"] = {"workload": "fnft_nsev bound states + norming constants + residues (Newton, niter 10), "
+                                     "D=4096, 8-soliton signals, one batch of %d over %d GPU(s)" % (C3["B"], world),
+                         "value": C3["B"] / dt, "unit": "signals/s", "ms_per_batch": dt * 1e3,
+                         "found_all_rank0": float((Ka == K3).mean()),
+                         "kernel_ms_rank0": {k: round(ms, 4) for k, (n, ms) in sorted(rep3.items())},
+                         "cpu_baseline": cpu_base.get("c3")}
+            idx, res = refs.get("c3", ([], []))
+            gate("config3", [compare3(Ka[i], bs[i], ncs[i], res[j], K3) for j, i in enumerate(idx)])
+        # --- config 4: fnft_kdvv, 4SPLIT4B, pinned host buffers
+        n4 = g4[1] - g4[0]
+        U = config4_inputs(g4[0], g4[1])
+        Uh = torch.empty((n4, C4["D"]), dtype=torch.complex128, pin_memory=True)
+        Uh.copy_(torch.from_numpy(U))
+        csh = torch.empty((n4, C4["M"]), dtype=torch.complex128, pin_memory=True)
+        rch = np.zeros(n4, dtype=np.int32)
+        o4 = F.kdvv_default_opts()
+        o4.discretization = F.KDV_4SPLIT4B
+        T4, XI4 = np.array(C4["T"]), np.array(C4["XI"])
+
+        def run4():
+            r = L.fnft_kdvv_batch(n4, C4["D"], Uh.data_ptr(), T4.ctypes.data, C4["M"], csh.data_ptr(),
+                                  XI4.ctypes.data, C.addressof(o4), rch.ctypes.data)
+            if r != 0:
+                raise SystemExit("config 4: fnft_kdvv_batch returned %d" % r)
+        dt, _ = timed_call(run4)
+        cfgs["4"] = {"workload": "fnft_kdvv reflection coefficient, 4SPLIT4B, D=M=8192, one batch of %d over "
+                                 "%d GPU(s), pinned host buffers" % (C4["B"], world),
+                     "value": C4["B"] / dt, "unit": "signals/s", "ms_per_batch": dt * 1e3,
+                     "cpu_baseline": cpu_base.get("c4")}
+        idx, res = refs.get("c4", ([], []))
+        got = csh.numpy()
+        gate("config4", [rel_err(got[i], res[j][1]) for j, i in enumerate(idx)])
+        # --- config 5: fnft_nsep grid search
+        Q5 = config5_inputs(g5[0], g5[1])
+        o5 = F.nsep_default_opts()
+        o5.localization = 1
+        o5.filtering = 1
+        o5.bounding_box[0], o5.bounding_box[1], o5.bounding_box[2], o5.bounding_box[3] = -10, 10, -10, 10
+        o5.discretization = F.NSE_2SPLIT4B
+        Km5 = 4 * C5["D"]
+        dt, (ret, Ka5, main5, Ma5, aux5, rcs5) = timed_call(lambda: F.nsep_batch(Q5, C5["T"], Km5, Km5, 1, o5), reps=2)
+        if ret != 0:
+            raise SystemExit("config 5: fnft_nsep_batch returned %d" % ret)
+        cfgs["5"] = {"workload": "fnft_nsep main + auxiliary spectrum (grid search, manual box), 2SPLIT4B, D=4096, "
+                                 "one batch of %d over %d GPU(s)" % (C5["B"], world),
+                     "value": C5["B"] / dt, "unit": "signals/s", "ms_per_batch": dt * 1e3,
+                     "cpu_baseline": cpu_base.get("c5")}
+        idx, res = refs.get("c5", ([], []))
+        gate("config5", [compare5(Ka5[i], main5[i], Ma5[i], aux5[i], res[j]) for j, i in enumerate(idx)])
+
+    # ------------------------------------------------------------------ parity gate: all ranks
+    # config 5: both implementations locate the roots from chirp-z samples on three rings; where the
+    # samples are small against max|p| the reference's cpow-based chirp has an absolute error floor that
+    # moves ITS roots by ~1e-7 (tests/test_gpu_parity.py::test_nsep_config5_roots_against_long_double);
+    # the gate for this configuration is therefore 1e-6 on the positions and exact point counts.
+    bounds = {"config5": 1e-6}
+    names = ["config2_device", "config2_e2e", "config2_strong", "config3", "config4", "config5"]
+    parity, ok = None, True
+    if have_ref:
+        parity = {"metric": "misc_rel_err(ours, reference) per signal (bound states: relative error per "
+                            "eigenvalue), max over the checked signals of every rank",
+                  "reference": "oracle/_ref/libfnft_ref.so (unmodified FNFT 0.4.1)", "ranks_checked": world,
+                  "checks": {}}
+        for nm in names:
+            mx = max_over_ranks(parity_local.get(nm, 0.0) if math.isfinite(parity_local.get(nm, 0.0)) else 1e300)
+            cnt = int(sum_over_ranks(float(parity_count.get(nm, 0))))
+            if cnt == 0:
+                continue
+            bnd = bounds.get(nm, PARITY_BOUND)
+            parity["checks"][nm] = {"max": mx, "bound": bnd, "signals": cnt, "ok": bool(mx <= bnd)}
+            ok = ok and mx <= bnd
+        parity["max"] = max(c["max"] for k, c in parity["checks"].items() if k.startswith("config2"))
+        parity["bound"] = PARITY_BOUND
+        parity["signals"] = sum(c["signals"] for k, c in parity["checks"].items() if k.startswith("config2"))
+        parity["ok"] = bool(ok)
 
     if rank == 0:
         line = {"metric": "fnft_nsev signals/sec at D=M=16384", "value": value, "unit": "signals/s",
@@ -437,10 +876,13 @@ def main():
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "parity": parity}
+                "cpu_baseline": cpu_base.get("weak"), "parity": parity, "strong": strong, "configs": cfgs}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        log("PARITY GATE FAILED: %s" % json.dumps(parity))
+        return 1
     return 0
 
 

@@ -88,6 +88,7 @@ EXPORTED_SYMBOLS = [
     "fnft_b200_synchronize", "fnft_b200_set_workspace_limit", "fnft_b200_stream",
     "fnft_b200_launch_count", "fnft_b200_release",
     "fnft_b200_profile_enable", "fnft_b200_profile_report",
+    "fnft_b200_set_devices", "fnft_b200_get_devices", "fnft_b200_probe_fp64_tflops",
 ]
 
 _lib = None
@@ -155,6 +156,11 @@ def lib():
     L.fnft_b200_launch_count.restype = C.c_ulonglong
     L.fnft_b200_profile_enable.argtypes = [i32]
     L.fnft_b200_profile_report.restype = C.c_char_p
+    L.fnft_b200_set_devices.restype = i32
+    L.fnft_b200_set_devices.argtypes = [i32, vp]
+    L.fnft_b200_get_devices.restype = i32
+    L.fnft_b200_get_devices.argtypes = [vp, i32]
+    L.fnft_b200_probe_fp64_tflops.restype = dbl
     _lib = L
     return L
 
@@ -177,6 +183,12 @@ def device_count():
 
 def set_device(dev):
     return int(lib().fnft_b200_set_device(int(dev)))
+
+
+def set_devices(devs):
+    """Several GPUs behind one *_batch call (host buffers): shard i of the batch runs on devs[i]."""
+    a = np.ascontiguousarray(list(devs), dtype=np.int32)
+    return int(lib().fnft_b200_set_devices(len(a), _p(a) if len(a) else None))
 
 
 def launch_count():

@@ -126,7 +126,10 @@ struct BoundArgs {
     int *flag;         // [B][Kmax] status per eigenvalue (3 = division by zero)
     // norming-constant pass
     cplx *a_out, *ap_out, *b_out;  // [B][Kmax]
-    cplx *phi;         // scratch [(D_given+1)][B*Kmax][2]
+    cplx *phi;         // scratch, one slot per eigenvalue actually present (slot = koff[s] + i):
+                       // [(D_given+1)][ktot][2] (blk_normconsts) or [ktot][D_given+1][2] (k_normconsts_warp)
+    const int *koff;   // [B] exclusive prefix sum of K
+    int ktot;          // sum of K
 };
 
 // forward sweep: returns PHI(D) and dPHI/dl(D); optionally stores PHI at the given
@@ -250,8 +253,8 @@ BLK void blk_normconsts(const BoundArgs &a, blk3 bid, int nt, void *)
                 const cplx *q = a.q + (size_t)s * a.D;
                 const cplx lcur = a.lam[gid];
                 const int Dg = a.D / a.upsampling;
-                cplx *store = a.phi + (size_t)gid * 2;
-                const size_t stride = (size_t)tot * 2;
+                cplx *store = a.phi + (size_t)(a.koff[s] + i) * 2;
+                const size_t stride = (size_t)a.ktot * 2;
                 cplx phi[2], dphi[2], av, apv;
                 bound_forward(a, q, lcur, phi, dphi, store, stride);
                 bound_a_aprime(a, lcur, phi, dphi, &av, &apv);

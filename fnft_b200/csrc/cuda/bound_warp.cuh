@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) k_newton_warp(const BoundArgs a)
 }
 
 // a, a', b for given eigenvalues, one warp per (signal, eigenvalue).  Scratch a.phi holds
-// PHI at the given sample points of every eigenvalue: [gid][D_given + 1][2].
+// PHI at the given sample points of every eigenvalue: [koff[s] + i][D_given + 1][2].
 __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
 {
     const int lane = threadIdx.x & 31;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
     const cplx l = cscale(lcur, a.lweight);
     const double tb = a.T0 - a.eps_t * a.bc;
     const double te = a.T1 + a.eps_t * a.bc;
-    cplx *store = a.phi + (size_t)gid * (size_t)(Dg + 1) * 2;
+    cplx *store = a.phi + (size_t)(a.koff[s] + i) * (size_t)(Dg + 1) * 2;
 
     // ---- forward: chunk products, ordered scan for the start vectors ------------------
     {

@@ -17,7 +17,7 @@
 #include <string>
 #include <vector>
 
-unsigned long long g_fnftb_launch_count = 0;
+std::atomic<unsigned long long> g_fnftb_launch_count{0};
 int g_fnftb_profile_on = 0;
 
 // ---------------------------------------------------------------------------
@@ -28,8 +28,9 @@ struct ProfRec {
     const char *name;
     cudaEvent_t e0, e1;
 };
-static std::vector<ProfRec> g_prof;
-static std::vector<cudaEvent_t> g_prof_pool;
+// per host thread, like the contexts (events belong to the thread's device)
+static thread_local std::vector<ProfRec> g_prof;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event()
 {
     if (!g_prof_pool.empty()) {
@@ -61,7 +62,7 @@ struct TraceRec {
     int chunk;
     cudaEvent_t ev;
 };
-static std::vector<TraceRec> g_trace;
+static thread_local std::vector<TraceRec> g_trace;
 static int trace_on()
 {
     static int v = -1;
@@ -96,7 +97,7 @@ static void trace_dump()
         cudaEventDestroy(r.ev);
     g_trace.clear();
 }
-static int g_trace_chunk = 0;
+static thread_local int g_trace_chunk = 0;
 
 static int fail(int code, const char *what, const char *file, int line)
 {
@@ -146,7 +147,7 @@ struct fnftb_ctx {
     // chirp-z workspace
     Buf ybuf, vhat, outbuf, pbuf, cztab;
     // bound-state workspace
-    Buf box3, lam, kcnt, flag, aout, apout, bout, phi;
+    Buf box3, lam, kcnt, flag, aout, apout, bout, phi, koff;
     // nsep workspace
     Buf fpoly, vals, roots, nraw, nkept;
     // root-finder workspace
@@ -228,7 +229,7 @@ int fnftb_device_count(void)
 
 const char *fnftb_last_error(void) { return g_err.c_str(); }
 
-unsigned long long fnftb_launch_count(void) { return g_fnftb_launch_count; }
+unsigned long long fnftb_launch_count(void) { return g_fnftb_launch_count.load(); }
 
 void fnftb_profile_enable(int on) { g_fnftb_profile_on = on; }
 
@@ -236,7 +237,7 @@ void fnftb_profile_enable(int on) { g_fnftb_profile_on = on; }
 // "name count total_ms\n..." (buffer owned by the library) and clears the records.
 const char *fnftb_profile_report(void)
 {
-    static std::string rep;
+    static thread_local std::string rep;
     std::map<std::string, std::pair<long, double>> acc;
     cudaDeviceSynchronize();
     for (ProfRec &r : g_prof) {
@@ -259,6 +260,24 @@ const char *fnftb_profile_report(void)
     return rep.c_str();
 }
 
+void fnftb_ctx_destroy(fnftb_ctx *c);
+
+static int ctx_init(fnftb_ctx *c)
+{
+    CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    std::vector<double> tw(2 * (size_t)c->twn);
+    fnftb_fill_twiddles(tw.data(), (size_t)c->twn);
+    CU(cudaMalloc((void **)&c->tw, sizeof(cplx) * c->twn));
+    CU(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * c->twn, cudaMemcpyHostToDevice));
+    // pass-major twiddle tables of the spectrum-carry tree kernels (tw_tables.cuh)
+    TwSet tmp;
+    const size_t n = twset_layout(&tmp);
+    RC(ensure(c->twmem, n * sizeof(cplx)));
+    RC(twset_build(&c->tws, (cplx *)c->twmem.p, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
 int fnftb_ctx_create(fnftb_ctx **out, int device)
 {
     if (!out)
@@ -276,18 +295,10 @@ int fnftb_ctx_create(fnftb_ctx **out, int device)
     CU(cudaSetDevice(device));
     fnftb_ctx *c = new fnftb_ctx();
     c->device = device;
-    CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    std::vector<double> tw(2 * (size_t)c->twn);
-    fnftb_fill_twiddles(tw.data(), (size_t)c->twn);
-    CU(cudaMalloc((void **)&c->tw, sizeof(cplx) * c->twn));
-    CU(cudaMemcpy(c->tw, tw.data(), sizeof(cplx) * c->twn, cudaMemcpyHostToDevice));
-    {
-        // pass-major twiddle tables of the spectrum-carry tree kernels (tw_tables.cuh)
-        TwSet tmp;
-        const size_t n = twset_layout(&tmp);
-        RC(ensure(c->twmem, n * sizeof(cplx)));
-        RC(twset_build(&c->tws, (cplx *)c->twmem.p, c->st));
-        CU(cudaStreamSynchronize(c->st));
+    const int rc = ctx_init(c);
+    if (rc != 0) {  // nothing of a half-built context survives
+        fnftb_ctx_destroy(c);
+        return rc;
     }
     *out = c;
     return 0;
@@ -298,13 +309,15 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
     if (!c)
         return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st);
+    if (c->st)
+        cudaStreamSynchronize(c->st);
     Buf *all[] = {&c->qbuf, &c->rbuf, &c->lev0, &c->lev1, &c->mx0, &c->mx1, &c->gbuf, &c->colbuf, &c->W,
                   &c->status, &c->tm, &c->tt0, &c->tt1, &c->twmem, &c->ybuf, &c->vhat, &c->outbuf, &c->pbuf, &c->cztab,
                   &c->qpre, &c->warn, &c->box3, &c->lam, &c->kcnt, &c->flag, &c->aout, &c->apout, &c->bout, &c->phi,
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept,
                   &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info, &c->rt_lam, &c->rt_cnt, &c->rs_a, &c->rs_b, &c->qrot, &c->qsub,
-                  &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1]};
+                  &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1],
+                  &c->rprebuf, &c->koff};
     for (Buf *b : all)
         release(*b);
     if (c->st_h2d)
@@ -437,6 +450,12 @@ static size_t per_signal_bytes(size_t D, int deg0, size_t M, int npoly)
 size_t fnftb_max_chunk(const fnftb_ctx *c, size_t D, int deg0, size_t M, int npoly,
                        size_t budget_bytes)
 {
+    return fnftb_max_chunk_ex(c, D, deg0, M, npoly, 0, budget_bytes);
+}
+
+size_t fnftb_max_chunk_ex(const fnftb_ctx *c, size_t D, int deg0, size_t M, int npoly, size_t extra_per_signal,
+                          size_t budget_bytes)
+{
     if (budget_bytes == 0) {
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(c->device);
@@ -447,7 +466,7 @@ size_t fnftb_max_chunk(const fnftb_ctx *c, size_t D, int deg0, size_t M, int npo
         if (budget_bytes > cap)
             budget_bytes = cap;
     }
-    size_t n = budget_bytes / per_signal_bytes(D, deg0, M, npoly);
+    size_t n = budget_bytes / (per_signal_bytes(D, deg0, M, npoly) + extra_per_signal);
     return n < 1 ? 1 : n;
 }
 
@@ -1562,23 +1581,64 @@ int fnftb_normconsts(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_h
     RC(ensure(c->aout, n * sizeof(cplx)));
     RC(ensure(c->apout, n * sizeof(cplx)));
     RC(ensure(c->bout, n * sizeof(cplx)));
+    RC(ensure(c->koff, c->B * sizeof(int)));
     const size_t Dg = c->D / (size_t)d->upsampling;
-    RC(ensure(c->phi, (Dg + 1) * n * 2 * sizeof(cplx)));
     CU(cudaMemsetAsync(c->aout.p, 0, n * sizeof(cplx), c->st));
     CU(cudaMemsetAsync(c->apout.p, 0, n * sizeof(cplx), c->st));
     CU(cudaMemsetAsync(c->bout.p, 0, n * sizeof(cplx), c->st));
-    BoundArgs a = bound_args(c, d);
+    // The PHI scratch has one slot of (D_given + 1) vectors per eigenvalue that is actually present (not per
+    // Kmax: callers following the reference convention pass Kmax = fnft_nsev_max_K(D)).  Signals are
+    // processed in groups whose slots fit the scratch budget.
+    static const size_t phi_budget = (size_t)tree_knob("FNFT_B200_PHI_MB", 4096) << 20;
+    const size_t slot_bytes = (Dg + 1) * 2 * sizeof(cplx);
+    std::vector<int> koff(c->B);
     static const int knob_warp = tree_knob("FNFT_B200_BOUND_WARP", 1);
-    if (knob_warp) {
-        if (g_fnftb_profile_on)
-            fnftb_profile_begin("bound_normconsts_warp", c->st);
-        k_normconsts_warp<<<(unsigned)((n + 3) / 4), 128, 0, c->st>>>(a);
-        if (g_fnftb_profile_on)
-            fnftb_profile_end(c->st);
-        ++g_fnftb_launch_count;
-        CU(cudaGetLastError());
-    } else {
-        RC((launch_blocks<BoundArgs, blk_normconsts, 128>(a, (unsigned)((n + 63) / 64), 64, 0, c->st, "bound_normconsts")));
+    for (size_t b0 = 0; b0 < c->B;) {
+        size_t b1 = b0, ktot = 0;
+        while (b1 < c->B && (b1 == b0 || (ktot + (size_t)K_host[b1]) * slot_bytes <= phi_budget)) {
+            koff[b1] = (int)ktot;
+            ktot += (size_t)K_host[b1];
+            ++b1;
+        }
+        if (ktot > 0) {
+            if (ktot > (size_t)0x7fffffff)
+                return fail(-6, "too many eigenvalues in one signal group", __FILE__, __LINE__);
+            RC(ensure(c->phi, ktot * slot_bytes));
+            CU(cudaMemcpyAsync((int *)c->koff.p + b0, koff.data() + b0, (b1 - b0) * sizeof(int),
+                               cudaMemcpyHostToDevice, c->st));
+            BoundArgs a = bound_args(c, d);
+            const size_t e0 = b0 * (size_t)d->Kmax;
+            a.q += b0 * c->D;
+            if (a.r)
+                a.r += b0 * c->D;
+            a.B = (int)(b1 - b0);
+            a.K += b0;
+            a.lam += e0;
+            a.flag += e0;
+            a.a_out += e0;
+            a.ap_out += e0;
+            a.b_out += e0;
+            if (a.box3)
+                a.box3 += b0;
+            a.koff = (const int *)c->koff.p + b0;
+            a.ktot = (int)ktot;
+            const size_t ng = (size_t)a.B * (size_t)d->Kmax;
+            if (knob_warp) {
+                if (g_fnftb_profile_on)
+                    fnftb_profile_begin("bound_normconsts_warp", c->st);
+                k_normconsts_warp<<<(unsigned)((ng + 3) / 4), 128, 0, c->st>>>(a);
+                if (g_fnftb_profile_on)
+                    fnftb_profile_end(c->st);
+                ++g_fnftb_launch_count;
+                CU(cudaGetLastError());
+            } else {
+                RC((launch_blocks<BoundArgs, blk_normconsts, 128>(a, (unsigned)((ng + 63) / 64), 64, 0, c->st,
+                                                                  "bound_normconsts")));
+            }
+            // koff (host vector) is reused by the next group only after this copy has been consumed
+            CU(cudaStreamSynchronize(c->st));
+        }
+        b0 = b1;
     }
     if (a_host)
         CU(cudaMemcpyAsync(a_host, c->aout.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));

@@ -86,6 +86,10 @@ int fnftb_pipeline_status(fnftb_ctx *ctx, const int32_t **status);
  * workspace budget (bytes; 0 = default budget). */
 size_t fnftb_max_chunk(const fnftb_ctx *ctx, size_t D, int deg0, size_t M, int npoly,
                        size_t budget_bytes);
+/* same with additional workspace per signal that the caller knows about (bound-state arrays of Kmax
+ * entries: eigenvalues, flags, a, a', b -- 68 bytes per entry) */
+size_t fnftb_max_chunk_ex(const fnftb_ctx *ctx, size_t D, int deg0, size_t M, int npoly,
+                          size_t extra_per_signal, size_t budget_bytes);
 
 /* Stage B signals of D samples.  q (and r if rmode is EXPLICIT) are host pointers
  * (copied) or, if on_device != 0, device pointers that are used in place. */
@@ -225,6 +229,9 @@ int fnftb_newton(fnftb_ctx *ctx, const fnftb_bound_desc *desc, const int32_t *K_
 /* a, a', b at the given eigenvalues (each output [B][Kmax], may be NULL) */
 int fnftb_normconsts(fnftb_ctx *ctx, const fnftb_bound_desc *desc, const int32_t *K_host,
                      const void *lam_host, void *a_host, void *ap_host, void *b_host);
+
+/* DFMA throughput of the context's device in TFLOP/s (probe kernel, ~10 ms); 0 on failure */
+double fnftb_probe_fp64_tflops(fnftb_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fnftb_kernel(const Args a)
 }
 
 // number of kernel launches issued by this library (reported by bench.py)
-extern unsigned long long g_fnftb_launch_count;
+#include <atomic>
+extern std::atomic<unsigned long long> g_fnftb_launch_count;  // contexts are per host thread
 // optional per-launch timing with CUDA events (device_api.cu); name is a literal
 void fnftb_profile_begin(const char *name, cudaStream_t st);
 void fnftb_profile_end(cudaStream_t st);

@@ -38,6 +38,12 @@ FNFT_INT fnftb__device_error(const char *func, const FNFT_INT line);
 fnftb_ctx *fnftb__ctx(void);          /* NULL (after printing why) if no GPU */
 int fnftb__device_pointers(void);     /* flag set by fnft_b200_set_device_pointers */
 size_t fnftb__workspace_limit(void);
+/* several devices behind one batched call (fnft_runtime.c) */
+typedef void (*fnftb_shard_fn)(void *arg, int shard, int nshards);
+int fnftb__fanout_shards(FNFT_UINT B); /* 1 = run in the calling thread */
+int fnftb__fanout_run(int nshards, fnftb_shard_fn fn, void *arg);
+void fnftb__shard_range(FNFT_UINT B, int shard, int nshards, FNFT_UINT *b0, FNFT_UINT *b1);
+void fnftb__fanout_shutdown(void);
 int fnftb__pipe_chunks(void);
 FNFT_UINT fnftb__pipe_step(FNFT_UINT b0, FNFT_UINT B, FNFT_UINT chunk);
 

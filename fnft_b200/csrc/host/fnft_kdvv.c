@@ -20,12 +20,42 @@ static const fnft_kdvv_opts_t kdvv_defaults = {.discretization = fnft_kdv_discre
 
 fnft_kdvv_opts_t fnft_kdvv_default_opts(void) { return kdvv_defaults; }
 
+/* one shard of a batch that fnft_b200_set_devices spreads over several GPUs (fnft_runtime.c) */
+typedef struct {
+    FNFT_UINT B, D, M;
+    FNFT_COMPLEX const *u;
+    FNFT_REAL const *T, *XI;
+    FNFT_COMPLEX *contspec;
+    fnft_kdvv_opts_t const *opts;
+    FNFT_INT *ret_codes;
+    FNFT_INT rc[16];
+} kdvv_job;
+
+static void kdvv_shard(void *arg, int shard, int nshards)
+{
+    kdvv_job *j = (kdvv_job *)arg;
+    FNFT_UINT b0, b1;
+    fnftb__shard_range(j->B, shard, nshards, &b0, &b1);
+    j->rc[shard] = fnft_kdvv_batch(b1 - b0, j->D, j->u + b0 * j->D, j->T, j->M, j->contspec + b0 * j->M, j->XI,
+                                   j->opts, j->ret_codes ? j->ret_codes + b0 : NULL);
+}
+
 FNFT_INT fnft_kdvv_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const u,
                          FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
                          FNFT_REAL const *const XI, fnft_kdvv_opts_t const *opts,
                          FNFT_INT *const ret_codes)
 {
     FNFT_INT ret_code = FNFT_SUCCESS;
+    const int nshards = (u != NULL && contspec != NULL) ? fnftb__fanout_shards(B) : 1;
+    if (nshards > 1) { /* several GPUs: every shard is this same call on its own device */
+        kdvv_job j = {B, D, M, u, T, XI, contspec, opts, ret_codes, {0}};
+        if (fnftb__fanout_run(nshards, kdvv_shard, &j) != 0)
+            return E_OTHER("Could not start the per-device worker threads.");
+        for (int i = 0; i < nshards; i++)
+            if (j.rc[i] != FNFT_SUCCESS)
+                return E_SUBROUTINE(j.rc[i]);
+        return FNFT_SUCCESS;
+    }
     if (B == 0)
         return E_INVALID_ARGUMENT(B);
     if (D < 2)

@@ -505,6 +505,33 @@ leave_fun:
     return ret_code;
 }
 
+/* one shard of a batch that fnft_b200_set_devices spreads over several GPUs (fnft_runtime.c) */
+typedef struct {
+    FNFT_UINT B, D, Kmax, Mmax;
+    FNFT_COMPLEX const *q;
+    FNFT_REAL const *T;
+    FNFT_REAL phase_shift;
+    FNFT_UINT *K, *Mcount;
+    FNFT_COMPLEX *main_spec, *aux_spec;
+    FNFT_INT kappa;
+    fnft_nsep_opts_t const *opts;
+    FNFT_INT *ret_codes;
+    FNFT_INT rc[16];
+} nsep_job;
+
+static void nsep_shard(void *arg, int shard, int nshards)
+{
+    nsep_job *j = (nsep_job *)arg;
+    FNFT_UINT b0, b1;
+    fnftb__shard_range(j->B, shard, nshards, &b0, &b1);
+    j->rc[shard] = fnft_nsep_batch(b1 - b0, j->D, j->q + b0 * j->D, j->T, j->phase_shift,
+                                   j->K ? j->K + b0 : NULL, j->Kmax,
+                                   j->main_spec ? j->main_spec + b0 * j->Kmax : NULL,
+                                   j->Mcount ? j->Mcount + b0 : NULL, j->Mmax,
+                                   j->aux_spec ? j->aux_spec + b0 * j->Mmax : NULL, j->kappa, j->opts,
+                                   j->ret_codes ? j->ret_codes + b0 : NULL);
+}
+
 FNFT_INT fnft_nsep_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
                          FNFT_REAL const *const T, FNFT_REAL const phase_shift,
                          FNFT_UINT *const K, const FNFT_UINT Kmax, FNFT_COMPLEX *const main_spec,
@@ -512,6 +539,21 @@ FNFT_INT fnft_nsep_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
                          FNFT_COMPLEX *const aux_spec, const FNFT_INT kappa,
                          fnft_nsep_opts_t const *opts, FNFT_INT *const ret_codes)
 {
+    /* the periodic transform assembles variable-length point lists on the host: host buffers only */
+    if (fnftb__device_pointers())
+        return E_NOT_YET_IMPLEMENTED(device pointers, fnft_nsep_batch takes host buffers;
+                                     call fnft_b200_set_device_pointers(0) first.);
+    const int nshards = (q != NULL) ? fnftb__fanout_shards(B) : 1;
+    if (nshards > 1) { /* several GPUs: every shard is this same call on its own device */
+        nsep_job j = {B, D, Kmax, Mmax, q, T, phase_shift, K, Mcount, main_spec, aux_spec, kappa, opts, ret_codes,
+                      {0}};
+        if (fnftb__fanout_run(nshards, nsep_shard, &j) != 0)
+            return E_OTHER("Could not start the per-device worker threads.");
+        for (int i = 0; i < nshards; i++)
+            if (j.rc[i] != FNFT_SUCCESS)
+                return E_SUBROUTINE(j.rc[i]);
+        return FNFT_SUCCESS;
+    }
     if (ret_codes != NULL)
         for (FNFT_UINT b = 0; b < B; b++)
             ret_codes[b] = FNFT_SUCCESS;

@@ -216,8 +216,10 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     const FNFT_UINT D_eff = D_given * upsampling;
     const FNFT_UINT cs_len = want_contspec ? contspec_len(opts->contspec_type, M) : 0;
 
-    size_t chunk = fnftb_max_chunk(ctx, D_eff, slow ? 1 : (int)deg0, (want_contspec && !slow) ? M : 0, 2,
-                                   fnftb__workspace_limit());
+    /* the bound-state kernels keep eigenvalue, flag, a, a' and b per entry of the [nb][Kmax] arrays */
+    size_t chunk = fnftb_max_chunk_ex(ctx, D_eff, slow ? 1 : (int)deg0, (want_contspec && !slow) ? M : 0, 2,
+                                      want_discspec ? Kmax * (4 * sizeof(FNFT_COMPLEX) + sizeof(int32_t)) : 0,
+                                      fnftb__workspace_limit());
     if (chunk > B)
         chunk = B;
     /* Continuous spectrum only, host buffers: overlap the host<->device copies of
@@ -250,7 +252,9 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     sd.deg0 = (int)deg0;
     sd.normalize = opts->normalization_flag ? 1 : 0;
     sd.eps_t = eps_t;
-    sd.defer_final = 1; /* only fnftb_contspec consumes the scattering result here */
+    /* fnftb_contspec may read (a, b) straight from the level buffer and skip the final tree kernel.
+     * FAST_EIGENVALUE reuses the transfer matrix of the chunk for the root finder, so it must exist. */
+    sd.defer_final = !(want_discspec && opts->bound_state_localization == fnft_nsev_bsloc_FAST_EIGENVALUE);
 
     if (piped && fnftb_pipeline_begin(ctx, B) != 0) {
         ret_code = E_DEVICE;
@@ -406,6 +410,34 @@ leave_fun:
     return ret_code;
 }
 
+/* one shard of a batch that fnft_b200_set_devices spreads over several GPUs (fnft_runtime.c) */
+typedef struct {
+    FNFT_UINT B, D, M, Kmax;
+    FNFT_COMPLEX const *q;
+    FNFT_REAL const *T, *XI;
+    FNFT_COMPLEX *contspec, *bound_states, *normconsts_or_residues;
+    FNFT_UINT *K;
+    FNFT_INT kappa;
+    fnft_nsev_opts_t const *opts;
+    FNFT_INT *ret_codes;
+    FNFT_INT rc[16];
+} nsev_job;
+
+static void nsev_shard(void *arg, int shard, int nshards)
+{
+    nsev_job *j = (nsev_job *)arg;
+    FNFT_UINT b0, b1;
+    fnftb__shard_range(j->B, shard, nshards, &b0, &b1);
+    const FNFT_UINT cs_len = (j->contspec != NULL) ? contspec_len(j->opts->contspec_type, j->M) : 0;
+    const FNFT_UINT nlen = (j->opts->discspec_type == fnft_nsev_dstype_BOTH) ? 2 * j->Kmax : j->Kmax;
+    j->rc[shard] = fnft_nsev_batch(b1 - b0, j->D, j->q + b0 * j->D, j->T, j->M,
+                                   j->contspec ? j->contspec + b0 * cs_len : NULL, j->XI,
+                                   j->K ? j->K + b0 : NULL, j->Kmax,
+                                   j->bound_states ? j->bound_states + b0 * j->Kmax : NULL,
+                                   j->normconsts_or_residues ? j->normconsts_or_residues + b0 * nlen : NULL,
+                                   j->kappa, j->opts, j->ret_codes ? j->ret_codes + b0 : NULL);
+}
+
 FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
                          FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
                          FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
@@ -415,6 +447,17 @@ FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
 {
     if (opts == NULL)
         opts = &nsev_defaults;
+    const int nshards = (q != NULL) ? fnftb__fanout_shards(B) : 1;
+    if (nshards > 1) { /* several GPUs: every shard is this same call on its own device */
+        nsev_job j = {B, D, M, Kmax, q, T, XI, contspec, bound_states, normconsts_or_residues, K, kappa, opts,
+                      ret_codes, {0}};
+        if (fnftb__fanout_run(nshards, nsev_shard, &j) != 0)
+            return E_OTHER("Could not start the per-device worker threads.");
+        for (int i = 0; i < nshards; i++)
+            if (j.rc[i] != FNFT_SUCCESS)
+                return E_SUBROUTINE(j.rc[i]);
+        return FNFT_SUCCESS;
+    }
     if (opts->richardson_extrapolation_flag != 1)
         return nsev_pass(B, D, q, T, M, contspec, XI, K, Kmax, bound_states, normconsts_or_residues, kappa,
                          opts, ret_codes, 0, NULL);

@@ -6,11 +6,28 @@
 #include "fnft_internal.h"
 #include <stdlib.h>
 #include <stdio.h>
+#include <pthread.h>
 
 static __thread fnftb_ctx *tl_ctx = NULL;
 static __thread int tl_device = -1; /* -1: take FNFT_B200_DEVICE or 0 on first use */
 static __thread int tl_devptr = 0;
 static __thread size_t tl_limit = 0;
+
+/* A thread that exits without calling fnft_b200_release() must not leak its context (device
+ * workspaces, streams): a pthread key whose destructor releases it. */
+static pthread_key_t ctx_key;
+static pthread_once_t ctx_key_once = PTHREAD_ONCE_INIT;
+static void ctx_key_dtor(void *p)
+{
+    if (p != NULL)
+        fnftb_ctx_destroy((fnftb_ctx *)p);
+}
+static void ctx_key_make(void) { (void)pthread_key_create(&ctx_key, ctx_key_dtor); }
+static void ctx_key_set(fnftb_ctx *c)
+{
+    (void)pthread_once(&ctx_key_once, ctx_key_make);
+    (void)pthread_setspecific(ctx_key, c);
+}
 
 fnftb_ctx *fnftb__ctx(void)
 {
@@ -32,6 +49,7 @@ fnftb_ctx *fnftb__ctx(void)
         return NULL;
     }
     tl_device = dev;
+    ctx_key_set(tl_ctx);
     return tl_ctx;
 }
 
@@ -89,6 +107,7 @@ FNFT_INT fnft_b200_set_device(FNFT_INT device)
     if (tl_ctx != NULL && fnftb_ctx_device(tl_ctx) != device) {
         fnftb_ctx_destroy(tl_ctx);
         tl_ctx = NULL;
+        ctx_key_set(NULL);
     }
     tl_device = device;
     return FNFT_SUCCESS;
@@ -129,9 +148,220 @@ const char *fnft_b200_profile_report(void) { return fnftb_profile_report(); }
 
 void fnft_b200_release(void)
 {
+    fnftb__fanout_shutdown();
     if (tl_ctx != NULL)
         fnftb_ctx_destroy(tl_ctx);
     tl_ctx = NULL;
+    ctx_key_set(NULL);
+}
+
+double fnft_b200_probe_fp64_tflops(void)
+{
+    fnftb_ctx *c = fnftb__ctx();
+    return c ? fnftb_probe_fp64_tflops(c) : 0.0;
+}
+
+/*
+ * ---- several GPUs behind ONE batched call -------------------------------
+ * fnft_b200_set_devices(n, ids) (or the environment variable FNFT_B200_DEVICES = "all" | "0,1,..")
+ * gives the calling thread a set of devices.  A *_batch call with host buffers then splits its batch
+ * into n contiguous shards; shard i runs on device ids[i] in a persistent worker thread that owns
+ * that device's context (so workspaces, pinned status arrays and streams survive between calls) and
+ * writes straight into the caller's [B][...] arrays.  Signals are independent: there is no
+ * exchange between the devices and no collective.
+ */
+#define FNFTB_MAX_DEV 16
+typedef struct {
+    pthread_t th;
+    int device, index, started;
+    struct fnftb_pool *pool;
+} fnftb_worker;
+typedef struct fnftb_pool {
+    int n;
+    fnftb_worker w[FNFTB_MAX_DEV];
+    pthread_mutex_t mu;
+    pthread_cond_t cv_job, cv_done;
+    unsigned long generation; /* incremented per job */
+    int pending, quit, nshards;
+    fnftb_shard_fn fn;
+    void *arg;
+    fnft_printf_ptr_t printf_ptr;
+    size_t limit;
+} fnftb_pool;
+
+static __thread int tl_ndev = -1; /* -1: FNFT_B200_DEVICES not looked at yet */
+static __thread int tl_devs[FNFTB_MAX_DEV];
+static __thread fnftb_pool *tl_pool = NULL;
+static __thread int tl_in_worker = 0;
+
+static void *worker_main(void *p)
+{
+    fnftb_worker *w = (fnftb_worker *)p;
+    fnftb_pool *pool = w->pool;
+    tl_in_worker = 1;
+    tl_ndev = 0;
+    tl_device = w->device;
+    unsigned long seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&pool->mu);
+        while (!pool->quit && pool->generation == seen)
+            pthread_cond_wait(&pool->cv_job, &pool->mu);
+        if (pool->quit) {
+            pthread_mutex_unlock(&pool->mu);
+            break;
+        }
+        seen = pool->generation;
+        const fnftb_shard_fn fn = pool->fn;
+        void *arg = pool->arg;
+        const int nshards = pool->nshards;
+        fnft_errwarn_setprintf(pool->printf_ptr); /* messages go where the caller's go */
+        tl_limit = pool->limit;
+        pthread_mutex_unlock(&pool->mu);
+        if (w->index < nshards)
+            fn(arg, w->index, nshards);
+        pthread_mutex_lock(&pool->mu);
+        if (--pool->pending == 0)
+            pthread_cond_signal(&pool->cv_done);
+        pthread_mutex_unlock(&pool->mu);
+    }
+    if (tl_ctx != NULL) {
+        fnftb_ctx_destroy(tl_ctx);
+        tl_ctx = NULL;
+        ctx_key_set(NULL);
+    }
+    return NULL;
+}
+
+void fnftb__fanout_shutdown(void)
+{
+    fnftb_pool *pool = tl_pool;
+    if (pool == NULL)
+        return;
+    pthread_mutex_lock(&pool->mu);
+    pool->quit = 1;
+    pthread_cond_broadcast(&pool->cv_job);
+    pthread_mutex_unlock(&pool->mu);
+    for (int i = 0; i < pool->n; i++)
+        if (pool->w[i].started)
+            pthread_join(pool->w[i].th, NULL);
+    pthread_mutex_destroy(&pool->mu);
+    pthread_cond_destroy(&pool->cv_job);
+    pthread_cond_destroy(&pool->cv_done);
+    free(pool);
+    tl_pool = NULL;
+}
+
+static void devices_from_env(void)
+{
+    tl_ndev = 0;
+    const char *e = getenv("FNFT_B200_DEVICES");
+    if (e == NULL || e[0] == '\0')
+        return;
+    const int have = fnftb_device_count();
+    if (strcmp(e, "all") == 0) {
+        for (int i = 0; i < have && i < FNFTB_MAX_DEV; i++)
+            tl_devs[tl_ndev++] = i;
+        return;
+    }
+    const char *p = e;
+    while (*p != '\0' && tl_ndev < FNFTB_MAX_DEV) {
+        char *end = NULL;
+        const long v = strtol(p, &end, 10);
+        if (end == p)
+            break;
+        if (v >= 0 && v < have)
+            tl_devs[tl_ndev++] = (int)v;
+        p = (*end == ',') ? end + 1 : end;
+    }
+}
+
+FNFT_INT fnft_b200_set_devices(FNFT_INT n, FNFT_INT const *devices)
+{
+    if (n < 0 || n > FNFTB_MAX_DEV)
+        return E_INVALID_ARGUMENT(n);
+    if (n > 0 && devices == NULL)
+        return E_INVALID_ARGUMENT(devices);
+    const int have = fnftb_device_count();
+    for (FNFT_INT i = 0; i < n; i++) /* an id may repeat: two contexts on one GPU overlap each other's copies */
+        if (devices[i] < 0 || devices[i] >= have)
+            return E_INVALID_ARGUMENT(devices);
+    fnftb__fanout_shutdown(); /* the workers of the previous set go away with their contexts */
+    tl_ndev = (int)n;
+    for (FNFT_INT i = 0; i < n; i++)
+        tl_devs[i] = (int)devices[i];
+    return FNFT_SUCCESS;
+}
+
+FNFT_INT fnft_b200_get_devices(FNFT_INT *devices, FNFT_INT capacity)
+{
+    if (tl_ndev < 0)
+        devices_from_env();
+    for (int i = 0; i < tl_ndev && i < capacity && devices != NULL; i++)
+        devices[i] = tl_devs[i];
+    return (FNFT_INT)tl_ndev;
+}
+
+/* Number of shards a batch of B signals given with host buffers is split into (1: no fan-out). */
+int fnftb__fanout_shards(FNFT_UINT B)
+{
+    if (tl_in_worker || tl_devptr)
+        return 1;
+    if (tl_ndev < 0)
+        devices_from_env();
+    if (tl_ndev < 2 || B < 2)
+        return 1;
+    return (B < (FNFT_UINT)tl_ndev) ? (int)B : tl_ndev;
+}
+
+void fnftb__shard_range(FNFT_UINT B, int shard, int nshards, FNFT_UINT *b0, FNFT_UINT *b1)
+{
+    const FNFT_UINT base = B / (FNFT_UINT)nshards, extra = B % (FNFT_UINT)nshards;
+    const FNFT_UINT s = (FNFT_UINT)shard;
+    *b0 = s * base + (s < extra ? s : extra);
+    *b1 = *b0 + base + (s < extra ? 1 : 0);
+}
+
+/* Runs fn(arg, i, nshards) for i < nshards, shard i on the worker of device tl_devs[i]; returns when
+ * all have finished.  0 on success. */
+int fnftb__fanout_run(int nshards, fnftb_shard_fn fn, void *arg)
+{
+    if (nshards < 1 || nshards > tl_ndev)
+        return -1;
+    fnftb_pool *pool = tl_pool;
+    if (pool == NULL) {
+        pool = calloc(1, sizeof(*pool));
+        if (pool == NULL)
+            return -1;
+        pthread_mutex_init(&pool->mu, NULL);
+        pthread_cond_init(&pool->cv_job, NULL);
+        pthread_cond_init(&pool->cv_done, NULL);
+        pool->n = tl_ndev;
+        tl_pool = pool;
+        for (int i = 0; i < pool->n; i++) {
+            pool->w[i].device = tl_devs[i];
+            pool->w[i].index = i;
+            pool->w[i].pool = pool;
+            if (pthread_create(&pool->w[i].th, NULL, worker_main, &pool->w[i]) != 0) {
+                fnftb__fanout_shutdown();
+                return -1;
+            }
+            pool->w[i].started = 1;
+        }
+    }
+    /* every worker wakes up for every job; those with index >= nshards have nothing to do */
+    pthread_mutex_lock(&pool->mu);
+    pool->fn = fn;
+    pool->arg = arg;
+    pool->nshards = nshards;
+    pool->printf_ptr = fnft_errwarn_getprintf();
+    pool->limit = tl_limit;
+    pool->pending = pool->n;
+    pool->generation++;
+    pthread_cond_broadcast(&pool->cv_job);
+    while (pool->pending > 0)
+        pthread_cond_wait(&pool->cv_done, &pool->mu);
+    pthread_mutex_unlock(&pool->mu);
+    return 0;
 }
 
 /*

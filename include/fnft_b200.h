@@ -363,6 +363,15 @@ FNFT_INT fnft_b200_device_count(void);
 /* Select the device used by the calling thread's subsequent calls (default 0, or
  * the value of the environment variable FNFT_B200_DEVICE). */
 FNFT_INT fnft_b200_set_device(FNFT_INT device);
+/* Several GPUs behind ONE batched call: give the calling thread a set of n
+ * devices (n = 0 or 1 switches the fan-out off; an id may repeat = several contexts on one GPU).  A subsequent fnft_nsev_batch /
+ * fnft_kdvv_batch / fnft_nsep_batch with HOST buffers splits its batch into n contiguous shards,
+ * runs shard i on devices[i] (persistent worker threads, one context per device) and lands all
+ * results in the caller's [B][...] arrays; signals are independent, so nothing is exchanged between
+ * the devices.  The environment variable FNFT_B200_DEVICES ("all" or "0,1,2,3") sets the default.
+ * fnft_b200_get_devices returns the number of devices in the set (and copies up to `capacity` ids). */
+FNFT_INT fnft_b200_set_devices(FNFT_INT n, FNFT_INT const *devices);
+FNFT_INT fnft_b200_get_devices(FNFT_INT *devices, FNFT_INT capacity);
 /* Declare that q / contspec pointers passed to the *_batch functions by this thread
  * are DEVICE pointers on the selected device (1) or host pointers (0, default).
  * With device pointers the calls are asynchronous; use fnft_b200_synchronize. */
@@ -379,8 +388,10 @@ unsigned long long fnft_b200_launch_count(void);
  * kernel; reading clears the records. */
 void fnft_b200_profile_enable(FNFT_INT on);
 const char *fnft_b200_profile_report(void);
-/* Releases the calling thread's GPU context. */
+/* Releases the calling thread's GPU context (and the workers of fnft_b200_set_devices). */
 void fnft_b200_release(void);
+/* Measured DFMA throughput (TFLOP/s) of the calling thread's device: the FP64 roofline denominator. */
+double fnft_b200_probe_fp64_tflops(void);
 
 #ifdef __cplusplus
 }
