@@ -40,6 +40,19 @@ struct Cz2Args {
 };
 
 // grid.x * 256 threads = narr * 4096 ; narr = B*npoly (or 1 for gen_v)
+static inline bool cz2_supported(int deg, int M)
+{
+    size_t need = (size_t)deg + (size_t)M, L = 1;
+    int l2 = 0;
+    while (L < need) {
+        L *= 2;
+        ++l2;
+    }
+    return l2 >= FNFTB_CZ2_ROW_L2 + 1 && l2 <= FNFTB_CZ2_ROW_L2 + 4 && l2 <= FNFTB_TW_MAXL;
+}
+
+// kernels instantiated in k_chirpz2.cu only
+#ifdef FNFTB_TU_CZ2
 template <int R>
 __global__ void __launch_bounds__(256, 3) k_cz2_cols_fwd(const Cz2Args a)
 {
@@ -377,20 +390,8 @@ static inline int cz2_launch(K kernel, const Cz2Args &a, unsigned grid, int nt, 
     return (int)cudaGetLastError();
 }
 
-static inline bool cz2_supported(int deg, int M)
-{
-    size_t need = (size_t)deg + (size_t)M, L = 1;
-    int l2 = 0;
-    while (L < need) {
-        L *= 2;
-        ++l2;
-    }
-    return l2 >= FNFTB_CZ2_ROW_L2 + 1 && l2 <= FNFTB_CZ2_ROW_L2 + 4 && l2 <= FNFTB_TW_MAXL;
-}
-
 // Same contract as cz_run (chirpz_driver.cuh); a.vhat doubles as the permuted FFT(v).
-static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st,
-                          const Cz2SymSrc *src = nullptr)
+int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2SymSrc *src)
 {
     size_t need = (size_t)c.deg + (size_t)c.M, L = 1;
     int l2L = 0;
@@ -492,7 +493,7 @@ static inline int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t 
 // first-generation blk_cz_rows (register-fused stride-1 passes, derived twiddles).  Nothing else
 // changes: the row kernel is self-contained as long as the filter spectrum comes from the same
 // kernel (gen_v), which stores it in its own permuted order.
-static inline int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
+int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
 {
     const CzGeom g = cz_geometry(a.deg, a.M);
     if (g.N2 != (1 << FNFTB_CZ2_ROW_L2))
@@ -559,4 +560,8 @@ static inline int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaS
     return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / g.C)), nt,
                                                           cz_cols_smem_bytes(g.C, g.N1, a.npoly), st, "cz_cols_inv");
 }
+#else
+int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2SymSrc *src = nullptr);
+int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st);
+#endif
 #endif  // !FNFTB_EMUL

@@ -41,6 +41,8 @@ static inline size_t cz_table_elems(const CzGeom &g, int deg, int M)
 // elements needed in ybuf for B signals / in vhat
 static inline size_t cz_ybuf_elems(const CzGeom &g, size_t B, int npoly) { return B * npoly * (size_t)g.L; }
 
+// (instantiated in k_chirpz2.cu and in the host emulation only)
+#if defined(FNFTB_TU_CZ2) || defined(FNFTB_EMUL)
 // Fills geometry/plans in `a` (a.deg, a.M, a.B, a.npoly must be set) and runs the
 // whole evaluation: vhat, forward columns, rows, inverse columns + epilogue.
 // `tables` must provide cz_table_elems() elements of device scratch.
@@ -102,3 +104,4 @@ static inline int cz_run(CzArgs a, cplx *tables, fnftb_stream_t st, int row_n = 
     return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / g.C)), nt,
                                                   cz_cols_smem_bytes(g.C, g.N1, a.npoly), st, "cz_cols_inv");
 }
+#endif

@@ -477,7 +477,7 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
                 lo.scheme = scheme;
                 lo.normalize = normalize;
                 lo.eps_t = eps_t;
-                rc = (deg0 == 2) ? low2g_launch_t<8, 2>(lo, st) : low2g_launch_t<8, 1>(lo, st);
+                rc = low2g_launch(lo, deg0, st);
                 if (rc)
                     return rc;
                 int cur = 0;

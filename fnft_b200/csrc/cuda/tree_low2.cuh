@@ -765,6 +765,8 @@ static inline size_t low2_smem_bytes(int log2m)
 // samples per CTA for (log2m, deg0)
 static inline int low2_samples(int log2m, int deg0) { return (1 << log2m) * (8 / deg0); }
 
+// The kernels are instantiated in ONE translation unit (k_tree_low2.cu); every other one sees the prototype.
+#ifdef FNFTB_TU_LOW2
 template <int LOG2M, int DEG0>
 static inline int low2_launch_t(const Low2Args &a, cudaStream_t st)
 {
@@ -783,10 +785,13 @@ static inline int low2_launch_t(const Low2Args &a, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-static inline int low2_launch(const Low2Args &a, int log2m, int deg0, cudaStream_t st)
+int low2_launch(const Low2Args &a, int log2m, int deg0, cudaStream_t st)
 {
     if (log2m == 6)
         return deg0 == 2 ? low2_launch_t<6, 2>(a, st) : low2_launch_t<6, 1>(a, st);
     return deg0 == 2 ? low2_launch_t<7, 2>(a, st) : low2_launch_t<7, 1>(a, st);
 }
+#else
+int low2_launch(const Low2Args &a, int log2m, int deg0, cudaStream_t st);
+#endif
 #endif  // !FNFTB_EMUL

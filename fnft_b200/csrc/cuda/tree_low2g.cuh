@@ -554,6 +554,7 @@ static inline size_t low2g_smem_bytes(int log2m)
 }
 static inline int low2g_samples(int log2m, int deg0) { return (1 << log2m) * (4 / deg0); }
 
+#ifdef FNFTB_TU_LOW2
 template <int LOG2M, int DEG0>
 static inline int low2g_launch_t(const Low2gArgs &a, cudaStream_t st)
 {
@@ -571,4 +572,12 @@ static inline int low2g_launch_t(const Low2gArgs &a, cudaStream_t st)
     ++g_fnftb_launch_count;
     return (int)cudaGetLastError();
 }
+// the one shape the driver uses: 256 threads per CTA
+int low2g_launch(const Low2gArgs &a, int deg0, cudaStream_t st)
+{
+    return (deg0 == 2) ? low2g_launch_t<8, 2>(a, st) : low2g_launch_t<8, 1>(a, st);
+}
+#else
+int low2g_launch(const Low2gArgs &a, int deg0, cudaStream_t st);
+#endif
 #endif  // !FNFTB_EMUL

@@ -500,6 +500,19 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_c(const UpArgs a)
 // host side
 // ---------------------------------------------------------------------------------------
 
+// can this level (operand length 1 << l2n) run on the spectrum path?
+static inline bool up_supported(int l2n, int l2smem_max)
+{
+    if (l2n < 11 || l2n > FNFTB_TW_MAXL)
+        return false;
+    if (l2n <= l2smem_max)
+        return true;
+    const int l2R = l2n - FNFTB_UP_ROW_L2;
+    return l2R >= 1 && l2R <= 6;  // radix 32 / 64 across the rows for operand lengths 2^17 / 2^18
+}
+
+// kernels instantiated in k_tree_up.cu only
+#ifdef FNFTB_TU_UP
 template <class K>
 static inline int up_launch(K kernel, const UpArgs &a, unsigned grid, int nt, size_t smem, cudaStream_t st,
                             const char *name)
@@ -516,17 +529,6 @@ static inline int up_launch(K kernel, const UpArgs &a, unsigned grid, int nt, si
         fnftb_profile_end(st);
     ++g_fnftb_launch_count;
     return (int)cudaGetLastError();
-}
-
-// can this level (operand length 1 << l2n) run on the spectrum path?
-static inline bool up_supported(int l2n, int l2smem_max)
-{
-    if (l2n < 11 || l2n > FNFTB_TW_MAXL)
-        return false;
-    if (l2n <= l2smem_max)
-        return true;
-    const int l2R = l2n - FNFTB_UP_ROW_L2;
-    return l2R >= 1 && l2R <= 6;  // radix 32 / 64 across the rows for operand lengths 2^17 / 2^18
 }
 
 template <bool SYM>
@@ -571,8 +573,11 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
     return up_launch(k_up_rows_c<128, SYM>, a, grid_rows, 128, smem, st, "tree_up_rows_c");
 }
 
-static inline int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym = true)
+int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym)
 {
     return sym ? up_level_t<true>(a, l2smem_max, st) : up_level_t<false>(a, l2smem_max, st);
 }
+#else
+int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym = true);
+#endif
 #endif  // !FNFTB_EMUL

@@ -21,7 +21,7 @@ struct TwSet {
     int pass_off[FNFTB_TW_MAXL + 1][7];  // [log2 len][log2 R] -> [q-1][o], o < len/R (radix 64: longest length only)
 };
 
-__global__ void k_tw_fill_pass(cplx *dst, int l2len, int l2r)
+static __global__ void k_tw_fill_pass(cplx *dst, int l2len, int l2r)
 {
     const int len = 1 << l2len, s = len >> l2r;
     const int total = ((1 << l2r) - 1) * s;
@@ -34,7 +34,7 @@ __global__ void k_tw_fill_pass(cplx *dst, int l2len, int l2r)
     }
 }
 
-__global__ void k_tw_fill_twist(cplx *dst, int l2n)
+static __global__ void k_tw_fill_twist(cplx *dst, int l2n)
 {
     const int N = 1 << l2n;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
