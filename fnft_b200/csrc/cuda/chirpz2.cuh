@@ -1,5 +1,7 @@
 // fnft_b200 -- fast path of the batched chirp-z evaluation (fnft__poly_chirpz.c:33-105)
-// for Bluestein lengths L = R * 4096, R in {2, 4, 8, 16}: same algorithm and tables as
+// for Bluestein lengths L = R * 4096, R in {2, 3, 4, 6, 8, 12, 16} (the smallest that holds deg + M: BASELINE
+// config 2 runs L = 12 * 4096 = 49152 like the reference's next_fast_size, fnft__poly_chirpz.c:52-56, instead
+// of the next power of two 65536): same algorithm and tables as
 // chirpz_kernels.cuh, but the two length-L transforms are organised like the tree kernels
 // (tree_up.cuh): bit-reversed DIF forward / DIT inverse, pass-major twiddle tables, and
 //
@@ -35,35 +37,157 @@ struct Cz2Args {
     Cz2SymSrc src;
     TwSet tw;
     cplx *vperm;  // [L] permuted FFT(v)
-    int l2L;
+    int l2L;      // log2 L when L is a power of two (pass-major twiddle table of the column pass)
+    int R, L;     // rows, L = R * 4096
     int gen_v;    // cols_fwd: generate the chirp filter; rows: forward half only -> vperm
 };
+
+// number of rows of 4096 for a Bluestein length >= need (0: not on the fast path)
+static inline int cz2_rows_for(size_t need)
+{
+    static const int cand[7] = {2, 3, 4, 6, 8, 12, 16};
+    if (need <= ((size_t)1 << FNFTB_CZ2_ROW_L2))
+        return 0;  // short transforms take the general path
+    for (int i = 0; i < 7; ++i)
+        if (((size_t)cand[i] << FNFTB_CZ2_ROW_L2) >= need)
+            return cand[i];
+    return 0;
+}
 
 // grid.x * 256 threads = narr * 4096 ; narr = B*npoly (or 1 for gen_v)
 static inline bool cz2_supported(int deg, int M)
 {
-    size_t need = (size_t)deg + (size_t)M, L = 1;
-    int l2 = 0;
-    while (L < need) {
-        L *= 2;
-        ++l2;
-    }
-    return l2 >= FNFTB_CZ2_ROW_L2 + 1 && l2 <= FNFTB_CZ2_ROW_L2 + 4 && l2 <= FNFTB_TW_MAXL;
+    return cz2_rows_for((size_t)deg + (size_t)M) != 0 && FNFTB_CZ2_ROW_L2 + 4 <= FNFTB_TW_MAXL;
 }
 
 // kernels instantiated in k_chirpz2.cu only
 #ifdef FNFTB_TU_CZ2
+// ---- column transforms of length R = 3 * P (P = 1, 2, 4) next to the power-of-two Dft<R> ---------
+template <int R>
+struct Cz2Radix {
+    static constexpr bool pow2 = (R & (R - 1)) == 0;
+    static constexpr int LR = Log2R<R>::value;
+    // row that holds element q of the column transform's digit-permuted side
+    DEV static constexpr int row(int q) { return pow2 ? brev_c(q, LR) : q; }
+};
+
+// v *= exp(DIR * 2 pi i K / 12)
+template <int K, int DIR>
+DEV cplx mul_root12(cplx v)
+{
+    constexpr int k = ((K % 12) + 12) % 12;
+    constexpr double h = 0.5, c30 = 0.8660254037844386;
+    constexpr double cs[12] = {1.0, c30, h, 0.0, -h, -c30, -1.0, -c30, -h, 0.0, h, c30};
+    constexpr double sn[12] = {0.0, h, c30, 1.0, c30, h, 0.0, -h, -c30, -1.0, -c30, -h};
+    if constexpr (k == 0) {
+        return v;
+    } else if constexpr (k == 6) {
+        return cneg(v);
+    } else if constexpr (k == 3) {
+        return (DIR > 0) ? cmuli(v) : cmulmi(v);
+    } else if constexpr (k == 9) {
+        return (DIR > 0) ? cmulmi(v) : cmuli(v);
+    } else {
+        constexpr double c = cs[k];
+        constexpr double s = (DIR > 0) ? sn[k] : -sn[k];
+        return make_cplx(v.x * c - v.y * s, v.x * s + v.y * c);
+    }
+}
+
+template <int DIR>
+DEV void dft3(cplx &a, cplx &b, cplx &c)
+{
+    constexpr double s60 = (DIR > 0) ? 0.8660254037844386 : -0.8660254037844386;
+    const cplx t1 = cadd(b, c);
+    const cplx t2 = make_cplx(a.x - 0.5 * t1.x, a.y - 0.5 * t1.y);
+    const cplx d = csub(b, c);
+    const cplx t3 = make_cplx(-s60 * d.y, s60 * d.x);  // i * s60 * (b - c)
+    a = cadd(a, t1);
+    b = cadd(t2, t3);
+    c = csub(t2, t3);
+}
+
+template <int R, int DIR, int N2_, int K1>
+struct Cz2Tw3 {  // y[N2_][K1] *= w_R^(N2_ * K1)
+    DEV static void run(cplx (*y)[R / 3])
+    {
+        if constexpr (K1 < R / 3) {
+            y[N2_][K1] = mul_root12<N2_ * K1 * (12 / R), DIR>(y[N2_][K1]);
+            Cz2Tw3<R, DIR, N2_, K1 + 1>::run(y);
+        }
+    }
+};
+
+// natural order in and out, X[k] = sum_n x[n] exp(DIR 2 pi i n k / R)
+template <int R, int DIR>
+struct DftAny {
+    DEV static void run(cplx *v)
+    {
+        if constexpr (Cz2Radix<R>::pow2) {
+            Dft<R, DIR>::run(v);
+        } else {
+            // n = 3 n1 + n2, k = k1 + P k2:  w^(nk) = w_P^(n1 k1) * w_R^(n2 k1) * w_3^(n2 k2)
+            constexpr int P = R / 3;
+            cplx y[3][P];
+#pragma unroll
+            for (int n2 = 0; n2 < 3; ++n2) {
+#pragma unroll
+                for (int n1 = 0; n1 < P; ++n1)
+                    y[n2][n1] = v[3 * n1 + n2];
+                Dft<P, DIR>::run(y[n2]);
+            }
+            Cz2Tw3<R, DIR, 1, 0>::run(y);
+            Cz2Tw3<R, DIR, 2, 0>::run(y);
+#pragma unroll
+            for (int k1 = 0; k1 < P; ++k1) {
+                dft3<DIR>(y[0][k1], y[1][k1], y[2][k1]);
+                v[k1] = y[0][k1];
+                v[k1 + P] = y[1][k1];
+                v[k1 + 2 * P] = y[2][k1];
+            }
+        }
+    }
+};
+
+// v[q] *= w1^q, q < R (powers by squarings / products of depth <= 4)
+template <int R>
+DEV void cz2_pow_mul(cplx *v, cplx w1)
+{
+    cplx w[R < 2 ? 2 : R];
+    w[1] = w1;
+#pragma unroll
+    for (int q = 2; q < R; ++q)
+        w[q] = (q & 1) ? cmul(w[q - 1], w1) : csq(w[q / 2]);
+#pragma unroll
+    for (int q = 1; q < R; ++q)
+        v[q] = cmul(v[q], w[q]);
+}
+
+// twiddle of the four-step split: element q of column o gets w_L^(o q) (CONJ: its conjugate)
+template <int R, bool CONJ>
+DEV void cz2_col_twiddle(cplx *v, const Cz2Args &a, int o)
+{
+    constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
+    if constexpr (Cz2Radix<R>::pow2) {
+        const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][Cz2Radix<R>::LR];
+        up_twiddle_mul<R, CONJ>(v, pt, N2, o);
+    } else {
+        double sn, cs;
+        sincospi(2.0 * (double)o / (double)a.L, &sn, &cs);
+        cz2_pow_mul<R>(v, make_cplx(cs, CONJ ? sn : -sn));
+    }
+}
+
 template <int R>
 __global__ void __launch_bounds__(256, 3) k_cz2_cols_fwd(const Cz2Args a)
 {
-    constexpr int LR = Log2R<R>::value;
     constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
     const CzArgs &c = a.c;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int o = (int)(gid & (N2 - 1));
     const size_t arr = (size_t)(gid >> FNFTB_CZ2_ROW_L2);
     const int Np = c.deg + 1;
-    const int L = 1 << a.l2L;
+    const int L = a.L;
     cplx v[R];
     if (!a.gen_v && a.src.lev) {
         // H11[deg-n] = scale * a[deg-n];  H21[deg-n] = -kappa * scale * conj(b[shift + n])
@@ -115,13 +239,12 @@ __global__ void __launch_bounds__(256, 3) k_cz2_cols_fwd(const Cz2Args a)
                                 : czero();
         }
     }
-    Dft<R, -1>::run(v);
-    const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][LR];
-    up_twiddle_mul<R, false>(v, pt, N2, o);
+    DftAny<R, -1>::run(v);
+    cz2_col_twiddle<R, false>(v, a, o);
     cplx *dst = c.ybuf + arr * (size_t)L;
 #pragma unroll
     for (int q = 0; q < R; ++q)
-        dst[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o] = v[q];
+        dst[((size_t)Cz2Radix<R>::row(q) << FNFTB_CZ2_ROW_L2) + o] = v[q];
 }
 
 // grid.x = narr * R rows, 128 threads, 64 KiB shared memory
@@ -132,8 +255,7 @@ __global__ void __launch_bounds__(128, 3) k_cz2_rows(const Cz2Args a)
     extern __shared__ double2 fnftb_smem_cz2[];
     cplx *S = (cplx *)fnftb_smem_cz2;
     const int tid = threadIdx.x;
-    const int l2R = a.l2L - FNFTB_CZ2_ROW_L2;
-    const int row = blockIdx.x & ((1 << l2R) - 1);
+    const int row = (int)(blockIdx.x % (unsigned)a.R);
     cplx *g = a.c.ybuf + (size_t)blockIdx.x * N2;  // rows are contiguous: arr*L + row*N2
     const cplx *pt12 = a.tw.base + a.tw.pass_off[12][4];  // len 4096, radix 16, s = 256
     // global -> forward radix-16 at stride 256 -> shared
@@ -239,7 +361,6 @@ DEV void cz2_epilogue(const CzArgs &c, size_t s, int m, cplx H0, cplx H1, cplx *
 template <int R>
 __global__ void __launch_bounds__(256) k_cz2_cols_inv(const Cz2Args a)
 {
-    constexpr int LR = Log2R<R>::value;
     constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
     const CzArgs &c = a.c;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,8 +368,7 @@ __global__ void __launch_bounds__(256) k_cz2_cols_inv(const Cz2Args a)
     const size_t s = (size_t)(gid >> FNFTB_CZ2_ROW_L2);
     if (o >= c.M)
         return;
-    const int L = 1 << a.l2L;
-    const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][LR];
+    const int L = a.L;
     cplx H[2][R];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -256,9 +376,9 @@ __global__ void __launch_bounds__(256) k_cz2_cols_inv(const Cz2Args a)
             const cplx *src = c.ybuf + (s * c.npoly + j) * (size_t)L;
 #pragma unroll
             for (int q = 0; q < R; ++q)
-                H[j][q] = src[((size_t)brev_c(q, LR) << FNFTB_CZ2_ROW_L2) + o];
-            up_twiddle_mul<R, true>(H[j], pt, N2, o);
-            Dft<R, +1>::run(H[j]);
+                H[j][q] = src[((size_t)Cz2Radix<R>::row(q) << FNFTB_CZ2_ROW_L2) + o];
+            cz2_col_twiddle<R, true>(H[j], a, o);
+            DftAny<R, +1>::run(H[j]);
         } else {
 #pragma unroll
             for (int q = 0; q < R; ++q)
@@ -300,6 +420,26 @@ DEV cplx unit_root16(int k)
     }
 }
 
+// exp(2 pi i k / 12)
+DEV cplx unit_root12(int k)
+{
+    const double c30 = 0.8660254037844386, h = 0.5;
+    switch (k % 12) {
+    case 0: return make_cplx(1.0, 0.0);
+    case 1: return make_cplx(c30, h);
+    case 2: return make_cplx(h, c30);
+    case 3: return make_cplx(0.0, 1.0);
+    case 4: return make_cplx(-h, c30);
+    case 5: return make_cplx(-c30, h);
+    case 6: return make_cplx(-1.0, 0.0);
+    case 7: return make_cplx(-c30, -h);
+    case 8: return make_cplx(-h, -c30);
+    case 9: return make_cplx(0.0, -1.0);
+    case 10: return make_cplx(h, -c30);
+    default: return make_cplx(c30, -h);
+    }
+}
+
 // Output-pruned variant: only the rows n < NOUT (m = o + n*4096 < M) of the radix-R inverse column
 // pass are wanted -- config 2 needs 4 of 16.  With q = s + S*t (S = R/NOUT):
 //   X[n] = sum_s w_R^(s n) * ( sum_t x[s + S t] w_NOUT^(t n) ),      n < NOUT,
@@ -309,22 +449,29 @@ DEV cplx unit_root16(int k)
 template <int R, int NOUT>
 __global__ void __launch_bounds__(256, 3) k_cz2_cols_inv_p(const Cz2Args a)
 {
-    constexpr int LR = Log2R<R>::value;
     constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
     constexpr int S = R / NOUT;
+    static_assert(S * NOUT == R, "NOUT must divide R");
     const CzArgs &c = a.c;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int o = (int)(gid & (N2 - 1));
     const size_t s = (size_t)(gid >> FNFTB_CZ2_ROW_L2);
     if (o >= c.M)
         return;
-    const int L = 1 << a.l2L;
-    const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][LR];
-    const cplx w1 = cconj(__ldg(&pt[o]));  // element q carries w1^q (up_twiddle_mul<R, true>)
+    const int L = a.L;
+    cplx w1;  // element q carries w1^q = conj(w_L^(o q)) (cz2_col_twiddle<R, true>)
+    if constexpr (Cz2Radix<R>::pow2) {
+        const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][Cz2Radix<R>::LR];
+        w1 = cconj(__ldg(&pt[o]));
+    } else {
+        double sn, cs;
+        sincospi(2.0 * (double)o / (double)L, &sn, &cs);
+        w1 = make_cplx(cs, sn);
+    }
     cplx wS = w1;
 #pragma unroll
-    for (int i = 1; i < S; i <<= 1)
-        wS = csq(wS);
+    for (int i = 1; i < S; ++i)
+        wS = cmul(wS, w1);
     cplx acc[2][NOUT];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -339,7 +486,7 @@ __global__ void __launch_bounds__(256, 3) k_cz2_cols_inv_p(const Cz2Args a)
                 cplx y[NOUT];
 #pragma unroll
                 for (int t = 0; t < NOUT; ++t)
-                    y[t] = src[((size_t)brev_c(sI + S * t, LR) << FNFTB_CZ2_ROW_L2) + o];
+                    y[t] = src[((size_t)Cz2Radix<R>::row(sI + S * t) << FNFTB_CZ2_ROW_L2) + o];
                 cplx tw = ws;
 #pragma unroll
                 for (int t = 0; t < NOUT; ++t) {
@@ -347,14 +494,16 @@ __global__ void __launch_bounds__(256, 3) k_cz2_cols_inv_p(const Cz2Args a)
                         y[t] = cmul(y[t], tw);
                     tw = cmul(tw, wS);
                 }
-                Dft<NOUT, +1>::run(y);
+                DftAny<NOUT, +1>::run(y);
 #pragma unroll
                 for (int n = 0; n < NOUT; ++n) {
-                    const int k16 = (sI * n * (16 / R)) & 15;
-                    if (k16 == 0) {
+                    // w_R^(sI n): a 16th root of unity for R | 16, a 12th root for R | 12
+                    const int k = Cz2Radix<R>::pow2 ? ((sI * n * (16 / (Cz2Radix<R>::pow2 ? R : 16))) & 15)
+                                                    : ((sI * n * (12 / (Cz2Radix<R>::pow2 ? 12 : R))) % 12);
+                    if (k == 0) {
                         acc[j][n] = cadd(acc[j][n], y[n]);
                     } else {
-                        cfma(acc[j][n], y[n], unit_root16(k16));
+                        cfma(acc[j][n], y[n], Cz2Radix<R>::pow2 ? unit_root16(k) : unit_root12(k));
                     }
                 }
                 ws = cmul(ws, w1);
@@ -393,17 +542,25 @@ static inline int cz2_launch(K kernel, const Cz2Args &a, unsigned grid, int nt, 
 // Same contract as cz_run (chirpz_driver.cuh); a.vhat doubles as the permuted FFT(v).
 int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2SymSrc *src)
 {
-    size_t need = (size_t)c.deg + (size_t)c.M, L = 1;
+    static const int knob_pow2 = [] {  // FNFT_B200_CZ2_POW2=1: power-of-two lengths only (round-1 behaviour)
+        const char *e = getenv("FNFT_B200_CZ2_POW2");
+        return (e && e[0]) ? atoi(e) : 0;
+    }();
+    const size_t need = (size_t)c.deg + (size_t)c.M;
+    int R = cz2_rows_for(need);
+    if (knob_pow2)
+        while (R & (R - 1))
+            ++R;
+    if (R == 0)
+        return -1;
+    const size_t L = (size_t)R << FNFTB_CZ2_ROW_L2;
     int l2L = 0;
-    while (L < need) {
-        L *= 2;
+    while (((size_t)1 << l2L) < L)
         ++l2L;
-    }
-    const int l2R = l2L - FNFTB_CZ2_ROW_L2;
     c.L = (int)L;
     c.N2 = 1 << FNFTB_CZ2_ROW_L2;
-    c.N1 = 1 << l2R;
-    c.plan1 = make_fft_plan(c.N1);  // only used by the table kernel's (unused) twiddle table
+    c.N1 = R;
+    c.plan1 = make_fft_plan(1 << (l2L - FNFTB_CZ2_ROW_L2));  // only used by the table kernel's (unused) twiddle table
     c.tab_y = tables;
     c.tab_out = c.tab_y + (c.deg + 1);
     c.tab_ph = c.tab_out + c.M;
@@ -427,14 +584,19 @@ int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2S
     a.tw = tw;
     a.vperm = c.vhat;
     a.l2L = l2L;
+    a.R = R;
+    a.L = (int)L;
     const size_t smem = sizeof(cplx) << FNFTB_CZ2_ROW_L2;
     const unsigned cols1 = (unsigned)((size_t)1 << FNFTB_CZ2_ROW_L2) / 256;
     const size_t narr = (size_t)c.B * c.npoly;
 #define CZ2_BY_R(KERNEL, ARGS, GRID, NAME)                                                     \
-    switch (l2R) {                                                                             \
-    case 1: rc = cz2_launch(KERNEL<2>, ARGS, GRID, 256, 0, st, NAME); break;                   \
-    case 2: rc = cz2_launch(KERNEL<4>, ARGS, GRID, 256, 0, st, NAME); break;                   \
-    case 3: rc = cz2_launch(KERNEL<8>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    switch (R) {                                                                               \
+    case 2: rc = cz2_launch(KERNEL<2>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    case 3: rc = cz2_launch(KERNEL<3>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    case 4: rc = cz2_launch(KERNEL<4>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    case 6: rc = cz2_launch(KERNEL<6>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    case 8: rc = cz2_launch(KERNEL<8>, ARGS, GRID, 256, 0, st, NAME); break;                   \
+    case 12: rc = cz2_launch(KERNEL<12>, ARGS, GRID, 256, 0, st, NAME); break;                 \
     default: rc = cz2_launch(KERNEL<16>, ARGS, GRID, 256, 0, st, NAME); break;                 \
     }
     // spectrum of the chirp filter (signal independent)
@@ -445,7 +607,7 @@ int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2S
         CZ2_BY_R(k_cz2_cols_fwd, v, cols1, "cz_filter");
         if (rc)
             return rc;
-        rc = cz2_launch(k_cz2_rows, v, 1u << l2R, 128, smem, st, "cz_filter");
+        rc = cz2_launch(k_cz2_rows, v, (unsigned)R, 128, smem, st, "cz_filter");
         if (rc)
             return rc;
     }
@@ -453,36 +615,40 @@ int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2S
     CZ2_BY_R(k_cz2_cols_fwd, a, (unsigned)(narr * cols1), "cz_cols_fwd");
     if (rc)
         return rc;
-    rc = cz2_launch(k_cz2_rows, a, (unsigned)(narr << l2R), 128, smem, st, "cz_rows");
+    rc = cz2_launch(k_cz2_rows, a, (unsigned)(narr * (size_t)R), 128, smem, st, "cz_rows");
     if (rc)
         return rc;
     {
         // rows of the last column pass that hold wanted outputs (m < M)
-        const int need = (c.M + (1 << FNFTB_CZ2_ROW_L2) - 1) >> FNFTB_CZ2_ROW_L2;
+        const int need_rows = (c.M + (1 << FNFTB_CZ2_ROW_L2) - 1) >> FNFTB_CZ2_ROW_L2;
         const unsigned grid = (unsigned)((size_t)c.B * cols1);
         static const int knob_prune = [] {
             const char *e = getenv("FNFT_B200_CZ2_PRUNE");
             return (e && e[0]) ? atoi(e) : 1;
         }();
-        const int R = 1 << l2R;
-        if (knob_prune && R >= 4 && need * 2 <= R) {
-            const bool quarter = (need * 4 <= R);
-            switch (l2R) {
-            case 2:
-                rc = quarter ? cz2_launch(k_cz2_cols_inv_p<4, 1>, a, grid, 256, 0, st, "cz_cols_inv")
-                             : cz2_launch(k_cz2_cols_inv_p<4, 2>, a, grid, 256, 0, st, "cz_cols_inv");
-                break;
-            case 3:
-                rc = quarter ? cz2_launch(k_cz2_cols_inv_p<8, 2>, a, grid, 256, 0, st, "cz_cols_inv")
-                             : cz2_launch(k_cz2_cols_inv_p<8, 4>, a, grid, 256, 0, st, "cz_cols_inv");
-                break;
-            default:
-                rc = quarter ? cz2_launch(k_cz2_cols_inv_p<16, 4>, a, grid, 256, 0, st, "cz_cols_inv")
-                             : cz2_launch(k_cz2_cols_inv_p<16, 8>, a, grid, 256, 0, st, "cz_cols_inv");
-                break;
+        // output-pruned kernels: NOUT = number of computed rows, a divisor of R
+        int nout = 0;
+        if (knob_prune) {
+            switch (R) {
+            case 4: nout = need_rows <= 1 ? 1 : (need_rows <= 2 ? 2 : 0); break;
+            case 6: nout = need_rows <= 3 ? 3 : 0; break;
+            case 8: nout = need_rows <= 2 ? 2 : (need_rows <= 4 ? 4 : 0); break;
+            case 12: nout = need_rows <= 4 ? 4 : (need_rows <= 6 ? 6 : 0); break;
+            case 16: nout = need_rows <= 4 ? 4 : (need_rows <= 8 ? 8 : 0); break;
+            default: break;
             }
-        } else {
-            CZ2_BY_R(k_cz2_cols_inv, a, grid, "cz_cols_inv");
+        }
+        switch (R * 100 + nout) {
+        case 401: rc = cz2_launch(k_cz2_cols_inv_p<4, 1>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 402: rc = cz2_launch(k_cz2_cols_inv_p<4, 2>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 603: rc = cz2_launch(k_cz2_cols_inv_p<6, 3>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 802: rc = cz2_launch(k_cz2_cols_inv_p<8, 2>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 804: rc = cz2_launch(k_cz2_cols_inv_p<8, 4>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 1204: rc = cz2_launch(k_cz2_cols_inv_p<12, 4>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 1206: rc = cz2_launch(k_cz2_cols_inv_p<12, 6>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 1604: rc = cz2_launch(k_cz2_cols_inv_p<16, 4>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        case 1608: rc = cz2_launch(k_cz2_cols_inv_p<16, 8>, a, grid, 256, 0, st, "cz_cols_inv"); break;
+        default: CZ2_BY_R(k_cz2_cols_inv, a, grid, "cz_cols_inv"); break;
         }
     }
 #undef CZ2_BY_R
@@ -526,6 +692,8 @@ int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
     r.tw = tw;
     r.vperm = a.vhat;
     r.l2L = ilog2i((unsigned)g.L);
+    r.R = g.N1;
+    r.L = g.L;
     const size_t smem = sizeof(cplx) << FNFTB_CZ2_ROW_L2;
     // 1. spectrum of the chirp filter: columns into array 0 of the workspace, rows -> vhat (permuted)
     {
