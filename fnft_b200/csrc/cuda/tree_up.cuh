@@ -23,6 +23,18 @@
 #include "tree_low2g.cuh"
 
 #define FNFTB_UP_ROW_L2 12  // row-split levels use rows of 4096 positions
+#ifndef FNFTB_UP_PIPE
+// 1: software-pipelined operand loads in the X stage (up_x_stage_pipe).  Measured on B200 (round 2,
+// profiles/r02_up_experiments.md): no gain -- ptxas spreads the in-flight loads over 3 of the 6 scoreboards of
+// a warp, so waiting for the oldest sub-batch also waits for the youngest one -- and k_up_rows_a gets slower.
+#define FNFTB_UP_PIPE 0
+#endif
+#ifndef FNFTB_UP_PIPE_G
+#define FNFTB_UP_PIPE_G 2      // positions per sub-batch (4 G loads)
+#endif
+#ifndef FNFTB_UP_PIPE_DEPTH
+#define FNFTB_UP_PIPE_DEPTH 3  // sub-batches in flight
+#endif
 
 struct UpArgs {
     const cplx *in;         // [B][n_in][E][N]      (E = 2 first-row-only, 4 general)
@@ -189,6 +201,94 @@ DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n
     }
 }
 
+// streaming operand load: read-only path, no L1 allocation (the twiddle tables stay in L1)
+DEV cplx up_ld_stream(const cplx *p)
+{
+    cplx v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// X stage with SOFTWARE-PIPELINED operand loads (round 2).  ncu, round 1: 66 % of the warp samples of
+// k_up_smem<12> sat in the X stage on long_scoreboard -- every lane loaded 16 values, waited for all of them,
+// computed, and only then issued the next 16, so on average half of the possible bytes were in flight.  Here
+// the NPOS positions of a lane are split into sub-batches of G positions (4 G loads); DEPTH sub-batches are
+// in flight while the oldest one is consumed.  The position range [p0, p0 + n) may straddle the half
+// boundary hb of the spectrum ((-1)^k changes sign there); chunks of 32*RX positions never do.
+// The pair prologue (dependent loads of max|c| and the tops) runs after the first loads have been issued.
+template <int RX, bool SYM, int NPOS, int G, int DEPTH>
+DEV UpPair<SYM> up_x_stage_pipe(const UpArgs &a, size_t sp, int s, int which, bool leader, int p0, int l0, int hb,
+                                double sg0, cplx *S, int tid, int nt)
+{
+    constexpr int LR = Log2R<RX>::value;
+    constexpr int E = UpT<SYM>::E;
+    constexpr int NSB = NPOS / G;       // sub-batches per lane
+    constexpr int SBC = RX / G;         // sub-batches per chunk of 32*RX positions
+    static_assert(NPOS % RX == 0 && RX % G == 0 && DEPTH >= 2 && DEPTH <= NSB, "shape");
+    const int N = 1 << a.l2n;
+    const cplx *mA = a.in + (2 * E * sp) * (size_t)N;  // matrix A, then matrix B
+    const cplx *mB = mA + (size_t)E * N;
+    const cplx *aA = SYM ? mA : mA + (size_t)(2 * (which >> 1)) * N;
+    const cplx *bA = aA + N;
+    const cplx *pz = SYM ? mB + (which ? 1 : 0) * (size_t)N : mB + (size_t)(which & 1) * N;
+    const cplx *pw = SYM ? mB + (which ? 0 : 1) * (size_t)N : mB + (size_t)(2 + (which & 1)) * N;
+    cplx *ge = a.last ? nullptr : a.out + (E * sp + which) * (size_t)(2 * N);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    // local offset of position i of sub-batch sb
+    auto off = [&](int sb, int i) {
+        return ((sb / SBC) * nwarps + warp) * (32 * RX) + 32 * ((sb % SBC) * G + i) + lane;
+    };
+    cplx bx[DEPTH][G], by[DEPTH][G], bz[DEPTH][G], bw[DEPTH][G];
+    auto issue = [&](int sb, int slot) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int pos = p0 + off(sb, i);
+            bx[slot][i] = up_ld_stream(&aA[pos]);
+            by[slot][i] = up_ld_stream(&bA[pos]);
+            bz[slot][i] = up_ld_stream(&pz[pos]);
+            bw[slot][i] = up_ld_stream(&pw[pos]);
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d)
+        issue(d, d);
+    const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, leader);
+    const double sc = P.sc;
+#pragma unroll
+    for (int sb = 0; sb < NSB; ++sb) {
+        if (sb + DEPTH - 1 < NSB)
+            issue(sb + DEPTH - 1, (sb + DEPTH - 1) % DEPTH);
+        const int slot = sb % DEPTH;
+        const double sg = (p0 + off(sb, 0) >= hb) ? -sg0 : sg0;
+        const double f = SYM ? (which ? sg * sc : -(double)a.kappa * sg * sc) : sc;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int loc = off(sb, i);
+            cplx r = cmul(cscale(bx[slot][i], sc), bz[slot][i]);
+            if (SYM)
+                cfmac(r, cscale(by[slot][i], f), bw[slot][i]);
+            else
+                cfma(r, cscale(by[slot][i], f), bw[slot][i]);
+            if (ge)
+                ge[p0 + loc] = r;
+            S[swz2(l0 + loc)] = r;
+        }
+        if (sb % SBC == SBC - 1) {  // chunk complete: first inverse pass (radix RX, stride 1) on it
+            __syncwarp();
+            const int b = l0 + ((sb / SBC) * nwarps + warp) * (32 * RX) + RX * lane;
+            cplx v[RX];
+#pragma unroll
+            for (int q = 0; q < RX; ++q)
+                v[q] = S[swz2(b + brev_c(q, LR))];
+            Dft<RX, +1>::run(v);
+#pragma unroll
+            for (int j = 0; j < RX; ++j)
+                S[swz2(b + j)] = v[j];
+        }
+    }
+    return P;
+}
+
 // F stage: last forward pass (radix RX, stride 1) of the CTA's n local elements, "- c_N",
 // coalesced store to the odd-bin region starting at godd (same warp-chunk scheme)
 template <int RX>
@@ -347,11 +447,16 @@ DEV void up_row_passes(cplx *S, const TwSet &tw, int tid, int nt)
 // ---------------------------------------------------------------------------------------
 // whole level in shared memory: grid.x = B * npairs * 2, blockDim.x = N / 32
 // ---------------------------------------------------------------------------------------
+#ifndef FNFTB_UP_TPP
+#define FNFTB_UP_TPP 32  // spectrum positions per thread of k_up_smem: 32 (168 registers) or 16 (128 registers, 16 warps per SM)
+#endif
 template <int L2N, bool SYM>
-__global__ void __launch_bounds__(1 << (L2N - 5), (L2N == 11) ? 6 : ((L2N == 12) ? 3 : 1)) k_up_smem(const UpArgs a)
+__global__ void __launch_bounds__((1 << L2N) / FNFTB_UP_TPP,
+                                  (FNFTB_UP_TPP == 32) ? ((L2N == 11) ? 6 : ((L2N == 12) ? 3 : 1))
+                                                       : ((L2N == 11) ? 4 : ((L2N == 12) ? 2 : 1))) k_up_smem(const UpArgs a)
 {
     constexpr int E = UpT<SYM>::E;
-    constexpr int N = 1 << L2N, NT = N / 32;
+    constexpr int N = 1 << L2N, NT = N / FNFTB_UP_TPP;
     constexpr int RX = (L2N == 12) ? 16 : 8;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
@@ -361,11 +466,17 @@ __global__ void __launch_bounds__(1 << (L2N - 5), (L2N == 11) ? 6 : ((L2N == 12)
     const size_t sp = blockIdx.x / E;
     const int npairs = a.n_in >> 1;
     const int s = (int)(sp / npairs);
+#if FNFTB_UP_PIPE
+    // X stage over all N positions; the half regions carry (-1)^k = +1 / -1
+    const UpPair<SYM> P = up_x_stage_pipe<RX, SYM, FNFTB_UP_TPP, FNFTB_UP_PIPE_G, FNFTB_UP_PIPE_DEPTH>(a, sp, s, which, which == 0, 0, 0, N / 2,
+                                                                                        1.0, S, tid, NT);
+#else
     const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0);
 
     // X stage: the two half regions carry (-1)^k = +1 / -1
     up_x_stage<RX, SYM>(a, sp, which, 0, 0, N / 2, 1.0, P, S, tid, NT);
     up_x_stage<RX, SYM>(a, sp, which, N / 2, N / 2, N / 2, -1.0, P, S, tid, NT);
+#endif
     __syncthreads();
     up_row_passes<+1, L2N, false>(S, a.tw, tid, NT);
     cplx *gcoef = a.last ? a.out + (E * sp + which) * (size_t)(N + 1) : nullptr;
@@ -401,10 +512,16 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
     const size_t sp = arr / E;
     const int npairs = a.n_in >> 1;
     const int s = (int)(sp / npairs);
-    const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0 && row == 0);
     const double sg = (row >> (l2R - 1)) ? -1.0 : 1.0;
     // X stage over positions [row*N2, (row+1)*N2): local index = position - row*N2
+#if FNFTB_UP_PIPE
+    static_assert(NT == 128, "32 positions per lane");
+    up_x_stage_pipe<16, SYM, 32, FNFTB_UP_PIPE_G, FNFTB_UP_PIPE_DEPTH>(a, sp, s, which, which == 0 && row == 0, row << l2row, 0,
+                                                                      0x7fffffff, sg, S, tid, NT);
+#else
+    const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0 && row == 0);
     up_x_stage<16, SYM>(a, sp, which, row << l2row, 0, N2, sg, P, S, tid, NT);
+#endif
     __syncthreads();
     up_row_passes<+1, FNFTB_UP_ROW_L2, true>(S, a.tw, tid, NT);
     cplx *dst = a.ws + arr * ((size_t)1 << l2n) + ((size_t)row << l2row);
@@ -543,9 +660,9 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
         const unsigned grid = (unsigned)a.B * (unsigned)npairs * (unsigned)E;
         const size_t smem = sizeof(cplx) * N + 64 * sizeof(double);
         switch (a.l2n) {
-        case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 64, smem, st, names_s[0]);
-        case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 128, smem, st, names_s[1]);
-        default: return up_launch(k_up_smem<13, SYM>, a, grid, 256, smem, st, names_s[2]);
+        case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 2048 / FNFTB_UP_TPP, smem, st, names_s[0]);
+        case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 4096 / FNFTB_UP_TPP, smem, st, names_s[1]);
+        default: return up_launch(k_up_smem<13, SYM>, a, grid, 8192 / FNFTB_UP_TPP, smem, st, names_s[2]);
         }
     }
     a.l2row = FNFTB_UP_ROW_L2;
