@@ -99,13 +99,162 @@ HD cplx bo_cf_w(int wsel, int i, int m)
 // wsel 2: CF5_3; wsel 3: CF6_4 (complex sums of bo_cf_w).
 HD cplx bo_l_at(cplx l, int wsel, int n)
 {
-    if (wsel == 0)
+    if (wsel == 0 || wsel >= 4)
         return l;
     if (wsel == 1)
         return cscale(l, ((n % 3) == 1) ? 9.0 / 20.0 : 11.0 / 40.0);
     const int i = (wsel == 2) ? (n % 3) : (n % 4);
     const cplx w0 = bo_cf_w(wsel, i, 0), w1 = bo_cf_w(wsel, i, 1), w2 = bo_cf_w(wsel, i, 2);
     return cmul(l, make_cplx(w0.x + w1.x + w2.x, w0.y + w1.y + w2.y));
+}
+
+// ---- ES4 / TES4 (round 2): fourth-order exponential schemes on the samples (q, q', q'') of a grid point -------
+// One step per grid point = one (ES4) or three (TES4) matrix exponentials written with the Pauli expansion
+// exp(a1 s1 + a2 s2 + a3 s3) = cos(w) I + sin(w)/w (a1 s1 + a2 s2 + a3 s3),  w = sqrt(-a1^2 - a2^2 - a3^2)
+// (/root/reference/src/private/fnft__akns_scatter_matrix.c:259-320, 464-515; with the lambda-derivative:
+// /root/reference/src/private/fnft__nse_scatter_bound_states.c:124-183, 343-470; backward sweep :535-630, whose
+// pre-computed quantities are the forward ones with the step h negated).  wsel 4 = ES4, 5 = TES4.
+#define FNFTB_WSEL_ES4 4
+#define FNFTB_WSEL_TES4 5
+
+HD void c_sincos(cplx z, cplx *sn, cplx *cs)
+{
+    double s, c;
+    SINCOS(z.x, &s, &c);
+    const double chy = cosh(z.y), shy = sinh(z.y);
+    *sn = make_cplx(s * chy, c * shy);
+    *cs = make_cplx(c * chy, -s * shy);
+}
+
+// U = exp(a1 s1 + a2 s2 + a3 s3); also returns w, sin(w)/w, cos(w), sin(w)
+HD void pauli_exp(cplx a1, cplx a2, cplx a3, cplx U[4], cplx *w_out, cplx *s_out, cplx *c_out, cplx *sinw_out)
+{
+    cplx w2 = cmul(a1, a1);
+    cfma(w2, a2, a2);
+    cfma(w2, a3, a3);
+    const cplx w = c_sqrt(cneg(w2));
+    cplx sn, cs;
+    c_sincos(w, &sn, &cs);
+    const cplx s = (w.x != 0.0 || w.y != 0.0) ? cdiv(sn, w) : make_cplx(1.0, 0.0);
+    const cplx sa3 = cmul(s, a3);
+    const cplx ia2 = cmuli(a2);
+    U[0] = cadd(cs, sa3);
+    U[1] = cmul(s, csub(a1, ia2));
+    U[2] = cmul(s, cadd(a1, ia2));
+    U[3] = csub(cs, sa3);
+    *w_out = w;
+    *s_out = s;
+    *c_out = cs;
+    *sinw_out = sn;
+}
+
+HD void mm2(const cplx *A, const cplx *B, cplx *C)
+{
+    C[0] = cmul(A[0], B[0]);
+    cfma(C[0], A[1], B[2]);
+    C[1] = cmul(A[0], B[1]);
+    cfma(C[1], A[1], B[3]);
+    C[2] = cmul(A[2], B[0]);
+    cfma(C[2], A[3], B[2]);
+    C[3] = cmul(A[2], B[1]);
+    cfma(C[3], A[3], B[3]);
+}
+
+// q3 = (q, q', q''), r3 likewise; l = spectral parameter; h = +-eps_t.  Ud (if WITH_D) follows the reference's
+// formulas literally (TES4: s_d = sin(w h)/w although w is already proportional to h).
+template <bool WITH_D>
+HD void es_step(const cplx *q3, const cplx *r3, cplx l, double h, bool tes, cplx U[4], cplx Ud[4])
+{
+    const double h2 = h * h, h3 = h2 * h;
+    const cplx q = q3[0], qd = q3[1], qdd = q3[2], r = r3[0], rd = r3[1], rdd = r3[2];
+    cplx w, s, c, sinw;
+    if (!tes) {
+        const cplx sdd = cadd(qdd, rdd), ddd = csub(qdd, rdd), sq = cadd(q, r), dq = csub(q, r);
+        const cplx sd = cadd(qd, rd), dd = csub(qd, rd);
+        // tmp1[n .. n+2] of the reference
+        const cplx t1 = cadd(cscale(sdd, h3 / 48.0), cscale(sq, 0.5 * h));
+        const cplx t2 = cmuli(cadd(cscale(dq, 0.5 * h), cscale(ddd, h3 / 48.0)));
+        const cplx t3 = cscale(csub(cmul(q, rd), cmul(qd, r)), -h3 / 12.0);
+        const cplx a1 = cadd(t1, cscale(cmuli(cmul(l, dd)), h3 / 12.0));
+        const cplx a2 = csub(t2, cscale(cmul(l, sd), h3 / 12.0));
+        const cplx a3 = cadd(cscale(cmuli(l), -h), t3);
+        pauli_exp(a1, a2, a3, U, &w, &s, &c, &sinw);
+        if (WITH_D) {
+            const cplx d1 = cscale(cmuli(dd), h3 / 12.0);  // tmp2[n .. n+2]
+            const cplx d2 = cscale(sd, -h3 / 12.0);
+            const cplx d3 = make_cplx(0.0, -h);
+            cplx acc = cmul(a1, d1);
+            cfma(acc, a2, d2);
+            cfma(acc, a3, d3);
+            const cplx w_d = cneg(cdiv(acc, w));
+            const cplx c_d = cneg(cmul(sinw, w_d));
+            const cplx s_d = cdiv(cmul(w_d, csub(c, s)), w);
+            const cplx sd3 = cmul(s, d3), sda3 = cmul(s_d, a3);
+            const cplx x = cadd(cmul(s_d, a1), cmul(s, d1));           // s_d a1 + s tmp2[n]
+            const cplx y = cmuli(cadd(cmul(s_d, a2), cmul(s, d2)));    // i (s_d a2 + s tmp2[n+1])
+            Ud[0] = cadd(cadd(c_d, sda3), sd3);
+            Ud[1] = csub(x, y);
+            Ud[2] = cadd(x, y);
+            Ud[3] = csub(csub(c_d, sda3), sd3);
+        }
+        return;
+    }
+    const cplx sdd = cadd(qdd, rdd), ddd = csub(qdd, rdd), sd = cadd(qd, rd), dd = csub(qd, rd);
+    cplx E1[4], E2[4], E3[4], T[4];
+    {
+        // tmp1[n], tmp1[n+1]:  h^3 (q''+r'')/96 - h^2 (q'+r')/24,  i h^3 (q''-r'')/96 + i h^2 (r'-q')/24
+        const cplx a1 = csub(cscale(sdd, h3 / 96.0), cscale(sd, h2 / 24.0));
+        const cplx a2 = cmuli(csub(cscale(ddd, h3 / 96.0), cscale(dd, h2 / 24.0)));
+        pauli_exp(a1, a2, czero(), E1, &w, &s, &c, &sinw);
+        // tmp2[n], tmp2[n+1]:  ... + h^2 (q'+r')/24,  ... + i h^2 (q'-r')/24
+        const cplx b1 = cadd(cscale(sdd, h3 / 96.0), cscale(sd, h2 / 24.0));
+        const cplx b2 = cmuli(cadd(cscale(ddd, h3 / 96.0), cscale(dd, h2 / 24.0)));
+        pauli_exp(b1, b2, czero(), E3, &w, &s, &c, &sinw);
+    }
+    const cplx a1 = cscale(cadd(q, r), 0.5 * h);
+    const cplx a2 = cscale(cmuli(csub(q, r)), 0.5 * h);
+    const cplx a3 = cscale(cmuli(l), -h);
+    pauli_exp(a1, a2, a3, E2, &w, &s, &c, &sinw);
+    mm2(E2, E1, T);
+    mm2(E3, T, U);
+    if (WITH_D) {
+        cplx snh, csh;
+        c_sincos(cscale(w, h), &snh, &csh);
+        const cplx s_d = cdiv(snh, w);
+        const cplx c_d = cscale(cmul(l, s_d), -h);
+        const cplx w3 = cmul(cmul(w, w), w);
+        const cplx w_d = cdiv(cmul(l, csub(cscale(cmul(w, csh), h), snh)), w3);
+        cplx UD[4];
+        const cplx isd = cmuli(s_d);
+        UD[0] = csub(c_d, isd);
+        UD[1] = cmul(w_d, q);
+        UD[2] = cmul(w_d, r);
+        UD[3] = cadd(c_d, isd);
+        mm2(UD, E1, T);
+        mm2(E3, T, Ud);
+    }
+}
+
+// One step of the slow recurrences starting at effective sample n: BO-type exponential of sample n (wsel 0..3),
+// or the ES4 / TES4 step of the grid point whose three samples start at n.  r == NULL: r = rsign * conj(q)
+// (rsign = -kappa).  Returns the number of effective samples consumed.
+template <bool WITH_D>
+HD int slow_step_at(const cplx *q, const cplx *r, int n, cplx l, double h, int wsel, double rsign, cplx U[4], cplx Ud[4])
+{
+    if (wsel >= FNFTB_WSEL_ES4) {
+        cplx q3[3], r3[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            q3[j] = q[n + j];
+            r3[j] = r ? r[n + j] : make_cplx(rsign * q3[j].x, -rsign * q3[j].y);
+        }
+        es_step<WITH_D>(q3, r3, l, h, wsel == FNFTB_WSEL_TES4, U, Ud);
+        return 3;
+    }
+    const cplx qn = q[n];
+    const cplx rn = r ? r[n] : make_cplx(rsign * qn.x, -rsign * qn.y);
+    bo_step<WITH_D>(qn, rn, bo_l_at(l, wsel, n), h, U, Ud);
+    return 1;
 }
 
 struct BoundArgs {

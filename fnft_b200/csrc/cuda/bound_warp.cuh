@@ -70,12 +70,11 @@ DEV BoMat bo_chunk(const cplx *q, const cplx *r, int lo, int hi, cplx l, double 
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         P.d[i] = czero();
-    for (int k = lo; k < hi; ++k) {
-        const int n = descending ? (hi - 1 - (k - lo)) : k;
-        const cplx qn = __ldg(&q[n]);
-        const cplx rn = r ? __ldg(&r[n]) : make_cplx(-qn.x, qn.y);
+    const int stp = (wsel >= FNFTB_WSEL_ES4) ? 3 : 1;  // ES4 / TES4: one step per grid point (3 samples)
+    for (int k = lo; k < hi; k += stp) {
+        const int n = descending ? (hi - stp - (k - lo)) : k;
         cplx U[4], Ud[4];
-        bo_step<WITH_D>(qn, rn, bo_l_at(l, wsel, n), h, U, Ud);
+        slow_step_at<WITH_D>(q, r, n, l, h, wsel, -1.0, U, Ud);
         cplx t[4];
         if (WITH_D) {
             cplx td[4];
@@ -242,19 +241,17 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
         }
         // re-sweep the chunk with the true start vector, storing PHI at the given points
         cplx p1 = s1, p2 = s2;
-        for (int n = lo; n < hi; ++n) {
-            const cplx qn = __ldg(&q[n]);
-            const cplx rn = rs ? __ldg(&rs[n]) : make_cplx(-qn.x, qn.y);
+        for (int n = lo; n < hi;) {
             cplx U[4], Ud[4];
-            bo_step<false>(qn, rn, bo_l_at(l, a.wsel, n), a.eps_t, U, Ud);
+            n += slow_step_at<false>(q, rs, n, l, a.eps_t, a.wsel, -1.0, U, Ud);
             cplx g = cmul(U[0], p1);
             cfma(g, U[1], p2);
             cplx f = cmul(U[2], p1);
             cfma(f, U[3], p2);
             p1 = g;
             p2 = f;
-            if (((n + 1) % up) == 0) {
-                const size_t ng = (size_t)(n + 1) / up;
+            if ((n % up) == 0) {  // n = first sample after this step
+                const size_t ng = (size_t)n / up;
                 store[ng * 2] = p1;
                 store[ng * 2 + 1] = p2;
             }
@@ -286,11 +283,10 @@ __global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
             v2 = nv2;
         }
         cplx psi1 = s1, psi2 = s2;
-        for (int n = hi - 1; n >= lo; --n) {
-            const cplx qn = __ldg(&q[n]);
-            const cplx rn = rs ? __ldg(&rs[n]) : make_cplx(-qn.x, qn.y);
+        const int stp = (a.wsel >= FNFTB_WSEL_ES4) ? 3 : 1;
+        for (int n = hi - stp; n >= lo; n -= stp) {
             cplx U[4], Ud[4];
-            bo_step<false>(qn, rn, bo_l_at(l, a.wsel, n), -a.eps_t, U, Ud);
+            slow_step_at<false>(q, rs, n, l, -a.eps_t, a.wsel, -1.0, U, Ud);
             cplx d = cmul(U[0], psi1);
             cfma(d, U[1], psi2);
             cplx c = cmul(U[2], psi1);

@@ -1323,10 +1323,41 @@ int fnftb_resample_cf_sub(fnftb_ctx *c, int wsel, int kappa, double eps_t, size_
     return resample_general(c, eps_t, nskip, Dsub, warn_host, wsel == 2 ? 3 : 4, wsel, kappa);
 }
 
-// The staged signals are CF4_3-preprocessed samples supplied by the caller (private API)
+// ES4 (wsel 4) / TES4 (wsel 5) preprocessing: (q, q', q'') per sub-sampled grid point by finite differences
+// (/root/reference/src/private/fnft__nse_discretization.c:609-631); the staged signals become [B][3*Dsub]
+int fnftb_preprocess_es4(fnftb_ctx *c, int wsel, double eps_t, size_t nskip, size_t Dsub)
+{
+    if (!c || !c->q || (wsel != 4 && wsel != 5))
+        return fail(-2, "invalid argument / no signals staged", __FILE__, __LINE__);
+    if (nskip < 1 || Dsub < 2 || (Dsub - 1) * nskip >= c->D)
+        return fail(-2, "invalid subsampling", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    Buf &dstbuf = (nskip > 1) ? c->qsub : c->qpre;  // a subsampled copy never replaces the full one
+    RC(ensure(dstbuf, c->B * 3 * Dsub * sizeof(cplx)));
+    Es4Args ea;
+    ea.q = c->q;
+    ea.out = (cplx *)dstbuf.p;
+    ea.B = (int)c->B;
+    ea.D = (int)c->D;
+    ea.nskip = (int)nskip;
+    ea.Dsub = (int)Dsub;
+    ea.eps_sub = eps_t * (double)nskip;
+    const long long total = (long long)c->B * (long long)Dsub;
+    RC((launch_blocks<Es4Args, blk_es4_preprocess>(ea, (unsigned)((total + 255) / 256), 256, 0, c->st,
+                                                   "es4_preprocess")));
+    c->q = (const cplx *)dstbuf.p;
+    c->r = nullptr;
+    c->D = 3 * Dsub;
+    c->have_box3 = 0;
+    c->slow_wsel = wsel;
+    c->rpre = nullptr;
+    return 0;
+}
+
+// The staged signals are preprocessed samples supplied by the caller (private API): CF4_3 (wsel 1), ES4 (4), TES4 (5)
 int fnftb_set_slow_weights(fnftb_ctx *c, int wsel)
 {
-    if (!c || wsel < 0 || wsel > 1)
+    if (!c || (wsel != 0 && wsel != 1 && wsel != 4 && wsel != 5))
         return fail(-2, "invalid argument", __FILE__, __LINE__);
     c->slow_wsel = wsel;
     c->rpre = nullptr;
@@ -1551,7 +1582,7 @@ int fnftb_newton(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_host,
     const size_t n = c->B * (size_t)d->Kmax;
     BoundArgs a = bound_args(c, d);
     static const int knob_warp = tree_knob("FNFT_B200_BOUND_WARP", 1);
-    if (knob_warp) {
+    if (knob_warp || c->slow_wsel >= 4) {  // (ES4 / TES4 exist in the warp kernels only)
         // one eigenvalue per warp (bound_warp.cuh)
         if (g_fnftb_profile_on)
             fnftb_profile_begin("bound_newton_warp", c->st);
@@ -1623,7 +1654,7 @@ int fnftb_normconsts(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_h
             a.koff = (const int *)c->koff.p + b0;
             a.ktot = (int)ktot;
             const size_t ng = (size_t)a.B * (size_t)d->Kmax;
-            if (knob_warp) {
+            if (knob_warp || c->slow_wsel >= 4) {
                 if (g_fnftb_profile_on)
                     fnftb_profile_begin("bound_normconsts_warp", c->st);
                 k_normconsts_warp<<<(unsigned)((ng + 3) / 4), 128, 0, c->st>>>(a);

@@ -118,6 +118,9 @@ int fnftb_resample_cf_sub(fnftb_ctx *ctx, int wsel, int kappa, double eps_t, siz
 /* Declares the staged signals to be CF4_3-preprocessed samples (wsel 1; 0 = BO / CF4_2), for callers
  * of the private API that pass preprocessed samples themselves. */
 int fnftb_set_slow_weights(fnftb_ctx *ctx, int wsel);
+/* ES4 (wsel 4) / TES4 (wsel 5) preprocessing of the staged signals: (q, q', q'') per sub-sampled grid point by
+ * central differences; the staged signals become [B][3*Dsub] (device resident) */
+int fnftb_preprocess_es4(fnftb_ctx *ctx, int wsel, double eps_t, size_t nskip, size_t Dsub);
 /* Plain subsampling of the staged signals (fnft__nse_discretization.c:463-470): keeps the
  * samples 0, nskip, ..., (Dsub-1)*nskip (device resident). */
 int fnftb_subsample(fnftb_ctx *ctx, size_t nskip, size_t Dsub);

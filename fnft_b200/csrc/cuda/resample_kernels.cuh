@@ -133,6 +133,35 @@ BLK void blk_subsample(const SubsampleArgs &a, blk3 bid, int nt, void * /*smem*/
     }
 }
 
+// ES4 / TES4 preprocessing (fnft__nse_discretization.c:609-631): every (sub-sampled) grid point becomes the three
+// effective samples (q, q', q'') with central differences over the sub-sampled grid, zero outside the window
+struct Es4Args {
+    const cplx *q;  // [B][D]
+    cplx *out;      // [B][3 * Dsub]
+    int B, D, nskip, Dsub;
+    double eps_sub;  // eps_t * nskip
+};
+
+BLK void blk_es4_preprocess(const Es4Args &a, blk3 bid, int nt, void * /*smem*/)
+{
+    FOR_THREADS(tid, nt)
+    {
+        const long long gid = (long long)bid.x * nt + tid;
+        if (gid < (long long)a.B * a.Dsub) {
+            const int s = (int)(gid / a.Dsub), i = (int)(gid % a.Dsub);
+            const cplx *qs = a.q + (size_t)s * a.D;
+            const cplx c = qs[(size_t)i * a.nskip];
+            const cplx m = (i > 0) ? qs[(size_t)(i - 1) * a.nskip] : czero();
+            const cplx p = (i + 1 < a.Dsub) ? qs[(size_t)(i + 1) * a.nskip] : czero();
+            const double d1 = 2.0 * a.eps_sub, d2 = a.eps_sub * a.eps_sub;
+            cplx *o = a.out + (size_t)gid * 3;
+            o[0] = c;
+            o[1] = make_cplx((p.x - m.x) / d1, (p.y - m.y) / d1);
+            o[2] = make_cplx(((p.x - 2.0 * c.x) + m.x) / d2, ((p.y - 2.0 * c.y) + m.y) / d2);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // General lengths (any D >= 4, not limited by shared memory): the length-D transforms are
 // evaluated as chirp-z transforms with the batched Bluestein machinery of chirpz_driver.cuh

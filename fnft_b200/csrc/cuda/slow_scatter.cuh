@@ -1,4 +1,5 @@
-// fnft_b200 -- continuous spectrum with the non-polynomial ("slow") discretizations BO, CF4_2, CF4_3, CF5_3 and CF6_4.
+// fnft_b200 -- continuous spectrum with the non-polynomial ("slow") discretizations BO, CF4_2, CF4_3, CF5_3, CF6_4,
+// ES4 and TES4.
 //
 // Replaces, for these two discretizations, the call of fnft__nse_scatter_matrix (derivative_flag 0)
 //   /root/reference/src/private/fnft__akns_scatter_matrix.c:112-126,206-232
@@ -34,11 +35,9 @@ DEV void bo_chunk_plain(const cplx *q, const cplx *r, int lo, int hi, cplx l, do
     Pm[2] = czero();
     Pm[3] = make_cplx(1.0, 0.0);
     const double ks = -(double)kappa;
-    for (int n = lo; n < hi; ++n) {
-        const cplx qn = __ldg(&q[n]);
-        const cplx rn = r ? __ldg(&r[n]) : make_cplx(ks * qn.x, -ks * qn.y);
+    for (int n = lo; n < hi;) {
         cplx U[4], Ud[4], t[4];
-        bo_step<false>(qn, rn, bo_l_at(l, wsel, n), h, U, Ud);
+        n += slow_step_at<false>(q, r, n, l, h, wsel, ks, U, Ud);
         bo_mm(U, Pm, t);
 #pragma unroll
         for (int i = 0; i < 4; ++i)

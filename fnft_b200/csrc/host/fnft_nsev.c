@@ -172,13 +172,16 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
      * continuous spectrum as one product of step matrices per spectral point (slow_scatter.cuh) */
     const int slow = (deg0 == 0);
     /* weight selector of the commutator-free schemes with more than two exponentials (bo_l_at) */
+    /* ... and of the exponential schemes on (q, q', q''): 4 = ES4, 5 = TES4 (es_step, bound_kernels.cuh) */
     const int cf_wsel = (akns == fnft__akns_discretization_CF4_3)   ? 1
                         : (akns == fnft__akns_discretization_CF5_3) ? 2
                         : (akns == fnft__akns_discretization_CF6_4) ? 3
+                        : (akns == fnft__akns_discretization_ES4)   ? 4
+                        : (akns == fnft__akns_discretization_TES4)  ? 5
                                                                     : 0;
+    const int es = (cf_wsel >= 4);
     if (slow && akns != fnft__akns_discretization_BO && akns != fnft__akns_discretization_CF4_2 && cf_wsel == 0)
-        return E_NOT_YET_IMPLEMENTED(opts->discretization,
-                                     Of the slow discretizations ES4 and TES4 do not run on the GPU.);
+        return E_INVALID_ARGUMENT(opts->discretization);
     if (!slow && !fnftb__akns_on_gpu(akns))
         return E_NOT_YET_IMPLEMENTED(opts->discretization,
                                      This splitting scheme has no GPU leaf kernel yet.);
@@ -282,6 +285,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                 goto leave_fun;
             }
             const int rc_sub = (upsampling == 2)   ? fnftb_resample_4split4_sub(ctx, eps_t_full, nskip, Dsub, NULL)
+                               : es                ? fnftb_preprocess_es4(ctx, cf_wsel, eps_t_full, nskip, Dsub)
                                : (upsampling >= 3) ? fnftb_resample_cf_sub(ctx, cf_wsel, (int)kappa, eps_t_full, nskip, Dsub, NULL)
                                                    : fnftb_subsample(ctx, nskip, Dsub);
             if (rc_sub != 0) {
@@ -306,7 +310,12 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                     goto leave_fun;
                 }
             }
-            if (upsampling >= 2) {
+            if (es) { /* finite differences on the (sub-sampled) grid, src/private/fnft__nse_discretization.c:609-631 */
+                if (fnftb_preprocess_es4(ctx, cf_wsel, eps_t_full, nskip_pass, D_given) != 0) {
+                    ret_code = E_DEVICE;
+                    goto leave_fun;
+                }
+            } else if (upsampling >= 2) {
                 int32_t *warn = devptr ? NULL : malloc(nb * sizeof(int32_t));
                 if ((upsampling == 2 ? fnftb_resample_4split4_sub(ctx, eps_t_full, nskip_pass, D_given, warn)
                                      : fnftb_resample_cf_sub(ctx, cf_wsel, (int)kappa, eps_t_full, nskip_pass, D_given,

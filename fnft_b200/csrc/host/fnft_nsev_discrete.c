@@ -195,7 +195,11 @@ FNFT_INT fnftb__nsev_discrete_chunk(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D_ef
     bd.eps_t = eps_t;
     bd.bc = 0.5;
     bd.lweight = (upsampling == 2) ? 0.5 : 1.0;
-    bd.scl = 1.0 / upsampling; /* fnft__nse_scatter_bound_states.c:225,235,247 */
+    /* fnft__nse_scatter_bound_states.c:225,235,247; ES4 / TES4: scl_factor = 1 (:132,157) */
+    bd.scl = (opts->discretization == fnft_nse_discretization_ES4 ||
+              opts->discretization == fnft_nse_discretization_TES4)
+                 ? 1.0
+                 : 1.0 / upsampling;
     bd.niter = (int)opts->niter;
 
     Kc = malloc(nb * sizeof(int32_t));

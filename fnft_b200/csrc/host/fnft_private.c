@@ -273,15 +273,19 @@ FNFT_INT fnft__nse_scatter_bound_states(const FNFT_UINT D, FNFT_COMPLEX const *c
         return E_INVALID_ARGUMENT(a_prime);
     if (b == NULL)
         return E_INVALID_ARGUMENT(b);
-    int upsampling;
+    int upsampling, wsel = 0;
     if (discretization == fnft_nse_discretization_BO)
         upsampling = 1;
     else if (discretization == fnft_nse_discretization_CF4_2)
         upsampling = 2;
-    else if (discretization == fnft_nse_discretization_CF4_3)
+    else if (discretization == fnft_nse_discretization_CF4_3) {
         upsampling = 3;
-    else
-        return E_NOT_YET_IMPLEMENTED(discretization, Only BO CF4_2 and CF4_3 run on the GPU.);
+        wsel = 1;
+    } else if (discretization == fnft_nse_discretization_ES4 || discretization == fnft_nse_discretization_TES4) {
+        upsampling = 3; /* the samples are (q, q', q'') per grid point */
+        wsel = (discretization == fnft_nse_discretization_ES4) ? 4 : 5;
+    } else
+        return E_NOT_YET_IMPLEMENTED(discretization, CF5_3 and CF6_4 need the explicit r samples of fnft_nsev.);
     if (D % upsampling != 0) /* fnft__nse_scatter_bound_states.c:231-246 */
         return E_ASSERTION_FAILED;
     if (r != NULL) {
@@ -292,7 +296,7 @@ FNFT_INT fnft__nse_scatter_bound_states(const FNFT_UINT D, FNFT_COMPLEX const *c
     fnftb_ctx *ctx = ctx_or_error();
     if (ctx == NULL)
         return FNFT_EC_OTHER;
-    if (fnftb_set_signals(ctx, 1, D, q, NULL, 0) != 0 || fnftb_set_slow_weights(ctx, upsampling == 3 ? 1 : 0) != 0)
+    if (fnftb_set_signals(ctx, 1, D, q, NULL, 0) != 0 || fnftb_set_slow_weights(ctx, wsel) != 0)
         return E_DEVICE;
     const FNFT_UINT D_given = D / upsampling;
     fnftb_bound_desc bd;
@@ -304,7 +308,7 @@ FNFT_INT fnft__nse_scatter_bound_states(const FNFT_UINT D, FNFT_COMPLEX const *c
     bd.eps_t = (T[1] - T[0]) / (D_given - 1);
     bd.bc = 0.5;
     bd.lweight = (upsampling == 2) ? 0.5 : 1.0;
-    bd.scl = 1.0 / upsampling;
+    bd.scl = (wsel >= 4) ? 1.0 : 1.0 / upsampling; /* fnft__nse_scatter_bound_states.c:132,157,225,235,247 */
     int32_t Kc = (int32_t)K;
     (void)skip_b_flag; /* b is cheap next to the sweeps; always computed */
     if (fnftb_normconsts(ctx, &bd, &Kc, bound_states, a_vals, aprime_vals, b) != 0)

@@ -59,7 +59,8 @@ NSE_CF4_2 = 22
 NSE_CF4_3 = 23
 NSE_CF5_3 = 24
 NSE_CF6_4 = 25
-_SLOW_UP = {NSE_CF4_2: 2, NSE_CF4_3: 3, NSE_CF5_3: 3, NSE_CF6_4: 4}   # upsampling factors of the slow schemes
+NSE_ES4, NSE_TES4 = 26, 27
+_SLOW_UP = {NSE_CF4_2: 2, NSE_CF4_3: 3, NSE_CF5_3: 3, NSE_CF6_4: 4, NSE_ES4: 3, NSE_TES4: 3}   # upsampling factors of the slow schemes
 # fnft_kdv_discretization_t (include/fnft_kdv_discretization_t.h:96-122)
 KDV_2SPLIT1A, KDV_2SPLIT1B, KDV_2SPLIT2A, KDV_2SPLIT2B, KDV_2SPLIT2S = range(5)
 KDV_2SPLIT4B = 9
@@ -327,7 +328,79 @@ def preprocess_signal(q, eps_t, kappa, nse_disc):
         for i in range(3):
             out[i::3] = w[i, 0] * q1 + w[i, 1] * q + w[i, 2] * q3
         return out
+    if nse_disc in (NSE_ES4, NSE_TES4):             # :609-631: (q, q', q'') by central differences, zero outside
+        D = q.shape[0]
+        qz = np.concatenate([[0.0], q, [0.0]])
+        out = np.empty(3 * D, dtype=np.complex128)
+        out[0::3] = q
+        out[1::3] = (qz[2:] - qz[:-2]) / (2 * eps_t)
+        out[2::3] = (qz[2:] - 2 * q + qz[:-2]) / (eps_t * eps_t)
+        return out
     return q.copy()
+
+
+def _pauli_exp(a1, a2, a3):
+    """exp of a1*sigma1 + a2*sigma2 + a3*sigma3 as the reference writes it
+    (src/private/fnft__akns_scatter_matrix.c:464-480): returns (U11, U12, U21, U22), s, c, w."""
+    w = np.sqrt(-(a1 * a1) - (a2 * a2) - (a3 * a3) + 0j)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = np.where(w != 0, np.sin(w) / np.where(w != 0, w, 1.0), 1.0)
+    c = np.cos(w)
+    return (c + s * a3, s * (a1 - 1j * a2), s * (a1 + 1j * a2), c - s * a3), s, c, w
+
+
+def _mm(A, B):
+    return (A[0] * B[0] + A[1] * B[2], A[0] * B[1] + A[1] * B[3],
+            A[2] * B[0] + A[3] * B[2], A[2] * B[1] + A[3] * B[3])
+
+
+def _es_step(q3, r3, l, h, tes, with_d=False):
+    """One step of ES4 (tes False) / TES4 (tes True) from the samples (q, q', q'') of a grid point, step h
+    (negative: the backward sweep, whose pre-computed quantities are the forward ones with -h,
+    src/private/fnft__nse_scatter_bound_states.c:124-183, :343-470, :535-630; continuous spectrum:
+    src/private/fnft__akns_scatter_matrix.c:259-320, :464-515).  Returns (U, Ud); Ud follows the
+    reference's formulas literally (TES4: s_d = sin(w*eps_t)/w with w already proportional to eps_t)."""
+    q, qd, qdd = q3
+    r, rd, rdd = r3
+    h2, h3 = h * h, h * h * h
+    if not tes:
+        t1 = h3 * (qdd + rdd) / 48.0 + (h * (q + r)) * 0.5
+        t2 = (h * (q - r) * 1j) * 0.5 + (h3 * (qdd - rdd) * 1j) / 48.0
+        t3 = -h3 * (q * rd - qd * r) / 12.0
+        a1 = t1 + h3 * (l * 1j * (qd - rd)) / 12.0
+        a2 = t2 - h3 * l * (qd + rd) / 12.0
+        a3 = -h * 1j * l + t3
+        U, s, c, w = _pauli_exp(a1, a2, a3)
+        Ud = None
+        if with_d:
+            d1 = 1j * h3 * (qd - rd) / 12.0
+            d2 = -h3 * (qd + rd) / 12.0
+            d3 = -1j * h
+            with np.errstate(divide="ignore", invalid="ignore"):
+                w_d = -(1 / w) * (a1 * d1 + a2 * d2 + a3 * d3)
+                c_d = -np.sin(w) * w_d
+                s_d = w_d * (c - s) / w
+            Ud = (c_d + s_d * a3 + s * d3, s_d * a1 + s * d1 - 1j * s_d * a2 - 1j * s * d2,
+                  s_d * a1 + s * d1 + 1j * s_d * a2 + 1j * s * d2, c_d - s_d * a3 - s * d3)
+        return U, Ud
+    e1 = (h3 * (qdd + rdd)) / 96.0 - (h2 * (qd + rd)) / 24.0, (h3 * (qdd - rdd) * 1j) / 96.0 + (h2 * (rd - qd) * 1j) / 24.0
+    e3 = (h3 * (qdd + rdd)) / 96.0 + (h2 * (qd + rd)) / 24.0, (h3 * (qdd - rdd) * 1j) / 96.0 + (h2 * (qd - rd) * 1j) / 24.0
+    E1, _, _, _ = _pauli_exp(e1[0], e1[1], 0.0)
+    a1 = (h * (q + r)) * 0.5
+    a2 = (h * (q * 1j - r * 1j)) * 0.5
+    a3 = -h * l * 1j
+    E2, s, c, w = _pauli_exp(a1, a2, a3)
+    E3, _, _, _ = _pauli_exp(e3[0], e3[1], 0.0)
+    U = _mm(E3, _mm(E2, E1))
+    Ud = None
+    if with_d:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s_d = np.sin(w * h) / w
+            c_d = -h * l * s_d
+            w_d = l * (h * w * np.cos(w * h) - np.sin(w * h)) / (w * w * w)
+        UD = (c_d - 1j * s_d, w_d * q, w_d * r, c_d + 1j * s_d)
+        Ud = _mm(E3, _mm(UD, E1))
+    return U, Ud
 
 
 def cf_complex_weights(nse_disc):
@@ -451,6 +524,12 @@ def nsev_contspec_slow(q, T, M, XI, kappa=+1, nse_disc=NSE_BO, cstype=0):
     xi = XI[0] + (XI[1] - XI[0]) / (M - 1) * np.arange(M)
     S11, S12 = np.ones(M, dtype=np.complex128), np.zeros(M, dtype=np.complex128)
     S21, S22 = np.zeros(M, dtype=np.complex128), np.ones(M, dtype=np.complex128)
+    if nse_disc in (NSE_ES4, NSE_TES4):
+        for n in range(0, qp.shape[0], 3):
+            (u11, u12, u21, u22), _ = _es_step(qp[n:n + 3], rp[n:n + 3], xi + 0j, eps_t, nse_disc == NSE_TES4)
+            S11, S12, S21, S22 = (u11 * S11 + u12 * S21, u11 * S12 + u12 * S22,
+                                  u21 * S11 + u22 * S21, u21 * S12 + u22 * S22)
+        qp = qp[:0]
     for n in range(qp.shape[0]):
         l = xi * lws[n % lws.size] + 0j
         (u11, u12, u21, u22), _ = _bo_step(qp[n], rp[n], l, eps_t)
@@ -524,8 +603,9 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1, r=None, nse_disc=None):
     r = -np.conj(q) if r is None else np.asarray(r, dtype=np.complex128)   # CF5_3 / CF6_4: explicit r
     eps_t = (T[1] - T[0]) / (Dg - 1)
     bc = 0.5
+    es = nse_disc in (NSE_ES4, NSE_TES4)
     lws = slow_lweights(upsampling, nse_disc)  # sums of the method weights (:214-221, 232-268)
-    scl = 1.0 / upsampling                     # :225, 235, 247
+    scl = 1.0 if es else 1.0 / upsampling      # :225, 235, 247; ES4 / TES4: :132, :157
     K = lam.shape[0]
     PHI = np.zeros((Dg + 1, 2, K), dtype=np.complex128)
     tb = T[0] - eps_t * bc
@@ -535,16 +615,19 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1, r=None, nse_disc=None):
     d2 = np.zeros(K, dtype=np.complex128)
     PHI[0, 0], PHI[0, 1] = phi1, phi2
     ng = 0
-    for n in range(D):                          # :289-338
+    for n in range(D):                          # :289-338 (ES4 / TES4: one step per grid point, :343-470)
+        if es and n % 3 != 0:
+            continue
         l = lam * lws[n % lws.size]
-        U, Ud = _bo_step(q[n], r[n], l, eps_t)
+        U, Ud = _es_step(q[n:n + 3], r[n:n + 3], lam, eps_t, nse_disc == NSE_TES4, True) if es else \
+            _bo_step(q[n], r[n], l, eps_t)
         c = Ud[0] * phi1 + Ud[1] * phi2 + U[0] * d1 + U[1] * d2
         d2 = Ud[2] * phi1 + Ud[3] * phi2 + U[2] * d1 + U[3] * d2
         d1 = c
         c = U[2] * phi1 + U[3] * phi2
         phi1 = U[0] * phi1 + U[1] * phi2
         phi2 = c
-        if (n + 1) % upsampling == 0:
+        if es or (n + 1) % upsampling == 0:
             ng += 1
             PHI[ng, 0], PHI[ng, 1] = phi1, phi2
     te = T[1] + eps_t * bc
@@ -558,8 +641,11 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1, r=None, nse_disc=None):
     PSI[Dg, 0], PSI[Dg, 1] = psi1, psi2
     ng = Dg
     for n in range(D - 1, -1, -1):
+        if es and n % 3 != 0:
+            continue
         l = lam * lws[n % lws.size]
-        U, _ = _bo_step(q[n], r[n], l, -eps_t)
+        U, _ = _es_step(q[n:n + 3], r[n:n + 3], lam, -eps_t, nse_disc == NSE_TES4) if es else \
+            _bo_step(q[n], r[n], l, -eps_t)
         c = U[2] * psi1 + U[3] * psi2
         psi1 = U[0] * psi1 + U[1] * psi2
         psi2 = c
@@ -621,7 +707,7 @@ def nsev_bound_states_newton(q, T, guesses, nse_disc=NSE_2SPLIT4B, niter=10, bsf
     eps_t = (T[1] - T[0]) / (D - 1)
     up = {NSE_4SPLIT4B: 2, 20: 2, **_SLOW_UP}.get(nse_disc, 1)
     qp, rp = preprocess_signal_qr(q, eps_t, +1, nse_disc)
-    wd = nse_disc if nse_disc in (NSE_CF5_3, NSE_CF6_4) else None
+    wd = nse_disc if nse_disc in (NSE_CF5_3, NSE_CF6_4, NSE_ES4, NSE_TES4) else None
     deg1 = 0 if nse_disc == NSE_BO or nse_disc in _SLOW_UP else akns_degree(_NSE2AKNS[nse_disc])
     map_coeff = 2.0 / deg1 if deg1 else 2.0     # src/fnft_nsev.c:612-616
     if bsfilt == 2:      # FULL :633-653

@@ -83,6 +83,71 @@ def test_reference_convention_kmax_does_not_blow_up_the_workspace(F):
     assert np.array_equal(nc[7, :K1], nc1[:K1])
 
 
+# ------------------------------------------------------------------ ES4 / TES4
+def _match(a, b):
+    return np.array([int(np.argmin(np.abs(a - x))) for x in b])
+
+
+def test_nsev_es4_tes4_vs_reference_runs(F):
+    """fnft_nse_discretization_ES4 / _TES4 (fnft__akns_scatter_matrix.c:259-320,464-515,
+    fnft__nse_scatter_bound_states.c:124-183,343-470,535-630, preprocessing fnft__nse_discretization.c:609-631):
+    continuous spectrum (rho, a, b), Newton bound states with norming constants and residues, Richardson
+    extrapolation, against outputs of the unmodified reference (tests/golden/make_golden_es4.py)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_es4.npz"))
+    cases = sorted({tuple(k.split("/")[1:5]) for k in g.files if k.startswith("refrun/slow")})
+    assert len(cases) == 14
+    for kind, disc, D, kappa in cases:
+        key = f"refrun/{kind}/{disc}/{D}/{kappa}"
+        q = g[f"refrun/slow/{disc}/{D}/{kappa}/q"]
+        gs = g[f"refrun/slow/{disc}/{D}/{kappa}/guesses"]
+        o = F.nsev_default_opts()
+        o.discretization, o.bound_state_localization, o.discspec_type, o.contspec_type = int(disc), 1, 2, 2
+        o.richardson_extrapolation_flag = 1 if kind == "slow_richardson" else 0
+        ret, cs, K, bs, nc = F.nsev(q, [-10, 10], 20, [-2, 2.5], int(kappa), o, K=3, bound_states=gs)
+        assert ret == 0, key
+        ref = g[key + "/cs"]
+        for part in range(3):
+            assert max(parity_contract(cs[part * 20:(part + 1) * 20], ref[part * 20:(part + 1) * 20])) < 1, key
+        rbs, rnc = g[key + "/bs"], g[key + "/nc"]
+        assert K == rbs.size, key
+        if K:
+            idx = _match(bs[:K], rbs)
+            assert (np.abs(bs[:K][idx] - rbs) <= 1e-9 * np.abs(rbs)).all(), key
+            for part in range(2):
+                assert (np.abs(nc[part * K:(part + 1) * K][idx] - rnc[part * K:(part + 1) * K])
+                        <= 1e-9 * np.abs(rnc[part * K:(part + 1) * K])).all(), key
+    # a batch gives the same values as single calls; oracle at another size
+    D = 250
+    t = np.linspace(-10, 10, D)
+    Q = np.stack([a / np.cosh(t) * np.exp(0.2j * a * t) for a in (0.8, 1.7, 2.6)])
+    for disc in (26, 27):
+        o = F.nsev_default_opts()
+        o.discretization = disc
+        o.bound_state_localization = 1
+        ret, csb, *_ = F.nsev_batch(Q, [-10, 10], 32, [-2, 2], -1, o)
+        assert ret == 0
+        for b in range(3):
+            r1, cs1, *_ = F.nsev(Q[b], [-10, 10], 32, [-2, 2], -1, o)
+            assert r1 == 0 and np.array_equal(cs1, csb[b])
+            assert O.misc_rel_err(cs1, O.nsev_contspec_slow(Q[b], [-10, 10], 32, [-2, 2], -1, disc, 0)) < 1e-9
+
+
+def test_private_scatter_bound_states_es4_tes4(F):
+    """fnft__nse_scatter_bound_states with ES4 / TES4 on caller-preprocessed samples (q, q', q'') against the oracle"""
+    D, T = 128, (-9.0, 9.0)
+    t = np.linspace(T[0], T[1], D)
+    q = 1.9 / np.cosh(t) * np.exp(0.3j * t)
+    eps_t = (T[1] - T[0]) / (D - 1)
+    lam = np.array([0.15 + 1.4j, -0.3 + 0.45j])
+    for disc in (26, 27):
+        qp = O.preprocess_signal(q, eps_t, 1, disc)
+        ret, a, ap, b = F.nse_scatter_bound_states(qp, None, T, lam, disc)
+        assert ret == 0
+        ra, rap, rb = O.nse_scatter_bound_states(qp, T, lam, 3, None, disc)
+        assert np.allclose(a, ra, rtol=1e-10, atol=1e-13) and np.allclose(ap, rap, rtol=1e-10)
+        assert np.allclose(b, rb, rtol=1e-9)
+
+
 # ------------------------------------------------------------------ devices other than 0
 def test_config2_shape_on_the_highest_device(F):
     n = F.device_count()

@@ -113,8 +113,8 @@ def test_argument_checks_mirror_reference(F):
 def test_not_yet_implemented_paths_are_loud(F):
     F.lib().fnft_errwarn_setprintf(None)
     o = F.nsev_default_opts()
-    o.discretization = 26  # ES4: slow discretization without a GPU kernel
-    assert _call_nsev(F, opts=o) == 6
+    o.discretization = 26  # ES4 (like every slow discretization) only with Newton localization: invalid argument
+    assert _call_nsev(F, opts=o) == 2
     o = F.nsev_default_opts()
     o.discretization = 1  # BO runs on the GPU, but only with Newton localization (src/fnft_nsev.c:209-219)
     assert _call_nsev(F, opts=o) == 2

@@ -157,3 +157,24 @@ def test_cf_schemes_vs_reference_runs():
             rbs, rnc = g[f"refrun/slow/{case}/bs"], g[f"refrun/slow/{case}/nc"]
             assert bs.size == rbs.size
             assert np.abs(bs - rbs).max() < 1e-11 and (np.abs(nc - rnc) <= 1e-9 * np.abs(rnc)).all(), case
+
+
+def test_es4_tes4_vs_reference_runs():
+    # ES4 / TES4 (one / three Pauli-expanded exponentials per step on (q, q', q''), finite-difference preprocessing,
+    # fnft__nse_discretization.c:609-631, fnft__akns_scatter_matrix.c:259-320,464-515,
+    # fnft__nse_scatter_bound_states.c:124-183,343-470,535-630): oracle against outputs of the unmodified
+    # reference (tests/golden/make_golden_es4.py)
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_es4.npz"))
+    cases = sorted({"/".join(k.split("/")[2:5]) for k in g.files if k.startswith("refrun/slow/")})
+    assert len(cases) == 10
+    for case in cases:
+        disc, D, kappa = map(int, case.split("/"))
+        q = g[f"refrun/slow/{case}/q"]
+        cs = O.nsev_contspec_slow(q, [-10, 10], 20, [-2, 2.5], kappa, disc, cstype=2)
+        assert rel_err(cs, g[f"refrun/slow/{case}/cs"]) < 1e-12, case
+        if kappa == 1:
+            bs, nc = O.nsev_bound_states_newton(q, [-10, 10], g[f"refrun/slow/{case}/guesses"], disc, 10, 2, 2)
+            rbs, rnc = g[f"refrun/slow/{case}/bs"], g[f"refrun/slow/{case}/nc"]
+            assert bs.size == rbs.size
+            assert np.abs(bs - rbs).max() < 1e-11 and (np.abs(nc - rnc) <= 1e-9 * np.abs(rnc)).all(), case
