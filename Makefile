@@ -32,7 +32,8 @@ $(BUILD)/cuda_%.o: fnft_b200/csrc/cuda/%.cu $(CUDA_HDR)
 
 $(LIB): $(HOST_OBJ) $(CUDA_OBJ)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lm
+	$(NVCC) $(ARCH) -shared -Xlinker -soname=libfnft.so.0 -o $@ $^ -lm
+	@ln -sf libfnft_b200.so $(LIBDIR)/libfnft.so.0 && ln -sf libfnft_b200.so $(LIBDIR)/libfnft.so
 
 emul:
 	g++ -O2 -std=c++17 -DFNFTB_EMUL -shared -fPIC -o tests/emul/libfnftb_emul.so tests/emul/emul_lib.cpp

@@ -753,6 +753,8 @@ def main():
                 out = fn()
                 L.fnft_b200_synchronize()
                 dt = max_over_ranks(time.perf_counter() - t0)
+                if os.environ.get("BENCH_DEBUG"):
+                    log("timed_call rep %d: %.2f ms" % (rep, dt * 1e3))
                 if rep > 0:
                     best = dt if best is None else min(best, dt)
             return best, out

@@ -89,6 +89,11 @@ EXPORTED_SYMBOLS = [
     "fnft_b200_launch_count", "fnft_b200_release",
     "fnft_b200_profile_enable", "fnft_b200_profile_report",
     "fnft_b200_set_devices", "fnft_b200_get_devices", "fnft_b200_probe_fp64_tflops",
+    "fnft__errmsg_aux", "fnft__warn_aux",
+    "fnft__poly_fmult_numel", "fnft__poly_fmult", "fnft__poly_eval", "fnft__poly_evalderiv",
+    "fnft__misc_print_buf", "fnft__misc_rel_err", "fnft__misc_hausdorff_dist", "fnft__misc_sech",
+    "fnft__misc_l2norm2", "fnft__misc_filter", "fnft__misc_filter_inv", "fnft__misc_filter_nonreal",
+    "fnft__misc_merge", "fnft__misc_downsample", "fnft__misc_CSINC", "fnft__misc_nextpowerof2",
 ]
 
 _lib = None
@@ -127,6 +132,30 @@ def lib():
     L.fnft__poly_fmult2x2_numel.argtypes = [sz, sz]
     L.fnft__poly_fmult2x2.restype = i32
     L.fnft__poly_fmult2x2.argtypes = [vp, sz, vp, vp, vp]
+    L.fnft__poly_fmult_numel.restype = sz
+    L.fnft__poly_fmult_numel.argtypes = [sz, sz]
+    L.fnft__poly_fmult.restype = i32
+    L.fnft__poly_fmult.argtypes = [vp, sz, vp, vp]
+    L.fnft__poly_eval.restype = i32
+    L.fnft__poly_eval.argtypes = [sz, vp, sz, vp]
+    L.fnft__poly_evalderiv.restype = i32
+    L.fnft__poly_evalderiv.argtypes = [sz, vp, sz, vp, vp]
+    L.fnft__misc_rel_err.restype = dbl
+    L.fnft__misc_rel_err.argtypes = [i32, vp, vp]
+    L.fnft__misc_hausdorff_dist.restype = dbl
+    L.fnft__misc_hausdorff_dist.argtypes = [sz, vp, sz, vp]
+    L.fnft__misc_l2norm2.restype = dbl
+    L.fnft__misc_l2norm2.argtypes = [sz, vp, dbl, dbl]
+    L.fnft__misc_filter.restype = i32
+    L.fnft__misc_filter.argtypes = [vp, vp, vp, vp]
+    L.fnft__misc_filter_inv.restype = i32
+    L.fnft__misc_filter_inv.argtypes = [vp, vp, vp, vp]
+    L.fnft__misc_filter_nonreal.restype = i32
+    L.fnft__misc_filter_nonreal.argtypes = [vp, vp, dbl]
+    L.fnft__misc_merge.restype = i32
+    L.fnft__misc_merge.argtypes = [vp, vp, dbl]
+    L.fnft__misc_nextpowerof2.restype = sz
+    L.fnft__misc_nextpowerof2.argtypes = [sz]
     L.fnft__poly_roots_fasteigen.restype = i32
     L.fnft__poly_roots_fasteigen.argtypes = [sz, vp, vp]
     L.fnft__poly_chirpz.restype = i32

@@ -39,6 +39,15 @@ void fnftb__warn(const char *func, const FNFT_INT line, const char *msg)
                   FNFT_VERSION_MINOR, FNFT_VERSION_PATCH, FNFT_VERSION_SUFFIX);
 }
 
+/* The names the reference's private error macros expand to (include/private/fnft__errwarn.h:36,125,
+ * src/private/fnft__errwarn.c:28-45): test programs compiled against the reference's headers call them. */
+FNFT_INT fnft__errmsg_aux(const FNFT_INT ec, const char *func, const FNFT_INT line, const char *msg)
+{
+    return fnftb__errmsg(ec, func, line, msg);
+}
+
+void fnft__warn_aux(const char *func, const FNFT_INT line, const char *msg) { fnftb__warn(func, line, msg); }
+
 FNFT_INT fnftb__device_error(const char *func, const FNFT_INT line)
 {
     char buf[640];

@@ -5,6 +5,7 @@
  * against this library.  Each is the B = 1 case of the batched device pipeline.
  */
 #include "fnft_internal.h"
+#include <stdlib.h>
 
 /* src/private/fnft__poly_fmult.c:40-43 */
 FNFT_UINT fnft__poly_fmult2x2_numel(FNFT_UINT deg, FNFT_UINT n)
@@ -54,6 +55,49 @@ FNFT_INT fnft__poly_fmult2x2(FNFT_UINT *const d, FNFT_UINT n, FNFT_COMPLEX *cons
     if (W_ptr != NULL)
         *W_ptr = W;
     return FNFT_SUCCESS;
+}
+
+/* src/private/fnft__poly_fmult.c:35-38 */
+FNFT_UINT fnft__poly_fmult_numel(FNFT_UINT deg, FNFT_UINT n) { return (deg + 1) * fnftb__nextpow2(n); }
+
+/*
+ * Product of n scalar polynomials of degree *d (src/private/fnft__poly_fmult.c:152-237): p holds them back to
+ * back, highest power first; on return the first *d + 1 entries hold the product and *d its degree.  The GPU
+ * tree multiplies 2x2 matrices, so the polynomials ride as diag(p_i, 1): one launch sequence of the general
+ * tree (tree_kernels.cuh), entry 11 of the result is the product.  With W_ptr the tree rescales by powers of
+ * two like poly_rescale (:330-374); result * 2^W is the product.
+ */
+FNFT_INT fnft__poly_fmult(FNFT_UINT *const d, FNFT_UINT n, FNFT_COMPLEX *const p, FNFT_INT *const W_ptr)
+{
+    if (d == NULL)
+        return E_INVALID_ARGUMENT(d);
+    if (p == NULL)
+        return E_INVALID_ARGUMENT(p);
+    if (n == 0)
+        return E_INVALID_ARGUMENT(n);
+    const FNFT_UINT deg = *d, d1 = deg + 1;
+    if (n == 1) {
+        if (W_ptr != NULL)
+            *W_ptr = 0;
+        return FNFT_SUCCESS;
+    }
+    const FNFT_UINT numel = fnft__poly_fmult2x2_numel(deg, n);
+    FNFT_COMPLEX *m = calloc(2 * numel, sizeof(FNFT_COMPLEX)); /* matrices, then the result */
+    if (m == NULL)
+        return E_NOMEM;
+    memcpy(m, p, n * d1 * sizeof(FNFT_COMPLEX)); /* entry 11 of every matrix */
+    for (FNFT_UINT i = 0; i < n; i++)
+        m[3 * n * d1 + i * d1 + deg] = 1.0; /* entry 22 = the constant 1 */
+    FNFT_UINT dout = deg;
+    FNFT_INT ret_code = fnft__poly_fmult2x2(&dout, n, m, m + numel, W_ptr);
+    if (ret_code == FNFT_SUCCESS) {
+        memcpy(p, m + numel, (dout + 1) * sizeof(FNFT_COMPLEX));
+        *d = dout;
+    } else {
+        ret_code = E_SUBROUTINE(ret_code);
+    }
+    free(m);
+    return ret_code;
 }
 
 /* src/private/fnft__poly_chirpz.c:33-105 */

@@ -324,6 +324,41 @@ FNFT_INT fnft__nse_scatter_bound_states(const FNFT_UINT D, FNFT_COMPLEX const *c
                                         fnft_nse_discretization_t discretization,
                                         FNFT_UINT skip_b_flag);
 
+/* include/private/fnft__errwarn.h:36,125, src/private/fnft__errwarn.c:28-45: what FNFT__ERRMSG / FNFT__WARN expand to */
+FNFT_INT fnft__errmsg_aux(const FNFT_INT ec, const char *func, const FNFT_INT line, const char *msg);
+void fnft__warn_aux(const char *func, const FNFT_INT line, const char *msg);
+/* include/private/fnft__poly_fmult.h:162,183, src/private/fnft__poly_fmult.c:35-38,152-237: product of n scalar
+ * polynomials (runs on the GPU tree as diag(p, 1) matrices) */
+FNFT_UINT fnft__poly_fmult_numel(FNFT_UINT deg, FNFT_UINT n);
+FNFT_INT fnft__poly_fmult(FNFT_UINT *const d, FNFT_UINT n, FNFT_COMPLEX *const p, FNFT_INT *const W_ptr);
+/* include/private/fnft__poly_eval.h:57,93, src/private/fnft__poly_eval.c:24-91 (host, O(deg) per point) */
+FNFT_INT fnft__poly_eval(const FNFT_UINT deg, FNFT_COMPLEX const *const p, const FNFT_UINT nz,
+                         FNFT_COMPLEX *const z);
+FNFT_INT fnft__poly_evalderiv(const FNFT_UINT deg, FNFT_COMPLEX const *const p, const FNFT_UINT nz,
+                              FNFT_COMPLEX *const z, FNFT_COMPLEX *const deriv);
+/* include/private/fnft__misc.h:42-219, src/private/fnft__misc.c:28-324: helpers the reference's test programs
+ * call (comparison metrics, filters); host code on caller memory.  Not exported: the single-shift resampling
+ * routine of that header (:241; the band-limited shift only exists as GPU preprocessing) and the pair-product
+ * routines of fnft__poly_fmult.h (:39,82,136), whose signatures carry Kiss FFT plan handles
+ * (include/private/fnft__fft_wrapper_plan_t.h). */
+void fnft__misc_print_buf(const FNFT_INT len, FNFT_COMPLEX const *const buf, char const *const varname);
+FNFT_REAL fnft__misc_rel_err(const FNFT_INT len, FNFT_COMPLEX const *const vec_numer,
+                             FNFT_COMPLEX const *const vec_exact);
+FNFT_REAL fnft__misc_hausdorff_dist(const FNFT_UINT lenA, FNFT_COMPLEX const *const vecA, const FNFT_UINT lenB,
+                                    FNFT_COMPLEX const *const vecB);
+FNFT_COMPLEX fnft__misc_sech(FNFT_COMPLEX Z);
+FNFT_REAL fnft__misc_l2norm2(const FNFT_UINT N, FNFT_COMPLEX const *const Z, const FNFT_REAL a, const FNFT_REAL b);
+FNFT_INT fnft__misc_filter(FNFT_UINT *const N_ptr, FNFT_COMPLEX *const vals, FNFT_COMPLEX *const rearrange_as_well,
+                           FNFT_REAL const *const bounding_box);
+FNFT_INT fnft__misc_filter_inv(FNFT_UINT *const N_ptr, FNFT_COMPLEX *const vals,
+                               FNFT_COMPLEX *const rearrange_as_well, FNFT_REAL const *const bounding_box);
+FNFT_INT fnft__misc_filter_nonreal(FNFT_UINT *N_ptr, FNFT_COMPLEX *const vals, const FNFT_REAL tol_im);
+FNFT_INT fnft__misc_merge(FNFT_UINT *N_ptr, FNFT_COMPLEX *const vals, FNFT_REAL tol);
+FNFT_INT fnft__misc_downsample(const FNFT_UINT D, FNFT_COMPLEX const *const q, FNFT_UINT *const Dsub_ptr,
+                               FNFT_COMPLEX **qsub_ptr, FNFT_UINT *const first_last_index);
+FNFT_COMPLEX fnft__misc_CSINC(FNFT_COMPLEX x);
+FNFT_UINT fnft__misc_nextpowerof2(const FNFT_UINT number);
+
 /* ---- NEW: batched entry points (not in the reference) ------------ */
 /*
  * B independent signals, row-major: q[b*D + n].  T, XI, M, kappa and opts are shared
