@@ -748,6 +748,53 @@ def nsev_bound_states_newton(q, T, guesses, nse_disc=NSE_2SPLIT4B, niter=10, bsf
     return bs, nc
 
 
+# ---------------------------------------------------------------------------------
+# periodic NFT: the polynomials of the grid search and one window of the search itself
+# ---------------------------------------------------------------------------------
+def nsep_gridsearch_polys(q, T, kappa=+1, nse_disc=NSE_2SPLIT4B):
+    """Polynomials whose roots fnft_nsep's grid search locates (src/fnft_nsep.c:222-436, no phase shift):
+    p+ and p- = z^(deg/2) (Delta(z) -/+ 2)-type polynomials of the main spectrum (:318-320, :358) and tm12 of the
+    auxiliary spectrum (:399).  Returns (p_plus, p_minus, p_aux, eps_t, deg); eps_t = (T1 - T0)/D (:252)."""
+    q = np.asarray(q, dtype=np.complex128)
+    D = q.shape[0]
+    eps_t = (T[1] - T[0]) / D
+    qp = preprocess_signal(q, eps_t, kappa, nse_disc)
+    tm, deg, W = akns_fscatter(qp, -kappa * np.conj(qp), eps_t, _NSE2AKNS[nse_disc], True)
+    pp = tm[0] + np.conj(tm[0][::-1])
+    pp[deg // 2] += 2.0 * 2.0 ** (-W)
+    pm = pp.copy()
+    pm[deg // 2] -= 4.0 * 2.0 ** (-W)
+    return pp, pm, tm[1].copy(), eps_t, deg
+
+
+def fftgridsearch_window(p, PHI, M, i, evaluate):
+    """One step i of poly_roots_fftgridsearch (src/private/fnft__poly_roots_fftgridsearch.c:78-148) with the nine
+    polynomial values supplied by evaluate(p, z) (e.g. Horner in long double) instead of the three chirp-z calls
+    (:68-75), which evaluate p at exp(i(PHI0 + j eps))/(1 + k eps).  Returns the root estimate or None."""
+    ld = np.longdouble
+    eps = (ld(PHI[1]) - ld(PHI[0])) / (M - 1)
+    ang = ld(PHI[0]) + np.arange(i - 1, i + 2).astype(ld) * eps
+    z = np.stack([np.exp(1j * ang.astype(np.clongdouble)) / (1 + k * eps) for k in (-1, 0, 1)])   # [k+1][j-i+1]
+    y = evaluate(p, z.reshape(-1)).reshape(3, 3)
+    y0 = y[1, 1]
+    if (np.abs(y) < np.abs(y0)).any():      # minimum modulus test :84-100
+        return None
+    z0 = np.exp(1j * np.clongdouble(ang[1]))
+    c, tmp = np.clongdouble(0), ld(0)
+    for jj, j in enumerate(range(i - 1, i + 2)):
+        for k in (-1, 0, 1):
+            if j == 0 and k == 0:           # (sic) :112-113
+                continue
+            zi = (1 - k * eps) * np.exp(1j * np.clongdouble(ang[jj]))
+            c += np.conj(zi - z0) * (y[k + 1, jj] - y0)
+            tmp += np.abs(zi - z0) ** 2
+    c /= tmp
+    if c == 0:
+        return z0 if y0 == 0 else None
+    zr = z0 - y0 / c
+    return None if np.abs(zr - z0) > eps else zr
+
+
 def misc_rel_err(num, exact):
     """misc_rel_err, src/private/fnft__misc.c:41-51 -- THE parity metric."""
     num = np.asarray(num)
