@@ -40,6 +40,7 @@ struct Cz2Args {
     int l2L;      // log2 L when L is a power of two (pass-major twiddle table of the column pass)
     int R, L;     // rows, L = R * 4096
     int gen_v;    // cols_fwd: generate the chirp filter; rows: forward half only -> vperm
+    int pf;       // L2 prefetch distance in CTAs (tree_up.cuh: l2_prefetch), 0 = off
 };
 
 // number of rows of 4096 for a Bluestein length >= need (0: not on the fast path)
@@ -205,6 +206,19 @@ __global__ void __launch_bounds__(256, 3) k_cz2_cols_fwd(const Cz2Args a)
         const cplx *pl = a.src.lev + (s * 2 + j) * (size_t)(a.src.d_full + 1);
         const int shift = a.src.d_full - c.deg;
         const double f = j ? -(double)a.src.kappa * scale : scale;
+        if (a.pf > 0 && threadIdx.x < R) {  // coefficient segments of the CTA `pf` places ahead
+            const size_t bp = (size_t)blockIdx.x + (size_t)a.pf;
+            const long long g0 = (long long)bp * blockDim.x;
+            const int n_lo = (int)(g0 & (N2 - 1)) + (int)threadIdx.x * N2;
+            int n_hi = n_lo + (int)blockDim.x;
+            n_hi = n_hi < Np ? n_hi : Np;
+            if (bp < gridDim.x && n_lo < n_hi) {
+                const size_t arrp = (size_t)(g0 >> FNFTB_CZ2_ROW_L2);
+                const cplx *pp = a.src.lev + arrp * (size_t)(a.src.d_full + 1);
+                const cplx *first = (arrp & 1) ? pp + shift + n_lo : pp + c.deg - (n_hi - 1);
+                l2_prefetch(first, (unsigned)(n_hi - n_lo) * (unsigned)sizeof(cplx));
+            }
+        }
 #pragma unroll
         for (int n1 = 0; n1 < R; ++n1) {
             const int n = o + n1 * N2;
@@ -257,6 +271,8 @@ __global__ void __launch_bounds__(128, 3) k_cz2_rows(const Cz2Args a)
     const int tid = threadIdx.x;
     const int row = (int)(blockIdx.x % (unsigned)a.R);
     cplx *g = a.c.ybuf + (size_t)blockIdx.x * N2;  // rows are contiguous: arr*L + row*N2
+    if (a.pf > 0 && (size_t)blockIdx.x + (size_t)a.pf < gridDim.x)
+        l2_prefetch_span(g + (size_t)a.pf * N2, N2, tid, 0);
     const cplx *pt12 = a.tw.base + a.tw.pass_off[12][4];  // len 4096, radix 16, s = 256
     // global -> forward radix-16 at stride 256 -> shared
 #pragma unroll 1
@@ -456,9 +472,20 @@ __global__ void __launch_bounds__(256, 3) k_cz2_cols_inv_p(const Cz2Args a)
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int o = (int)(gid & (N2 - 1));
     const size_t s = (size_t)(gid >> FNFTB_CZ2_ROW_L2);
+    const int L = a.L;
+    if (a.pf > 0 && (int)threadIdx.x < R * c.npoly) {  // the column segments of the CTA `pf` places ahead
+        const size_t bp = (size_t)blockIdx.x + (size_t)a.pf;
+        const long long g0 = (long long)bp * blockDim.x;
+        const int o0 = (int)(g0 & (N2 - 1));
+        if (bp < gridDim.x && o0 < c.M) {
+            const size_t sp = (size_t)(g0 >> FNFTB_CZ2_ROW_L2);
+            const int j = (int)threadIdx.x / R, row = (int)threadIdx.x % R;
+            l2_prefetch(c.ybuf + (sp * c.npoly + j) * (size_t)L + ((size_t)row << FNFTB_CZ2_ROW_L2) + o0,
+                        blockDim.x * (unsigned)sizeof(cplx));
+        }
+    }
     if (o >= c.M)
         return;
-    const int L = a.L;
     cplx w1;  // element q carries w1^q = conj(w_L^(o q)) (cz2_col_twiddle<R, true>)
     if constexpr (Cz2Radix<R>::pow2) {
         const cplx *pt = a.tw.base + a.tw.pass_off[a.l2L][Cz2Radix<R>::LR];
@@ -586,6 +613,11 @@ int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2S
     a.l2L = l2L;
     a.R = R;
     a.L = (int)L;
+    static const int knob_pf = [] {  // L2 prefetch distance of the three kernels (CTAs), 0 = off
+        const char *e = getenv("FNFT_B200_PFD_CZ");
+        return (e && e[0]) ? atoi(e) : 12;
+    }();
+    a.pf = knob_pf;
     const size_t smem = sizeof(cplx) << FNFTB_CZ2_ROW_L2;
     const unsigned cols1 = (unsigned)((size_t)1 << FNFTB_CZ2_ROW_L2) / 256;
     const size_t narr = (size_t)c.B * c.npoly;
@@ -603,6 +635,7 @@ int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2S
     {
         Cz2Args v = a;
         v.gen_v = 1;
+        v.pf = 0;
         v.c.ybuf = c.ybuf;  // array 0 of the workspace as scratch
         CZ2_BY_R(k_cz2_cols_fwd, v, cols1, "cz_filter");
         if (rc)
@@ -721,6 +754,7 @@ int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
     // 3. rows
     r.c = a;
     r.gen_v = 0;
+    r.pf = 6;  // L2 prefetch of the row six CTAs ahead
     rc = cz2_launch(k_cz2_rows, r, (unsigned)((size_t)a.B * a.npoly * g.N1), 128, smem, st, "cz_rows");
     if (rc)
         return rc;

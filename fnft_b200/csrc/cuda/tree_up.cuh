@@ -48,8 +48,33 @@ struct UpArgs {
     int B, n_in, l2n;
     int normalize, kappa, last;
     int l2row;              // row-split: log2(N2)
+    int pf;                 // L2 prefetch distance in CTAs (0: off), see up_prefetch
     TwSet tw;
 };
+
+// L2 PREFETCH (round 2).  The upper levels are bound by memory-level parallelism, not by a saturated unit
+// (profiles/r02_up_experiments.md): 12 warps per SM whose registers hold the loads in flight, and shared memory
+// is full of work buffers, so there is no room to land asynchronous copies.  cp.async.bulk.prefetch.L2 (SASS
+// UBLKPF.L2, executed by the TMA unit) needs neither registers nor shared memory: every CTA asks for the operands
+// of the CTA that runs `pf` CTAs after it -- a fraction of a CTA lifetime ahead, since CTAs are dispatched in
+// index order -- so that the demand loads of the X stage find their lines in L2 (~250 cycles instead of a
+// loaded-DRAM latency of 800+), and the DRAM transfers overlap the compute phases of the resident CTAs.
+DEV void l2_prefetch(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// n complex values starting at p, split over the first threads of the CTA in pieces of 1024 values (16 KB);
+// slot0 = first thread slot to use, returns the next free slot
+DEV int l2_prefetch_span(const cplx *p, int n, int tid, int slot0)
+{
+    const int pieces = (n + 1023) >> 10;
+    const int k = tid - slot0;
+    if (k >= 0 && k < pieces) {
+        const int cnt = (n - (k << 10)) < 1024 ? (n - (k << 10)) : 1024;
+        l2_prefetch(p + ((size_t)k << 10), (unsigned)cnt * (unsigned)sizeof(cplx));
+    }
+    return slot0 + pieces;
+}
 
 // SYM = first-row-only NSE mode (2 stored entries, conj symmetry), !SYM = general 2x2
 template <bool SYM>
@@ -198,6 +223,32 @@ DEV void up_x_stage(const UpArgs &a, size_t sp, int which, int p0, int l0, int n
 #pragma unroll
         for (int j = 0; j < RX; ++j)
             S[swz2(b + j)] = v[j];
+    }
+}
+
+// prefetch of the four operand streams that up_x_stage reads for (pair sp, entry which), positions [p0, p0 + n)
+template <bool SYM>
+DEV void up_prefetch_operands(const UpArgs &a, size_t sp, int which, int p0, int n, int tid)
+{
+    constexpr int E = UpT<SYM>::E;
+    const int N = 1 << a.l2n;
+    const cplx *mA = a.in + (2 * E * sp) * (size_t)N;
+    const cplx *mB = mA + (size_t)E * N;
+    if (SYM) {
+        if (n == N) {  // whole pair: one contiguous block [aA bA aB bB]
+            l2_prefetch_span(mA, 4 * N, tid, 0);
+            return;
+        }
+        int sl = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            sl = l2_prefetch_span(mA + (size_t)e * N + p0, n, tid, sl);
+    } else {
+        const cplx *aA = mA + (size_t)(2 * (which >> 1)) * N;
+        int sl = l2_prefetch_span(aA + p0, n, tid, 0);
+        sl = l2_prefetch_span(aA + N + p0, n, tid, sl);
+        sl = l2_prefetch_span(mB + (size_t)(which & 1) * N + p0, n, tid, sl);
+        l2_prefetch_span(mB + (size_t)(2 + (which & 1)) * N + p0, n, tid, sl);
     }
 }
 
@@ -466,6 +517,11 @@ __global__ void __launch_bounds__((1 << L2N) / FNFTB_UP_TPP,
     const size_t sp = blockIdx.x / E;
     const int npairs = a.n_in >> 1;
     const int s = (int)(sp / npairs);
+    if (a.pf > 0) {  // operands of the CTA `pf` places ahead (the SYM pair's two CTAs read the same block)
+        const size_t bp = (size_t)blockIdx.x + (size_t)a.pf;
+        if (bp < gridDim.x && (!SYM || (bp % E) == 0))
+            up_prefetch_operands<SYM>(a, bp / E, (int)(bp % E), 0, N, tid);
+    }
 #if FNFTB_UP_PIPE
     // X stage over all N positions; the half regions carry (-1)^k = +1 / -1
     const UpPair<SYM> P = up_x_stage_pipe<RX, SYM, FNFTB_UP_TPP, FNFTB_UP_PIPE_G, FNFTB_UP_PIPE_DEPTH>(a, sp, s, which, which == 0, 0, 0, N / 2,
@@ -513,6 +569,12 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_a(const UpArgs a)
     const int npairs = a.n_in >> 1;
     const int s = (int)(sp / npairs);
     const double sg = (row >> (l2R - 1)) ? -1.0 : 1.0;
+    if (a.pf > 0) {
+        const size_t bp = (size_t)blockIdx.x + (size_t)a.pf;
+        const size_t arrp = bp >> l2R;
+        if (bp < gridDim.x && (!SYM || (arrp % E) == 0))
+            up_prefetch_operands<SYM>(a, arrp / E, (int)(arrp % E), (int)(bp & ((1 << l2R) - 1)) << l2row, N2, tid);
+    }
     // X stage over positions [row*N2, (row+1)*N2): local index = position - row*N2
 #if FNFTB_UP_PIPE
     static_assert(NT == 128, "32 positions per lane");
@@ -550,6 +612,14 @@ __global__ void __launch_bounds__((R >= 64) ? 128 : 256, (R >= 32) ? 1 : ((R >= 
     const cplx *pt = a.tw.base + a.tw.pass_off[l2n][LR];
     const cplx *tt = a.tw.base + a.tw.twist_off[l2n];
     const double invN = 1.0 / (double)N;
+    if (a.pf > 0 && threadIdx.x < R) {  // the R column segments of the CTA `pf` places ahead
+        const size_t bp = (size_t)blockIdx.x + (size_t)a.pf;
+        if (bp < gridDim.x) {
+            const long long g0 = (long long)bp * blockDim.x;
+            const cplx *wp = a.ws + (size_t)(g0 >> l2row) * (size_t)N + (size_t)(g0 & ((1 << l2row) - 1));
+            l2_prefetch(wp + ((size_t)brev_c((int)threadIdx.x, LR) << l2row), blockDim.x * (unsigned)sizeof(cplx));
+        }
+    }
     cplx v[R];
 #pragma unroll
     for (int q = 0; q < R; ++q)
@@ -605,6 +675,11 @@ __global__ void __launch_bounds__(NT, 3) k_up_rows_c(const UpArgs a)
     const size_t sp = arr / E;
     const Tops Tn = ((const Tops *)a.tt_out)[sp];
     const cplx *src = a.ws + arr * ((size_t)1 << l2n) + ((size_t)row << l2row);
+    if (a.pf > 0) {
+        const size_t bp = (size_t)blockIdx.x + (size_t)a.pf;
+        if (bp < gridDim.x)
+            l2_prefetch_span(a.ws + (bp << l2row), N2, tid, 0);  // rows are contiguous in block order
+    }
     for (int i = tid; i < N2; i += NT)
         S[swz2(i)] = src[i];
     __syncthreads();
@@ -648,6 +723,26 @@ static inline int up_launch(K kernel, const UpArgs &a, unsigned grid, int nt, si
     return (int)cudaGetLastError();
 }
 
+// L2 prefetch distance in CTAs per kernel family (environment FNFT_B200_PFD_<family>; 0 = off).  Measured on
+// B200 (profiles/r02_l2_prefetch.md): the best distance is about one loaded-DRAM latency of CTA starts -- the L2
+// does not retain a line much longer than 10 us at 4 TB/s of streaming traffic, so longer distances lose.
+enum { UP_PF_SMEM11 = 0, UP_PF_SMEM12, UP_PF_SMEM13, UP_PF_ROWS_A, UP_PF_COLS, UP_PF_ROWS_C, UP_PF_FAMILIES };
+static inline int up_pf_distance(int family)
+{
+    static int init = 0, dist[UP_PF_FAMILIES];
+    static const char *names[UP_PF_FAMILIES] = {"FNFT_B200_PFD_SMEM11", "FNFT_B200_PFD_SMEM12", "FNFT_B200_PFD_SMEM13",
+                                                "FNFT_B200_PFD_ROWS_A", "FNFT_B200_PFD_COLS",   "FNFT_B200_PFD_ROWS_C"};
+    static const int dflt[UP_PF_FAMILIES] = {8, 4, 2, 2, 6, 6};
+    if (!init) {
+        for (int f = 0; f < UP_PF_FAMILIES; ++f) {
+            const char *e = getenv(names[f]);
+            dist[f] = (e && e[0]) ? atoi(e) : dflt[f];
+        }
+        init = 1;
+    }
+    return dist[family];
+}
+
 template <bool SYM>
 static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
 {
@@ -659,6 +754,7 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
     if (a.l2n <= l2smem_max) {
         const unsigned grid = (unsigned)a.B * (unsigned)npairs * (unsigned)E;
         const size_t smem = sizeof(cplx) * N + 64 * sizeof(double);
+        a.pf = up_pf_distance(UP_PF_SMEM11 + (a.l2n - 11));
         switch (a.l2n) {
         case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 2048 / FNFTB_UP_TPP, smem, st, names_s[0]);
         case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 4096 / FNFTB_UP_TPP, smem, st, names_s[1]);
@@ -669,9 +765,11 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
     const int l2R = a.l2n - a.l2row;
     const unsigned grid_rows = (unsigned)a.B * (unsigned)npairs * (unsigned)E << l2R;
     const size_t smem = sizeof(cplx) << a.l2row;
+    a.pf = up_pf_distance(UP_PF_ROWS_A);
     int rc = up_launch(k_up_rows_a<128, SYM>, a, grid_rows, 128, smem, st, "tree_up_rows_a");
     if (rc)
         return rc;
+    a.pf = up_pf_distance(UP_PF_COLS);
     const unsigned grid_cols = (unsigned)(((size_t)a.B * npairs * E << a.l2row) / 256);
     switch (l2R) {
     case 1: rc = up_launch(k_up_cols<2, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
@@ -687,6 +785,7 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
     }
     if (rc || a.last)
         return rc;
+    a.pf = up_pf_distance(UP_PF_ROWS_C);
     return up_launch(k_up_rows_c<128, SYM>, a, grid_rows, 128, smem, st, "tree_up_rows_c");
 }
 

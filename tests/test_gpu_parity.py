@@ -336,12 +336,13 @@ def test_nsev_slow_discretizations_bo_cf4_2_vs_reference_runs(F, golden):
             for part in range(2):
                 assert (np.abs(nc[part * K:(part + 1) * K][idx] - rnc[part * K:(part + 1) * K])
                         <= 1e-9 * np.abs(rnc[part * K:(part + 1) * K])).all()
-    # the other slow discretizations are not implemented, and say so; default localization is
-    # rejected for slow discretizations like in the reference (src/fnft_nsev.c:209-219)
+    # every discretization of the reference runs on the GPU now; an unknown enum value is an invalid argument
+    # (src/fnft_nsev.c:199-203), and the default localization is rejected for slow discretizations like in the
+    # reference (src/fnft_nsev.c:209-219)
     o = F.nsev_default_opts()
-    o.discretization = 26
+    o.discretization = 99
     o.bound_state_localization = 1
-    assert F.nsev(np.ones(16), [-1, 1], 4, [-1, 1], 1, o)[0] == 6
+    assert abs(F.nsev(np.ones(16), [-1, 1], 4, [-1, 1], 1, o)[0]) == 2
     o.discretization = 1
     o.bound_state_localization = 2
     assert F.nsev(np.ones(16), [-1, 1], 4, [-1, 1], 1, o)[0] == 2
