@@ -592,10 +592,13 @@ def _bo_step(q, r, l, h):
     return U, Ud
 
 
-def nse_scatter_bound_states(q, T, lam, upsampling=1, r=None, nse_disc=None):
+def nse_scatter_bound_states(q, T, lam, upsampling=1, r=None, nse_disc=None, ties=None):
     """fnft__nse_scatter_bound_states for BO (upsampling 1), CF4_2 (upsampling 2) and CF4_3 (3),
     src/private/fnft__nse_scatter_bound_states.c:29-667.  q are the effective
-    (preprocessed) samples, r = -conj(q).  Returns (a, aprime, b)."""
+    (preprocessed) samples, r = -conj(q).  Returns (a, aprime, b).
+    ties: optional list; receives, per spectral point, the b values of ALL sample points whose error metric is
+    within 1e-9 (relative) of the minimum -- for a lambda that is not an eigenvalue of a symmetric potential the
+    metric has exact two-way ties and the last bit decides which sample point the reference takes."""
     q = np.asarray(q, dtype=np.complex128)
     lam = np.asarray(lam, dtype=np.complex128)
     D = q.shape[0]
@@ -663,6 +666,8 @@ def nse_scatter_bound_states(q, T, lam, upsampling=1, r=None, nse_disc=None):
             if metric[n, k] < best:
                 best = metric[n, k]
                 b[k] = ratio[n, k]
+        if ties is not None:
+            ties.append(ratio[np.nonzero(metric[:, k] <= best * (1 + 1e-9))[0], k])
     return a, ap, b
 
 
@@ -793,6 +798,35 @@ def fftgridsearch_window(p, PHI, M, i, evaluate):
         return z0 if y0 == 0 else None
     zr = z0 - y0 / c
     return None if np.abs(zr - z0) > eps else zr
+
+
+def fftgridsearch_windows(p, PHI, M, idx, evaluate):
+    """fftgridsearch_window for an array of steps idx at once (one batched call of evaluate); NaN where the step
+    yields no root.  Same arithmetic, src/private/fnft__poly_roots_fftgridsearch.c:78-148."""
+    ld = np.longdouble
+    idx = np.asarray(idx, dtype=np.int64)
+    eps = (ld(PHI[1]) - ld(PHI[0])) / (M - 1)
+    ang = ld(PHI[0]) + (idx[:, None] + np.arange(-1, 2)[None, :]).astype(ld) * eps          # [n][jj]
+    e = np.exp(1j * ang.astype(np.clongdouble))
+    rad = np.array([1 / (1 + k * eps) for k in (-1, 0, 1)], dtype=ld)                     # evaluation radii :68-75
+    z = e[:, None, :] * rad[None, :, None]                                                # [n][k+1][jj]
+    y = evaluate(p, z.reshape(-1)).reshape(z.shape)
+    y0 = y[:, 1, 1]
+    ok = ~(np.abs(y) < np.abs(y0)[:, None, None]).any(axis=(1, 2))
+    z0 = e[:, 1]
+    c = np.zeros(len(idx), dtype=np.clongdouble)
+    tmp = np.zeros(len(idx), dtype=ld)
+    for jj in range(3):
+        for k in (-1, 0, 1):
+            skip = ((idx + jj - 1) == 0) & (k == 0)                                        # (sic) :112-113
+            zi = (1 - k * eps) * e[:, jj]
+            c += np.where(skip, 0, np.conj(zi - z0) * (y[:, k + 1, jj] - y0))
+            tmp += np.where(skip, 0, np.abs(zi - z0) ** 2)
+    c = c / tmp
+    with np.errstate(all="ignore"):
+        zr = z0 - y0 / c
+    ok &= (c != 0) & (np.abs(zr - z0) <= eps)
+    return np.where(ok, zr, np.nan + 0j)
 
 
 def misc_rel_err(num, exact):
