@@ -129,7 +129,7 @@ def test_config5_nsep_gridsearch_full_size_and_whose_error_it_is(F, BM, R):
     # Ours must sit on it, the reference (chirp-z with cpow(W, n^2/2), absolute error floor ~1e-11 max|p|,
     # DESIGN.md 5) is the one that is off.
     from oracle import fnft_oracle as O
-    idx = np.array([0, 136, 614])            # 614 / 136: the largest differences of a 16-signal survey (below)
+    idx = np.array([0, 10, 614])             # 10: bench.py's worst case (1.7e-7 relative); 614: survey below
     n = len(idx)
     q = np.stack([BM.config5_inputs(i, i + 1)[0] for i in idx])
     ref = _pool(BM._ref5, [(q[i],) for i in range(n)])
@@ -171,15 +171,17 @@ def test_config5_nsep_gridsearch_full_size_and_whose_error_it_is(F, BM, R):
               (float(np.abs(a1 - ideal).max()), float(np.abs(a0 - ideal).max())),
               "| main: ours-ideal %.2e ref-ideal %.2e" % (float(np.abs(m1 - idl).max()), float(np.abs(m0 - idl).max())))
     print("config 5, |lambda - ideal estimator output|:", worst)
-    # Survey of 16 signals (session log, one B200 box): |ours - ref| <= 4.5e-9 everywhere; auxiliary spectrum:
+    # Signal 10 is the one behind the 1.7e-7 (relative to |lambda| <= 10) that bench.py's parity gate reports for
+    # config 5: the REFERENCE is 1.66e-6 away from the idealised estimator there (CPU-only survey of the first 16
+    # signals: all others <= 3.7e-8).  Survey of 16 more signals with the GPU (session log, one B200 box): |ours - ref| <= 4.5e-9 everywhere; auxiliary spectrum:
     # both 5.9e-9 from the idealised estimator and 1e-13 from each other (the idealisation puts the samples exactly
     # on the rings, the implementations put them where the rounded W of the reference puts them; d lambda =
     # d z / eps_t amplifies 1e-11 in z 650 times); main spectrum: ours 3.0e-9 on 12 signals where the reference is
     # 3e-9 ... 4.5e-8 (signal 614: 2.99e-9 vs 4.54e-8, signal 136: 2.98e-9 vs 1.15e-8), and 1.4 - 2.5e-8 for both on
     # the four signals with near-double points (273, 409, 887, 1023), where the two agree to 2e-9.
     assert worst["ours_aux"] <= 1e-8 and abs(worst["ours_aux"] - worst["ref_aux"]) <= 1e-10, worst
-    assert worst["ours_main"] <= 5e-9, worst             # on the ideal estimator up to the idealisation
-    assert worst["ref_main"] >= 4 * worst["ours_main"], worst      # ... where the reference is not
+    assert worst["ours_main"] <= 3e-8, worst             # signal 10: 1.86e-8 (near-double points), others 3.0e-9
+    assert worst["ref_main"] >= 50 * worst["ours_main"], worst    # ... the reference is the one that is off: 1.66e-6
     assert worst["diff"] <= worst["ref_main"] + worst["ours_main"], worst
 
 
