@@ -26,9 +26,12 @@ $(BUILD)/host_%.o: fnft_b200/csrc/host/%.c $(HOST_HDR)
 	@mkdir -p $(BUILD)
 	$(CC) $(CFLAGS) -c $< -o $@
 
-$(BUILD)/cuda_%.o: fnft_b200/csrc/cuda/%.cu $(CUDA_HDR)
+# dependencies of every CUDA object come from nvcc -MMD (build/cuda_*.d), so touching one header only rebuilds
+# the translation units that include it
+$(BUILD)/cuda_%.o: fnft_b200/csrc/cuda/%.cu
 	@mkdir -p $(BUILD)
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) -MMD -MF $(BUILD)/cuda_$*.d -c $< -o $@
+-include $(wildcard $(BUILD)/cuda_*.d)
 
 $(LIB): $(HOST_OBJ) $(CUDA_OBJ)
 	@mkdir -p $(LIBDIR)

@@ -94,6 +94,8 @@ EXPORTED_SYMBOLS = [
     "fnft__misc_print_buf", "fnft__misc_rel_err", "fnft__misc_hausdorff_dist", "fnft__misc_sech",
     "fnft__misc_l2norm2", "fnft__misc_filter", "fnft__misc_filter_inv", "fnft__misc_filter_nonreal",
     "fnft__misc_merge", "fnft__misc_downsample", "fnft__misc_CSINC", "fnft__misc_nextpowerof2",
+    "fnft_nsev_inverse_default_opts", "fnft_nsev_inverse_XI", "fnft_nsev_inverse", "fnft_nsev_inverse_batch",
+    "fnft__nse_finvscatter", "fnft__poly_specfact",
 ]
 
 _lib = None

@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(256, 3) k_cz2_cols_fwd(const Cz2Args a)
                 dn = (double)n;
             else if (n > L - Np)
                 dn = (double)(L - n);
-            v[n1] = (dn >= 0.0) ? chirp_factor(-c.lwr * (0.5 * dn * dn), -c.lwi, 0.5 * dn * dn, 0.0, 0.0)
+            v[n1] = (dn >= 0.0) ? (c.dft_n > 0 ? chirp_dft((long long)dn, c.dft_n, c.lwi < 0.0 ? 1.0 : -1.0)
+                                               : chirp_factor(-c.lwr * (0.5 * dn * dn), -c.lwi, 0.5 * dn * dn, 0.0, 0.0))
                                 : czero();
         }
     }
@@ -762,7 +763,11 @@ int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
     return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / g.C)), nt,
                                                           cz_cols_smem_bytes(g.C, g.N1, a.npoly), st, "cz_cols_inv");
 }
+// the general four-step path with the first-generation row kernels (table twiddles): plain DFTs of the inverse
+// transform, where 1e-15 matters more than speed
+int cz_run_exact(CzArgs a, cplx *tables, cudaStream_t st) { return cz_run(a, tables, st); }
 #else
+int cz_run_exact(CzArgs a, cplx *tables, cudaStream_t st);
 int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2SymSrc *src = nullptr);
 int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st);
 #endif

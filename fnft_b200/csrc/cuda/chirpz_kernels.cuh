@@ -33,6 +33,9 @@ struct CzArgs {
     int log2C;
     FftPlan plan1, plan2;
     double lwr, lwi; // ln|W|, arg W
+    int dft_n;       // > 0: plain DFT of this length, W = exp(+-2 pi i / dft_n) and A = 1; the chirp factors are then
+                     // formed from k^2 mod 2 dft_n with sincospi (exact argument reduction) instead of arg W * k^2 / 2,
+                     // whose rounding of 2 pi / n costs ~1e-12 at n ~ 4000 (inverse transform, resampling)
     double lar, lai; // ln|A|, arg A
     cplx *ybuf;      // [B][npoly][N1][N2]
     cplx *vhat;      // [N1][N2]
@@ -77,6 +80,13 @@ HD cplx chirp_factor(double mag_arg, double li1, double h1, double li2, double h
     return r;
 }
 
+// W^(+-k^2/2) of a DFT of length n, W = exp(sign 2 pi i / n): exp(sign i pi (k^2 mod 2n) / n)
+HD cplx chirp_dft(long long k, int n, double sign)
+{
+    const long long m = (k * k) % (2LL * n);
+    return cispi(sign * (double)m / (double)n);
+}
+
 // fills the signal-independent tables; grid covers max(deg+1, M, L) elements
 BLK void blk_cz_tables(const CzArgs &a, blk3 bid, int nt, void *)
 {
@@ -85,12 +95,14 @@ BLK void blk_cz_tables(const CzArgs &a, blk3 bid, int nt, void *)
         const long long i = (long long)bid.x * nt + tid;
         if (i <= a.deg) {
             const double dn = (double)i;
-            a.tab_y[i] = chirp_factor(-a.lar * dn + a.lwr * (0.5 * dn * dn), a.lwi, 0.5 * dn * dn,
-                                      -a.lai, dn);
+            a.tab_y[i] = a.dft_n > 0 ? chirp_dft(i, a.dft_n, a.lwi < 0.0 ? -1.0 : 1.0)
+                                     : chirp_factor(-a.lar * dn + a.lwr * (0.5 * dn * dn), a.lwi, 0.5 * dn * dn,
+                                                    -a.lai, dn);
         }
         if (i < a.M) {
             const double dm = (double)i;
-            a.tab_out[i] = cscale(chirp_factor(a.lwr * (0.5 * dm * dm), a.lwi, 0.5 * dm * dm, 0.0, 0.0),
+            a.tab_out[i] = cscale(a.dft_n > 0 ? chirp_dft(i, a.dft_n, a.lwi < 0.0 ? -1.0 : 1.0)
+                                              : chirp_factor(a.lwr * (0.5 * dm * dm), a.lwi, 0.5 * dm * dm, 0.0, 0.0),
                                   1.0 / (double)a.L);
             double sn, cs;
             if (a.mode == FNFTB_CZ_NSEV) {
@@ -191,7 +203,8 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
                 else if (n > (long long)a.L - Np)
                     dn = (double)(a.L - n);
                 if (dn >= 0.0)
-                    v = chirp_factor(-a.lwr * (0.5 * dn * dn), -a.lwi, 0.5 * dn * dn, 0.0, 0.0);
+                    v = a.dft_n > 0 ? chirp_dft((long long)dn, a.dft_n, a.lwi < 0.0 ? 1.0 : -1.0)
+                                    : chirp_factor(-a.lwr * (0.5 * dn * dn), -a.lwi, 0.5 * dn * dn, 0.0, 0.0);
             }
             S[(size_t)c * N1 + swz(n1)] = v;
         }

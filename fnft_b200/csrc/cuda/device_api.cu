@@ -177,6 +177,9 @@ struct fnftb_ctx {
     // batch, filled chunk by chunk; the host never waits inside the loop
     int32_t *st_all = nullptr;
     size_t st_all_cap = 0, st_all_off = 0, st_all_total = 0;
+    // workspace of the inverse transform (inverse_api.cu, its own translation unit) and its destructor
+    void *inv_ws = nullptr;
+    void (*inv_free)(void *) = nullptr;
 };
 
 static TwTable ctx_tw(const fnftb_ctx *c)
@@ -320,6 +323,9 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
                   &c->rprebuf, &c->koff};
     for (Buf *b : all)
         release(*b);
+    if (c->inv_ws && c->inv_free)
+        c->inv_free(c->inv_ws);
+    c->inv_ws = nullptr;
     if (c->st_h2d)
         cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h)
@@ -1254,6 +1260,7 @@ static int resample_general(fnftb_ctx *c, double eps_t, size_t nskip, size_t Dsu
     a.M = (int)D;
     a.lwr = 0.0;
     a.lwi = -2.0 * 3.14159265358979323846 / (double)D;  // W = exp(-2 pi i / D), A = 1
+    a.dft_n = (int)D;
     a.ybuf = (cplx *)c->ybuf.p;
     a.vhat = (cplx *)c->vhat.p;
     a.T = ctx_tw(c);
@@ -1682,3 +1689,85 @@ int fnftb_normconsts(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_h
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// hooks for inverse_api.cu (ctx_hooks.h): the inverse transform lives in its own translation
+// unit and borrows the stream, the general 2x2 pair product and the any-length DFT from here
+// ---------------------------------------------------------------------------------------
+#include "ctx_hooks.h"
+cudaStream_t fnftb__stream(fnftb_ctx *c) { return c->st; }
+int fnftb__activate(fnftb_ctx *c)
+{
+    CU(cudaSetDevice(c->device));
+    return 0;
+}
+void **fnftb__inv_slot(fnftb_ctx *c, void (***dtor)(void *))
+{
+    *dtor = &c->inv_free;
+    return &c->inv_ws;
+}
+int fnftb__fail(int code, const char *what, const char *file, int line) { return fail(code, what, file, line); }
+
+// B products of two 2x2 polynomial matrices of degree d (a power of two; general coefficient path of
+// tree_driver.cuh, no normalisation).  prepare: *lev0 = operand buffer [B][2][4][d+1] to be filled on the
+// context's stream; run: *res = result [B][4][2d+1] = matrix 0 * matrix 1 (valid until the next tree call).
+int fnftb__pair2x2_prepare(fnftb_ctx *c, size_t B, size_t d, cplx **lev0)
+{
+    if (!c || B == 0 || d == 0 || (d & (d - 1)) != 0 || d > ((size_t)1 << 15))
+        return fail(-6, "pair product: degree must be a power of two <= 32768", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure_tree(c, B, 2, d, 2 * d));
+    c->deferred.valid = 0;
+    c->tmB = 0;
+    *lev0 = (cplx *)c->lev0.p;
+    return 0;
+}
+int fnftb__pair2x2_run(fnftb_ctx *c, size_t B, size_t d, const cplx **res)
+{
+    const TwTable T = ctx_tw(c);
+    int cur = 0;
+    const TreeWork w = tree_work(c);
+    RC(tree_levels(w, (int)B, 2, (int)d, 0, T, c->st, &cur));
+    *res = w.lev[cur];
+    return 0;
+}
+
+// B discrete Fourier transforms of any length n (sign -1: forward, +1: inverse, both unnormalised) as
+// chirp-z transforms (W = exp(sign 2 pi i / n), A = 1) through the general four-step path, like the
+// resampling step.  in_rev holds the inputs REVERSED (x[n-1-k], polynomial coefficients in descending order).
+int fnftb__dft(fnftb_ctx *c, size_t B, size_t n, const cplx *in_rev, cplx *out, int sign)
+{
+    if (!c || B == 0 || n < 2 || 2 * n > ((size_t)1 << 24))
+        return fail(-6, "DFT length not supported", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const CzGeom g = cz_geometry((int)n - 1, (int)n);
+    RC(ensure(c->ybuf, cz_ybuf_elems(g, B, 1) * sizeof(cplx)));
+    RC(ensure(c->vhat, (size_t)g.L * sizeof(cplx)));
+    RC(ensure(c->cztab, cz_table_elems(g, (int)n - 1, (int)n) * sizeof(cplx)));
+    RC(ensure(c->status, B * sizeof(int)));
+    CzArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tm = in_rev;
+    a.tm_sstride = n;
+    a.ent[0] = 0;
+    a.ent[1] = 0;
+    a.npoly = 1;
+    a.deg = (int)n - 1;
+    a.B = (int)B;
+    a.M = (int)n;
+    a.lwr = 0.0;
+    a.lwi = (double)sign * 2.0 * 3.14159265358979323846 / (double)n;
+    a.dft_n = (int)n;
+    a.ybuf = (cplx *)c->ybuf.p;
+    a.vhat = (cplx *)c->vhat.p;
+    a.T = ctx_tw(c);
+    a.mode = FNFTB_CZ_RAW;
+    a.out = out;
+    a.out_sstride = n;
+    a.status = (int *)c->status.p;
+    // the first-generation row kernels (table twiddles, ~1e-15) rather than the register-derived twiddles of the
+    // fast row kernel (~1e-12): the spectral factorisation takes logarithms and exponentials of these transforms
+    RC(cz_run_exact(a, (cplx *)c->cztab.p, c->st));
+    return 0;
+}
+

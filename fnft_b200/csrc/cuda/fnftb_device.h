@@ -233,6 +233,26 @@ int fnftb_newton(fnftb_ctx *ctx, const fnftb_bound_desc *desc, const int32_t *K_
 int fnftb_normconsts(fnftb_ctx *ctx, const fnftb_bound_desc *desc, const int32_t *K_host,
                      const void *lam_host, void *a_host, void *ap_host, void *b_host);
 
+/* ---- inverse transform (inverse_api.cu) ------------------------------------------------- */
+/* fast inverse scattering of B transfer matrices [B][4][deg+1] -> q [B][deg] (deg = power of two <= 32768, degree-1
+ * discretizations; modal = 1: 2SPLIT2_MODAL, 0: 2SPLIT2A); status_host[b] = 1 where |Q| >= 1 (kappa = -1) */
+int fnftb_finvscatter(fnftb_ctx *ctx, size_t B, size_t deg, const void *tm, void *q, double eps_t, int kappa,
+                      int modal, int on_device, int32_t *status_host);
+/* Darboux transforms: K solitons per signal (bs sorted by descending imaginary part, nc norming constants, host
+ * [B][K]) added to zero (seed = 0) or to the potential in q (seed = 1); q [B][D] */
+int fnftb_inv_add_solitons(fnftb_ctx *ctx, size_t B, size_t K, size_t D, const void *bs, const void *nc, void *q,
+                           double T0, double T1, int zc_point, int seed, int q_on_device);
+/* transfer matrices [B][4][deg+1] (kept on the device for fnftb_finvscatter_staged) from continuous spectra, and
+ * spectral factorisation; see inverse_api.cu */
+int fnftb_inv_tm_from_contspec(fnftb_ctx *ctx, size_t B, size_t M, size_t D, size_t deg, const void *contspec_host,
+                               int cstype, int kappa, double eps_t, size_t oversampling, int32_t *warn_host);
+int fnftb_inv_tm_ab_from_iter(fnftb_ctx *ctx, size_t D, const void *contspec_host, int kappa, size_t max_iter,
+                              int32_t *hit_max, int32_t *warn_host);
+int fnftb_finvscatter_staged(fnftb_ctx *ctx, size_t B, size_t deg, void *q_host, double eps_t, int kappa, int modal,
+                             int32_t *status_host);
+int fnftb_specfact(fnftb_ctx *ctx, size_t B, size_t deg, const void *poly_host, void *result_host, size_t oversampling,
+                   int kappa, int32_t *warn_host);
+
 /* DFMA throughput of the context's device in TFLOP/s (probe kernel, ~10 ms); 0 on failure */
 double fnftb_probe_fp64_tflops(fnftb_ctx *ctx);
 

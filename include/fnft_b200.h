@@ -428,6 +428,57 @@ void fnft_b200_release(void);
 /* Measured DFMA throughput (TFLOP/s) of the calling thread's device: the FP64 roofline denominator. */
 double fnft_b200_probe_fp64_tflops(void);
 
+/* ---- inverse NFT (include/fnft_nsev_inverse.h) --------------------------------------- */
+typedef enum {
+    fnft_nsev_inverse_cstype_REFLECTION_COEFFICIENT,
+    fnft_nsev_inverse_cstype_B_OF_XI,
+    fnft_nsev_inverse_cstype_B_OF_TAU
+} fnft_nsev_inverse_cstype_t; /* include/fnft_nsev_inverse.h:54-58 */
+typedef enum {
+    fnft_nsev_inverse_dstype_NORMING_CONSTANTS,
+    fnft_nsev_inverse_dstype_RESIDUES
+} fnft_nsev_inverse_dstype_t; /* :72-75 */
+typedef enum {
+    fnft_nsev_inverse_csmethod_DEFAULT,
+    fnft_nsev_inverse_csmethod_TFMATRIX_CONTAINS_REFL_COEFF,
+    fnft_nsev_inverse_csmethod_TFMATRIX_CONTAINS_AB_FROM_ITER,
+    fnft_nsev_inverse_csmethod_USE_SEED_POTENTIAL_INSTEAD
+} fnft_nsev_inverse_csmethod_t; /* :105-110 */
+typedef struct {
+    fnft_nse_discretization_t discretization;
+    fnft_nsev_inverse_cstype_t contspec_type;
+    fnft_nsev_inverse_csmethod_t contspec_inversion_method;
+    fnft_nsev_inverse_dstype_t discspec_type;
+    FNFT_UINT max_iter;
+    FNFT_UINT oversampling_factor;
+} fnft_nsev_inverse_opts_t; /* :151-158, 32 bytes on LP64 */
+fnft_nsev_inverse_opts_t fnft_nsev_inverse_default_opts(void); /* :168 */
+FNFT_INT fnft_nsev_inverse_XI(const FNFT_UINT D, FNFT_REAL const *const T, const FNFT_UINT M, FNFT_REAL *const XI,
+                              const fnft_nse_discretization_t discretization); /* :187-190 */
+/* include/fnft_nsev_inverse.h:258-263, src/fnft_nsev_inverse.c:121-249.  Like the reference, contspec is modified
+ * in place (boundary phase factors, Blaschke precompensation). */
+FNFT_INT fnft_nsev_inverse(const FNFT_UINT M, FNFT_COMPLEX *const contspec, FNFT_REAL const *const XI,
+                           FNFT_UINT const K, FNFT_COMPLEX const *const bound_states,
+                           FNFT_COMPLEX const *const normconsts_or_residues, const FNFT_UINT D,
+                           FNFT_COMPLEX *const q, FNFT_REAL const *const T, const FNFT_INT kappa,
+                           fnft_nsev_inverse_opts_t *opts_ptr);
+/* NEW: B independent inverse transforms with shared M, XI, K, D, T, kappa and options; row-major arrays
+ * contspec[b*M + i] (may be NULL), bound_states[b*K + i], normconsts_or_residues[b*K + i], q[b*D + n];
+ * ret_codes[b] (may be NULL) receives the per-signal code. */
+FNFT_INT fnft_nsev_inverse_batch(const FNFT_UINT B, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                                 FNFT_REAL const *const XI, FNFT_UINT const K,
+                                 FNFT_COMPLEX const *const bound_states,
+                                 FNFT_COMPLEX const *const normconsts_or_residues, const FNFT_UINT D,
+                                 FNFT_COMPLEX *const q, FNFT_REAL const *const T, const FNFT_INT kappa,
+                                 fnft_nsev_inverse_opts_t const *opts_ptr, FNFT_INT *ret_codes);
+/* include/private/fnft__nse_finvscatter.h:61-63, src/private/fnft__nse_finvscatter.c:243-366 */
+FNFT_INT fnft__nse_finvscatter(const FNFT_UINT deg, FNFT_COMPLEX *const transfer_matrix, FNFT_COMPLEX *const q,
+                               const FNFT_REAL eps_t, const FNFT_INT kappa,
+                               const fnft_nse_discretization_t discretization);
+/* include/private/fnft__poly_specfact.h:62-66, src/private/fnft__poly_specfact.c:25-147 */
+FNFT_INT fnft__poly_specfact(const FNFT_UINT deg, FNFT_COMPLEX const *const poly, FNFT_COMPLEX *const result,
+                             const FNFT_UINT oversampling_factor, const FNFT_INT kappa);
+
 #ifdef __cplusplus
 }
 #endif

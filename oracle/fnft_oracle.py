@@ -829,6 +829,93 @@ def fftgridsearch_windows(p, PHI, M, idx, evaluate):
     return np.where(ok, zr, np.nan + 0j)
 
 
+def poly_specfact(poly, oversampling_factor, kappa):
+    """poly_specfact, src/private/fnft__poly_specfact.c:25-147 (cepstral spectral factorisation, Dumitrescu B.4):
+    log-magnitude on an oversampled grid (:76-108), Hilbert transform including the zeroed bin M/2 - 1 (:116-121),
+    exponential, truncation (:130-137).  numpy's FFT at the reference's length kiss_fft_next_fast_size((deg+1) *
+    oversampling); pinned to the reference to 1e-15 where that length is a power of two -- at other lengths the
+    reference's Kiss FFT (radix-3 / radix-5 butterflies) is itself only accurate to ~1e-12, which the logarithm and
+    exponential turn into 2e-11 (tests/test_oracle.py::test_specfact_vs_reference_runs)."""
+    poly = np.asarray(poly, dtype=np.complex128)
+    deg = poly.shape[0] - 1
+    M = next_fast_size((deg + 1) * oversampling_factor)
+    buf = np.zeros(M, dtype=np.complex128)
+    buf[:deg + 1] = poly
+    ab = np.abs(np.fft.fft(buf))
+    if kappa == 0:
+        x = np.log(ab + 0j)
+    else:
+        x = 0.5 * np.log(1.0 - kappa * ab * ab + 0j)
+    X = np.fft.fft(x)
+    X[0] = 0.0
+    X[1:M // 2 - 1] *= -1j / M
+    X[M // 2 - 1] = 0.0
+    X[M // 2:] *= 1j / M
+    y = np.fft.ifft(X) * M                      # unnormalised inverse transform
+    out = np.fft.ifft(np.exp(x - 1j * y) / M) * M
+    return np.conj(out[deg::-1])
+
+
+def nse_finvscatter(tm, eps_t, kappa, nse_disc):
+    """nse_finvscatter, src/private/fnft__nse_finvscatter.c:70-366, for 2SPLIT2A / 2SPLIT2_MODAL.  tm: [4][deg+1],
+    highest power first.  The reference splits the samples recursively and multiplies polynomial matrices with FFTs;
+    the base case (:157-196) reads Q = -kappa conj(T21(0) / T11(0)), q = atan|Q| e^{i arg Q} / eps_t (2SPLIT2A) or
+    Q / eps_t (modal), and the inverse of the one-sample matrix is c [[z, -Q z], [kappa conj(Q), 1]], c = (1 + kappa
+    |Q|^2)^(-1/2).  Restated here as plain layer peeling (one sample per step, O(D^2)): the same arithmetic in exact
+    terms, only practical for small D.  Returns q[deg]."""
+    tm = np.asarray(tm, dtype=np.complex128).reshape(4, -1)
+    n = tm.shape[1] - 1
+    R = [tm[e, ::-1].copy() for e in range(4)]          # by power of z
+    q = np.zeros(n, dtype=np.complex128)
+    for k in range(n):
+        Q = -kappa * np.conj(R[2][0] / R[0][0])
+        den = 1.0 + kappa * abs(Q) ** 2
+        if den <= 0:
+            raise ValueError("A reconstruced sample violates the condition |q[n]|<1.")   # :172-176
+        c = 1.0 / np.sqrt(den)
+        q[n - 1 - k] = Q / eps_t if nse_disc == NSE_2SPLIT2_MODAL else np.arctan(abs(Q)) * np.exp(1j * np.angle(Q)) / eps_t
+        m = n - k
+        new = [c * (R[0][:m] - Q * R[2][:m]), c * (R[1][:m] - Q * R[3][:m]),
+               c * (kappa * np.conj(Q) * R[0][1:m + 1] + R[2][1:m + 1]),
+               c * (kappa * np.conj(Q) * R[1][1:m + 1] + R[3][1:m + 1])]
+        R = new
+    return q
+
+
+def nsev_inverse_pure_solitons(bound_states, normconsts, D, T, residues=False):
+    """fnft_nsev_inverse without a continuous spectrum, src/fnft_nsev_inverse.c:680-846: sort by descending imaginary
+    part (:741-752), residues -> norming constants (:764-789), then per sample the recursion over rho_k (:808-846)."""
+    bs = np.array(bound_states, dtype=np.complex128)
+    nc = np.array(normconsts, dtype=np.complex128)
+    K = bs.shape[0]
+    for i in range(K):                                   # the reference's exchange sort
+        for j in range(i + 1, K):
+            if bs[i].imag < bs[j].imag:
+                bs[i], bs[j] = bs[j], bs[i]
+                nc[i], nc[j] = nc[j], nc[i]
+    if residues:
+        for i in range(K):
+            tmp = 1.0 + 0j
+            for j in range(K):
+                if j != i:
+                    tmp = tmp * (bs[i] - bs[j]) / (bs[i] - np.conj(bs[j]))
+            nc[i] = (nc[i] / (2j * bs[i].imag)) * tmp
+    eps_t = (T[1] - T[0]) / (D - 1)
+    t = T[0] + eps_t * np.arange(D)
+    zc = int(np.argmax(t >= 0.0)) if (t >= 0.0).any() else 0
+    right = np.arange(D) >= zc
+    rhok = [np.where(right, nc[i] * np.exp(2j * bs[i] * t), (1 / nc[i]) * np.exp(-2j * bs[i] * t)) for i in range(K)]
+    qt = np.zeros(D, dtype=np.complex128)
+    for i in range(K):
+        rho = rhok[i]
+        f = (2j * bs[i].imag) / (1 + np.abs(rho) ** 2)
+        qt = qt + 2j * np.conj(rho) * f
+        for j in range(i + 1, K):
+            rhok[j] = ((bs[j] - bs[i]) * rhok[j] + (rhok[j] - rho) * f) / \
+                      (bs[j] - np.conj(bs[i]) - (1 + np.conj(rho) * rhok[j]) * f)
+    return np.where(right, qt, np.conj(qt))
+
+
 def misc_rel_err(num, exact):
     """misc_rel_err, src/private/fnft__misc.c:41-51 -- THE parity metric."""
     num = np.asarray(num)

@@ -20,7 +20,8 @@ ok=0; bad=0
 for src in $REF/test/fnft__poly/fnft__poly_fmult*.c $REF/test/fnft__poly/fnft__poly_chirpz_test.c \
            $REF/test/fnft__poly/fnft__poly_eval_test.c $REF/test/fnft__poly/fnft__poly_roots_fasteigen_test.c \
            $REF/test/fnft__akns_fscatter/*.c $REF/test/fnft__nse_scatter/fnft__nse_scatter_bound_states_test_bo.c \
-           $REF/test/fnft_version_test.c "$@"; do
+           $REF/test/fnft_version_test.c $REF/test/fnft__nse_finvscatter/*.c $REF/test/fnft__poly/fnft__poly_specfact_test*.c \
+           $REF/test/fnft_nsev_inverse/*.c $REF/test/fnft_nsev_inverse/*/*.c "$@"; do
   name=$(basename "$src" .c)
   if gcc -std=gnu99 -O1 -w $INC "$src" -Lfnft_b200/lib -lfnft -lm -Wl,-rpath,'$ORIGIN/../../fnft_b200/lib' \
          -o $OUT/$name 2> $OUT/$name.linkerr; then
