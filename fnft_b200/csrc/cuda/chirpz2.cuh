@@ -30,6 +30,10 @@ struct Cz2SymSrc {
     const double *mx;  // [B] max|coeff| -> pending power-of-two scale
     int *W;            // [B] the exponent of that scale is added here (what blk_tree_final does)
     int d_full, kappa, normalize;
+    // fused = 1: the coefficients do not exist yet -- `up` describes the pending column pass of the last tree level
+    // (tree_up.cuh: k_up_cols, last = 1) and k_up_cols_cz computes them on the way into the first chirp-z stage
+    int fused;
+    UpArgs up;
 };
 
 struct Cz2Args {
@@ -59,6 +63,18 @@ static inline int cz2_rows_for(size_t need)
 static inline bool cz2_supported(int deg, int M)
 {
     return cz2_rows_for((size_t)deg + (size_t)M) != 0 && FNFTB_CZ2_ROW_L2 + 4 <= FNFTB_TW_MAXL;
+}
+
+// can the last column pass of the spectrum-carry tree (radix RT = 2^(l2n - 12) across rows of 4096) be fused with the
+// forward column pass of the chirp-z (RC rows)?  Needs an unpadded product (deg == d_full, i.e. D a power of two) and
+// one of the instantiated (RT, RC) pairs
+static inline bool cz2_fused_cols_supported(const UpArgs &u, int deg, int M, int d_full)
+{
+    if (deg != d_full || u.l2row != FNFTB_CZ2_ROW_L2 || deg != (1 << u.l2n))
+        return false;
+    const int RT = 1 << (u.l2n - u.l2row), RC = cz2_rows_for((size_t)deg + (size_t)M);
+    return (RT == 2 && (RC == 3 || RC == 4)) || (RT == 4 && (RC == 6 || RC == 8)) ||
+           (RT == 8 && (RC == 12 || RC == 16));
 }
 
 // kernels instantiated in k_chirpz2.cu only
@@ -260,6 +276,83 @@ __global__ void __launch_bounds__(256, 3) k_cz2_cols_fwd(const Cz2Args a)
 #pragma unroll
     for (int q = 0; q < R; ++q)
         dst[((size_t)Cz2Radix<R>::row(q) << FNFTB_CZ2_ROW_L2) + o] = v[q];
+}
+
+// FUSED (round 2): last column pass of the product tree + first chirp-z stage.  k_up_cols<RT> (last level) turns
+// column o of the row-split workspace into the coefficients g[o + n*4096], n < RT (+ g[N] from the tops for o = 0);
+// k_cz2_cols_fwd<RC> needs, for chirp column o', the coefficients g[N - n] (polynomial a) or g[n] (polynomial b) with
+// n = o' + n1*4096: for b that is the thread's own column (o' = o), for a it is column o' = (4096 - o) mod 4096 with the
+// rows in reverse order -- either way every value a thread needs it has just computed.  The coefficients are never
+// written (2 MB per signal less DRAM traffic each way).  No scaling by max|c| here: the max over the whole matrix is
+// not known before all CTAs have finished, powers of two commute with everything, and rho = b / a does not see it; the
+// exponent W[s] keeps describing the values that flow on (the epilogue multiplies a and b by 2^W).
+template <int RT, int RC>
+__global__ void __launch_bounds__(256, 3) k_up_cols_cz(const Cz2Args a)
+{
+    constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2;
+    constexpr int LR = Log2R<RT>::value;
+    const UpArgs &u = a.src.up;
+    const CzArgs &c = a.c;
+    const int l2n = u.l2n, l2row = l2n - LR;
+    const int N = 1 << l2n;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = (int)(gid & (N2 - 1));
+    const size_t arr = (size_t)(gid >> l2row);  // = 2 * signal + which (one pair per signal on the last level)
+    const int which = (int)(arr & 1);
+    const size_t sp = arr >> 1;
+    const Low2Tops Tn = ((const Low2Tops *)u.tt_out)[sp];
+    const cplx *w = u.ws + arr * (size_t)N;
+    const cplx *pt = u.tw.base + u.tw.pass_off[l2n][LR];
+    const double invN = 1.0 / (double)N;
+    if (u.pf > 0 && threadIdx.x < RT) {  // the RT column segments of the CTA `pf` places ahead
+        const size_t bp = (size_t)blockIdx.x + (size_t)u.pf;
+        if (bp < gridDim.x) {
+            const long long g0 = (long long)bp * blockDim.x;
+            const cplx *wp = u.ws + (size_t)(g0 >> l2row) * (size_t)N + (size_t)(g0 & ((1 << l2row) - 1));
+            l2_prefetch(wp + ((size_t)brev_c((int)threadIdx.x, LR) << l2row), blockDim.x * (unsigned)sizeof(cplx));
+        }
+    }
+    cplx g[RT];
+#pragma unroll
+    for (int q = 0; q < RT; ++q)
+        g[q] = w[o + ((size_t)brev_c(q, LR) << l2row)];
+    up_twiddle_mul<RT, true>(g, pt, 1 << l2row, o);
+    Dft<RT, +1>::run(g);
+#pragma unroll
+    for (int n = 0; n < RT; ++n)
+        g[n] = cscale(g[n], invN);
+    if (o == 0)
+        g[0] = up_bot(Tn, which);
+    const cplx gtop = up_top(Tn, which);  // g[N], used by the column-0 thread only
+    // ---- first chirp-z stage: y_n = x_n * tab_y[n], radix-RC DIF pass across the rows
+    const int Np = c.deg + 1;
+    const int oc = which ? o : ((N2 - o) & (N2 - 1));  // chirp column this thread feeds
+    const double fb = -(double)a.src.kappa;
+    cplx v[RC];
+#pragma unroll
+    for (int n1 = 0; n1 < RC; ++n1) {
+        const int n = oc + n1 * N2;
+        cplx x = czero();
+        if (n < Np) {
+            if (which) {  // H21[deg - n] = -kappa conj(b[n])
+                const cplx b = (n1 < RT) ? g[n1 < RT ? n1 : 0] : gtop;  // n1 == RT only occurs for o == 0 (n == N)
+                x = make_cplx(b.x * fb, -b.y * fb);
+            } else {      // H11[deg - n] = a[N - n]
+                if (o == 0)
+                    x = (n1 == 0) ? gtop : g[(RT - n1) >= 0 && (RT - n1) < RT ? RT - n1 : 0];
+                else
+                    x = g[(RT - 1 - n1) >= 0 ? RT - 1 - n1 : 0];
+            }
+            x = cmul(x, __ldg(&c.tab_y[n]));
+        }
+        v[n1] = x;
+    }
+    DftAny<RC, -1>::run(v);
+    cz2_col_twiddle<RC, false>(v, a, oc);
+    cplx *dst = c.ybuf + arr * (size_t)a.L;
+#pragma unroll
+    for (int q = 0; q < RC; ++q)
+        dst[((size_t)Cz2Radix<RC>::row(q) << FNFTB_CZ2_ROW_L2) + oc] = v[q];
 }
 
 // grid.x = narr * R rows, 128 threads, 64 KiB shared memory
@@ -646,7 +739,21 @@ int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2S
             return rc;
     }
     a.gen_v = 0;
-    CZ2_BY_R(k_cz2_cols_fwd, a, (unsigned)(narr * cols1), "cz_cols_fwd");
+    if (a.src.fused) {
+        const int RT = 1 << (a.src.up.l2n - a.src.up.l2row);
+        const unsigned grid = (unsigned)(narr * cols1);
+        switch (RT * 100 + R) {
+        case 203: rc = cz2_launch(k_up_cols_cz<2, 3>, a, grid, 256, 0, st, "tree_up_cols_cz"); break;
+        case 204: rc = cz2_launch(k_up_cols_cz<2, 4>, a, grid, 256, 0, st, "tree_up_cols_cz"); break;
+        case 406: rc = cz2_launch(k_up_cols_cz<4, 6>, a, grid, 256, 0, st, "tree_up_cols_cz"); break;
+        case 408: rc = cz2_launch(k_up_cols_cz<4, 8>, a, grid, 256, 0, st, "tree_up_cols_cz"); break;
+        case 812: rc = cz2_launch(k_up_cols_cz<8, 12>, a, grid, 256, 0, st, "tree_up_cols_cz"); break;
+        case 816: rc = cz2_launch(k_up_cols_cz<8, 16>, a, grid, 256, 0, st, "tree_up_cols_cz"); break;
+        default: return -1065;  // cz2_fused_cols_supported said yes for a pair that is not instantiated
+        }
+    } else {
+        CZ2_BY_R(k_cz2_cols_fwd, a, (unsigned)(narr * cols1), "cz_cols_fwd");
+    }
     if (rc)
         return rc;
     rc = cz2_launch(k_cz2_rows, a, (unsigned)(narr * (size_t)R), 128, smem, st, "cz_rows");

@@ -139,7 +139,7 @@ struct fnftb_ctx {
     // tree workspace
     Buf lev0, lev1, mx0, mx1, gbuf, colbuf, W, status, tm, tt0, tt1, twmem;
     TwSet tws;
-    TreeDeferred deferred = {0, 0, 0, 0, 0, 0, 0, 0};  // pending blk_tree_final (see ctx_finalize)
+    TreeDeferred deferred = {};  // pending blk_tree_final (see ctx_finalize)
     // result description
     size_t deg = 0;        // degree of the transfer matrices held in tm
     size_t tmB = 0;        // number of matrices held
@@ -560,6 +560,7 @@ static int ctx_finalize(fnftb_ctx *c)
 {
     if (!c->deferred.valid)
         return 0;
+    RC(tree_finish_cols(c->deferred, c->st));
     const TreeDeferred &f = c->deferred;
     RC(tree_finalize(tree_work(c), f.cur, f.B, f.d_full, f.deg_out, f.normalize, (cplx *)c->tm.p, c->st,
                      f.sym, f.kappa));
@@ -590,7 +591,7 @@ int fnftb_fscatter(fnftb_ctx *c, const fnftb_scatter_desc *d)
                      d->scheme, d->eps_t, d->normalize, (cplx *)c->tm.p, T, c->st, 1, FNFTB_TREE_SMEM_N,
                      (knob_defer && d->defer_final) ? &c->deferred : nullptr));
     if (!(knob_defer && d->defer_final))
-        c->deferred.valid = 0;
+        c->deferred.valid = c->deferred.cols_pending = 0;
     c->deg = deg_out;
     c->tmB = c->B;
     c->tm_entries = 4;
@@ -612,7 +613,7 @@ int fnftb_fmult2x2(fnftb_ctx *c, size_t deg, size_t n, const void *p_host, int n
     const TwTable T = ctx_tw(c);
     RC(tree_fmult2x2(tree_work(c), (const cplx *)c->pbuf.p, (int)n, (int)deg, normalize,
                      (cplx *)c->tm.p, T, c->st));
-    c->deferred.valid = 0;
+    c->deferred.valid = c->deferred.cols_pending = 0;
     c->deg = deg * n;
     c->tmB = 1;
     c->tm_entries = 4;
@@ -658,7 +659,7 @@ int fnftb_set_polynomial(fnftb_ctx *c, size_t deg, const void *p_host)
     CU(cudaMemcpyAsync(c->tm.p, p_host, (deg + 1) * sizeof(cplx), cudaMemcpyHostToDevice, c->st));
     CU(cudaMemsetAsync(c->W.p, 0, sizeof(int), c->st));
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->st));
-    c->deferred.valid = 0;
+    c->deferred.valid = c->deferred.cols_pending = 0;
     c->deg = deg;
     c->tmB = 1;
     c->tm_entries = 1;
@@ -748,6 +749,17 @@ int fnftb_contspec(fnftb_ctx *c, const fnftb_contspec_desc *d, void *out, size_t
                 src.d_full = f.d_full;
                 src.kappa = f.kappa;
                 src.normalize = f.normalize;
+                if (f.cols_pending) {
+                    // the last column pass of the tree and the first chirp-z stage in one kernel, when that
+                    // combination of radices exists; otherwise the column pass runs now
+                    if (cz2_fused_cols_supported(f.cols, (int)c->deg, (int)d->M, f.d_full)) {
+                        src.fused = 1;
+                        src.up = f.cols;
+                        c->deferred.cols_pending = 0;
+                    } else {
+                        RC(tree_finish_cols(c->deferred, c->st));
+                    }
+                }
                 c->deferred.valid = 0;  // the exponent of the last matrix is added to W by the kernel
             } else {
                 RC(ctx_finalize(c));
@@ -1717,7 +1729,7 @@ int fnftb__pair2x2_prepare(fnftb_ctx *c, size_t B, size_t d, cplx **lev0)
         return fail(-6, "pair product: degree must be a power of two <= 32768", __FILE__, __LINE__);
     CU(cudaSetDevice(c->device));
     RC(ensure_tree(c, B, 2, d, 2 * d));
-    c->deferred.valid = 0;
+    c->deferred.valid = c->deferred.cols_pending = 0;
     c->tmB = 0;
     *lev0 = (cplx *)c->lev0.p;
     return 0;

@@ -312,7 +312,19 @@ struct TreeDeferred {
     int valid;          // 1: finalisation pending, fields below describe it
     int cur;            // level buffer holding the single matrix per signal
     int B, d_full, deg_out, normalize, sym, kappa;
+    // the column pass of the last (row-split) level has not run yet: either the chirp-z fuses it with its first
+    // stage (k_up_cols_cz) or tree_finish_cols launches it
+    int cols_pending;
+    UpArgs cols;
 };
+
+static inline int tree_finish_cols(TreeDeferred &f, fnftb_stream_t st)
+{
+    if (!f.cols_pending)
+        return 0;
+    f.cols_pending = 0;
+    return up_cols_pending(f.cols, st);
+}
 
 static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, int deg_out,
                                 int normalize, cplx *tm, fnftb_stream_t st, int sym = 0, int kappa = 0)
@@ -425,9 +437,16 @@ static inline int tree_fscatter(const TreeWork &w, const cplx *q, const cplx *r,
                     ua.kappa = kappa;
                     ua.last = (n == 2) ? 1 : 0;
                     ua.tw = *(const TwSet *)w.tws;
-                    rc = up_level(ua, knob_up_smem, st);
+                    UpArgs pend;
+                    memset(&pend, 0, sizeof(pend));
+                    static const int knob_fuse = tree_knob("FNFT_B200_FUSE_COLS_CZ", 1);
+                    rc = up_level(ua, knob_up_smem, st, true, (defer && ua.last && knob_fuse) ? &pend : nullptr);
                     if (rc)
                         return rc;
+                    if (defer) {
+                        defer->cols_pending = (pend.B != 0) ? 1 : 0;
+                        defer->cols = pend;
+                    }
                     cur = 1 - cur;
                 }
                 if (defer) {  // first-row-only result stays in the level buffer

@@ -498,16 +498,18 @@ DEV void up_row_passes(cplx *S, const TwSet &tw, int tid, int nt)
 // ---------------------------------------------------------------------------------------
 // whole level in shared memory: grid.x = B * npairs * 2, blockDim.x = N / 32
 // ---------------------------------------------------------------------------------------
+// spectrum positions per thread of k_up_smem: 32 (168 registers) for N = 2048 / 4096, 16 (128 registers, 512 threads)
+// for N = 8192, whose single CTA per SM then has 16 warps (measured with the L2 prefetch on: 5.03 -> 4.84 ms per 4096
+// signals; for the smaller N 16 positions per thread lose: 3.53 -> 3.73, 4.01 -> 5.20)
 #ifndef FNFTB_UP_TPP
-#define FNFTB_UP_TPP 32  // spectrum positions per thread of k_up_smem: 32 (168 registers) or 16 (128 registers, 16 warps per SM)
+#define FNFTB_UP_TPP(L2N) (((L2N) == 13) ? 16 : 32)
 #endif
 template <int L2N, bool SYM>
-__global__ void __launch_bounds__((1 << L2N) / FNFTB_UP_TPP,
-                                  (FNFTB_UP_TPP == 32) ? ((L2N == 11) ? 6 : ((L2N == 12) ? 3 : 1))
-                                                       : ((L2N == 11) ? 4 : ((L2N == 12) ? 2 : 1))) k_up_smem(const UpArgs a)
+__global__ void __launch_bounds__((1 << L2N) / FNFTB_UP_TPP(L2N), (L2N == 11) ? 6 : ((L2N == 12) ? 3 : 1))
+    k_up_smem(const UpArgs a)
 {
     constexpr int E = UpT<SYM>::E;
-    constexpr int N = 1 << L2N, NT = N / FNFTB_UP_TPP;
+    constexpr int N = 1 << L2N, NT = N / FNFTB_UP_TPP(L2N);
     constexpr int RX = (L2N == 12) ? 16 : 8;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__((1 << L2N) / FNFTB_UP_TPP,
     }
 #if FNFTB_UP_PIPE
     // X stage over all N positions; the half regions carry (-1)^k = +1 / -1
-    const UpPair<SYM> P = up_x_stage_pipe<RX, SYM, FNFTB_UP_TPP, FNFTB_UP_PIPE_G, FNFTB_UP_PIPE_DEPTH>(a, sp, s, which, which == 0, 0, 0, N / 2,
+    const UpPair<SYM> P = up_x_stage_pipe<RX, SYM, FNFTB_UP_TPP(L2N), FNFTB_UP_PIPE_G, FNFTB_UP_PIPE_DEPTH>(a, sp, s, which, which == 0, 0, 0, N / 2,
                                                                                         1.0, S, tid, NT);
 #else
     const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0);
@@ -743,8 +745,32 @@ static inline int up_pf_distance(int family)
     return dist[family];
 }
 
+// launches the column pass of a row-split level (a.l2row, a.pf set)
 template <bool SYM>
-static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
+static inline int up_cols_launch(const UpArgs &a, cudaStream_t st)
+{
+    constexpr int E = UpT<SYM>::E;
+    const int npairs = a.n_in / 2;
+    const int l2R = a.l2n - a.l2row;
+    const unsigned grid_cols = (unsigned)(((size_t)a.B * npairs * E << a.l2row) / 256);
+    switch (l2R) {
+    case 1: return up_launch(k_up_cols<2, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols");
+    case 2: return up_launch(k_up_cols<4, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols");
+    case 3: return up_launch(k_up_cols<8, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols");
+    case 4: return up_launch(k_up_cols<16, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols");
+    case 5: return up_launch(k_up_cols<32, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols");
+    default:
+        if (!a.last)
+            return -1064;  // radix 64 only exists for the last level (coefficient output)
+        return up_launch(k_up_cols<64, SYM>, a, grid_cols * 2, 128, 0, st, "tree_up_cols");
+    }
+}
+
+// pending_cols (SYM, last level, row split only): the column pass is NOT launched; *pending_cols receives its
+// arguments so that the caller can fuse it with the first chirp-z stage (chirpz2.cuh: k_up_cols_cz) or run it
+// later with up_cols_pending
+template <bool SYM>
+static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st, UpArgs *pending_cols = nullptr)
 {
     constexpr int E = UpT<SYM>::E;
     const int npairs = a.n_in / 2;
@@ -756,9 +782,9 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
         const size_t smem = sizeof(cplx) * N + 64 * sizeof(double);
         a.pf = up_pf_distance(UP_PF_SMEM11 + (a.l2n - 11));
         switch (a.l2n) {
-        case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 2048 / FNFTB_UP_TPP, smem, st, names_s[0]);
-        case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 4096 / FNFTB_UP_TPP, smem, st, names_s[1]);
-        default: return up_launch(k_up_smem<13, SYM>, a, grid, 8192 / FNFTB_UP_TPP, smem, st, names_s[2]);
+        case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 2048 / FNFTB_UP_TPP(11), smem, st, names_s[0]);
+        case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 4096 / FNFTB_UP_TPP(12), smem, st, names_s[1]);
+        default: return up_launch(k_up_smem<13, SYM>, a, grid, 8192 / FNFTB_UP_TPP(13), smem, st, names_s[2]);
         }
     }
     a.l2row = FNFTB_UP_ROW_L2;
@@ -770,30 +796,24 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st)
     if (rc)
         return rc;
     a.pf = up_pf_distance(UP_PF_COLS);
-    const unsigned grid_cols = (unsigned)(((size_t)a.B * npairs * E << a.l2row) / 256);
-    switch (l2R) {
-    case 1: rc = up_launch(k_up_cols<2, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    case 2: rc = up_launch(k_up_cols<4, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    case 3: rc = up_launch(k_up_cols<8, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    case 4: rc = up_launch(k_up_cols<16, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    case 5: rc = up_launch(k_up_cols<32, SYM>, a, grid_cols, 256, 0, st, "tree_up_cols"); break;
-    default:
-        if (!a.last)
-            return -1064;  // radix 64 only exists for the last level (coefficient output)
-        rc = up_launch(k_up_cols<64, SYM>, a, grid_cols * 2, 128, 0, st, "tree_up_cols");
-        break;
+    if (SYM && a.last && pending_cols != nullptr && l2R <= 5) {
+        *pending_cols = a;
+        return 0;
     }
+    rc = up_cols_launch<SYM>(a, st);
     if (rc || a.last)
         return rc;
     a.pf = up_pf_distance(UP_PF_ROWS_C);
     return up_launch(k_up_rows_c<128, SYM>, a, grid_rows, 128, smem, st, "tree_up_rows_c");
 }
 
-int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym)
+int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym, UpArgs *pending_cols)
 {
-    return sym ? up_level_t<true>(a, l2smem_max, st) : up_level_t<false>(a, l2smem_max, st);
+    return sym ? up_level_t<true>(a, l2smem_max, st, pending_cols) : up_level_t<false>(a, l2smem_max, st);
 }
+int up_cols_pending(const UpArgs &a, cudaStream_t st) { return up_cols_launch<true>(a, st); }
 #else
-int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym = true);
+int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym = true, UpArgs *pending_cols = nullptr);
+int up_cols_pending(const UpArgs &a, cudaStream_t st);
 #endif
 #endif  // !FNFTB_EMUL
