@@ -87,6 +87,24 @@ HD cplx chirp_dft(long long k, int n, double sign)
     return cispi(sign * (double)m / (double)n);
 }
 
+// (column, row) of element idx of a [C columns][N1 rows] tile that lives column-major in shared memory (columns
+// N1 * 16 bytes apart: a multiple of the 128-byte bank period) and row-major in global memory.  With consecutive
+// lanes on consecutive columns every lane of a warp hits the same banks (round 1 ncu: 62 % of the shared-memory
+// wavefronts of blk_cz_cols_inv were conflicts).  Here a warp covers 4 columns x 8 rows: the 8 rows fill one 128-byte
+// bank period and the 4 columns cost the 4 wavefronts that 512 bytes need anyway, while the global accesses are
+// 64-byte segments (two full sectors).
+HD void cz_tile_index(int idx, int log2C, int N1, int *c, int *row)
+{
+    if (log2C >= 2 && N1 >= 8) {
+        const int hi = idx >> 5;
+        *c = (idx & 3) | ((hi & ((1 << (log2C - 2)) - 1)) << 2);
+        *row = ((idx >> 2) & 7) | ((hi >> (log2C - 2)) << 3);
+    } else {
+        *c = idx & ((1 << log2C) - 1);
+        *row = idx >> log2C;
+    }
+}
+
 // fills the signal-independent tables; grid covers max(deg+1, M, L) elements
 BLK void blk_cz_tables(const CzArgs &a, blk3 bid, int nt, void *)
 {
@@ -187,7 +205,8 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
     FOR_THREADS(tid, nt)
     {
         for (int idx = tid; idx < C * N1; idx += nt) {
-            const int c = idx & (C - 1), n1 = idx >> a.log2C;
+            int c, n1;
+            cz_tile_index(idx, a.log2C, N1, &c, &n1);
             const long long n = (long long)n1 * N2 + n2_0 + c;
             cplx v = czero();
             if (!a.gen_v) {
@@ -216,7 +235,8 @@ BLK void blk_cz_cols_fwd(const CzArgs &a, blk3 bid, int nt, void *smem)
     {
         cplx *dst = (a.gen_v ? a.vhat : a.ybuf + (size_t)sj * a.L);
         for (int idx = tid; idx < C * N1; idx += nt) {
-            const int c = idx & (C - 1), pos = idx >> a.log2C;
+            int c, pos;
+            cz_tile_index(idx, a.log2C, N1, &c, &pos);
             const int n2 = n2_0 + c;
             const cplx w = a.tab_tw[(size_t)pos * N2 + n2];
             dst[(size_t)pos * N2 + n2] = cmul(S[(size_t)c * N1 + swz(pos)], w);
@@ -278,7 +298,8 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
         for (int j = 0; j < a.npoly; ++j) {
             const cplx *src = a.ybuf + ((size_t)s * a.npoly + j) * a.L;
             for (int idx = tid; idx < C * N1; idx += nt) {
-                const int c = idx & (C - 1), pos = idx >> a.log2C;
+                int c, pos;
+                cz_tile_index(idx, a.log2C, N1, &c, &pos);
                 const int n2 = n2_0 + c;
                 const cplx w = cconj(a.tab_tw[(size_t)pos * N2 + n2]);
                 S[((size_t)j * C + c) * N1 + swz(pos)] = cmul(src[(size_t)pos * N2 + n2], w);
@@ -291,7 +312,8 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
     FOR_THREADS(tid, nt)
     {
         for (int idx = tid; idx < C * N1; idx += nt) {
-            const int c = idx & (C - 1), n1 = idx >> a.log2C;
+            int c, n1;
+            cz_tile_index(idx, a.log2C, N1, &c, &n1);
             const long long m = (long long)n1 * N2 + n2_0 + c;
             if (m >= a.M)
                 continue;

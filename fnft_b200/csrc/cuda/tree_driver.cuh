@@ -315,7 +315,9 @@ struct TreeDeferred {
     // the column pass of the last (row-split) level has not run yet: either the chirp-z fuses it with its first
     // stage (k_up_cols_cz) or tree_finish_cols launches it
     int cols_pending;
+#ifndef FNFTB_EMUL
     UpArgs cols;
+#endif
 };
 
 static inline int tree_finish_cols(TreeDeferred &f, fnftb_stream_t st)
@@ -323,7 +325,12 @@ static inline int tree_finish_cols(TreeDeferred &f, fnftb_stream_t st)
     if (!f.cols_pending)
         return 0;
     f.cols_pending = 0;
+#ifndef FNFTB_EMUL
     return up_cols_pending(f.cols, st);
+#else
+    (void)st;
+    return 0;
+#endif
 }
 
 static inline int tree_finalize(const TreeWork &w, int cur, int B, int d_full, int deg_out,
