@@ -682,10 +682,29 @@ def main():
                 "algorithmic_bytes_per_signal": bts, "tree_ms_per_step": tree_ms,
                 "tree_launches_per_step": tree_launches, "tree_share_of_step": tree_ms / total_ms,
                 "kernel_ms_per_step": {k: round(ms, 4) for k, (n, ms) in sorted(rep.items())}}
-    # FP64 pipe: DFMA throughput of this GPU measured by the library's own probe kernel
+    # the algorithmic model of SURVEY 8(d) counts every level read and written once as coefficients; the
+    # spectrum-carry tree moves less than half of that, so `frac` can exceed 1 -- the physical figure beside it
+    roofline["frac_physical"] = (roofline["physical_gbs"] / peak) if roofline["physical_gbs"] else None
+    # FP64 pipe: DFMA throughput of this GPU measured by the library's own probe kernel, and the issue-slot
+    # utilisation of the dominant kernel k_tree_low2 (every FP64 warp instruction occupies the pipe like an FMA;
+    # instruction count from the committed ncu capture, time from this run's CUDA events)
     if hasattr(L, "fnft_b200_probe_fp64_tflops"):
         L.fnft_b200_probe_fp64_tflops.restype = C.c_double
-        roofline["fp64_peak_tflops_measured"] = float(L.fnft_b200_probe_fp64_tflops())
+        fp64_peak = float(L.fnft_b200_probe_fp64_tflops())
+        roofline["fp64_peak_tflops_measured"] = fp64_peak
+        try:
+            with open(os.path.join(ROOT, "profiles", "low2_fp64_instr.json")) as f:
+                lj = json.load(f)
+            low2_ms = rep["tree_low2"][1]
+            ach = lj["fp64_warp_instructions_per_signal"] * B * 64 / (low2_ms * 1e-3) / 1e12
+            roofline["fp64"] = {"kernel": "k_tree_low2 (%.1f %% of the step)" % (100.0 * low2_ms / total_ms),
+                                "bound": "fp64 pipe issue slots", "achieved": ach, "peak": fp64_peak,
+                                "unit": "TFLOP/s, every FP64 warp instruction counted as one FMA slot (64 flop)",
+                                "frac": ach / fp64_peak if fp64_peak > 0 else None,
+                                "fp64_warp_instructions_per_signal": lj["fp64_warp_instructions_per_signal"],
+                                "source": "profiles/low2_fp64_instr.json (ncu opcode histogram)"}
+        except Exception:
+            pass
 
     # ---- end to end through the C-ABI with pinned host buffers ("e2e")
     L.fnft_b200_set_device_pointers(0)

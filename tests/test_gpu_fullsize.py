@@ -188,6 +188,10 @@ def test_config5_nsep_gridsearch_full_size_and_whose_error_it_is(F, BM, R):
 def _ref7(args):
     """the reference with its DEFAULT options (SUBSAMPLE_AND_REFINE, eiscor replaced by the LAPACK companion-matrix
     shim of oracle/eiscor_shim.c) plus residues, on one signal"""
+    # one BLAS thread per worker: the shim's LAPACK call otherwise starts a thread per core in every one of the
+    # worker processes and the box thrashes (9 minutes instead of 10 seconds)
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "SCIPY_OPENBLAS_NUM_THREADS"):
+        os.environ[var] = "1"
     sys.path.insert(0, ROOT)
     from oracle import ref_lib as Rl
     q, T, kmax = args
@@ -200,12 +204,12 @@ def _ref7(args):
 
 def test_config7_default_options_find_what_the_reference_finds(F, BM, solitons):
     # fnft_nsev with its default options (bsloc SUBSAMPLE_AND_REFINE: roots of the sub-sampled a(z) by the GPU
-    # Aberth-Ehrlich finder instead of eiscor, Newton refinement on the full signal) on 16 of config 3's 8-soliton
+    # Aberth-Ehrlich finder instead of eiscor, Newton refinement on the full signal) on 12 of config 3's 8-soliton
     # signals, D = 4096: the same NUMBER of bound states as the reference on every signal and the same eigenvalues,
     # norming constants and residues to 1e-9 (Newton on the same recurrence converges to the same zeros whatever
     # root finder supplied the start values).
     idx, q, _ = solitons
-    n, kmax = 16, 64
+    n, kmax = 12, 64
     q = q[:n]
     ref = _pool(_ref7, [(q[i], BM.C3["T"], kmax) for i in range(n)])
     o = F.nsev_default_opts()
