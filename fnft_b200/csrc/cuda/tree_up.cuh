@@ -552,6 +552,113 @@ __global__ void __launch_bounds__((1 << L2N) / FNFTB_UP_TPP(L2N), (L2N == 11) ? 
 }
 
 // ---------------------------------------------------------------------------------------
+// N = 8192 as a CLUSTER of two CTAs (round 2).  k_up_smem<13> needs the whole 128 KiB work buffer in one CTA, so one
+// CTA is resident per SM and its memory phase (X stage) and compute phases never overlap anything (3.5 TB/s where
+// the N = 4096 kernel with three CTAs per SM reaches 4.35).  Here each CTA of a pair holds one half of the positions
+// (64 KiB, three CTAs per SM like N = 4096): the X stage, the inverse / forward passes at strides < 4096 and the
+// F stage stay inside a half -- the two halves are exactly the regions with (-1)^k = +1 / -1 -- and only the M stage
+// (radix 16 at stride 512: 8 elements from either half per butterfly) reads and writes the partner's half through
+// distributed shared memory, with a cluster barrier on either side.
+// grid.x = B * npairs * E * 2, cluster (2, 1, 1), blockDim.x = 128
+// ---------------------------------------------------------------------------------------
+DEV unsigned up_cluster_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+DEV void up_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// generic address of the same shared-memory location in CTA `rank` of the cluster
+DEV cplx *up_cluster_map(cplx *p, unsigned rank)
+{
+    unsigned long long in = (unsigned long long)p, out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(in), "r"(rank));
+    return (cplx *)out;
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(128, 3) k_up_smem13_cluster(const UpArgs a)
+{
+    constexpr int E = UpT<SYM>::E;
+    constexpr int L2N = 13, N = 1 << L2N, H = N / 2, NT = 128, RX = 8;
+    extern __shared__ double2 fnftb_smem_up[];
+    cplx *S = (cplx *)fnftb_smem_up;
+    double *red = (double *)(S + H);
+    const int tid = threadIdx.x;
+    const unsigned h = up_cluster_rank();
+    const unsigned item = blockIdx.x >> 1;
+    const int which = item % E;
+    const size_t sp = item / E;
+    const int npairs = a.n_in >> 1;
+    const int s = (int)(sp / npairs);
+    if (a.pf > 0 && h == 0) {  // operands of the item `pf` places ahead, issued by the first half only
+        const size_t ip = (size_t)item + (size_t)a.pf;
+        if (ip < (gridDim.x >> 1) && (!SYM || (ip % E) == 0))
+            up_prefetch_operands<SYM>(a, ip / E, (int)(ip % E), 0, N, tid);
+    }
+    const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0 && h == 0);
+    up_x_stage<RX, SYM>(a, sp, which, (int)h * H, 0, H, h ? -1.0 : 1.0, P, S, tid, NT);
+    __syncthreads();
+    up_p_pass<8, +1>(S, H, 3, a.tw, tid, NT);
+    __syncthreads();
+    up_p_pass<8, +1>(S, H, 6, a.tw, tid, NT);
+    up_cluster_sync();
+    // M stage: butterflies o = h * 256 .. h * 256 + 255; element o + r * 512, r < 16: r < 8 in half 0, else in half 1
+    cplx *S0 = up_cluster_map(S, 0), *S1 = up_cluster_map(S, 1);
+    double m2 = 0.0;
+    {
+        constexpr int R = 16, LR = 4, l2s = L2N - LR, st = 1 << l2s;
+        const double invN = 1.0 / (double)N;
+        const cplx *pt = a.tw.base + a.tw.pass_off[L2N][LR];
+        const cplx *tt = a.tw.base + a.tw.twist_off[L2N];
+#pragma unroll 1
+        for (int o = (int)h * (st / 2) + tid; o < ((int)h + 1) * (st / 2); o += NT) {
+            cplx v[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int r = brev_c(q, LR);
+                v[q] = (r < 8) ? S0[swz2(o + (r << l2s))] : S1[swz2(o + ((r - 8) << l2s))];
+            }
+            up_twiddle_mul<R, true>(v, pt, st, o);
+            Dft<R, +1>::run(v);
+#pragma unroll
+            for (int n = 0; n < R; ++n)
+                v[n] = cscale(v[n], invN);
+            if (o == 0)
+                v[0] = up_bot(P.Tn, which);
+#pragma unroll
+            for (int n = 0; n < R; ++n)
+                m2 = fmax(m2, cabs2(v[n]));
+            up_twist16(v, __ldg(&tt[o]));
+            Dft<R, -1>::run(v);
+            up_twiddle_mul<R, false>(v, pt, st, o);
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int r = brev_c(q, LR);
+                if (r < 8)
+                    S0[swz2(o + (r << l2s))] = v[q];
+                else
+                    S1[swz2(o + ((r - 8) << l2s))] = v[q];
+            }
+        }
+    }
+    up_cluster_sync();
+    up_p_pass<8, -1>(S, H, 6, a.tw, tid, NT);
+    __syncthreads();
+    up_p_pass<8, -1>(S, H, 3, a.tw, tid, NT);
+    __syncthreads();
+    cplx *godd = a.out + (E * sp + which) * (size_t)(2 * N) + N + (size_t)h * H;
+    up_f_stage<RX>(S, H, up_top(P.Tn, which), godd, tid, NT);
+    double mm = m2;
+    if (tid == 0 && h == 0)
+        mm = fmax(mm, cabs2(up_top(P.Tn, which)));
+    up_publish_max(mm, red, &a.mx_out[sp], tid, NT);
+}
+
+// ---------------------------------------------------------------------------------------
 // row-split levels, N = R * N2
 // (a) grid.x = B * npairs * 2 * R: pointwise product + inverse passes inside row r
 // ---------------------------------------------------------------------------------------
@@ -781,6 +888,37 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st, UpArgs *
         const unsigned grid = (unsigned)a.B * (unsigned)npairs * (unsigned)E;
         const size_t smem = sizeof(cplx) * N + 64 * sizeof(double);
         a.pf = up_pf_distance(UP_PF_SMEM11 + (a.l2n - 11));
+        static const int knob_cluster = [] {
+            const char *e = getenv("FNFT_B200_UP13_CLUSTER");  // 0: one CTA per item (k_up_smem<13>)
+            return (e && e[0]) ? atoi(e) : 1;                  // measured 4.84 -> 4.54 ms per 4096 signals
+        }();
+        if (a.l2n == 13 && !a.last && knob_cluster) {
+            auto kern = k_up_smem13_cluster<SYM>;
+            const size_t smem_h = sizeof(cplx) * (N / 2) + 64 * sizeof(double);
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
+            if (e != cudaSuccess)
+                return (int)e;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid * 2, 1, 1);
+            cfg.blockDim = dim3(128, 1, 1);
+            cfg.dynamicSmemBytes = smem_h;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (g_fnftb_profile_on)
+                fnftb_profile_begin(names_s[2], st);
+            e = cudaLaunchKernelEx(&cfg, kern, a);
+            if (g_fnftb_profile_on)
+                fnftb_profile_end(st);
+            ++g_fnftb_launch_count;
+            return (int)e;
+        }
         switch (a.l2n) {
         case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 2048 / FNFTB_UP_TPP(11), smem, st, names_s[0]);
         case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 4096 / FNFTB_UP_TPP(12), smem, st, names_s[1]);

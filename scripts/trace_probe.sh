@@ -7,7 +7,7 @@ import bench, fnft_b200 as F
 B = 4096
 L = F.lib(); L.fnft_b200_set_device(0); torch.cuda.set_device(0)
 P = bench.signal_params(B)
-q = bench.signals_torch(P, B, torch.device("cuda:0"))
+q = bench.signals_torch(P, 0, B, torch.device("cuda:0"))
 qh = torch.empty((B, bench.D), dtype=torch.complex128, pin_memory=True); qh.copy_(q)
 oh = torch.empty((B, bench.M), dtype=torch.complex128, pin_memory=True); oh.zero_()
 T = np.array(bench.TT); XI = np.array(bench.XI)
