@@ -579,48 +579,55 @@ DEV cplx *up_cluster_map(cplx *p, unsigned rank)
     return (cplx *)out;
 }
 
-template <bool SYM>
-__global__ void __launch_bounds__(128, 3) k_up_smem13_cluster(const UpArgs a)
+// L2N = 13: cluster of 2 (RX = 8, passes at strides 8 and 64, M stage at stride 512); L2N = 14: cluster of 4 (RX = 16,
+// passes at strides 16 and 128, M stage at stride 1024: four elements of a butterfly in each quarter) -- this one
+// replaces the three row-split kernels of the N = 16384 level and their workspace round trip (34 GB -> 17 GB).
+template <int L2N, bool SYM>
+__global__ void __launch_bounds__(128, 3) k_up_smem_cluster(const UpArgs a)
 {
     constexpr int E = UpT<SYM>::E;
-    constexpr int L2N = 13, N = 1 << L2N, H = N / 2, NT = 128, RX = 8;
+    constexpr int N = 1 << L2N, H = 4096, CL = N / H, NT = 128;
+    constexpr int RX = (L2N == 13) ? 8 : 16, L2RX = (L2N == 13) ? 3 : 4;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
     double *red = (double *)(S + H);
     const int tid = threadIdx.x;
     const unsigned h = up_cluster_rank();
-    const unsigned item = blockIdx.x >> 1;
+    const unsigned item = blockIdx.x / CL;
     const int which = item % E;
     const size_t sp = item / E;
     const int npairs = a.n_in >> 1;
     const int s = (int)(sp / npairs);
-    if (a.pf > 0 && h == 0) {  // operands of the item `pf` places ahead, issued by the first half only
+    if (a.pf > 0 && h == 0) {  // operands of the item `pf` places ahead, issued by the first CTA of the cluster only
         const size_t ip = (size_t)item + (size_t)a.pf;
-        if (ip < (gridDim.x >> 1) && (!SYM || (ip % E) == 0))
+        if (ip < (gridDim.x / CL) && (!SYM || (ip % E) == 0))
             up_prefetch_operands<SYM>(a, ip / E, (int)(ip % E), 0, N, tid);
     }
     const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0 && h == 0);
-    up_x_stage<RX, SYM>(a, sp, which, (int)h * H, 0, H, h ? -1.0 : 1.0, P, S, tid, NT);
+    up_x_stage<RX, SYM>(a, sp, which, (int)h * H, 0, H, (h >= CL / 2) ? -1.0 : 1.0, P, S, tid, NT);
     __syncthreads();
-    up_p_pass<8, +1>(S, H, 3, a.tw, tid, NT);
+    up_p_pass<8, +1>(S, H, L2RX, a.tw, tid, NT);
     __syncthreads();
-    up_p_pass<8, +1>(S, H, 6, a.tw, tid, NT);
+    up_p_pass<8, +1>(S, H, L2RX + 3, a.tw, tid, NT);
     up_cluster_sync();
-    // M stage: butterflies o = h * 256 .. h * 256 + 255; element o + r * 512, r < 16: r < 8 in half 0, else in half 1
-    cplx *S0 = up_cluster_map(S, 0), *S1 = up_cluster_map(S, 1);
+    // M stage: this CTA's share of the N / 16 butterflies; element o + r * st, r < 16, lives in CTA r / (16 / CL)
+    cplx *Sr[CL];
+#pragma unroll
+    for (int c = 0; c < CL; ++c)
+        Sr[c] = up_cluster_map(S, (unsigned)c);
     double m2 = 0.0;
     {
-        constexpr int R = 16, LR = 4, l2s = L2N - LR, st = 1 << l2s;
+        constexpr int R = 16, LR = 4, l2s = L2N - LR, st = 1 << l2s, PER = R / CL;
         const double invN = 1.0 / (double)N;
         const cplx *pt = a.tw.base + a.tw.pass_off[L2N][LR];
         const cplx *tt = a.tw.base + a.tw.twist_off[L2N];
 #pragma unroll 1
-        for (int o = (int)h * (st / 2) + tid; o < ((int)h + 1) * (st / 2); o += NT) {
+        for (int o = (int)h * (st / CL) + tid; o < ((int)h + 1) * (st / CL); o += NT) {
             cplx v[R];
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int r = brev_c(q, LR);
-                v[q] = (r < 8) ? S0[swz2(o + (r << l2s))] : S1[swz2(o + ((r - 8) << l2s))];
+                v[q] = Sr[r / PER][swz2(o + ((r % PER) << l2s))];
             }
             up_twiddle_mul<R, true>(v, pt, st, o);
             Dft<R, +1>::run(v);
@@ -638,17 +645,14 @@ __global__ void __launch_bounds__(128, 3) k_up_smem13_cluster(const UpArgs a)
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int r = brev_c(q, LR);
-                if (r < 8)
-                    S0[swz2(o + (r << l2s))] = v[q];
-                else
-                    S1[swz2(o + ((r - 8) << l2s))] = v[q];
+                Sr[r / PER][swz2(o + ((r % PER) << l2s))] = v[q];
             }
         }
     }
     up_cluster_sync();
-    up_p_pass<8, -1>(S, H, 6, a.tw, tid, NT);
+    up_p_pass<8, -1>(S, H, L2RX + 3, a.tw, tid, NT);
     __syncthreads();
-    up_p_pass<8, -1>(S, H, 3, a.tw, tid, NT);
+    up_p_pass<8, -1>(S, H, L2RX, a.tw, tid, NT);
     __syncthreads();
     cplx *godd = a.out + (E * sp + which) * (size_t)(2 * N) + N + (size_t)h * H;
     up_f_stage<RX>(S, H, up_top(P.Tn, which), godd, tid, NT);
@@ -852,6 +856,37 @@ static inline int up_pf_distance(int family)
     return dist[family];
 }
 
+// cluster launch of k_up_smem_cluster: `items` work items, CL CTAs of 128 threads and 64 KiB each per item
+template <class K>
+static inline int up_launch_cluster(K kern, const UpArgs &a, unsigned items, unsigned CL, cudaStream_t st,
+                                    const char *name)
+{
+    const size_t smem_h = sizeof(cplx) * 4096 + 64 * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
+    if (e != cudaSuccess)
+        return (int)e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(items * CL, 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = smem_h;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin(name, st);
+    e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(st);
+    ++g_fnftb_launch_count;
+    return (int)e;
+}
+
 // launches the column pass of a row-split level (a.l2row, a.pf set)
 template <bool SYM>
 static inline int up_cols_launch(const UpArgs &a, cudaStream_t st)
@@ -892,38 +927,22 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st, UpArgs *
             const char *e = getenv("FNFT_B200_UP13_CLUSTER");  // 0: one CTA per item (k_up_smem<13>)
             return (e && e[0]) ? atoi(e) : 1;                  // measured 4.84 -> 4.54 ms per 4096 signals
         }();
-        if (a.l2n == 13 && !a.last && knob_cluster) {
-            auto kern = k_up_smem13_cluster<SYM>;
-            const size_t smem_h = sizeof(cplx) * (N / 2) + 64 * sizeof(double);
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
-            if (e != cudaSuccess)
-                return (int)e;
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3(grid * 2, 1, 1);
-            cfg.blockDim = dim3(128, 1, 1);
-            cfg.dynamicSmemBytes = smem_h;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            if (g_fnftb_profile_on)
-                fnftb_profile_begin(names_s[2], st);
-            e = cudaLaunchKernelEx(&cfg, kern, a);
-            if (g_fnftb_profile_on)
-                fnftb_profile_end(st);
-            ++g_fnftb_launch_count;
-            return (int)e;
-        }
+        if (a.l2n == 13 && !a.last && knob_cluster)
+            return up_launch_cluster(k_up_smem_cluster<13, SYM>, a, grid, 2, st, names_s[2]);
         switch (a.l2n) {
         case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 2048 / FNFTB_UP_TPP(11), smem, st, names_s[0]);
         case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 4096 / FNFTB_UP_TPP(12), smem, st, names_s[1]);
         default: return up_launch(k_up_smem<13, SYM>, a, grid, 8192 / FNFTB_UP_TPP(13), smem, st, names_s[2]);
         }
+    }
+    static const int knob_cluster14 = [] {
+        const char *e = getenv("FNFT_B200_UP14_CLUSTER");  // 0: row-split kernels (rows_a / cols / rows_c)
+        return (e && e[0]) ? atoi(e) : 1;
+    }();
+    if (a.l2n == 14 && !a.last && knob_cluster14 && l2smem_max >= 13) {
+        a.pf = up_pf_distance(UP_PF_SMEM13);
+        return up_launch_cluster(k_up_smem_cluster<14, SYM>, a, (unsigned)a.B * (unsigned)npairs * (unsigned)E, 4, st,
+                                 "tree_up_smem_N16384");
     }
     a.l2row = FNFTB_UP_ROW_L2;
     const int l2R = a.l2n - a.l2row;
