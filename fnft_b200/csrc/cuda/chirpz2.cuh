@@ -355,6 +355,91 @@ __global__ void __launch_bounds__(256, 3) k_up_cols_cz(const Cz2Args a)
         dst[((size_t)Cz2Radix<RC>::row(q) << FNFTB_CZ2_ROW_L2) + oc] = v[q];
 }
 
+// The WHOLE last tree level + first chirp-z stage as a cluster of RT CTAs (round 2).  CTA h of a cluster holds row h
+// (4096 positions, 64 KiB) of one (signal, polynomial): X stage and the inverse passes inside the row like k_up_rows_a,
+// then -- instead of writing the row to the workspace for k_up_cols -- a cluster barrier and the column stage of
+// k_up_cols_cz straight from the RT shared memories (distributed shared memory reads), so that between the operands of
+// the last pair product and the first chirp-z buffer nothing touches DRAM.
+// grid.x = B * 2 * RT, cluster (RT, 1, 1), 128 threads
+template <int RT, int RC>
+__global__ void __launch_bounds__(128, 3) k_up_last_cluster_cz(const Cz2Args a)
+{
+    constexpr int N2 = 1 << FNFTB_CZ2_ROW_L2, NT = 128;
+    constexpr int LR = Log2R<RT>::value;
+    extern __shared__ double2 fnftb_smem_cz2[];
+    cplx *S = (cplx *)fnftb_smem_cz2;
+    const UpArgs &u = a.src.up;
+    const CzArgs &c = a.c;
+    const int tid = threadIdx.x;
+    const unsigned h = up_cluster_rank();
+    const unsigned item = blockIdx.x / RT;   // = 2 * signal + which (one pair per signal on the last level)
+    const int which = (int)(item & 1);
+    const size_t sp = item >> 1;
+    const int l2n = u.l2n;
+    const int N = 1 << l2n;
+    if (u.pf_rows > 0 && h == 0) {
+        const size_t ip = (size_t)item + (size_t)u.pf_rows;
+        if (ip < (gridDim.x / RT) && (ip & 1) == 0)
+            up_prefetch_operands<true>(u, ip >> 1, 0, 0, N, tid);
+    }
+    const UpPair<true> P = up_pair_setup<true>(u, sp, (int)sp, which == 0 && h == 0);
+    up_x_stage<16, true>(u, sp, which, (int)h << FNFTB_CZ2_ROW_L2, 0, N2, (h >= RT / 2) ? -1.0 : 1.0, P, S, tid, NT);
+    __syncthreads();
+    up_row_passes<+1, FNFTB_UP_ROW_L2, true>(S, u.tw, tid, NT);
+    up_cluster_sync();
+    cplx *Sr[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+        Sr[r] = up_cluster_map(S, (unsigned)r);
+    const cplx *pt = u.tw.base + u.tw.pass_off[l2n][LR];
+    const double invN = 1.0 / (double)N;
+    const int Np = c.deg + 1;
+    const double fb = -(double)a.src.kappa;
+    const size_t arr = item;
+    cplx *dst = c.ybuf + arr * (size_t)a.L;
+#pragma unroll 1
+    for (int o = (int)h * (N2 / RT) + tid; o < ((int)h + 1) * (N2 / RT); o += NT) {
+        cplx g[RT];
+#pragma unroll
+        for (int q = 0; q < RT; ++q)
+            g[q] = Sr[brev_c(q, LR)][swz2(o)];
+        up_twiddle_mul<RT, true>(g, pt, N2, o);
+        Dft<RT, +1>::run(g);
+#pragma unroll
+        for (int n = 0; n < RT; ++n)
+            g[n] = cscale(g[n], invN);
+        if (o == 0)
+            g[0] = up_bot(P.Tn, which);
+        const cplx gtop = up_top(P.Tn, which);
+        const int oc = which ? o : ((N2 - o) & (N2 - 1));
+        cplx v[RC];
+#pragma unroll
+        for (int n1 = 0; n1 < RC; ++n1) {
+            const int n = oc + n1 * N2;
+            cplx x = czero();
+            if (n < Np) {
+                if (which) {
+                    const cplx b = (n1 < RT) ? g[n1 < RT ? n1 : 0] : gtop;
+                    x = make_cplx(b.x * fb, -b.y * fb);
+                } else {
+                    if (o == 0)
+                        x = (n1 == 0) ? gtop : g[(RT - n1) >= 0 && (RT - n1) < RT ? RT - n1 : 0];
+                    else
+                        x = g[(RT - 1 - n1) >= 0 ? RT - 1 - n1 : 0];
+                }
+                x = cmul(x, __ldg(&c.tab_y[n]));
+            }
+            v[n1] = x;
+        }
+        DftAny<RC, -1>::run(v);
+        cz2_col_twiddle<RC, false>(v, a, oc);
+#pragma unroll
+        for (int q = 0; q < RC; ++q)
+            dst[((size_t)Cz2Radix<RC>::row(q) << FNFTB_CZ2_ROW_L2) + oc] = v[q];
+    }
+    up_cluster_sync();  // nobody leaves while a partner may still read its shared memory
+}
+
 // grid.x = narr * R rows, 128 threads, 64 KiB shared memory
 __global__ void __launch_bounds__(128, 3) k_cz2_rows(const Cz2Args a)
 {
@@ -660,6 +745,35 @@ static inline int cz2_launch(K kernel, const Cz2Args &a, unsigned grid, int nt, 
     return (int)cudaGetLastError();
 }
 
+template <class K>
+static inline int cz2_launch_cluster(K kernel, const Cz2Args &a, unsigned items, unsigned CL, cudaStream_t st)
+{
+    const size_t smem = sizeof(cplx) << FNFTB_CZ2_ROW_L2;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return (int)e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(items * CL, 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (g_fnftb_profile_on)
+        fnftb_profile_begin("tree_up_last_cz", st);
+    e = cudaLaunchKernelEx(&cfg, kernel, a);
+    if (g_fnftb_profile_on)
+        fnftb_profile_end(st);
+    ++g_fnftb_launch_count;
+    return (int)e;
+}
+
 // Same contract as cz_run (chirpz_driver.cuh); a.vhat doubles as the permuted FFT(v).
 int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2SymSrc *src)
 {
@@ -739,7 +853,30 @@ int cz2_run(CzArgs c, cplx *tables, const TwSet &tw, cudaStream_t st, const Cz2S
             return rc;
     }
     a.gen_v = 0;
-    if (a.src.fused) {
+    // 1: the whole last level as one cluster kernel.  OFF by default: measured 5.58 ms per 4096 signals against
+    // 2.67 + 1.70 ms for k_up_rows_a + k_up_cols_cz -- with eight CTAs per cluster 7/8 of the column stage's reads are
+    // remote shared-memory reads, which cost more than the 2 MB per signal of DRAM round trip they save (the cluster of
+    // four of the N = 16384 level, k_up_smem_cluster<14>, does pay: 6.43 -> 5.52 ms)
+    static const int knob_last_cluster = [] {
+        const char *e = getenv("FNFT_B200_LAST_CLUSTER");
+        return (e && e[0]) ? atoi(e) : 0;
+    }();
+    if (a.src.fused && a.src.up.rows_pending && knob_last_cluster) {
+        const int RT = 1 << (a.src.up.l2n - a.src.up.l2row);
+        const unsigned items = (unsigned)narr;
+        switch (RT * 100 + R) {
+        case 203: rc = cz2_launch_cluster(k_up_last_cluster_cz<2, 3>, a, items, 2, st); break;
+        case 204: rc = cz2_launch_cluster(k_up_last_cluster_cz<2, 4>, a, items, 2, st); break;
+        case 406: rc = cz2_launch_cluster(k_up_last_cluster_cz<4, 6>, a, items, 4, st); break;
+        case 408: rc = cz2_launch_cluster(k_up_last_cluster_cz<4, 8>, a, items, 4, st); break;
+        case 812: rc = cz2_launch_cluster(k_up_last_cluster_cz<8, 12>, a, items, 8, st); break;
+        case 816: rc = cz2_launch_cluster(k_up_last_cluster_cz<8, 16>, a, items, 8, st); break;
+        default: return -1066;
+        }
+    } else if (a.src.fused) {
+        rc = up_rows_a_pending(a.src.up, st);
+        if (rc)
+            return rc;
         const int RT = 1 << (a.src.up.l2n - a.src.up.l2row);
         const unsigned grid = (unsigned)(narr * cols1);
         switch (RT * 100 + R) {

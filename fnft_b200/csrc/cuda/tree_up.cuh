@@ -49,6 +49,8 @@ struct UpArgs {
     int normalize, kappa, last;
     int l2row;              // row-split: log2(N2)
     int pf;                 // L2 prefetch distance in CTAs (0: off), see up_prefetch
+    int rows_pending;       // a pending last level (up_level with pending_cols): k_up_rows_a has not run either
+    int pf_rows;            // its prefetch distance
     TwSet tw;
 };
 
@@ -948,15 +950,20 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st, UpArgs *
     const int l2R = a.l2n - a.l2row;
     const unsigned grid_rows = (unsigned)a.B * (unsigned)npairs * (unsigned)E << l2R;
     const size_t smem = sizeof(cplx) << a.l2row;
+    if (SYM && a.last && pending_cols != nullptr && l2R <= 5) {
+        // the whole level stays pending: the chirp-z either runs it as one cluster kernel (chirpz2.cuh:
+        // k_up_last_cluster_cz) or as k_up_rows_a + k_up_cols_cz, and up_cols_pending runs the plain kernels
+        a.rows_pending = 1;
+        a.pf_rows = up_pf_distance(UP_PF_ROWS_A);
+        a.pf = up_pf_distance(UP_PF_COLS);
+        *pending_cols = a;
+        return 0;
+    }
     a.pf = up_pf_distance(UP_PF_ROWS_A);
     int rc = up_launch(k_up_rows_a<128, SYM>, a, grid_rows, 128, smem, st, "tree_up_rows_a");
     if (rc)
         return rc;
     a.pf = up_pf_distance(UP_PF_COLS);
-    if (SYM && a.last && pending_cols != nullptr && l2R <= 5) {
-        *pending_cols = a;
-        return 0;
-    }
     rc = up_cols_launch<SYM>(a, st);
     if (rc || a.last)
         return rc;
@@ -968,8 +975,25 @@ int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym, UpArgs 
 {
     return sym ? up_level_t<true>(a, l2smem_max, st, pending_cols) : up_level_t<false>(a, l2smem_max, st);
 }
-int up_cols_pending(const UpArgs &a, cudaStream_t st) { return up_cols_launch<true>(a, st); }
+// k_up_rows_a of a pending last level (SYM)
+int up_rows_a_pending(UpArgs &a, cudaStream_t st)
+{
+    if (!a.rows_pending)
+        return 0;
+    UpArgs r = a;
+    r.pf = a.pf_rows;
+    const unsigned grid_rows = (unsigned)a.B * (unsigned)(a.n_in / 2) * 2u << (a.l2n - a.l2row);
+    a.rows_pending = 0;
+    return up_launch(k_up_rows_a<128, true>, r, grid_rows, 128, sizeof(cplx) << a.l2row, st, "tree_up_rows_a");
+}
+int up_cols_pending(const UpArgs &a_in, cudaStream_t st)
+{
+    UpArgs a = a_in;
+    const int rc = up_rows_a_pending(a, st);
+    return rc ? rc : up_cols_launch<true>(a, st);
+}
 #else
+int up_rows_a_pending(UpArgs &a, cudaStream_t st);
 int up_level(const UpArgs &a, int l2smem_max, cudaStream_t st, bool sym = true, UpArgs *pending_cols = nullptr);
 int up_cols_pending(const UpArgs &a, cudaStream_t st);
 #endif
