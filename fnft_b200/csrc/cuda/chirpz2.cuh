@@ -731,10 +731,10 @@ template <class K>
 static inline int cz2_launch(K kernel, const Cz2Args &a, unsigned grid, int nt, size_t smem, cudaStream_t st,
                              const char *name)
 {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return (int)e;
+    {
+        const int e = fnftb_smem_optin((const void *)kernel, smem);
+        if (e != 0)
+            return e;
     }
     if (g_fnftb_profile_on)
         fnftb_profile_begin(name, st);
@@ -749,9 +749,10 @@ template <class K>
 static inline int cz2_launch_cluster(K kernel, const Cz2Args &a, unsigned items, unsigned CL, cudaStream_t st)
 {
     const size_t smem = sizeof(cplx) << FNFTB_CZ2_ROW_L2;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess)
-        return (int)e;
+    const int eo = fnftb_smem_optin((const void *)kernel, smem);
+    if (eo != 0)
+        return eo;
+    cudaError_t e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(items * CL, 1, 1);

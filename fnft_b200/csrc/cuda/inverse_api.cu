@@ -3,6 +3,7 @@
 // 2x2 pair product and the any-length DFT through ctx_hooks.h.
 #include "ctx_hooks.h"
 #include "inverse_kernels.cuh"
+#include "launch.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -98,8 +99,7 @@ int launch_block(const FinvCall &f, InvPoly T, size_t n, InvPoly Ti, cplx *q, si
     a.modal = f.modal;
     a.eps_t = f.eps_t;
     const size_t smem = 2 * 8 * (n + 2) * sizeof(cplx);
-    if (smem > 48 * 1024)
-        ICU(cudaFuncSetAttribute(k_inv_block<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IRC(fnftb_smem_optin((const void *)k_inv_block<256>, smem));
     k_inv_block<256><<<(unsigned)f.B, 256, smem, f.st>>>(a);
     ++g_fnftb_launch_count;
     ICU(cudaGetLastError());

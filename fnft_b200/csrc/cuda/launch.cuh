@@ -38,6 +38,38 @@ void fnftb_profile_begin(const char *name, cudaStream_t st);
 void fnftb_profile_end(cudaStream_t st);
 extern int g_fnftb_profile_on;
 
+// Opt-in to more than 48 KiB of dynamic shared memory, ONCE per (device, kernel) and to the device maximum.
+// Setting the attribute to the size of the current launch on every launch is a race when several host threads (the
+// per-device workers of fnft_b200_set_devices, possibly several on one GPU) launch the same kernel with different
+// sizes: a smaller value set by one thread between another thread's set and its launch makes that launch fail with
+// cudaErrorInvalidValue.  The maximum costs nothing: occupancy follows the size given at launch.
+#include <mutex>
+#include <set>
+#include <utility>
+static inline int fnftb_smem_optin(const void *kernel, size_t smem_bytes)
+{
+    if (smem_bytes <= 48 * 1024)
+        return 0;
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return (int)e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count(std::make_pair(dev, kernel)))
+        return 0;
+    int maxs = 0;
+    e = cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess)
+        return (int)e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+    if (e != cudaSuccess)
+        return (int)e;
+    done.insert(std::make_pair(dev, kernel));
+    return 0;
+}
+
 template <class Args, void (*F)(const Args &, blk3, int, void *), int MAXT = 256, int MINB = 1>
 static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t smem_bytes,
                                 fnftb_stream_t st, const char *name = "")
@@ -46,12 +78,10 @@ static inline int launch_blocks(const Args &a, unsigned grid, int nt, size_t sme
         return 0;
     if (nt > MAXT)
         return -77;
-    if (smem_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fnftb_kernel<Args, F, MAXT, MINB>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem_bytes);
-        if (e != cudaSuccess)
-            return (int)e;
+    {
+        const int e = fnftb_smem_optin((const void *)fnftb_kernel<Args, F, MAXT, MINB>, smem_bytes);
+        if (e != 0)
+            return e;
     }
     if (g_fnftb_profile_on)
         fnftb_profile_begin(name, st);

@@ -277,10 +277,10 @@ static inline int roots_launch_r(const RootsArgs &a, int B, int nt, cudaStream_t
 {
     const size_t smem = a.in_global ? 0 : sizeof(cplx) * (size_t)a.n;
     auto kern = k_roots_aberth<R, MAXNT>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return (int)e;
+    {
+        const int e = fnftb_smem_optin((const void *)kern, smem);
+        if (e != 0)
+            return e;
     }
     kern<<<B, nt, smem, st>>>(a);
     return 0;

@@ -559,10 +559,9 @@ template <int LOG2M, int DEG0>
 static inline int low2g_launch_t(const Low2gArgs &a, cudaStream_t st)
 {
     const size_t smem = low2g_smem_bytes(LOG2M);
-    cudaError_t e = cudaFuncSetAttribute(k_tree_low2g<LOG2M, DEG0>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess)
-        return (int)e;
+    const int e = fnftb_smem_optin((const void *)k_tree_low2g<LOG2M, DEG0>, smem);
+    if (e != 0)
+        return e;
     const unsigned grid = (unsigned)a.B * (unsigned)(a.npad / low2g_samples(LOG2M, DEG0));
     if (g_fnftb_profile_on)
         fnftb_profile_begin("tree_low2g", st);

@@ -824,10 +824,10 @@ template <class K>
 static inline int up_launch(K kernel, const UpArgs &a, unsigned grid, int nt, size_t smem, cudaStream_t st,
                             const char *name)
 {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return (int)e;
+    {
+        const int e = fnftb_smem_optin((const void *)kernel, smem);
+        if (e != 0)
+            return e;
     }
     if (g_fnftb_profile_on)
         fnftb_profile_begin(name, st);
@@ -864,9 +864,10 @@ static inline int up_launch_cluster(K kern, const UpArgs &a, unsigned items, uns
                                     const char *name)
 {
     const size_t smem_h = sizeof(cplx) * 4096 + 64 * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
-    if (e != cudaSuccess)
-        return (int)e;
+    const int eo = fnftb_smem_optin((const void *)kern, smem_h);
+    if (eo != 0)
+        return eo;
+    cudaError_t e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(items * CL, 1, 1);
