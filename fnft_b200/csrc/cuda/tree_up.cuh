@@ -584,11 +584,12 @@ DEV cplx *up_cluster_map(cplx *p, unsigned rank)
 // L2N = 13: cluster of 2 (RX = 8, passes at strides 8 and 64, M stage at stride 512); L2N = 14: cluster of 4 (RX = 16,
 // passes at strides 16 and 128, M stage at stride 1024: four elements of a butterfly in each quarter) -- this one
 // replaces the three row-split kernels of the N = 16384 level and their workspace round trip (34 GB -> 17 GB).
-template <int L2N, bool SYM>
-__global__ void __launch_bounds__(128, 3) k_up_smem_cluster(const UpArgs a)
+// L2H: log2 of the positions per CTA (12: 128 threads, three CTAs per SM; 11: 64 threads, six CTAs per SM)
+template <int L2N, int L2H, bool SYM>
+__global__ void __launch_bounds__((1 << L2H) / 32, (L2H == 12) ? 3 : 6) k_up_smem_cluster(const UpArgs a)
 {
     constexpr int E = UpT<SYM>::E;
-    constexpr int N = 1 << L2N, H = 4096, CL = N / H, NT = 128;
+    constexpr int N = 1 << L2N, H = 1 << L2H, CL = N / H, NT = H / 32;
     constexpr int RX = (L2N == 13) ? 8 : 16, L2RX = (L2N == 13) ? 3 : 4;
     extern __shared__ double2 fnftb_smem_up[];
     cplx *S = (cplx *)fnftb_smem_up;
@@ -608,9 +609,13 @@ __global__ void __launch_bounds__(128, 3) k_up_smem_cluster(const UpArgs a)
     const UpPair<SYM> P = up_pair_setup<SYM>(a, sp, s, which == 0 && h == 0);
     up_x_stage<RX, SYM>(a, sp, which, (int)h * H, 0, H, (h >= CL / 2) ? -1.0 : 1.0, P, S, tid, NT);
     __syncthreads();
-    up_p_pass<8, +1>(S, H, L2RX, a.tw, tid, NT);
-    __syncthreads();
-    up_p_pass<8, +1>(S, H, L2RX + 3, a.tw, tid, NT);
+    if constexpr (L2N == 12) {  // 16 * 16 * 16
+        up_p_pass<16, +1>(S, H, 4, a.tw, tid, NT);
+    } else {                    // 8 * 8 * 8 * 16 or 16 * 8 * 8 * 16
+        up_p_pass<8, +1>(S, H, L2RX, a.tw, tid, NT);
+        __syncthreads();
+        up_p_pass<8, +1>(S, H, L2RX + 3, a.tw, tid, NT);
+    }
     up_cluster_sync();
     // M stage: this CTA's share of the N / 16 butterflies; element o + r * st, r < 16, lives in CTA r / (16 / CL)
     cplx *Sr[CL];
@@ -652,9 +657,13 @@ __global__ void __launch_bounds__(128, 3) k_up_smem_cluster(const UpArgs a)
         }
     }
     up_cluster_sync();
-    up_p_pass<8, -1>(S, H, L2RX + 3, a.tw, tid, NT);
-    __syncthreads();
-    up_p_pass<8, -1>(S, H, L2RX, a.tw, tid, NT);
+    if constexpr (L2N == 12) {
+        up_p_pass<16, -1>(S, H, 4, a.tw, tid, NT);
+    } else {
+        up_p_pass<8, -1>(S, H, L2RX + 3, a.tw, tid, NT);
+        __syncthreads();
+        up_p_pass<8, -1>(S, H, L2RX, a.tw, tid, NT);
+    }
     __syncthreads();
     cplx *godd = a.out + (E * sp + which) * (size_t)(2 * N) + N + (size_t)h * H;
     up_f_stage<RX>(S, H, up_top(P.Tn, which), godd, tid, NT);
@@ -861,9 +870,9 @@ static inline int up_pf_distance(int family)
 // cluster launch of k_up_smem_cluster: `items` work items, CL CTAs of 128 threads and 64 KiB each per item
 template <class K>
 static inline int up_launch_cluster(K kern, const UpArgs &a, unsigned items, unsigned CL, cudaStream_t st,
-                                    const char *name)
+                                    const char *name, unsigned H = 4096)
 {
-    const size_t smem_h = sizeof(cplx) * 4096 + 64 * sizeof(double);
+    const size_t smem_h = sizeof(cplx) * H + 64 * sizeof(double);
     const int eo = fnftb_smem_optin((const void *)kern, smem_h);
     if (eo != 0)
         return eo;
@@ -871,7 +880,7 @@ static inline int up_launch_cluster(K kern, const UpArgs &a, unsigned items, uns
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(items * CL, 1, 1);
-    cfg.blockDim = dim3(128, 1, 1);
+    cfg.blockDim = dim3(H / 32, 1, 1);
     cfg.dynamicSmemBytes = smem_h;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -930,8 +939,21 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st, UpArgs *
             const char *e = getenv("FNFT_B200_UP13_CLUSTER");  // 0: one CTA per item (k_up_smem<13>)
             return (e && e[0]) ? atoi(e) : 1;                  // measured 4.84 -> 4.54 ms per 4096 signals
         }();
-        if (a.l2n == 13 && !a.last && knob_cluster)
-            return up_launch_cluster(k_up_smem_cluster<13, SYM>, a, grid, 2, st, names_s[2]);
+        static const int knob_h13 = [] {  // positions per CTA of the N = 8192 cluster kernel: 12 (cluster of 2) or 11 (of 4)
+            const char *e = getenv("FNFT_B200_UP13_L2H");
+            return (e && e[0]) ? atoi(e) : 12;
+        }();
+        static const int knob_cluster12 = [] {  // 1: N = 4096 as a cluster of two CTAs of 2048 positions
+            const char *e = getenv("FNFT_B200_UP12_CLUSTER");
+            return (e && e[0]) ? atoi(e) : 0;
+        }();
+        if (a.l2n == 13 && !a.last && knob_cluster) {
+            if (knob_h13 == 11)
+                return up_launch_cluster(k_up_smem_cluster<13, 11, SYM>, a, grid, 4, st, names_s[2], 2048);
+            return up_launch_cluster(k_up_smem_cluster<13, 12, SYM>, a, grid, 2, st, names_s[2]);
+        }
+        if (a.l2n == 12 && !a.last && knob_cluster12)
+            return up_launch_cluster(k_up_smem_cluster<12, 11, SYM>, a, grid, 2, st, names_s[1], 2048);
         switch (a.l2n) {
         case 11: return up_launch(k_up_smem<11, SYM>, a, grid, 2048 / FNFTB_UP_TPP(11), smem, st, names_s[0]);
         case 12: return up_launch(k_up_smem<12, SYM>, a, grid, 4096 / FNFTB_UP_TPP(12), smem, st, names_s[1]);
@@ -944,7 +966,7 @@ static inline int up_level_t(UpArgs a, int l2smem_max, cudaStream_t st, UpArgs *
     }();
     if (a.l2n == 14 && !a.last && knob_cluster14 && l2smem_max >= 13) {
         a.pf = up_pf_distance(UP_PF_SMEM13);
-        return up_launch_cluster(k_up_smem_cluster<14, SYM>, a, (unsigned)a.B * (unsigned)npairs * (unsigned)E, 4, st,
+        return up_launch_cluster(k_up_smem_cluster<14, 12, SYM>, a, (unsigned)a.B * (unsigned)npairs * (unsigned)E, 4, st,
                                  "tree_up_smem_N16384");
     }
     a.l2row = FNFTB_UP_ROW_L2;

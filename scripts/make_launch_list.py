@@ -11,7 +11,8 @@ def name(e):
     if e["grid"] < 100:
         return "cz_filter"
     for pat, n in (("k_tree_low2", "tree_low2"), ("k_up_smem<11", "tree_up_smem_N2048"), ("k_up_smem<12", "tree_up_smem_N4096"),
-                   ("k_up_smem<13", "tree_up_smem_N8192"), ("k_up_rows_a", "tree_up_rows_a"), ("k_up_cols_cz", "tree_up_cols_cz"),
+                   ("k_up_smem<13", "tree_up_smem_N8192"),
+                   ("k_up_smem_cluster<13", "tree_up_smem_N8192"), ("k_up_smem_cluster<14", "tree_up_smem_N16384"), ("k_up_rows_a", "tree_up_rows_a"), ("k_up_cols_cz", "tree_up_cols_cz"),
                    ("k_up_cols", "tree_up_cols"), ("k_up_rows_c", "tree_up_rows_c"), ("k_cz2_cols_fwd", "cz_cols_fwd"),
                    ("k_cz2_rows", "cz_rows"), ("k_cz2_cols_inv", "cz_cols_inv")):
         if k.startswith(pat):
@@ -24,7 +25,7 @@ for e in d["launches"]:
     a[1] += e["ms"]
     a[2] += e["dram_read_bytes_per_signal"] + e["dram_write_bytes_per_signal"]
 tot = sum(a[1] for a in agg.values())
-print("# Round 2 -- ncu launch list of one config-2 step (current kernels: L2 prefetch, fused last column pass)\n")
+print("# Round 2 -- ncu launch list of one config-2 step (current kernels: L2 prefetch, cluster kernels for N = 8192 / 16384, fused last column pass)\n")
 print("`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none`")
 print("around `python bench.py --steps 1 --warmup 1 --batch 1024 --no-cpu-baseline --no-extras` (`scripts/ncu_traffic.sh`,")
 print("raw CSV reduced by `scripts/make_tree_dram_json.py` into `profiles/tree_dram_bytes.json`; this table:")
