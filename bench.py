@@ -823,6 +823,35 @@ def main():
                          "cpu_baseline": cpu_base.get("c3")}
             idx, res = refs.get("c3", ([], []))
             gate("config3", [compare3(Ka[i], bs[i], ncs[i], res[j], K3) for j, i in enumerate(idx)])
+            # --- inverse direction: the same 8-soliton signals from fnft_nsev_inverse_batch on the GPU
+            # (Darboux kernels), checked against the signals the reference synthesised for config 3
+            lam3, bn3, _ = config3_params()
+            lam_s = np.ascontiguousarray(lam3[g3[0]:g3[1]])
+            bn_s = np.ascontiguousarray(bn3[g3[0]:g3[1]])
+            q_inv = np.zeros((n3, C3["D"]), dtype=np.complex128)
+            rc_inv = np.zeros(n3, dtype=np.int32)
+            L.fnft_nsev_inverse_default_opts.restype = InvOpts
+            oi = L.fnft_nsev_inverse_default_opts()
+            T3a = np.array(C3["T"], dtype=np.float64)
+            pv = lambda a: a.ctypes.data_as(C.c_void_p)
+
+            def run_inv():
+                r = L.fnft_nsev_inverse_batch(C.c_size_t(n3), C.c_size_t(0), None, None, C.c_size_t(K3), pv(lam_s),
+                                              pv(bn_s), C.c_size_t(C3["D"]), pv(q_inv), pv(T3a), C.c_int32(1),
+                                              C.byref(oi), pv(rc_inv))
+                if r != 0:
+                    raise SystemExit("inverse: fnft_nsev_inverse_batch returned %d" % r)
+            dt, _ = timed_call(run_inv)
+            t0 = time.perf_counter()
+            for i in range(4):
+                _soliton_worker((lam3[i], bn3[i], C3["D"], C3["T"]))
+            t_ref1 = (time.perf_counter() - t0) / 4
+            cfgs["3_inverse"] = {"workload": "fnft_nsev_inverse_batch, 8 solitons per signal from (eigenvalue, norming "
+                                             "constant) pairs, D=4096, one batch of %d over %d GPU(s)" % (C3["B"], world),
+                                 "value": C3["B"] / dt, "unit": "signals/s", "ms_per_batch": dt * 1e3,
+                                 "cpu_baseline": {"value": 1.0 / t_ref1, "unit": "signals/s", "cores": 1,
+                                                  "kind": "reference", "sample": "4 signals on one core"}}
+            gate("config3_inverse", [rel_err(q_inv[i], Q3[i]) for i in range(n3)])
         # --- config 4: fnft_kdvv, 4SPLIT4B, pinned host buffers
         n4 = g4[1] - g4[0]
         U = config4_inputs(g4[0], g4[1])
@@ -871,7 +900,7 @@ def main():
     # moves ITS roots by ~1e-7 (tests/test_gpu_parity.py::test_nsep_config5_roots_against_long_double);
     # the gate for this configuration is therefore 1e-6 on the positions and exact point counts.
     bounds = {"config5": 1e-6}
-    names = ["config2_device", "config2_e2e", "config2_strong", "config3", "config4", "config5"]
+    names = ["config2_device", "config2_e2e", "config2_strong", "config3", "config3_inverse", "config4", "config5"]
     parity, ok = None, True
     if have_ref:
         parity = {"metric": "misc_rel_err(ours, reference) per signal (bound states: relative error per "

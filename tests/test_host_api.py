@@ -184,3 +184,64 @@ def test_c_caller_compiles_and_links_against_the_drop_in_headers(F, tmp_path):
                            "-L" + os.path.join(ROOT, "fnft_b200", "lib"), "-lfnft_b200",
                            "-Wl,-rpath," + os.path.join(ROOT, "fnft_b200", "lib"), "-lm", "-o", exe])
     assert os.path.exists(exe)
+
+
+# ------------------------------------------------------------------ inverse transform: host logic without a GPU
+def _inv():
+    import inverse_bindings as IB
+    return IB
+
+
+def test_inverse_opts_layout_and_defaults(F):
+    # include/fnft_nsev_inverse.h:151-158 (32 bytes on LP64), defaults of src/fnft_nsev_inverse.c:26-33
+    IB = _inv()
+    assert C.sizeof(IB.InverseOpts) == 32
+    assert [getattr(IB.InverseOpts, f).offset for f, _ in IB.InverseOpts._fields_] == [0, 4, 8, 12, 16, 24]
+    o = IB.default_opts(F.lib())
+    assert (o.discretization, o.contspec_type, o.contspec_inversion_method, o.discspec_type) == (4, 0, 0, 0)
+    assert (o.max_iter, o.oversampling_factor) == (100, 8)
+
+
+def test_inverse_xi_grid_matches_the_reference_formula(F):
+    # fnft_nsev_inverse_XI, src/fnft_nsev_inverse.c:40-66: xi of z = exp(2 pi i (M/2+1)/M) and of z = -1
+    IB = _inv()
+    for D, M, T in ((256, 512, (-2.0, 2.0)), (1024, 1024, (-7.0, 9.0))):
+        for disc in (4, 0):
+            ret, XI = IB.inverse_XI(F.lib(), D, T, M, disc)
+            assert ret == 0
+            eps_t = (T[1] - T[0]) / (D - 1)
+            z0 = np.exp(2j * np.pi * (M // 2 + 1) / M)
+            want = np.array([(np.log(z0) / (2j * eps_t)).real, (np.log(-1 + 0j) / (2j * eps_t)).real])
+            assert np.allclose(XI, want, rtol=1e-15, atol=0)
+            assert XI[0] < 0 < XI[1]
+    assert IB.inverse_XI(F.lib(), 1, (-1.0, 1.0), 8, 4)[0] != 0          # D < 2
+    assert IB.inverse_XI(F.lib(), 8, (1.0, -1.0), 8, 4)[0] != 0          # T
+
+
+def test_inverse_argument_checks_need_no_gpu(F):
+    # the checks of src/fnft_nsev_inverse.c:134-172 run before any device work: the same codes with or without a GPU
+    IB = _inv()
+    F.lib().fnft_errwarn_setprintf(None)
+    bs = np.array([0.3 + 1.0j, -0.2 + 0.5j])
+    nc = np.array([1.0 + 0j, 2.0 - 1j])
+    cs = np.ones(64, dtype=np.complex128)
+    XI = np.array([-1.0, 1.0])
+    o = IB.default_opts(F.lib())
+    E_INVALID, E_SANITY = 2, 7
+    assert IB.nsev_inverse(F.lib(), cs[:63], XI, None, None, 32, (-1, 1), 1, o)[0] == E_INVALID     # odd M
+    assert IB.nsev_inverse(F.lib(), cs[:16], XI, None, None, 32, (-1, 1), 1, o)[0] == E_INVALID     # M < D
+    assert IB.nsev_inverse(F.lib(), cs, XI, None, None, 48, (-1, 1), 1, o)[0] == E_INVALID          # D not 2^k
+    assert IB.nsev_inverse(F.lib(), None, None, bs, nc, 32, (1, -1), 1, o)[0] == E_INVALID          # T
+    assert IB.nsev_inverse(F.lib(), None, None, bs, nc, 32, (-1, 1), 2, o)[0] == E_INVALID          # kappa
+    assert IB.nsev_inverse(F.lib(), None, None, bs, nc, 32, (-1, 1), -1, o)[0] == E_SANITY          # solitons, defocusing
+    assert IB.nsev_inverse(F.lib(), None, None, np.conj(bs), nc, 32, (-1, 1), 1, o)[0] == E_SANITY  # lower half plane
+    assert IB.nsev_inverse(F.lib(), None, None, None, None, 32, (-1, 1), 1, o)[0] == E_SANITY       # nothing given
+    assert IB.nsev_inverse(F.lib(), cs, None, None, None, 32, (-1, 1), 1, o)[0] == E_INVALID        # XI missing
+    o.discretization = 11
+    assert IB.nsev_inverse(F.lib(), None, None, bs, nc, 32, (-1, 1), 1, o)[0] == E_INVALID          # 2SPLIT4B
+    # private symbols: argument checks of fnft__nse_finvscatter (:249-265) and fnft__poly_specfact (:31-38)
+    tm = np.zeros(4 * 9, dtype=np.complex128)
+    assert IB.nse_finvscatter(F.lib(), tm, -0.1, 1, 4)[0] == E_INVALID      # eps_t
+    assert IB.nse_finvscatter(F.lib(), tm, 0.1, 0, 4)[0] == E_INVALID       # kappa
+    assert IB.nse_finvscatter(F.lib(), tm, 0.1, 1, 11)[0] != 0              # D = deg / 2 = 4 but not invertible scheme
+    assert IB.poly_specfact(F.lib(), np.ones(4, dtype=np.complex128), 0, 1)[0] == E_INVALID   # oversampling 0
