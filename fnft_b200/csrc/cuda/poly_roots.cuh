@@ -183,15 +183,29 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth(const RootsArgs a)
             }
             if (gdone != (1u << R) - 1u) {
                 // Horner for p, p' and the running error bound: p(z) for |z| <= 1, q(1/z) = p(z)/z^m else
-                for (int k = 0; k <= m; ++k) {
-                    const cplx cf = LDG(&c[k]), cb = LDG(&c[m - k]);
-                    const double af = LDG(&ac[k]), ab = LDG(&ac[m - k]);
+                if constexpr (R == 1) {
+                    // one coefficient stream, in the direction this root needs (same arithmetic as below)
+                    const cplx *cp = small[0] ? c : c + m;
+                    const double *ap = small[0] ? ac : ac + m;
+                    const int stp = small[0] ? 1 : -1;
+                    for (int k = 0; k <= m; ++k) {
+                        const cplx ck = LDG(cp + stp * k);
+                        const double ak = LDG(ap + stp * k);
+                        dp[0] = cadd(cmul(dp[0], w[0]), p[0]);
+                        p[0] = cadd(cmul(p[0], w[0]), ck);
+                        e[0] = e[0] * aw[0] + ak;
+                    }
+                } else {
+                    for (int k = 0; k <= m; ++k) {
+                        const cplx cf = LDG(&c[k]), cb = LDG(&c[m - k]);
+                        const double af = LDG(&ac[k]), ab = LDG(&ac[m - k]);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const cplx ck = small[r] ? cf : cb;
-                        dp[r] = cadd(cmul(dp[r], w[r]), p[r]);
-                        p[r] = cadd(cmul(p[r], w[r]), ck);
-                        e[r] = e[r] * aw[r] + (small[r] ? af : ab);
+                        for (int r = 0; r < R; ++r) {
+                            const cplx ck = small[r] ? cf : cb;
+                            dp[r] = cadd(cmul(dp[r], w[r]), p[r]);
+                            p[r] = cadd(cmul(p[r], w[r]), ck);
+                            e[r] = e[r] * aw[r] + (small[r] ? af : ab);
+                        }
                     }
                 }
 #pragma unroll
