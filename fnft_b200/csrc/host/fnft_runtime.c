@@ -73,29 +73,48 @@ int fnftb__pipe_chunks(void)
 
 /* Size of the chunk that starts at signal b0 in a pipelined batch loop.  The copy-in of the
  * first chunk and the copy-out of the last one are the only transfers that nothing overlaps,
- * so the sizes taper at both ends: c/4, c/2, c, ..., c, c/2, c/4 (FNFT_B200_PIPE_TAPER=0: off). */
+ * so the sizes taper at both ends over `depth` halvings (FNFT_B200_PIPE_TAPER, 0: off, default 2):
+ * c/4, c/2, c, ..., c, c/2, c/4 for depth 2. */
 FNFT_UINT fnftb__pipe_step(FNFT_UINT b0, FNFT_UINT B, FNFT_UINT chunk)
 {
     static int taper = -1;
     if (taper < 0) {
         const char *e = getenv("FNFT_B200_PIPE_TAPER");
-        taper = (e && e[0]) ? atoi(e) : 1;
+        taper = (e && e[0]) ? atoi(e) : 2;
+        if (taper == 1)
+            taper = 2; /* the round-1 meaning of "on" */
+        if (taper > 5)
+            taper = 5;
     }
-    FNFT_UINT step = chunk;
-    if (!taper || b0 >= B || chunk < 64)
-        return step;
-    const FNFT_UINT rem = B - b0, q4 = chunk / 4, h2 = chunk / 2;
-    if (b0 == 0)
-        step = q4;
-    else if (b0 == q4)
-        step = h2;
-    if (rem <= q4)
-        step = rem;
-    else if (rem <= q4 + h2)
-        step = rem - q4;
-    else if (step > rem - q4 - h2)
-        step = rem - q4 - h2;
-    return step;
+    if (!taper || b0 >= B || chunk < ((FNFT_UINT)16 << taper))
+        return chunk;
+    /* ramp: chunk >> taper, ..., chunk >> 1; its total length */
+    FNFT_UINT ramp = 0;
+    for (int k = taper; k >= 1; k--)
+        ramp += chunk >> k;
+    if (B < 2 * ramp + chunk)
+        return chunk; /* too small a batch for both ramps */
+    /* inside the leading ramp? */
+    FNFT_UINT pos = 0;
+    for (int k = taper; k >= 1; k--) {
+        if (b0 == pos)
+            return chunk >> k;
+        pos += chunk >> k;
+    }
+    /* trailing ramp: the last `ramp` signals, sizes chunk >> 1, ..., chunk >> taper */
+    const FNFT_UINT rem = B - b0;
+    if (rem <= ramp) {
+        FNFT_UINT left = ramp;
+        for (int k = 1; k <= taper; k++) {
+            if (rem == left)
+                return chunk >> k;
+            left -= chunk >> k;
+        }
+        return rem; /* not on a ramp boundary (cannot happen when the loop only uses these steps) */
+    }
+    /* middle: full chunks, the last one shortened so that the trailing ramp starts exactly */
+    const FNFT_UINT mid = rem - ramp;
+    return mid < chunk ? mid : chunk;
 }
 
 FNFT_INT fnft_b200_device_count(void) { return (FNFT_INT)fnftb_device_count(); }
