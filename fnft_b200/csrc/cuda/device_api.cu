@@ -165,6 +165,8 @@ struct fnftb_ctx {
     int slow_wsel = 0;
     const cplx *rpre = nullptr;
     Buf rprebuf;
+    // continuous spectrum by segments (signals longer than one product tree): accumulated and current (a, b)
+    Buf segacc, segcur;
     // pipelined host transfers (fnftb_pipeline_begin): two slots, copy streams, events
     int pipe_on = 0, slot = 0;
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
@@ -320,7 +322,7 @@ void fnftb_ctx_destroy(fnftb_ctx *c)
                   &c->fpoly, &c->vals, &c->roots, &c->nraw, &c->nkept,
                   &c->rt_roots, &c->rt_absc, &c->rt_lg, &c->rt_hull, &c->rt_info, &c->rt_lam, &c->rt_cnt, &c->rs_a, &c->rs_b, &c->qrot, &c->qsub,
                   &c->qslot[0], &c->qslot[1], &c->outslot[0], &c->outslot[1], &c->stslot[0], &c->stslot[1],
-                  &c->rprebuf, &c->koff};
+                  &c->rprebuf, &c->koff, &c->segacc, &c->segcur};
     for (Buf *b : all)
         release(*b);
     if (c->inv_ws && c->inv_free)
@@ -1701,6 +1703,151 @@ int fnftb_normconsts(fnftb_ctx *c, const fnftb_bound_desc *d, const int32_t *K_h
     if (b_host)
         CU(cudaMemcpyAsync(b_host, c->bout.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Continuous spectrum by SEGMENTS, for signals whose transfer matrix is longer than one product tree can hold
+// (degree > 2^18).  The reference has no such limit (src/private/fnft__poly_fmult.c:404-445 multiplies whatever
+// it is given); here the host (fnft_nsev.c: nsev_pass_segmented) cuts the signal into pieces the tree can
+// multiply, gets the scattering coefficients (a_s, b_s)(xi) of every piece on its own time window through the
+// normal path (tree + chirp-z, contspec type AB), and chains them on the real xi grid:
+//     a <- a_s a - kappa conj(b_s) b,     b <- b_s a + conj(a_s) b        (pieces in order of increasing time)
+// which is the product of the pieces' transfer matrices [a_s, -kappa b_s*; b_s, a_s*] evaluated point by point
+// instead of coefficient by coefficient.  The epilogue of src/fnft_nsev.c:846-876 follows on the chained values.
+// ---------------------------------------------------------------------------------------
+__global__ void k_seg_compose(cplx *acc, const cplx *cur, size_t n, int M, double kap, int first)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const size_t s = i / (size_t)M, m = i % (size_t)M;
+    const cplx as = cur[s * 2 * M + m], bs = cur[s * 2 * M + M + m];
+    if (first) {
+        acc[s * 2 * M + m] = as;
+        acc[s * 2 * M + M + m] = bs;
+        return;
+    }
+    const cplx a = acc[s * 2 * M + m], b = acc[s * 2 * M + M + m];
+    cplx an = cmul(as, a);
+    cfmac(an, cscale(b, -kap), bs);  // - kappa * b * conj(b_s)
+    cplx bn = cmul(bs, a);
+    cfmac(bn, b, as);                // + b * conj(a_s)
+    acc[s * 2 * M + m] = an;
+    acc[s * 2 * M + M + m] = bn;
+}
+
+__global__ void k_seg_finish(const cplx *acc, cplx *out, size_t out_sstride, size_t n, int M, int cstype, int *status)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const size_t s = i / (size_t)M, m = i % (size_t)M;
+    const cplx a = acc[s * 2 * M + m], b = acc[s * 2 * M + M + m];
+    cplx *o = out + s * out_sstride;
+    size_t off = 0;
+    if (cstype == 0 || cstype == 2) {
+        if (a.x == 0.0 && a.y == 0.0) {
+            status[s] = 3;  // FNFT_EC_DIV_BY_ZERO, src/fnft_nsev.c:850-852
+            o[m] = make_cplx(NAN, NAN);
+        } else {
+            o[m] = cdiv(b, a);
+        }
+        off = (size_t)M;
+    }
+    if (cstype == 1 || cstype == 2) {
+        o[off + m] = a;
+        o[off + M + m] = b;
+    }
+}
+
+extern "C" {
+
+size_t fnftb_tree_max_samples(int scheme, int deg0)
+{
+    if (deg0 < 1)
+        return 0;
+    const size_t dtree = (size_t)tree_leaf_degree(scheme, deg0);
+    size_t n = 1;
+    while (2 * n * dtree <= ((size_t)1 << 18))  // the same bound as fnftb_fscatter
+        n *= 2;
+    // FNFT_B200_TREE_MAX_SAMPLES: a smaller limit (tests exercise the segmented path at sizes the direct path
+    // also handles)
+    static const int knob = tree_knob("FNFT_B200_TREE_MAX_SAMPLES", 0);
+    if (knob >= 2 && (size_t)knob < n)
+        n = (size_t)knob;
+    return n;
+}
+
+// stage B pieces of Dseg samples each, taken with a row stride of `stride` samples from q (host or device)
+int fnftb_set_signals_strided(fnftb_ctx *c, size_t B, size_t Dseg, const void *q, size_t stride, int on_device)
+{
+    if (!c || !q || B == 0 || Dseg == 0 || stride < Dseg)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    c->B = B;
+    c->D = Dseg;
+    c->have_box3 = 0;
+    c->slow_wsel = 0;
+    c->rpre = nullptr;
+    RC(ensure(c->qbuf, B * Dseg * sizeof(cplx)));
+    CU(cudaMemcpy2DAsync(c->qbuf.p, Dseg * sizeof(cplx), q, stride * sizeof(cplx), Dseg * sizeof(cplx), B,
+                         on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
+    c->q = (const cplx *)c->qbuf.p;
+    c->r = nullptr;
+    return 0;
+}
+
+// device buffer [B][2M] that receives the (a, b) of the current piece (fnftb_contspec with on_device = 1)
+void *fnftb_seg_buffer(fnftb_ctx *c, size_t B, size_t M)
+{
+    if (!c || cudaSetDevice(c->device) != cudaSuccess)
+        return nullptr;
+    if (ensure(c->segcur, B * 2 * M * sizeof(cplx)) != 0 || ensure(c->segacc, B * 2 * M * sizeof(cplx)) != 0)
+        return nullptr;
+    return c->segcur.p;
+}
+
+int fnftb_seg_compose(fnftb_ctx *c, size_t B, size_t M, int kappa, int first)
+{
+    if (!c || B == 0 || M == 0 || !c->segcur.p || !c->segacc.p)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t n = B * M;
+    k_seg_compose<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>((cplx *)c->segacc.p, (const cplx *)c->segcur.p, n, (int)M,
+                                                                (double)kappa, first);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// epilogue on the chained values; out: [B][out_sstride] (host, or device if on_device); status_host may be NULL
+int fnftb_seg_finish(fnftb_ctx *c, size_t B, size_t M, int cstype, void *out, size_t out_sstride, int on_device,
+                     int32_t *status_host)
+{
+    if (!c || !out || B == 0 || M == 0 || !c->segacc.p)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    RC(ensure(c->status, B * sizeof(int)));
+    CU(cudaMemsetAsync(c->status.p, 0, B * sizeof(int), c->st));
+    cplx *dst = (cplx *)out;
+    if (!on_device) {
+        RC(ensure(c->outbuf, B * out_sstride * sizeof(cplx)));
+        dst = (cplx *)c->outbuf.p;
+    }
+    const size_t n = B * M;
+    k_seg_finish<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>((const cplx *)c->segacc.p, dst, out_sstride, n, (int)M, cstype,
+                                                               (int *)c->status.p);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    if (!on_device) {
+        CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+        if (status_host)
+            CU(cudaMemcpyAsync(status_host, c->status.p, B * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
     return 0;
 }
 

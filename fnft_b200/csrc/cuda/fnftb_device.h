@@ -165,6 +165,19 @@ int fnftb_set_polynomial(fnftb_ctx *ctx, size_t deg, const void *p_host);
 int fnftb_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, void *out,
                    size_t out_sstride, int on_device, int32_t *status_host);
 
+/* ---- continuous spectrum by segments (signals longer than one product tree) ------------ */
+/* Largest number of samples (a power of two) whose transfer matrix one product tree can hold for this scheme. */
+size_t fnftb_tree_max_samples(int scheme, int deg0);
+/* Stage B pieces of Dseg samples, read with a row stride of `stride` samples from q (host or device pointer). */
+int fnftb_set_signals_strided(fnftb_ctx *ctx, size_t B, size_t Dseg, const void *q, size_t stride, int on_device);
+/* Device buffer [B][2M] for the (a, b) of the current piece (target of fnftb_contspec with on_device = 1). */
+void *fnftb_seg_buffer(fnftb_ctx *ctx, size_t B, size_t M);
+/* acc = cur (first != 0) or acc = [a_s, -kappa b_s*; b_s, a_s*] acc, point by point on the real xi grid. */
+int fnftb_seg_compose(fnftb_ctx *ctx, size_t B, size_t M, int kappa, int first);
+/* Epilogue of src/fnft_nsev.c:846-876 on the chained (a, b): cstype 0 rho, 1 a|b, 2 rho|a|b. */
+int fnftb_seg_finish(fnftb_ctx *ctx, size_t B, size_t M, int cstype, void *out, size_t out_sstride, int on_device,
+                     int32_t *status_host);
+
 /* Continuous spectrum of the staged signals with the slow discretizations BO (upsampling 1),
  * CF4_2 and CF4_3 (upsampling 2 and 3; the staged signals are the resampled ones): one product of D step matrices
  * per spectral point, src/fnft_nsev.c:794-814 + epilogue :836-876.  Uses mode / cstype / M / xi0 /

@@ -47,13 +47,12 @@ static FNFT_UINT contspec_len(fnft_nsev_cstype_t t, FNFT_UINT M)
  * Mirrors nsev_compute_contspec (src/fnft_nsev.c:744-891) for the polynomial
  * (fast) discretizations: chirp constants :822-827, epilogue :846-876.
  */
-static FNFT_INT nsev_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL const *T,
-                                    FNFT_UINT M, FNFT_REAL const *XI, fnft_nsev_opts_t const *opts,
-                                    FNFT_COMPLEX *out, int on_device, int32_t *status)
+static FNFT_INT nsev_contspec_chunk_eps(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL const *T, FNFT_REAL eps_t,
+                                        FNFT_UINT M, FNFT_REAL const *XI, fnft_nsev_opts_t const *opts,
+                                        FNFT_COMPLEX *out, int on_device, int32_t *status, int unit_circle)
 {
     const fnft_nse_discretization_t disc = opts->discretization;
     const FNFT_REAL step_div = (FNFT_REAL)(fnftb__nse_degree(disc) * fnftb__nse_upsampling(disc));
-    const FNFT_REAL eps_t = (T[1] - T[0]) / (D_given - 1);
     const FNFT_REAL eps_xi = (XI[1] - XI[0]) / (M - 1);
     fnftb_contspec_desc cd;
     memset(&cd, 0, sizeof(cd));
@@ -69,6 +68,11 @@ static FNFT_INT nsev_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL
     const FNFT_COMPLEX A = cexp(2 * I * (-XI[0]) * eps_t / step_div);
     fnftb__logpolar(V, &cd.lwr, &cd.lwi);
     fnftb__logpolar(A, &cd.lar, &cd.lai);
+    /* The rounded V and A are a few 1e-17 off the unit circle, and the reference evaluates at A V^-m as rounded
+     * (|z_m|^deg = 1 + O(m deg 1e-17)).  The chaining of segments relies on |z| = 1 (second row of a piece from
+     * the conjugates of the first), so there the points are put exactly on the circle. */
+    if (unit_circle)
+        cd.lwr = cd.lar = 0.0;
     cd.xi0 = XI[0];
     cd.eps_xi = eps_xi;
     FNFT_INT ret_code;
@@ -82,6 +86,57 @@ static FNFT_INT nsev_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL
     if (ret_code != FNFT_SUCCESS)
         return E_SUBROUTINE(ret_code);
     if (fnftb_contspec(ctx, &cd, out, contspec_len(opts->contspec_type, M), on_device, status) != 0)
+        return E_DEVICE;
+    return FNFT_SUCCESS;
+}
+
+static FNFT_INT nsev_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT_REAL const *T,
+                                    FNFT_UINT M, FNFT_REAL const *XI, fnft_nsev_opts_t const *opts,
+                                    FNFT_COMPLEX *out, int on_device, int32_t *status)
+{
+    return nsev_contspec_chunk_eps(ctx, D_given, T, (T[1] - T[0]) / (D_given - 1), M, XI, opts, out, on_device,
+                                   status, 0);
+}
+
+/*
+ * Continuous spectrum of nb signals that are LONGER than one product tree can hold (transfer matrix of degree
+ * > 2^18; the reference multiplies polynomials of any length, src/private/fnft__poly_fmult.c:404-445).  The
+ * signals are cut into nseg pieces of nearly equal length; piece s (samples n0 .. n1-1, window
+ * [T0 + n0 eps_t, T0 + (n1-1) eps_t], same step) goes through the normal path -- leaves, product tree,
+ * chirp-z, contspec type AB -- which gives its scattering coefficients (a_s, b_s) on the xi grid, and the
+ * pieces are chained on the device in order of increasing time (fnftb_seg_compose).  On the real axis this is
+ * the same product of transfer matrices, taken point by point instead of coefficient by coefficient.
+ */
+static FNFT_INT nsev_contspec_segmented(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT D, FNFT_UINT Dseg_max,
+                                        FNFT_COMPLEX const *q, FNFT_REAL const *T, FNFT_REAL eps_t, FNFT_UINT M,
+                                        FNFT_REAL const *XI, FNFT_INT kappa, fnft_nsev_opts_t const *opts,
+                                        fnftb_scatter_desc const *sd, FNFT_COMPLEX *out, int on_device,
+                                        int32_t *status)
+{
+    const FNFT_UINT nseg = (D + Dseg_max - 1) / Dseg_max;
+    const FNFT_UINT base = D / nseg, extra = D % nseg;
+    fnft_nsev_opts_t o = *opts;
+    o.contspec_type = fnft_nsev_cstype_AB;
+    FNFT_COMPLEX *cur = (FNFT_COMPLEX *)fnftb_seg_buffer(ctx, nb, M);
+    if (cur == NULL)
+        return E_DEVICE;
+    FNFT_UINT n0 = 0;
+    for (FNFT_UINT s = 0; s < nseg; s++) {
+        const FNFT_UINT len = base + (s < extra ? 1 : 0);
+        const FNFT_REAL Ts[2] = {T[0] + n0 * eps_t, T[0] + (n0 + len - 1) * eps_t};
+        if (fnftb_set_signals_strided(ctx, nb, len, q + n0, D, on_device) != 0)
+            return E_DEVICE;
+        if (fnftb_fscatter(ctx, sd) != 0)
+            return E_DEVICE;
+        FNFT_INT ret_code = nsev_contspec_chunk_eps(ctx, len, Ts, eps_t, M, XI, &o, cur, 1, NULL, 1);
+        if (ret_code != FNFT_SUCCESS)
+            return E_SUBROUTINE(ret_code);
+        if (fnftb_seg_compose(ctx, nb, M, (int)kappa, s == 0) != 0)
+            return E_DEVICE;
+        n0 += len;
+    }
+    if (fnftb_seg_finish(ctx, nb, M, (int)opts->contspec_type, out, contspec_len(opts->contspec_type, M), on_device,
+                         status) != 0)
         return E_DEVICE;
     return FNFT_SUCCESS;
 }
@@ -219,9 +274,21 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     const FNFT_UINT D_eff = D_given * upsampling;
     const FNFT_UINT cs_len = want_contspec ? contspec_len(opts->contspec_type, M) : 0;
 
+    /* signals whose transfer matrix is longer than one product tree: continuous spectrum by segments */
+    const FNFT_UINT Dtree_max = slow ? 0 : (FNFT_UINT)fnftb_tree_max_samples((int)akns, (int)deg0);
+    const int segmented = (!slow && want_contspec && D_eff > Dtree_max);
+    if (!slow && D_eff > Dtree_max) {
+        if (want_contspec && (upsampling != 1 || Dsub_req != 0))
+            return E_NOT_YET_IMPLEMENTED(D, Signals this long are only supported without resampling and Richardson extrapolation.);
+        if (want_discspec && bsloc != fnft_nsev_bsloc_NEWTON)
+            return E_NOT_YET_IMPLEMENTED(D, Signals this long need bound_state_localization NEWTON.);
+    }
+    const FNFT_UINT D_ws = segmented ? Dtree_max : D_eff; /* what the tree workspace has to hold at a time */
+
     /* the bound-state kernels keep eigenvalue, flag, a, a' and b per entry of the [nb][Kmax] arrays */
-    size_t chunk = fnftb_max_chunk_ex(ctx, D_eff, slow ? 1 : (int)deg0, (want_contspec && !slow) ? M : 0, 2,
-                                      want_discspec ? Kmax * (4 * sizeof(FNFT_COMPLEX) + sizeof(int32_t)) : 0,
+    size_t chunk = fnftb_max_chunk_ex(ctx, D_ws, slow ? 1 : (int)deg0, (want_contspec && !slow) ? M : 0, 2,
+                                      (want_discspec ? Kmax * (4 * sizeof(FNFT_COMPLEX) + sizeof(int32_t)) : 0) +
+                                          (segmented ? (4 * M + (want_discspec ? D : 0)) * sizeof(FNFT_COMPLEX) : 0),
                                       fnftb__workspace_limit());
     if (chunk > B)
         chunk = B;
@@ -229,7 +296,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
      * neighbouring chunks with the kernels (fnftb_pipeline_*); at least 8 chunks for
      * large batches so that only a small first copy-in / last copy-out stay exposed. */
     const int piped = (!devptr && want_contspec && !want_discspec && B >= 16 && fnftb__pipe_chunks() > 0 &&
-                       Dsub_req == 0 && !slow);
+                       Dsub_req == 0 && !slow && !segmented);
     if (piped) {
         const size_t nch = (size_t)fnftb__pipe_chunks();
         size_t c8 = (B + nch - 1) / nch;
@@ -297,7 +364,12 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                                                  Kmax, bound_states + b0 * Kmax, opts);
             CHECK_RETCODE(ret_code, leave_fun);
         }
-        if (nb > 0) {
+        if (nb > 0 && segmented) {
+            ret_code = nsev_contspec_segmented(ctx, nb, D, Dtree_max, q + b0 * D, T, eps_t, M, XI, kappa, opts, &sd,
+                                               contspec + b0 * cs_len, devptr, st_cur);
+            CHECK_RETCODE(ret_code, leave_fun);
+        }
+        if (nb > 0 && (!segmented || want_discspec)) {
             /* preprocessing (src/fnft_nsev.c:272): plain copy for upsampling 1; the
              * 4SPLIT4 schemes resample on the device */
             if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, devptr) != 0) {
@@ -337,7 +409,9 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
 
             /* transfer matrix: nse_fscatter (src/fnft_nsev.c:527).  The Newton path never
              * reads it, so it is only built when a continuous spectrum is wanted. */
-            if (want_contspec && slow) {
+            if (segmented) {
+                /* done above */
+            } else if (want_contspec && slow) {
                 ret_code = nsev_slow_contspec_chunk(ctx, D_given, T, M, XI, kappa, (int)upsampling, opts,
                                                     contspec + b0 * cs_len, devptr, st_cur);
                 CHECK_RETCODE(ret_code, leave_fun);
