@@ -1763,6 +1763,52 @@ __global__ void k_seg_finish(const cplx *acc, cplx *out, size_t out_sstride, siz
     }
 }
 
+// general 2x2 chaining (KdV): cur = [H12 | H22 | H11 | H21] of the piece at the same points z_m, acc = second column
+// (v1, v2) of the product of the pieces so far; later pieces multiply from the left
+__global__ void k_seg_compose_general(cplx *acc, const cplx *cur, size_t n, int M, int first)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const size_t s = i / (size_t)M, m = i % (size_t)M;
+    const cplx *c = cur + s * 4 * M;
+    cplx *a = acc + s * 2 * M;
+    if (first) {
+        a[m] = c[m];
+        a[M + m] = c[M + m];
+        return;
+    }
+    const cplx v1 = a[m], v2 = a[M + m];
+    cplx n1 = cmul(c[2 * (size_t)M + m], v1);
+    cfma(n1, c[m], v2);
+    cplx n2 = cmul(c[3 * (size_t)M + m], v1);
+    cfma(n2, c[M + m], v2);
+    a[m] = n1;
+    a[M + m] = n2;
+}
+
+// src/fnft_kdvv.c:186-203 on the chained (H12, H22); same formulas as the epilogue of blk_cz_cols_inv
+__global__ void k_seg_finish_kdv(const cplx *acc, cplx *out, size_t out_sstride, size_t n, int M, double xi0, double eps_xi,
+                                 double kdv_ph, double kdv_sqrtz)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const size_t s = i / (size_t)M, m = i % (size_t)M;
+    const double xi = -xi0 - (double)m * eps_xi;
+    cplx h12 = acc[s * 2 * M + m];
+    const cplx h22 = acc[s * 2 * M + M + m];
+    double sn, cs;
+    if (kdv_sqrtz != 0.0) {
+        sincos(xi * kdv_sqrtz, &sn, &cs);
+        h12 = cdiv(h12, make_cplx(cs, sn));
+    }
+    sincos(2.0 * xi * kdv_ph, &sn, &cs);
+    const cplx num = cmul(make_cplx(cs, sn), h12);
+    const cplx den = make_cplx(-2.0 * xi * h22.y - h12.x, 2.0 * xi * h22.x - h12.y);
+    out[s * out_sstride + m] = cdiv(num, den);
+}
+
 extern "C" {
 
 size_t fnftb_tree_max_samples(int scheme, int deg0)
@@ -1801,13 +1847,49 @@ int fnftb_set_signals_strided(fnftb_ctx *c, size_t B, size_t Dseg, const void *q
 }
 
 // device buffer [B][2M] that receives the (a, b) of the current piece (fnftb_contspec with on_device = 1)
-void *fnftb_seg_buffer(fnftb_ctx *c, size_t B, size_t M)
+void *fnftb_seg_buffer(fnftb_ctx *c, size_t B, size_t M, int nent)
 {
-    if (!c || cudaSetDevice(c->device) != cudaSuccess)
+    if (!c || nent < 2 || nent > 4 || cudaSetDevice(c->device) != cudaSuccess)
         return nullptr;
-    if (ensure(c->segcur, B * 2 * M * sizeof(cplx)) != 0 || ensure(c->segacc, B * 2 * M * sizeof(cplx)) != 0)
+    if (ensure(c->segcur, B * (size_t)nent * M * sizeof(cplx)) != 0 || ensure(c->segacc, B * 2 * M * sizeof(cplx)) != 0)
         return nullptr;
     return c->segcur.p;
+}
+
+int fnftb_seg_compose_general(fnftb_ctx *c, size_t B, size_t M, int first)
+{
+    if (!c || B == 0 || M == 0 || !c->segcur.p || !c->segacc.p)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    const size_t n = B * M;
+    k_seg_compose_general<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>((cplx *)c->segacc.p, (const cplx *)c->segcur.p, n,
+                                                                        (int)M, first);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int fnftb_seg_finish_kdv(fnftb_ctx *c, size_t B, size_t M, double xi0, double eps_xi, double kdv_ph, double kdv_sqrtz,
+                         void *out, size_t out_sstride, int on_device)
+{
+    if (!c || !out || B == 0 || M == 0 || !c->segacc.p)
+        return fail(-2, "invalid argument", __FILE__, __LINE__);
+    CU(cudaSetDevice(c->device));
+    cplx *dst = (cplx *)out;
+    if (!on_device) {
+        RC(ensure(c->outbuf, B * out_sstride * sizeof(cplx)));
+        dst = (cplx *)c->outbuf.p;
+    }
+    const size_t n = B * M;
+    k_seg_finish_kdv<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>((const cplx *)c->segacc.p, dst, out_sstride, n, (int)M, xi0,
+                                                                   eps_xi, kdv_ph, kdv_sqrtz);
+    ++g_fnftb_launch_count;
+    CU(cudaGetLastError());
+    if (!on_device) {
+        CU(cudaMemcpyAsync(out, dst, B * out_sstride * sizeof(cplx), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    return 0;
 }
 
 int fnftb_seg_compose(fnftb_ctx *c, size_t B, size_t M, int kappa, int first)

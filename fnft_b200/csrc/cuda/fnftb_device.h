@@ -165,13 +165,19 @@ int fnftb_set_polynomial(fnftb_ctx *ctx, size_t deg, const void *p_host);
 int fnftb_contspec(fnftb_ctx *ctx, const fnftb_contspec_desc *desc, void *out,
                    size_t out_sstride, int on_device, int32_t *status_host);
 
+/* general 2x2 chaining of raw transfer-matrix values (fnft_kdvv): acc = second column of the product so far */
+int fnftb_seg_compose_general(fnftb_ctx *ctx, size_t B, size_t M, int first);
+/* epilogue of src/fnft_kdvv.c:186-203 on the chained (H12, H22) */
+int fnftb_seg_finish_kdv(fnftb_ctx *ctx, size_t B, size_t M, double xi0, double eps_xi, double kdv_ph, double kdv_sqrtz,
+                         void *out, size_t out_sstride, int on_device);
 /* ---- continuous spectrum by segments (signals longer than one product tree) ------------ */
 /* Largest number of samples (a power of two) whose transfer matrix one product tree can hold for this scheme. */
 size_t fnftb_tree_max_samples(int scheme, int deg0);
 /* Stage B pieces of Dseg samples, read with a row stride of `stride` samples from q (host or device pointer). */
 int fnftb_set_signals_strided(fnftb_ctx *ctx, size_t B, size_t Dseg, const void *q, size_t stride, int on_device);
-/* Device buffer [B][2M] for the (a, b) of the current piece (target of fnftb_contspec with on_device = 1). */
-void *fnftb_seg_buffer(fnftb_ctx *ctx, size_t B, size_t M);
+/* Device buffer [B][nent*M] for the values of the current piece (target of fnftb_contspec with on_device = 1):
+ * nent = 2: (a, b) of fnft_nsev; nent = 4: [H12 | H22 | H11 | H21] of fnft_kdvv (FNFTB_MODE_RAW). */
+void *fnftb_seg_buffer(fnftb_ctx *ctx, size_t B, size_t M, int nent);
 /* acc = cur (first != 0) or acc = [a_s, -kappa b_s*; b_s, a_s*] acc, point by point on the real xi grid. */
 int fnftb_seg_compose(fnftb_ctx *ctx, size_t B, size_t M, int kappa, int first);
 /* Epilogue of src/fnft_nsev.c:846-876 on the chained (a, b): cstype 0 rho, 1 a|b, 2 rho|a|b. */

@@ -118,12 +118,59 @@ FNFT_INT fnft_kdvv_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX cons
     cd.kdv_sqrtz =
         (opts->discretization == fnft_kdv_discretization_2SPLIT2A) ? eps_t / degree1step : 0.0;
 
-    size_t chunk = fnftb_max_chunk(ctx, D, (int)deg0, M, 2, fnftb__workspace_limit());
+    /* signals whose transfer matrix is longer than one product tree can hold: by segments (below) */
+    const FNFT_UINT Dtree_max = (FNFT_UINT)fnftb_tree_max_samples((int)akns, (int)deg0);
+    const int segmented = (D > Dtree_max);
+    size_t chunk = segmented ? fnftb_max_chunk_ex(ctx, Dtree_max, (int)deg0, M, 2, 6 * M * sizeof(FNFT_COMPLEX),
+                                                  fnftb__workspace_limit())
+                             : fnftb_max_chunk(ctx, D, (int)deg0, M, 2, fnftb__workspace_limit());
     if (chunk > B)
         chunk = B;
     if (ret_codes != NULL)
         for (FNFT_UINT b = 0; b < B; b++)
             ret_codes[b] = FNFT_SUCCESS;
+
+    if (segmented) {
+        /* The reference multiplies polynomials of any length (src/private/fnft__poly_fmult.c:404-445).  Here the
+         * signal is cut into pieces the tree can multiply; the four entries of every piece's transfer matrix are
+         * evaluated at the same points z_m (chirp-z, raw values: the power-of-two scale of a piece is common to
+         * its entries and drops out of the ratio below), the second column of the product is chained piece by
+         * piece on the device, and the epilogue of src/fnft_kdvv.c:186-203 follows. */
+        const FNFT_UINT nseg = (D + Dtree_max - 1) / Dtree_max;
+        const FNFT_UINT base = D / nseg, extra = D % nseg;
+        fnftb_contspec_desc raw = cd;
+        raw.mode = FNFTB_MODE_RAW;
+        for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
+            const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
+            FNFT_COMPLEX *cur = (FNFT_COMPLEX *)fnftb_seg_buffer(ctx, nb, M, 4);
+            if (cur == NULL)
+                return E_DEVICE;
+            FNFT_UINT n0 = 0;
+            for (FNFT_UINT s = 0; s < nseg; s++) {
+                const FNFT_UINT len = base + (s < extra ? 1 : 0);
+                if (fnftb_set_signals_strided(ctx, nb, len, u + b0 * D + n0, D, devptr) != 0 ||
+                    fnftb_fscatter(ctx, &sd) != 0)
+                    return E_DEVICE;
+                raw.ent[0] = 1; /* H12, H22 */
+                raw.ent[1] = 3;
+                if (fnftb_contspec(ctx, &raw, cur, 4 * M, 1, NULL) != 0)
+                    return E_DEVICE;
+                if (s > 0) { /* the first piece only contributes its second column */
+                    raw.ent[0] = 0; /* H11, H21 */
+                    raw.ent[1] = 2;
+                    if (fnftb_contspec(ctx, &raw, cur + 2 * M, 4 * M, 1, NULL) != 0)
+                        return E_DEVICE;
+                }
+                if (fnftb_seg_compose_general(ctx, nb, M, s == 0) != 0)
+                    return E_DEVICE;
+                n0 += len;
+            }
+            if (fnftb_seg_finish_kdv(ctx, nb, M, cd.xi0, cd.eps_xi, cd.kdv_ph, cd.kdv_sqrtz, contspec + b0 * M, M,
+                                     devptr) != 0)
+                return E_DEVICE;
+        }
+        return FNFT_SUCCESS;
+    }
 
     /* host buffers: overlap the copies of neighbouring chunks with the kernels */
     const int piped = (!devptr && B >= 16 && fnftb__pipe_chunks() > 0);

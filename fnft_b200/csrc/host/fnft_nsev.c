@@ -117,7 +117,7 @@ static FNFT_INT nsev_contspec_segmented(fnftb_ctx *ctx, FNFT_UINT nb, FNFT_UINT 
     const FNFT_UINT base = D / nseg, extra = D % nseg;
     fnft_nsev_opts_t o = *opts;
     o.contspec_type = fnft_nsev_cstype_AB;
-    FNFT_COMPLEX *cur = (FNFT_COMPLEX *)fnftb_seg_buffer(ctx, nb, M);
+    FNFT_COMPLEX *cur = (FNFT_COMPLEX *)fnftb_seg_buffer(ctx, nb, M, 2);
     if (cur == NULL)
         return E_DEVICE;
     FNFT_UINT n0 = 0;

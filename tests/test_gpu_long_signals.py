@@ -54,8 +54,19 @@ for kappa in (+1, -1):
         ret, cs1, _, _, _ = F.nsev(Q[1], T, M, XI, kappa, o)
         assert ret == 0
         out["s_%%d_%%d" %% (kappa, cst)] = cs1
+U = (Q.real * 0.8 + 0.3 * np.abs(Q)).astype(np.complex128)
+for disc in (%(kdv_discs)s):
+    o = F.kdvv_default_opts()
+    o.discretization = disc
+    ret, cs, rcs = F.kdvv_batch(U, T, M, XI, o)
+    assert ret == 0 and (rcs == 0).all(), (ret, rcs)
+    out["kdv_b_%%d" %% disc] = cs
+    ret, cs1 = F.kdvv(U[2], T, M, XI, o)
+    assert ret == 0
+    out["kdv_s_%%d" %% disc] = cs1
 np.savez(%(outp)r, **out)
 """
+KDV_DISCS = "2, 9, 19"  # fnft_kdv_discretization_2SPLIT2A (sqrt(z) correction), 2SPLIT4B, 4SPLIT4B
 
 
 def _run_child(tmp_path, tag, Q, T, XI, M, limit):
@@ -65,7 +76,7 @@ def _run_child(tmp_path, tag, Q, T, XI, M, limit):
     env.pop("FNFT_B200_TREE_MAX_SAMPLES", None)
     if limit:
         env["FNFT_B200_TREE_MAX_SAMPLES"] = str(limit)
-    r = subprocess.run([sys.executable, "-c", _CHILD % {"root": ROOT, "inp": inp, "outp": outp}], env=env,
+    r = subprocess.run([sys.executable, "-c", _CHILD % {"root": ROOT, "inp": inp, "outp": outp, "kdv_discs": KDV_DISCS}], env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     return np.load(outp)
@@ -143,6 +154,21 @@ def test_signal_longer_than_one_tree_against_the_reference(F):
             assert max(parity_contract(cs[part * M:(part + 1) * M], ref[part * M:(part + 1) * M])) < 1, part
         print("long signal: ours vs truth %.2e, reference vs truth %.2e (x 1e-9)" %
               (max(parity_contract(rho[idx], truth)), max(parity_contract(ref[:M][idx], truth))))
+
+
+def test_kdvv_longer_than_one_tree_against_the_reference(F):
+    """fnft_kdvv, D = 150 001: two pieces, general 2x2 chaining of the raw transfer-matrix values."""
+    D, T, XI, M = 150001, (-40.0, 40.0), (0.2, 5.0), 64
+    t = np.linspace(T[0], T[1], D)
+    rng = np.random.default_rng(5)
+    u = (1.1 / np.cosh(t - 0.3) ** 2 + 0.4 / np.cosh(0.7 * (t + 9.0)) ** 2 + 0.01 * rng.standard_normal(D)).astype(np.complex128)
+    ret, cs = F.kdvv(u, T, M, XI, None)
+    assert ret == 0 and np.isfinite(cs.view(np.float64)).all()
+    assert np.abs(cs).max() > 1e-3
+    if R.available():
+        rret, ref = R.kdvv(u, np.array(T), M, np.array(XI))
+        assert rret == 0
+        assert max(parity_contract(cs, ref)) < 1
 
 
 def test_long_signal_bound_states_with_newton(F):
