@@ -156,6 +156,28 @@ def test_signal_longer_than_one_tree_against_the_reference(F):
               (max(parity_contract(rho[idx], truth)), max(parity_contract(ref[:M][idx], truth))))
 
 
+@pytest.mark.parametrize("disc,D", [(16, 3000), (18, 12000)])
+def test_high_degree_schemes_beyond_one_tree(F, disc, D):
+    """2SPLIT7A (degree 105 per sample, padded to 128: one tree holds 2048 samples) at D = 3000 and 2SPLIT8A (degree 24,
+    8192 samples) at D = 12000 against the reference."""
+    if not R.available():
+        pytest.skip("oracle/_ref not present on this box")
+    T, XI, M = (-10.0, 10.0), (-3.0, 3.0), 48
+    q = _signals(1, D, T, 77)[0]
+    o = F.nsev_default_opts()
+    o.discretization = disc
+    o.contspec_type = 2
+    ret, cs, _, _, _ = F.nsev(q, T, M, XI, 1, o)
+    assert ret == 0
+    ro = R.nsev_default_opts()
+    ro.discretization = disc
+    ro.contspec_type = 2
+    rret, ref, _, _, _ = R.nsev(q, np.array(T), M, np.array(XI), 1, ro)
+    assert rret == 0
+    for part in range(3):
+        assert max(parity_contract(cs[part * M:(part + 1) * M], ref[part * M:(part + 1) * M])) < 1, part
+
+
 def test_kdvv_longer_than_one_tree_against_the_reference(F):
     """fnft_kdvv, D = 150 001: two pieces, general 2x2 chaining of the raw transfer-matrix values."""
     D, T, XI, M = 150001, (-40.0, 40.0), (0.2, 5.0), 64

@@ -496,7 +496,7 @@ def test_nsev_higher_order_schemes_long_signals_vs_oracle(F, disc, D, kappa):
 def test_nsev_longest_supported_signal_vs_oracle(F, D):
     # 2SPLIT4B at D = 131072: final degree 2^18, the last tree level has operand length 2^18 (radix-64
     # column pass).  Beyond that fnft_nsev chains the continuous spectra of shorter pieces
-    # (tests/test_gpu_long_signals.py); fnft_kdvv reports "signal too long" instead of computing
+    # and so does fnft_kdvv (tests/test_gpu_long_signals.py); the private coefficient API reports "signal too long"
     M = 32
     T, XI = [-40.0, 40.0], [-4.0, 4.0]
     q = sech_chirp(D, T, amp=2.2, chirp=0.02)
@@ -505,7 +505,7 @@ def test_nsev_longest_supported_signal_vs_oracle(F, D):
     assert max(parity_contract(cs, O.nsev_contspec(q, T, M, XI, 1))) < 1
     if D == 131072:
         F.lib().fnft_errwarn_setprintf(None)
-        ret, _ = F.kdvv(np.ones(2 * D + 2, dtype=np.complex128) * 0.01, T, M, XI, None)
+        ret, *_ = F.nse_fscatter(np.ones(2 * D + 2, dtype=np.complex128) * 0.01, 1e-3, 1, F.NSE_2SPLIT4B)
         assert ret == 5   # FNFT_EC_OTHER from the device layer: loud, no fallback
 
 
