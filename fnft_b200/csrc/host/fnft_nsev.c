@@ -280,8 +280,10 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     if (!slow && D_eff > Dtree_max) {
         if (want_contspec && (upsampling != 1 || Dsub_req != 0))
             return E_NOT_YET_IMPLEMENTED(D, Signals this long are only supported without resampling and Richardson extrapolation.);
-        if (want_discspec && bsloc != fnft_nsev_bsloc_NEWTON)
-            return E_NOT_YET_IMPLEMENTED(D, Signals this long need bound_state_localization NEWTON.);
+        /* Newton and the default SUBSAMPLE_AND_REFINE (fast eigenvalues of the SUBSAMPLED signal, then Newton)
+         * never need the long polynomial; FAST_EIGENVALUE on the full signal does */
+        if (want_discspec && bsloc == fnft_nsev_bsloc_FAST_EIGENVALUE)
+            return E_NOT_YET_IMPLEMENTED(D, Signals this long need bound_state_localization NEWTON or SUBSAMPLE_AND_REFINE.);
     }
     const FNFT_UINT D_ws = segmented ? Dtree_max : D_eff; /* what the tree workspace has to hold at a time */
 

@@ -204,6 +204,12 @@ def test_long_signal_bound_states_with_newton(F):
     ret, cs, K, bs, nc = F.nsev(q, T, M, XI, 1, o, K=2, bound_states=np.array([0.4j, 1.7j]))
     assert ret == 0 and K == 2
     assert np.abs(np.sort(bs.imag) - np.array([0.8, 1.8])).max() < 1e-6 and np.abs(bs.real).max() < 1e-9
+    # the default options (SUBSAMPLE_AND_REFINE: fast eigenvalues of the subsampled signal, Newton on the full one)
+    od = F.nsev_default_opts()
+    ret, cs2, K2, bs2, nc2 = F.nsev(q, T, M, XI, 1, od, K=64)
+    assert ret == 0 and K2 == 2, (ret, K2)
+    assert np.abs(np.sort(bs2.imag) - np.array([0.8, 1.8])).max() < 1e-6
+    assert max(parity_contract(cs2, cs)) < 1
     o.bound_state_localization = F.BSLOC_FAST_EIGENVALUE
     ret, _, _, _, _ = F.nsev(q, T, M, XI, 1, o, K=16)
     assert ret != 0
