@@ -1112,9 +1112,20 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
         sa.out = (cplx *)c->roots.p;
         sa.n_raw = (int *)c->nraw.p;
         sa.n_kept = (int *)c->nkept.p;
-        const int nt = 256;
-        RC((launch_blocks<ScanArgs, blk_nsep_scan>(sa, (unsigned)(B * npoly), nt, 2 * nt * sizeof(int),
-                                                   c->st, "nsep_scan")));
+        static const int knob_scan = tree_knob("FNFT_B200_NSEP_SCAN_TILED", 1);  // 0: blk_nsep_scan (round 1)
+        if (knob_scan) {
+            if (g_fnftb_profile_on)
+                fnftb_profile_begin("nsep_scan", c->st);
+            k_nsep_scan_tiled<512><<<(unsigned)(B * npoly), 512, 0, c->st>>>(sa);
+            if (g_fnftb_profile_on)
+                fnftb_profile_end(c->st);
+            ++g_fnftb_launch_count;
+            CU(cudaGetLastError());
+        } else {
+            const int nt = 256;
+            RC((launch_blocks<ScanArgs, blk_nsep_scan>(sa, (unsigned)(B * npoly), nt, 2 * nt * sizeof(int),
+                                                       c->st, "nsep_scan")));
+        }
         CU(cudaMemcpyAsync(nraw.data(), c->nraw.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaMemcpyAsync(nkept.data(), c->nkept.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));

@@ -202,3 +202,98 @@ BLK void blk_nsep_scan(const ScanArgs &a, blk3 bid, int nt, void *smem)
         }
     }
 }
+
+#ifndef FNFTB_EMUL
+// ---------------------------------------------------------------------------------------
+// Round 2: the same scan with coalesced loads and one |p| per sample.  blk_nsep_scan gives every thread a
+// contiguous range of grid indices (lanes 16 KB apart: every warp load touches 32 sectors) and evaluates
+// hypot nine times per grid point, twice (count pass + write pass): 47 ms per 1024 signals of BASELINE config 5.
+// Here a CTA walks over tiles of blockDim.x consecutive grid indices: |p| of the three rings goes to shared
+// memory once per sample (coalesced 16-byte loads, next tile prefetched into registers), the 8 comparisons of
+// the minimum-modulus test (fnft__poly_roots_fftgridsearch.c:86-104) read shared memory, and only the few
+// points that pass run gridsearch_point (the same function as before: identical decisions and values).  The
+// output keeps the scan order: warp ballots + per-warp counts give every kept value its slot.
+// grid.x = B * npoly, blockDim.x = NT (multiple of 32), shared memory 3 * (NT + 2) doubles + 2 * NT / 32 ints
+// ---------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 2) k_nsep_scan_tiled(const ScanArgs a)
+{
+    __shared__ double habs[3][NT + 2];
+    __shared__ int wraw[NT / 32], wkeep[NT / 32];
+    const int M = a.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const cplx *v = a.vals + (size_t)blockIdx.x * 3 * M;
+    cplx *o = a.out + (size_t)blockIdx.x * a.cap;
+    int base_raw = 0, base_keep = 0;
+    // values of tile 0 (indices 1 + tid)
+    cplx nx[3];
+    {
+        const int i = 1 + tid;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            nx[k] = (i < M) ? v[(size_t)k * M + i] : czero();
+    }
+    for (int t0 = 1; t0 < M - 1; t0 += NT) {
+        const int i = t0 + tid;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            habs[k][tid + 1] = hypot(nx[k].x, nx[k].y);
+        if (tid < 3) {  // left halo (index t0 - 1 >= 0) ...
+            const cplx h = v[(size_t)tid * M + (t0 - 1)];
+            habs[tid][0] = hypot(h.x, h.y);
+        } else if (tid >= 32 && tid < 35) {  // ... and right halo (index t0 + NT), another warp
+            const int k = tid - 32, j = t0 + NT;
+            const cplx h = (j < M) ? v[(size_t)k * M + j] : czero();
+            habs[k][NT + 1] = hypot(h.x, h.y);
+        }
+        {  // prefetch the next tile
+            const int j = i + NT;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                nx[k] = (j < M) ? v[(size_t)k * M + j] : czero();
+        }
+        __syncthreads();
+        int pass = 0;
+        if (i < M - 1) {
+            const double tmp = habs[1][tid + 1];
+            pass = !(tmp > habs[0][tid]) && !(tmp > habs[0][tid + 1]) && !(tmp > habs[0][tid + 2]) &&
+                   !(tmp > habs[1][tid]) && !(tmp > habs[1][tid + 2]) && !(tmp > habs[2][tid]) &&
+                   !(tmp > habs[2][tid + 1]) && !(tmp > habs[2][tid + 2]);
+        }
+        int raw = 0, keep = 0;
+        cplx lam = czero();
+        if (pass) {
+            cplx zr;
+            if (gridsearch_point(a, v, i, &zr)) {
+                raw = 1;
+                keep = scan_keep(a, zr, &lam);
+            }
+        }
+        const unsigned mraw = __ballot_sync(0xffffffffu, raw), mkeep = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) {
+            wraw[warp] = __popc(mraw);
+            wkeep[warp] = __popc(mkeep);
+        }
+        if (__syncthreads_or(raw)) {  // rare: a root in this tile
+            int before = 0, tot_keep = 0, tot_raw = 0;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) {
+                before += (w < warp) ? wkeep[w] : 0;
+                tot_keep += wkeep[w];
+                tot_raw += wraw[w];
+            }
+            if (keep) {
+                const int off = base_keep + before + __popc(mkeep & ((1u << lane) - 1u));
+                if (off < a.cap)
+                    o[off] = lam;
+            }
+            base_keep += tot_keep;
+            base_raw += tot_raw;
+            __syncthreads();  // wraw / wkeep are rewritten in the next tile
+        }
+    }
+    if (tid == 0) {
+        a.n_raw[blockIdx.x] = base_raw;
+        a.n_kept[blockIdx.x] = base_keep;
+    }
+}
+#endif
