@@ -351,18 +351,34 @@ def nsep(q, T, kappa=+1, opts=None, K=None, M=None, phase_shift=0.0):
     return ret, main[:Kc.value], aux[:Mc.value]
 
 
-def nsep_batch(q, T, Kmax, Mmax, kappa=+1, opts=None, phase_shift=0.0):
-    """fnft_nsep_batch.  Returns (ret, K[B], main[B,Kmax], Mcount[B], aux[B,Mmax], rcs)."""
+def nsep_buffers(B, Kmax, Mmax):
+    """Output arrays of fnft_nsep_batch, allocated AND touched (a fresh np.zeros array is mapped lazily: the first
+    write into every 2 MiB region costs a page fault + zero fill, ~55 ms for the 2 x 268 MB of BASELINE config 5,
+    which a timed call would otherwise pay).  Pass them as `out` to nsep_batch and reuse them."""
+    bufs = (np.zeros(B, dtype=np.uint64), np.empty((B, Kmax), dtype=np.complex128), np.zeros(B, dtype=np.uint64),
+            np.empty((B, Mmax), dtype=np.complex128), np.zeros(B, dtype=np.int32))
+    bufs[1].fill(0)
+    bufs[3].fill(0)
+    return bufs
+
+
+def nsep_batch(q, T, Kmax, Mmax, kappa=+1, opts=None, phase_shift=0.0, out=None):
+    """fnft_nsep_batch.  Returns (ret, K[B], main[B,Kmax], Mcount[B], aux[B,Mmax], rcs); out = nsep_buffers(...)
+    reuses the caller's arrays (only the first K[b] / Mcount[b] entries of a row are written, like the reference)."""
     L = lib()
     q = _c128(q)
     B, D = q.shape
     if opts is None:
         opts = L.fnft_nsep_default_opts()
-    Ka = np.zeros(B, dtype=np.uint64)
-    Ma = np.zeros(B, dtype=np.uint64)
-    main = np.zeros((B, Kmax), dtype=np.complex128)
-    aux = np.zeros((B, Mmax), dtype=np.complex128)
-    rcs = np.zeros(B, dtype=np.int32)
+    if out is None:
+        Ka = np.zeros(B, dtype=np.uint64)
+        Ma = np.zeros(B, dtype=np.uint64)
+        main = np.zeros((B, Kmax), dtype=np.complex128)
+        aux = np.zeros((B, Mmax), dtype=np.complex128)
+        rcs = np.zeros(B, dtype=np.int32)
+    else:
+        Ka, main, Ma, aux, rcs = out
+        assert main.shape == (B, Kmax) and aux.shape == (B, Mmax) and Ka.shape == (B,) and Ma.shape == (B,)
     ret = L.fnft_nsep_batch(B, D, _p(q), _p(_f64(T)), phase_shift, _p(Ka), Kmax, _p(main), _p(Ma),
                             Mmax, _p(aux), kappa, C.addressof(opts), _p(rcs))
     return ret, Ka, main, Ma, aux, rcs

@@ -1045,6 +1045,20 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
     for (size_t b = 0; b < B; ++b)
         status_host[b] = 0;
 
+    // FNFT_B200_NSEP_TIMING=1: host wall time of the phases (each closed by a stream synchronisation)
+    static const int knob_timing = tree_knob("FNFT_B200_NSEP_TIMING", 0);
+    struct timespec t_last;
+    clock_gettime(CLOCK_MONOTONIC, &t_last);
+    auto tick = [&](const char *label) {
+        if (!knob_timing)
+            return;
+        cudaStreamSynchronize(c->st);
+        struct timespec now;
+        clock_gettime(CLOCK_MONOTONIC, &now);
+        fprintf(stderr, "[nsep timing]     %-24s %8.3f ms\n", label,
+                (now.tv_sec - t_last.tv_sec) * 1e3 + (now.tv_nsec - t_last.tv_nsec) * 1e-6);
+        t_last = now;
+    };
     const double eps = (d->PHI1 - d->PHI0) / (double)(Mpts - 1);
     for (int pass = 0; pass < 2; ++pass) {  // 0: main (p+, p-), 1: aux (tm12)
         if ((pass == 0 && !want_main) || (pass == 1 && !want_aux))
@@ -1095,6 +1109,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
             a.status = (int *)c->status.p;
             RC(cz_run_fastrows(a, (cplx *)c->cztab.p, c->tws, c->st));
         }
+        tick("polys + 3 chirp-z rings");
         ScanArgs sa;
         memset(&sa, 0, sizeof(sa));
         sa.vals = (const cplx *)c->vals.p;
@@ -1129,6 +1144,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
         CU(cudaMemcpyAsync(nraw.data(), c->nraw.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaMemcpyAsync(nkept.data(), c->nkept.p, B * npoly * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
+        tick("scan + counts");
         // copy only as many values per row as the fullest row holds (typically tens of the `cap` slots)
         size_t maxn = 0;
         for (size_t i = 0; i < B * npoly; ++i) {
@@ -1142,6 +1158,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
                                  maxn * sizeof(cplx), B * npoly, cudaMemcpyDeviceToHost, c->st));
             CU(cudaStreamSynchronize(c->st));
         }
+        tick("copy of the kept values");
         for (size_t b = 0; b < B; ++b) {
             if (pass == 0) {
                 cplx *dst = (cplx *)main_host + b * d->Kmax;
@@ -1175,6 +1192,7 @@ int fnftb_nsep_gridsearch(fnftb_ctx *c, const fnftb_nsep_desc *d, uint64_t *K_ho
                 M_host[b] = n;
             }
         }
+        tick("assembly of the user arrays");
     }
     return 0;
 }

