@@ -1004,9 +1004,26 @@ int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
     rc = cz2_launch(k_cz2_rows, r, (unsigned)((size_t)a.B * a.npoly * g.N1), 128, smem, st, "cz_rows");
     if (rc)
         return rc;
-    // 4. inverse columns + epilogue
-    return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / g.C)), nt,
-                                                          cz_cols_smem_bytes(g.C, g.N1, a.npoly), st, "cz_cols_inv");
+    // 4. inverse columns + epilogue, on the transposed tile when the tile has a multiple of 32 columns
+    // (FNFT_B200_CZ_INV_T=0: the column-major tile of the first generation)
+    static const int knob_inv_t = [] {
+        const char *e = getenv("FNFT_B200_CZ_INV_T");
+        return (e && e[0]) ? atoi(e) : 1;
+    }();
+    int Ci = g.C;
+    if (knob_inv_t) {
+        while ((Ci * a.npoly) % 32 != 0 && 2 * Ci <= g.N2 && cz_cols_smem_bytes(2 * Ci, g.N1, a.npoly) <= (size_t)72 * 1024)
+            Ci *= 2;
+        if ((Ci * a.npoly) % 32 == 0) {
+            a.C = Ci;
+            a.log2C = ilog2i((unsigned)Ci);
+            a.inv_t = 1;
+        } else {
+            Ci = g.C;
+        }
+    }
+    return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / Ci)), nt,
+                                                          cz_cols_smem_bytes(Ci, g.N1, a.npoly), st, "cz_cols_inv");
 }
 // the general four-step path with the first-generation row kernels (table twiddles): plain DFTs of the inverse
 // transform, where 1e-15 matters more than speed

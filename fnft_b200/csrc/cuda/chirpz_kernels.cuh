@@ -38,6 +38,7 @@ struct CzArgs {
                      // whose rounding of 2 pi / n costs ~1e-12 at n ~ 4000 (inverse transform, resampling)
     double lar, lai; // ln|A|, arg A
     cplx *ybuf;      // [B][npoly][N1][N2]
+    int inv_t;       // blk_cz_cols_inv: 1 = transposed shared-memory tile [row][column] (C * npoly a multiple of 32)
     cplx *vhat;      // [N1][N2]
     // signal-independent tables, filled once per call by blk_cz_tables:
     cplx *tab_y;     // [deg+1]  A^-n W^(n^2/2)
@@ -283,6 +284,35 @@ BLK void blk_cz_rows(const CzArgs &a, blk3 bid, int nt, void *smem)
     }
 }
 
+// One radix-R butterfly of an inverse pass (same arithmetic as fft_pass_butterfly<R, +1>) on a TRANSPOSED tile:
+// element `pos` of column `col` lives at S[pos * NC + col].  The 32 lanes of a warp take the same butterfly of
+// 32 consecutive columns, so every shared-memory access of a warp is 512 contiguous bytes whatever the stride,
+// and the twiddle loads are uniform.  (ncu, round 2: the column-major tile of the first generation spent 49 % of
+// its shared-memory wavefronts on bank conflicts in the stride-4 / stride-1 passes -- the kernel was bound by the
+// shared-memory pipe at 96 %, 1.6 TB/s of DRAM.)
+template <int R>
+HD void cz_inv_butterfly_t(cplx *S, int NC, int col, int u, int log2s, const TwTable &T)
+{
+    const int s = 1 << log2s;
+    const int g = u >> log2s;
+    const int o = u & (s - 1);
+    const int base = (g << (Log2R<R>::value + log2s)) + o;
+    const int len = Log2R<R>::value + log2s;
+    cplx v[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        v[j] = S[(size_t)(base + j * s) * NC + col];
+    if (o != 0) {
+#pragma unroll
+        for (int j = 1; j < R; ++j)
+            v[j] = cmul(v[j], tw_lookup<+1>(T, j * o, len));
+    }
+    Dft<R, +1>::run(v);
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        S[(size_t)(base + j * s) * NC + col] = v[j];
+}
+
 // grid.x = B * (N2 / C); handles all npoly polynomials of a signal so that the
 // epilogue can combine them.  Only output indices m < M are produced.
 BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
@@ -293,27 +323,65 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
     const int tile = bid.x % tiles;
     const int s = bid.x / tiles;
     const int n2_0 = tile * C;
+    const int NC = C * a.npoly;  // columns of the tile
+    const bool tr = (a.inv_t != 0);
+    // element (column cc, row pos) of the tile
+#define FNFTB_CZ_TILE(cc, pos) (tr ? S[(size_t)(pos) * NC + (cc)] : S[(size_t)(cc) * N1 + swz(pos)])
     FOR_THREADS(tid, nt)
     {
         for (int j = 0; j < a.npoly; ++j) {
             const cplx *src = a.ybuf + ((size_t)s * a.npoly + j) * a.L;
             for (int idx = tid; idx < C * N1; idx += nt) {
                 int c, pos;
-                cz_tile_index(idx, a.log2C, N1, &c, &pos);
+                if (tr) {  // lanes over consecutive columns: C * 16 contiguous bytes per row, global and shared
+                    c = idx & (C - 1);
+                    pos = idx >> a.log2C;
+                } else {
+                    cz_tile_index(idx, a.log2C, N1, &c, &pos);
+                }
                 const int n2 = n2_0 + c;
                 const cplx w = cconj(a.tab_tw[(size_t)pos * N2 + n2]);
-                S[((size_t)j * C + c) * N1 + swz(pos)] = cmul(src[(size_t)pos * N2 + n2], w);
+                FNFTB_CZ_TILE(j * C + c, pos) = cmul(src[(size_t)pos * N2 + n2], w);
             }
         }
     }
     BLOCK_SYNC();
-    FNFTB_SMEM_FFT_INV(S, C * a.npoly, a.plan1, nt, a.T);
-    BLOCK_SYNC();
+    if (tr) {
+        // the inverse passes of FNFTB_SMEM_FFT_INV (reverse plan order, strides 1, r_last, ...) on the transposed tile
+        int l2s = 0;
+        for (int p = a.plan1.npass - 1; p >= 0; --p) {
+            const int R = a.plan1.radix[p];
+            const int l2r = ilog2i(R);
+            const int items = NC << (a.plan1.log2n - l2r);
+            FOR_THREADS(tid, nt)
+            {
+                for (int idx = tid; idx < items; idx += nt) {
+                    const int col = idx & (NC - 1), u = idx / NC;
+                    switch (R) {
+                    case 16: cz_inv_butterfly_t<16>(S, NC, col, u, l2s, a.T); break;
+                    case 8: cz_inv_butterfly_t<8>(S, NC, col, u, l2s, a.T); break;
+                    case 4: cz_inv_butterfly_t<4>(S, NC, col, u, l2s, a.T); break;
+                    default: cz_inv_butterfly_t<2>(S, NC, col, u, l2s, a.T); break;
+                    }
+                }
+            }
+            BLOCK_SYNC();
+            l2s += l2r;
+        }
+    } else {
+        FNFTB_SMEM_FFT_INV(S, C * a.npoly, a.plan1, nt, a.T);
+        BLOCK_SYNC();
+    }
     FOR_THREADS(tid, nt)
     {
         for (int idx = tid; idx < C * N1; idx += nt) {
             int c, n1;
-            cz_tile_index(idx, a.log2C, N1, &c, &n1);
+            if (tr) {
+                c = idx & (C - 1);
+                n1 = idx >> a.log2C;
+            } else {
+                cz_tile_index(idx, a.log2C, N1, &c, &n1);
+            }
             const long long m = (long long)n1 * N2 + n2_0 + c;
             if (m >= a.M)
                 continue;
@@ -321,7 +389,7 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
             cplx H[2];
             H[1] = czero();
             for (int j = 0; j < a.npoly; ++j)
-                H[j] = cmul(S[((size_t)j * C + c) * N1 + swz(n1)], ch);
+                H[j] = cmul(FNFTB_CZ_TILE(j * C + c, n1), ch);
             cplx *o = a.out + (size_t)s * a.out_sstride;
             if (a.mode == FNFTB_CZ_RAW) {
                 const size_t js = a.out_jstride ? a.out_jstride : (size_t)a.M;
@@ -360,3 +428,4 @@ BLK void blk_cz_cols_inv(const CzArgs &a, blk3 bid, int nt, void *smem)
         }
     }
 }
+#undef FNFTB_CZ_TILE
