@@ -1022,8 +1022,11 @@ int cz_run_fastrows(CzArgs a, cplx *tables, const TwSet &tw, cudaStream_t st)
             Ci = g.C;
         }
     }
-    return launch_blocks<CzArgs, blk_cz_cols_inv, 256, 3>(a, (unsigned)((size_t)a.B * (g.N2 / Ci)), nt,
-                                                          cz_cols_smem_bytes(Ci, g.N1, a.npoly), st, "cz_cols_inv");
+#ifndef FNFTB_CZ_INV_MINB
+#define FNFTB_CZ_INV_MINB 3  // resident CTAs per SM the register budget of the inverse column kernel is cut for
+#endif
+    return launch_blocks<CzArgs, blk_cz_cols_inv, 256, FNFTB_CZ_INV_MINB>(a, (unsigned)((size_t)a.B * (g.N2 / Ci)), nt,
+                                                                          cz_cols_smem_bytes(Ci, g.N1, a.npoly), st, "cz_cols_inv");
 }
 // the general four-step path with the first-generation row kernels (table twiddles): plain DFTs of the inverse
 // transform, where 1e-15 matters more than speed
