@@ -210,6 +210,9 @@ typedef struct fnftb_pool {
 
 static __thread int tl_ndev = -1; /* -1: FNFT_B200_DEVICES not looked at yet */
 static __thread int tl_devs[FNFTB_MAX_DEV];
+/* 1: tl_devs = {d, d} was filled in automatically (two pipelines on the current device, see fnftb__fanout_shards);
+ * the user has not configured any devices and fnft_b200_get_devices keeps reporting none */
+static __thread int tl_auto = 0;
 static __thread fnftb_pool *tl_pool = NULL;
 static __thread int tl_in_worker = 0;
 
@@ -305,6 +308,7 @@ FNFT_INT fnft_b200_set_devices(FNFT_INT n, FNFT_INT const *devices)
         if (devices[i] < 0 || devices[i] >= have)
             return E_INVALID_ARGUMENT(devices);
     fnftb__fanout_shutdown(); /* the workers of the previous set go away with their contexts */
+    tl_auto = 0;
     tl_ndev = (int)n;
     for (FNFT_INT i = 0; i < n; i++)
         tl_devs[i] = (int)devices[i];
@@ -315,9 +319,32 @@ FNFT_INT fnft_b200_get_devices(FNFT_INT *devices, FNFT_INT capacity)
 {
     if (tl_ndev < 0)
         devices_from_env();
+    if (tl_auto)
+        return 0;
     for (int i = 0; i < tl_ndev && i < capacity && devices != NULL; i++)
         devices[i] = tl_devs[i];
     return (FNFT_INT)tl_ndev;
+}
+
+/* Two pipelines on ONE device.  A large batch given with host buffers runs as chunks whose copies overlap the kernels
+ * of the neighbouring chunks (fnftb_pipeline_*); what stays exposed are the tails of the ~10 kernels of every chunk
+ * and the first copy-in / last copy-out.  Two contexts on the same GPU, each with one half of the batch, fill each
+ * other's gaps: BASELINE config 2 (4096 signals, D = M = 16384) 46.24 -> 44.85 ms per call, measured
+ * (profiles/r02_two_contexts.txt).  The mechanism is the fan-out below with the current device listed twice; it is
+ * applied automatically when the caller has not configured devices and the batch has at least
+ * FNFT_B200_CTX_MIN_BATCH signals (default 4096; FNFT_B200_CTX_PER_DEVICE=1 turns it off). */
+static int auto_contexts(FNFT_UINT B)
+{
+    static int per_dev = -1;
+    static long min_batch = 4096;
+    if (per_dev < 0) {
+        const char *e = getenv("FNFT_B200_CTX_PER_DEVICE");
+        per_dev = (e && e[0]) ? atoi(e) : 2;
+        e = getenv("FNFT_B200_CTX_MIN_BATCH");
+        if (e && e[0])
+            min_batch = atol(e);
+    }
+    return (per_dev >= 2 && min_batch > 0 && B >= (FNFT_UINT)min_batch) ? 2 : 1;
 }
 
 /* Number of shards a batch of B signals given with host buffers is split into (1: no fan-out). */
@@ -327,6 +354,24 @@ int fnftb__fanout_shards(FNFT_UINT B)
         return 1;
     if (tl_ndev < 0)
         devices_from_env();
+    if (tl_ndev == 0 || tl_auto) { /* no devices configured by the caller */
+        if (auto_contexts(B) < 2 || fnftb_device_count() < 1)
+            return 1;
+        if (tl_device < 0) { /* same rule as fnftb__ctx */
+            const char *env = getenv("FNFT_B200_DEVICE");
+            const int dev = (env != NULL && env[0] != '\0') ? atoi(env) : 0;
+            if (dev < 0 || dev >= fnftb_device_count())
+                return 1;
+            tl_device = dev;
+        }
+        if (!tl_auto || tl_devs[0] != tl_device) { /* first use, or the thread moved to another device */
+            fnftb__fanout_shutdown();
+            tl_devs[0] = tl_devs[1] = tl_device;
+            tl_ndev = 2;
+            tl_auto = 1;
+        }
+        return 2;
+    }
     if (tl_ndev < 2 || B < 2)
         return 1;
     return (B < (FNFT_UINT)tl_ndev) ? (int)B : tl_ndev;
