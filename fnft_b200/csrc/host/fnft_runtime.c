@@ -332,11 +332,11 @@ FNFT_INT fnft_b200_get_devices(FNFT_INT *devices, FNFT_INT capacity)
  * other's gaps: BASELINE config 2 (4096 signals, D = M = 16384) 46.24 -> 44.85 ms per call, measured
  * (profiles/r02_two_contexts.txt).  The mechanism is the fan-out below with the current device listed twice; it is
  * applied automatically when the caller has not configured devices and the batch has at least
- * FNFT_B200_CTX_MIN_BATCH signals (default 4096; FNFT_B200_CTX_PER_DEVICE=1 turns it off). */
+ * FNFT_B200_CTX_MIN_BATCH signals (default 2048: config 4, fnft_kdvv with 2048 signals of 8192 samples, 24.65 -> 23.40 ms; FNFT_B200_CTX_PER_DEVICE=1 turns it off). */
 static int auto_contexts(FNFT_UINT B)
 {
     static int per_dev = -1;
-    static long min_batch = 4096;
+    static long min_batch = 2048;
     if (per_dev < 0) {
         const char *e = getenv("FNFT_B200_CTX_PER_DEVICE");
         per_dev = (e && e[0]) ? atoi(e) : 2;
