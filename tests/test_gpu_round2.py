@@ -201,6 +201,25 @@ def test_fanout_nsev_batch_equals_single_device(F):
     assert np.array_equal(K2, K3) and np.array_equal(bs2, bs3) and np.array_equal(nc2, nc3)
 
 
+def test_two_pipelines_per_device_are_automatic_and_change_nothing(F):
+    """Host-buffer batches of at least 2048 signals run as two pipelines (two contexts) on the current device without
+    any configuration (fnft_runtime.c: fnftb__fanout_shards); the results are those of the plain path, bit for bit,
+    and fnft_b200_get_devices keeps reporting that the caller has not configured devices."""
+    B, D, M, T, XI = 2049, 256, 96, (-9.0, 9.0), (-3.0, 3.0)
+    Q = _signals(B, D, T, 17)
+    ret, cs, *_ = F.nsev_batch(Q, T, M, XI, 1)       # 1025 + 1024 signals on two contexts
+    got = np.zeros(4, dtype=np.int32)
+    assert F.lib().fnft_b200_get_devices(got.ctypes.data_as(C.c_void_p), 4) == 0
+    ret_a, cs_a, *_ = F.nsev_batch(Q[:2047], T, M, XI, 1)  # below the threshold: the caller's own context
+    ret_b, cs_b, *_ = F.nsev_batch(Q[2047:], T, M, XI, 1)
+    assert ret == 0 and ret_a == 0 and ret_b == 0
+    assert np.array_equal(cs[:2047], cs_a) and np.array_equal(cs[2047:], cs_b)
+    U = (Q.real * 0.5).astype(np.complex128)
+    r1, k1, _ = F.kdvv_batch(U, T, M, (0.1, 3.0))
+    r2, k2, _ = F.kdvv_batch(U[:1500], T, M, (0.1, 3.0))
+    assert r1 == 0 and r2 == 0 and np.array_equal(k1[:1500], k2)
+
+
 def test_fanout_kdvv_and_nsep_batch_equal_single_device(F):
     B, D = 11, 1024
     t = np.linspace(-16, 15, D)
