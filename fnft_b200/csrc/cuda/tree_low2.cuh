@@ -436,6 +436,14 @@ DEV int low2_wbase(int p, int which, int l2n)
 // P pass: radix R at stride 4 on the workspace arrays.  DIR = +1: inverse (DIT, bit-reversed
 // input), DIR = -1: forward (DIF, bit-reversed output).
 // ---------------------------------------------------------------------------------------
+// FNFTB_LOW2_BATCH (experiment, off): a thread that owns several butterflies of a stage (radix 4: four, radix 8: two)
+// loads all of them, transforms all of them and stores all of them, instead of one after the other.  Same arithmetic,
+// same results, same 168 registers -- and SLOWER on B200: 15.50 ms per 4096 signals with the serial loops, 16.79 with
+// batched P passes (= 1), 18.83 with batched P passes and M stages (= 2): the serial loop body is a quarter of the
+// code and the three resident CTAs already give the scheduler independent chains (round 2, gpurun_out/r5c).
+#ifndef FNFTB_LOW2_BATCH
+#define FNFTB_LOW2_BATCH 0
+#endif
 template <int LOG2M, int R, int DIR>
 DEV void low2_p_pass(cplx *S, const TwSet &tw, int t, int l2n, int sb)
 {
@@ -444,6 +452,50 @@ DEV void low2_p_pass(cplx *S, const TwSet &tw, int t, int l2n, int sb)
     constexpr int PER = 16 / R;  // items per thread
     const int l2gr = l2n - 2 - LR;  // groups per array (log2)
     const cplx *pt = tw.base + tw.pass_off[LR + 2][LR];  // [q-1][o], o < 4
+#if FNFTB_LOW2_BATCH
+    cplx v[PER][R];
+    int bases[PER], os[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int idx = swapbit2(t + k * M, sb);
+        os[k] = idx & 3;
+        const int rest = idx >> 2;
+        const int g = rest & ((1 << l2gr) - 1);
+        const int wv = rest >> l2gr;
+        bases[k] = low2_wbase(wv >> 1, wv & 1, l2n) + (g << (LR + 2)) + os[k];
+        if (DIR > 0) {
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                v[k][q] = S[swz2(bases[k] + 4 * brev_c(q, LR))];
+        } else {
+#pragma unroll
+            for (int n = 0; n < R; ++n)
+                v[k][n] = S[swz2(bases[k] + 4 * n)];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        if (DIR > 0) {
+            up_twiddle_mul<R, true>(v[k], pt, 4, os[k]);
+            Dft<R, +1>::run(v[k]);
+        } else {
+            Dft<R, -1>::run(v[k]);
+            up_twiddle_mul<R, false>(v[k], pt, 4, os[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        if (DIR > 0) {
+#pragma unroll
+            for (int n = 0; n < R; ++n)
+                S[swz2(bases[k] + 4 * n)] = v[k][n];
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                S[swz2(bases[k] + 4 * brev_c(q, LR))] = v[k][q];
+        }
+    }
+#else
 #pragma unroll 1
     for (int k = 0; k < PER; ++k) {
         const int idx = swapbit2(t + k * M, sb);
@@ -473,6 +525,7 @@ DEV void low2_p_pass(cplx *S, const TwSet &tw, int t, int l2n, int sb)
                 S[swz2(base + 4 * brev_c(q, LR))] = v[q];
         }
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -491,6 +544,50 @@ DEV double low2_m_stage(cplx *S, const TwSet &tw, const Low2Tops *TTn, int t, in
     const cplx *pt = tw.base + tw.pass_off[l2n][LR];  // [q-1][o], o < s
     const cplx *tt = tw.base + tw.twist_off[l2n];     // w_2N^i
     double m2 = 0.0;
+#if FNFTB_LOW2_BATCH >= 2
+    if constexpr (PER > 1) {
+        cplx v[PER][R];
+        int bases[PER], os[PER], ps[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            int idx = t + k * M;
+            if (l2s == 2)
+                idx = swapbit2(idx, sb);
+            os[k] = idx & (s - 1);
+            const int wv = idx >> l2s;
+            ps[k] = wv;
+            bases[k] = low2_wbase(wv >> 1, wv & 1, l2n) + os[k];
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                v[k][q] = S[swz2(bases[k] + (brev_c(q, LR) << l2s))];
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            up_twiddle_mul<R, true>(v[k], pt, s, os[k]);
+            Dft<R, +1>::run(v[k]);
+#pragma unroll
+            for (int n = 0; n < R; ++n)
+                v[k][n] = cscale(v[k][n], invN);
+            if (os[k] == 0)
+                v[k][0] = (ps[k] & 1) ? TTn[ps[k] >> 1].bb : TTn[ps[k] >> 1].ba;
+            if (want_max) {
+#pragma unroll
+                for (int n = 0; n < R; ++n)
+                    m2 = fmax(m2, cabs2(v[k][n]));
+            }
+            UpTwist<R, 0>::run(v[k], __ldg(&tt[os[k]]));
+            Dft<R, -1>::run(v[k]);
+            up_twiddle_mul<R, false>(v[k], pt, s, os[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                S[swz2(bases[k] + (brev_c(q, LR) << l2s))] = v[k][q];
+        }
+        return m2;
+    }
+#endif
 #pragma unroll 1
     for (int k = 0; k < PER; ++k) {
         int idx = t + k * M;

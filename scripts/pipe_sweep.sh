@@ -1,6 +1,6 @@
 #!/bin/bash
-# host-buffer path: number of pipeline chunks / taper depth (halvings of the chunk size at both ends)
-for cfg in "8 2" "8 3" "8 4" "6 3" "4 3" "4 4" "12 3" "5 3" "3 4"; do
+# host-buffer path (two pipelines per GPU, the default): chunks per pipeline / taper depth
+for cfg in "8 2" "8 3" "6 3" "5 2" "4 2" "6 2" "4 3"; do
   set -- $cfg
   echo "== FNFT_B200_PIPE=$1 FNFT_B200_PIPE_TAPER=$2"
   FNFT_B200_PIPE=$1 FNFT_B200_PIPE_TAPER=$2 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-extras --parity-signals 4 2>/dev/null | python -c "
