@@ -1484,6 +1484,7 @@ static int roots_run(fnftb_ctx *c, const cplx *coef, long long cstride, size_t B
     static const int knob_maxit = tree_knob("FNFT_B200_ROOTS_MAXIT", 64);
     ra.maxit = knob_maxit;
     ra.in_global = 0;
+    ra.stats = 0;
     if (g_fnftb_profile_on)
         fnftb_profile_begin("poly_roots", c->st);
     const int rc = roots_launch(ra, (int)B, c->st);

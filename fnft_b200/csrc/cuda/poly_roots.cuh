@@ -44,6 +44,7 @@ struct RootsArgs {
     int *info;          // [B][4]: lead, m (effective degree), sweeps used, roots not converged
     int maxit;
     int in_global;      // 1: the sweeps work on `roots` in global memory (degree > 8192)
+    int stats;          // 1: the compacting kernel adds its work counters to g_roots_stat
 };
 
 // ---- start values -------------------------------------------------------------------------
@@ -286,6 +287,220 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth(const RootsArgs a)
         a.info[4 * b + 2] = it;
 }
 
+// ---- Aberth-Ehrlich sweeps with compaction of the roots that still move ------------------------
+// The kernel above keeps a warp busy until the last of its 32 roots has converged.  Here the roots that
+// still move are kept as an ordered list in shared memory: every sweep walks the list in chunks of
+// blockDim.x roots (Jacobi inside a chunk, Gauss-Seidel from chunk to chunk), rebuilds it by an ordered
+// compaction (ballots, warp counts, no atomics: the schedule and with it every bit of the result is
+// reproducible), and the work of a sweep shrinks with the list.  The double-precision roots stay in the
+// output array (a root is read and written once per sweep by the thread that has it); shared memory
+// holds every root as a pair of floats per component (hi = (float)x, lo = (float)(x - hi)), from which
+// the Aberth sum forms its differences as (hi_i - hi_j) + (lo_i - lo_j) -- exact to 2^-48 |z| for
+// neighbouring roots and free of FP64 -> FP32 conversions, which issue at a quarter of the FP64 rate.
+__device__ unsigned long long g_roots_stat[4];  // FNFT_B200_ROOTS_STATS=1: root-sweeps, polynomials, sweeps, roots
+
+// one MUFU.RCP (__frcp_rn adds a Newton step, a range test and a branch to a slow path: twice the instructions of the loop)
+static __device__ __forceinline__ float roots_rcp(const float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+static __device__ __forceinline__ float4 roots_split(const cplx v)
+{
+    const float hx = (float)v.x, hy = (float)v.y;
+    return make_float4(hx, hy, (float)(v.x - (double)hx), (float)(v.y - (double)hy));
+}
+
+// CS: the coefficients and their moduli are staged in shared memory as well (44 instead of 20 bytes per root): the Horner
+// recurrences of a CTA's last few roots then run at shared-memory latency instead of waiting for L2 every few steps.
+template <int MAXNT, bool CS>
+__global__ void __launch_bounds__(MAXNT) k_roots_aberth_c(const RootsArgs a)
+{
+    extern __shared__ double2 fnftb_smem[];
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
+    const int n = a.n;
+    const int lead = a.info[4 * b + 0], m = a.info[4 * b + 1];
+    if (m <= 0)
+        return;
+    const cplx *c = a.coef + (size_t)b * a.cstride + lead;
+    const double *ac = a.absc + (size_t)b * (n + 1) + lead;
+    cplx *groots = a.roots + (size_t)b * n;
+    float4 *zf = (float4 *)fnftb_smem;                  // [n]
+    cplx *sc = (cplx *)(zf + n);                        // [n + 1] (CS)
+    double *sa = (double *)(sc + (CS ? n + 1 : 0));     // [n + 1] (CS)
+    int *s_wcnt = (int *)(sa + (CS ? n + 1 : 0));       // [32]
+    unsigned short *lst0 = (unsigned short *)(s_wcnt + 32);  // [n] roots that still move, ascending
+    unsigned short *lst1 = lst0 + n;                         // [n] the list of the next sweep
+    for (int i = tid; i < m; i += nt) {
+        zf[i] = roots_split(groots[i]);
+        lst0[i] = (unsigned short)i;
+    }
+    if constexpr (CS) {
+        for (int i = tid; i <= m; i += nt) {
+            sc[i] = c[i];
+            sa[i] = ac[i];
+        }
+    }
+    __syncthreads();
+    const double tol = 4.0 * (double)m * 2.220446049250313e-16;
+    int it = 0, nact = m;
+    unsigned long long work = 0;
+    for (; it < a.maxit && nact > 0; ++it) {
+        work += (unsigned long long)nact;
+        const unsigned short *cur = (it & 1) ? lst1 : lst0;
+        unsigned short *nxt = (it & 1) ? lst0 : lst1;
+        int nnext = 0;
+        for (int base = 0; base < nact; base += nt) {
+            const int k = base + tid;
+            bool moving = false;
+            int i = 0;
+            cplx zi = czero();
+            if (k < nact) {
+                i = cur[k];
+                zi = groots[i];
+                const double az = hypot(zi.x, zi.y);
+                const bool small = (az <= 1.0);
+                const cplx w = small ? zi : cdiv(make_cplx(1.0, 0.0), zi);
+                const double aw = small ? az : 1.0 / az;
+                cplx p = czero(), dp = czero();
+                double e = 0.0;
+                // Horner for p, p' and the running error bound: p(z) for |z| <= 1, q(1/z) = p(z)/z^m else
+                const cplx *cp = small ? (CS ? sc : c) : (CS ? sc : c) + m;
+                const double *ap = small ? (CS ? sa : ac) : (CS ? sa : ac) + m;
+                const int stp = small ? 1 : -1;
+#pragma unroll 4
+                for (int q = 0; q <= m; ++q) {
+                    cplx ck;
+                    double ak;
+                    if constexpr (CS) {
+                        ck = cp[stp * q];
+                        ak = ap[stp * q];
+                    } else {
+                        ck = LDG(cp + stp * q);
+                        ak = LDG(ap + stp * q);
+                    }
+                    // dp = dp w + p, p = p w + c_k as four fused multiply-adds each
+                    const double dx = fma(dp.x, w.x, fma(-dp.y, w.y, p.x));
+                    dp.y = fma(dp.x, w.y, fma(dp.y, w.x, p.y));
+                    dp.x = dx;
+                    const double px = fma(p.x, w.x, fma(-p.y, w.y, ck.x));
+                    p.y = fma(p.x, w.y, fma(p.y, w.x, ck.y));
+                    p.x = px;
+                    e = fma(e, aw, ak);
+                }
+                if (!(hypot(p.x, p.y) <= tol * e)) {  // else: converged, leaves the list
+                    moving = true;
+                    cplx Nw;
+                    if (small) {
+                        Nw = cdiv(p, dp);
+                    } else {  // N = z / (m - w q'(w)/q(w))
+                        const cplx t = cmul(w, cdiv(dp, p));
+                        Nw = cdiv(zi, make_cplx((double)m - t.x, -t.y));
+                    }
+                    if (!(isfinite(Nw.x) && isfinite(Nw.y))) {  // p' = 0: leave the stationary point sideways
+                        Nw = make_cplx(1e-3 * az + 1e-6, 1e-3 * az + 1e-6);
+                    }
+                    const float4 fi = roots_split(zi);
+                    float sx0 = 0.f, sy0 = 0.f, sx1 = 0.f, sy1 = 0.f;
+                    int j = 0;
+#pragma unroll 2
+                    for (; j + 1 < m; j += 2) {
+                        const float4 f0 = zf[j], f1 = zf[j + 1];
+                        const float dx0 = (fi.x - f0.x) + (fi.z - f0.z), dy0 = (fi.y - f0.y) + (fi.w - f0.w);
+                        const float dx1 = (fi.x - f1.x) + (fi.z - f1.z), dy1 = (fi.y - f1.y) + (fi.w - f1.w);
+                        const float i0 = roots_rcp(fmaxf(fmaf(dx0, dx0, dy0 * dy0), 1e-37f));
+                        const float i1 = roots_rcp(fmaxf(fmaf(dx1, dx1, dy1 * dy1), 1e-37f));
+                        sx0 = fmaf(dx0, i0, sx0);
+                        sy0 = fmaf(-dy0, i0, sy0);
+                        sx1 = fmaf(dx1, i1, sx1);
+                        sy1 = fmaf(-dy1, i1, sy1);
+                    }
+                    if (j < m) {
+                        const float4 f0 = zf[j];
+                        const float dx0 = (fi.x - f0.x) + (fi.z - f0.z), dy0 = (fi.y - f0.y) + (fi.w - f0.w);
+                        const float i0 = roots_rcp(fmaxf(fmaf(dx0, dx0, dy0 * dy0), 1e-37f));
+                        sx0 = fmaf(dx0, i0, sx0);
+                        sy0 = fmaf(-dy0, i0, sy0);
+                    }
+                    const cplx S = make_cplx((double)sx0 + (double)sx1, (double)sy0 + (double)sy1);
+                    const cplx den = csub(make_cplx(1.0, 0.0), cmul(Nw, S));
+                    cplx dz = cdiv(Nw, den);
+                    if (!(isfinite(dz.x) && isfinite(dz.y)))
+                        dz = Nw;
+                    zi = csub(zi, dz);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, moving);
+            __syncthreads();  // every Aberth sum of this chunk has read the old values
+            if (moving) {
+                groots[i] = zi;
+                zf[i] = roots_split(zi);
+            }
+            if (lane == 0)
+                s_wcnt[wid] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int q = 0; q < nw; ++q) {
+                const int cq = s_wcnt[q];
+                before += (q < wid) ? cq : 0;
+                total += cq;
+            }
+            if (moving)
+                nxt[nnext + before + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)i;
+            nnext += total;
+            // s_wcnt is rewritten only after the first barrier of the next chunk, nxt is read only in the next sweep
+        }
+        __syncthreads();
+        nact = nnext;
+    }
+    // still moving after maxit sweeps: not a root, say so
+    const unsigned short *cur = (it & 1) ? lst1 : lst0;
+    for (int k = tid; k < nact; k += nt)
+        groots[cur[k]] = make_cplx(nan(""), nan(""));
+    if (tid == 0) {
+        a.info[4 * b + 2] = it;
+        a.info[4 * b + 3] = nact;
+        if (a.stats) {
+            atomicAdd(&g_roots_stat[0], work);
+            atomicAdd(&g_roots_stat[1], 1ull);
+            atomicAdd(&g_roots_stat[2], (unsigned long long)it);
+            atomicAdd(&g_roots_stat[3], (unsigned long long)m);
+        }
+    }
+}
+
+static inline int roots_launch_c(const RootsArgs &a, int B, cudaStream_t st)
+{
+    // CTA size: with many polynomials in flight small CTAs (6 - 8 per SM) fill the SM while others are down to
+    // their last few roots; a single polynomial wants as many threads as it has roots
+    static const int knob_cs = [] {
+        const char *e = getenv("FNFT_B200_ROOTS_SMEM_COEF");
+        return e ? atoi(e) : 1;
+    }();
+    static const int knob_nt = [] {
+        const char *e = getenv("FNFT_B200_ROOTS_NT");
+        return e ? atoi(e) : 0;
+    }();
+    const bool cs = knob_cs && a.n <= 4096;
+    int want = (B >= 296) ? 256 : (B >= 74) ? 512 : 1024;
+    if (knob_nt)
+        want = knob_nt;
+    const int nt = std::min(want, ((a.n + 31) / 32) * 32);
+    const size_t smem = (sizeof(float4) + 2 * sizeof(unsigned short)) * (size_t)a.n + 32 * sizeof(int) +
+                        (cs ? (sizeof(cplx) + sizeof(double)) * ((size_t)a.n + 1) : 0);
+    auto kern = cs ? k_roots_aberth_c<1024, true> : k_roots_aberth_c<1024, false>;
+    {
+        const int e = fnftb_smem_optin((const void *)kern, smem);
+        if (e != 0)
+            return e;
+    }
+    kern<<<B, nt, smem, st>>>(a);
+    return 0;
+}
+
 template <int R, int MAXNT>
 static inline int roots_launch_r(const RootsArgs &a, int B, int nt, cudaStream_t st)
 {
@@ -312,6 +527,37 @@ static inline int roots_launch(const RootsArgs &a_in, int B, cudaStream_t st)
     a.in_global = (a.n > 8192) ? 1 : 0;
     k_roots_init<<<B, 256, 0, st>>>(a);
     ++g_fnftb_launch_count;
+    // Up to degree 8192 (the float copies of the roots fit in shared memory): the compacting kernel.  Config 7
+    // (1024 polynomials of degree 1638 / 2048): see profiles/r02_roots_compact.md; FNFT_B200_ROOTS_COMPACT=0 selects the
+    // kernel below.
+    static const int knob_compact = [] {
+        const char *e = getenv("FNFT_B200_ROOTS_COMPACT");
+        return e ? atoi(e) : 1;
+    }();
+    if (knob_compact && a.n <= 8192) {
+        static const int knob_stats = [] {
+            const char *e = getenv("FNFT_B200_ROOTS_STATS");
+            return e ? atoi(e) : 0;
+        }();
+        a.in_global = 1;
+        a.stats = knob_stats;
+        if (knob_stats) {
+            const unsigned long long z4[4] = {0, 0, 0, 0};
+            cudaMemcpyToSymbolAsync(g_roots_stat, z4, sizeof(z4), 0, cudaMemcpyHostToDevice, st);
+        }
+        const int rc = roots_launch_c(a, B, st);
+        if (rc)
+            return rc;
+        ++g_fnftb_launch_count;
+        if (knob_stats) {
+            unsigned long long s4[4];
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(s4, g_roots_stat, sizeof(s4));
+            fprintf(stderr, "[roots] %llu polynomials, %llu roots, %.2f sweeps per polynomial, %.2f sweeps per root\n", s4[1],
+                    s4[3], (double)s4[2] / (double)(s4[1] ? s4[1] : 1), (double)s4[0] / (double)(s4[3] ? s4[3] : 1));
+        }
+        return (int)cudaGetLastError();
+    }
     // One root per group (R = 1) measured fastest on B200: converged roots drop out one by one,
     // which saves more than sharing the coefficient / root loads between the R roots of a group
     // (R = 4 with 416 threads: 259 ms, R = 1 with 832 threads: 134 ms for 1024 polynomials of
