@@ -280,10 +280,11 @@ def nsev(q, T, M=0, XI=None, kappa=+1, opts=None, K=0, bound_states=None,
 
 
 def nsev_batch(q, T, M=0, XI=None, kappa=+1, opts=None, K=None, Kmax=0, bound_states=None,
-               want_normconsts=True):
+               want_normconsts=True, contspec_out=None):
     """fnft_nsev_batch (include/fnft_b200.h).  q: [B, D].  Returns
     (ret, contspec[B, len] or None, K[B] or None, bound_states[B, Kmax] or None,
-     normconsts[B, nlen] or None, ret_codes[B])."""
+     normconsts[B, nlen] or None, ret_codes[B]).  contspec_out: a caller-owned (e.g. pinned, already touched)
+    complex128 array [B, len] that receives the continuous spectrum instead of a fresh np.zeros array."""
     L = lib()
     q = _c128(q)
     B, D = q.shape
@@ -292,7 +293,12 @@ def nsev_batch(q, T, M=0, XI=None, kappa=+1, opts=None, K=None, Kmax=0, bound_st
         opts = L.fnft_nsev_default_opts()
     cs = None
     if M > 0 and XI is not None:
-        cs = np.zeros((B, _CS_LEN[opts.contspec_type] * M), dtype=np.complex128)
+        if contspec_out is not None:
+            cs = contspec_out
+            if cs.dtype != np.complex128 or not cs.flags.c_contiguous or cs.shape != (B, _CS_LEN[opts.contspec_type] * M):
+                raise ValueError("contspec_out must be a C-contiguous complex128 array [B, len]")
+        else:
+            cs = np.zeros((B, _CS_LEN[opts.contspec_type] * M), dtype=np.complex128)
     XIa = None if XI is None else _f64(XI)
     Ka = bs = nc = None
     if Kmax > 0:

@@ -136,6 +136,8 @@ struct fnftb_ctx {
     size_t B = 0, D = 0;
     const cplx *q = nullptr, *r = nullptr;
     Buf qbuf, rbuf, qpre, warn;
+    const void *qbuf_host = nullptr;  // host batch that qbuf holds (fnftb_signals_staged), with its shape
+    size_t qbuf_B = 0, qbuf_D = 0;
     // tree workspace
     Buf lev0, lev1, mx0, mx1, gbuf, colbuf, W, status, tm, tt0, tt1, twmem;
     TwSet tws;
@@ -513,12 +515,36 @@ int fnftb_set_signals(fnftb_ctx *c, size_t B, size_t D, const void *q, const voi
     CU(cudaMemcpyAsync(c->qbuf.p, q, bytes, cudaMemcpyHostToDevice, c->st));
     c->q = (const cplx *)c->qbuf.p;
     c->r = nullptr;
+    c->qbuf_host = q;
+    c->qbuf_B = B;
+    c->qbuf_D = D;
     if (r) {
         RC(ensure(c->rbuf, bytes));
         CU(cudaMemcpyAsync(c->rbuf.p, r, bytes, cudaMemcpyHostToDevice, c->st));
         c->r = (const cplx *)c->rbuf.p;
     }
     return 0;
+}
+
+// One shot: 1 when the signal buffer still holds the host batch (q, B, D) that the previous fnftb_set_signals call
+// uploaded (the sub-sampling / resampling steps write elsewhere); the batch is then staged again without a second copy.
+// fnft_nsev uses it between the two passes of SUBSAMPLE_AND_REFINE over the same chunk.
+int fnftb_signals_staged(fnftb_ctx *c, size_t B, size_t D, const void *q)
+{
+    if (!c)
+        return 0;
+    const int same = (q != nullptr && c->qbuf_host == q && c->qbuf_B == B && c->qbuf_D == D && c->qbuf.p != nullptr);
+    c->qbuf_host = nullptr;
+    if (!same || cudaSetDevice(c->device) != cudaSuccess)
+        return 0;
+    c->B = B;
+    c->D = D;
+    c->have_box3 = 0;
+    c->slow_wsel = 0;
+    c->rpre = nullptr;
+    c->q = (const cplx *)c->qbuf.p;
+    c->r = nullptr;
+    return 1;
 }
 
 static int ensure_tree(fnftb_ctx *c, size_t B, size_t npad, size_t deg0, size_t deg_out)
@@ -1869,6 +1895,7 @@ int fnftb_set_signals_strided(fnftb_ctx *c, size_t B, size_t Dseg, const void *q
     c->slow_wsel = 0;
     c->rpre = nullptr;
     RC(ensure(c->qbuf, B * Dseg * sizeof(cplx)));
+    c->qbuf_host = nullptr;
     CU(cudaMemcpy2DAsync(c->qbuf.p, Dseg * sizeof(cplx), q, stride * sizeof(cplx), Dseg * sizeof(cplx), B,
                          on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
     c->q = (const cplx *)c->qbuf.p;

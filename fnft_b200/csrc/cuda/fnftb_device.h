@@ -93,6 +93,9 @@ size_t fnftb_max_chunk_ex(const fnftb_ctx *ctx, size_t D, int deg0, size_t M, in
 
 /* Stage B signals of D samples.  q (and r if rmode is EXPLICIT) are host pointers
  * (copied) or, if on_device != 0, device pointers that are used in place. */
+/* One shot: 1 (and the batch staged again) when the signal buffer still holds the host batch that the previous
+ * fnftb_set_signals call uploaded -- saves the second host-to-device copy of SUBSAMPLE_AND_REFINE. */
+int fnftb_signals_staged(fnftb_ctx *ctx, size_t B, size_t D, const void *q);
 int fnftb_set_signals(fnftb_ctx *ctx, size_t B, size_t D, const void *q, const void *r,
                       int on_device);
 

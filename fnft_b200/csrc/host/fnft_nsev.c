@@ -181,6 +181,32 @@ static FNFT_INT nsev_slow_contspec_chunk(fnftb_ctx *ctx, FNFT_UINT D_given, FNFT
  * (nse_discretization_preprocess_signal with *Dsub_ptr = Dsub_req; second pass of the
  * Richardson extrapolation, :374-391); the time window and step size follow (:382-384).
  */
+/* FNFT_B200_NSEV_TIMING=1: host wall time of the phases of one chunk of fnft_nsev_batch (each closed by a device sync) */
+#include <stdio.h>
+#include <time.h>
+static int nsev_timing_on(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("FNFT_B200_NSEV_TIMING");
+        v = (e && e[0]) ? atoi(e) : 0;
+    }
+    return v;
+}
+static void nsev_tick(fnftb_ctx *ctx, const char *label)
+{
+    static __thread struct timespec last;
+    if (!nsev_timing_on())
+        return;
+    fnftb_ctx_sync(ctx);
+    struct timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    if (label != NULL)
+        fprintf(stderr, "[nsev timing] %-36s %8.3f ms\n", label,
+                (now.tv_sec - last.tv_sec) * 1e3 + (now.tv_nsec - last.tv_nsec) * 1e-6);
+    last = now;
+}
+
 static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
                           FNFT_REAL const *const T_full, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
                           FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
@@ -337,7 +363,10 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         step = piped ? fnftb__pipe_step(b0, B, chunk) : chunk; /* tapered at both ends */
         const FNFT_UINT nb = (B - b0 < step) ? (B - b0) : step;
         int32_t *st_cur = status;
+        int staged_above = 0;
+        nsev_tick(ctx, NULL);
         if (nb > 0 && want_discspec && bsloc == fnft_nsev_bsloc_SUBSAMPLE_AND_REFINE && Dsub_req == 0) {
+            staged_above = 1;
             /* First step of the mixed method (src/fnft_nsev.c:276-296): initial guesses from
              * the fast eigenvalue method on a subsampled signal. */
             FNFT_UINT Dsub = opts->Dsub;
@@ -361,10 +390,12 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                 ret_code = E_DEVICE;
                 goto leave_fun;
             }
+            nsev_tick(ctx, "copy in + sub-sampling");
             const FNFT_REAL Tsub[2] = {T[0], T[0] + ((Dsub - 1) * nskip) * eps_t_full}; /* :290-291 */
             ret_code = fnftb__nsev_fasteig_chunk(ctx, nb, Dsub * upsampling, Dsub, Tsub, kappa, 0, K + b0,
                                                  Kmax, bound_states + b0 * Kmax, opts);
             CHECK_RETCODE(ret_code, leave_fun);
+            nsev_tick(ctx, "sub-sampled fast eigenvalue pass");
         }
         if (nb > 0 && segmented) {
             ret_code = nsev_contspec_segmented(ctx, nb, D, Dtree_max, q + b0 * D, T, eps_t, M, XI, kappa, opts, &sd,
@@ -373,8 +404,10 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
         }
         if (nb > 0 && (!segmented || want_discspec)) {
             /* preprocessing (src/fnft_nsev.c:272): plain copy for upsampling 1; the
-             * 4SPLIT4 schemes resample on the device */
-            if (fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, devptr) != 0) {
+             * 4SPLIT4 schemes resample on the device.  The chunk is still on the device when the
+             * sub-sampled pass above has just uploaded it. */
+            if (!(staged_above && !devptr && !segmented && fnftb_signals_staged(ctx, nb, D, q + b0 * D)) &&
+                fnftb_set_signals(ctx, nb, D, q + b0 * D, NULL, devptr) != 0) {
                 ret_code = E_DEVICE;
                 goto leave_fun;
             }
@@ -427,6 +460,8 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                 CHECK_RETCODE(ret_code, leave_fun);
             }
         }
+        if (!piped)
+            nsev_tick(ctx, "staging + continuous spectrum");
         /* status of this chunk (pipelined mode: all chunks at once after the loop) */
         if (want_contspec && !devptr && !piped) {
             const FNFT_UINT cb0 = b0, cnb = nb;
@@ -463,6 +498,7 @@ static FNFT_INT nsev_pass(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX con
                 ret_code = rc2;
             if (rc2 != FNFT_SUCCESS && ret_codes == NULL)
                 goto leave_fun;
+            nsev_tick(ctx, "Newton + norming constants");
         } else if (K != NULL && !devptr) {
             for (FNFT_UINT b = 0; b < nb; b++)
                 K[b0 + b] = 0; /* src/fnft_nsev.c:558-560 */
