@@ -856,6 +856,42 @@ def main():
                                  "cpu_baseline": {"value": 1.0 / t_ref1, "unit": "signals/s", "cores": 1,
                                                   "kind": "reference", "sample": "4 signals on one core"}}
             gate("config3_inverse", [rel_err(q_inv[i], Q3[i]) for i in range(n3)])
+            # --- config 7: the same signals through fnft_nsev with its DEFAULT options (SUBSAMPLE_AND_REFINE: GPU root
+            # finder on the sub-sampled signal, Newton refinement on the full one) + norming constants, residues and the
+            # reflection coefficient at M = D points.  The reference needs ~6 s per signal for this (companion-matrix
+            # stand-in for its Fortran root finder), so the gate compares with config 3's result above -- Newton from the
+            # TRUE eigenvalues, itself gated against the reference -- on every signal where all K3 bound states were found
+            # (tests/test_gpu_fullsize.py checks the number of bound states against the reference itself).
+            o7 = F.nsev_default_opts()
+            o7.discspec_type = F.DSTYPE_BOTH
+            K7max = 64
+            cs7h = torch.empty((n3, C3["D"]), dtype=torch.complex128, pin_memory=True)
+            cs7 = cs7h.numpy()
+            cs7[...] = 0
+            K70, G70 = np.zeros(n3), np.zeros((n3, K7max), dtype=np.complex128)
+            dt7, (ret7, _, Ka7, bs7, nc7, _) = timed_call(
+                lambda: F.nsev_batch(Q3p, C3["T"], C3["D"], (-4.0, 4.0), 1, o7, K=K70, Kmax=K7max, bound_states=G70,
+                                     contspec_out=cs7))
+            if ret7 != 0:
+                raise SystemExit("config 7: fnft_nsev_batch returned %d" % ret7)
+            L.fnft_b200_profile_enable(1)
+            F.nsev_batch(Q3p, C3["T"], C3["D"], (-4.0, 4.0), 1, o7, K=K70, Kmax=K7max, bound_states=G70, contspec_out=cs7)
+            rep7 = parse_report(L.fnft_b200_profile_report())
+            L.fnft_b200_profile_enable(0)
+            errs7 = []
+            for i in range(n3):
+                if int(Ka7[i]) != K3 or int(Ka[i]) != K3:
+                    continue
+                # the residues follow the K norming constants that were found (src/fnft_nsev.c:950-954)
+                errs7.append(compare3(Ka7[i], bs7[i], nc7[i], (0, K3, bs[i, :K3], ncs[i, :2 * K3]), K3))
+            cfgs["7"] = {"workload": "fnft_nsev DEFAULT options (SUBSAMPLE_AND_REFINE bound states, norming constants + "
+                                     "residues, reflection coefficient at M = D), D=4096, 8-soliton signals, one batch of %d "
+                                     "over %d GPU(s), pinned host buffers" % (C3["B"], world),
+                         "value": C3["B"] / dt7, "unit": "signals/s", "ms_per_batch": dt7 * 1e3,
+                         "found_all_rank0": float((Ka7 == K3).mean()), "mean_K_rank0": float(Ka7.mean()),
+                         "compared_with_config3_rank0": len(errs7),
+                         "kernel_ms_rank0": {k: round(ms, 4) for k, (n, ms) in sorted(rep7.items())}}
+            gate("config7_vs_config3", errs7)
         # --- config 4: fnft_kdvv, 4SPLIT4B, pinned host buffers
         n4 = g4[1] - g4[0]
         U = config4_inputs(g4[0], g4[1])
@@ -911,7 +947,8 @@ def main():
     # moves ITS roots by ~1e-7 (tests/test_gpu_parity.py::test_nsep_config5_roots_against_long_double);
     # the gate for this configuration is therefore 1e-6 on the positions and exact point counts.
     bounds = {"config5": 1e-6}
-    names = ["config2_device", "config2_e2e", "config2_strong", "config3", "config3_inverse", "config4", "config5"]
+    names = ["config2_device", "config2_e2e", "config2_strong", "config3", "config3_inverse", "config7_vs_config3", "config4",
+             "config5"]
     parity, ok = None, True
     if have_ref:
         parity = {"metric": "misc_rel_err(ours, reference) per signal (bound states: relative error per "

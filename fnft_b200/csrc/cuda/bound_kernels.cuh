@@ -43,21 +43,33 @@ HD void bo_step(cplx q, cplx r, cplx l, double h, cplx U[4], cplx Ud[4])
     const cplx k = c_sqrt(ks);
     cplx ch, shk;
     c_coshsinh(cscale(k, h), &ch, &shk);
-    cplx sh;
-    if (ks.x != 0.0 || ks.y != 0.0)
-        sh = cdiv(shk, k);
-    else
-        sh = make_cplx(h, 0.0);
+    const bool nz = (ks.x != 0.0 || ks.y != 0.0);
+    // sinh(k h)/k enters U itself: a true division (the reference's own tests bound the norming constants of a sech
+    // pulse by 5e-14 after 2049 steps, which products with a reciprocal miss by a factor 1.4)
+    const cplx sh = nz ? cdiv(shk, k) : make_cplx(h, 0.0);
     const cplx u1 = cmuli(cmul(l, sh));  // l*sh*i
     U[0] = csub(ch, u1);
     U[1] = cmul(q, sh);
     U[2] = cmul(r, sh);
     U[3] = cadd(ch, u1);
     if (WITH_D) {
-        const cplx chi = cdiv(ch, ks);
-        const cplx ud1 = cmuli(cscale(cmul(l2, chi), h));                    // h*l^2*chi*i
-        const cplx ud2 = cdiv(cmul(l, csub(cscale(ch, h), sh)), ks);         // l*(h*ch-sh)/ks
-        const cplx l2i_ks = cdiv(cmuli(l2), ks);                             // l^2*i/ks
+        // The three quotients of the derivative share the denominator ks: ONE complex reciprocal (two real divisions)
+        // and products instead of three complex divisions (nine real ones, the longest dependency chains of the step).
+        // ks == 0: infinite like the reference's formulas.
+        cplx jks = make_cplx(INFINITY, 0.0);
+        if (nz) {
+            if (fabs(ks.x) >= fabs(ks.y)) {
+                const double t = ks.y / ks.x, d = 1.0 / (ks.x + ks.y * t);
+                jks = make_cplx(d, -t * d);
+            } else {
+                const double t = ks.x / ks.y, d = 1.0 / (ks.x * t + ks.y);
+                jks = make_cplx(t * d, -d);
+            }
+        }
+        const cplx chi = cmul(ch, jks);
+        const cplx ud1 = cmuli(cscale(cmul(l2, chi), h));                     // h*l^2*chi*i
+        const cplx ud2 = cmul(cmul(l, csub(cscale(ch, h), sh)), jks);         // l*(h*ch-sh)/ks
+        const cplx l2i_ks = cmul(cmuli(l2), jks);                             // l^2*i/ks
         // (l*h + i + l^2 i/ks) and (l*h - i - l^2 i/ks)
         const cplx t1 = make_cplx(l.x * h + l2i_ks.x, l.y * h + 1.0 + l2i_ks.y);
         const cplx t2 = make_cplx(l.x * h - l2i_ks.x, l.y * h - 1.0 - l2i_ks.y);
