@@ -100,8 +100,11 @@ DEV void bo_chunk_bounds(int D, int up, int lane, int *lo, int *hi)
     *hi = (int)(((long long)(lane + 1) * Dg) / 32) * up;
 }
 
-// Newton iterations, one warp per (signal, eigenvalue).  blockDim.x = 128
-__global__ void __launch_bounds__(128) k_newton_warp(const BoundArgs a)
+// Newton iterations, one warp per (signal, eigenvalue).  blockDim.x = 128.  The kernel is bound by the dependency chains
+// of the step (sqrt, cosh/sinh, divisions: 49 % of the stalls are fixed-latency waits at 3 warps per scheduler, FP64 pipe
+// 45 %, profiles/r02_roots_compact.md): four CTAs per SM (128 registers, 128 bytes of spills) beat three (166 registers),
+// 6.99 -> 6.40 ms per 1024 signals of config 3; five (96 registers) measure the same as four.
+__global__ void __launch_bounds__(128, 4) k_newton_warp(const BoundArgs a)
 {
     const int lane = threadIdx.x & 31;
     const long long gid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -176,7 +179,8 @@ __global__ void __launch_bounds__(128) k_newton_warp(const BoundArgs a)
 
 // a, a', b for given eigenvalues, one warp per (signal, eigenvalue).  Scratch a.phi holds
 // PHI at the given sample points of every eigenvalue: [koff[s] + i][D_given + 1][2].
-__global__ void __launch_bounds__(128) k_normconsts_warp(const BoundArgs a)
+// (launch bounds: five CTAs per SM, 96 registers: 5.60 -> 4.74 ms per 1024 signals of config 3; four: 5.12)
+__global__ void __launch_bounds__(128, 5) k_normconsts_warp(const BoundArgs a)
 {
     const int lane = threadIdx.x & 31;
     const long long gid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
