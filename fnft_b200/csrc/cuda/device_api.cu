@@ -17,8 +17,16 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 std::atomic<unsigned long long> g_fnftb_launch_count{0};
-int g_fnftb_profile_on = 0;
+// bit 0: CUDA-event timing of every launch (fnftb_profile_enable), bit 1: NVTX ranges around every launch, named like the
+// entries of the profile report (FNFT_B200_NVTX=1; read once at load time, header-only NVTX3: nothing happens unless a
+// tool is attached).  The launch sites test the word, fnftb_profile_begin / _end look at the bits.
+int g_fnftb_profile_on = [] {
+    const char *e = getenv("FNFT_B200_NVTX");
+    return (e && e[0] == '1') ? 2 : 0;
+}();
 
 // ---------------------------------------------------------------------------
 // optional per-launch timing (used by bench.py for the roofline numbers)
@@ -44,6 +52,10 @@ static cudaEvent_t prof_event()
 }
 void fnftb_profile_begin(const char *name, cudaStream_t st)
 {
+    if (g_fnftb_profile_on & 2)
+        nvtxRangePushA(name);
+    if (!(g_fnftb_profile_on & 1))
+        return;
     ProfRec r;
     r.name = name;
     r.e0 = prof_event();
@@ -51,7 +63,24 @@ void fnftb_profile_begin(const char *name, cudaStream_t st)
     cudaEventRecord(r.e0, st);
     g_prof.push_back(r);
 }
-void fnftb_profile_end(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
+void fnftb_profile_end(cudaStream_t st)
+{
+    if (g_fnftb_profile_on & 1)
+        cudaEventRecord(g_prof.back().e1, st);
+    if (g_fnftb_profile_on & 2)
+        nvtxRangePop();
+}
+// NVTX ranges of the host layer (one per public *_batch call and per phase of a chunk); no-ops without FNFT_B200_NVTX=1
+extern "C" void fnftb_range_push(const char *name)
+{
+    if (g_fnftb_profile_on & 2)
+        nvtxRangePushA(name);
+}
+extern "C" void fnftb_range_pop(void)
+{
+    if (g_fnftb_profile_on & 2)
+        nvtxRangePop();
+}
 
 static thread_local std::string g_err;
 
@@ -238,7 +267,7 @@ const char *fnftb_last_error(void) { return g_err.c_str(); }
 
 unsigned long long fnftb_launch_count(void) { return g_fnftb_launch_count.load(); }
 
-void fnftb_profile_enable(int on) { g_fnftb_profile_on = on; }
+void fnftb_profile_enable(int on) { g_fnftb_profile_on = (g_fnftb_profile_on & 2) | (on ? 1 : 0); }
 
 // Sums the recorded launches per kernel name into a text report
 // "name count total_ms\n..." (buffer owned by the library) and clears the records.

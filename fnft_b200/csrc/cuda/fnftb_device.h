@@ -93,11 +93,16 @@ size_t fnftb_max_chunk_ex(const fnftb_ctx *ctx, size_t D, int deg0, size_t M, in
 
 /* Stage B signals of D samples.  q (and r if rmode is EXPLICIT) are host pointers
  * (copied) or, if on_device != 0, device pointers that are used in place. */
+int fnftb_set_signals(fnftb_ctx *ctx, size_t B, size_t D, const void *q, const void *r,
+                      int on_device);
 /* One shot: 1 (and the batch staged again) when the signal buffer still holds the host batch that the previous
  * fnftb_set_signals call uploaded -- saves the second host-to-device copy of SUBSAMPLE_AND_REFINE. */
 int fnftb_signals_staged(fnftb_ctx *ctx, size_t B, size_t D, const void *q);
-int fnftb_set_signals(fnftb_ctx *ctx, size_t B, size_t D, const void *q, const void *r,
-                      int on_device);
+/* NVTX ranges (FNFT_B200_NVTX=1): every kernel launch is wrapped in a range named like its entry of the profile
+ * report; the host layer adds one range per public call and per phase of a chunk. */
+void fnftb_range_push(const char *name);
+void fnftb_range_pop(void);
+
 
 /* 4SPLIT4 preprocessing of the staged signals: replaces them by the 2*D resampled and
  * weighted samples (device resident).  warn_host[B] (may be NULL) gets 1 where the

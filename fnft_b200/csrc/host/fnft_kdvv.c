@@ -40,7 +40,24 @@ static void kdvv_shard(void *arg, int shard, int nshards)
                                    j->opts, j->ret_codes ? j->ret_codes + b0 : NULL);
 }
 
+static FNFT_INT kdvv_batch_impl(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const u,
+                         FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                         FNFT_REAL const *const XI, fnft_kdvv_opts_t const *opts,
+                         FNFT_INT *const ret_codes);
+
+/* public entry: NVTX range around the call (FNFT_B200_NVTX=1, no-op otherwise) */
 FNFT_INT fnft_kdvv_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const u,
+                         FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                         FNFT_REAL const *const XI, fnft_kdvv_opts_t const *opts,
+                         FNFT_INT *const ret_codes)
+{
+    fnftb_range_push("fnft_kdvv_batch");
+    const FNFT_INT rc = kdvv_batch_impl(B, D, u, T, M, contspec, XI, opts, ret_codes);
+    fnftb_range_pop();
+    return rc;
+}
+
+static FNFT_INT kdvv_batch_impl(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const u,
                          FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
                          FNFT_REAL const *const XI, fnft_kdvv_opts_t const *opts,
                          FNFT_INT *const ret_codes)

@@ -562,7 +562,28 @@ static void nsep_shard(void *arg, int shard, int nshards)
                                    j->ret_codes ? j->ret_codes + b0 : NULL);
 }
 
+static FNFT_INT nsep_batch_impl(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
+                         FNFT_REAL const *const T, FNFT_REAL const phase_shift,
+                         FNFT_UINT *const K, const FNFT_UINT Kmax, FNFT_COMPLEX *const main_spec,
+                         FNFT_UINT *const Mcount, const FNFT_UINT Mmax,
+                         FNFT_COMPLEX *const aux_spec, const FNFT_INT kappa,
+                         fnft_nsep_opts_t const *opts, FNFT_INT *const ret_codes);
+
+/* public entry: NVTX range around the call (FNFT_B200_NVTX=1, no-op otherwise) */
 FNFT_INT fnft_nsep_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
+                         FNFT_REAL const *const T, FNFT_REAL const phase_shift,
+                         FNFT_UINT *const K, const FNFT_UINT Kmax, FNFT_COMPLEX *const main_spec,
+                         FNFT_UINT *const Mcount, const FNFT_UINT Mmax,
+                         FNFT_COMPLEX *const aux_spec, const FNFT_INT kappa,
+                         fnft_nsep_opts_t const *opts, FNFT_INT *const ret_codes)
+{
+    fnftb_range_push("fnft_nsep_batch");
+    const FNFT_INT rc = nsep_batch_impl(B, D, q, T, phase_shift, K, Kmax, main_spec, Mcount, Mmax, aux_spec, kappa, opts, ret_codes);
+    fnftb_range_pop();
+    return rc;
+}
+
+static FNFT_INT nsep_batch_impl(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
                          FNFT_REAL const *const T, FNFT_REAL const phase_shift,
                          FNFT_UINT *const K, const FNFT_UINT Kmax, FNFT_COMPLEX *const main_spec,
                          FNFT_UINT *const Mcount, const FNFT_UINT Mmax,

@@ -559,7 +559,28 @@ static void nsev_shard(void *arg, int shard, int nshards)
                                    j->kappa, j->opts, j->ret_codes ? j->ret_codes + b0 : NULL);
 }
 
+static FNFT_INT nsev_batch_impl(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
+                         FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                         FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
+                         FNFT_COMPLEX *const bound_states,
+                         FNFT_COMPLEX *const normconsts_or_residues, const FNFT_INT kappa,
+                         fnft_nsev_opts_t const *opts, FNFT_INT *const ret_codes);
+
+/* public entry: NVTX range around the call (FNFT_B200_NVTX=1, no-op otherwise) */
 FNFT_INT fnft_nsev_batch(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
+                         FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                         FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
+                         FNFT_COMPLEX *const bound_states,
+                         FNFT_COMPLEX *const normconsts_or_residues, const FNFT_INT kappa,
+                         fnft_nsev_opts_t const *opts, FNFT_INT *const ret_codes)
+{
+    fnftb_range_push("fnft_nsev_batch");
+    const FNFT_INT rc = nsev_batch_impl(B, D, q, T, M, contspec, XI, K, Kmax, bound_states, normconsts_or_residues, kappa, opts, ret_codes);
+    fnftb_range_pop();
+    return rc;
+}
+
+static FNFT_INT nsev_batch_impl(const FNFT_UINT B, const FNFT_UINT D, FNFT_COMPLEX const *const q,
                          FNFT_REAL const *const T, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
                          FNFT_REAL const *const XI, FNFT_UINT *const K, const FNFT_UINT Kmax,
                          FNFT_COMPLEX *const bound_states,

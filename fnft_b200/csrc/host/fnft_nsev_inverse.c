@@ -191,7 +191,28 @@ static FNFT_INT inverse_checks(const FNFT_UINT M, FNFT_COMPLEX const *contspec, 
     return FNFT_SUCCESS;
 }
 
+static FNFT_INT nsev_inverse_batch_impl(const FNFT_UINT B, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                                 FNFT_REAL const *const XI, FNFT_UINT const K,
+                                 FNFT_COMPLEX const *const bound_states,
+                                 FNFT_COMPLEX const *const normconsts_or_residues, const FNFT_UINT D,
+                                 FNFT_COMPLEX *const q, FNFT_REAL const *const T, const FNFT_INT kappa,
+                                 fnft_nsev_inverse_opts_t const *opts_ptr, FNFT_INT *ret_codes);
+
+/* public entry: NVTX range around the call (FNFT_B200_NVTX=1, no-op otherwise) */
 FNFT_INT fnft_nsev_inverse_batch(const FNFT_UINT B, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
+                                 FNFT_REAL const *const XI, FNFT_UINT const K,
+                                 FNFT_COMPLEX const *const bound_states,
+                                 FNFT_COMPLEX const *const normconsts_or_residues, const FNFT_UINT D,
+                                 FNFT_COMPLEX *const q, FNFT_REAL const *const T, const FNFT_INT kappa,
+                                 fnft_nsev_inverse_opts_t const *opts_ptr, FNFT_INT *ret_codes)
+{
+    fnftb_range_push("fnft_nsev_inverse_batch");
+    const FNFT_INT rc = nsev_inverse_batch_impl(B, M, contspec, XI, K, bound_states, normconsts_or_residues, D, q, T, kappa, opts_ptr, ret_codes);
+    fnftb_range_pop();
+    return rc;
+}
+
+static FNFT_INT nsev_inverse_batch_impl(const FNFT_UINT B, const FNFT_UINT M, FNFT_COMPLEX *const contspec,
                                  FNFT_REAL const *const XI, FNFT_UINT const K,
                                  FNFT_COMPLEX const *const bound_states,
                                  FNFT_COMPLEX const *const normconsts_or_residues, const FNFT_UINT D,

@@ -245,3 +245,19 @@ def test_inverse_argument_checks_need_no_gpu(F):
     assert IB.nse_finvscatter(F.lib(), tm, 0.1, 0, 4)[0] == E_INVALID       # kappa
     assert IB.nse_finvscatter(F.lib(), tm, 0.1, 1, 11)[0] != 0              # D = deg / 2 = 4 but not invertible scheme
     assert IB.poly_specfact(F.lib(), np.ones(4, dtype=np.complex128), 0, 1)[0] == E_INVALID   # oversampling 0
+
+
+def test_nvtx_ranges_are_harmless_without_a_tool():
+    # FNFT_B200_NVTX=1 wraps every launch and every public *_batch call in an NVTX range (header-only NVTX3: without an
+    # attached tool the calls return at once).  A fresh process, because the variable is read when the library is loaded.
+    import subprocess
+    import sys
+    code = ("import ctypes, os; L = ctypes.CDLL(os.path.join(%r, 'fnft_b200', 'lib', 'libfnft_b200.so'));"
+            "L.fnftb_range_push(b'test'); L.fnftb_range_pop();"
+            "L.fnft_nsev_batch.restype = ctypes.c_int32;"
+            "rc = L.fnft_nsev_batch(ctypes.c_size_t(0), ctypes.c_size_t(0), None, None, ctypes.c_size_t(0), None, None, None,"
+            " ctypes.c_size_t(0), None, None, ctypes.c_int32(1), None, None); print('rc', rc)" % ROOT)
+    env = dict(os.environ, FNFT_B200_NVTX="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "rc" in out.stdout and "rc 0" not in out.stdout     # invalid arguments are refused, through the ranges
