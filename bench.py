@@ -827,6 +827,24 @@ def main():
                          "cpu_baseline": cpu_base.get("c3")}
             idx, res = refs.get("c3", ([], []))
             gate("config3", [compare3(Ka[i], bs[i], ncs[i], res[j], K3) for j, i in enumerate(idx)])
+
+            def fp64_entry(kernel, key, ms):
+                # FP64 issue-slot roofline of a kernel of configs 3 / 7: counted FP64 warp instructions of the seeded
+                # signals (profiles/bound_fp64_instr.json, ncu opcode histogram) over the live CUDA-event time
+                try:
+                    with open(os.path.join(ROOT, "profiles", "bound_fp64_instr.json")) as f:
+                        cnt = json.load(f)[kernel]["fp64_warp_instructions_per_signal"]
+                    peak64 = float(roofline["fp64_peak_tflops_measured"])  # DFMA micro-benchmark of this run
+                    ach = cnt * n3 * 64 / (ms * 1e-3) / 1e12
+                    return {"kernel": kernel, "bound": "fp64 pipe issue slots", "achieved": ach, "peak": peak64,
+                            "unit": "TFLOP/s, every FP64 warp instruction counted as one FMA slot (64 flop)",
+                            "frac": ach / peak64 if peak64 > 0 else None, "ms": ms,
+                            "source": "profiles/bound_fp64_instr.json (ncu opcode histogram of the seeded signals)"}
+                except Exception:
+                    return None
+            cfgs["3"]["fp64"] = [e for e in (fp64_entry("k_newton_warp", "bound_newton_warp", rep3["bound_newton_warp"][1]),
+                                             fp64_entry("k_normconsts_warp", "bound_normconsts_warp",
+                                                        rep3["bound_normconsts_warp"][1])) if e]
             # --- inverse direction: the same 8-soliton signals from fnft_nsev_inverse_batch on the GPU
             # (Darboux kernels), checked against the signals the reference synthesised for config 3
             lam3, bn3, _ = config3_params()
@@ -891,6 +909,10 @@ def main():
                          "found_all_rank0": float((Ka7 == K3).mean()), "mean_K_rank0": float(Ka7.mean()),
                          "compared_with_config3_rank0": len(errs7),
                          "kernel_ms_rank0": {k: round(ms, 4) for k, (n, ms) in sorted(rep7.items())}}
+            if "poly_roots" in rep7:
+                e7 = fp64_entry("k_roots_aberth_c", "poly_roots", rep7["poly_roots"][1])
+                if e7:
+                    cfgs["7"]["fp64"] = [e7]
             gate("config7_vs_config3", errs7)
         # --- config 4: fnft_kdvv, 4SPLIT4B, pinned host buffers
         n4 = g4[1] - g4[0]
