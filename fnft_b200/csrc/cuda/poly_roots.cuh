@@ -315,6 +315,18 @@ static __device__ __forceinline__ float4 roots_split(const cplx v)
 
 // CS: the coefficients and their moduli are staged in shared memory as well (44 instead of 20 bytes per root): the Horner
 // recurrences of a CTA's last few roots then run at shared-memory latency instead of waiting for L2 every few steps.
+// shared-memory copy of root i for the Aberth sums: slot i & 1 of the pair i >> 1, negated (the loop only adds)
+static __device__ __forceinline__ void roots_publish(float4 *zf, const int i, const cplx v)
+{
+    const float4 f = roots_split(v);
+    float *hi = (float *)(zf + 2 * (i >> 1)), *lo = hi + 4;
+    const int sl = i & 1;
+    hi[sl] = -f.x;
+    hi[2 + sl] = -f.y;
+    lo[sl] = -f.z;
+    lo[2 + sl] = -f.w;
+}
+
 template <int MAXNT, bool CS>
 __global__ void __launch_bounds__(MAXNT) k_roots_aberth_c(const RootsArgs a)
 {
@@ -328,16 +340,20 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth_c(const RootsArgs a)
     const cplx *c = a.coef + (size_t)b * a.cstride + lead;
     const double *ac = a.absc + (size_t)b * (n + 1) + lead;
     cplx *groots = a.roots + (size_t)b * n;
-    float4 *zf = (float4 *)fnftb_smem;                  // [n]
-    cplx *sc = (cplx *)(zf + n);                        // [n + 1] (CS)
+    // roots 2p and 2p+1 as NEGATED float pairs, packed for the f32x2 instructions of sm_100:
+    // zf[2p] = -(hi.x0, hi.x1, hi.y0, hi.y1), zf[2p+1] = -(lo.x0, lo.x1, lo.y0, lo.y1)
+    float4 *zf = (float4 *)fnftb_smem;                  // [n + 1]
+    cplx *sc = (cplx *)(zf + n + 1);                    // [n + 1] (CS)
     double *sa = (double *)(sc + (CS ? n + 1 : 0));     // [n + 1] (CS)
     int *s_wcnt = (int *)(sa + (CS ? n + 1 : 0));       // [32]
     unsigned short *lst0 = (unsigned short *)(s_wcnt + 32);  // [n] roots that still move, ascending
     unsigned short *lst1 = lst0 + n;                         // [n] the list of the next sweep
     for (int i = tid; i < m; i += nt) {
-        zf[i] = roots_split(groots[i]);
+        roots_publish(zf, i, groots[i]);
         lst0[i] = (unsigned short)i;
     }
+    if (tid == 0 && (m & 1))  // partner of the last root of an odd degree: far away, its term is (-1e30) * rcp(inf) = 0
+        roots_publish(zf, m, make_cplx(1e30, 0.0));
     if constexpr (CS) {
         for (int i = tid; i <= m; i += nt) {
             sc[i] = c[i];
@@ -404,27 +420,23 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth_c(const RootsArgs a)
                         Nw = make_cplx(1e-3 * az + 1e-6, 1e-3 * az + 1e-6);
                     }
                     const float4 fi = roots_split(zi);
-                    float sx0 = 0.f, sy0 = 0.f, sx1 = 0.f, sy1 = 0.f;
-                    int j = 0;
-#pragma unroll 2
-                    for (; j + 1 < m; j += 2) {
-                        const float4 f0 = zf[j], f1 = zf[j + 1];
-                        const float dx0 = (fi.x - f0.x) + (fi.z - f0.z), dy0 = (fi.y - f0.y) + (fi.w - f0.w);
-                        const float dx1 = (fi.x - f1.x) + (fi.z - f1.z), dy1 = (fi.y - f1.y) + (fi.w - f1.w);
-                        const float i0 = roots_rcp(fmaxf(fmaf(dx0, dx0, dy0 * dy0), 1e-37f));
-                        const float i1 = roots_rcp(fmaxf(fmaf(dx1, dx1, dy1 * dy1), 1e-37f));
-                        sx0 = fmaf(dx0, i0, sx0);
-                        sy0 = fmaf(-dy0, i0, sy0);
-                        sx1 = fmaf(dx1, i1, sx1);
-                        sy1 = fmaf(-dy1, i1, sy1);
+                    const float2 fhx = make_float2(fi.x, fi.x), fhy = make_float2(fi.y, fi.y);
+                    const float2 flx = make_float2(fi.z, fi.z), fly = make_float2(fi.w, fi.w);
+                    float2 sx = make_float2(0.f, 0.f), sy = make_float2(0.f, 0.f);
+                    const int np = (m + 1) >> 1;
+                    // two roots per iteration in packed single precision (FADD2 / FMUL2 / FFMA2): differences
+                    // (hi_i - hi_j) + (lo_i - lo_j), 1 / |d|^2 by MUFU.RCP, sums of d / |d|^2 (conjugated at the end)
+#pragma unroll 4
+                    for (int pj = 0; pj < np; ++pj) {
+                        const float4 A = zf[2 * pj], Bq = zf[2 * pj + 1];
+                        const float2 dx = __fadd2_rn(__fadd2_rn(fhx, make_float2(A.x, A.y)), __fadd2_rn(flx, make_float2(Bq.x, Bq.y)));
+                        const float2 dy = __fadd2_rn(__fadd2_rn(fhy, make_float2(A.z, A.w)), __fadd2_rn(fly, make_float2(Bq.z, Bq.w)));
+                        const float2 r2 = __ffma2_rn(dy, dy, __fmul2_rn(dx, dx));
+                        const float2 inv = make_float2(roots_rcp(fmaxf(r2.x, 1e-37f)), roots_rcp(fmaxf(r2.y, 1e-37f)));
+                        sx = __ffma2_rn(dx, inv, sx);
+                        sy = __ffma2_rn(dy, inv, sy);
                     }
-                    if (j < m) {
-                        const float4 f0 = zf[j];
-                        const float dx0 = (fi.x - f0.x) + (fi.z - f0.z), dy0 = (fi.y - f0.y) + (fi.w - f0.w);
-                        const float i0 = roots_rcp(fmaxf(fmaf(dx0, dx0, dy0 * dy0), 1e-37f));
-                        sx0 = fmaf(dx0, i0, sx0);
-                        sy0 = fmaf(-dy0, i0, sy0);
-                    }
+                    const float sx0 = sx.x, sx1 = sx.y, sy0 = -sy.x, sy1 = -sy.y;
                     const cplx S = make_cplx((double)sx0 + (double)sx1, (double)sy0 + (double)sy1);
                     const cplx den = csub(make_cplx(1.0, 0.0), cmul(Nw, S));
                     cplx dz = cdiv(Nw, den);
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(MAXNT) k_roots_aberth_c(const RootsArgs a)
             __syncthreads();  // every Aberth sum of this chunk has read the old values
             if (moving) {
                 groots[i] = zi;
-                zf[i] = roots_split(zi);
+                roots_publish(zf, i, zi);
             }
             if (lane == 0)
                 s_wcnt[wid] = __popc(bal);
@@ -489,7 +501,7 @@ static inline int roots_launch_c(const RootsArgs &a, int B, cudaStream_t st)
     if (knob_nt)
         want = knob_nt;
     const int nt = std::min(want, ((a.n + 31) / 32) * 32);
-    const size_t smem = (sizeof(float4) + 2 * sizeof(unsigned short)) * (size_t)a.n + 32 * sizeof(int) +
+    const size_t smem = sizeof(float4) * ((size_t)a.n + 1) + 2 * sizeof(unsigned short) * (size_t)a.n + 32 * sizeof(int) +
                         (cs ? (sizeof(cplx) + sizeof(double)) * ((size_t)a.n + 1) : 0);
     auto kern = cs ? k_roots_aberth_c<1024, true> : k_roots_aberth_c<1024, false>;
     {
