@@ -292,3 +292,29 @@ def test_bench_parity_gate_trips_on_a_corrupted_output():
     assert bad.returncode == 1, (bad.returncode, bad.stderr[-2000:])
     line = json.loads(bad.stdout.strip().splitlines()[-1])
     assert not line["parity"]["ok"] and line["parity"]["checks"]["config2_device"]["max"] > 1e-9
+
+
+def test_default_options_root_finder_cta_sizes_agree(F):
+    """The compacting root finder (poly_roots.cuh, k_roots_aberth_c) picks its CTA size by the number of polynomials in
+    flight: 256 threads from 296 polynomials, 512 from 74, one CTA with as many threads as roots for fewer.  The three
+    schedules update the roots in different orders; after the Newton refinement of SUBSAMPLE_AND_REFINE the default
+    fnft_nsev must return the same bound states whichever one ran."""
+    D, T = 2048, (-14.0, 14.0)   # Dsub = 499: a(z) of degree 998, CTAs of 256 / 512 / 1024 threads
+    B = 320
+    Q = _signals(B, D, T, 77)
+    o = F.nsev_default_opts()
+    Kmax = 16
+    K0, G0 = np.zeros(B), np.zeros((B, Kmax), dtype=np.complex128)
+    ret_a, _, Ka, bsa, _, rca = F.nsev_batch(Q, T, 0, None, 1, o, K=K0, Kmax=Kmax, bound_states=G0)       # 256 threads
+    nb = 96
+    ret_b, _, Kb, bsb, _, rcb = F.nsev_batch(Q[:nb], T, 0, None, 1, o, K=K0[:nb], Kmax=Kmax, bound_states=G0[:nb])  # 512
+    assert ret_a == 0 and ret_b == 0 and (rca == 0).all() and (rcb == 0).all()
+    assert (Ka[:nb] == Kb).all() and Ka.sum() >= B          # sech pulses of amplitude 0.6 ... 3: about two each
+    for i in range(nb):
+        k = int(Ka[i])
+        assert np.abs(np.sort_complex(bsa[i, :k]) - np.sort_complex(bsb[i, :k])).max() <= 1e-10 if k else True
+    for i in (0, 5, 17):                                      # single calls: one CTA per polynomial, 1024 threads
+        r1, _, K1, bs1, _ = F.nsev(Q[i], T, 0, None, 1, o, K=Kmax, want_contspec=False)
+        assert r1 == 0 and K1 == int(Ka[i])
+        if K1:
+            assert np.abs(np.sort_complex(bs1[:K1]) - np.sort_complex(bsa[i, :K1])).max() <= 1e-10
