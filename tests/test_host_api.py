@@ -261,3 +261,13 @@ def test_nvtx_ranges_are_harmless_without_a_tool():
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "rc" in out.stdout and "rc 0" not in out.stdout     # invalid arguments are refused, through the ranges
+
+
+def test_nsev_batch_wrapper_checks_the_caller_owned_spectrum_array(F):
+    # contspec_out (fnft_b200.nsev_batch): a caller-owned, pre-touched array for the continuous spectrum; its shape and
+    # layout are checked before anything reaches the library
+    q = np.zeros((2, 8), dtype=np.complex128)
+    for bad in (np.zeros((2, 3), dtype=np.complex128), np.zeros((2, 4), dtype=np.complex64),
+                np.zeros((4, 2), dtype=np.complex128).T):
+        with pytest.raises(ValueError):
+            F.nsev_batch(q, (-1.0, 1.0), 4, (-1.0, 1.0), 1, None, contspec_out=bad)
