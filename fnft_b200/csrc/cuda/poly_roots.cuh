@@ -26,6 +26,10 @@
 //     spaced arguments on every circle, golden-ratio offsets between the circles;
 //   * values that are still moving after maxit sweeps are returned as NaN (the callers' box
 //     filter drops them; fnft__poly_roots_fasteigen reports the failure like eiscor's info).
+//   * degree <= 8192 (round 2): k_roots_aberth_c below -- the sweeps walk an ordered, compacted list of the roots that
+//     still move, the Aberth sums run in packed single precision on float hi/lo copies of the roots
+//     (profiles/r02_roots_compact.md: 3.4x faster on BASELINE config 7); k_roots_aberth is the round-1 kernel that
+//     still serves degrees 8193 ... 32768 and FNFT_B200_ROOTS_COMPACT=0.
 // Exactly zero leading / trailing coefficients are split off (roots reported as 0, which
 // the callers' z -> lambda map sends to infinity and the bounding-box filter drops).
 #pragma once
