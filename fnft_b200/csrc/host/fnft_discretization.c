@@ -102,6 +102,16 @@ FNFT_INT fnftb__kdv_to_akns(fnft_kdv_discretization_t d, fnft__akns_discretizati
     return FNFT_SUCCESS;
 }
 
+/* the same without an error message (the _numel helpers report an unknown discretization as 0 elements and must not
+ * touch the process-wide printf hook to stay quiet: another thread's messages would go with it) */
+int fnftb__kdv_to_akns_quiet(fnft_kdv_discretization_t d, fnft__akns_discretization_t *out)
+{
+    if ((int)d < 0 || (int)d >= KDV_COUNT)
+        return 0;
+    *out = kdv_map[d];
+    return 1;
+}
+
 FNFT_UINT fnftb__nse_degree(fnft_nse_discretization_t d)
 {
     return ((int)d >= 0 && (int)d < NSE_COUNT) ? fnftb__akns_degree(nse_map[d]) : 0;

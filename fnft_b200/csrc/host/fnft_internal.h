@@ -57,6 +57,7 @@ FNFT_UINT fnftb__akns_method_order(fnft__akns_discretization_t d);
 FNFT_REAL fnftb__akns_boundary_coeff(fnft__akns_discretization_t d);
 FNFT_INT fnftb__nse_to_akns(fnft_nse_discretization_t d, fnft__akns_discretization_t *out);
 FNFT_INT fnftb__kdv_to_akns(fnft_kdv_discretization_t d, fnft__akns_discretization_t *out);
+int fnftb__kdv_to_akns_quiet(fnft_kdv_discretization_t d, fnft__akns_discretization_t *out); /* 1 = known, no message */
 /* 1 if the leaf construction of this scheme exists as a CUDA kernel */
 int fnftb__akns_on_gpu(fnft__akns_discretization_t d);
 FNFT_UINT fnftb__nse_degree(fnft_nse_discretization_t d);

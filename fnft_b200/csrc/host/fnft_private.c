@@ -260,11 +260,7 @@ FNFT_INT fnft__nse_fscatter(const FNFT_UINT D, FNFT_COMPLEX const *const q, cons
 FNFT_UINT fnft__kdv_fscatter_numel(FNFT_UINT D, fnft_kdv_discretization_t discretization)
 {
     fnft__akns_discretization_t akns;
-    fnft_printf_ptr_t keep = fnft_errwarn_getprintf();
-    fnft_errwarn_setprintf(NULL);
-    const FNFT_INT rc = fnftb__kdv_to_akns(discretization, &akns);
-    fnft_errwarn_setprintf(keep);
-    if (rc != FNFT_SUCCESS)
+    if (!fnftb__kdv_to_akns_quiet(discretization, &akns))
         return 0;
     return fnft__akns_fscatter_numel(D, akns);
 }
